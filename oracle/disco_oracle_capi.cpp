@@ -1,0 +1,146 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see disco_oracle.hpp).  extern "C" surface for ctypes.
+#include "disco_oracle.hpp"
+
+#include <string>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static thread_local std::string g_err;
+static std::string g_last_err;
+
+extern "C" {
+
+const char* oracle_last_error() { return g_last_err.c_str(); }
+
+int oracle_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// Arrays follow the reference's C-ABI layouts: ssa/ext [nloc, nwavel] column-major (q + nloc*w),
+// leg [nleg, nloc, nwavel], d_leg [nleg, nloc, nwavel, ngroups], radiance [nwavel, nlos] C-order,
+// native [nwavel, nlos, nloc*(2+ngroups)+1], lanes [nwavel, nlos, L*(ngroups+2)+1].
+int oracle_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nlos, const double* alt, int interp, int geotype,
+                       double cos_sza, double earth_radius, const double* los_cos_vza, const double* los_rel_az,
+                       const double* ssa, const double* ext, const double* leg, const double* solar,
+                       const double* albedo, const double* d_leg, int ngroups, int include_ss, int num_azimuth,
+                       int calc_derivs, int nthreads, void* dgeev_ptr, double* radiance, double* native,
+                       double* lanes_out) {
+    using namespace oracle;
+    try {
+        std::vector<double> a(alt, alt + nloc), cz(los_cos_vza, los_cos_vza + nlos), az(los_rel_az, los_rel_az + nlos);
+        Plan P = make_plan(nstr, a, interp, geotype, cos_sza, earth_radius, cz, az);
+        dgeev_fn dgeev = (dgeev_fn)dgeev_ptr;
+        const int G = (calc_derivs && d_leg) ? ngroups : 0;
+        const int L = nloc - 1;
+        const int nd = calc_derivs ? L * (G + 2) + 1 : 0;
+        const int nnative = nloc * (2 + G) + 1;
+        int failed = 0;
+#ifdef _OPENMP
+        if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int w = 0; w < nwavel; ++w) {
+            if (failed) continue;
+            try {
+                WavelInputs in;
+                in.ext = ext + size_t(nloc) * w;
+                in.ssa = ssa + size_t(nloc) * w;
+                in.leg = leg + size_t(nleg) * nloc * w;
+                in.nleg = nleg;
+                in.f = nullptr;
+                in.solar = solar[w];
+                in.albedo = albedo[w];
+                in.ngroups = G;
+                in.include_ss = include_ss != 0;
+                in.num_azimuth = num_azimuth > 0 ? num_azimuth : nstr;
+                if (!calc_derivs) {
+                    in.d_leg = nullptr;
+                    Solver<double> S(P, dgeev);
+                    S.solve_wavelength(in, radiance + size_t(w) * nlos, nullptr);
+                } else {
+                    nd_ref() = nd;
+                    // per-wavelength view of d_leg [nleg, nloc, nwavel, ngroups] -> [nleg, nloc, ngroups]
+                    std::vector<double> dl;
+                    if (G > 0) {
+                        dl.resize(size_t(nleg) * nloc * G);
+                        for (int g = 0; g < G; ++g)
+                            std::memcpy(&dl[size_t(nleg) * nloc * g],
+                                        d_leg + size_t(nleg) * nloc * (w + size_t(nwavel) * g),
+                                        sizeof(double) * nleg * nloc);
+                        in.d_leg = dl.data();
+                    } else {
+                        in.d_leg = nullptr;
+                    }
+                    Solver<Dual> S(P, dgeev);
+                    S.lanes.L = L;
+                    S.lanes.G = G;
+                    std::vector<double> dlane(size_t(nlos) * nd);
+                    Layers<Dual> Ly;
+                    S.solve_wavelength(in, radiance + size_t(w) * nlos, dlane.data(), &Ly);
+                    for (int j = 0; j < nlos; ++j) {
+                        if (native)
+                            map_to_native(P, S.lanes, in, Ly.tot_ext, Ly.scat_ext, Ly.ssa_value, &dlane[size_t(j) * nd],
+                                          native + (size_t(w) * nlos + j) * nnative);
+                        if (lanes_out)
+                            std::memcpy(lanes_out + (size_t(w) * nlos + j) * nd, &dlane[size_t(j) * nd], sizeof(double) * nd);
+                    }
+                    nd_ref() = 0;
+                }
+            } catch (const std::exception& e) {
+#pragma omp critical
+                {
+                    failed = 1;
+                    g_last_err = e.what();
+                }
+            }
+        }
+        return failed ? -3 : 0;
+    } catch (const std::exception& e) {
+        g_last_err = e.what();
+        return -3;
+    }
+}
+
+// Geometry plan export, for checking the product's host-side tables against the oracle's.
+int oracle_plan(int nstr, int nloc, int nlos, const double* alt, int interp, int geotype, double cos_sza,
+                double earth_radius, const double* los_cos_vza, const double* los_rel_az, double* mu, double* wt,
+                double* lp_mu, double* lp_csz, double* lp_los, double* W, double* chapman) {
+    using namespace oracle;
+    try {
+        std::vector<double> a(alt, alt + nloc), cz(los_cos_vza, los_cos_vza + nlos), az(los_rel_az, los_rel_az + nlos);
+        Plan P = make_plan(nstr, a, interp, geotype, cos_sza, earth_radius, cz, az);
+        std::copy(P.mu.begin(), P.mu.end(), mu);
+        std::copy(P.wt.begin(), P.wt.end(), wt);
+        std::copy(P.lp_mu.begin(), P.lp_mu.end(), lp_mu);
+        std::copy(P.lp_csz.begin(), P.lp_csz.end(), lp_csz);
+        std::copy(P.lp_los.begin(), P.lp_los.end(), lp_los);
+        std::copy(P.W.begin(), P.W.end(), W);
+        std::copy(P.chapman.begin(), P.chapman.end(), chapman);
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_err = e.what();
+        return -3;
+    }
+}
+
+// Band solver check (restates the generator idea of the reference's test_band_factorization.cpp:64-227):
+// solves A x = b (trans = 0) or A^T x = b (trans = 1) for a dense row-major A with bandwidths kl = ku.
+int oracle_band_solve(int n, int kl, const double* dense_a, double* b, int trans) {
+    oracle::BandLU lu;
+    lu.init(n, kl, kl);
+    for (int i = 0; i < n; ++i)
+        for (int j = std::max(0, i - kl); j <= std::min(n - 1, i + kl); ++j) lu.at(i, j) = dense_a[size_t(i) * n + j];
+    int info = lu.factor();
+    if (info != 0) return info;
+    if (trans)
+        lu.solve_transposed(b);
+    else
+        lu.solve(b);
+    return 0;
+}
+}

@@ -1,0 +1,162 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of the CPU restatement in oracle/disco_oracle.hpp (built by oracle/Makefile into
+oracle/liboracle_disco.so).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; the product (sasktran2_b200/) never does.
+
+The eigen-solver is LAPACK dgeev from the OpenBLAS that ships inside scipy (symbol scipy_dgeev_),
+located at import time and handed to the C++ side as a function pointer.
+"""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+_DGEEV = None
+_BLAS = None
+
+
+def build(force: bool = False) -> Path:
+    so = _HERE / "liboracle_disco.so"
+    srcs = [_HERE / "disco_oracle_capi.cpp", _HERE / "disco_oracle.hpp"]
+    if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
+        subprocess.run(["make", "-C", str(_HERE), "-B" if force else "-s"], check=True, capture_output=True)
+    return so
+
+
+def _find_openblas() -> str:
+    import scipy  # noqa: F401  (only to locate scipy.libs)
+
+    root = Path(scipy.__file__).resolve().parent.parent / "scipy.libs"
+    cands = sorted(glob.glob(str(root / "libscipy_openblas*.so")))
+    if not cands:
+        raise RuntimeError("oracle: scipy's bundled OpenBLAS (dgeev) not found")
+    return cands[0]
+
+
+def lib():
+    global _LIB, _DGEEV, _BLAS
+    if _LIB is None:
+        so = build()
+        _BLAS = ctypes.CDLL(_find_openblas(), mode=ctypes.RTLD_GLOBAL)
+        _DGEEV = ctypes.cast(getattr(_BLAS, "scipy_dgeev_"), ctypes.c_void_p)
+        # keep OpenBLAS single-threaded: the oracle parallelises over wavelengths itself
+        try:
+            _BLAS.scipy_openblas_set_num_threads(1)
+        except AttributeError:
+            pass
+        _LIB = ctypes.CDLL(str(so))
+        _LIB.oracle_last_error.restype = ctypes.c_char_p
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
+
+
+def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az,
+                ssa, ext, leg, solar=None, albedo, d_leg=None, include_ss=True, num_azimuth=0,
+                calc_derivs=False, nthreads=0, return_lanes=False):
+    """Run the oracle.
+
+    ssa, ext: [nloc, nwavel] (Fortran order is used internally, as the reference does);
+    leg: [nleg, nloc, nwavel]; d_leg: [nleg, nloc, nwavel, ngroups] or None; albedo: [nwavel].
+    Returns dict(radiance [nwavel, nlos], native [nwavel, nlos, nloc*(2+G)+1] if calc_derivs).
+    """
+    L = lib()
+    alt = np.ascontiguousarray(alt, dtype=np.float64)
+    nloc = alt.size
+    ssa = np.asfortranarray(ssa, dtype=np.float64)
+    ext = np.asfortranarray(ext, dtype=np.float64)
+    leg = np.asfortranarray(leg, dtype=np.float64)
+    nwavel = ssa.shape[1]
+    nleg = leg.shape[0]
+    assert ssa.shape == (nloc, nwavel) and ext.shape == (nloc, nwavel) and leg.shape == (nleg, nloc, nwavel)
+    cz = np.ascontiguousarray(los_cos_vza, dtype=np.float64)
+    az = np.ascontiguousarray(los_rel_az, dtype=np.float64)
+    nlos = cz.size
+    solar = np.ones(nwavel) if solar is None else np.ascontiguousarray(solar, dtype=np.float64)
+    albedo = np.ascontiguousarray(np.broadcast_to(albedo, (nwavel,)), dtype=np.float64)
+    G = 0
+    if d_leg is not None:
+        d_leg = np.asfortranarray(d_leg, dtype=np.float64)
+        G = d_leg.shape[3]
+        assert d_leg.shape == (nleg, nloc, nwavel, G)
+    rad = np.zeros((nwavel, nlos))
+    native = lanes = None
+    nl = nloc - 1
+    if calc_derivs:
+        native = np.zeros((nwavel, nlos, nloc * (2 + G) + 1))
+        if return_lanes:
+            lanes = np.zeros((nwavel, nlos, nl * (G + 2) + 1))
+    rc = L.oracle_do_radiance(
+        ctypes.c_int(nstr), ctypes.c_int(nloc), ctypes.c_int(nwavel), ctypes.c_int(nleg), ctypes.c_int(nlos),
+        _p(alt), ctypes.c_int(interp), ctypes.c_int(geotype), ctypes.c_double(cos_sza), ctypes.c_double(earth_radius),
+        _p(cz), _p(az), _p(ssa), _p(ext), _p(leg), _p(solar), _p(albedo), _p(d_leg), ctypes.c_int(G),
+        ctypes.c_int(int(include_ss)), ctypes.c_int(num_azimuth), ctypes.c_int(int(calc_derivs)),
+        ctypes.c_int(nthreads), _DGEEV, _p(rad), _p(native), _p(lanes))
+    if rc != 0:
+        raise RuntimeError(f"oracle failed ({rc}): {L.oracle_last_error().decode()}")
+    out = {"radiance": rad}
+    if native is not None:
+        out["native"] = native
+    if lanes is not None:
+        out["lanes"] = lanes
+    return out
+
+
+def plan(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az):
+    L = lib()
+    alt = np.ascontiguousarray(alt, dtype=np.float64)
+    nloc = alt.size
+    cz = np.ascontiguousarray(los_cos_vza, dtype=np.float64)
+    az = np.ascontiguousarray(los_rel_az, dtype=np.float64)
+    nlos = cz.size
+    N = nstr // 2
+    nl = nloc - 1
+    out = dict(mu=np.zeros(nstr), wt=np.zeros(nstr), lp_mu=np.zeros((nstr, N, nstr)), lp_csz=np.zeros((nstr, nstr)),
+               lp_los=np.zeros((nlos, nstr, nstr)), W=np.zeros((nl, nloc)), chapman=np.zeros((nl, nl)))
+    rc = L.oracle_plan(ctypes.c_int(nstr), ctypes.c_int(nloc), ctypes.c_int(nlos), _p(alt), ctypes.c_int(interp),
+                       ctypes.c_int(geotype), ctypes.c_double(cos_sza), ctypes.c_double(earth_radius), _p(cz), _p(az),
+                       _p(out["mu"]), _p(out["wt"]), _p(out["lp_mu"]), _p(out["lp_csz"]), _p(out["lp_los"]),
+                       _p(out["W"]), _p(out["chapman"]))
+    if rc != 0:
+        raise RuntimeError(f"oracle_plan failed: {L.oracle_last_error().decode()}")
+    return out
+
+
+def band_solve(a_dense, b, kl, trans=False):
+    L = lib()
+    a = np.ascontiguousarray(a_dense, dtype=np.float64)
+    x = np.array(b, dtype=np.float64, copy=True)
+    rc = L.oracle_band_solve(ctypes.c_int(a.shape[0]), ctypes.c_int(kl), _p(a), _p(x), ctypes.c_int(int(trans)))
+    if rc != 0:
+        raise RuntimeError(f"band solve info={rc}")
+    return x
+
+
+def apply_mappings(native, mappings, nloc, ngroups):
+    """native [nwavel, nlos, nnative] -> dict name -> WF [nout, nwavel, nlos] following OutputC::assign_lane
+    (cpp/lib/output/outputc.cpp:37-160).  mappings: dict name -> dict(d_ssa [nloc,nw], d_extinction [nloc,nw],
+    scat_factor [nloc,nw] or None, scat_index int, interpolator [nloc, nout] or None).
+    """
+    out = {}
+    d_k = native[:, :, 0:nloc]
+    d_w = native[:, :, nloc:2 * nloc]
+    for name, mp in mappings.items():
+        s = d_w * mp["d_ssa"].T[:, None, :] + d_k * mp["d_extinction"].T[:, None, :]
+        if mp.get("scat_factor") is not None:
+            g = mp["scat_index"]
+            d_s = native[:, :, 2 * nloc + g * nloc: 2 * nloc + (g + 1) * nloc]
+            s = s + d_s * mp["scat_factor"].T[:, None, :]
+        if mp.get("interpolator") is not None:
+            s = s @ mp["interpolator"]
+        out[name] = np.ascontiguousarray(np.moveaxis(s, 2, 0))
+    return out

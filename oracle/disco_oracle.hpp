@@ -410,10 +410,11 @@ struct DenseLU {
         return true;
     }
     void solve(double* b) const {
-        for (int k = 0; k < n; ++k) {
+        // full rows were swapped in factor() (LAPACK getrf convention): permute b first, then L, then U
+        for (int k = 0; k < n; ++k)
             if (piv[k] != k) std::swap(b[k], b[piv[k]]);
+        for (int k = 0; k < n; ++k)
             for (int i = k + 1; i < n; ++i) b[i] -= a[i * n + k] * b[k];
-        }
         for (int k = n - 1; k >= 0; --k) {
             for (int c = k + 1; c < n; ++c) b[k] -= a[k * n + c] * b[c];
             b[k] /= a[k * n + k];

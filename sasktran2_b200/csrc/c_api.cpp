@@ -1,0 +1,817 @@
+// C ABI of the B200 discrete-ordinates engine: the reference's `sk_*` entry points for this path
+// (cpp/include/c_api/*.h, implemented upstream in cpp/c_api/*.cpp) re-pointed at the CUDA solver.
+#include "../../include/sasktran2_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "disco_engine.h"
+
+namespace {
+thread_local std::string g_last_error;
+int g_log_level = 3;  // spdlog::level::warn (cpp/lib/config/config.cpp:21)
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    if (g_log_level <= 4) std::fprintf(stderr, "[sasktran2_b200] %s\n", msg.c_str());
+    return code;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// handle types
+// ---------------------------------------------------------------------------------------------------
+struct Config {
+    int num_stokes = 1;
+    int multiple_scatter_source = 3;  // none
+    int single_scatter_source = 0;    // exact
+    int num_streams = 16;
+    int num_threads = 1;
+    int threading_model = 0;
+    int wavelength_batch_size = 1;
+    int num_singlescatter_moments = 16;
+    int apply_delta_scaling = 0;
+    int num_do_sza = 1;
+    int num_do_forced_azimuth = -1;
+    int do_backprop = 0;
+    int emission_source = 1;     // none
+    int occultation_source = 1;  // none
+    int solar_refraction = 0;
+    int wf_enabled = 1;
+    int wf_precision = 0;
+    int input_validation_mode = 0;
+    int log_level = 3;
+};
+
+struct Geometry1D {
+    disco::GeometrySpec spec;
+};
+
+struct ViewingGeometry {
+    std::vector<disco::LineOfSight> rays;
+    std::vector<double> ray_cos_sza;
+    int num_flux_observers = 0;
+};
+
+struct MappingImpl {
+    int nwavel = 0, nloc = 0, nleg = 0;
+    std::vector<double> d_ssa, d_extinction, scat_factor, d_legendre;
+    bool has_d_ssa = false, has_d_extinction = false, has_legendre = false;
+    int scat_deriv_index = -1;
+    std::string interp_dim = "altitude", assign_name;
+    bool log_radiance_space = false;
+    std::vector<double> interpolator;  // column-major [dim1 = nloc, dim2 = nout]
+    int interp_d1 = 0, interp_d2 = 0;
+    bool is_scattering() const { return has_legendre; }
+    int num_output() const { return interp_d2 > 0 ? interp_d2 : nloc; }
+};
+struct DerivativeMapping {
+    MappingImpl* impl;
+};
+
+struct SurfaceMappingImpl {
+    int nwavel = 0, nargs = 1;
+    std::vector<double> d_brdf;  // [nwavel, nargs] column-major
+    bool has_d_brdf = false;
+    std::string interp_dim = "dummy";
+};
+struct SurfaceDerivativeMapping {
+    SurfaceMappingImpl* impl;
+};
+
+struct AtmosphereStorage {
+    int nloc = 0, nwavel = 0, nleg = 0, nstokes = 1;
+    double *ssa = nullptr, *ext = nullptr, *emission = nullptr, *leg = nullptr, *solar = nullptr;
+    std::map<std::string, MappingImpl> mappings;  // name order == the reference's std::map order
+    int num_scat_groups = 0;
+};
+
+struct BRDF {
+    int kind = 0;  // 0 lambertian
+    int nstokes = 1;
+};
+
+struct Surface {
+    int nwavel = 0, nstokes = 1;
+    double* emission = nullptr;
+    BRDF* brdf = nullptr;
+    double* brdf_args = nullptr;  // [nargs, nwavel]; Lambertian: albedo[nwavel]
+    std::vector<double> default_albedo;
+    std::map<std::string, SurfaceMappingImpl> mappings;
+};
+
+struct Atmosphere {
+    AtmosphereStorage* storage = nullptr;
+    Surface* surface = nullptr;
+    bool calc_derivs = false;
+    bool calc_emission_derivs = false;
+};
+
+struct DerivMem {
+    double* ptr;
+    int nrad, nstokes, nderiv;
+};
+struct OutputC {
+    double* radiance = nullptr;
+    int nrad = 0, nstokes = 1;
+    double* flux = nullptr;
+    int nflux = 0;
+    std::map<std::string, DerivMem> derivs;
+    std::map<std::string, DerivMem> surface_derivs;
+};
+
+struct Engine {
+    Config cfg;
+    Geometry1D* geometry = nullptr;
+    ViewingGeometry* viewing = nullptr;
+    std::unique_ptr<disco::DeviceEngine> dev;
+    Atmosphere* atmosphere = nullptr;  // set by calculate_radiance(only_initialize) for block calls
+    int staged_start = 0, staged_count = 0;
+    std::mutex mtx;
+};
+
+namespace {
+
+disco::AtmosphereArrays arrays_of(const Atmosphere* atm) {
+    disco::AtmosphereArrays a;
+    const AtmosphereStorage* s = atm->storage;
+    a.nloc = s->nloc;
+    a.nwavel = s->nwavel;
+    a.nleg = s->nleg;
+    a.ssa = s->ssa;
+    a.ext = s->ext;
+    a.leg = s->leg;
+    a.solar = s->solar;
+    const Surface* sf = atm->surface;
+    a.albedo = sf->brdf_args ? sf->brdf_args : sf->default_albedo.data();
+    return a;
+}
+
+// sasktran2::Sasktran2::validate_input_atmosphere (cpp/lib/engine/engine.cpp:481-540), the parts that
+// concern this path
+int validate(const Engine* e, const Atmosphere* atm, const OutputC* out, bool check_output) {
+    if (!atm || !atm->storage || !atm->surface) return fail(-1, "atmosphere handle is null or incomplete");
+    const AtmosphereStorage* s = atm->storage;
+    if (s->nstokes != 1) return fail(-2, "B200 DO path supports num_stokes = 1 only");
+    if (s->nloc != (int)e->geometry->spec.altitudes.size())
+        return fail(-2, "atmosphere storage and geometry have a different number of grid points");
+    if (!s->ssa || !s->ext || !s->leg || !s->solar) return fail(-1, "atmosphere storage arrays are null");
+    if (s->nleg < 1) return fail(-2, "atmosphere storage needs at least one phase moment");
+    if (atm->surface->nwavel != s->nwavel) return fail(-2, "surface and storage have a different number of wavelengths");
+    if (atm->surface->brdf && atm->surface->brdf->kind != 0) return fail(-2, "B200 DO path supports the Lambertian BRDF only");
+    if (check_output) {
+        if (!out || !out->radiance) return fail(-1, "output handle is null");
+        if (out->nstokes != 1) return fail(-2, "output num_stokes must be 1");
+        const long long need = (long long)s->nwavel * (long long)e->viewing->rays.size();
+        if (out->nrad != need) return fail(-2, "output radiance has the wrong size (expected nwavel * nlos)");
+    }
+    return 0;
+}
+
+int run_range(Engine* e, Atmosphere* atm, OutputC* out, int start, int count) {
+    try {
+        if (!out->derivs.empty() || !out->surface_derivs.empty()) {
+            if (atm->calc_derivs && e->cfg.wf_enabled)
+                return fail(-3, "weighting functions are not available in this build of the B200 DO path");
+        }
+        const int nlos = (int)e->viewing->rays.size();
+        e->dev->calculate(arrays_of(atm), start, count, out->radiance + (size_t)start * nlos);
+        e->staged_start = start;
+        e->staged_count = count;
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------------
+// Config
+// ---------------------------------------------------------------------------------------------------
+Config* sk_config_create() { return new Config(); }
+void sk_config_destroy(Config* c) { delete c; }
+
+#define CFG_GETSET(name, field)                                   \
+    int sk_config_get_##name(Config* c, int* v) {                 \
+        if (!c || !v) return -1;                                  \
+        *v = c->field;                                            \
+        return 0;                                                 \
+    }                                                             \
+    int sk_config_set_##name(Config* c, int v) {                  \
+        if (!c) return -1;                                        \
+        c->field = v;                                             \
+        return 0;                                                 \
+    }
+CFG_GETSET(num_stokes, num_stokes)
+CFG_GETSET(multiple_scatter_source, multiple_scatter_source)
+CFG_GETSET(single_scatter_source, single_scatter_source)
+CFG_GETSET(num_streams, num_streams)
+CFG_GETSET(num_threads, num_threads)
+CFG_GETSET(threading_model, threading_model)
+CFG_GETSET(wavelength_batch_size, wavelength_batch_size)
+CFG_GETSET(num_singlescatter_moments, num_singlescatter_moments)
+CFG_GETSET(apply_delta_scaling, apply_delta_scaling)
+CFG_GETSET(num_do_sza, num_do_sza)
+CFG_GETSET(num_do_forced_azimuth, num_do_forced_azimuth)
+CFG_GETSET(do_backprop, do_backprop)
+CFG_GETSET(emission_source, emission_source)
+CFG_GETSET(occultation_source, occultation_source)
+CFG_GETSET(solar_refraction, solar_refraction)
+CFG_GETSET(wf_enabled, wf_enabled)
+CFG_GETSET(wf_precision, wf_precision)
+CFG_GETSET(input_validation_mode, input_validation_mode)
+int sk_config_get_log_level(Config* c, int* v) {
+    if (!c || !v) return -1;
+    *v = c->log_level;
+    return 0;
+}
+int sk_config_set_log_level(Config* c, int v) {
+    if (!c) return -1;
+    c->log_level = v;
+    g_log_level = v;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Geometry / viewing geometry
+// ---------------------------------------------------------------------------------------------------
+Geometry1D* sk_geometry1d_create(double cos_sza, double saa, double earth_radius, double* grid_values, int ngrid_values,
+                                 int interp_method, int geotype) {
+    if (!grid_values || ngrid_values < 2) {
+        fail(-2, "sk_geometry1d_create: need at least two grid values");
+        return nullptr;
+    }
+    auto* g = new Geometry1D();
+    g->spec.altitudes.assign(grid_values, grid_values + ngrid_values);
+    g->spec.interp = interp_method;
+    g->spec.geotype = geotype;
+    g->spec.cos_sza = cos_sza;
+    g->spec.saa = saa;
+    g->spec.earth_radius = earth_radius;
+    return g;
+}
+void sk_geometry1d_destroy(Geometry1D* g) { delete g; }
+int sk_geometry1d_get_num_altitudes(const Geometry1D* g) { return g ? (int)g->spec.altitudes.size() : -1; }
+int sk_geometry1d_get_altitudes(const Geometry1D* g, double* altitudes) {
+    if (!g || !altitudes) return -1;
+    std::copy(g->spec.altitudes.begin(), g->spec.altitudes.end(), altitudes);
+    return 0;
+}
+
+ViewingGeometry* sk_viewing_geometry_create() { return new ViewingGeometry(); }
+void sk_viewing_geometry_destroy(ViewingGeometry* v) { delete v; }
+void sk_viewing_geometry_add_ground_viewing_solar(ViewingGeometry* v, double cos_sza, double relative_azimuth_angle,
+                                                  double observeraltitude, double cos_viewing_zenith) {
+    if (!v) return;
+    v->rays.push_back({cos_viewing_zenith, relative_azimuth_angle, observeraltitude});
+    v->ray_cos_sza.push_back(cos_sza);
+}
+int sk_viewing_geometry_num_rays(ViewingGeometry* v, int* num_rays) {
+    if (!v || !num_rays) return -1;
+    *num_rays = (int)v->rays.size();
+    return 0;
+}
+int sk_viewing_geometry_num_flux_observers(ViewingGeometry* v, int* n) {
+    if (!v || !n) return -1;
+    *n = v->num_flux_observers;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Atmosphere storage, mappings, surface
+// ---------------------------------------------------------------------------------------------------
+AtmosphereStorage* sk_atmosphere_storage_create(int nlocation, int nwavel, int nphase_moments, int nstokes, double* ssa,
+                                                double* total_extinction, double* emission_source, double* leg_coeff,
+                                                double* solar_irradiance) {
+    if (nstokes != 1 && nstokes != 3) {
+        fail(-2, "sk_atmosphere_storage_create: nstokes must be 1 or 3");
+        return nullptr;
+    }
+    auto* s = new AtmosphereStorage();
+    s->nloc = nlocation;
+    s->nwavel = nwavel;
+    s->nleg = nphase_moments;
+    s->nstokes = nstokes;
+    s->ssa = ssa;
+    s->ext = total_extinction;
+    s->emission = emission_source;
+    s->leg = leg_coeff;
+    s->solar = solar_irradiance;
+    return s;
+}
+void sk_atmosphere_storage_destroy(AtmosphereStorage* s) { delete s; }
+
+int sk_atmosphere_storage_get_derivative_mapping(AtmosphereStorage* s, const char* name, DerivativeMapping** mapping) {
+    if (!s || !name || !mapping) return -1;
+    auto it = s->mappings.find(name);
+    if (it == s->mappings.end()) {
+        MappingImpl m;
+        m.nwavel = s->nwavel;
+        m.nloc = s->nloc;
+        m.nleg = s->nleg;
+        m.assign_name = name;
+        it = s->mappings.emplace(name, std::move(m)).first;
+    }
+    *mapping = new DerivativeMapping{&it->second};
+    return 0;
+}
+int sk_atmosphere_storage_get_num_derivative_mappings(AtmosphereStorage* s, int* n) {
+    if (!s || !n) return -1;
+    *n = (int)s->mappings.size();
+    return 0;
+}
+int sk_atmosphere_storage_get_derivative_mapping_name(AtmosphereStorage* s, int index, const char** name) {
+    if (!s || !name) return -1;
+    if (index < 0 || index >= (int)s->mappings.size()) return -2;
+    auto it = s->mappings.begin();
+    std::advance(it, index);
+    *name = it->first.c_str();
+    return 0;
+}
+int sk_atmosphere_storage_get_derivative_mapping_by_index(AtmosphereStorage* s, int index, DerivativeMapping** mapping) {
+    if (!s || !mapping) return -1;
+    if (index < 0 || index >= (int)s->mappings.size()) return -2;
+    auto it = s->mappings.begin();
+    std::advance(it, index);
+    *mapping = new DerivativeMapping{&it->second};
+    return 0;
+}
+// AtmosphereGridStorageFull::finalize_scattering_derivatives (cpp/include/sasktran2/atmosphere/grid_storage.h:186-209):
+// scattering mappings get consecutive group indices in name order
+int sk_atmosphere_storage_finalize_scattering_derivatives(AtmosphereStorage* s) {
+    if (!s) return -1;
+    int idx = 0;
+    for (auto& kv : s->mappings)
+        if (kv.second.is_scattering()) kv.second.scat_deriv_index = idx++;
+    s->num_scat_groups = idx;
+    return 0;
+}
+int sk_atmosphere_storage_set_zero(AtmosphereStorage* s) {
+    if (!s) return -1;
+    const size_t n = (size_t)s->nloc * s->nwavel;
+    if (s->ssa) std::fill(s->ssa, s->ssa + n, 0.0);
+    if (s->ext) std::fill(s->ext, s->ext + n, 0.0);
+    if (s->emission) std::fill(s->emission, s->emission + n, 0.0);
+    if (s->leg) std::fill(s->leg, s->leg + n * s->nleg * (s->nstokes == 3 ? 4 : 1), 0.0);
+    for (auto& kv : s->mappings) {
+        DerivativeMapping tmp{&kv.second};
+        sk_deriv_mapping_set_zero(&tmp);
+    }
+    return 0;
+}
+
+int sk_deriv_mapping_destroy(DerivativeMapping* m) {
+    if (!m) return -1;
+    delete m;  // the mapping itself is owned by the storage (cpp/c_api/deriv_mapping.cpp:7-14)
+    return 0;
+}
+int sk_deriv_mapping_set_zero(DerivativeMapping* m) {
+    if (!m) return -1;
+    for (auto* v : {&m->impl->d_ssa, &m->impl->d_extinction, &m->impl->scat_factor, &m->impl->d_legendre})
+        std::fill(v->begin(), v->end(), 0.0);
+    return 0;
+}
+int sk_deriv_mapping_get_d_ssa(DerivativeMapping* m, double** p) {
+    if (!m || !p) return -1;
+    if (!m->impl->has_d_ssa) {
+        m->impl->d_ssa.assign((size_t)m->impl->nloc * m->impl->nwavel, 0.0);
+        m->impl->has_d_ssa = true;
+    }
+    *p = m->impl->d_ssa.data();
+    return 0;
+}
+int sk_deriv_mapping_get_d_extinction(DerivativeMapping* m, double** p) {
+    if (!m || !p) return -1;
+    if (!m->impl->has_d_extinction) {
+        m->impl->d_extinction.assign((size_t)m->impl->nloc * m->impl->nwavel, 0.0);
+        m->impl->has_d_extinction = true;
+    }
+    *p = m->impl->d_extinction.data();
+    return 0;
+}
+static void alloc_legendre(MappingImpl* mi) {
+    if (!mi->has_legendre) {
+        mi->d_legendre.assign((size_t)mi->nleg * mi->nloc * mi->nwavel, 0.0);
+        mi->scat_factor.assign((size_t)mi->nloc * mi->nwavel, 0.0);
+        mi->has_legendre = true;
+    }
+}
+int sk_deriv_mapping_get_scat_factor(DerivativeMapping* m, double** p) {
+    if (!m || !p) return -1;
+    alloc_legendre(m->impl);
+    *p = m->impl->scat_factor.data();
+    return 0;
+}
+int sk_deriv_mapping_get_d_legendre(DerivativeMapping* m, double** p) {
+    if (!m || !p) return -1;
+    alloc_legendre(m->impl);
+    *p = m->impl->d_legendre.data();
+    return 0;
+}
+int sk_deriv_mapping_get_scat_deriv_index(DerivativeMapping* m, int* v) {
+    if (!m || !v) return -1;
+    *v = m->impl->scat_deriv_index;
+    return 0;
+}
+int sk_deriv_mapping_set_scat_deriv_index(DerivativeMapping* m, int v) {
+    if (!m) return -1;
+    m->impl->scat_deriv_index = v;
+    return 0;
+}
+int sk_deriv_mapping_get_num_location(DerivativeMapping* m, int* v) {
+    if (!m || !v) return -1;
+    *v = m->impl->nloc;
+    return 0;
+}
+int sk_deriv_mapping_get_num_wavel(DerivativeMapping* m, int* v) {
+    if (!m || !v) return -1;
+    *v = m->impl->nwavel;
+    return 0;
+}
+int sk_deriv_mapping_get_num_legendre(DerivativeMapping* m, int* v) {
+    if (!m || !v) return -1;
+    *v = m->impl->nleg;
+    return 0;
+}
+int sk_deriv_mapping_set_interp_dim(DerivativeMapping* m, const char* name) {
+    if (!m || !name) return -1;
+    m->impl->interp_dim = name;
+    return 0;
+}
+int sk_deriv_mapping_set_assign_name(DerivativeMapping* m, const char* name) {
+    if (!m || !name) return -1;
+    m->impl->assign_name = name;
+    return 0;
+}
+int sk_deriv_mapping_set_log_radiance_space(DerivativeMapping* m, int v) {
+    if (!m) return -1;
+    m->impl->log_radiance_space = v != 0;
+    return 0;
+}
+int sk_deriv_mapping_get_log_radiance_space(DerivativeMapping* m, int* v) {
+    if (!m || !m->impl || !v) return -1;
+    *v = m->impl->log_radiance_space ? 1 : 0;
+    return 0;
+}
+int sk_deriv_mapping_is_scattering_derivative(DerivativeMapping* m, int* v) {
+    if (!m || !v) return -1;
+    *v = m->impl->is_scattering() ? 1 : 0;
+    return 0;
+}
+int sk_deriv_mapping_get_num_output(DerivativeMapping* m, int* v) {
+    if (!m || !v) return -1;
+    *v = m->impl->num_output();
+    return 0;
+}
+int sk_deriv_mapping_get_assign_name(DerivativeMapping* m, const char** name) {
+    if (!m || !name) return -1;
+    *name = m->impl->assign_name.c_str();
+    return 0;
+}
+int sk_deriv_mapping_get_interp_dim(DerivativeMapping* m, const char** name) {
+    if (!m || !name) return -1;
+    *name = m->impl->interp_dim.c_str();
+    return 0;
+}
+int sk_deriv_mapping_set_interpolator(DerivativeMapping* m, double* interpolator, int dim1, int dim2) {
+    if (!m || !interpolator) return -1;
+    if (dim1 != m->impl->nloc) return -2;
+    m->impl->interpolator.assign(interpolator, interpolator + (size_t)dim1 * dim2);
+    m->impl->interp_d1 = dim1;
+    m->impl->interp_d2 = dim2;
+    return 0;
+}
+int sk_deriv_mapping_clear_interpolator(DerivativeMapping* m) {
+    if (!m) return -1;
+    m->impl->interpolator.clear();
+    m->impl->interp_d1 = m->impl->interp_d2 = 0;
+    return 0;
+}
+int sk_deriv_mapping_get_interpolator(DerivativeMapping* m, double** interpolator, int* dim1, int* dim2) {
+    if (!m || !interpolator || !dim1 || !dim2) return -1;
+    *interpolator = m->impl->interpolator.empty() ? nullptr : m->impl->interpolator.data();
+    *dim1 = m->impl->interp_d1;
+    *dim2 = m->impl->interp_d2;
+    return 0;
+}
+
+Atmosphere* sk_atmosphere_create(AtmosphereStorage* storage, Surface* surface, int calculate_derivatives,
+                                 int calculate_emission_derivatives) {
+    if (!storage || !surface) {
+        fail(-1, "sk_atmosphere_create: null storage or surface");
+        return nullptr;
+    }
+    auto* a = new Atmosphere();
+    a->storage = storage;
+    a->surface = surface;
+    a->calc_derivs = calculate_derivatives != 0;
+    a->calc_emission_derivs = calculate_emission_derivatives != 0;
+    return a;
+}
+void sk_atmosphere_destroy(Atmosphere* a) { delete a; }
+int sk_atmosphere_apply_delta_m_scaling(Atmosphere* a, int) {
+    if (!a) return -1;
+    return fail(-3, "delta-M scaling (cpp/lib/atmosphere/atmosphere.cpp:69-203) is a host pre-pass outside the B200 DO path");
+}
+
+Surface* sk_surface_create(int nwavel, int nstokes, double* emission) {
+    auto* s = new Surface();
+    s->nwavel = nwavel;
+    s->nstokes = nstokes;
+    s->emission = emission;
+    s->default_albedo.assign(nwavel > 0 ? nwavel : 0, 0.0);
+    return s;
+}
+void sk_surface_destroy(Surface* s) { delete s; }
+int sk_surface_set_brdf(Surface* s, BRDF* brdf, double* brdf_args) {
+    if (!s || !brdf) return -1;
+    s->brdf = brdf;
+    s->brdf_args = brdf_args;
+    return 0;
+}
+int sk_surface_get_derivative_mapping(Surface* s, const char* name, SurfaceDerivativeMapping** mapping) {
+    if (!s || !name || !mapping) return -1;
+    auto it = s->mappings.find(name);
+    if (it == s->mappings.end()) {
+        SurfaceMappingImpl m;
+        m.nwavel = s->nwavel;
+        m.nargs = 1;
+        it = s->mappings.emplace(name, std::move(m)).first;
+    }
+    *mapping = new SurfaceDerivativeMapping{&it->second};
+    return 0;
+}
+int sk_surface_get_num_derivative_mappings(Surface* s, int* n) {
+    if (!s || !n) return -1;
+    *n = (int)s->mappings.size();
+    return 0;
+}
+int sk_surface_get_derivative_mapping_name(Surface* s, int index, const char** name) {
+    if (!s || !name) return -1;
+    if (index < 0 || index >= (int)s->mappings.size()) return -2;
+    auto it = s->mappings.begin();
+    std::advance(it, index);
+    *name = it->first.c_str();
+    return 0;
+}
+int sk_surface_set_zero(Surface* s) {
+    if (!s) return -1;
+    if (s->brdf_args) std::fill(s->brdf_args, s->brdf_args + s->nwavel, 0.0);
+    if (s->emission) std::fill(s->emission, s->emission + s->nwavel, 0.0);
+    for (auto& kv : s->mappings) std::fill(kv.second.d_brdf.begin(), kv.second.d_brdf.end(), 0.0);
+    return 0;
+}
+int sk_surface_deriv_mapping_get_num_wavel(SurfaceDerivativeMapping* m, int* v) {
+    if (!m || !v) return -1;
+    *v = m->impl->nwavel;
+    return 0;
+}
+int sk_surface_deriv_mapping_get_num_brdf_args(SurfaceDerivativeMapping* m, int* v) {
+    if (!m || !v) return -1;
+    *v = m->impl->nargs;
+    return 0;
+}
+int sk_surface_deriv_mapping_get_d_brdf(SurfaceDerivativeMapping* m, double** p) {
+    if (!m || !p) return -1;
+    if (!m->impl->has_d_brdf) {
+        m->impl->d_brdf.assign((size_t)m->impl->nwavel * m->impl->nargs, 0.0);
+        m->impl->has_d_brdf = true;
+    }
+    *p = m->impl->d_brdf.data();
+    return 0;
+}
+int sk_surface_deriv_mapping_set_zero(SurfaceDerivativeMapping* m) {
+    if (!m) return -1;
+    std::fill(m->impl->d_brdf.begin(), m->impl->d_brdf.end(), 0.0);
+    return 0;
+}
+int sk_surface_deriv_mapping_destroy(SurfaceDerivativeMapping* m) {
+    if (!m) return -1;
+    delete m;
+    return 0;
+}
+
+BRDF* sk_brdf_create_lambertian(int nstokes) {
+    auto* b = new BRDF();
+    b->kind = 0;
+    b->nstokes = nstokes;
+    return b;
+}
+int sk_brdf_get_num_deriv(BRDF* b, int* n) {
+    if (!b || !n) return -1;
+    *n = 1;
+    return 0;
+}
+int sk_brdf_get_num_args(BRDF* b, int* n) {
+    if (!b || !n) return -1;
+    *n = 1;
+    return 0;
+}
+void sk_brdf_destroy(BRDF* b) { delete b; }
+
+// ---------------------------------------------------------------------------------------------------
+// Output
+// ---------------------------------------------------------------------------------------------------
+OutputC* sk_output_create(double* radiance, int nrad, int nstokes, double* flux, int nflux) {
+    auto* o = new OutputC();
+    o->radiance = radiance;
+    o->nrad = nrad;
+    o->nstokes = nstokes;
+    o->flux = flux;
+    o->nflux = nflux;
+    return o;
+}
+void sk_output_destroy(OutputC* o) { delete o; }
+int sk_output_assign_derivative_memory(OutputC* o, const char* name, double* mem, int nrad, int nstokes, int nderiv) {
+    if (!o || !name || !mem) return -1;
+    o->derivs[name] = DerivMem{mem, nrad, nstokes, nderiv};
+    return 0;
+}
+int sk_output_assign_surface_derivative_memory(OutputC* o, const char* name, double* mem, int nrad, int nstokes) {
+    if (!o || !name || !mem) return -1;
+    o->surface_derivs[name] = DerivMem{mem, nrad, nstokes, 1};
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Engine
+// ---------------------------------------------------------------------------------------------------
+Engine* sk_engine_create(Config* config, Geometry1D* geometry, ViewingGeometry* viewing) {
+    if (!config || !geometry || !viewing) {
+        fail(-1, "sk_engine_create: null handle");
+        return nullptr;
+    }
+    // Refuse everything outside the CUDA path loudly (there is no CPU fallback)
+    if (config->num_stokes != 1) {
+        fail(-2, "B200 DO path: num_stokes must be 1");
+        return nullptr;
+    }
+    if (config->multiple_scatter_source != 0) {
+        fail(-2, "B200 DO path: multiple_scatter_source must be DiscreteOrdinates (0)");
+        return nullptr;
+    }
+    if (config->single_scatter_source != 2 && config->single_scatter_source != 3) {
+        fail(-2, "B200 DO path: single_scatter_source must be DiscreteOrdinates (2) or None (3)");
+        return nullptr;
+    }
+    if (config->emission_source != 1) {
+        fail(-2, "B200 DO path: emission sources are not supported");
+        return nullptr;
+    }
+    if (config->solar_refraction) {
+        fail(-2, "B200 DO path: solar refraction is not supported");
+        return nullptr;
+    }
+    if (config->apply_delta_scaling) {
+        fail(-2, "B200 DO path: delta scaling is not supported");
+        return nullptr;
+    }
+    for (size_t i = 0; i < viewing->rays.size(); ++i) {
+        if (std::abs(viewing->ray_cos_sza[i] - geometry->spec.cos_sza) > 1e-12) {
+            fail(-2, "B200 DO path: every ground-viewing ray must use the geometry's cos_sza");
+            return nullptr;
+        }
+    }
+    try {
+        auto* e = new Engine();
+        e->cfg = *config;
+        e->geometry = geometry;
+        e->viewing = viewing;
+        disco::HostPlan plan = disco::build_plan(config->num_streams, geometry->spec, viewing->rays);
+        disco::EngineOptions opt;
+        opt.nstr = config->num_streams;
+        opt.include_ss = config->single_scatter_source == 2;
+        opt.forced_azimuth = config->num_do_forced_azimuth;
+        if (const char* env = std::getenv("SK_B200_WORKSPACE_GB")) opt.workspace_gb = std::atof(env);
+        e->dev = std::make_unique<disco::DeviceEngine>(opt, plan);
+        return e;
+    } catch (const std::exception& ex) {
+        fail(-3, ex.what());
+        return nullptr;
+    }
+}
+void sk_engine_destroy(Engine* e) { delete e; }
+
+int sk_engine_calculate_radiance(Engine* e, Atmosphere* atm, OutputC* out, int only_initialize) {
+    if (!e || !e->dev) return fail(-1, "engine handle is null");
+    std::lock_guard<std::mutex> lock(e->mtx);
+    int rc = validate(e, atm, out, true);
+    if (rc != 0) return rc;
+    e->atmosphere = atm;
+    if (only_initialize) return 0;
+    return run_range(e, atm, out, 0, atm->storage->nwavel);
+}
+
+int sk_engine_calculate_radiance_block_thread(Engine* e, OutputC* out, int wavelength_start, int wavelength_count, int) {
+    if (!e || !e->dev) return fail(-1, "engine handle is null");
+    std::lock_guard<std::mutex> lock(e->mtx);  // one GPU stream: concurrent host threads are serialised
+    if (!e->atmosphere) return fail(-1, "sk_engine_calculate_radiance(only_initialize=1) must be called first");
+    int rc = validate(e, e->atmosphere, out, true);
+    if (rc != 0) return rc;
+    if (wavelength_start < 0 || wavelength_count < 0 || wavelength_start + wavelength_count > e->atmosphere->storage->nwavel)
+        return fail(-2, "wavelength block out of range");
+    return run_range(e, e->atmosphere, out, wavelength_start, wavelength_count);
+}
+
+// The reference collapses to 1 for DO sources (cpp/lib/engine/engine.cpp:869-892); a batched GPU engine wants
+// the whole spectrum in one call so that the Rayon scheduler hands over one block
+int sk_engine_effective_wavelength_batch_size(Engine* e, int num_wavelengths) {
+    if (!e) return -1;
+    return num_wavelengths > 0 ? num_wavelengths : 1;
+}
+int sk_engine_supports_linearization(Engine* e, int, int* supported) {
+    if (!e || !supported) return -1;
+    *supported = 1;
+    return 0;
+}
+int sk_engine_linearization_backend(Engine* e, int, int* backend) {
+    if (!e || !backend) return -1;
+    *backend = 0;  // Jacobian-only ("StreamingJacobian" on the Rust side)
+    return 0;
+}
+int sk_openmp_support_enabled() { return 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// extensions
+// ---------------------------------------------------------------------------------------------------
+const char* sk_b200_last_error() { return g_last_error.c_str(); }
+int sk_b200_device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+int sk_b200_set_device(int device) {
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess) return fail(-3, std::string("cudaSetDevice: ") + cudaGetErrorString(err));
+    return 0;
+}
+int sk_b200_engine_stage_atmosphere(Engine* e, Atmosphere* atm, int wavelength_start, int wavelength_count) {
+    if (!e || !e->dev) return fail(-1, "engine handle is null");
+    std::lock_guard<std::mutex> lock(e->mtx);
+    int rc = validate(e, atm, nullptr, false);
+    if (rc != 0) return rc;
+    if (wavelength_count < 0) wavelength_count = atm->storage->nwavel - wavelength_start;
+    try {
+        e->dev->stage(arrays_of(atm), wavelength_start, wavelength_count);
+        e->atmosphere = atm;
+        e->staged_start = wavelength_start;
+        e->staged_count = wavelength_count;
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+int sk_b200_engine_solve_staged(Engine* e) {
+    if (!e || !e->dev) return fail(-1, "engine handle is null");
+    std::lock_guard<std::mutex> lock(e->mtx);
+    try {
+        e->dev->solve_staged();
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+int sk_b200_engine_fetch_output(Engine* e, OutputC* out) {
+    if (!e || !e->dev) return fail(-1, "engine handle is null");
+    if (!out || !out->radiance) return fail(-1, "output handle is null");
+    std::lock_guard<std::mutex> lock(e->mtx);
+    try {
+        const int nlos = (int)e->viewing->rays.size();
+        if ((long long)out->nrad < (long long)(e->staged_start + e->staged_count) * nlos)
+            return fail(-2, "output radiance too small for the staged wavelength range");
+        e->dev->fetch(out->radiance + (size_t)e->staged_start * nlos);
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+int sk_b200_engine_get_timings(Engine* e, double* out_ms, int n) {
+    if (!e || !e->dev || !out_ms) return -1;
+    const double* t = e->dev->timings_ms();
+    for (int i = 0; i < n; ++i) out_ms[i] = i < disco::T_NSLOTS ? t[i] : 0.0;
+    return 0;
+}
+long long sk_b200_engine_kernel_launches(Engine* e) { return (e && e->dev) ? e->dev->kernel_launches() : -1; }
+int sk_b200_engine_info(Engine* e, int* num_azimuth, int* chunk_wavelengths, double* workspace_mb_per_wavelength) {
+    if (!e || !e->dev) return -1;
+    if (num_azimuth) *num_azimuth = e->dev->num_azimuth_solved();
+    if (chunk_wavelengths) *chunk_wavelengths = e->dev->chunk_wavelengths();
+    if (workspace_mb_per_wavelength) *workspace_mb_per_wavelength = e->dev->workspace_bytes_per_wavelength() / 1048576.0;
+    return 0;
+}
+int sk_b200_engine_set_workspace_gb(Engine* e, double gb) {
+    if (!e || !e->dev) return -1;
+    e->dev->set_workspace_gb(gb);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+// Per-thread bodies of the batched DO kernels, written as host/device functions so that the CUDA kernels
+// (disco_kernels.cu) stay thin and the same arithmetic can be exercised on the CPU by tests/host_emul.cpp.
+#pragma once
+#include <stddef.h>
+
+#include "disco_core.h"
+
+namespace disco {
+
+// Device-side view of one wavelength chunk (all pointers device memory)
+struct ChunkView {
+    // geometry
+    Tables T;
+    const double* layer_dh;   // [L]
+    const int* interp_idx;    // [L][2]
+    const double* interp_w;   // [L][2]
+    const double* chapman;    // [L][L]
+    int plane_parallel;
+    // atmosphere inputs of the chunk (reference C-ABI layouts, wavelength slowest)
+    int nw;                   // wavelengths in this chunk
+    int nleg;
+    const double* ext;        // [nloc, nw]
+    const double* ssa;        // [nloc, nw]
+    const double* leg;        // [nleg, nloc, nw]
+    const double* albedo;     // [nw]
+    const double* solar;      // [nw]
+    int include_ss;
+    int M;                    // azimuth orders actually solved
+    const int* m_list;        // [M] azimuth order of each solved slot
+    // per-layer optics
+    double* lay_od;           // [nw][L]   optical thickness
+    double* lay_ssa;          // [nw][L]
+    double* lay_beta;         // [nw][L][nstr]
+    double* lay_secant;       // [nw][L]
+    double* lay_trans;        // [nw][L+1] beam transmittance at layer boundaries (x solar irradiance)
+    double* lay_cumod;        // [nw][L+1] vertical optical depth above each boundary
+    double* lay_totext;       // [nw][L]
+    double* lay_scatext;      // [nw][L]
+    // per (w, m, layer) solution
+    double* Wp;               // [nw][M][L][N*N] row-major (stream, solution)
+    double* Wm;
+    double* kth;              // [nw][M][L][2N]  k | theta
+    double* G;                // [nw][M][L][4N]  G+top | G-top | G+bot | G-bot
+    double* surf;             // [nw][2N+1]      s+_j | s-_j | sG   (bottom layer, m = 0)
+    double* wvec;             // [nw][M][nlos][L][2N]  d(radiance_m)/d(L_j, M_j)
+    double* vsrc;             // [nw][M][nlos][L]      particular + single-scatter (+ ground direct) terms
+    double* xsol;             // [nw][M][L][2N]        BVP solution L | M
+    double* fac;              // [nw][M][L][2N][4N+1]  pivot rows of the staircase LU
+    double* radiance;         // [nw][nlos]
+    unsigned int* status;     // error bits
+};
+
+
+DISCO_HD void raise_status(unsigned int* status, unsigned int bits) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(status, bits);
+#else
+    *status |= bits;
+#endif
+}
+
+// K1 body: one (wavelength, layer)
+DISCO_HD void optics_body(const ChunkView& V, long long idx) {
+    const int L = V.T.L, nstr = V.T.nstr, nloc = V.T.nloc;
+    const int w = (int)(idx / L), p = (int)(idx % L);
+    const double* ext = V.ext + (size_t)nloc * w;
+    const double* ssa = V.ssa + (size_t)nloc * w;
+    const double* leg = V.leg + (size_t)V.nleg * nloc * w;
+    double od = 0.0, sc = 0.0;
+    double* beta = V.lay_beta + (size_t)idx * nstr;
+    for (int l = 0; l < nstr; ++l) beta[l] = 0.0;
+    for (int c = 0; c < 2; ++c) {
+        const int q = V.interp_idx[p * 2 + c];
+        if (q < 0) continue;
+        const double wgt = V.interp_w[p * 2 + c];
+        const double kext = ext[q];
+        const double kscat = ssa[q] * kext;
+        od += kext * wgt;
+        sc += kscat * wgt;
+        const int nl = nstr < V.nleg ? nstr : V.nleg;
+        for (int l = 0; l < nl; ++l) beta[l] += wgt * kscat * leg[l + (size_t)V.nleg * q];
+    }
+    if (sc > 0.0) {
+        for (int l = 0; l < nstr; ++l) beta[l] /= sc;
+    } else {
+        beta[0] = 0.0;
+    }
+    double ssa_l = sc / od;
+    const double dh = V.layer_dh[p];
+    od *= dh;
+    const double total_ext = od / dh;
+    double scat_ext = total_ext * ssa_l;
+    scat_ext = fmax(scat_ext, total_ext * kSsaDither);
+    double m_ssa = scat_ext / total_ext;
+    if (1.0 - m_ssa < kSsaDither) m_ssa = 1.0 - kSsaDither;
+    V.lay_od[idx] = od;  // raw; k_beam turns it into the reference's floor - ceiling difference
+    V.lay_ssa[idx] = m_ssa;
+    V.lay_totext[idx] = total_ext;
+    V.lay_scatext[idx] = scat_ext;
+}
+
+// K1b body: one wavelength
+DISCO_HD void beam_body(const ChunkView& V, int w) {
+    const int L = V.T.L;
+    double* od = V.lay_od + (size_t)w * L;
+    double* cum = V.lay_cumod + (size_t)w * (L + 1);
+    double* sec = V.lay_secant + (size_t)w * L;
+    double* tr = V.lay_trans + (size_t)w * (L + 1);
+    double ceiling = 0.0, floor_d = 0.0;
+    cum[0] = 0.0;
+    for (int p = 0; p < L; ++p) {
+        floor_d += od[p];
+        od[p] = floor_d - ceiling;  // M_OPTICAL_THICKNESS (sktran_do_opticallayer.cpp:21)
+        ceiling = floor_d;
+        cum[p + 1] = floor_d;
+    }
+    const double f0 = V.solar[w];
+    tr[0] = f0;
+    double prev = 0.0;
+    for (int p = 0; p < L; ++p) {
+        double slant = 0.0;
+        const double* ch = V.chapman + (size_t)p * L;
+        for (int q = 0; q <= p; ++q) slant += ch[q] * od[q];
+        sec[p] = (slant - prev) / od[p];
+        tr[p + 1] = exp(-slant) * f0;
+        prev = slant;
+    }
+}
+
+// K2 body: one (wavelength, azimuth slot, layer)
+template <int N>
+DISCO_HD void layer_problem_body(const ChunkView& V, long long idx) {
+    constexpr int NSTR = 2 * N;
+    const int L = V.T.L, M = V.M, nlos = V.T.nlos;
+    const int p = (int)(idx % L);
+    const int ms = (int)((idx / L) % M);
+    const int w = (int)(idx / ((long long)L * M));
+    const int m = V.m_list[ms];
+    const size_t wl = (size_t)w * L + p;
+    const double od = V.lay_od[wl], ssa = V.lay_ssa[wl], secant = V.lay_secant[wl];
+    const double trans_top = V.lay_trans[(size_t)w * (L + 1) + p];
+    double beta[NSTR];
+#pragma unroll
+    for (int l = 0; l < NSTR; ++l) beta[l] = V.lay_beta[wl * NSTR + l];
+
+    LayerSol<N> S;
+    layer_solve<N>(V.T, m, od, ssa, beta, secant, trans_top, S);
+    if (S.status) raise_status(V.status, (unsigned)S.status);
+
+    double* Wp = V.Wp + (size_t)idx * N * N;
+    double* Wm = V.Wm + (size_t)idx * N * N;
+    for (int i = 0; i < N * N; ++i) {
+        Wp[i] = S.Wp[i];
+        Wm[i] = S.Wm[i];
+    }
+    double* kth = V.kth + (size_t)idx * 2 * N;
+    double* G = V.G + (size_t)idx * 4 * N;
+    for (int j = 0; j < N; ++j) {
+        kth[j] = S.k[j];
+        kth[N + j] = S.theta[j];
+        G[j] = S.Gpt[j];
+        G[N + j] = S.Gmt[j];
+        G[2 * N + j] = S.Gpb[j];
+        G[3 * N + j] = S.Gmb[j];
+    }
+    // Lambertian surface couples only m = 0 (sktran_do_surface.h:53-60, sktran_do_rte.h:116-152)
+    const bool ground = (p == L - 1) && (m == 0);
+    double sp[N], sm[N], sG = 0.0;
+    if (ground) {
+        for (int j = 0; j < N; ++j) {
+            double a = 0.0, b = 0.0;
+            for (int i = 0; i < N; ++i) {
+                a += V.T.wt[i] * V.T.mu[i] * S.Wp[i * N + j];
+                b += V.T.wt[i] * V.T.mu[i] * S.Wm[i * N + j];
+            }
+            sp[j] = a;
+            sm[j] = b;
+        }
+        for (int i = 0; i < N; ++i) sG += V.T.wt[i] * V.T.mu[i] * S.Gpb[i];
+        double* surf = V.surf + (size_t)w * (2 * N + 1);
+        for (int j = 0; j < N; ++j) {
+            surf[j] = sp[j];
+            surf[N + j] = sm[j];
+        }
+        surf[2 * N] = sG;
+    }
+    const double cum_top = V.lay_cumod[(size_t)w * (L + 1) + p];
+    const double cum_all = V.lay_cumod[(size_t)w * (L + 1) + L];
+    const double albedo = V.albedo[w];
+    const double trans_floor = V.lay_trans[(size_t)w * (L + 1) + L];
+    for (int los = 0; los < nlos; ++los) {
+        double cpos[N], cneg[N], v;
+        los_layer_terms<N>(V.T, m, los, od, ssa, beta, secant, trans_top, V.include_ss != 0, S, cpos, cneg, v);
+        const double mu = V.T.los_mu[los];
+        const double att = exp(-cum_top / mu);
+        const size_t o = (((size_t)w * M + ms) * nlos + los) * L + p;
+        double* wv = V.wvec + o * 2 * N;
+        double vv = v * att;
+        if (ground) {
+            // ground-leaving radiance toward the LOS (sktran_do_layerarray.cpp:5-288) attenuated by the
+            // whole column: linear in (L, M) of the bottom layer plus constants
+            const double attg = exp(-cum_all / mu) * albedo;
+            for (int j = 0; j < N; ++j) {
+                wv[j] = cpos[j] * att + attg * 2.0 * sp[j] * S.theta[j];
+                wv[N + j] = cneg[j] * att + attg * 2.0 * sm[j];
+            }
+            double direct = V.include_ss ? V.T.csz / kPi * trans_floor : 0.0;
+            vv += attg * (direct + 2.0 * sG);
+        } else {
+            for (int j = 0; j < N; ++j) {
+                wv[j] = cpos[j] * att;
+                wv[N + j] = cneg[j] * att;
+            }
+        }
+        V.vsrc[o] = vv;
+    }
+}
+
+// K4 body: one (wavelength, LOS)
+DISCO_HD void radiance_body(const ChunkView& V, long long idx) {
+    const int L = V.T.L, M = V.M, nlos = V.T.nlos, N = V.T.N, nstr = V.T.nstr;
+    const int w = (int)(idx / nlos), los = (int)(idx % nlos);
+    double total = 0.0;
+    for (int ms = 0; ms < M; ++ms) {
+        const int m = V.m_list[ms];
+        const size_t o = (((size_t)w * M + ms) * nlos + los) * L;
+        const double* wv = V.wvec + o * 2 * N;
+        const double* vs = V.vsrc + o;
+        const double* x = V.xsol + ((size_t)w * M + ms) * L * 2 * N;
+        double comp = 0.0;
+        // same accumulation order as the reference's upward recursion: ground/bottom layer first
+        for (int p = L - 1; p >= 0; --p) {
+            double s = vs[p];
+            for (int j = 0; j < 2 * N; ++j) s += wv[(size_t)p * 2 * N + j] * x[(size_t)p * 2 * N + j];
+            comp += s;
+        }
+        total += comp * V.T.los_cosmphi[(size_t)los * nstr + m];
+    }
+    V.radiance[idx] = total;
+}
+
+}  // namespace disco

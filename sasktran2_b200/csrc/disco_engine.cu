@@ -1,0 +1,282 @@
+#include "disco_engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+namespace disco {
+
+#define CUDA_OK(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " +    \
+                                     __FILE__ + ":" + std::to_string(__LINE__));                        \
+    } while (0)
+
+template <class T>
+T* DeviceEngine::dalloc(size_t n) {
+    T* p = nullptr;
+    CUDA_OK(cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+
+template <class T>
+static T* upload(const std::vector<T>& v) {
+    T* p = nullptr;
+    CUDA_OK(cudaMalloc((void**)&p, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+
+DeviceEngine::DeviceEngine(const EngineOptions& opt, const HostPlan& plan) : m_opt(opt), m_plan(plan) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw std::runtime_error("sasktran2_b200: no CUDA device available (there is no CPU fallback)");
+    if (opt.device >= 0) CUDA_OK(cudaSetDevice(opt.device));
+    if (!nstr_supported(plan.nstr))
+        throw std::runtime_error("sasktran2_b200: num_streams must be one of 2, 4, 8, 16, 32");
+    CUDA_OK(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking));
+    for (auto& ev : m_ev) CUDA_OK(cudaEventCreate(&ev));
+    d_mu = upload(plan.mu);
+    d_wt = upload(plan.wt);
+    d_lp_mu = upload(plan.lp_mu);
+    d_lp_csz = upload(plan.lp_csz);
+    d_lp_los = upload(plan.lp_los);
+    d_los_mu = upload(plan.los_mu);
+    d_los_cosmphi = upload(plan.los_cosmphi);
+    d_layer_dh = upload(plan.layer_dh);
+    d_interp_w = upload(plan.interp_w);
+    d_interp_idx = upload(plan.interp_idx);
+    d_chapman = upload(plan.chapman);
+    // Azimuth orders to solve.  The reference sums all nstr orders (do_source_planeparallel.cpp:55-62);
+    // an order whose LOS Legendre table P_l^m(mu_los) is identically zero for every line of sight (m > 0 at
+    // exactly nadir, d^l_{m0}(0) = 0) contributes exactly zero to every output and is skipped.
+    const int nstr = plan.nstr;
+    const int nazi = (opt.forced_azimuth > 0) ? std::min(opt.forced_azimuth, nstr) : nstr;
+    for (int m = 0; m < nazi; ++m) {
+        bool any = false;
+        for (int j = 0; j < plan.nlos && !any; ++j)
+            for (int l = 0; l < nstr && !any; ++l)
+                if (plan.lp_los[((size_t)j * nstr + m) * nstr + l] != 0.0) any = true;
+        if (any || plan.nlos == 0) m_mlist.push_back(m);
+    }
+    if (m_mlist.empty()) m_mlist.push_back(0);
+    d_mlist = upload(m_mlist);
+    d_status = dalloc<unsigned int>(1);
+    CUDA_OK(cudaMemset(d_status, 0, sizeof(unsigned int)));
+}
+
+DeviceEngine::~DeviceEngine() {
+    free_inputs();
+    free_workspace();
+    for (void* p : {(void*)d_mu, (void*)d_wt, (void*)d_lp_mu, (void*)d_lp_csz, (void*)d_lp_los, (void*)d_los_mu,
+                    (void*)d_los_cosmphi, (void*)d_layer_dh, (void*)d_interp_w, (void*)d_interp_idx,
+                    (void*)d_chapman, (void*)d_mlist, (void*)d_status})
+        if (p) cudaFree(p);
+    for (auto& ev : m_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (m_stream) cudaStreamDestroy(m_stream);
+}
+
+void DeviceEngine::free_inputs() {
+    for (void* p : {(void*)d_ext, (void*)d_ssa, (void*)d_leg, (void*)d_solar, (void*)d_albedo, (void*)d_radiance})
+        if (p) cudaFree(p);
+    d_ext = d_ssa = d_leg = d_solar = d_albedo = d_radiance = nullptr;
+    m_cap_nw = m_cap_nleg = 0;
+}
+
+void DeviceEngine::free_workspace() {
+    for (void* p : m_ws_ptrs)
+        if (p) cudaFree(p);
+    m_ws_ptrs.clear();
+    m_ws_chunk = 0;
+}
+
+size_t DeviceEngine::workspace_bytes_per_wavelength() const {
+    const size_t N = m_plan.N, L = m_plan.L, nstr = m_plan.nstr, nlos = m_plan.nlos, M = m_mlist.size();
+    size_t d = L * (6 + nstr) + 2 * (L + 1);                       // layer optics
+    d += 2 * M * L * N * N + M * L * 2 * N + M * L * 4 * N;         // W+, W-, k|theta, G
+    d += 2 * N + 1;                                                 // surface sums
+    d += M * nlos * L * 2 * N + M * nlos * L;                       // wvec, vsrc
+    d += M * L * 2 * N;                                             // x
+    d += M * L * 2 * N * (4 * N + 1);                               // LU pivot rows
+    return d * sizeof(double);
+}
+
+int DeviceEngine::chunk_wavelengths() const {
+    const double budget = m_opt.workspace_gb * 1024.0 * 1024.0 * 1024.0;
+    long long c = (long long)(budget / (double)workspace_bytes_per_wavelength());
+    c = std::max<long long>(c, 1);
+    return (int)std::min<long long>(c, std::max(m_nw, 1));
+}
+
+void DeviceEngine::ensure_workspace(int chunk) {
+    if (chunk <= m_ws_chunk) return;
+    free_workspace();
+    const size_t N = m_plan.N, L = m_plan.L, nstr = m_plan.nstr, nlos = m_plan.nlos, M = m_mlist.size();
+    const size_t c = chunk;
+    auto A = [&](size_t n) {
+        double* p = dalloc<double>(n);
+        m_ws_ptrs.push_back(p);
+        return p;
+    };
+    ChunkView& V = m_view;
+    V.lay_od = A(c * L);
+    V.lay_ssa = A(c * L);
+    V.lay_beta = A(c * L * nstr);
+    V.lay_secant = A(c * L);
+    V.lay_trans = A(c * (L + 1));
+    V.lay_cumod = A(c * (L + 1));
+    V.lay_totext = A(c * L);
+    V.lay_scatext = A(c * L);
+    V.Wp = A(c * M * L * N * N);
+    V.Wm = A(c * M * L * N * N);
+    V.kth = A(c * M * L * 2 * N);
+    V.G = A(c * M * L * 4 * N);
+    V.surf = A(c * (2 * N + 1));
+    V.wvec = A(c * M * nlos * L * 2 * N);
+    V.vsrc = A(c * M * nlos * L);
+    V.xsol = A(c * M * L * 2 * N);
+    V.fac = A(c * M * L * 2 * N * (4 * N + 1));
+    m_ws_chunk = chunk;
+}
+
+void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw) {
+    if (atm.nloc != m_plan.nloc) throw std::runtime_error("atmosphere and geometry grids differ in size");
+    if (w0 < 0 || nw < 0 || w0 + nw > atm.nwavel) throw std::runtime_error("wavelength range out of bounds");
+    const size_t nloc = atm.nloc;
+    if (nw > m_cap_nw || atm.nleg != m_cap_nleg) {
+        free_inputs();
+        d_ext = dalloc<double>(nloc * nw);
+        d_ssa = dalloc<double>(nloc * nw);
+        d_leg = dalloc<double>((size_t)atm.nleg * nloc * nw);
+        d_solar = dalloc<double>(nw);
+        d_albedo = dalloc<double>(nw);
+        d_radiance = dalloc<double>((size_t)nw * std::max(m_plan.nlos, 1));
+        m_cap_nw = nw;
+        m_cap_nleg = atm.nleg;
+    }
+    m_nw = nw;
+    m_nleg = atm.nleg;
+    CUDA_OK(cudaEventRecord(m_ev[0], m_stream));
+    if (nw > 0) {
+        CUDA_OK(cudaMemcpyAsync(d_ext, atm.ext + nloc * w0, sizeof(double) * nloc * nw, cudaMemcpyHostToDevice, m_stream));
+        CUDA_OK(cudaMemcpyAsync(d_ssa, atm.ssa + nloc * w0, sizeof(double) * nloc * nw, cudaMemcpyHostToDevice, m_stream));
+        CUDA_OK(cudaMemcpyAsync(d_leg, atm.leg + (size_t)atm.nleg * nloc * w0, sizeof(double) * atm.nleg * nloc * nw,
+                                cudaMemcpyHostToDevice, m_stream));
+        CUDA_OK(cudaMemcpyAsync(d_solar, atm.solar + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
+        CUDA_OK(cudaMemcpyAsync(d_albedo, atm.albedo + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
+    }
+    CUDA_OK(cudaEventRecord(m_ev[1], m_stream));
+    CUDA_OK(cudaStreamSynchronize(m_stream));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, m_ev[0], m_ev[1]));
+    m_ms[T_H2D] = ms;
+}
+
+void DeviceEngine::solve_staged() {
+    for (int i = T_OPTICS; i < T_NSLOTS; ++i)
+        if (i != T_D2H) m_ms[i] = 0.0;
+    m_launches = 0;
+    if (m_nw == 0 || m_plan.nlos == 0) return;
+    const int chunk = chunk_wavelengths();
+    ensure_workspace(chunk);
+    CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(unsigned int), m_stream));
+    ChunkView V = m_view;
+    V.T.nstr = m_plan.nstr;
+    V.T.N = m_plan.N;
+    V.T.L = m_plan.L;
+    V.T.nloc = m_plan.nloc;
+    V.T.nlos = m_plan.nlos;
+    V.T.csz = m_plan.csz;
+    V.T.mu = d_mu;
+    V.T.wt = d_wt;
+    V.T.lp_mu = d_lp_mu;
+    V.T.lp_csz = d_lp_csz;
+    V.T.lp_los = d_lp_los;
+    V.T.los_mu = d_los_mu;
+    V.T.los_cosmphi = d_los_cosmphi;
+    V.layer_dh = d_layer_dh;
+    V.interp_idx = d_interp_idx;
+    V.interp_w = d_interp_w;
+    V.chapman = d_chapman;
+    V.plane_parallel = m_plan.plane_parallel ? 1 : 0;
+    V.nleg = m_nleg;
+    V.include_ss = m_opt.include_ss ? 1 : 0;
+    V.M = (int)m_mlist.size();
+    V.m_list = d_mlist;
+    V.status = d_status;
+    const size_t nloc = m_plan.nloc;
+    struct Span { cudaEvent_t a, b; int slot; };
+    // per-kernel timing: events are recorded around every launch; elapsed times are read after the final sync
+    std::vector<cudaEvent_t> evs;
+    std::vector<int> slots;
+    auto mark = [&]() {
+        cudaEvent_t ev;
+        CUDA_OK(cudaEventCreate(&ev));
+        CUDA_OK(cudaEventRecord(ev, m_stream));
+        evs.push_back(ev);
+    };
+    mark();
+    for (int w0 = 0; w0 < m_nw; w0 += chunk) {
+        V.nw = std::min(chunk, m_nw - w0);
+        V.ext = d_ext + nloc * w0;
+        V.ssa = d_ssa + nloc * w0;
+        V.leg = d_leg + (size_t)m_nleg * nloc * w0;
+        V.albedo = d_albedo + w0;
+        V.solar = d_solar + w0;
+        V.radiance = d_radiance + (size_t)w0 * m_plan.nlos;
+        launch_layer_optics(V, m_stream);
+        launch_beam(V, m_stream);
+        mark(); slots.push_back(T_OPTICS);
+        launch_layer_solve(V, m_stream);
+        mark(); slots.push_back(T_LAYER);
+        launch_bvp(V, m_stream);
+        mark(); slots.push_back(T_BVP);
+        launch_radiance(V, m_stream);
+        mark(); slots.push_back(T_RADIANCE);
+        m_launches += 5;
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(m_stream));
+    for (size_t i = 0; i + 1 < evs.size(); ++i) {
+        float ms = 0;
+        CUDA_OK(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
+        m_ms[slots[i]] += ms;
+    }
+    float tot = 0;
+    CUDA_OK(cudaEventElapsedTime(&tot, evs.front(), evs.back()));
+    m_ms[T_TOTAL_KERNELS] = tot;
+    for (auto ev : evs) cudaEventDestroy(ev);
+    unsigned int st = 0;
+    CUDA_OK(cudaMemcpy(&st, d_status, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st & 1u) throw std::runtime_error("DO homogeneous solution: S- is not positive definite (invalid phase moments?)");
+    if (st & 2u)
+        throw std::runtime_error(
+            "An homogeneous solution was found to be imaginary. An insufficient number of streams is likely.");
+    if (st & 4u) throw std::runtime_error("BVP could not be solved since the coefficient matrix was singular.");
+}
+
+void DeviceEngine::fetch(double* radiance_host) {
+    CUDA_OK(cudaEventRecord(m_ev[2], m_stream));
+    if (m_nw > 0 && m_plan.nlos > 0)
+        CUDA_OK(cudaMemcpyAsync(radiance_host, d_radiance, sizeof(double) * (size_t)m_nw * m_plan.nlos,
+                                cudaMemcpyDeviceToHost, m_stream));
+    CUDA_OK(cudaEventRecord(m_ev[3], m_stream));
+    CUDA_OK(cudaStreamSynchronize(m_stream));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, m_ev[2], m_ev[3]));
+    m_ms[T_D2H] = ms;
+}
+
+void DeviceEngine::calculate(const AtmosphereArrays& atm, int w0, int nw, double* radiance_host) {
+    stage(atm, w0, nw);
+    solve_staged();
+    fetch(radiance_host);
+}
+
+}  // namespace disco

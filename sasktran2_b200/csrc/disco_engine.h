@@ -1,0 +1,87 @@
+// Host orchestration of the CUDA discrete-ordinates solve: device memory, wavelength chunking, streams,
+// CUDA-event timing.  Plain CUDA runtime, no framework dependencies.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "disco_kernels.cuh"
+#include "disco_plan.h"
+
+namespace disco {
+
+struct EngineOptions {
+    int nstr = 16;
+    bool include_ss = true;     // single_scatter_source == discrete_ordinates
+    int forced_azimuth = -1;    // num_do_forced_azimuth (<= 0: all nstr orders)
+    double workspace_gb = 8.0;  // per-chunk workspace budget
+    int device = -1;            // -1: current device
+};
+
+// Caller-owned host arrays in the reference's C-ABI layouts (cpp/include/c_api/atmosphere.h:86-91)
+struct AtmosphereArrays {
+    int nloc = 0, nwavel = 0, nleg = 0;
+    const double* ssa = nullptr;    // [nloc, nwavel]
+    const double* ext = nullptr;    // [nloc, nwavel]
+    const double* leg = nullptr;    // [nleg, nloc, nwavel]
+    const double* solar = nullptr;  // [nwavel]
+    const double* albedo = nullptr; // [nwavel]
+};
+
+enum TimingSlot { T_H2D = 0, T_OPTICS, T_LAYER, T_BVP, T_RADIANCE, T_D2H, T_TOTAL_KERNELS, T_NSLOTS };
+
+class DeviceEngine {
+  public:
+    DeviceEngine(const EngineOptions& opt, const HostPlan& plan);
+    ~DeviceEngine();
+    DeviceEngine(const DeviceEngine&) = delete;
+    DeviceEngine& operator=(const DeviceEngine&) = delete;
+
+    // Copy wavelengths [w0, w0+nw) of the atmosphere to the device and keep them resident.
+    void stage(const AtmosphereArrays& atm, int w0, int nw);
+    // Run the kernels on the staged wavelengths; results stay on the device.
+    void solve_staged();
+    // Copy radiance [nw, nlos] of the staged range back to the host.
+    void fetch(double* radiance_host);
+    // stage + solve + fetch
+    void calculate(const AtmosphereArrays& atm, int w0, int nw, double* radiance_host);
+
+    const double* timings_ms() const { return m_ms; }   // accumulated over the last solve / calculate
+    long long kernel_launches() const { return m_launches; }
+    int staged_wavelengths() const { return m_nw; }
+    int num_azimuth_solved() const { return (int)m_mlist.size(); }
+    size_t workspace_bytes_per_wavelength() const;
+    int chunk_wavelengths() const;
+    const HostPlan& plan() const { return m_plan; }
+    void set_workspace_gb(double gb) { m_opt.workspace_gb = gb; }
+
+  private:
+    void free_inputs();
+    void free_workspace();
+    void ensure_workspace(int chunk);
+    template <class T> T* dalloc(size_t n);
+
+    EngineOptions m_opt;
+    HostPlan m_plan;
+    cudaStream_t m_stream = nullptr;
+    cudaEvent_t m_ev[8] = {};
+    // geometry tables on device
+    double *d_mu = nullptr, *d_wt = nullptr, *d_lp_mu = nullptr, *d_lp_csz = nullptr, *d_lp_los = nullptr;
+    double *d_los_mu = nullptr, *d_los_cosmphi = nullptr, *d_layer_dh = nullptr, *d_interp_w = nullptr, *d_chapman = nullptr;
+    int *d_interp_idx = nullptr, *d_mlist = nullptr;
+    std::vector<int> m_mlist;
+    // staged inputs
+    int m_nw = 0, m_nleg = 0, m_cap_nw = 0, m_cap_nleg = 0;
+    double *d_ext = nullptr, *d_ssa = nullptr, *d_leg = nullptr, *d_solar = nullptr, *d_albedo = nullptr;
+    double* d_radiance = nullptr;
+    unsigned int* d_status = nullptr;
+    // chunk workspace
+    int m_ws_chunk = 0;
+    std::vector<void*> m_ws_ptrs;
+    ChunkView m_view{};
+    double m_ms[T_NSLOTS] = {};
+    long long m_launches = 0;
+};
+
+}  // namespace disco

@@ -1,0 +1,18 @@
+// CUDA kernels of the batched discrete-ordinates radiance solve (sm_100a, fp64).
+// Batched over wavelength x azimuth order x layer; see DESIGN.md for the data layout and rooflines.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "disco_bodies.h"
+
+namespace disco {
+
+void launch_layer_optics(const ChunkView& V, cudaStream_t s);
+void launch_beam(const ChunkView& V, cudaStream_t s);
+void launch_layer_solve(const ChunkView& V, cudaStream_t s);
+void launch_bvp(const ChunkView& V, cudaStream_t s);
+void launch_radiance(const ChunkView& V, cudaStream_t s);
+bool nstr_supported(int nstr);
+
+}  // namespace disco

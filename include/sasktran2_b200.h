@@ -191,6 +191,8 @@ long long sk_b200_engine_kernel_launches(Engine* engine);
 /* number of azimuth orders solved and wavelengths per workspace chunk (diagnostics) */
 int sk_b200_engine_info(Engine* engine, int* num_azimuth, int* chunk_wavelengths, double* workspace_mb_per_wavelength);
 int sk_b200_engine_set_workspace_gb(Engine* engine, double gb);
+/* DFMA micro-benchmark on the current device: the FP64 roofline denominator (TFLOP/s) */
+double sk_b200_measure_fp64_tflops();
 
 #ifdef __cplusplus
 }

@@ -808,6 +808,7 @@ int sk_b200_engine_info(Engine* e, int* num_azimuth, int* chunk_wavelengths, dou
     if (workspace_mb_per_wavelength) *workspace_mb_per_wavelength = e->dev->workspace_bytes_per_wavelength() / 1048576.0;
     return 0;
 }
+double sk_b200_measure_fp64_tflops() { return disco::measure_fp64_tflops(); }
 int sk_b200_engine_set_workspace_gb(Engine* e, double gb) {
     if (!e || !e->dev) return -1;
     e->dev->set_workspace_gb(gb);

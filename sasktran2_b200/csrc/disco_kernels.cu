@@ -352,6 +352,50 @@ static void launch_bvp_n(const ChunkView& V, cudaStream_t s) {
         default: break;                            \
     }
 
+// FP64 roofline denominator: DFMA micro-benchmark (16 independent accumulators per thread, no memory traffic)
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    const double b = 1.0000001, c = 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma(a[i], b, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 12345.678) out[0] = s;  // never true; keeps the chain alive
+}
+
+double measure_fp64_tflops() {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* d = nullptr;
+    cudaMalloc(&d, sizeof(double));
+    const int blocks = sms * 8, threads = 256, iters = 20000;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_dfma_peak<<<blocks, threads>>>(d, 2000);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        k_dfma_peak<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+    return flops / (best * 1e-3) / 1e12;
+}
+
 bool nstr_supported(int nstr) { return nstr == 2 || nstr == 4 || nstr == 8 || nstr == 16 || nstr == 32; }
 void launch_layer_solve(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_N(launch_layer_solve_n, V, s) }
 void launch_bvp(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_N(launch_bvp_n, V, s) }

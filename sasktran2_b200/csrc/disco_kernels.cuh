@@ -14,5 +14,6 @@ void launch_layer_solve(const ChunkView& V, cudaStream_t s);
 void launch_bvp(const ChunkView& V, cudaStream_t s);
 void launch_radiance(const ChunkView& V, cudaStream_t s);
 bool nstr_supported(int nstr);
+double measure_fp64_tflops();
 
 }  // namespace disco

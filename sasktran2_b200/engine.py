@@ -1,0 +1,117 @@
+"""Mirror of sasktran2.Engine (src/sasktran2/engine.py:72-166, 474-560): same constructor and
+calculate_radiance(atmosphere) contract, results as numpy arrays with the reference's dimension order
+(radiance [wavelength, los, stokes]; weighting functions [<interp_dim>, wavelength, los, stokes])."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+TIMING_NAMES = ("h2d", "optics", "layer", "bvp", "radiance", "d2h", "kernels_total", "wf")
+
+
+class Result(dict):
+    """dict of numpy arrays; `dims` gives the dimension names of every entry."""
+
+    def __init__(self):
+        super().__init__()
+        self.dims = {}
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+class Engine:
+    def __init__(self, config, model_geometry, viewing_geo):
+        self._config = config
+        self._geometry = model_geometry
+        self._viewing_geometry = viewing_geo
+        self._engine = _lib.lib().sk_engine_create(config._config, model_geometry._geometry,
+                                                   viewing_geo._viewing_geometry)
+        if not self._engine:
+            raise _lib.SasktranError(f"sk_engine_create failed: {_lib.last_error()}")
+        self._keepalive = None
+
+    def __del__(self):
+        try:
+            _lib.lib().sk_engine_destroy(self._engine)
+        except Exception:
+            pass
+
+    # ---- the reference call -------------------------------------------------------------------------
+    def _make_output(self, atmosphere, radiance_buffer=None):
+        nw = atmosphere.num_wavel
+        nlos = self._viewing_geometry.num_rays
+        rad = radiance_buffer if radiance_buffer is not None else np.zeros((nw, nlos, 1))
+        assert rad.shape == (nw, nlos, 1) and rad.flags["C_CONTIGUOUS"]
+        out = _lib.lib().sk_output_create(_lib.dptr(rad), nw * nlos, 1, None, 0)
+        res = Result()
+        res["radiance"] = rad
+        res.dims["radiance"] = ("wavelength", "los", "stokes")
+        if atmosphere.calculate_derivatives and self._config.wf_enabled:
+            for name in atmosphere.storage.derivative_mapping_names:
+                m = atmosphere.storage.get_derivative_mapping(name)
+                nout = m.num_output
+                buf = np.zeros((nout, nw, nlos, 1))
+                _lib.check(_lib.lib().sk_output_assign_derivative_memory(out, name.encode(), _lib.dptr(buf),
+                                                                         nw * nlos, 1, nout))
+                key = m.assign_name or name
+                res[key] = buf
+                res.dims[key] = (m.interp_dim, "wavelength", "los", "stokes")
+            for name in atmosphere.surface._mapping_names:
+                buf = np.zeros((1, nw, nlos, 1))
+                _lib.check(_lib.lib().sk_output_assign_surface_derivative_memory(out, name.encode(),
+                                                                                 _lib.dptr(buf), nw * nlos, 1))
+                res[name] = buf[0]
+                res.dims[name] = ("wavelength", "los", "stokes")
+                res["_" + name + "_buf"] = buf
+        return out, res
+
+    def calculate_radiance(self, atmosphere, radiance_buffer=None) -> Result:
+        out, res = self._make_output(atmosphere, radiance_buffer)
+        try:
+            rc = _lib.lib().sk_engine_calculate_radiance(self._engine, atmosphere.internal_object(), out, 0)
+            _lib.check(rc, "sk_engine_calculate_radiance")
+        finally:
+            _lib.lib().sk_output_destroy(out)
+        if atmosphere.wavelengths_nm is not None:
+            res["wavelength"] = atmosphere.wavelengths_nm
+        return res
+
+    # ---- device-resident extension (bench / pipelines that keep the atmosphere on the GPU) -----------
+    def stage(self, atmosphere, wavelength_start: int = 0, wavelength_count: int = -1) -> None:
+        self._keepalive = atmosphere
+        _lib.check(_lib.lib().sk_b200_engine_stage_atmosphere(self._engine, atmosphere.internal_object(),
+                                                              wavelength_start, wavelength_count), "stage")
+
+    def solve_staged(self) -> None:
+        _lib.check(_lib.lib().sk_b200_engine_solve_staged(self._engine), "solve_staged")
+
+    def fetch(self, atmosphere, radiance_buffer=None) -> Result:
+        out, res = self._make_output(atmosphere, radiance_buffer)
+        try:
+            _lib.check(_lib.lib().sk_b200_engine_fetch_output(self._engine, out), "fetch")
+        finally:
+            _lib.lib().sk_output_destroy(out)
+        return res
+
+    def timings_ms(self) -> dict:
+        buf = np.zeros(len(TIMING_NAMES))
+        _lib.check(_lib.lib().sk_b200_engine_get_timings(self._engine, _lib.dptr(buf), buf.size))
+        return dict(zip(TIMING_NAMES, buf.tolist()))
+
+    def kernel_launches(self) -> int:
+        return int(_lib.lib().sk_b200_engine_kernel_launches(self._engine))
+
+    def info(self) -> dict:
+        a, c, mb = C.c_int(0), C.c_int(0), C.c_double(0)
+        _lib.check(_lib.lib().sk_b200_engine_info(self._engine, C.byref(a), C.byref(c), C.byref(mb)))
+        return {"num_azimuth": a.value, "chunk_wavelengths": c.value, "workspace_mb_per_wavelength": mb.value}
+
+    def set_workspace_gb(self, gb: float) -> None:
+        _lib.check(_lib.lib().sk_b200_engine_set_workspace_gb(self._engine, float(gb)))

@@ -48,6 +48,14 @@ class Scenario:
         return self.los_cos_vza.size
 
 
+# Grey continuum absorption as a fraction of the Rayleigh extinction.  It keeps every layer's single-scatter
+# albedo at least ~1e-3 away from 1: in (nearly) conservative layers the DO eigen-solution loses digits by
+# cancellation in S+ X (noise ~ eps / (1 - omega), ~1e-7 at the reference's 1e-9 dither, for the reference
+# and for this implementation alike — DESIGN.md "Conditioning"), which would turn a 1e-9 parity check into a
+# comparison of rounding noise.
+CONTINUUM_ABSORPTION = 1.0e-3
+
+
 def rayleigh_extinction(z_m: np.ndarray) -> np.ndarray:
     return 7.0e-5 * np.exp(-z_m / 7400.0)
 
@@ -91,7 +99,8 @@ def config1(nwavel: int = 1000, nlayers: int = 50) -> Scenario:
     g_lam = 0.5 * (1 - np.cos(2 * np.pi * np.arange(nwavel) / max(nwavel - 1, 1) * 3.0))
     # keep a small absorption floor so no layer is exactly conservative
     k_o3 = 3e-5 * np.exp(-(((z - 25e3) / 8e3) ** 2))[:, None] * (0.02 + g_lam)[None, :]
-    k, ssa, leg, _ = _mix([(k_ray, 1.0, rayleigh_moments(nleg)), (k_o3, 0.0, np.zeros(nleg))], nleg)
+    k, ssa, leg, _ = _mix([(k_ray, 1.0, rayleigh_moments(nleg)), (k_o3, 0.0, np.zeros(nleg)),
+                           (CONTINUUM_ABSORPTION * k_ray, 0.0, np.zeros(nleg))], nleg)
     return Scenario("C1", 4, z, 1, 0, 0.6, np.array([1.0]), np.array([0.0]), 200e3,
                     np.asfortranarray(ssa), np.asfortranarray(k), np.asfortranarray(leg),
                     np.full(nwavel, 0.3), np.ones(nwavel))
@@ -119,7 +128,7 @@ def config2(nwavel: int = 100000, nlayers: int = 100, nstr: int = 16, nlos: int 
     w_aer = 0.95
     b_aer = hg_moments(0.7, nleg)
     comps = [(k_ray, 1.0, rayleigh_moments(nleg)), (k_aer, w_aer, b_aer), (k_o3, 0.0, np.zeros(nleg)),
-             (k_no2, 0.0, np.zeros(nleg))]
+             (k_no2, 0.0, np.zeros(nleg)), (CONTINUUM_ABSORPTION * k_ray, 0.0, np.zeros(nleg))]
     k, ssa, leg, ks = _mix(comps, nleg)
     sc = Scenario("C5" if with_wf else "C2", nstr, z, 1, 1, 0.6, np.linspace(1.0, 0.55, nlos),
                   np.linspace(0.0, np.pi, nlos), 200e3, np.asfortranarray(ssa), np.asfortranarray(k),

@@ -45,7 +45,9 @@ struct ChunkView {
     double* wvec;             // [nw][M][nlos][L][2N]  d(radiance_m)/d(L_j, M_j)
     double* vsrc;             // [nw][M][nlos][L]      particular + single-scatter (+ ground direct) terms
     double* xsol;             // [nw][M][L][2N]        BVP solution L | M
-    double* fac;              // [nw][M][L][2N][4N+1]  pivot rows of the staircase LU
+    double* fac;              // [group][fac_stride]   pivot rows of the staircase LU (forward and adjoint)
+    size_t fac_stride;        // doubles per solve group: (L+1) * 2N * (4N + max nrhs)
+    double* zadj;             // [nw][M][nlos][2N*L]   adjoint BVP solutions A^T z = wvec (weighting functions)
     double* radiance;         // [nw][nlos]
     unsigned int* status;     // error bits
 };

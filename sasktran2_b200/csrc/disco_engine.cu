@@ -103,7 +103,7 @@ size_t DeviceEngine::workspace_bytes_per_wavelength() const {
     d += 2 * N + 1;                                                 // surface sums
     d += M * nlos * L * 2 * N + M * nlos * L;                       // wvec, vsrc
     d += M * L * 2 * N;                                             // x
-    d += M * L * 2 * N * (4 * N + 1);                               // LU pivot rows
+    d += M * (L + 1) * 2 * N * (4 * N + 1);                         // LU pivot rows
     return d * sizeof(double);
 }
 
@@ -141,7 +141,9 @@ void DeviceEngine::ensure_workspace(int chunk) {
     V.wvec = A(c * M * nlos * L * 2 * N);
     V.vsrc = A(c * M * nlos * L);
     V.xsol = A(c * M * L * 2 * N);
-    V.fac = A(c * M * L * 2 * N * (4 * N + 1));
+    V.fac_stride = (L + 1) * 2 * N * (4 * N + 1);
+    V.fac = A(c * M * V.fac_stride);
+    V.zadj = nullptr;
     m_ws_chunk = chunk;
 }
 

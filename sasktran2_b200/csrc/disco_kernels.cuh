@@ -12,6 +12,9 @@ void launch_layer_optics(const ChunkView& V, cudaStream_t s);
 void launch_beam(const ChunkView& V, cudaStream_t s);
 void launch_layer_solve(const ChunkView& V, cudaStream_t s);
 void launch_bvp(const ChunkView& V, cudaStream_t s);
+void launch_bvp_adjoint(const ChunkView& V, cudaStream_t s);
+int adjoint_groups_per_problem(int nlos);
+int adjoint_max_rhs(int nlos);
 void launch_radiance(const ChunkView& V, cudaStream_t s);
 bool nstr_supported(int nstr);
 double measure_fp64_tflops();

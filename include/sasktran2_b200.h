@@ -179,8 +179,10 @@ int sk_openmp_support_enabled();
 const char* sk_b200_last_error();
 int sk_b200_device_count();
 int sk_b200_set_device(int device);
-/* Copy wavelengths [start, start+count) of the atmosphere to the device and keep them resident. */
-int sk_b200_engine_stage_atmosphere(Engine* engine, Atmosphere* atmosphere, int wavelength_start, int wavelength_count);
+/* Copy wavelengths [start, start+count) of the atmosphere (and, when `output` has derivative memory assigned,
+ * the derivative mappings) to the device and keep them resident.  `output` may be NULL (radiances only). */
+int sk_b200_engine_stage_atmosphere(Engine* engine, Atmosphere* atmosphere, OutputC* output, int wavelength_start,
+                                    int wavelength_count);
 /* Run the kernels on the staged wavelengths; nothing crosses PCIe. */
 int sk_b200_engine_solve_staged(Engine* engine);
 /* Copy the staged range's results into the output buffers (same offsets as the full-spectrum call). */

@@ -108,7 +108,7 @@ def _declare(lib):
     f("sk_b200_last_error", C.c_char_p)
     f("sk_b200_device_count", i)
     f("sk_b200_set_device", i, i)
-    f("sk_b200_engine_stage_atmosphere", i, vp, vp, i, i)
+    f("sk_b200_engine_stage_atmosphere", i, vp, vp, vp, i, i)
     f("sk_b200_engine_solve_staged", i, vp)
     f("sk_b200_engine_fetch_output", i, vp, vp)
     f("sk_b200_engine_get_timings", i, vp, c_double_p, i)

@@ -174,14 +174,60 @@ int validate(const Engine* e, const Atmosphere* atm, const OutputC* out, bool ch
     return 0;
 }
 
+// Collect the derivative mappings that have output memory assigned (OutputC::m_derivatives upstream)
+int build_wf_request(Engine* e, Atmosphere* atm, OutputC* out, disco::WfRequest& req) {
+    if (!out || !(atm->calc_derivs && e->cfg.wf_enabled && e->cfg.wf_precision == 0)) return 0;
+    if (out->derivs.empty() && out->surface_derivs.empty()) return 0;
+    AtmosphereStorage* s = atm->storage;
+    const int nlos = (int)e->viewing->rays.size();
+    const long long nrad = (long long)s->nwavel * nlos;
+    sk_atmosphere_storage_finalize_scattering_derivatives(s);
+    req.d_legendre.assign(s->num_scat_groups, nullptr);
+    for (auto& kv : s->mappings)
+        if (kv.second.is_scattering()) req.d_legendre[kv.second.scat_deriv_index] = kv.second.d_legendre.data();
+    for (auto& kv : out->derivs) {
+        auto it = s->mappings.find(kv.first);
+        if (it == s->mappings.end()) return fail(-2, "derivative memory assigned for unknown mapping '" + kv.first + "'");
+        MappingImpl& mi = it->second;
+        if (kv.second.nrad != nrad || kv.second.nstokes != 1 || kv.second.nderiv != mi.num_output())
+            return fail(-2, "derivative memory of mapping '" + kv.first + "' has the wrong shape");
+        DerivativeMapping tmp{&mi};
+        double* dummy;
+        sk_deriv_mapping_get_d_ssa(&tmp, &dummy);         // allocate (zeros) if the caller never touched them
+        sk_deriv_mapping_get_d_extinction(&tmp, &dummy);
+        disco::WfMapping m;
+        m.d_ssa = mi.d_ssa.data();
+        m.d_extinction = mi.d_extinction.data();
+        m.scat_factor = mi.is_scattering() ? mi.scat_factor.data() : nullptr;
+        m.scat_index = mi.scat_deriv_index;
+        m.interpolator = mi.interpolator.empty() ? nullptr : mi.interpolator.data();
+        m.nout = mi.num_output();
+        m.log_radiance_space = mi.log_radiance_space;
+        m.out = kv.second.ptr;
+        req.mappings.push_back(m);
+    }
+    for (auto& kv : out->surface_derivs) {
+        auto it = atm->surface->mappings.find(kv.first);
+        if (it == atm->surface->mappings.end()) return fail(-2, "surface derivative memory assigned for unknown mapping '" + kv.first + "'");
+        if (kv.second.nrad != nrad || kv.second.nstokes != 1) return fail(-2, "surface derivative memory has the wrong shape");
+        SurfaceDerivativeMapping tmp{&it->second};
+        double* dummy;
+        sk_surface_deriv_mapping_get_d_brdf(&tmp, &dummy);
+        disco::WfSurface sf;
+        sf.d_brdf = it->second.d_brdf.data();
+        sf.out = kv.second.ptr;
+        req.surfaces.push_back(sf);
+    }
+    return 0;
+}
+
 int run_range(Engine* e, Atmosphere* atm, OutputC* out, int start, int count) {
     try {
-        if (!out->derivs.empty() || !out->surface_derivs.empty()) {
-            if (atm->calc_derivs && e->cfg.wf_enabled)
-                return fail(-3, "weighting functions are not available in this build of the B200 DO path");
-        }
+        disco::WfRequest req;
+        int rc = build_wf_request(e, atm, out, req);
+        if (rc != 0) return rc;
         const int nlos = (int)e->viewing->rays.size();
-        e->dev->calculate(arrays_of(atm), start, count, out->radiance + (size_t)start * nlos);
+        e->dev->calculate(arrays_of(atm), start, count, out->radiance + (size_t)start * nlos, req.enabled() ? &req : nullptr);
         e->staged_start = start;
         e->staged_count = count;
         return 0;
@@ -754,14 +800,17 @@ int sk_b200_set_device(int device) {
     if (err != cudaSuccess) return fail(-3, std::string("cudaSetDevice: ") + cudaGetErrorString(err));
     return 0;
 }
-int sk_b200_engine_stage_atmosphere(Engine* e, Atmosphere* atm, int wavelength_start, int wavelength_count) {
+int sk_b200_engine_stage_atmosphere(Engine* e, Atmosphere* atm, OutputC* out, int wavelength_start, int wavelength_count) {
     if (!e || !e->dev) return fail(-1, "engine handle is null");
     std::lock_guard<std::mutex> lock(e->mtx);
-    int rc = validate(e, atm, nullptr, false);
+    int rc = validate(e, atm, out, out != nullptr);
     if (rc != 0) return rc;
     if (wavelength_count < 0) wavelength_count = atm->storage->nwavel - wavelength_start;
     try {
-        e->dev->stage(arrays_of(atm), wavelength_start, wavelength_count);
+        disco::WfRequest req;
+        rc = build_wf_request(e, atm, out, req);
+        if (rc != 0) return rc;
+        e->dev->stage(arrays_of(atm), wavelength_start, wavelength_count, req.enabled() ? &req : nullptr);
         e->atmosphere = atm;
         e->staged_start = wavelength_start;
         e->staged_count = wavelength_count;

@@ -49,6 +49,16 @@ struct ChunkView {
     size_t fac_stride;        // doubles per solve group: (L+1) * 2N * (4N + max nrhs)
     double* zadj;             // [nw][M][nlos][2N*L]   adjoint BVP solutions A^T z = wvec (weighting functions)
     double* radiance;         // [nw][nlos]
+    // ---- weighting functions (null / 0 when not requested)
+    int ngroups;              // scattering derivative groups G
+    const double* dleg;       // [G][nleg, nloc, nw_staged]: d_leg_coeff of group g (chunk-offset applied)
+    size_t dleg_gstride;      // doubles between groups
+    double* lay_dbeta;        // [nw][L][G][nstr] layer-level Legendre derivative direction per group
+    double* wf_loc;           // [nw][M][nlos][L][G+4]
+    double* wf_src;           // [nw][M][nlos][L]
+    double* wf_gnd;           // [nw][nlos][3]
+    double* wf_native;        // [nw][nlos][nloc*(2+G)+1]
+    double* wf_scratch;       // [nw][nlos][3][L+1]
     unsigned int* status;     // error bits
 };
 
@@ -86,6 +96,21 @@ DISCO_HD void optics_body(const ChunkView& V, long long idx) {
         for (int l = 0; l < nstr; ++l) beta[l] /= sc;
     } else {
         beta[0] = 0.0;
+    }
+    if (V.ngroups > 0) {
+        // Layer-level derivative direction of the Legendre moments for each scattering group.  The reference
+        // overwrites it for every contributing grid point, so the last (highest) one wins
+        // (sktran_do_layerarray.cpp:761-800); delta-M f = 0 on this path.
+        int ql = V.interp_idx[p * 2 + 1] >= 0 ? V.interp_idx[p * 2 + 1] : V.interp_idx[p * 2];
+        for (int g = 0; g < V.ngroups; ++g) {
+            const double* dl = V.dleg + g * V.dleg_gstride + (size_t)V.nleg * nloc * w;
+            double* db = V.lay_dbeta + ((size_t)idx * V.ngroups + g) * nstr;
+            for (int l = 0; l < nstr; ++l) {
+                const double ph = (l < V.nleg && ql >= 0) ? leg[l + (size_t)V.nleg * ql] : 0.0;
+                const double dv = (l < V.nleg && ql >= 0) ? dl[l + (size_t)V.nleg * ql] : 0.0;
+                db[l] = dv + (ph - beta[l]);
+            }
+        }
     }
     double ssa_l = sc / od;
     const double dh = V.layer_dh[p];

@@ -1,0 +1,293 @@
+// Staircase LU (forward and adjoint boundary-value solves) — templates, instantiated per stream count in
+// disco_bvp_inst.cu (one translation unit per N so that the build parallelises).
+#pragma once
+#include "disco_bvp_rows.h"
+#include "disco_kernels.cuh"
+
+namespace disco {
+
+#define FULL_MASK 0xffffffffu
+
+// -------------------------------------------------------------------------------------------------
+// K3: boundary value problem per (w, m), forward (A x = b) and adjoint (A^T z = w_los).
+//
+// Unknowns x = [L_0 M_0 | L_1 M_1 | ...] (2N per layer).  Rows: N TOA rows, 2N continuity rows per interface,
+// N ground rows.  Eliminating the 2N unknowns of layer p only ever involves the N rows left over from the
+// layers above plus the 2N rows of interface p+1, i.e. a 3N x (4N + nrhs) panel ("staircase").  One lane owns
+// one panel row in registers; the pivot row is broadcast through shared memory.  The candidate rows of every
+// column are exactly the rows LAPACK's banded partial pivoting (kl = ku = 3N-1) would search, so the
+// factorisation is the reference's dgbsv in a different storage scheme.  The transposed system has the same
+// staircase shape with the roles of layers and interfaces exchanged (unknown blocks N, 2N, ..., 2N, N), so
+// the adjoint solve (the reference's dgbtrs('T') in RTESolver::backprop, sktran_do_rte.cpp:1793-1836) is the
+// same elimination with a different row loader and one right-hand side per line of sight.
+// -------------------------------------------------------------------------------------------------
+template <int N, int NRHS>
+struct BvpCfg {
+    static constexpr int NC = 2 * N;
+    static constexpr int ROWS = 3 * N;
+    static constexpr int GL = ROWS <= 4 ? 4 : (ROWS <= 8 ? 8 : (ROWS <= 16 ? 16 : 32));
+    static constexpr int R = (ROWS + GL - 1) / GL;
+    static constexpr int ROWLEN = 4 * N + NRHS;
+    static constexpr int GROUPS_PER_WARP = 32 / GL;
+    static constexpr int WARPS_PER_BLOCK = (N >= 16) ? 2 : 4;
+    static constexpr int GROUPS_PER_BLOCK = GROUPS_PER_WARP * WARPS_PER_BLOCK;
+    static constexpr int BUF = ROWLEN + 1;  // padded
+    static constexpr int SMEM_DOUBLES_PER_GROUP = 2 * BUF + NC * ROWLEN + NRHS * NC;
+};
+
+template <int N, class Prob>
+__device__ __forceinline__ void staircase_solve(const Prob& prob, double* gs, double* fac, int lane, unsigned gbase,
+                                                unsigned gmask, bool valid, unsigned int* status) {
+    constexpr int NRHS = Prob::NRHS;
+    using C = BvpCfg<N, NRHS>;
+    constexpr int NC = C::NC, GL = C::GL, R = C::R, ROWLEN = C::ROWLEN;
+    double* buf = gs;                      // [2][BUF]
+    double* facs = gs + 2 * C::BUF;        // [NC][ROWLEN]
+    double* xs = facs + NC * ROWLEN;       // [NRHS][NC]
+
+    double a[R][ROWLEN];
+    bool act[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        act[r] = false;
+#pragma unroll
+        for (int c = 0; c < ROWLEN; ++c) a[r][c] = 0.0;
+    }
+    const unsigned lt_mask = (lane == 0) ? 0u : (((1u << lane) - 1u) << gbase);
+    bool singular = false;
+    const int nsteps = prob.nsteps();
+
+    for (int step = 0; step < nsteps; ++step) {
+        // ---- bring the new rows of this step into free slots
+        {
+            unsigned freeb[R];
+            bool wasfree[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                wasfree[r] = !act[r];
+                freeb[r] = __ballot_sync(FULL_MASK, wasfree[r]) & gmask;
+            }
+            const int needed = prob.nnew(step);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (wasfree[r]) {
+                    // rank of this free slot in slot-id order (slot id = lane * R + r)
+                    int rank = 0;
+#pragma unroll
+                    for (int r2 = 0; r2 < R; ++r2) rank += __popc(freeb[r2] & lt_mask);
+#pragma unroll
+                    for (int r2 = 0; r2 < R; ++r2)
+                        if (r2 < r && wasfree[r2]) rank += 1;
+                    if (rank < needed) {
+                        act[r] = true;
+                        prob.load(step, rank, a[r]);
+                    }
+                }
+            }
+        }
+        // ---- eliminate the unknowns of this block
+        const int nleft = prob.nleft(step);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (c < nleft) {
+                double best = -1.0;
+                int bsid = 0x7fffffff;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (act[r]) {
+                        const double v = fabs(a[r][c]);
+                        if (v > best) {
+                            best = v;
+                            bsid = lane * R + r;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int off = GL / 2; off > 0; off >>= 1) {
+                    const double ov = __shfl_xor_sync(FULL_MASK, best, off);
+                    const int oi = __shfl_xor_sync(FULL_MASK, bsid, off);
+                    if (ov > best || (ov == best && oi < bsid)) {
+                        best = ov;
+                        bsid = oi;
+                    }
+                }
+                if (!(best > 0.0)) singular = true;
+                double* bc = buf + (c & 1) * C::BUF;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (act[r] && bsid == lane * R + r) {
+                        act[r] = false;
+#pragma unroll
+                        for (int cc = 0; cc < ROWLEN; ++cc) {
+                            const double v = (cc >= c) ? a[r][cc] : 0.0;
+                            if (cc >= c) bc[cc] = v;
+                            facs[c * ROWLEN + cc] = v;
+                        }
+                    }
+                }
+                __syncwarp();
+                const double pinv = 1.0 / bc[c];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (act[r]) {
+                        const double f = a[r][c] * pinv;
+#pragma unroll
+                        for (int cc = c + 1; cc < ROWLEN; ++cc) a[r][cc] -= f * bc[cc];
+                        a[r][c] = 0.0;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- flush the pivot rows of this block (coalesced) and slide the panel window
+        if (valid) {
+            double* dst = fac + (size_t)step * NC * ROWLEN;
+            for (int e = lane; e < nleft * ROWLEN; e += GL) dst[e] = facs[e];
+        }
+        __syncwarp();
+        if (step < nsteps - 1) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    a[r][j] = a[r][NC + j];
+                    a[r][NC + j] = 0.0;
+                }
+            }
+        }
+    }
+    if (singular && valid) atomicOr(status, 4u);
+
+    // ---- back substitution, last block first; lane c owns pivot row c
+    for (int step = nsteps - 1; step >= 0; --step) {
+        const int nleft = prob.nleft(step);
+        const int nright = prob.nright(step);
+        if (step < nsteps - 1) {
+            const double* src = fac + (size_t)step * NC * ROWLEN;
+            for (int e = lane; e < nleft * ROWLEN; e += GL) facs[e] = src[e];
+            __syncwarp();
+        }
+        double acc[NRHS], myx[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            acc[r] = 0.0;
+            myx[r] = 0.0;
+        }
+        if (lane < nleft) {
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) acc[r] = facs[lane * ROWLEN + 4 * N + r];
+            for (int j = 0; j < nright; ++j) {
+                const double rj = facs[lane * ROWLEN + NC + j];
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) acc[r] -= rj * xs[r * NC + j];
+            }
+        }
+#pragma unroll
+        for (int cc = NC - 1; cc >= 0; --cc) {
+            if (cc < nleft) {
+                const double dinv = 1.0 / facs[cc * ROWLEN + cc];
+                const double u = (lane < cc) ? facs[lane * ROWLEN + cc] : 0.0;
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) {
+                    double xv = (lane == cc) ? acc[r] * dinv : 0.0;
+                    xv = __shfl_sync(FULL_MASK, xv, (int)gbase + cc);
+                    if (lane < cc) acc[r] -= u * xv;
+                    if (lane == cc) myx[r] = xv;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < nleft) {
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                xs[r * NC + lane] = myx[r];
+                if (valid) prob.store(step, lane, r, myx[r]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(BvpCfg<N, 1>::WARPS_PER_BLOCK * 32) k_bvp(ChunkView V) {
+    using C = BvpCfg<N, 1>;
+    extern __shared__ double smem[];
+    const int lane_w = threadIdx.x & 31;
+    const int gidx_in_block = threadIdx.x / C::GL;
+    const int lane = threadIdx.x % C::GL;
+    const unsigned gbase = (unsigned)((lane_w / C::GL) * C::GL);
+    const unsigned gmask = (C::GL == 32) ? FULL_MASK : (((1u << C::GL) - 1u) << gbase);
+    long long prob = (long long)blockIdx.x * C::GROUPS_PER_BLOCK + gidx_in_block;
+    const long long nprob = (long long)V.nw * V.M;
+    const bool valid = prob < nprob;
+    if (!valid) prob = nprob - 1;
+    const int w = (int)(prob / V.M), ms = (int)(prob % V.M);
+    ForwardRows<N> rows(V, w, ms);
+    double* fac = V.fac + (size_t)prob * V.fac_stride;
+    staircase_solve<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
+                       V.status);
+}
+
+// one group per (w, m, batch of NRHS lines of sight)
+template <int N, int NRHS>
+__global__ void __launch_bounds__(BvpCfg<N, NRHS>::WARPS_PER_BLOCK * 32) k_bvp_adjoint(ChunkView V, int los0, int nbatch) {
+    using C = BvpCfg<N, NRHS>;
+    extern __shared__ double smem[];
+    const int lane_w = threadIdx.x & 31;
+    const int gidx_in_block = threadIdx.x / C::GL;
+    const int lane = threadIdx.x % C::GL;
+    const unsigned gbase = (unsigned)((lane_w / C::GL) * C::GL);
+    const unsigned gmask = (C::GL == 32) ? FULL_MASK : (((1u << C::GL) - 1u) << gbase);
+    long long gid = (long long)blockIdx.x * C::GROUPS_PER_BLOCK + gidx_in_block;
+    const long long ngroups = (long long)V.nw * V.M * nbatch;
+    const bool valid = gid < ngroups;
+    if (!valid) gid = ngroups - 1;
+    const int batch = (int)(gid % nbatch);
+    const long long prob = gid / nbatch;
+    const int w = (int)(prob / V.M), ms = (int)(prob % V.M);
+    AdjointRows<N, NRHS> rows(V, w, ms, los0 + batch * NRHS);
+    double* fac = V.fac + (size_t)gid * V.fac_stride;
+    staircase_solve<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
+                       V.status);
+}
+
+template <int N>
+static void launch_bvp_n(const ChunkView& V, cudaStream_t s) {
+    using C = BvpCfg<N, 1>;
+    const long long nprob = (long long)V.nw * V.M;
+    const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_bvp<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    k_bvp<N><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
+}
+template <int N, int NRHS>
+static void launch_adj_batch(const ChunkView& V, int los0, int nbatch, cudaStream_t s) {
+    using C = BvpCfg<N, NRHS>;
+    const long long ngroups = (long long)V.nw * V.M * nbatch;
+    const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_bvp_adjoint<N, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    k_bvp_adjoint<N, NRHS><<<(unsigned)((ngroups + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK),
+                             C::WARPS_PER_BLOCK * 32, smem, s>>>(V, los0, nbatch);
+}
+// Lines of sight are solved in batches of NRHS right-hand sides per factorisation of A^T (a partially filled
+// last batch carries zero columns): 4 when there are at most 4 lines of sight, else 10.
+static int adj_rhs_for(int nlos) { return nlos <= 4 ? 4 : 10; }
+template <int N>
+static void launch_bvp_adjoint_n(const ChunkView& V, cudaStream_t s) {
+    const int nlos = V.T.nlos;
+    const int nrhs = adj_rhs_for(nlos);
+    const int nbatch = (nlos + nrhs - 1) / nrhs;
+    if (nrhs == 4)
+        launch_adj_batch<N, 4>(V, 0, nbatch, s);
+    else
+        launch_adj_batch<N, 10>(V, 0, nbatch, s);
+}
+
+}  // namespace disco

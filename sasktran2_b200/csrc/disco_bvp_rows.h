@@ -1,0 +1,178 @@
+// Row loaders of the staircase systems (forward A x = b and adjoint A^T z = wvec), host/device so that the
+// CPU emulation in tests/host_emul.cpp exercises exactly the rows the CUDA kernels eliminate.
+#pragma once
+#include "disco_bodies.h"
+
+namespace disco {
+
+// Row loader of the forward system A x = b (sktran_do_rte.cpp:1898-2294, sktran_do_rte.h:116-345)
+template <int N>
+struct ForwardRows {
+    static constexpr int NRHS = 1;
+    const ChunkView& V;
+    int w, ms, m, L;
+    const double *Wp, *Wm, *kth, *G;
+    DISCO_HD ForwardRows(const ChunkView& V_, int w_, int ms_) : V(V_), w(w_), ms(ms_) {
+        L = V.T.L;
+        m = V.m_list[ms];
+        const size_t lay0 = ((size_t)w * V.M + ms) * L;
+        Wp = V.Wp + lay0 * N * N;
+        Wm = V.Wm + lay0 * N * N;
+        kth = V.kth + lay0 * 2 * N;
+        G = V.G + lay0 * 4 * N;
+    }
+    DISCO_HD int nsteps() const { return L; }
+    DISCO_HD int nleft(int) const { return 2 * N; }
+    DISCO_HD int nright(int step) const { return step < L - 1 ? 2 * N : 0; }
+    DISCO_HD int nnew(int step) const { return (step == 0 ? N : 0) + (step < L - 1 ? 2 * N : N); }
+    DISCO_HD void load(int step, int rank, double* a) const {
+        const int p = step;
+        if (step == 0 && rank < N) {
+            // TOA rows: W+_0 L + W-_0 Theta_0 M = -G+top_0
+            const int i = rank;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                a[j] = Wp[i * N + j];
+                a[N + j] = Wm[i * N + j] * kth[N + j];
+                a[2 * N + j] = 0.0;
+                a[3 * N + j] = 0.0;
+            }
+            a[4 * N] = -G[i];
+            return;
+        }
+        if (step == 0) rank -= N;
+        const double* Wpu = Wp + (size_t)p * N * N;
+        const double* Wmu = Wm + (size_t)p * N * N;
+        const double* thu = kth + (size_t)p * 2 * N + N;
+        const double* Gu = G + (size_t)p * 4 * N;
+        if (p < L - 1) {
+            // continuity between layer p (upper) and p+1 (lower)
+            const double* Wpl = Wpu + N * N;
+            const double* Wml = Wmu + N * N;
+            const double* thl = thu + 2 * N;
+            const double* Gl = Gu + 4 * N;
+            const bool first = rank < N;  // rows i: W- family; rows i+N: W+ family
+            const int i = first ? rank : rank - N;
+            const double* A1 = first ? Wmu : Wpu;  // multiplies L_upper (with theta)
+            const double* A2 = first ? Wpu : Wmu;  // multiplies M_upper
+            const double* B1 = first ? Wml : Wpl;  // multiplies L_lower
+            const double* B2 = first ? Wpl : Wml;  // multiplies M_lower (with theta)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                a[j] = A1[i * N + j] * thu[j];
+                a[N + j] = A2[i * N + j];
+                a[2 * N + j] = -B1[i * N + j];
+                a[3 * N + j] = -(B2[i * N + j] * thl[j]);
+            }
+            a[4 * N] = first ? (-Gu[3 * N + i] + Gl[N + i]) : (-Gu[2 * N + i] + Gl[i]);
+        } else {
+            // ground rows (Lambertian: only m = 0 reflects)
+            const int i = rank;
+            const bool refl = (m == 0);
+            const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
+            const double* surf = V.surf + (size_t)w * (2 * N + 1);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                double vm = Wmu[i * N + j], vp = Wpu[i * N + j];
+                if (refl) {
+                    vm -= alb2 * surf[j];      // - (1+d_m0) rho sum_q w mu W+_qj
+                    vp -= alb2 * surf[N + j];  // - (1+d_m0) rho sum_q w mu W-_qj
+                }
+                a[j] = vm * thu[j];
+                a[N + j] = vp;
+                a[2 * N + j] = 0.0;
+                a[3 * N + j] = 0.0;
+            }
+            double rhs = -Gu[3 * N + i];
+            if (refl) {
+                rhs += alb2 * surf[2 * N];
+                rhs += V.T.csz * V.albedo[w] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
+            }
+            a[4 * N] = rhs;
+        }
+    }
+    // unknown c of block `step`, right-hand side r
+    DISCO_HD void store(int step, int c, int, double v) const {
+        V.xsol[(((size_t)w * V.M + ms) * L + step) * 2 * N + c] = v;
+    }
+};
+
+// Row loader of the transposed system A^T z = wvec(los): equation block b = columns of layer b, unknown
+// blocks = rows of A (TOA rows, interface rows, ground rows).
+template <int N, int NRHS_>
+struct AdjointRows {
+    static constexpr int NRHS = NRHS_;
+    const ChunkView& V;
+    int w, ms, m, L, los0, nl;
+    const double *Wp, *Wm, *kth;
+    DISCO_HD AdjointRows(const ChunkView& V_, int w_, int ms_, int los0_) : V(V_), w(w_), ms(ms_), los0(los0_) {
+        L = V.T.L;
+        m = V.m_list[ms];
+        nl = V.T.nlos - los0 < NRHS ? V.T.nlos - los0 : NRHS;
+        const size_t lay0 = ((size_t)w * V.M + ms) * L;
+        Wp = V.Wp + lay0 * N * N;
+        Wm = V.Wm + lay0 * N * N;
+        kth = V.kth + lay0 * 2 * N;
+    }
+    DISCO_HD int nsteps() const { return L + 1; }
+    DISCO_HD int nleft(int step) const { return (step == 0 || step == L) ? N : 2 * N; }
+    DISCO_HD int nright(int step) const { return step < L - 1 ? 2 * N : (step == L - 1 ? N : 0); }
+    DISCO_HD int nnew(int step) const { return step < L ? 2 * N : 0; }
+    DISCO_HD void load(int step, int rank, double* a) const {
+        const int b = step;  // layer whose unknown column `rank` this equation belongs to
+        const bool isL = rank < N;
+        const int j = isL ? rank : rank - N;
+        const double* Wpb = Wp + (size_t)b * N * N;
+        const double* Wmb = Wm + (size_t)b * N * N;
+        const double th = kth[(size_t)b * 2 * N + N + j];
+#pragma unroll
+        for (int c = 0; c < 4 * N; ++c) a[c] = 0.0;
+        if (b == 0) {
+            // column of the TOA block [W+ | W- Theta]
+#pragma unroll
+            for (int i = 0; i < N; ++i) a[i] = isL ? Wpb[i * N + j] : Wmb[i * N + j] * th;
+        } else {
+            // column of -V_b (layer b is the lower layer of interface b)
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                a[i] = isL ? -Wmb[i * N + j] : -(Wpb[i * N + j] * th);
+                a[N + i] = isL ? -Wpb[i * N + j] : -(Wmb[i * N + j] * th);
+            }
+        }
+        if (b < L - 1) {
+            // column of U_{b+1} (layer b is the upper layer of interface b+1)
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                a[2 * N + i] = isL ? Wmb[i * N + j] * th : Wpb[i * N + j];
+                a[3 * N + i] = isL ? Wpb[i * N + j] * th : Wmb[i * N + j];
+            }
+        } else {
+            // column of the ground block [v- Theta | v+]
+            const bool refl = (m == 0);
+            const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
+            const double* surf = V.surf + (size_t)w * (2 * N + 1);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double vm = Wmb[i * N + j], vp = Wpb[i * N + j];
+                if (refl) {
+                    vm -= alb2 * surf[j];
+                    vp -= alb2 * surf[N + j];
+                }
+                a[2 * N + i] = isL ? vm * th : vp;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            const int los = los0 + (r < nl ? r : 0);
+            const size_t o = (((size_t)w * V.M + ms) * V.T.nlos + los) * L + b;
+            a[4 * N + r] = (r < nl) ? V.wvec[o * 2 * N + rank] : 0.0;
+        }
+    }
+    DISCO_HD void store(int step, int c, int r, double v) const {
+        if (r >= nl) return;
+        const int row = (step == 0) ? c : N + (step - 1) * 2 * N + c;
+        V.zadj[(((size_t)w * V.M + ms) * V.T.nlos + (los0 + r)) * ((size_t)2 * N * L) + row] = v;
+    }
+};
+
+}  // namespace disco

@@ -1,4 +1,5 @@
 #include "disco_engine.h"
+#include "disco_wf_body.h"
 
 #include <algorithm>
 #include <cmath>
@@ -70,7 +71,23 @@ DeviceEngine::DeviceEngine(const EngineOptions& opt, const HostPlan& plan) : m_o
     CUDA_OK(cudaMemset(d_status, 0, sizeof(unsigned int)));
 }
 
+void DeviceEngine::free_wf_inputs() {
+    if (d_dleg) cudaFree(d_dleg);
+    d_dleg = nullptr;
+    for (auto& m : m_maps)
+        for (void* p : {(void*)m.d_ssa, (void*)m.d_ext, (void*)m.scat, (void*)m.interp, (void*)m.out})
+            if (p) cudaFree(p);
+    for (auto& s : m_surfs)
+        for (void* p : {(void*)s.d_brdf, (void*)s.out})
+            if (p) cudaFree(p);
+    m_maps.clear();
+    m_surfs.clear();
+    m_wf_on = false;
+    m_ngroups = 0;
+}
+
 DeviceEngine::~DeviceEngine() {
+    free_wf_inputs();
     free_inputs();
     free_workspace();
     for (void* p : {(void*)d_mu, (void*)d_wt, (void*)d_lp_mu, (void*)d_lp_csz, (void*)d_lp_los, (void*)d_los_mu,
@@ -103,7 +120,16 @@ size_t DeviceEngine::workspace_bytes_per_wavelength() const {
     d += 2 * N + 1;                                                 // surface sums
     d += M * nlos * L * 2 * N + M * nlos * L;                       // wvec, vsrc
     d += M * L * 2 * N;                                             // x
-    d += M * (L + 1) * 2 * N * (4 * N + 1);                         // LU pivot rows
+    if (!m_wf_on) {
+        d += M * (L + 1) * 2 * N * (4 * N + 1);                     // LU pivot rows (forward solve)
+    } else {
+        const size_t G = m_ngroups, nrhs = adjoint_max_rhs((int)nlos), ngrp = adjoint_groups_per_problem((int)nlos);
+        d += M * ngrp * (L + 1) * 2 * N * (4 * N + nrhs);           // LU pivot rows (forward and adjoint)
+        d += M * nlos * 2 * N * L;                                  // adjoint solutions
+        d += L * G * nstr;                                          // Legendre derivative directions
+        d += M * nlos * L * (G + 4) + M * nlos * L + nlos * 3;      // local lanes, sources, ground terms
+        d += nlos * (m_plan.nloc * (2 + G) + 1) + nlos * 3 * (L + 1);  // native derivatives, chain scratch
+    }
     return d * sizeof(double);
 }
 
@@ -115,7 +141,7 @@ int DeviceEngine::chunk_wavelengths() const {
 }
 
 void DeviceEngine::ensure_workspace(int chunk) {
-    if (chunk <= m_ws_chunk) return;
+    if (chunk <= m_ws_chunk && m_ws_wf == m_wf_on) return;
     free_workspace();
     const size_t N = m_plan.N, L = m_plan.L, nstr = m_plan.nstr, nlos = m_plan.nlos, M = m_mlist.size();
     const size_t c = chunk;
@@ -141,13 +167,28 @@ void DeviceEngine::ensure_workspace(int chunk) {
     V.wvec = A(c * M * nlos * L * 2 * N);
     V.vsrc = A(c * M * nlos * L);
     V.xsol = A(c * M * L * 2 * N);
-    V.fac_stride = (L + 1) * 2 * N * (4 * N + 1);
-    V.fac = A(c * M * V.fac_stride);
-    V.zadj = nullptr;
+    if (!m_wf_on) {
+        V.fac_stride = (L + 1) * 2 * N * (4 * N + 1);
+        V.fac = A(c * M * V.fac_stride);
+        V.zadj = nullptr;
+        V.lay_dbeta = V.wf_loc = V.wf_src = V.wf_gnd = V.wf_native = V.wf_scratch = nullptr;
+    } else {
+        const size_t G = m_ngroups, nrhs = adjoint_max_rhs((int)nlos), ngrp = adjoint_groups_per_problem((int)nlos);
+        V.fac_stride = (L + 1) * 2 * N * (4 * N + nrhs);
+        V.fac = A(c * M * ngrp * V.fac_stride);
+        V.zadj = A(c * M * nlos * 2 * N * L);
+        V.lay_dbeta = A(c * L * G * nstr);
+        V.wf_loc = A(c * M * nlos * L * (G + 4));
+        V.wf_src = A(c * M * nlos * L);
+        V.wf_gnd = A(c * nlos * 3);
+        V.wf_native = A(c * nlos * (m_plan.nloc * (2 + G) + 1));
+        V.wf_scratch = A(c * nlos * 3 * (L + 1));
+    }
+    m_ws_wf = m_wf_on;
     m_ws_chunk = chunk;
 }
 
-void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw) {
+void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRequest* wf) {
     if (atm.nloc != m_plan.nloc) throw std::runtime_error("atmosphere and geometry grids differ in size");
     if (w0 < 0 || nw < 0 || w0 + nw > atm.nwavel) throw std::runtime_error("wavelength range out of bounds");
     const size_t nloc = atm.nloc;
@@ -172,6 +213,49 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw) {
                                 cudaMemcpyHostToDevice, m_stream));
         CUDA_OK(cudaMemcpyAsync(d_solar, atm.solar + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
         CUDA_OK(cudaMemcpyAsync(d_albedo, atm.albedo + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
+    }
+    // weighting-function inputs of the staged range
+    free_wf_inputs();
+    m_w0 = w0;
+    m_nw_total = atm.nwavel;
+    if (wf && wf->enabled() && nw > 0) {
+        if (wf->d_legendre.size() > 2) throw std::runtime_error("B200 DO path supports at most 2 scattering derivative groups");
+        m_wf_on = true;
+        m_ngroups = (int)wf->d_legendre.size();
+        const size_t nl3 = (size_t)atm.nleg * nloc * nw;
+        if (m_ngroups > 0) {
+            d_dleg = dalloc<double>(nl3 * m_ngroups);
+            for (int g = 0; g < m_ngroups; ++g)
+                CUDA_OK(cudaMemcpyAsync(d_dleg + nl3 * g, wf->d_legendre[g] + (size_t)atm.nleg * nloc * w0,
+                                        sizeof(double) * nl3, cudaMemcpyHostToDevice, m_stream));
+        }
+        const size_t n2 = nloc * (size_t)nw;
+        for (const auto& mp : wf->mappings) {
+            DevMapping dm;
+            dm.host = mp;
+            dm.d_ssa = dalloc<double>(n2);
+            dm.d_ext = dalloc<double>(n2);
+            CUDA_OK(cudaMemcpyAsync(dm.d_ssa, mp.d_ssa + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
+            CUDA_OK(cudaMemcpyAsync(dm.d_ext, mp.d_extinction + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
+            if (mp.scat_factor) {
+                dm.scat = dalloc<double>(n2);
+                CUDA_OK(cudaMemcpyAsync(dm.scat, mp.scat_factor + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
+            }
+            if (mp.interpolator) {
+                dm.interp = dalloc<double>(nloc * (size_t)mp.nout);
+                CUDA_OK(cudaMemcpyAsync(dm.interp, mp.interpolator, sizeof(double) * nloc * mp.nout, cudaMemcpyHostToDevice, m_stream));
+            }
+            dm.out = dalloc<double>((size_t)mp.nout * nw * m_plan.nlos);
+            m_maps.push_back(dm);
+        }
+        for (const auto& sf : wf->surfaces) {
+            DevSurface ds;
+            ds.host = sf;
+            ds.d_brdf = dalloc<double>(nw);
+            CUDA_OK(cudaMemcpyAsync(ds.d_brdf, sf.d_brdf + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
+            ds.out = dalloc<double>((size_t)nw * m_plan.nlos);
+            m_surfs.push_back(ds);
+        }
     }
     CUDA_OK(cudaEventRecord(m_ev[1], m_stream));
     CUDA_OK(cudaStreamSynchronize(m_stream));
@@ -212,6 +296,7 @@ void DeviceEngine::solve_staged() {
     V.M = (int)m_mlist.size();
     V.m_list = d_mlist;
     V.status = d_status;
+    V.ngroups = m_wf_on ? m_ngroups : 0;
     const size_t nloc = m_plan.nloc;
     struct Span { cudaEvent_t a, b; int slot; };
     // per-kernel timing: events are recorded around every launch; elapsed times are read after the final sync
@@ -232,6 +317,8 @@ void DeviceEngine::solve_staged() {
         V.albedo = d_albedo + w0;
         V.solar = d_solar + w0;
         V.radiance = d_radiance + (size_t)w0 * m_plan.nlos;
+        V.dleg = d_dleg ? d_dleg + (size_t)m_nleg * nloc * w0 : nullptr;
+        V.dleg_gstride = (size_t)m_nleg * nloc * m_nw;
         launch_layer_optics(V, m_stream);
         launch_beam(V, m_stream);
         mark(); slots.push_back(T_OPTICS);
@@ -242,6 +329,29 @@ void DeviceEngine::solve_staged() {
         launch_radiance(V, m_stream);
         mark(); slots.push_back(T_RADIANCE);
         m_launches += 5;
+        if (m_wf_on) {
+            launch_bvp_adjoint(V, m_stream);
+            launch_wf_layer(V, m_stream);
+            launch_wf_chain(V, m_stream);
+            m_launches += 3;
+            for (auto& dm : m_maps) {
+                MappingView mv;
+                mv.d_ssa = dm.d_ssa;
+                mv.d_ext = dm.d_ext;
+                mv.scat_factor = dm.scat;
+                mv.scat_index = dm.host.scat_index;
+                mv.interp = dm.interp;
+                mv.nout = dm.host.nout;
+                mv.out = dm.out;
+                launch_wf_map(V, mv, w0, m_nw, dm.host.log_radiance_space, m_stream);
+                m_launches += dm.host.log_radiance_space ? 2 : 1;
+            }
+            for (auto& ds : m_surfs) {
+                launch_wf_surface(V, ds.d_brdf, ds.out, w0, m_stream);
+                m_launches += 1;
+            }
+            mark(); slots.push_back(T_WF);
+        }
     }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(m_stream));
@@ -268,6 +378,15 @@ void DeviceEngine::fetch(double* radiance_host) {
     if (m_nw > 0 && m_plan.nlos > 0)
         CUDA_OK(cudaMemcpyAsync(radiance_host, d_radiance, sizeof(double) * (size_t)m_nw * m_plan.nlos,
                                 cudaMemcpyDeviceToHost, m_stream));
+    if (m_wf_on && m_nw > 0) {
+        const size_t nlos = m_plan.nlos;
+        const size_t width = sizeof(double) * (size_t)m_nw * nlos;
+        for (auto& dm : m_maps)
+            CUDA_OK(cudaMemcpy2DAsync(dm.host.out + (size_t)m_w0 * nlos, sizeof(double) * (size_t)m_nw_total * nlos, dm.out,
+                                      width, width, dm.host.nout, cudaMemcpyDeviceToHost, m_stream));
+        for (auto& ds : m_surfs)
+            CUDA_OK(cudaMemcpyAsync(ds.host.out + (size_t)m_w0 * nlos, ds.out, width, cudaMemcpyDeviceToHost, m_stream));
+    }
     CUDA_OK(cudaEventRecord(m_ev[3], m_stream));
     CUDA_OK(cudaStreamSynchronize(m_stream));
     float ms = 0;
@@ -275,8 +394,8 @@ void DeviceEngine::fetch(double* radiance_host) {
     m_ms[T_D2H] = ms;
 }
 
-void DeviceEngine::calculate(const AtmosphereArrays& atm, int w0, int nw, double* radiance_host) {
-    stage(atm, w0, nw);
+void DeviceEngine::calculate(const AtmosphereArrays& atm, int w0, int nw, double* radiance_host, const WfRequest* wf) {
+    stage(atm, w0, nw, wf);
     solve_staged();
     fetch(radiance_host);
 }

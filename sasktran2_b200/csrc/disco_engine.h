@@ -29,7 +29,30 @@ struct AtmosphereArrays {
     const double* albedo = nullptr; // [nwavel]
 };
 
-enum TimingSlot { T_H2D = 0, T_OPTICS, T_LAYER, T_BVP, T_RADIANCE, T_D2H, T_TOTAL_KERNELS, T_NSLOTS };
+// Weighting-function request: which derivative mappings to evaluate and where the results go
+// (OutputC::assign_lane, cpp/lib/output/outputc.cpp:37-160).  All pointers are caller-owned host memory.
+struct WfMapping {
+    const double* d_ssa = nullptr;        // [nloc, nwavel]
+    const double* d_extinction = nullptr; // [nloc, nwavel]
+    const double* scat_factor = nullptr;  // [nloc, nwavel] or null (absorber)
+    int scat_index = -1;                  // scattering group of this mapping
+    const double* interpolator = nullptr; // [nloc, nout] column-major or null
+    int nout = 0;
+    bool log_radiance_space = false;
+    double* out = nullptr;                // [nout][nwavel][nlos]
+};
+struct WfSurface {
+    const double* d_brdf = nullptr;       // [nwavel]
+    double* out = nullptr;                // [nwavel][nlos]
+};
+struct WfRequest {
+    std::vector<const double*> d_legendre;  // per scattering group: [nleg, nloc, nwavel]
+    std::vector<WfMapping> mappings;
+    std::vector<WfSurface> surfaces;
+    bool enabled() const { return !mappings.empty() || !surfaces.empty(); }
+};
+
+enum TimingSlot { T_H2D = 0, T_OPTICS, T_LAYER, T_BVP, T_RADIANCE, T_D2H, T_TOTAL_KERNELS, T_WF, T_NSLOTS };
 
 class DeviceEngine {
   public:
@@ -39,13 +62,14 @@ class DeviceEngine {
     DeviceEngine& operator=(const DeviceEngine&) = delete;
 
     // Copy wavelengths [w0, w0+nw) of the atmosphere to the device and keep them resident.
-    void stage(const AtmosphereArrays& atm, int w0, int nw);
+    void stage(const AtmosphereArrays& atm, int w0, int nw, const WfRequest* wf = nullptr);
     // Run the kernels on the staged wavelengths; results stay on the device.
     void solve_staged();
     // Copy radiance [nw, nlos] of the staged range back to the host.
     void fetch(double* radiance_host);
     // stage + solve + fetch
-    void calculate(const AtmosphereArrays& atm, int w0, int nw, double* radiance_host);
+    void calculate(const AtmosphereArrays& atm, int w0, int nw, double* radiance_host, const WfRequest* wf = nullptr);
+    bool wf_active() const { return m_wf_on; }
 
     const double* timings_ms() const { return m_ms; }   // accumulated over the last solve / calculate
     long long kernel_launches() const { return m_launches; }
@@ -76,6 +100,22 @@ class DeviceEngine {
     double *d_ext = nullptr, *d_ssa = nullptr, *d_leg = nullptr, *d_solar = nullptr, *d_albedo = nullptr;
     double* d_radiance = nullptr;
     unsigned int* d_status = nullptr;
+    // weighting functions
+    struct DevMapping {
+        double *d_ssa = nullptr, *d_ext = nullptr, *scat = nullptr, *interp = nullptr, *out = nullptr;
+        WfMapping host;
+    };
+    struct DevSurface {
+        double *d_brdf = nullptr, *out = nullptr;
+        WfSurface host;
+    };
+    void free_wf_inputs();
+    bool m_wf_on = false;
+    int m_ngroups = 0, m_w0 = 0, m_nw_total = 0;
+    double* d_dleg = nullptr;
+    std::vector<DevMapping> m_maps;
+    std::vector<DevSurface> m_surfs;
+    bool m_ws_wf = false;
     // chunk workspace
     int m_ws_chunk = 0;
     std::vector<void*> m_ws_ptrs;

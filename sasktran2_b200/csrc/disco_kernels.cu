@@ -12,6 +12,7 @@
 //  K4  k_radiance       thread per (wavelength, LOS): azimuth sum of w.x + v
 //                       (source_term/do_source_planeparallel.cpp:69-158)
 #include "disco_kernels.cuh"
+#include "disco_wf_body.h"
 
 namespace disco {
 
@@ -46,419 +47,6 @@ __global__ void __launch_bounds__(128) k_layer_solve(ChunkView V) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// K3: boundary value problem per (w, m), forward (A x = b) and adjoint (A^T z = w_los).
-//
-// Unknowns x = [L_0 M_0 | L_1 M_1 | ...] (2N per layer).  Rows: N TOA rows, 2N continuity rows per interface,
-// N ground rows.  Eliminating the 2N unknowns of layer p only ever involves the N rows left over from the
-// layers above plus the 2N rows of interface p+1, i.e. a 3N x (4N + nrhs) panel ("staircase").  One lane owns
-// one panel row in registers; the pivot row is broadcast through shared memory.  The candidate rows of every
-// column are exactly the rows LAPACK's banded partial pivoting (kl = ku = 3N-1) would search, so the
-// factorisation is the reference's dgbsv in a different storage scheme.  The transposed system has the same
-// staircase shape with the roles of layers and interfaces exchanged (unknown blocks N, 2N, ..., 2N, N), so
-// the adjoint solve (the reference's dgbtrs('T') in RTESolver::backprop, sktran_do_rte.cpp:1793-1836) is the
-// same elimination with a different row loader and one right-hand side per line of sight.
-// -------------------------------------------------------------------------------------------------
-template <int N, int NRHS>
-struct BvpCfg {
-    static constexpr int NC = 2 * N;
-    static constexpr int ROWS = 3 * N;
-    static constexpr int GL = ROWS <= 4 ? 4 : (ROWS <= 8 ? 8 : (ROWS <= 16 ? 16 : 32));
-    static constexpr int R = (ROWS + GL - 1) / GL;
-    static constexpr int ROWLEN = 4 * N + NRHS;
-    static constexpr int GROUPS_PER_WARP = 32 / GL;
-    static constexpr int WARPS_PER_BLOCK = (N >= 16) ? 2 : 4;
-    static constexpr int GROUPS_PER_BLOCK = GROUPS_PER_WARP * WARPS_PER_BLOCK;
-    static constexpr int BUF = ROWLEN + 1;  // padded
-    static constexpr int SMEM_DOUBLES_PER_GROUP = 2 * BUF + NC * ROWLEN + NRHS * NC;
-};
-
-// Row loader of the forward system A x = b (sktran_do_rte.cpp:1898-2294, sktran_do_rte.h:116-345)
-template <int N>
-struct ForwardRows {
-    static constexpr int NRHS = 1;
-    const ChunkView& V;
-    int w, ms, m, L;
-    const double *Wp, *Wm, *kth, *G;
-    __device__ ForwardRows(const ChunkView& V_, int w_, int ms_) : V(V_), w(w_), ms(ms_) {
-        L = V.T.L;
-        m = V.m_list[ms];
-        const size_t lay0 = ((size_t)w * V.M + ms) * L;
-        Wp = V.Wp + lay0 * N * N;
-        Wm = V.Wm + lay0 * N * N;
-        kth = V.kth + lay0 * 2 * N;
-        G = V.G + lay0 * 4 * N;
-    }
-    __device__ int nsteps() const { return L; }
-    __device__ int nleft(int) const { return 2 * N; }
-    __device__ int nright(int step) const { return step < L - 1 ? 2 * N : 0; }
-    __device__ int nnew(int step) const { return (step == 0 ? N : 0) + (step < L - 1 ? 2 * N : N); }
-    __device__ void load(int step, int rank, double* a) const {
-        const int p = step;
-        if (step == 0 && rank < N) {
-            // TOA rows: W+_0 L + W-_0 Theta_0 M = -G+top_0
-            const int i = rank;
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                a[j] = Wp[i * N + j];
-                a[N + j] = Wm[i * N + j] * kth[N + j];
-                a[2 * N + j] = 0.0;
-                a[3 * N + j] = 0.0;
-            }
-            a[4 * N] = -G[i];
-            return;
-        }
-        if (step == 0) rank -= N;
-        const double* Wpu = Wp + (size_t)p * N * N;
-        const double* Wmu = Wm + (size_t)p * N * N;
-        const double* thu = kth + (size_t)p * 2 * N + N;
-        const double* Gu = G + (size_t)p * 4 * N;
-        if (p < L - 1) {
-            // continuity between layer p (upper) and p+1 (lower)
-            const double* Wpl = Wpu + N * N;
-            const double* Wml = Wmu + N * N;
-            const double* thl = thu + 2 * N;
-            const double* Gl = Gu + 4 * N;
-            const bool first = rank < N;  // rows i: W- family; rows i+N: W+ family
-            const int i = first ? rank : rank - N;
-            const double* A1 = first ? Wmu : Wpu;  // multiplies L_upper (with theta)
-            const double* A2 = first ? Wpu : Wmu;  // multiplies M_upper
-            const double* B1 = first ? Wml : Wpl;  // multiplies L_lower
-            const double* B2 = first ? Wpl : Wml;  // multiplies M_lower (with theta)
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                a[j] = A1[i * N + j] * thu[j];
-                a[N + j] = A2[i * N + j];
-                a[2 * N + j] = -B1[i * N + j];
-                a[3 * N + j] = -(B2[i * N + j] * thl[j]);
-            }
-            a[4 * N] = first ? (-Gu[3 * N + i] + Gl[N + i]) : (-Gu[2 * N + i] + Gl[i]);
-        } else {
-            // ground rows (Lambertian: only m = 0 reflects)
-            const int i = rank;
-            const bool refl = (m == 0);
-            const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
-            const double* surf = V.surf + (size_t)w * (2 * N + 1);
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                double vm = Wmu[i * N + j], vp = Wpu[i * N + j];
-                if (refl) {
-                    vm -= alb2 * surf[j];      // - (1+d_m0) rho sum_q w mu W+_qj
-                    vp -= alb2 * surf[N + j];  // - (1+d_m0) rho sum_q w mu W-_qj
-                }
-                a[j] = vm * thu[j];
-                a[N + j] = vp;
-                a[2 * N + j] = 0.0;
-                a[3 * N + j] = 0.0;
-            }
-            double rhs = -Gu[3 * N + i];
-            if (refl) {
-                rhs += alb2 * surf[2 * N];
-                rhs += V.T.csz * V.albedo[w] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
-            }
-            a[4 * N] = rhs;
-        }
-    }
-    // unknown c of block `step`, right-hand side r
-    __device__ void store(int step, int c, int, double v) const {
-        V.xsol[(((size_t)w * V.M + ms) * L + step) * 2 * N + c] = v;
-    }
-};
-
-// Row loader of the transposed system A^T z = wvec(los): equation block b = columns of layer b, unknown
-// blocks = rows of A (TOA rows, interface rows, ground rows).
-template <int N, int NRHS_>
-struct AdjointRows {
-    static constexpr int NRHS = NRHS_;
-    const ChunkView& V;
-    int w, ms, m, L, los0, nl;
-    const double *Wp, *Wm, *kth;
-    __device__ AdjointRows(const ChunkView& V_, int w_, int ms_, int los0_) : V(V_), w(w_), ms(ms_), los0(los0_) {
-        L = V.T.L;
-        m = V.m_list[ms];
-        nl = V.T.nlos - los0 < NRHS ? V.T.nlos - los0 : NRHS;
-        const size_t lay0 = ((size_t)w * V.M + ms) * L;
-        Wp = V.Wp + lay0 * N * N;
-        Wm = V.Wm + lay0 * N * N;
-        kth = V.kth + lay0 * 2 * N;
-    }
-    __device__ int nsteps() const { return L + 1; }
-    __device__ int nleft(int step) const { return (step == 0 || step == L) ? N : 2 * N; }
-    __device__ int nright(int step) const { return step < L - 1 ? 2 * N : (step == L - 1 ? N : 0); }
-    __device__ int nnew(int step) const { return step < L ? 2 * N : 0; }
-    __device__ void load(int step, int rank, double* a) const {
-        const int b = step;  // layer whose unknown column `rank` this equation belongs to
-        const bool isL = rank < N;
-        const int j = isL ? rank : rank - N;
-        const double* Wpb = Wp + (size_t)b * N * N;
-        const double* Wmb = Wm + (size_t)b * N * N;
-        const double th = kth[(size_t)b * 2 * N + N + j];
-#pragma unroll
-        for (int c = 0; c < 4 * N; ++c) a[c] = 0.0;
-        if (b == 0) {
-            // column of the TOA block [W+ | W- Theta]
-#pragma unroll
-            for (int i = 0; i < N; ++i) a[i] = isL ? Wpb[i * N + j] : Wmb[i * N + j] * th;
-        } else {
-            // column of -V_b (layer b is the lower layer of interface b)
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                a[i] = isL ? -Wmb[i * N + j] : -(Wpb[i * N + j] * th);
-                a[N + i] = isL ? -Wpb[i * N + j] : -(Wmb[i * N + j] * th);
-            }
-        }
-        if (b < L - 1) {
-            // column of U_{b+1} (layer b is the upper layer of interface b+1)
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                a[2 * N + i] = isL ? Wmb[i * N + j] * th : Wpb[i * N + j];
-                a[3 * N + i] = isL ? Wpb[i * N + j] * th : Wmb[i * N + j];
-            }
-        } else {
-            // column of the ground block [v- Theta | v+]
-            const bool refl = (m == 0);
-            const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
-            const double* surf = V.surf + (size_t)w * (2 * N + 1);
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                double vm = Wmb[i * N + j], vp = Wpb[i * N + j];
-                if (refl) {
-                    vm -= alb2 * surf[j];
-                    vp -= alb2 * surf[N + j];
-                }
-                a[2 * N + i] = isL ? vm * th : vp;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) {
-            const int los = los0 + (r < nl ? r : 0);
-            const size_t o = (((size_t)w * V.M + ms) * V.T.nlos + los) * L + b;
-            a[4 * N + r] = (r < nl) ? V.wvec[o * 2 * N + rank] : 0.0;
-        }
-    }
-    __device__ void store(int step, int c, int r, double v) const {
-        if (r >= nl) return;
-        const int row = (step == 0) ? c : N + (step - 1) * 2 * N + c;
-        V.zadj[(((size_t)w * V.M + ms) * V.T.nlos + (los0 + r)) * ((size_t)2 * N * L) + row] = v;
-    }
-};
-
-template <int N, class Prob>
-__device__ __forceinline__ void staircase_solve(const Prob& prob, double* gs, double* fac, int lane, unsigned gbase,
-                                                unsigned gmask, bool valid, unsigned int* status) {
-    constexpr int NRHS = Prob::NRHS;
-    using C = BvpCfg<N, NRHS>;
-    constexpr int NC = C::NC, GL = C::GL, R = C::R, ROWLEN = C::ROWLEN;
-    double* buf = gs;                      // [2][BUF]
-    double* facs = gs + 2 * C::BUF;        // [NC][ROWLEN]
-    double* xs = facs + NC * ROWLEN;       // [NRHS][NC]
-
-    double a[R][ROWLEN];
-    bool act[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        act[r] = false;
-#pragma unroll
-        for (int c = 0; c < ROWLEN; ++c) a[r][c] = 0.0;
-    }
-    const unsigned lt_mask = (lane == 0) ? 0u : (((1u << lane) - 1u) << gbase);
-    bool singular = false;
-    const int nsteps = prob.nsteps();
-
-    for (int step = 0; step < nsteps; ++step) {
-        // ---- bring the new rows of this step into free slots
-        {
-            unsigned freeb[R];
-            bool wasfree[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                wasfree[r] = !act[r];
-                freeb[r] = __ballot_sync(FULL_MASK, wasfree[r]) & gmask;
-            }
-            const int needed = prob.nnew(step);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (wasfree[r]) {
-                    // rank of this free slot in slot-id order (slot id = lane * R + r)
-                    int rank = 0;
-#pragma unroll
-                    for (int r2 = 0; r2 < R; ++r2) rank += __popc(freeb[r2] & lt_mask);
-#pragma unroll
-                    for (int r2 = 0; r2 < R; ++r2)
-                        if (r2 < r && wasfree[r2]) rank += 1;
-                    if (rank < needed) {
-                        act[r] = true;
-                        prob.load(step, rank, a[r]);
-                    }
-                }
-            }
-        }
-        // ---- eliminate the unknowns of this block
-        const int nleft = prob.nleft(step);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            if (c < nleft) {
-                double best = -1.0;
-                int bsid = 0x7fffffff;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (act[r]) {
-                        const double v = fabs(a[r][c]);
-                        if (v > best) {
-                            best = v;
-                            bsid = lane * R + r;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int off = GL / 2; off > 0; off >>= 1) {
-                    const double ov = __shfl_xor_sync(FULL_MASK, best, off);
-                    const int oi = __shfl_xor_sync(FULL_MASK, bsid, off);
-                    if (ov > best || (ov == best && oi < bsid)) {
-                        best = ov;
-                        bsid = oi;
-                    }
-                }
-                if (!(best > 0.0)) singular = true;
-                double* bc = buf + (c & 1) * C::BUF;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (act[r] && bsid == lane * R + r) {
-                        act[r] = false;
-#pragma unroll
-                        for (int cc = 0; cc < ROWLEN; ++cc) {
-                            const double v = (cc >= c) ? a[r][cc] : 0.0;
-                            if (cc >= c) bc[cc] = v;
-                            facs[c * ROWLEN + cc] = v;
-                        }
-                    }
-                }
-                __syncwarp();
-                const double pinv = 1.0 / bc[c];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (act[r]) {
-                        const double f = a[r][c] * pinv;
-#pragma unroll
-                        for (int cc = c + 1; cc < ROWLEN; ++cc) a[r][cc] -= f * bc[cc];
-                        a[r][c] = 0.0;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        // ---- flush the pivot rows of this block (coalesced) and slide the panel window
-        if (valid) {
-            double* dst = fac + (size_t)step * NC * ROWLEN;
-            for (int e = lane; e < nleft * ROWLEN; e += GL) dst[e] = facs[e];
-        }
-        __syncwarp();
-        if (step < nsteps - 1) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-#pragma unroll
-                for (int j = 0; j < NC; ++j) {
-                    a[r][j] = a[r][NC + j];
-                    a[r][NC + j] = 0.0;
-                }
-            }
-        }
-    }
-    if (singular && valid) atomicOr(status, 4u);
-
-    // ---- back substitution, last block first; lane c owns pivot row c
-    for (int step = nsteps - 1; step >= 0; --step) {
-        const int nleft = prob.nleft(step);
-        const int nright = prob.nright(step);
-        if (step < nsteps - 1) {
-            const double* src = fac + (size_t)step * NC * ROWLEN;
-            for (int e = lane; e < nleft * ROWLEN; e += GL) facs[e] = src[e];
-            __syncwarp();
-        }
-        double acc[NRHS], myx[NRHS];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) {
-            acc[r] = 0.0;
-            myx[r] = 0.0;
-        }
-        if (lane < nleft) {
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) acc[r] = facs[lane * ROWLEN + 4 * N + r];
-            for (int j = 0; j < nright; ++j) {
-                const double rj = facs[lane * ROWLEN + NC + j];
-#pragma unroll
-                for (int r = 0; r < NRHS; ++r) acc[r] -= rj * xs[r * NC + j];
-            }
-        }
-#pragma unroll
-        for (int cc = NC - 1; cc >= 0; --cc) {
-            if (cc < nleft) {
-                const double dinv = 1.0 / facs[cc * ROWLEN + cc];
-                const double u = (lane < cc) ? facs[lane * ROWLEN + cc] : 0.0;
-#pragma unroll
-                for (int r = 0; r < NRHS; ++r) {
-                    double xv = (lane == cc) ? acc[r] * dinv : 0.0;
-                    xv = __shfl_sync(FULL_MASK, xv, (int)gbase + cc);
-                    if (lane < cc) acc[r] -= u * xv;
-                    if (lane == cc) myx[r] = xv;
-                }
-            }
-        }
-        __syncwarp();
-        if (lane < nleft) {
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) {
-                xs[r * NC + lane] = myx[r];
-                if (valid) prob.store(step, lane, r, myx[r]);
-            }
-        }
-        __syncwarp();
-    }
-}
-
-template <int N>
-__global__ void __launch_bounds__(BvpCfg<N, 1>::WARPS_PER_BLOCK * 32) k_bvp(ChunkView V) {
-    using C = BvpCfg<N, 1>;
-    extern __shared__ double smem[];
-    const int lane_w = threadIdx.x & 31;
-    const int gidx_in_block = threadIdx.x / C::GL;
-    const int lane = threadIdx.x % C::GL;
-    const unsigned gbase = (unsigned)((lane_w / C::GL) * C::GL);
-    const unsigned gmask = (C::GL == 32) ? FULL_MASK : (((1u << C::GL) - 1u) << gbase);
-    long long prob = (long long)blockIdx.x * C::GROUPS_PER_BLOCK + gidx_in_block;
-    const long long nprob = (long long)V.nw * V.M;
-    const bool valid = prob < nprob;
-    if (!valid) prob = nprob - 1;
-    const int w = (int)(prob / V.M), ms = (int)(prob % V.M);
-    ForwardRows<N> rows(V, w, ms);
-    double* fac = V.fac + (size_t)prob * V.fac_stride;
-    staircase_solve<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
-                       V.status);
-}
-
-// one group per (w, m, batch of NRHS lines of sight)
-template <int N, int NRHS>
-__global__ void __launch_bounds__(BvpCfg<N, NRHS>::WARPS_PER_BLOCK * 32) k_bvp_adjoint(ChunkView V, int los0, int nbatch) {
-    using C = BvpCfg<N, NRHS>;
-    extern __shared__ double smem[];
-    const int lane_w = threadIdx.x & 31;
-    const int gidx_in_block = threadIdx.x / C::GL;
-    const int lane = threadIdx.x % C::GL;
-    const unsigned gbase = (unsigned)((lane_w / C::GL) * C::GL);
-    const unsigned gmask = (C::GL == 32) ? FULL_MASK : (((1u << C::GL) - 1u) << gbase);
-    long long gid = (long long)blockIdx.x * C::GROUPS_PER_BLOCK + gidx_in_block;
-    const long long ngroups = (long long)V.nw * V.M * nbatch;
-    const bool valid = gid < ngroups;
-    if (!valid) gid = ngroups - 1;
-    const int batch = (int)(gid % nbatch);
-    const long long prob = gid / nbatch;
-    const int w = (int)(prob / V.M), ms = (int)(prob % V.M);
-    AdjointRows<N, NRHS> rows(V, w, ms, los0 + batch * NRHS);
-    double* fac = V.fac + (size_t)gid * V.fac_stride;
-    staircase_solve<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
-                       V.status);
-}
-
-// -------------------------------------------------------------------------------------------------
 // K4: radiance[w, los] = sum_m cos(m phi) * sum_p ( wvec . x + v )
 // -------------------------------------------------------------------------------------------------
 __global__ void k_radiance(ChunkView V) {
@@ -481,44 +69,40 @@ static void launch_layer_solve_n(const ChunkView& V, cudaStream_t s) {
     const long long n = (long long)V.nw * V.M * V.T.L;
     k_layer_solve<N><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V);
 }
-template <int N>
-static void launch_bvp_n(const ChunkView& V, cudaStream_t s) {
-    using C = BvpCfg<N, 1>;
-    const long long nprob = (long long)V.nw * V.M;
-    const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_bvp<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
-    k_bvp<N><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
-}
-template <int N, int NRHS>
-static void launch_adj_batch(const ChunkView& V, int los0, int nbatch, cudaStream_t s) {
-    using C = BvpCfg<N, NRHS>;
-    const long long ngroups = (long long)V.nw * V.M * nbatch;
-    const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_bvp_adjoint<N, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
-    k_bvp_adjoint<N, NRHS><<<(unsigned)((ngroups + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK),
-                             C::WARPS_PER_BLOCK * 32, smem, s>>>(V, los0, nbatch);
-}
-// Lines of sight are solved in batches of NRHS right-hand sides per factorisation of A^T (a partially filled
-// last batch carries zero columns): 4 when there are at most 4 lines of sight, else 10.
+// per-N entry points live in disco_bvp_inst.cu (compiled once per N)
+#define DISCO_DECL_BVP(N) void launch_bvp_n##N(const ChunkView&, cudaStream_t); void launch_bvp_adjoint_n##N(const ChunkView&, cudaStream_t);
+DISCO_DECL_BVP(1) DISCO_DECL_BVP(2) DISCO_DECL_BVP(4) DISCO_DECL_BVP(8) DISCO_DECL_BVP(16)
 static int adj_rhs_for(int nlos) { return nlos <= 4 ? 4 : 10; }
-template <int N>
-static void launch_bvp_adjoint_n(const ChunkView& V, cudaStream_t s) {
-    const int nlos = V.T.nlos;
-    const int nrhs = adj_rhs_for(nlos);
-    const int nbatch = (nlos + nrhs - 1) / nrhs;
-    if (nrhs == 4)
-        launch_adj_batch<N, 4>(V, 0, nbatch, s);
-    else
-        launch_adj_batch<N, 10>(V, 0, nbatch, s);
+#define DISCO_DECL_WF(N) void launch_wf_layer_n##N(const ChunkView&, cudaStream_t);
+DISCO_DECL_WF(1) DISCO_DECL_WF(2) DISCO_DECL_WF(4) DISCO_DECL_WF(8) DISCO_DECL_WF(16)
+
+__global__ void k_wf_chain(ChunkView V, int G) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)V.nw * V.T.nlos) return;
+    wf_chain_body(V, idx, G);
 }
+__global__ void k_wf_map(ChunkView V, MappingView Mp, int w0, int nw_total, int G) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)V.nw * V.T.nlos * Mp.nout) return;
+    wf_map_body(V, Mp, w0, nw_total, idx, G);
+}
+// surface (albedo) weighting function and log-radiance scaling
+__global__ void k_wf_surface(ChunkView V, const double* d_brdf, double* out, int w0, int G) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)V.nw * V.T.nlos) return;
+    const int nnative = V.T.nloc * (2 + G) + 1;
+    const int w = (int)(idx / V.T.nlos);
+    out[(size_t)w0 * V.T.nlos + idx] = V.wf_native[(size_t)idx * nnative + nnative - 1] * d_brdf[w0 + w];
+}
+__global__ void k_wf_log_scale(ChunkView V, double* out, int nout, int w0, int nw_total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)V.nw * V.T.nlos * nout) return;
+    const int o = (int)(idx % nout);
+    const long long wl = idx / nout;
+    const int los = (int)(wl % V.T.nlos), w = (int)(wl / V.T.nlos);
+    out[((size_t)o * nw_total + (w0 + w)) * V.T.nlos + los] /= V.radiance[(size_t)w * V.T.nlos + los];
+}
+
 
 #define DISCO_DISPATCH_N(fn, V, s)                 \
     switch (V.T.N) {                               \
@@ -576,8 +160,31 @@ double measure_fp64_tflops() {
 
 bool nstr_supported(int nstr) { return nstr == 2 || nstr == 4 || nstr == 8 || nstr == 16 || nstr == 32; }
 void launch_layer_solve(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_N(launch_layer_solve_n, V, s) }
-void launch_bvp(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_N(launch_bvp_n, V, s) }
-void launch_bvp_adjoint(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_N(launch_bvp_adjoint_n, V, s) }
+#define DISCO_DISPATCH_FN(prefix, V, s)            \
+    switch (V.T.N) {                               \
+        case 1: prefix##1(V, s); break;            \
+        case 2: prefix##2(V, s); break;            \
+        case 4: prefix##4(V, s); break;            \
+        case 8: prefix##8(V, s); break;            \
+        case 16: prefix##16(V, s); break;          \
+        default: break;                            \
+    }
+void launch_bvp(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_FN(launch_bvp_n, V, s) }
+void launch_bvp_adjoint(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_FN(launch_bvp_adjoint_n, V, s) }
+void launch_wf_layer(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_FN(launch_wf_layer_n, V, s) }
+void launch_wf_chain(const ChunkView& V, cudaStream_t s) {
+    const long long n = (long long)V.nw * V.T.nlos;
+    k_wf_chain<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(V, V.ngroups);
+}
+void launch_wf_map(const ChunkView& V, const MappingView& Mp, int w0, int nw_total, bool log_space, cudaStream_t s) {
+    const long long n = (long long)V.nw * V.T.nlos * Mp.nout;
+    k_wf_map<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V, Mp, w0, nw_total, V.ngroups);
+    if (log_space) k_wf_log_scale<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V, Mp.out, Mp.nout, w0, nw_total);
+}
+void launch_wf_surface(const ChunkView& V, const double* d_brdf, double* out, int w0, cudaStream_t s) {
+    const long long n = (long long)V.nw * V.T.nlos;
+    k_wf_surface<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V, d_brdf, out, w0, V.ngroups);
+}
 int adjoint_groups_per_problem(int nlos) { const int r = adj_rhs_for(nlos); return (nlos + r - 1) / r; }
 int adjoint_max_rhs(int nlos) { return adj_rhs_for(nlos); }
 void launch_radiance(const ChunkView& V, cudaStream_t s) {

@@ -36,9 +36,12 @@ class Engine:
         if not self._engine:
             raise _lib.SasktranError(f"sk_engine_create failed: {_lib.last_error()}")
         self._keepalive = None
+        self._staged_out = None
 
     def __del__(self):
         try:
+            if self._staged_out is not None:
+                _lib.lib().sk_output_destroy(self._staged_out[0])
             _lib.lib().sk_engine_destroy(self._engine)
         except Exception:
             pass
@@ -84,20 +87,23 @@ class Engine:
         return res
 
     # ---- device-resident extension (bench / pipelines that keep the atmosphere on the GPU) -----------
-    def stage(self, atmosphere, wavelength_start: int = 0, wavelength_count: int = -1) -> None:
+    def stage(self, atmosphere, wavelength_start: int = 0, wavelength_count: int = -1, radiance_buffer=None) -> None:
+        """Copy the atmosphere (and its derivative mappings when weighting functions are on) to the device."""
         self._keepalive = atmosphere
+        if self._staged_out is not None:
+            _lib.lib().sk_output_destroy(self._staged_out[0])
+        self._staged_out = self._make_output(atmosphere, radiance_buffer)
         _lib.check(_lib.lib().sk_b200_engine_stage_atmosphere(self._engine, atmosphere.internal_object(),
-                                                              wavelength_start, wavelength_count), "stage")
+                                                              self._staged_out[0], wavelength_start, wavelength_count),
+                   "stage")
 
     def solve_staged(self) -> None:
         _lib.check(_lib.lib().sk_b200_engine_solve_staged(self._engine), "solve_staged")
 
-    def fetch(self, atmosphere, radiance_buffer=None) -> Result:
-        out, res = self._make_output(atmosphere, radiance_buffer)
-        try:
-            _lib.check(_lib.lib().sk_b200_engine_fetch_output(self._engine, out), "fetch")
-        finally:
-            _lib.lib().sk_output_destroy(out)
+    def fetch(self, atmosphere=None, radiance_buffer=None) -> Result:
+        """Copy the results of the last staged solve into the output buffers created by stage()."""
+        out, res = self._staged_out
+        _lib.check(_lib.lib().sk_b200_engine_fetch_output(self._engine, out), "fetch")
         return res
 
     def timings_ms(self) -> dict:

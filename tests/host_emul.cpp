@@ -11,41 +11,29 @@
 #include <vector>
 
 #include "../sasktran2_b200/csrc/disco_bodies.h"
+#include "../sasktran2_b200/csrc/disco_bvp_rows.h"
+#include "../sasktran2_b200/csrc/disco_wf_body.h"
 #include "../sasktran2_b200/csrc/disco_plan.h"
 
 using namespace disco;
 
 static std::string g_err;
 
-template <int N>
-static void bvp_emul(const ChunkView& V, int w, int ms, unsigned* status) {
-    constexpr int NC = 2 * N, ROWS = 3 * N, ROWLEN = 4 * N + 1;
+// Lane-serial transcription of staircase_solve (sasktran2_b200/csrc/disco_bvp.cuh): same slots, ranks, pivot
+// search, pivot-row storage and back substitution, driven by the same row loaders as the CUDA kernels.
+template <int N, class Prob>
+static void staircase_emul(const Prob& prob, unsigned* status) {
+    constexpr int NRHS = Prob::NRHS;
+    constexpr int NC = 2 * N, ROWS = 3 * N, ROWLEN = 4 * N + NRHS;
     constexpr int GL = ROWS <= 4 ? 4 : (ROWS <= 8 ? 8 : (ROWS <= 16 ? 16 : 32));
     constexpr int R = (ROWS + GL - 1) / GL;
     constexpr int NSLOT = GL * R;
-    const int L = V.T.L, M = V.M;
-    const int m = V.m_list[ms];
-    const size_t lay0 = ((size_t)w * M + ms) * L;
-    const double* Wp = V.Wp + lay0 * N * N;
-    const double* Wm = V.Wm + lay0 * N * N;
-    const double* kth = V.kth + lay0 * 2 * N;
-    const double* G = V.G + lay0 * 4 * N;
-    double* fac = V.fac + lay0 * NC * ROWLEN;
-    double* xout = V.xsol + lay0 * NC;
+    const int nsteps = prob.nsteps();
     std::vector<double> a((size_t)NSLOT * ROWLEN, 0.0);
     std::vector<char> act(NSLOT, 0);
-    for (int sid = 0; sid < N; ++sid) {
-        act[sid] = 1;
-        for (int j = 0; j < N; ++j) {
-            a[sid * ROWLEN + j] = Wp[sid * N + j];
-            a[sid * ROWLEN + N + j] = Wm[sid * N + j] * kth[N + j];
-        }
-        a[sid * ROWLEN + 4 * N] = -G[sid];
-    }
-    std::vector<double> facs(NC * ROWLEN), xs(NC, 0.0);
-    for (int p = 0; p < L; ++p) {
-        const bool last = (p == L - 1);
-        const int needed = last ? N : NC;
+    std::vector<double> fac((size_t)nsteps * NC * ROWLEN, 0.0), facs(NC * ROWLEN), xs(NRHS * NC, 0.0);
+    for (int step = 0; step < nsteps; ++step) {
+        const int needed = prob.nnew(step);
         int rank = 0;
         std::vector<char> wasfree(NSLOT);
         for (int sid = 0; sid < NSLOT; ++sid) wasfree[sid] = !act[sid];
@@ -53,56 +41,12 @@ static void bvp_emul(const ChunkView& V, int w, int ms, unsigned* status) {
             if (!wasfree[sid]) continue;
             if (rank < needed) {
                 act[sid] = 1;
-                double* row = &a[sid * ROWLEN];
-                const double* Wpu = Wp + (size_t)p * N * N;
-                const double* Wmu = Wm + (size_t)p * N * N;
-                const double* thu = kth + (size_t)p * 2 * N + N;
-                const double* Gu = G + (size_t)p * 4 * N;
-                if (!last) {
-                    const double* Wpl = Wpu + N * N;
-                    const double* Wml = Wmu + N * N;
-                    const double* thl = thu + 2 * N;
-                    const double* Gl = Gu + 4 * N;
-                    const bool first = rank < N;
-                    const int i = first ? rank : rank - N;
-                    const double* A1 = first ? Wmu : Wpu;
-                    const double* A2 = first ? Wpu : Wmu;
-                    const double* B1 = first ? Wml : Wpl;
-                    const double* B2 = first ? Wpl : Wml;
-                    for (int j = 0; j < N; ++j) {
-                        row[j] = A1[i * N + j] * thu[j];
-                        row[N + j] = A2[i * N + j];
-                        row[2 * N + j] = -B1[i * N + j];
-                        row[3 * N + j] = -(B2[i * N + j] * thl[j]);
-                    }
-                    row[4 * N] = first ? (-Gu[3 * N + i] + Gl[N + i]) : (-Gu[2 * N + i] + Gl[i]);
-                } else {
-                    const int i = rank;
-                    const bool refl = (m == 0);
-                    const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
-                    const double* surf = V.surf + (size_t)w * (2 * N + 1);
-                    for (int j = 0; j < N; ++j) {
-                        double vm = Wmu[i * N + j], vp = Wpu[i * N + j];
-                        if (refl) {
-                            vm -= alb2 * surf[j];
-                            vp -= alb2 * surf[N + j];
-                        }
-                        row[j] = vm * thu[j];
-                        row[N + j] = vp;
-                        row[2 * N + j] = 0.0;
-                        row[3 * N + j] = 0.0;
-                    }
-                    double rhs = -Gu[3 * N + i];
-                    if (refl) {
-                        rhs += alb2 * surf[2 * N];
-                        rhs += V.T.csz * V.albedo[w] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
-                    }
-                    row[4 * N] = rhs;
-                }
+                prob.load(step, rank, &a[sid * ROWLEN]);
             }
             ++rank;
         }
-        for (int c = 0; c < NC; ++c) {
+        const int nleft = prob.nleft(step);
+        for (int c = 0; c < nleft; ++c) {
             double best = -1.0;
             int bsid = -1;
             for (int sid = 0; sid < NSLOT; ++sid)
@@ -124,35 +68,67 @@ static void bvp_emul(const ChunkView& V, int w, int ms, unsigned* status) {
                     a[sid * ROWLEN + c] = 0.0;
                 }
         }
-        std::copy(facs.begin(), facs.end(), fac + (size_t)p * NC * ROWLEN);
-        if (!last)
+        std::copy(facs.begin(), facs.begin() + nleft * ROWLEN, fac.begin() + (size_t)step * NC * ROWLEN);
+        if (step < nsteps - 1)
             for (int sid = 0; sid < NSLOT; ++sid)
                 for (int j = 0; j < NC; ++j) {
                     a[sid * ROWLEN + j] = a[sid * ROWLEN + NC + j];
                     a[sid * ROWLEN + NC + j] = 0.0;
                 }
     }
-    for (int p = L - 1; p >= 0; --p) {
-        const double* f = fac + (size_t)p * NC * ROWLEN;
-        std::vector<double> acc(NC), x(NC);
-        for (int c = 0; c < NC; ++c) {
-            acc[c] = f[c * ROWLEN + 4 * N];
-            if (p < L - 1)
-                for (int j = 0; j < NC; ++j) acc[c] -= f[c * ROWLEN + NC + j] * xs[j];
-        }
-        for (int cc = NC - 1; cc >= 0; --cc) {
-            x[cc] = acc[cc] / f[cc * ROWLEN + cc];
-            for (int c = 0; c < cc; ++c) acc[c] -= f[c * ROWLEN + cc] * x[cc];
-        }
-        for (int c = 0; c < NC; ++c) {
-            xs[c] = x[c];
-            xout[(size_t)p * NC + c] = x[c];
+    for (int step = nsteps - 1; step >= 0; --step) {
+        const int nleft = prob.nleft(step), nright = prob.nright(step);
+        const double* f = &fac[(size_t)step * NC * ROWLEN];
+        for (int r = 0; r < NRHS; ++r) {
+            std::vector<double> acc(NC, 0.0), x(NC, 0.0);
+            for (int c = 0; c < nleft; ++c) {
+                acc[c] = f[c * ROWLEN + 4 * N + r];
+                for (int j = 0; j < nright; ++j) acc[c] -= f[c * ROWLEN + NC + j] * xs[r * NC + j];
+            }
+            for (int cc = nleft - 1; cc >= 0; --cc) {
+                x[cc] = acc[cc] * (1.0 / f[cc * ROWLEN + cc]);
+                for (int c = 0; c < cc; ++c) acc[c] -= f[c * ROWLEN + cc] * x[cc];
+            }
+            for (int c = 0; c < nleft; ++c) {
+                xs[r * NC + c] = x[c];
+                prob.store(step, c, r, x[c]);
+            }
         }
     }
 }
 
 template <int N>
-static void run_all(ChunkView& V, unsigned* status) {
+static void bvp_emul(const ChunkView& V, int w, int ms, unsigned* status) {
+    ForwardRows<N> rows(V, w, ms);
+    staircase_emul<N>(rows, status);
+}
+
+template <int N>
+static void bvp_adjoint_emul(const ChunkView& V, int w, int ms, unsigned* status) {
+    const int nlos = V.T.nlos;
+    if (nlos <= 4) {
+        for (int los0 = 0; los0 < nlos; los0 += 4) {
+            AdjointRows<N, 4> rows(V, w, ms, los0);
+            staircase_emul<N>(rows, status);
+        }
+    } else {
+        for (int los0 = 0; los0 < nlos; los0 += 10) {
+            AdjointRows<N, 10> rows(V, w, ms, los0);
+            staircase_emul<N>(rows, status);
+        }
+    }
+}
+
+template <int N, int G>
+static void run_wf(ChunkView& V, unsigned* status) {
+    for (int w = 0; w < V.nw; ++w)
+        for (int ms = 0; ms < V.M; ++ms) bvp_adjoint_emul<N>(V, w, ms, status);
+    for (long long i = 0; i < (long long)V.nw * V.M * V.T.L; ++i) wf_layer_body<N, G>(V, i);
+    for (long long i = 0; i < (long long)V.nw * V.T.nlos; ++i) wf_chain_body(V, i, G);
+}
+
+template <int N>
+static void run_all(ChunkView& V, unsigned* status, bool wf) {
     const int L = V.T.L;
     for (long long i = 0; i < (long long)V.nw * L; ++i) optics_body(V, i);
     for (int w = 0; w < V.nw; ++w) beam_body(V, w);
@@ -160,6 +136,14 @@ static void run_all(ChunkView& V, unsigned* status) {
     for (int w = 0; w < V.nw; ++w)
         for (int ms = 0; ms < V.M; ++ms) bvp_emul<N>(V, w, ms, status);
     for (long long i = 0; i < (long long)V.nw * V.T.nlos; ++i) radiance_body(V, i);
+    if (wf) {
+        switch (V.ngroups) {
+            case 0: run_wf<N, 0>(V, status); break;
+            case 1: run_wf<N, 1>(V, status); break;
+            case 2: run_wf<N, 2>(V, status); break;
+            default: throw std::runtime_error("unsupported number of scattering groups");
+        }
+    }
 }
 
 extern "C" const char* emul_last_error() { return g_err.c_str(); }
@@ -168,7 +152,7 @@ extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nl
                                 int geotype, double cos_sza, double earth_radius, const double* los_cos_vza,
                                 const double* los_rel_az, const double* ssa, const double* ext, const double* leg,
                                 const double* solar, const double* albedo, int include_ss, double* radiance,
-                                int* num_azimuth_solved) {
+                                int* num_azimuth_solved, const double* d_leg, int ngroups, double* native) {
     try {
         GeometrySpec geo;
         geo.altitudes.assign(alt, alt + nloc);
@@ -206,14 +190,28 @@ extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nl
         V.G = A(c * M * L * 4 * N); V.surf = A(c * (2 * N + 1)); V.wvec = A(c * M * nlos * L * 2 * N);
         V.vsrc = A(c * M * nlos * L); V.xsol = A(c * M * L * 2 * N); V.fac = A(c * M * L * 2 * N * (4 * N + 1));
         V.radiance = radiance;
+        const bool wf = native != nullptr;
+        const size_t G = wf ? ngroups : 0;
+        V.ngroups = (int)G;
+        V.dleg = d_leg;
+        V.dleg_gstride = (size_t)nleg * nloc * nwavel;
+        if (wf) {
+            V.zadj = A(c * M * nlos * 2 * N * L);
+            V.lay_dbeta = A(c * L * (G ? G : 1) * nstr);
+            V.wf_loc = A(c * M * nlos * L * (G + 4));
+            V.wf_src = A(c * M * nlos * L);
+            V.wf_gnd = A(c * nlos * 3);
+            V.wf_scratch = A(c * nlos * 3 * (L + 1));
+            V.wf_native = native;
+        }
         unsigned status = 0;
         V.status = &status;
         switch (N) {
-            case 1: run_all<1>(V, &status); break;
-            case 2: run_all<2>(V, &status); break;
-            case 4: run_all<4>(V, &status); break;
-            case 8: run_all<8>(V, &status); break;
-            case 16: run_all<16>(V, &status); break;
+            case 1: run_all<1>(V, &status, wf); break;
+            case 2: run_all<2>(V, &status, wf); break;
+            case 4: run_all<4>(V, &status, wf); break;
+            case 8: run_all<8>(V, &status, wf); break;
+            case 16: run_all<16>(V, &status, wf); break;
             default: throw std::runtime_error("unsupported nstr");
         }
         if (status) {

@@ -151,3 +151,85 @@ def test_cuda_staged_api_matches_full_call():
     t = eng.timings_ms()
     assert t["kernels_total"] > 0 and eng.kernel_launches() >= 5
     np.testing.assert_array_equal(eng.fetch(atm)["radiance"], base)
+
+
+RTOL_WF = 1e-7
+
+
+def _oracle_wf(oracle_mod, sc):
+    names = sorted(n for n, mp in sc.mappings.items() if "d_legendre" in mp)
+    d_leg = None
+    if names:
+        d_leg = np.stack([sc.mappings[n]["d_legendre"] for n in names], axis=-1)
+    ora = oracle_mod.do_radiance(nstr=sc.nstr, alt=sc.altitudes, interp=sc.interp, geotype=sc.geotype, cos_sza=sc.cos_sza,
+                                 earth_radius=sc.earth_radius, los_cos_vza=sc.los_cos_vza, los_rel_az=sc.los_rel_az,
+                                 ssa=sc.ssa, ext=sc.total_extinction, leg=sc.leg_coeff, albedo=sc.albedo, d_leg=d_leg,
+                                 calc_derivs=True)
+    maps = {}
+    for n, mp in sc.mappings.items():
+        maps[n] = dict(d_ssa=mp["d_ssa"], d_extinction=mp["d_extinction"], scat_factor=mp.get("scat_factor"),
+                       scat_index=names.index(n) if n in names else -1, interpolator=mp.get("interpolator"))
+    wf = oracle_mod.apply_mappings(ora["native"], maps, sc.nloc, len(names))
+    return ora, wf
+
+
+@pytest.mark.parametrize("nstr,interp,geotype,nlos,nlayers", [(4, 2, 0, 2, 9), (8, 1, 1, 3, 12), (16, 1, 1, 6, 25),
+                                                             (2, 1, 1, 2, 9), (32, 1, 1, 2, 6)])
+def test_cuda_weighting_functions_vs_oracle(oracle_mod, nstr, interp, geotype, nlos, nlayers):
+    import sasktran2_b200 as sk
+    from sasktran2_b200 import scenarios
+
+    sc = scenarios.small_wf_case(nstr=nstr, nlayers=nlayers, nwavel=5, nlos=nlos, interp=interp, geotype=geotype)
+    # an interpolated mapping (coarser output grid) on top of the three native-grid ones
+    interp_mat = np.zeros((sc.nloc, 3))
+    for q in range(sc.nloc):
+        interp_mat[q, min(q * 3 // sc.nloc, 2)] = 1.0 + 0.1 * q
+    sc.mappings["wf_o3_coarse"] = dict(sc.mappings["wf_o3_vmr"], interpolator=interp_mat)
+    _, _, _, eng, atm = sk.engine_for_scenario(sc)
+    atm.surface.enable_albedo_derivative("wf_albedo")
+    res = eng.calculate_radiance(atm)
+    ora, wf = _oracle_wf(oracle_mod, sc)
+    np.testing.assert_allclose(res["radiance"][:, :, 0], ora["radiance"], rtol=RTOL_RADIANCE)
+    for name, ref in wf.items():
+        got = res[name][..., 0]
+        assert got.shape == ref.shape
+        scale = np.abs(ref).max(axis=0, keepdims=True)
+        assert np.max(np.abs(got - ref) / scale) < RTOL_WF, name
+    np.testing.assert_allclose(res["wf_albedo"][:, :, 0], ora["native"][:, :, -1], rtol=RTOL_WF)
+
+
+def test_cuda_weighting_functions_chunked_and_staged():
+    import sasktran2_b200 as sk
+    from sasktran2_b200 import scenarios
+
+    sc = scenarios.small_wf_case(nstr=8, nlayers=14, nwavel=11, nlos=5)
+    _, _, _, eng, atm = sk.engine_for_scenario(sc)
+    base = eng.calculate_radiance(atm)
+    eng.set_workspace_gb(eng.info()["workspace_mb_per_wavelength"] * 3 / 1024.0)
+    again = eng.calculate_radiance(atm)
+    for k in base:
+        np.testing.assert_array_equal(base[k], again[k])
+    eng.stage(atm)
+    assert eng.info()["chunk_wavelengths"] == 3
+    eng.solve_staged()
+    staged = eng.fetch()
+    for k in base:
+        np.testing.assert_array_equal(base[k], staged[k])
+    assert eng.timings_ms()["wf"] > 0
+
+
+def test_cuda_weighting_functions_config5_shape(oracle_mod):
+    """BASELINE configs[4] shape (16 streams, 100 layers, 10 LOS, O3 / NO2 / aerosol mappings) on a 3-wavelength
+    sample against the oracle's dense forward-mode derivatives."""
+    import sasktran2_b200 as sk
+    from sasktran2_b200 import scenarios
+
+    full = scenarios.config2(nwavel=3, with_wf=True)
+    _, _, _, eng, atm = sk.engine_for_scenario(full)
+    res = eng.calculate_radiance(atm)
+    ora, wf = _oracle_wf(oracle_mod, full)
+    np.testing.assert_allclose(res["radiance"][:, :, 0], ora["radiance"], rtol=RTOL_RADIANCE)
+    for name, ref in wf.items():
+        got = res[name][..., 0]
+        scale = np.abs(ref).max(axis=0, keepdims=True)
+        assert np.max(np.abs(got - ref) / scale) < RTOL_WF, name

@@ -17,7 +17,8 @@ ROOT = Path(__file__).resolve().parent.parent
 def emul():
     so = ROOT / "tests" / "libhost_emul.so"
     srcs = [ROOT / "tests" / "host_emul.cpp", ROOT / "sasktran2_b200" / "csrc" / "disco_plan.cpp",
-            ROOT / "sasktran2_b200" / "csrc" / "disco_core.h", ROOT / "sasktran2_b200" / "csrc" / "disco_bodies.h"]
+            ROOT / "sasktran2_b200" / "csrc" / "disco_core.h", ROOT / "sasktran2_b200" / "csrc" / "disco_bodies.h",
+            ROOT / "sasktran2_b200" / "csrc" / "disco_bvp_rows.h", ROOT / "sasktran2_b200" / "csrc" / "disco_wf_body.h"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(srcs[0]), str(srcs[1])],
                        check=True)
@@ -28,7 +29,7 @@ def emul():
         return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
     def run(nstr, alt, interp, geotype, cos_sza, los_cos_vza, los_rel_az, ssa, ext, leg, albedo,
-            earth_radius=6372000.0, include_ss=True, solar=None, **_):
+            earth_radius=6372000.0, include_ss=True, solar=None, d_leg=None, want_native=False, **_):
         alt = np.ascontiguousarray(alt, float)
         ssa = np.asfortranarray(ssa, float)
         ext = np.asfortranarray(ext, float)
@@ -40,11 +41,20 @@ def emul():
         alb = np.ascontiguousarray(np.broadcast_to(albedo, (nw,)), float)
         rad = np.zeros((nw, cz.size))
         naz = ctypes.c_int(0)
+        G = 0
+        dl = None
+        if d_leg is not None:
+            dl = np.asfortranarray(d_leg, float)  # [nleg, nloc, nw, G]
+            G = dl.shape[3]
+        native = np.zeros((nw, cz.size, nloc * (2 + G) + 1)) if want_native else None
         rc = lib.emul_do_radiance(nstr, nloc, nw, nleg, cz.size, P(alt), interp, geotype, ctypes.c_double(cos_sza),
                                   ctypes.c_double(earth_radius), P(cz), P(az), P(ssa), P(ext), P(leg), P(solar), P(alb),
-                                  int(include_ss), P(rad), ctypes.byref(naz))
+                                  int(include_ss), P(rad), ctypes.byref(naz), P(dl) if dl is not None else None, G,
+                                  P(native) if native is not None else None)
         if rc:
             raise RuntimeError(lib.emul_last_error().decode())
+        if want_native:
+            return rad, naz.value, native
         return rad, naz.value
 
     return run
@@ -79,3 +89,25 @@ def test_kernel_bodies_pseudo_spherical_and_nadir_skip(emul, oracle_mod):
     rad, naz = emul(**inp)
     assert naz == 1  # exactly-nadir LOS: azimuth orders m > 0 contribute exactly zero and are skipped
     np.testing.assert_allclose(rad, oracle_mod.do_radiance(**inp)["radiance"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("nstr,interp,geotype,nlos", [(4, 2, 0, 2), (8, 1, 1, 3), (8, 1, 1, 6), (16, 1, 1, 2), (2, 1, 1, 2)])
+def test_kernel_bodies_weighting_functions_match_oracle(emul, oracle_mod, nstr, interp, geotype, nlos):
+    """Reverse-mode (adjoint BVP + layer-local duals + cross-layer chain) native derivatives of the product's
+    kernel bodies vs the oracle's forward-mode duals.  Tolerance: 1e-7 relative to the largest derivative of
+    each kind (BASELINE.json north_star: 1e-7 on weighting functions)."""
+    from sasktran2_b200 import scenarios
+
+    sc = scenarios.small_wf_case(nstr=nstr, nlayers=9, nwavel=2, nlos=nlos, interp=interp, geotype=geotype)
+    d_leg = sc.mappings["wf_aerosol_extinction"]["d_legendre"][..., None]
+    inp = dict(nstr=sc.nstr, alt=sc.altitudes, interp=sc.interp, geotype=sc.geotype, cos_sza=sc.cos_sza,
+               los_cos_vza=sc.los_cos_vza, los_rel_az=sc.los_rel_az, ssa=sc.ssa, ext=sc.total_extinction,
+               leg=sc.leg_coeff, albedo=sc.albedo)
+    rad, _, native = emul(**inp, d_leg=d_leg, want_native=True)
+    ora = oracle_mod.do_radiance(**inp, d_leg=d_leg, calc_derivs=True)
+    np.testing.assert_allclose(rad, ora["radiance"], rtol=1e-10)
+    nloc = sc.nloc
+    for lo, hi in ((0, nloc), (nloc, 2 * nloc), (2 * nloc, 3 * nloc), (3 * nloc, 3 * nloc + 1)):
+        a, b = native[..., lo:hi], ora["native"][..., lo:hi]
+        scale = np.abs(b).max(axis=-1, keepdims=True)
+        assert np.max(np.abs(a - b) / scale) < 1e-7, (lo, np.max(np.abs(a - b) / scale))

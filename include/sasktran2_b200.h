@@ -195,6 +195,8 @@ int sk_b200_engine_info(Engine* engine, int* num_azimuth, int* chunk_wavelengths
 int sk_b200_engine_set_workspace_gb(Engine* engine, double gb);
 /* DFMA micro-benchmark on the current device: the FP64 roofline denominator (TFLOP/s) */
 double sk_b200_measure_fp64_tflops();
+/* test/debug: copy a named workspace array of the last solved chunk (names: see disco_engine.cu) */
+long long sk_b200_engine_debug_copy(Engine* engine, const char* name, double* host, long long max_n);
 
 #ifdef __cplusplus
 }

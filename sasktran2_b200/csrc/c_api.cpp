@@ -857,6 +857,10 @@ int sk_b200_engine_info(Engine* e, int* num_azimuth, int* chunk_wavelengths, dou
     if (workspace_mb_per_wavelength) *workspace_mb_per_wavelength = e->dev->workspace_bytes_per_wavelength() / 1048576.0;
     return 0;
 }
+long long sk_b200_engine_debug_copy(Engine* e, const char* name, double* host, long long max_n) {
+    if (!e || !e->dev || !name || !host) return -1;
+    return (long long)e->dev->debug_copy(name, host, (size_t)max_n);
+}
 double sk_b200_measure_fp64_tflops() { return disco::measure_fp64_tflops(); }
 int sk_b200_engine_set_workspace_gb(Engine* e, double gb) {
     if (!e || !e->dev) return -1;

@@ -145,9 +145,11 @@ void DeviceEngine::ensure_workspace(int chunk) {
     free_workspace();
     const size_t N = m_plan.N, L = m_plan.L, nstr = m_plan.nstr, nlos = m_plan.nlos, M = m_mlist.size();
     const size_t c = chunk;
+    m_dbg.clear();
     auto A = [&](size_t n) {
         double* p = dalloc<double>(n);
         m_ws_ptrs.push_back(p);
+        m_dbg.push_back({"", {p, n}});
         return p;
     };
     ChunkView& V = m_view;
@@ -185,6 +187,14 @@ void DeviceEngine::ensure_workspace(int chunk) {
         V.wf_scratch = A(c * nlos * 3 * (L + 1));
     }
     m_ws_wf = m_wf_on;
+    {
+        static const char* base[] = {"lay_od", "lay_ssa", "lay_beta", "lay_secant", "lay_trans", "lay_cumod", "lay_totext",
+                                     "lay_scatext", "Wp", "Wm", "kth", "G", "surf", "wvec", "vsrc", "xsol", "fac"};
+        static const char* wfn[] = {"zadj", "lay_dbeta", "wf_loc", "wf_src", "wf_gnd", "wf_native", "wf_scratch"};
+        size_t i = 0;
+        for (; i < 17 && i < m_dbg.size(); ++i) m_dbg[i].first = base[i];
+        for (size_t j = 0; i < m_dbg.size() && j < 7; ++i, ++j) m_dbg[i].first = wfn[j];
+    }
     m_ws_chunk = chunk;
 }
 
@@ -400,4 +410,16 @@ void DeviceEngine::calculate(const AtmosphereArrays& atm, int w0, int nw, double
     fetch(radiance_host);
 }
 
+}  // namespace disco
+
+namespace disco {
+size_t DeviceEngine::debug_copy(const char* name, double* host, size_t max_n) {
+    for (auto& e : m_dbg)
+        if (e.first == name) {
+            const size_t n = std::min(max_n, e.second.second);
+            cudaMemcpy(host, e.second.first, n * sizeof(double), cudaMemcpyDeviceToHost);
+            return n;
+        }
+    return 0;
+}
 }  // namespace disco

@@ -70,6 +70,9 @@ class DeviceEngine {
     // stage + solve + fetch
     void calculate(const AtmosphereArrays& atm, int w0, int nw, double* radiance_host, const WfRequest* wf = nullptr);
     bool wf_active() const { return m_wf_on; }
+    // test/debug: copy a workspace array of the LAST chunk to the host; returns the number of doubles copied
+    size_t debug_copy(const char* name, double* host, size_t max_n);
+    std::vector<std::pair<std::string, std::pair<double*, size_t>>> m_dbg;
 
     const double* timings_ms() const { return m_ms; }   // accumulated over the last solve / calculate
     long long kernel_launches() const { return m_launches; }

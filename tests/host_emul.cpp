@@ -18,6 +18,7 @@
 using namespace disco;
 
 static std::string g_err;
+static std::vector<std::pair<std::string, std::vector<double>>> g_dump;
 
 // Lane-serial transcription of staircase_solve (sasktran2_b200/csrc/disco_bvp.cuh): same slots, ranks, pivot
 // search, pivot-row storage and back substitution, driven by the same row loaders as the CUDA kernels.
@@ -147,6 +148,15 @@ static void run_all(ChunkView& V, unsigned* status, bool wf) {
 }
 
 extern "C" const char* emul_last_error() { return g_err.c_str(); }
+extern "C" long long emul_dump(const char* name, double* out, long long max_n) {
+    for (auto& e : g_dump)
+        if (e.first == name) {
+            long long n = std::min<long long>(max_n, (long long)e.second.size());
+            std::copy(e.second.begin(), e.second.begin() + n, out);
+            return n;
+        }
+    return 0;
+}
 
 extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nlos, const double* alt, int interp,
                                 int geotype, double cos_sza, double earth_radius, const double* los_cos_vza,
@@ -213,6 +223,19 @@ extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nl
             case 8: run_all<8>(V, &status, wf); break;
             case 16: run_all<16>(V, &status, wf); break;
             default: throw std::runtime_error("unsupported nstr");
+        }
+        {
+            g_dump.clear();
+            auto D = [&](const char* nm, const double* p, size_t n) { if (p) g_dump.push_back({nm, std::vector<double>(p, p + n)}); };
+            D("lay_od", V.lay_od, c * L); D("lay_secant", V.lay_secant, c * L); D("lay_trans", V.lay_trans, c * (L + 1));
+            D("lay_beta", V.lay_beta, c * L * nstr); D("kth", V.kth, c * M * L * 2 * N); D("Wp", V.Wp, c * M * L * N * N);
+            D("G", V.G, c * M * L * 4 * N); D("wvec", V.wvec, c * M * nlos * L * 2 * N); D("vsrc", V.vsrc, c * M * nlos * L);
+            D("xsol", V.xsol, c * M * L * 2 * N);
+            if (wf) {
+                D("zadj", V.zadj, c * M * nlos * 2 * N * L); D("lay_dbeta", V.lay_dbeta, c * L * G * nstr);
+                D("wf_loc", V.wf_loc, c * M * nlos * L * (G + 4)); D("wf_src", V.wf_src, c * M * nlos * L);
+                D("wf_gnd", V.wf_gnd, c * nlos * 3);
+            }
         }
         if (status) {
             g_err = "status bits " + std::to_string(status);

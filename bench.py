@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=8.0)
+    ap.add_argument("--wf", type=int, default=1, help="1: with weighting functions (O3, NO2, aerosol mappings + albedo), 0: radiances only")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -215,17 +216,20 @@ def main():
     from sasktran2_b200.parallel import wavelength_block
 
     start, count = wavelength_block(nw_total, rank, world)
-    sc = scenarios.config2(nwavel=nw_total, nlayers=args.layers, nstr=args.nstr, nlos=args.nlos) if world == 1 else None
+    with_wf = bool(args.wf)
+    sc = scenarios.config2(nwavel=nw_total, nlayers=args.layers, nstr=args.nstr, nlos=args.nlos, with_wf=with_wf) if world == 1 else None
     if sc is None:
         # build only this rank's block (same formulae; block boundaries chosen by wavelength_block)
         full_axis = scenarios.config2  # noqa: F841
-        sc_full = scenarios.config2(nwavel=nw_total, nlayers=args.layers, nstr=args.nstr, nlos=args.nlos)
+        sc_full = scenarios.config2(nwavel=nw_total, nlayers=args.layers, nstr=args.nstr, nlos=args.nlos, with_wf=with_wf)
         from sasktran2_b200.parallel import shard_scenario
 
         sc, start, count = shard_scenario(sc_full, rank, world)
         del sc_full
     sk._lib.check(sk._lib.lib().sk_b200_set_device(local_rank), "set_device")
     _, geo, view, eng, atm = sk.engine_for_scenario(sc)
+    if with_wf:
+        atm.surface.enable_albedo_derivative("wf_albedo")
     eng.set_workspace_gb(args.workspace_gb)
     nloc, nleg, nlos, nw = sc.nloc, sc.leg_coeff.shape[0], sc.nlos, sc.nwavel
 
@@ -241,6 +245,13 @@ def main():
     h2d_bytes = sum(a.nbytes for a in (atm.storage.ssa, atm.storage.total_extinction, atm.storage.leg_coeff,
                                        atm.storage.solar_irradiance, atm.surface.albedo))
     d2h_bytes = rad_buf.nbytes
+    nwf_out = 0
+    if with_wf:
+        for mp in sc.mappings.values():
+            h2d_bytes += sum(v.nbytes for v in mp.values() if isinstance(v, np.ndarray))
+            nwf_out += sc.nloc
+        nwf_out += 1
+        d2h_bytes += 8 * nwf_out * nw * nlos
 
     # ---- device-resident timing (value)
     eng.stage(atm, radiance_buffer=rad_buf)
@@ -259,7 +270,7 @@ def main():
         eng.solve_staged()
         t = eng.timings_ms()
         dev_ms += t["kernels_total"]
-        for k in ("optics", "layer", "bvp", "radiance", "wf"):
+        for k in ("optics", "layer", "bvp", "radiance", "wf"):  # wf = adjoint BVP + layer derivatives + chain + mapping
             per_kernel[k] = per_kernel.get(k, 0.0) + t.get(k, 0.0)
         launches += eng.kernel_launches()
     barrier()
@@ -315,7 +326,7 @@ def main():
         "peak_source": "DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP64 figure)",
         "share_of_step": per_kernel[dom] / max(sum(per_kernel.values()), 1e-12),
         "whole_step": {"flops_per_wavelength": fm["total"], "achieved_tflops": fm["total"] * nw / (ms_per_step * 1e-3) / 1e12 if world == 1 else fm["total"] * nw_total / world / (ms_per_step * 1e-3) / 1e12},
-        "hbm_view": {"bound": "hbm", "achieved": bytes_model(nloc, nleg, nlos) * (nw_total / world) / (ms_per_step * 1e-3) / 1e9,
+        "hbm_view": {"bound": "hbm", "achieved": bytes_model(nloc, nleg, nlos, nwf_out) * (nw_total / world) / (ms_per_step * 1e-3) / 1e9,
                      "peak": hbm_peak, "unit": "GB/s",
                      "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
     }
@@ -327,7 +338,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1] shape: pseudo-spherical DO, {args.nstr} streams, {args.layers} layers, "
                                f"Rayleigh+aerosol+O3/NO2, {nlos} ground-viewing LOS, {args.nwavel} wavelengths per GPU, "
-                               f"radiances only (weighting functions not in this line)",
+                               + ("weighting functions w.r.t. O3 VMR, NO2 VMR, aerosol extinction (3 x 101 outputs) and albedo"
+                                  if with_wf else "radiances only"),
                    "wavelengths_per_gpu": args.nwavel, "azimuth_orders": len(m_list), "chunk_wavelengths": chunk,
                    "l2": "inputs+workspace per step far exceed the 126 MB L2 (no flush needed)",
                    "wall_ms_per_step": wall_ms / args.steps},

@@ -187,7 +187,8 @@ int sk_b200_engine_stage_atmosphere(Engine* engine, Atmosphere* atmosphere, Outp
 int sk_b200_engine_solve_staged(Engine* engine);
 /* Copy the staged range's results into the output buffers (same offsets as the full-spectrum call). */
 int sk_b200_engine_fetch_output(Engine* engine, OutputC* output);
-/* ms of the last staged solve / full call: [h2d, optics, layer, bvp, radiance, d2h, kernels_total, wf] */
+/* ms of the last staged solve / full call: [h2d, optics, layer, bvp, radiance, d2h, kernels_total, wf,
+   wf_adjoint, wf_layer, wf_chain, wf_map] (wf = sum of the last four) */
 int sk_b200_engine_get_timings(Engine* engine, double* out_ms, int n);
 long long sk_b200_engine_kernel_launches(Engine* engine);
 /* number of azimuth orders solved and wavelengths per workspace chunk (diagnostics) */

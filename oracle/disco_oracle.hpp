@@ -100,6 +100,47 @@ inline double val(const Dual& x) { return x.v; }
 inline double exp(double x) { return std::exp(x); }
 inline double sqrt(double x) { return std::sqrt(x); }
 
+// ---- "stable multipliers" variant (NOT the reference's formulas; off by default) -------------------------
+// The reference evaluates the particular-solution multipliers C+ (sktran_do_rte.cpp:1203-1226), D- and h-
+// (sktran_do_opticallayer.cpp:339-344, 897-938) as differences of exponentials divided by (secant - k) or
+// (1 - mu k); within ~1e-3 of those degeneracies the values lose digits and the derivatives w.r.t. the secant
+// lose twice as many, which the layer -> optical-depth chain then divides by the layer optical depth.  With
+//   phi(x) = (1 - exp(-x)) / x,   psi(a; k1, k2) = (e^{-a k1} - e^{-a k2}) / (a (k2 - k1)) = e^{-a min} phi(a |k2 - k1|)
+// the same quantities are  C+ = t a psi(a; k, s),  h- = (a/mu) psi(a; k, 1/mu),
+// D- = t (mu h+ - a e^{-a/mu} psi(a; k, s)) / (1 + mu s), without a removable singularity.  Where the reference
+// switches to its own Taylor branches (|secant - k| <= 1e-4, |1 - mu k| <= 1e-4) those are kept verbatim, so the
+// two variants differ only by the rounding noise of the reference's direct formulas.  Used by the tests to tell
+// the CUDA path's accuracy apart from that noise.
+inline int& stable_multipliers_ref() {
+    static int flag = 0;
+    return flag;
+}
+inline double phi_value(double x) { return x == 0.0 ? 1.0 : -std::expm1(-x) / x; }
+inline double phi_deriv(double x) {
+    if (std::abs(x) > 0.01) return (std::exp(-x) - phi_value(x)) / x;
+    // phi'(x) = sum_n (-1)^(n+1) (n+1) x^n / (n+2)!
+    double term = -0.5, sum = -0.5;
+    for (int n = 1; n < 9; ++n) {
+        term *= -x * (n + 1.0) / (n * (n + 2.0));
+        sum += term;
+    }
+    return sum;
+}
+inline double phi(double x) { return phi_value(x); }
+inline Dual phi(const Dual& x) {
+    Dual r;
+    r.v = phi_value(x.v);
+    const double dp = phi_deriv(x.v);
+    for (size_t i = 0; i < x.d.size(); ++i) r.d[i] = dp * x.d[i];
+    return r;
+}
+// psi(a; k1, k2) with e1 = exp(-a k1), e2 = exp(-a k2) supplied by the caller
+template <class T>
+inline T psi(const T& a, const T& k1, const T& k2, const T& e1, const T& e2) {
+    if (val(k2) >= val(k1)) return e1 * phi(a * (k2 - k1));
+    return e2 * phi(a * (k1 - k2));
+}
+
 // ---------------------------------------------------------------------------------------------------
 //  Geometry-only plan
 // ---------------------------------------------------------------------------------------------------
@@ -703,7 +744,8 @@ struct Solver {
             T exp_k = exp(-od * S.k[j]);
             T Cp, Cm;
             if (std::abs(val(secant) - val(S.k[j])) > GREENS_EPS)
-                Cp = trans_top * (exp_k - exp_sec) / (secant - S.k[j]);
+                Cp = stable_multipliers_ref() ? trans_top * od * psi(od, S.k[j], secant, exp_k, exp_sec)
+                                              : trans_top * (exp_k - exp_sec) / (secant - S.k[j]);
             else
                 Cp = trans_top * exp_k * od * (T(1.0) - od / T(2.0) * (secant - S.k[j]));
             if (std::abs(val(secant) + val(S.k[j])) > GREENS_EPS)
@@ -922,7 +964,9 @@ struct Solver {
                 }
                 {
                     T den = T(1.0) - T(mu) * k;
-                    if (std::abs(val(den)) > 0.0001) {
+                    if (std::abs(val(den)) > 0.0001 && stable_multipliers_ref()) {
+                        hm = od / T(mu) * psi(od, k, T(1.0 / mu), exp(-k * od), exp(-od / T(mu)));
+                    } else if (std::abs(val(den)) > 0.0001) {
                         T e1 = exp(-k * od);
                         T e2 = exp(-od / T(mu));
                         hm = (e1 - e2) / den;
@@ -934,7 +978,10 @@ struct Solver {
                 J += Yp * hp * S.Lc[i];
                 J += Ym * hm * S.Mc[i];
                 T Dp = (-t * expfactor * hm + E) / (s + k);
-                T Dm = (t * hp - E) / (s - k);
+                T Dm = stable_multipliers_ref()
+                           ? t * (T(mu) * hp - od * exp(-od / T(mu)) * psi(od, k, s, exp(-k * od), expfactor)) /
+                                 (T(1.0) + T(mu) * s)
+                           : (t * hp - E) / (s - k);
                 V += S.Ap[i] * Yp * Dm + S.Am[i] * Ym * Dp;
             }
             I += J + V + Q * E;

@@ -13,6 +13,9 @@ extern "C" {
 
 const char* oracle_last_error() { return g_last_err.c_str(); }
 
+// 0: the reference's multiplier formulas (default); 1: removable singularities evaluated with phi/psi
+void oracle_set_stable_multipliers(int on) { oracle::stable_multipliers_ref() = on; }
+
 int oracle_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -63,12 +63,14 @@ def _p(a):
 
 def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az,
                 ssa, ext, leg, solar=None, albedo, d_leg=None, include_ss=True, num_azimuth=0,
-                calc_derivs=False, nthreads=0, return_lanes=False):
+                calc_derivs=False, nthreads=0, return_lanes=False, stable=False):
     """Run the oracle.
 
     ssa, ext: [nloc, nwavel] (Fortran order is used internally, as the reference does);
     leg: [nleg, nloc, nwavel]; d_leg: [nleg, nloc, nwavel, ngroups] or None; albedo: [nwavel].
     Returns dict(radiance [nwavel, nlos], native [nwavel, nlos, nloc*(2+G)+1] if calc_derivs).
+    stable=True switches the particular-solution multipliers from the reference's formulas to the
+    singularity-free phi/psi forms (see disco_oracle.hpp, "stable multipliers"); default is the reference's.
     """
     L = lib()
     alt = np.ascontiguousarray(alt, dtype=np.float64)
@@ -96,6 +98,7 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
         native = np.zeros((nwavel, nlos, nloc * (2 + G) + 1))
         if return_lanes:
             lanes = np.zeros((nwavel, nlos, nl * (G + 2) + 1))
+    L.oracle_set_stable_multipliers(ctypes.c_int(int(stable)))
     rc = L.oracle_do_radiance(
         ctypes.c_int(nstr), ctypes.c_int(nloc), ctypes.c_int(nwavel), ctypes.c_int(nleg), ctypes.c_int(nlos),
         _p(alt), ctypes.c_int(interp), ctypes.c_int(geotype), ctypes.c_double(cos_sza), ctypes.c_double(earth_radius),

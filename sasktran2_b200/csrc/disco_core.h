@@ -26,6 +26,31 @@ constexpr double kPi = 3.14159265358979323846;
 constexpr double kGreensEps = 1e-4;   // SKTRAN_DO_GREENS_EPS (sktran_do_types.h:11)
 constexpr double kSsaDither = 1e-9;   // sktran_do_specs.h:104
 
+// Particular-solution multipliers without removable singularities.  The reference evaluates C+, h- and D-
+// (sktran_do_rte.cpp:1203-1226, sktran_do_opticallayer.cpp:339-344, 897-938) as differences of exponentials over
+// (secant - k) or (1 - mu k); close to those degeneracies the values lose digits and the secant-derivatives lose
+// twice as many, which the weighting-function chain then divides by the layer optical depth.  With
+//   phi(x) = (1 - e^-x) / x,   psi(a; k1, k2) = (e^{-a k1} - e^{-a k2}) / (a (k2 - k1)) = e^{-a min(k1,k2)} phi(a |k2 - k1|)
+// the same quantities are  C+ = t a psi(a; k, s),  h- = (a / mu) psi(a; k, 1/mu),
+// D- = t (mu h+ - a e^{-a/mu} psi(a; k, s)) / (1 + mu s).  The reference's own Taylor branches (|secant - k| <= 1e-4,
+// |1 - mu k| <= 1e-4) are kept verbatim, so results differ from the reference's only by the rounding noise of its
+// direct formulas.
+DISCO_HD double phi_value(double x) { return x == 0.0 ? 1.0 : -expm1(-x) / x; }
+DISCO_HD double phi_deriv(double x) {
+    if (fabs(x) > 0.01) return (exp(-x) - phi_value(x)) / x;
+    double term = -0.5, sum = -0.5;  // phi'(x) = sum_n (-1)^(n+1) (n+1) x^n / (n+2)!
+#pragma unroll
+    for (int n = 1; n < 9; ++n) {
+        term *= -x * (n + 1.0) / (n * (n + 2.0));
+        sum += term;
+    }
+    return sum;
+}
+// e1 = exp(-a k1), e2 = exp(-a k2)
+DISCO_HD double psi_value(double a, double k1, double k2, double e1, double e2) {
+    return (k2 >= k1) ? e1 * phi_value(a * (k2 - k1)) : e2 * phi_value(a * (k1 - k2));
+}
+
 // Geometry tables (device or host pointers), see disco_plan.h for layouts
 struct Tables {
     int nstr, N, L, nloc, nlos;
@@ -212,7 +237,7 @@ DISCO_HD void layer_solve(const Tables& T, int m, double od, double ssa, const d
         double kj = S.k[j], exp_k = S.theta[j];
         double Cp, Cm;
         if (fabs(secant - kj) > kGreensEps)
-            Cp = trans_top * (exp_k - exp_sec) / (secant - kj);
+            Cp = trans_top * od * psi_value(od, kj, secant, exp_k, exp_sec);
         else
             Cp = trans_top * exp_k * od * (1.0 - od / 2.0 * (secant - kj));
         if (fabs(secant + kj) > kGreensEps)
@@ -284,14 +309,14 @@ DISCO_HD void los_layer_terms(const Tables& T, int m, int los, double od, double
         {
             double den = 1.0 - mu * k;
             if (fabs(den) > 0.0001)
-                hm = (S.theta[j] - att) / den;
+                hm = od / mu * psi_value(od, k, 1.0 / mu, S.theta[j], att);
             else
                 hm = S.theta[j] * od / mu * (1.0 - od * (k - 1.0 / mu));
         }
         cpos[j] = Yp * hp;
         cneg[j] = Ym * hm;
         double Dp = (-trans_top * expfactor * hm + E) / (secant + k);
-        double Dm = (trans_top * hp - E) / (secant - k);
+        double Dm = trans_top * (mu * hp - od * att * psi_value(od, k, secant, S.theta[j], expfactor)) / (1.0 + mu * secant);
         V += S.Ap[j] * Yp * Dm + S.Am[j] * Ym * Dp;
     }
     v = V + Q * E;

@@ -341,8 +341,11 @@ void DeviceEngine::solve_staged() {
         m_launches += 5;
         if (m_wf_on) {
             launch_bvp_adjoint(V, m_stream);
+            mark(); slots.push_back(T_WF_ADJOINT);
             launch_wf_layer(V, m_stream);
+            mark(); slots.push_back(T_WF_LAYER);
             launch_wf_chain(V, m_stream);
+            mark(); slots.push_back(T_WF_CHAIN);
             m_launches += 3;
             for (auto& dm : m_maps) {
                 MappingView mv;
@@ -360,7 +363,7 @@ void DeviceEngine::solve_staged() {
                 launch_wf_surface(V, ds.d_brdf, ds.out, w0, m_stream);
                 m_launches += 1;
             }
-            mark(); slots.push_back(T_WF);
+            mark(); slots.push_back(T_WF_MAP);
         }
     }
     CUDA_OK(cudaGetLastError());
@@ -370,6 +373,7 @@ void DeviceEngine::solve_staged() {
         CUDA_OK(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
         m_ms[slots[i]] += ms;
     }
+    m_ms[T_WF] = m_ms[T_WF_ADJOINT] + m_ms[T_WF_LAYER] + m_ms[T_WF_CHAIN] + m_ms[T_WF_MAP];
     float tot = 0;
     CUDA_OK(cudaEventElapsedTime(&tot, evs.front(), evs.back()));
     m_ms[T_TOTAL_KERNELS] = tot;

@@ -52,7 +52,7 @@ struct WfRequest {
     bool enabled() const { return !mappings.empty() || !surfaces.empty(); }
 };
 
-enum TimingSlot { T_H2D = 0, T_OPTICS, T_LAYER, T_BVP, T_RADIANCE, T_D2H, T_TOTAL_KERNELS, T_WF, T_NSLOTS };
+enum TimingSlot { T_H2D = 0, T_OPTICS, T_LAYER, T_BVP, T_RADIANCE, T_D2H, T_TOTAL_KERNELS, T_WF, T_WF_ADJOINT, T_WF_LAYER, T_WF_CHAIN, T_WF_MAP, T_NSLOTS };
 
 class DeviceEngine {
   public:

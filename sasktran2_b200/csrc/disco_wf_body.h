@@ -106,6 +106,21 @@ DISCO_HD Dk<NL> dexp(const Dk<NL>& a) {
     return r;
 }
 
+template <int NL>
+DISCO_HD Dk<NL> dphi(const Dk<NL>& a) {
+    Dk<NL> r;
+    r.v = phi_value(a.v);
+    const double dp = phi_deriv(a.v);
+    for (int i = 0; i < NL; ++i) r.d[i] = dp * a.d[i];
+    return r;
+}
+// psi(a; k1, k2) of disco_core.h with dual arguments; e1 = exp(-a k1), e2 = exp(-a k2)
+template <int NL>
+DISCO_HD Dk<NL> dpsi(const Dk<NL>& a, const Dk<NL>& k1, const Dk<NL>& k2, const Dk<NL>& e1, const Dk<NL>& e2) {
+    if (k2.v >= k1.v) return e1 * dphi(a * (k2 - k1));
+    return e2 * dphi(a * (k1 - k2));
+}
+
 // Green's function particular solution with dual inputs (same formulas and branches as layer_solve)
 template <int N, int NL>
 DISCO_HD void particular_dual(const Tables& T, int m, const Dk<NL>& od, const Dk<NL>& ssa, const Dk<NL>* beta,
@@ -147,7 +162,7 @@ DISCO_HD void particular_dual(const Tables& T, int m, const Dk<NL>& od, const Dk
         const D& exp_k = theta[j];
         D Cp, Cm;
         if (fabs(secant.v - kj.v) > kGreensEps)
-            Cp = trans_top * (exp_k - exp_sec) / (secant - kj);
+            Cp = trans_top * od * dpsi(od, kj, secant, exp_k, exp_sec);
         else
             Cp = trans_top * exp_k * od * (1.0 - od * 0.5 * (secant - kj));
         if (fabs(secant.v + kj.v) > kGreensEps)
@@ -220,12 +235,12 @@ DISCO_HD Dk<NL> los_source_dual(const Tables& T, int m, int los, const Dk<NL>& o
         {
             const D den = 1.0 - kj * mu;
             if (fabs(den.v) > 0.0001)
-                hm = (theta[j] - att) / den;
+                hm = od * (1.0 / mu) * dpsi(od, kj, D(1.0 / mu), theta[j], att);
             else
                 hm = theta[j] * od * (1.0 / mu) * (1.0 - od * (kj - 1.0 / mu));
         }
         const D Dp = (E - trans_top * expfactor * hm) / (secant + kj);
-        const D Dm = (trans_top * hp - E) / (secant - kj);
+        const D Dm = trans_top * (hp * mu - od * att * dpsi(od, kj, secant, theta[j], expfactor)) / (1.0 + secant * mu);
         src = src + Yp * hp * Lc[j] + Ym * hm * Mc[j] + Ap[j] * Yp * Dm + Am[j] * Ym * Dp;
     }
     return src + Q * E;

@@ -9,7 +9,8 @@ import numpy as np
 
 from . import _lib
 
-TIMING_NAMES = ("h2d", "optics", "layer", "bvp", "radiance", "d2h", "kernels_total", "wf")
+TIMING_NAMES = ("h2d", "optics", "layer", "bvp", "radiance", "d2h", "kernels_total", "wf", "wf_adjoint", "wf_layer",
+                "wf_chain", "wf_map")
 
 
 class Result(dict):

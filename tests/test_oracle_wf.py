@@ -25,8 +25,9 @@ def species_atmosphere(nstr, nlayers, nwavel, scale=None):
     return z, build, k_aer0, k_abs0, w_aer, b_aer
 
 
+@pytest.mark.parametrize("stable", [False, True], ids=["reference-formulas", "stable-multipliers"])
 @pytest.mark.parametrize("interp,geotype,nstr", [(2, 0, 4), (2, 1, 8), (1, 1, 8)])
-def test_oracle_wf_matches_finite_differences(oracle_mod, interp, geotype, nstr):
+def test_oracle_wf_matches_finite_differences(oracle_mod, interp, geotype, nstr, stable):
     nlayers, nwavel = 8, 2
     z, build, k_aer0, k_abs0, w_aer, b_aer = species_atmosphere(nstr, nlayers, nwavel)
     nloc = z.size
@@ -37,7 +38,8 @@ def test_oracle_wf_matches_finite_differences(oracle_mod, interp, geotype, nstr)
 
     k, ssa, leg, ks = build(k_aer0, k_abs0)
     d_leg = (b_aer[:, None, None] - leg)[..., None]
-    base = oracle_mod.do_radiance(**common, ssa=ssa, ext=k, leg=leg, albedo=albedo, d_leg=d_leg, calc_derivs=True)
+    base = oracle_mod.do_radiance(**common, ssa=ssa, ext=k, leg=leg, albedo=albedo, d_leg=d_leg, calc_derivs=True,
+                                  stable=stable)
     maps = {
         "abs": dict(d_extinction=np.ones_like(k), d_ssa=-ssa / k),
         "aer": dict(d_extinction=np.ones_like(k), d_ssa=(w_aer - ssa) / k, scat_factor=w_aer / ks, scat_index=0),
@@ -47,7 +49,7 @@ def test_oracle_wf_matches_finite_differences(oracle_mod, interp, geotype, nstr)
 
     def rad(k_aer, k_abs, alb=albedo):
         kk, ss, ll, _ = build(k_aer, k_abs)
-        return oracle_mod.do_radiance(**common, ssa=ss, ext=kk, leg=ll, albedo=alb)["radiance"]
+        return oracle_mod.do_radiance(**common, ssa=ss, ext=kk, leg=ll, albedo=alb, stable=stable)["radiance"]
 
     # with linear interpolation the reference takes the scattering-derivative direction from one grid point
     # only (sktran_do_layerarray.cpp:761-800, see oracle map_to_native), so its aerosol WF is approximate there.
@@ -70,3 +72,31 @@ def test_oracle_wf_matches_finite_differences(oracle_mod, interp, geotype, nstr)
     h = 1e-5
     fd = (rad(k_aer0, k_abs0, albedo + h) - rad(k_aer0, k_abs0, albedo - h)) / (2 * h)
     np.testing.assert_allclose(d_albedo, fd, rtol=2e-7)
+
+
+def test_oracle_stable_multipliers_agree_with_reference_formulas(oracle_mod):
+    """The singularity-free multipliers (phi/psi forms) reproduce the reference's formulas to rounding on the
+    radiance and to within the reference formulas' own rounding noise on the native derivatives; their own noise
+    floor on dI/dk is orders of magnitude lower (16 streams at cos_sza = 0.6: some layer always sits close to the
+    secant = eigenvalue degeneracy, DESIGN.md "Conditioning")."""
+    sc = scn.small_wf_case(nstr=16, nlayers=25, nwavel=5, nlos=6)
+    d_leg = sc.mappings["wf_aerosol_extinction"]["d_legendre"][..., None]
+    inp = dict(nstr=sc.nstr, alt=sc.altitudes, interp=sc.interp, geotype=sc.geotype, cos_sza=sc.cos_sza,
+               los_cos_vza=sc.los_cos_vza, los_rel_az=sc.los_rel_az, ssa=sc.ssa, leg=sc.leg_coeff, albedo=sc.albedo,
+               d_leg=d_leg, calc_derivs=True)
+    nloc = sc.nloc
+    k_block = slice(0, nloc)
+
+    def run(stable, eps=0.0):
+        return oracle_mod.do_radiance(**inp, ext=sc.total_extinction * (1.0 + eps), stable=stable)
+
+    ref, stb = run(False), run(True)
+    np.testing.assert_allclose(stb["radiance"], ref["radiance"], rtol=1e-12)
+
+    def rel(a, b):
+        return np.max(np.abs(a - b)[..., k_block] / np.abs(b[..., k_block]).max(axis=-1, keepdims=True))
+
+    noise_ref = max(rel(run(False, e)["native"], ref["native"]) for e in (1e-12, -1e-12, 1e-11))
+    noise_stb = max(rel(run(True, e)["native"], stb["native"]) for e in (1e-12, -1e-12, 1e-11))
+    assert rel(stb["native"], ref["native"]) <= 10.0 * max(noise_ref, noise_stb)
+    assert noise_stb < 1e-9

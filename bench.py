@@ -270,7 +270,8 @@ def main():
         eng.solve_staged()
         t = eng.timings_ms()
         dev_ms += t["kernels_total"]
-        for k in ("optics", "layer", "bvp", "radiance", "wf"):  # wf = adjoint BVP + layer derivatives + chain + mapping
+        # weighting functions: adjoint BVP, layer derivatives, cross-layer chain, mapping
+        for k in ("optics", "layer", "bvp", "radiance", "wf_adjoint", "wf_layer", "wf_chain", "wf_map"):
             per_kernel[k] = per_kernel.get(k, 0.0) + t.get(k, 0.0)
         launches += eng.kernel_launches()
     barrier()

@@ -43,7 +43,7 @@ struct ChunkView {
     double* G;                // [nw][M][L][4N]  G+top | G-top | G+bot | G-bot
     double* surf;             // [nw][2N+1]      s+_j | s-_j | sG   (bottom layer, m = 0)
     double* wvec;             // [nw][M][nlos][L][2N]  d(radiance_m)/d(L_j, M_j)
-    double* vsrc;             // [nw][M][nlos][L]      particular + single-scatter (+ ground direct) terms
+    double* vsrc;             // [nw][M][nlos][L][vsrc_w]  particular + single-scatter (+ ground direct) terms
     double* xsol;             // [nw][M][L][2N]        BVP solution L | M
     double* fac;              // [group][fac_stride]   pivot rows of the staircase LU (forward and adjoint)
     size_t fac_stride;        // doubles per solve group: (L+1) * 2N * (4N + max nrhs)
@@ -59,6 +59,13 @@ struct ChunkView {
     double* wf_gnd;           // [nw][nlos][3]
     double* wf_native;        // [nw][nlos][nloc*(2+G)+1]
     double* wf_scratch;       // [nw][nlos][3][L+1]
+    // ---- register-resident fast path (N <= 8): [element][problem] staging planes of the eigen-solve
+    double* eigS;             // [N(N+1)/2][nw*M*L] packed symmetric S~+
+    double* eigH;             // [N(N+1)/2][nw*M*L] packed Cholesky factor of S~-
+    double* eigC;             // [N(N+1)/2][nw*M*L] packed symmetric C = H^T S~+ H
+    double* los_att;          // [nw][nlos][L+1]  exp(-cum_od / mu_los)
+    double* los_lay;          // [nw][nlos][L][3] exp(-od / mu_los) | E | 1 / (1 + mu secant)
+    int vsrc_w;               // entries of vsrc per (w, m, los, layer): 1 (generic path) or N (per-solution partials)
     unsigned int* status;     // error bits
 };
 
@@ -252,12 +259,13 @@ DISCO_HD void radiance_body(const ChunkView& V, long long idx) {
         const int m = V.m_list[ms];
         const size_t o = (((size_t)w * M + ms) * nlos + los) * L;
         const double* wv = V.wvec + o * 2 * N;
-        const double* vs = V.vsrc + o;
+        const double* vs = V.vsrc + o * V.vsrc_w;
         const double* x = V.xsol + ((size_t)w * M + ms) * L * 2 * N;
         double comp = 0.0;
         // same accumulation order as the reference's upward recursion: ground/bottom layer first
         for (int p = L - 1; p >= 0; --p) {
-            double s = vs[p];
+            double s = 0.0;
+            for (int c = 0; c < V.vsrc_w; ++c) s += vs[(size_t)p * V.vsrc_w + c];
             for (int j = 0; j < 2 * N; ++j) s += wv[(size_t)p * 2 * N + j] * x[(size_t)p * 2 * N + j];
             comp += s;
         }

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -67,6 +68,12 @@ DeviceEngine::DeviceEngine(const EngineOptions& opt, const HostPlan& plan) : m_o
     }
     if (m_mlist.empty()) m_mlist.push_back(0);
     d_mlist = upload(m_mlist);
+    // register-resident layer solve for N = 2, 4, 8; SK_B200_GENERIC=1 forces the generic thread-per-problem
+    // kernels (differential testing of the two code paths)
+    {
+        const char* g = std::getenv("SK_B200_GENERIC");
+        m_fast = fast_path_supported(plan.N) && !(g && g[0] == '1');
+    }
     d_status = dalloc<unsigned int>(1);
     CUDA_OK(cudaMemset(d_status, 0, sizeof(unsigned int)));
 }
@@ -118,7 +125,9 @@ size_t DeviceEngine::workspace_bytes_per_wavelength() const {
     size_t d = L * (6 + nstr) + 2 * (L + 1);                       // layer optics
     d += 2 * M * L * N * N + M * L * 2 * N + M * L * 4 * N;         // W+, W-, k|theta, G
     d += 2 * N + 1;                                                 // surface sums
-    d += M * nlos * L * 2 * N + M * nlos * L;                       // wvec, vsrc
+    const size_t vw = m_fast ? N : 1;
+    d += M * nlos * L * 2 * N + M * nlos * L * vw;                  // wvec, vsrc
+    if (m_fast) d += 3 * (N * (N + 1) / 2) * M * L + nlos * (L + 1) + nlos * L * 3;  // eigen planes, LOS exponentials
     d += M * L * 2 * N;                                             // x
     if (!m_wf_on) {
         d += M * (L + 1) * 2 * N * (4 * N + 1);                     // LU pivot rows (forward solve)
@@ -146,55 +155,57 @@ void DeviceEngine::ensure_workspace(int chunk) {
     const size_t N = m_plan.N, L = m_plan.L, nstr = m_plan.nstr, nlos = m_plan.nlos, M = m_mlist.size();
     const size_t c = chunk;
     m_dbg.clear();
-    auto A = [&](size_t n) {
+    auto A = [&](const char* name, size_t n) {
         double* p = dalloc<double>(n);
         m_ws_ptrs.push_back(p);
-        m_dbg.push_back({"", {p, n}});
+        m_dbg.push_back({name, {p, n}});
         return p;
     };
     ChunkView& V = m_view;
-    V.lay_od = A(c * L);
-    V.lay_ssa = A(c * L);
-    V.lay_beta = A(c * L * nstr);
-    V.lay_secant = A(c * L);
-    V.lay_trans = A(c * (L + 1));
-    V.lay_cumod = A(c * (L + 1));
-    V.lay_totext = A(c * L);
-    V.lay_scatext = A(c * L);
-    V.Wp = A(c * M * L * N * N);
-    V.Wm = A(c * M * L * N * N);
-    V.kth = A(c * M * L * 2 * N);
-    V.G = A(c * M * L * 4 * N);
-    V.surf = A(c * (2 * N + 1));
-    V.wvec = A(c * M * nlos * L * 2 * N);
-    V.vsrc = A(c * M * nlos * L);
-    V.xsol = A(c * M * L * 2 * N);
+    V.lay_od = A("lay_od", c * L);
+    V.lay_ssa = A("lay_ssa", c * L);
+    V.lay_beta = A("lay_beta", c * L * nstr);
+    V.lay_secant = A("lay_secant", c * L);
+    V.lay_trans = A("lay_trans", c * (L + 1));
+    V.lay_cumod = A("lay_cumod", c * (L + 1));
+    V.lay_totext = A("lay_totext", c * L);
+    V.lay_scatext = A("lay_scatext", c * L);
+    V.Wp = A("Wp", c * M * L * N * N);
+    V.Wm = A("Wm", c * M * L * N * N);
+    V.kth = A("kth", c * M * L * 2 * N);
+    V.G = A("G", c * M * L * 4 * N);
+    V.surf = A("surf", c * (2 * N + 1));
+    V.wvec = A("wvec", c * M * nlos * L * 2 * N);
+    V.vsrc_w = m_fast ? (int)N : 1;
+    V.vsrc = A("vsrc", c * M * nlos * L * V.vsrc_w);
+    V.eigS = V.eigH = V.eigC = V.los_att = V.los_lay = nullptr;
+    if (m_fast) {
+        const size_t ts = N * (N + 1) / 2;
+        V.eigS = A("eigS", ts * c * M * L);
+        V.eigH = A("eigH", ts * c * M * L);
+        V.eigC = A("eigC", ts * c * M * L);
+        V.los_att = A("los_att", c * nlos * (L + 1));
+        V.los_lay = A("los_lay", c * nlos * L * 3);
+    }
+    V.xsol = A("xsol", c * M * L * 2 * N);
     if (!m_wf_on) {
         V.fac_stride = (L + 1) * 2 * N * (4 * N + 1);
-        V.fac = A(c * M * V.fac_stride);
+        V.fac = A("fac", c * M * V.fac_stride);
         V.zadj = nullptr;
         V.lay_dbeta = V.wf_loc = V.wf_src = V.wf_gnd = V.wf_native = V.wf_scratch = nullptr;
     } else {
         const size_t G = m_ngroups, nrhs = adjoint_max_rhs((int)nlos), ngrp = adjoint_groups_per_problem((int)nlos);
         V.fac_stride = (L + 1) * 2 * N * (4 * N + nrhs);
-        V.fac = A(c * M * ngrp * V.fac_stride);
-        V.zadj = A(c * M * nlos * 2 * N * L);
-        V.lay_dbeta = A(c * L * G * nstr);
-        V.wf_loc = A(c * M * nlos * L * (G + 4));
-        V.wf_src = A(c * M * nlos * L);
-        V.wf_gnd = A(c * nlos * 3);
-        V.wf_native = A(c * nlos * (m_plan.nloc * (2 + G) + 1));
-        V.wf_scratch = A(c * nlos * 3 * (L + 1));
+        V.fac = A("fac", c * M * ngrp * V.fac_stride);
+        V.zadj = A("zadj", c * M * nlos * 2 * N * L);
+        V.lay_dbeta = A("lay_dbeta", c * L * G * nstr);
+        V.wf_loc = A("wf_loc", c * M * nlos * L * (G + 4));
+        V.wf_src = A("wf_src", c * M * nlos * L);
+        V.wf_gnd = A("wf_gnd", c * nlos * 3);
+        V.wf_native = A("wf_native", c * nlos * (m_plan.nloc * (2 + G) + 1));
+        V.wf_scratch = A("wf_scratch", c * nlos * 3 * (L + 1));
     }
     m_ws_wf = m_wf_on;
-    {
-        static const char* base[] = {"lay_od", "lay_ssa", "lay_beta", "lay_secant", "lay_trans", "lay_cumod", "lay_totext",
-                                     "lay_scatext", "Wp", "Wm", "kth", "G", "surf", "wvec", "vsrc", "xsol", "fac"};
-        static const char* wfn[] = {"zadj", "lay_dbeta", "wf_loc", "wf_src", "wf_gnd", "wf_native", "wf_scratch"};
-        size_t i = 0;
-        for (; i < 17 && i < m_dbg.size(); ++i) m_dbg[i].first = base[i];
-        for (size_t j = 0; i < m_dbg.size() && j < 7; ++i, ++j) m_dbg[i].first = wfn[j];
-    }
     m_ws_chunk = chunk;
 }
 
@@ -332,7 +343,12 @@ void DeviceEngine::solve_staged() {
         launch_layer_optics(V, m_stream);
         launch_beam(V, m_stream);
         mark(); slots.push_back(T_OPTICS);
-        launch_layer_solve(V, m_stream);
+        if (m_fast) {
+            launch_layer_solve_fast(V, m_stream);
+            m_launches += 3;
+        } else {
+            launch_layer_solve(V, m_stream);
+        }
         mark(); slots.push_back(T_LAYER);
         launch_bvp(V, m_stream);
         mark(); slots.push_back(T_BVP);

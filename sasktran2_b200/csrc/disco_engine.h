@@ -70,6 +70,7 @@ class DeviceEngine {
     // stage + solve + fetch
     void calculate(const AtmosphereArrays& atm, int w0, int nw, double* radiance_host, const WfRequest* wf = nullptr);
     bool wf_active() const { return m_wf_on; }
+    bool fast_path() const { return m_fast; }
     // test/debug: copy a workspace array of the LAST chunk to the host; returns the number of doubles copied
     size_t debug_copy(const char* name, double* host, size_t max_n);
     std::vector<std::pair<std::string, std::pair<double*, size_t>>> m_dbg;
@@ -119,6 +120,7 @@ class DeviceEngine {
     std::vector<DevMapping> m_maps;
     std::vector<DevSurface> m_surfs;
     bool m_ws_wf = false;
+    bool m_fast = false;      // register-resident layer solve (disco_fast*.cuh)
     // chunk workspace
     int m_ws_chunk = 0;
     std::vector<void*> m_ws_ptrs;

@@ -1,0 +1,39 @@
+// Register-resident fast path of the layer solve (N = 2, 4, 8 streams per hemisphere): instantiations + launchers.
+#include "disco_fast_eig.cuh"
+#include "disco_fast_post.cuh"
+
+namespace disco {
+
+bool fast_path_supported(int N) { return N == 2 || N == 4 || N == 8; }
+
+template <int N>
+static void launch_fast_n(const ChunkView& V, cudaStream_t s) {
+    const long long nq = (long long)V.nw * V.T.L;
+    {
+        const long long n = (long long)V.nw * V.T.nlos * (V.T.L + 1);
+        k_los_atten<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V);
+    }
+    const dim3 grid_t((unsigned)((nq + 127) / 128), (unsigned)V.M);
+    k_eig_setup<N><<<grid_t, 128, 0, s>>>(V);
+    k_eig_jacobi<N><<<grid_t, 128, 0, s>>>(V);
+    const size_t smem = (size_t)post_smem_doubles<N>(V.T.nlos) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_layer_post<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    const dim3 grid_p((unsigned)((nq + PostCfg<N>::PPB - 1) / PostCfg<N>::PPB), (unsigned)V.M);
+    k_layer_post<N><<<grid_p, 128, smem, s>>>(V);
+}
+
+// launches 4 kernels
+void launch_layer_solve_fast(const ChunkView& V, cudaStream_t s) {
+    switch (V.T.N) {
+        case 2: launch_fast_n<2>(V, s); break;
+        case 4: launch_fast_n<4>(V, s); break;
+        case 8: launch_fast_n<8>(V, s); break;
+        default: break;
+    }
+}
+
+}  // namespace disco

@@ -49,10 +49,35 @@ __global__ void __launch_bounds__(128) k_layer_solve(ChunkView V) {
 // -------------------------------------------------------------------------------------------------
 // K4: radiance[w, los] = sum_m cos(m phi) * sum_p ( wvec . x + v )
 // -------------------------------------------------------------------------------------------------
-__global__ void k_radiance(ChunkView V) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)V.nw * V.T.nlos) return;
-    radiance_body(V, idx);
+// One warp per (wavelength, LOS): the lanes stream the contiguous [L][2N] slabs of wvec and x (coalesced) and
+// the partial sums are combined with a butterfly at the end.  (radiance_body in disco_bodies.h is the serial
+// statement of the same sum, used by the host emulation.)
+__global__ void __launch_bounds__(128) k_radiance(ChunkView V) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= (long long)V.nw * V.T.nlos) return;
+    const int L = V.T.L, M = V.M, nlos = V.T.nlos, nstr = V.T.nstr;
+    const int w = (int)(warp / nlos), los = (int)(warp % nlos);
+    const int n = L * nstr;  // 2N unknowns per layer
+    double total = 0.0;
+    for (int ms = 0; ms < M; ++ms) {
+        const size_t o = (((size_t)w * M + ms) * nlos + los) * L;
+        const double* __restrict__ wv = V.wvec + o * nstr;
+        const double* __restrict__ vs = V.vsrc + o * V.vsrc_w;
+        const double* __restrict__ x = V.xsol + ((size_t)w * M + ms) * n;
+        double a0 = 0.0, a1 = 0.0;
+        int e = lane;
+        for (; e + 32 < n; e += 64) {
+            a0 = fma(wv[e], x[e], a0);
+            a1 = fma(wv[e + 32], x[e + 32], a1);
+        }
+        if (e < n) a0 = fma(wv[e], x[e], a0);
+        for (int p = lane; p < L * V.vsrc_w; p += 32) a1 += vs[p];
+        total = fma(a0 + a1, V.T.los_cosmphi[(size_t)los * nstr + V.m_list[ms]], total);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(FULL_MASK, total, off);
+    if (lane == 0) V.radiance[warp] = total;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -188,8 +213,8 @@ void launch_wf_surface(const ChunkView& V, const double* d_brdf, double* out, in
 int adjoint_groups_per_problem(int nlos) { const int r = adj_rhs_for(nlos); return (nlos + r - 1) / r; }
 int adjoint_max_rhs(int nlos) { return adj_rhs_for(nlos); }
 void launch_radiance(const ChunkView& V, cudaStream_t s) {
-    const long long n = (long long)V.nw * V.T.nlos;
-    k_radiance<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V);
+    const long long n = (long long)V.nw * V.T.nlos;  // warps
+    k_radiance<<<(unsigned)((n + 3) / 4), 128, 0, s>>>(V);
 }
 
 }  // namespace disco

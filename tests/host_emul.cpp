@@ -198,6 +198,7 @@ extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nl
         V.lay_trans = A(c * (L + 1)); V.lay_cumod = A(c * (L + 1)); V.lay_totext = A(c * L); V.lay_scatext = A(c * L);
         V.Wp = A(c * M * L * N * N); V.Wm = A(c * M * L * N * N); V.kth = A(c * M * L * 2 * N);
         V.G = A(c * M * L * 4 * N); V.surf = A(c * (2 * N + 1)); V.wvec = A(c * M * nlos * L * 2 * N);
+        V.vsrc_w = 1;
         V.vsrc = A(c * M * nlos * L); V.xsol = A(c * M * L * 2 * N); V.fac = A(c * M * L * 2 * N * (4 * N + 1));
         V.radiance = radiance;
         const bool wf = native != nullptr;

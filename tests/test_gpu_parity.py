@@ -207,38 +207,39 @@ def _oracle_noise(oracle_mod, sc, wf, stable, perturbations=(1e-12, -1e-12, 3e-1
     return noise
 
 
-def _assert_wf_one(res, wf, noise, amplified, loose=()):
-    """`amplified`: mappings with a scat_factor / d_ssa ~ 1/k ~ 1e10 at the top of the atmosphere; everywhere else the
-    noise floor is far below 1e-7, so the bound below IS 1e-7 there (asserted explicitly)."""
-    for name, ref in wf.items():
-        got = res["wf_albedo"][None, :, :, 0] if name == "__albedo__" else res[name][..., 0]
-        assert got.shape == ref.shape
-        scale = np.abs(ref).max(axis=0, keepdims=True)
-        err = np.abs(got - ref) / scale
-        tol = np.maximum(RTOL_WF, 10.0 * noise[name])[None, :, None]
-        if name in loose:
-            tol = np.maximum(tol, 0.05)
-        assert np.all(err <= tol), (name, float(err.max()), float((err / tol).max()))
-        if name not in amplified:
-            assert np.all(err <= RTOL_WF), (name, float(err.max()))
+def _get(res, name):
+    return res["wf_albedo"][None, :, :, 0] if name == "__albedo__" else res[name][..., 0]
 
 
 def _assert_wf(oracle_mod, sc, res, perturbations=(1e-12, -1e-12, 3e-12, -3e-12, 1e-11, -1e-11)):
     """Weighting functions vs the oracle, relative to the column maximum of each weighting function:
       1. against the oracle with singularity-free multipliers: |cuda - oracle| <= 1e-7 for every mapping except the
          scatterer-extinction ones, whose 1/k mapping factors amplify the common noise floor at the top of the
-         atmosphere: there max(1e-7, 10 x that oracle's own noise floor) - this pins the CUDA path's accuracy;
-      2. against the oracle with the reference's formulas verbatim: |cuda - oracle| <= max(1e-7, 10 x ITS noise
-         floor) - parity with the reference wherever the reference's own result is reproducible.  For the
-         scatterer-extinction mappings it is not: the direct D- / C+ formulas put 1e-5..1e-2 of heavy-tailed noise
-         on them at the top of the atmosphere (test_oracle_stable_multipliers_agree_with_reference_formulas), so
-         those are only held to a 5 % sanity bound here and to the tight bound in 1."""
+         atmosphere: there max(1e-7, 10 x that oracle's own noise floor).  This pins the CUDA path's accuracy.
+      2. against the oracle with the reference's formulas verbatim: radiance to 1e-9, weighting functions to
+         max(1e-7, 10 x ITS sampled noise floor) or, where the direct C+ / D- formulas are ill-conditioned (their
+         error is frozen rounding / (secant - k)^2 and a 1e-12 perturbation does not resample it), to within
+         twice the distance between the two oracle variants: the CUDA result is then as close to the reference's
+         as an exact evaluation of the reference's own formulas is."""
     amplified = {n for n, mp in sc.mappings.items() if mp.get("scat_factor") is not None and "probe" not in n}
-    for stable in (True, False):
-        ora, wf = _oracle_wf(oracle_mod, sc, stable=stable)
-        np.testing.assert_allclose(res["radiance"][:, :, 0], ora["radiance"], rtol=RTOL_RADIANCE)
-        _assert_wf_one(res, wf, _oracle_noise(oracle_mod, sc, wf, stable, perturbations),
-                       amplified if stable else set(wf), loose=() if stable else amplified)
+    ora_s, wf_s = _oracle_wf(oracle_mod, sc, stable=True)
+    np.testing.assert_allclose(res["radiance"][:, :, 0], ora_s["radiance"], rtol=RTOL_RADIANCE)
+    noise_s = _oracle_noise(oracle_mod, sc, wf_s, True, perturbations)
+    for name, ref in wf_s.items():
+        got = _get(res, name)
+        assert got.shape == ref.shape
+        err = np.abs(got - ref) / np.abs(ref).max(axis=0, keepdims=True)
+        tol = np.maximum(RTOL_WF, 10.0 * noise_s[name])[None, :, None] if name in amplified else RTOL_WF
+        assert np.all(err <= tol), ("stable", name, float(err.max()), float((err / tol).max()))
+    ora_r, wf_r = _oracle_wf(oracle_mod, sc, stable=False)
+    np.testing.assert_allclose(res["radiance"][:, :, 0], ora_r["radiance"], rtol=RTOL_RADIANCE)
+    noise_r = _oracle_noise(oracle_mod, sc, wf_r, False, perturbations[:3])
+    for name, ref in wf_r.items():
+        scale = np.abs(ref).max(axis=0, keepdims=True)
+        err = np.abs(_get(res, name) - ref) / scale
+        tol = np.maximum(np.maximum(RTOL_WF, 10.0 * noise_r[name])[None, :, None],
+                         RTOL_WF + 2.0 * np.abs(wf_s[name] - ref) / scale)
+        assert np.all(err <= tol), ("reference formulas", name, float(err.max()), float((err / tol).max()))
 
 
 @pytest.mark.parametrize("nstr,interp,geotype,nlos,nlayers", [(4, 2, 0, 2, 9), (8, 1, 1, 3, 12), (16, 1, 1, 6, 25),

@@ -358,7 +358,10 @@ void DeviceEngine::solve_staged() {
         if (m_wf_on) {
             launch_bvp_adjoint(V, m_stream);
             mark(); slots.push_back(T_WF_ADJOINT);
-            launch_wf_layer(V, m_stream);
+            if (m_fast && wf_layer_fast_smem_bytes(m_plan.N, m_ngroups, m_plan.nlos) <= 200 * 1024)
+                launch_wf_layer_fast(V, m_stream);
+            else
+                launch_wf_layer(V, m_stream);
             mark(); slots.push_back(T_WF_LAYER);
             launch_wf_chain(V, m_stream);
             mark(); slots.push_back(T_WF_CHAIN);

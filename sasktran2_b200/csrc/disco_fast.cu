@@ -1,6 +1,7 @@
 // Register-resident fast path of the layer solve (N = 2, 4, 8 streams per hemisphere): instantiations + launchers.
 #include "disco_fast_eig.cuh"
 #include "disco_fast_post.cuh"
+#include "disco_fast_wf.cuh"
 
 namespace disco {
 
@@ -32,6 +33,44 @@ void launch_layer_solve_fast(const ChunkView& V, cudaStream_t s) {
         case 2: launch_fast_n<2>(V, s); break;
         case 4: launch_fast_n<4>(V, s); break;
         case 8: launch_fast_n<8>(V, s); break;
+        default: break;
+    }
+}
+
+template <int N, int G>
+static void launch_wf_fast_ng(const ChunkView& V, cudaStream_t s) {
+    using Cf = WfCfg<N, G>;
+    const long long nq = (long long)V.nw * V.T.L;
+    const size_t smem = (size_t)Cf::smem_doubles(V.T.nlos) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_wf_layer_fast<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_set = true;
+    }
+    const dim3 grid((unsigned)((nq + Cf::PPB - 1) / Cf::PPB), (unsigned)V.M);
+    k_wf_layer_fast<N, G><<<grid, 128, smem, s>>>(V);
+}
+template <int N>
+static void launch_wf_fast_n(const ChunkView& V, cudaStream_t s) {
+    switch (V.ngroups) {
+        case 0: launch_wf_fast_ng<N, 0>(V, s); break;
+        case 1: launch_wf_fast_ng<N, 1>(V, s); break;
+        case 2: launch_wf_fast_ng<N, 2>(V, s); break;
+        default: break;
+    }
+}
+// shared memory the fast weighting-function kernel needs for this problem shape (bytes)
+size_t wf_layer_fast_smem_bytes(int N, int G, int nlos) {
+    const int nstr = 2 * N, NL = G + 4, NH = G + 1, ppb = (32 / N) * 4;
+    const int exch = nstr * N + 2 * N * N + 2 * N, red = nlos * (NL + 1) * N;
+    const int per_problem = nlos * 2 * NH * N + (red > exch ? red : exch);
+    return sizeof(double) * (size_t)(2 * nstr * N + nlos * nstr + nstr + N + ppb * per_problem);
+}
+void launch_wf_layer_fast(const ChunkView& V, cudaStream_t s) {
+    switch (V.T.N) {
+        case 2: launch_wf_fast_n<2>(V, s); break;
+        case 4: launch_wf_fast_n<4>(V, s); break;
+        case 8: launch_wf_fast_n<8>(V, s); break;
         default: break;
     }
 }

@@ -1,0 +1,619 @@
+// Layer-local weighting-function kernel, N lanes per (wavelength, order, layer) problem; lane j owns solution j:
+// column j of W+-, its derivatives and every scalar indexed by j live in registers.
+//
+// What is computed is disco_wf_body.h's wf_layer_body (reverse mode: dI = d(source) + z^T (db - dA x); reference:
+// sktran_do_rte.cpp:198-298, 903-1332, 1793-1895; sktran_do_opticallayer.cpp:94-555).  How:
+//   * only the "heavy" lanes e in {eps_g, omega} touch matrices; tau, t (beam transmittance) and s (secant) enter
+//     through scalar functions of (k_j, tau, s, t) whose partials are written out by hand (everything particular
+//     is linear in t);
+//   * eigen-derivatives by perturbation theory in projected form: with p_l[j] = sum_a w_a P_l(mu_a) X_aj the
+//     coupling matrix is P_ij = -[sum_odd c_l pm_l[i] pm_l[j] + lambda_i sum_even c_l p_l[i] p_l[j]] / n_i, i.e. a
+//     contraction of a shared (all-gathered) [l][i] table with lane-private coefficients; S+ dX_j = sum_i Xm_i Q_ij
+//     needs no S+;
+//   * the adjoint term is regrouped per solution:  adj_j = W+_j . xi+ + W-_j . xi- with
+//     xi+ = L zeta1 + A zeta2 + B zeta3 + M zeta4, xi- = A zeta1 + L zeta2 + M zeta3 + B zeta4,
+//     A = theta M + A- C-, B = theta L + A+ C+, zeta = the four N-slices of z on the layer's two boundaries, so the
+//     derivative is d(adj_j) = dW+_j . xi+ + dW-_j . xi- + dA (W+_j.zeta2 + W-_j.zeta1) + dB (W+_j.zeta3 + W-_j.zeta4);
+//   * exchanges (projection tables, X / Xm, the per-LOS phase sums, the final sum over j) go through shared memory
+//     as uniform LDS.128 broadcasts; no shuffles on the hot path.
+#pragma once
+#include "disco_fast_post.cuh"
+
+namespace disco {
+
+struct R3 {  // value and partials with respect to (k_j, tau, secant)
+    double v, k, a, s;
+};
+
+// phi(x) = (1 - e^-x)/x and phi'(x) for x >= 0, given r = e^-x (only used when x > 0.1)
+__device__ __forceinline__ void phi_pair(double x, double r, double& ph, double& dph) {
+    if (x > 0.1) {
+        const double ix = div_fast(1.0, x);
+        ph = (1.0 - r) * ix;
+        dph = (r - ph) * ix;
+    } else {
+        double s = 1.0 / 39916800.0;
+        s = fma(s, -x, 1.0 / 3628800.0);
+        s = fma(s, -x, 1.0 / 362880.0);
+        s = fma(s, -x, 1.0 / 40320.0);
+        s = fma(s, -x, 1.0 / 5040.0);
+        s = fma(s, -x, 1.0 / 720.0);
+        s = fma(s, -x, 1.0 / 120.0);
+        s = fma(s, -x, 1.0 / 24.0);
+        s = fma(s, -x, 1.0 / 6.0);
+        s = fma(s, -x, 0.5);
+        ph = fma(s, -x, 1.0);
+        // phi'(x) = sum_n (-1)^(n+1) (n+1) x^n / (n+2)!
+        double d = -10.0 / 39916800.0;
+        d = fma(d, -x, -9.0 / 3628800.0);
+        d = fma(d, -x, -8.0 / 362880.0);
+        d = fma(d, -x, -7.0 / 40320.0);
+        d = fma(d, -x, -6.0 / 5040.0);
+        d = fma(d, -x, -5.0 / 720.0);
+        d = fma(d, -x, -4.0 / 120.0);
+        d = fma(d, -x, -3.0 / 24.0);
+        d = fma(d, -x, -2.0 / 6.0);
+        dph = fma(d, -x, -0.5);
+    }
+}
+
+// psi(a; k1, k2) = (e1 - e2)/(a (k2 - k1)) with partials w.r.t. k1 (-> .k), a (-> .a) and k2 (-> .s)
+__device__ __forceinline__ R3 psi_dual(double a, double k1, double k2, double e1, double e2) {
+    R3 r;
+    double ph, dph;
+    if (k2 >= k1) {
+        const double x = a * (k2 - k1);
+        const double ratio = (x > 0.1 && e1 > 0.0) ? div_fast(e2, e1) : 0.0;
+        phi_pair(x, ratio, ph, dph);
+        r.v = e1 * ph;
+        r.k = -a * e1 * (ph + dph);
+        r.a = e1 * fma(dph, k2 - k1, -k1 * ph);
+        r.s = a * e1 * dph;
+    } else {
+        const double x = a * (k1 - k2);
+        const double ratio = (x > 0.1 && e2 > 0.0) ? div_fast(e1, e2) : 0.0;
+        phi_pair(x, ratio, ph, dph);
+        r.v = e2 * ph;
+        r.k = a * e2 * dph;
+        r.a = e2 * fma(dph, k1 - k2, -k2 * ph);
+        r.s = -a * e2 * (ph + dph);
+    }
+    return r;
+}
+
+template <int N, int G>
+struct WfCfg {
+    static constexpr int NSTR = 2 * N;
+    static constexpr int NL = G + 4, NH = G + 1;
+    static constexpr int PPW = 32 / N, WARPS = 4, PPB = PPW * WARPS;
+    // per-problem shared memory (doubles)
+    static constexpr int EXCH = NSTR * N + 2 * N * N + 2 * N;  // projs | Xs | Xms | lam, pad
+    __host__ __device__ static constexpr int lps_doubles(int nlos) { return nlos * 2 * NH * N; }
+    __host__ __device__ static constexpr int red_doubles(int nlos) { return nlos * (NL + 1) * N; }
+    __host__ __device__ static constexpr int per_problem(int nlos) {
+        return lps_doubles(nlos) + (red_doubles(nlos) > EXCH ? red_doubles(nlos) : EXCH);
+    }
+    // block tables: tW[NSTR][N] | tM[NSTR][N] | tL[nlos][NSTR] | lpc[NSTR] | wmu[N]
+    __host__ __device__ static constexpr int table_doubles(int nlos) { return 2 * NSTR * N + nlos * NSTR + NSTR + N; }
+    __host__ __device__ static constexpr int smem_doubles(int nlos) { return table_doubles(nlos) + PPB * per_problem(nlos); }
+};
+
+template <int N, int G>
+__global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
+    using Cf = WfCfg<N, G>;
+    constexpr int NSTR = Cf::NSTR, NL = Cf::NL, NH = Cf::NH;
+    constexpr int iTau = G, iOm = G + 1, iT = G + 2, iS = G + 3;
+    extern __shared__ __align__(16) double smem[];
+    const int L = V.T.L, M = V.M, nlos = V.T.nlos;
+    double* tW = smem;                   // [l][q]  w_q P_l^m(mu_q)
+    double* tM = tW + NSTR * N;          // [l][a]  P_l^m(mu_a) / mu_a
+    double* tL = tM + NSTR * N;          // [los][l]
+    double* lpc = tL + nlos * NSTR;      // [l]
+    double* wmu = lpc + NSTR;            // [i] w_i mu_i
+    const int ms = blockIdx.y;
+    const int m = V.m_list[ms];
+    for (int e = threadIdx.x; e < NSTR * N; e += blockDim.x) {
+        const int l = e / N, q = e % N;
+        const double lp = V.T.lp_mu[((size_t)m * N + q) * NSTR + l];
+        tW[e] = V.T.wt[q] * lp;
+        tM[e] = lp / V.T.mu[q];
+    }
+    for (int e = threadIdx.x; e < nlos * NSTR; e += blockDim.x)
+        tL[e] = V.T.lp_los[((size_t)(e / NSTR) * NSTR + m) * NSTR + (e % NSTR)];
+    if (threadIdx.x < NSTR) lpc[threadIdx.x] = V.T.lp_csz[(size_t)m * NSTR + threadIdx.x];
+    if (threadIdx.x < N) wmu[threadIdx.x] = V.T.wt[threadIdx.x] * V.T.mu[threadIdx.x];
+    __syncthreads();
+
+    const int j = threadIdx.x % N;
+    const int pib = threadIdx.x / N;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned gmask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (lane / N * N));
+    double* pp = smem + Cf::table_doubles(nlos) + (size_t)pib * Cf::per_problem(nlos);
+    double* lpsS = pp;                            // [los][2 NH][q]: minus, plus, then (d minus, d plus) per group
+    double* red = pp + Cf::lps_doubles(nlos);     // [los][NL + 1][j]   (aliases the eigen exchange area)
+    double* projs = red;                          // [lo][i]
+    double* Xs = projs + NSTR * N;                // [a][i]
+    double* Xms = Xs + N * N;                     // [a][i]
+    double* lam = Xms + N * N;                    // [i]
+
+    long long q = (long long)blockIdx.x * Cf::PPB + pib;  // w * L + p
+    const long long nq = (long long)V.nw * L;
+    const bool valid = q < nq;
+    if (!valid) q = nq - 1;
+    const int w = (int)(q / L), p = (int)(q % L);
+    const size_t idx = ((size_t)w * M + ms) * L + p;
+    const double od = V.lay_od[q], ssa = V.lay_ssa[q], secant = V.lay_secant[q];
+    const double trans_top = V.lay_trans[(size_t)w * (L + 1) + p];
+    const double* __restrict__ beta = V.lay_beta + (size_t)q * NSTR;
+    const double* __restrict__ dbeta = V.lay_dbeta + (size_t)q * G * NSTR;  // [g][l]
+    const int nl = NSTR - m;
+    const double f0 = (m == 0 ? 1.0 : 2.0) * (1.0 / (4.0 * kPi));
+
+    // ---- prologue: LOS phase sums lps-+[q] (lane q) and their eps_g derivatives for every LOS -> shared memory
+    {
+        double ob[NSTR], tq[NSTR], obd[G > 0 ? G : 1][NSTR];
+#pragma unroll
+        for (int lo = 0; lo < NSTR; ++lo) {
+            const bool in = lo < nl;
+            const int l = in ? m + lo : m;
+            ob[lo] = in ? ssa * beta[l] : 0.0;
+            tq[lo] = in ? 0.5 * tW[l * N + j] : 0.0;
+#pragma unroll
+            for (int g = 0; g < G; ++g) obd[g][lo] = in ? ssa * dbeta[g * NSTR + l] : 0.0;
+        }
+        for (int los = 0; los < nlos; ++los) {
+            const double* __restrict__ tl = tL + los * NSTR + m;
+            double a = 0.0, b = 0.0, da[G > 0 ? G : 1], db[G > 0 ? G : 1];
+#pragma unroll
+            for (int g = 0; g < G; ++g) da[g] = db[g] = 0.0;
+#pragma unroll
+            for (int c = 0; c < NSTR / 4; ++c) {
+                if (4 * c < nl) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int lo = 4 * c + r;
+                        const double x = tl[lo] * tq[lo];
+                        const double sx = (lo & 1) ? -x : x;
+                        a = fma(ob[lo], x, a);
+                        b = fma(ob[lo], sx, b);
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            da[g] = fma(obd[g][lo], x, da[g]);
+                            db[g] = fma(obd[g][lo], sx, db[g]);
+                        }
+                    }
+                }
+            }
+            double* o = lpsS + (size_t)los * 2 * NH * N;
+            o[j] = a;          // lps_minus
+            o[N + j] = b;      // lps_plus
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                o[(2 + 2 * g) * N + j] = da[g];
+                o[(3 + 2 * g) * N + j] = db[g];
+            }
+        }
+    }
+
+    // ---- column j of W+-, eigenvalue, BVP solution
+    double wp[N], wm[N];
+    {
+        const double* __restrict__ Wp = V.Wp + idx * N * N + j;
+        const double* __restrict__ Wm = V.Wm + idx * N * N + j;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            wp[i] = Wp[i * N];
+            wm[i] = Wm[i * N];
+        }
+    }
+    const double kj = V.kth[idx * 2 * N + j], thj = V.kth[idx * 2 * N + N + j];
+    const double Lj = V.xsol[idx * 2 * N + j], Mj = V.xsol[idx * 2 * N + N + j];
+    const double lamj = kj * kj;
+    double norm = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) norm = fma(wmu[i], fma(wp[i], wp[i], -wm[i] * wm[i]), norm);
+    const double inv_norm = 1.0 / norm;
+
+    // ---- pass 1: projections of X = W+ + W- (even l - m) and Xm = k (W+ - W-) (odd) -> exchange
+    double pr[NSTR];
+    {
+        const double sc_even = kj * inv_norm;  // lambda_j / n_j,  n_j = k_j norm_j
+        const double sc_odd = inv_norm / kj;   // 1 / n_j
+#pragma unroll
+        for (int lo = 0; lo < NSTR; ++lo) {
+            pr[lo] = 0.0;
+            if (lo < nl) {
+                const double* __restrict__ t = tW + (m + lo) * N;
+                double u = 0.0, v = 0.0;
+#pragma unroll
+                for (int qq = 0; qq < N; ++qq) {
+                    u = fma(t[qq], wp[qq], u);
+                    v = fma(t[qq], wm[qq], v);
+                }
+                pr[lo] = (lo & 1) ? kj * (u - v) : (u + v);
+            }
+            projs[lo * N + j] = pr[lo] * ((lo & 1) ? sc_odd : sc_even);
+        }
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+            Xs[a * N + j] = wp[a] + wm[a];
+            Xms[a * N + j] = kj * (wp[a] - wm[a]);
+        }
+        lam[j] = lamj;
+    }
+    __syncwarp();
+
+    // ---- pass 2: eigen-derivatives for the heavy lanes e = eps_0..eps_{G-1}, omega
+    double dwp[NH][N], dwm[NH][N], dk[NH];
+    {
+        double P[NH][N], dxm[NH][N];
+#pragma unroll
+        for (int e = 0; e < NH; ++e)
+#pragma unroll
+            for (int i = 0; i < N; ++i) P[e][i] = dxm[e][i] = 0.0;
+#pragma unroll
+        for (int lo = 0; lo < NSTR; ++lo) {
+            if (lo < nl) {
+                const int l = m + lo;
+                double cp[NH];
+#pragma unroll
+                for (int e = 0; e < NH; ++e) cp[e] = -pr[lo] * (e < G ? ssa * dbeta[(e < G ? e : 0) * NSTR + l] : beta[l]);
+                const double* __restrict__ ps = projs + lo * N;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double x = ps[i];
+#pragma unroll
+                    for (int e = 0; e < NH; ++e) P[e][i] = fma(cp[e], x, P[e][i]);
+                }
+                if (!(lo & 1)) {  // dS+ X: -(1/mu_a) sum_even c_l P_l(mu_a) p_l[j]
+                    const double* __restrict__ tm = tM + l * N;
+#pragma unroll
+                    for (int a = 0; a < N; ++a) {
+                        const double x = tm[a];
+#pragma unroll
+                        for (int e = 0; e < NH; ++e) dxm[e][a] = fma(cp[e], x, dxm[e][a]);
+                    }
+                }
+            }
+        }
+        // Q_ij = P_ij / (lambda_j - lambda_i), dk_j = P_jj / (2 k_j)
+        double Q[NH][N];
+#pragma unroll
+        for (int e = 0; e < NH; ++e) dk[e] = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool self = (i == j);
+            const double rden = self ? 0.0 : 1.0 / (lamj - lam[i]);
+#pragma unroll
+            for (int e = 0; e < NH; ++e) {
+                if (self) dk[e] = P[e][i] / (2.0 * kj);
+                Q[e][i] = P[e][i] * rden;
+            }
+        }
+        const double ikj = 1.0 / kj;
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+            double dx[NH];
+#pragma unroll
+            for (int e = 0; e < NH; ++e) dx[e] = 0.0;
+            const double* __restrict__ xr = Xs + a * N;
+            const double* __restrict__ xmr = Xms + a * N;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double x = xr[i], xm = xmr[i];
+#pragma unroll
+                for (int e = 0; e < NH; ++e) {
+                    dx[e] = fma(x, Q[e][i], dx[e]);
+                    dxm[e][a] = fma(xm, Q[e][i], dxm[e][a]);
+                }
+            }
+            const double xmj = wp[a] - wm[a];  // Xm_aj / k_j
+#pragma unroll
+            for (int e = 0; e < NH; ++e) {
+                const double t1 = (dxm[e][a] - xmj * dk[e]) * ikj;
+                dwp[e][a] = 0.5 * (dx[e] + t1);
+                dwm[e][a] = 0.5 * (dx[e] - t1);
+            }
+        }
+    }
+    __syncwarp();  // the exchange area is reused by the LOS reduction below
+
+    // ---- pass 3: Green's coefficients A+-_j with heavy-lane derivatives
+    double ap, am, dap[NH], dam[NH];
+    {
+        double apn = 0.0, amn = 0.0, dapn[NH], damn[NH], dnorm[NH];
+#pragma unroll
+        for (int e = 0; e < NH; ++e) dapn[e] = damn[e] = dnorm[e] = 0.0;
+#pragma unroll
+        for (int lo = 0; lo < NSTR; ++lo) {
+            if (lo < nl) {
+                const int l = m + lo;
+                const double* __restrict__ t = tW + l * N;
+                double u = 0.0, v = 0.0, du[NH], dv[NH];
+#pragma unroll
+                for (int e = 0; e < NH; ++e) du[e] = dv[e] = 0.0;
+#pragma unroll
+                for (int qq = 0; qq < N; ++qq) {
+                    const double x = t[qq];
+                    u = fma(x, wp[qq], u);
+                    v = fma(x, wm[qq], v);
+#pragma unroll
+                    for (int e = 0; e < NH; ++e) {
+                        du[e] = fma(x, dwp[e][qq], du[e]);
+                        dv[e] = fma(x, dwm[e][qq], dv[e]);
+                    }
+                }
+                const double bl = beta[l], lc = lpc[l];
+                const double c = ssa * bl * lc;
+                const double s1 = (lo & 1) ? (u - v) : (u + v);   // u + s v
+                const double s2 = (lo & 1) ? (v - u) : (u + v);   // s u + v
+                apn = fma(c, s1, apn);
+                amn = fma(c, s2, amn);
+#pragma unroll
+                for (int e = 0; e < NH; ++e) {
+                    const double dc = (e < G ? ssa * dbeta[(e < G ? e : 0) * NSTR + l] : bl) * lc;
+                    const double d1 = (lo & 1) ? (du[e] - dv[e]) : (du[e] + dv[e]);
+                    const double d2 = (lo & 1) ? (dv[e] - du[e]) : (du[e] + dv[e]);
+                    dapn[e] = fma(dc, s1, fma(c, d1, dapn[e]));
+                    damn[e] = fma(dc, s2, fma(c, d2, damn[e]));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int e = 0; e < NH; ++e)
+                dnorm[e] = fma(2.0 * wmu[i], fma(wp[i], dwp[e][i], -wm[i] * dwm[e][i]), dnorm[e]);
+        ap = f0 * apn * inv_norm;
+        am = f0 * amn * inv_norm;
+#pragma unroll
+        for (int e = 0; e < NH; ++e) {
+            dap[e] = (f0 * dapn[e] - ap * dnorm[e]) * inv_norm;
+            dam[e] = (f0 * damn[e] - am * dnorm[e]) * inv_norm;
+        }
+    }
+
+    // ---- scalars of solution j with partials (k, tau, s); everything particular is linear in t
+    const double exp_sec = exp(-od * secant);
+    const R3 psk = psi_dual(od, kj, secant, thj, exp_sec);
+    R3 Cp, Cm;
+    if (fabs(secant - kj) > kGreensEps) {
+        Cp.v = trans_top * od * psk.v;
+        Cp.k = trans_top * od * psk.k;
+        Cp.a = trans_top * fma(od, psk.a, psk.v);
+        Cp.s = trans_top * od * psk.s;
+    } else {
+        const double g = 1.0 - 0.5 * od * (secant - kj);
+        Cp.v = trans_top * thj * od * g;
+        Cp.k = trans_top * od * thj * (0.5 * od - od * g);
+        Cp.a = trans_top * thj * (g + od * (-kj * g - 0.5 * (secant - kj)));
+        Cp.s = -0.5 * trans_top * od * od * thj;
+    }
+    {
+        const double est = exp_sec * thj, ispk = 1.0 / (secant + kj);
+        Cm.v = trans_top * (1.0 - est) * ispk;
+        Cm.k = (trans_top * od * est - Cm.v) * ispk;
+        Cm.a = trans_top * est;
+        Cm.s = Cm.k;
+    }
+    const double amc = am * Cm.v, apc = ap * Cp.v;
+    const double Aj = fma(thj, Mj, amc), Bj = fma(thj, Lj, apc);
+    // dA, dB per output lane [eps.. | tau | omega | t | s]
+    double dA[NL], dB[NL];
+#pragma unroll
+    for (int e = 0; e < NH; ++e) {
+        const int ln = e < G ? e : iOm;
+        const double dth = -od * thj * dk[e];
+        dA[ln] = fma(Mj, dth, fma(dam[e], Cm.v, am * Cm.k * dk[e]));
+        dB[ln] = fma(Lj, dth, fma(dap[e], Cp.v, ap * Cp.k * dk[e]));
+    }
+    dA[iTau] = fma(Mj, -kj * thj, am * Cm.a);
+    dB[iTau] = fma(Lj, -kj * thj, ap * Cp.a);
+    dA[iS] = am * Cm.s;
+    dB[iS] = ap * Cp.s;
+    dA[iT] = amc / trans_top;
+    dB[iT] = apc / trans_top;
+
+    const bool bottom = (p == L - 1);
+    const bool refl = bottom && (m == 0);
+    const double albedo = V.albedo[w];
+    const double t_floor = V.lay_trans[(size_t)w * (L + 1) + L];
+    const double inv_spk = 1.0 / (secant + kj);
+    // this lane's share of the single-scatter phase sum Q (l' = 2j, 2j+1) and its heavy-lane derivatives
+    double cq0[NH + 1], cq1[NH + 1];  // [value, d eps_g.., d omega]
+    {
+        const bool i0 = 2 * j < nl, i1 = 2 * j + 1 < nl;
+        const int l0 = i0 ? m + 2 * j : m, l1 = i1 ? m + 2 * j + 1 : m;
+        const double b0 = i0 ? beta[l0] * lpc[l0] : 0.0, b1 = i1 ? -beta[l1] * lpc[l1] : 0.0;
+        cq0[0] = ssa * b0;
+        cq1[0] = ssa * b1;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            cq0[1 + g] = i0 ? ssa * dbeta[g * NSTR + l0] * lpc[l0] : 0.0;
+            cq1[1 + g] = i1 ? -ssa * dbeta[g * NSTR + l1] * lpc[l1] : 0.0;
+        }
+        cq0[NH] = b0;
+        cq1[NH] = b1;
+    }
+    const size_t nrow = (size_t)2 * N * L;
+    double gsum_v = 0.0;
+    if (refl) {  // 2 sG + 2 sum_j (s+_j theta_j L_j + s-_j M_j), rare
+        const double* surf = V.surf + (size_t)w * (2 * N + 1);
+        double s = fma(surf[j] * thj, Lj, surf[N + j] * Mj);
+#pragma unroll
+        for (int off = N / 2; off > 0; off >>= 1) s += __shfl_xor_sync(gmask, s, off);
+        gsum_v = 2.0 * (surf[2 * N] + s);
+    }
+
+    for (int los = 0; los < nlos; ++los) {
+        const double mu = V.T.los_mu[los];
+        const double* __restrict__ ll = V.los_lay + (((size_t)w * nlos + los) * L + p) * 3;
+        const double att = ll[0], E = ll[1], inv_1mus = ll[2];
+        const double att_top = V.los_att[((size_t)w * nlos + los) * (L + 1) + p];
+        // -- source part: Y+-_j and heavy-lane derivatives from the shared phase sums
+        const double* __restrict__ ls = lpsS + (size_t)los * 2 * NH * N;
+        double Yp = 0.0, Ym = 0.0, dYp[NH], dYm[NH];
+#pragma unroll
+        for (int e = 0; e < NH; ++e) dYp[e] = dYm[e] = 0.0;
+#pragma unroll
+        for (int qq = 0; qq < N; ++qq) {
+            const double a = ls[qq], b = ls[N + qq];  // lps_minus, lps_plus
+            Yp = fma(b, wp[qq], fma(a, wm[qq], Yp));
+            Ym = fma(b, wm[qq], fma(a, wp[qq], Ym));
+#pragma unroll
+            for (int e = 0; e < NH; ++e) {
+                dYp[e] = fma(b, dwp[e][qq], fma(a, dwm[e][qq], dYp[e]));
+                dYm[e] = fma(b, dwm[e][qq], fma(a, dwp[e][qq], dYm[e]));
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const double da = ls[(2 + 2 * g) * N + qq], db = ls[(3 + 2 * g) * N + qq];
+                dYp[g] = fma(db, wp[qq], fma(da, wm[qq], dYp[g]));
+                dYm[g] = fma(db, wm[qq], fma(da, wp[qq], dYm[g]));
+            }
+        }
+        {
+            const double iw = 1.0 / ssa;
+            dYp[G] = fma(Yp, iw, dYp[G]);
+            dYm[G] = fma(Ym, iw, dYm[G]);
+        }
+        // -- multipliers with partials (k, tau, s)
+        const double tha = thj * att;
+        R3 hp, hm, Dp, Dm;
+        {
+            const double iden = div_fast(1.0, 1.0 + mu * kj);
+            hp.v = (1.0 - tha) * iden;
+            hp.k = (od * tha - hp.v * mu) * iden;
+            hp.a = (kj + 1.0 / mu) * tha * iden;
+        }
+        {
+            const double den = 1.0 - mu * kj;
+            const double imu = 1.0 / mu;
+            if (fabs(den) > 0.0001) {
+                const R3 ps = psi_dual(od, kj, imu, thj, att);
+                hm.v = od * imu * ps.v;
+                hm.k = od * imu * ps.k;
+                hm.a = imu * fma(od, ps.a, ps.v);
+            } else {
+                const double g = 1.0 - od * (kj - imu);
+                hm.v = thj * od * imu * g;
+                hm.k = od * imu * (-od * thj * g - od * thj);
+                hm.a = imu * thj * g + od * imu * (-kj * thj * g - thj * (kj - imu));
+            }
+        }
+        const double esa = exp_sec * att;
+        const double E_a = trans_top * inv_1mus * (secant + 1.0 / mu) * esa;
+        const double E_s = fma(-mu * inv_1mus, E, trans_top * inv_1mus * od * esa);
+        {
+            const double tes = trans_top * exp_sec;
+            const double F_k = tes * hm.k;
+            const double F_a = tes * fma(-secant, hm.v, hm.a);
+            const double F_s = -od * tes * hm.v;
+            Dp.v = (E - tes * hm.v) * inv_spk;
+            Dp.k = (-F_k - Dp.v) * inv_spk;
+            Dp.a = (E_a - F_a) * inv_spk;
+            Dp.s = (E_s - F_s - Dp.v) * inv_spk;
+        }
+        {
+            const double H_v = od * att * psk.v;
+            const double H_k = od * att * psk.k;
+            const double H_a = att * (psk.v - od / mu * psk.v + od * psk.a);
+            const double H_s = od * att * psk.s;
+            const double ti = trans_top * inv_1mus;
+            Dm.v = ti * (mu * hp.v - H_v);
+            Dm.k = ti * (mu * hp.k - H_k);
+            Dm.a = ti * (mu * hp.a - H_a);
+            Dm.s = -ti * H_s - mu * inv_1mus * Dm.v;
+        }
+        const double* __restrict__ tl = tL + los * NSTR + m;
+        const double t0 = tl[2 * j], t1 = tl[2 * j + 1];
+        const double Qj = V.include_ss ? f0 * fma(cq0[0], t0, cq1[0] * t1) : 0.0;
+        const double alp = fma(hp.v, Lj, ap * Dm.v), alm = fma(hm.v, Mj, am * Dp.v);
+        const double srcj = fma(Yp, alp, fma(Ym, alm, Qj * E));
+        const double Sk = fma(Yp, fma(Lj, hp.k, ap * Dm.k), Ym * fma(Mj, hm.k, am * Dp.k));
+        double out[NL];
+        out[iTau] = fma(Yp, fma(Lj, hp.a, ap * Dm.a), fma(Ym, fma(Mj, hm.a, am * Dp.a), Qj * E_a));
+        out[iS] = fma(Yp * ap, Dm.s, fma(Ym * am, Dp.s, Qj * E_s));
+        out[iT] = fma(Yp * ap, Dm.v, fma(Ym * am, Dp.v, Qj * E)) / trans_top;
+#pragma unroll
+        for (int e = 0; e < NH; ++e) {
+            const int ln = e < G ? e : iOm;
+            const double dQ = V.include_ss ? f0 * fma(cq0[1 + e], t0, cq1[1 + e] * t1) : 0.0;
+            out[ln] = fma(dYp[e], alp, fma(dYm[e], alm, fma(Yp * Dm.v, dap[e], fma(Ym * Dp.v, dam[e], fma(dk[e], Sk, dQ * E)))));
+        }
+#pragma unroll
+        for (int c = 0; c < NL; ++c) out[c] *= att_top;
+
+        // -- adjoint part: zeta slices of z on the two boundaries of the layer
+        const double* __restrict__ z = V.zadj + (((size_t)w * M + ms) * nlos + los) * nrow;
+        const double* __restrict__ zt = (p == 0) ? z : z + N + (size_t)(p - 1) * 2 * N;
+        const double* __restrict__ zb = z + N + (size_t)p * 2 * N;
+        double zg_sum = 0.0;
+        if (bottom) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) zg_sum += zb[i];
+        }
+        const double attg = bottom ? V.los_att[((size_t)w * nlos + los) * (L + 1) + L] : 0.0;
+        double s21 = 0.0, s34 = 0.0;          // W+.zeta2 + W-.zeta1,  W+.zeta3 + W-.zeta4
+        double dadj[NH];
+#pragma unroll
+        for (int e = 0; e < NH; ++e) dadj[e] = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double z1, z2, z3, z4;
+            if (p == 0) {
+                z1 = -zt[i];
+                z2 = 0.0;
+            } else {
+                z2 = zt[i];
+                z1 = zt[N + i];
+            }
+            z4 = -zb[i];
+            if (!bottom)
+                z3 = -zb[N + i];
+            else
+                z3 = refl ? 2.0 * wmu[i] * albedo * (zg_sum + attg) : 0.0;
+            const double xp = fma(Lj, z1, fma(Aj, z2, fma(Bj, z3, Mj * z4)));
+            const double xm = fma(Aj, z1, fma(Lj, z2, fma(Mj, z3, Bj * z4)));
+            s21 = fma(wp[i], z2, fma(wm[i], z1, s21));
+            s34 = fma(wp[i], z3, fma(wm[i], z4, s34));
+#pragma unroll
+            for (int e = 0; e < NH; ++e) dadj[e] = fma(dwp[e][i], xp, fma(dwm[e][i], xm, dadj[e]));
+        }
+#pragma unroll
+        for (int c = 0; c < NL; ++c) out[c] = fma(dA[c], s21, fma(dB[c], s34, out[c]));
+#pragma unroll
+        for (int e = 0; e < NH; ++e) out[e < G ? e : iOm] += dadj[e];
+        // -- partials of this solution -> reduction buffer
+        double* r = red + (size_t)los * (NL + 1) * N;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) r[c * N + j] = out[c];
+        r[NL * N + j] = srcj * att_top;
+        if (refl && j == 0 && valid) {
+            const double direct = V.include_ss ? V.T.csz / kPi * t_floor : 0.0;
+            double* gnd = V.wf_gnd + ((size_t)w * nlos + los) * 3;
+            gnd[0] = attg * (direct + gsum_v) + zg_sum * (V.T.csz * t_floor / kPi + gsum_v);
+            gnd[1] = (V.include_ss ? attg * albedo * V.T.csz / kPi : 0.0) + zg_sum * V.T.csz * albedo / kPi;
+            gnd[2] = attg * albedo * (direct + gsum_v);
+        }
+    }
+    __syncwarp();
+    // ---- sum over the solutions j and store: rows (los, c) are dealt round-robin to the problem's lanes
+    if (valid) {
+        const int nrows = nlos * (NL + 1);
+        for (int row = j; row < nrows; row += N) {
+            const double* r = red + (size_t)row * N;
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) s += r[i];
+            const int los = row / (NL + 1), c = row % (NL + 1);
+            const size_t o = (((size_t)w * M + ms) * nlos + los) * L + p;
+            if (c < NL)
+                V.wf_loc[o * NL + c] = s;
+            else
+                V.wf_src[o] = s;
+        }
+    }
+}
+
+}  // namespace disco

@@ -14,6 +14,8 @@ void launch_layer_solve(const ChunkView& V, cudaStream_t s);
 // register-resident path for N = 2, 4, 8 (disco_fast*.cuh); needs the eig*/los_* planes and vsrc_w = N
 bool fast_path_supported(int N);
 void launch_layer_solve_fast(const ChunkView& V, cudaStream_t s);
+void launch_wf_layer_fast(const ChunkView& V, cudaStream_t s);
+size_t wf_layer_fast_smem_bytes(int N, int G, int nlos);
 void launch_bvp(const ChunkView& V, cudaStream_t s);
 void launch_bvp_adjoint(const ChunkView& V, cudaStream_t s);
 struct MappingView;

@@ -208,6 +208,227 @@ __device__ __forceinline__ void staircase_solve(const Prob& prob, double* gs, do
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Version 2 of the staircase solve for 3N <= lanes per group (N = 1, 2, 4, 8), one panel row per lane:
+//   * pivot search in 3 instructions: REDUX.MAX over the high words of |a_c| (non-negative doubles order like
+//     their bit patterns), ballot, find-first-set.  The pivot is the largest candidate up to the 2^-20 resolution
+//     of the high word - threshold partial pivoting with threshold 1 - 1e-6, the same candidate set as LAPACK's
+//     dgbtf2 (kl = ku = 3N - 1);
+//   * the pivot row goes to shared memory once: the per-column rows of the step's factor block double as the
+//     broadcast buffer (uniform LDS.128 for the rank-1 update, 2 DFMA per load) and are flushed to HBM coalesced at
+//     the end of the step together with 1/pivot, so the back substitution does not divide;
+//   * back substitution: one right-hand side - lane c owns pivot row c, x broadcast by shuffle; several right-hand
+//     sides (adjoint, one per line of sight) - lane r owns right-hand side r and runs the whole block solve from
+//     uniform shared-memory loads, no shuffles (a 64-bit shuffle costs 4 DFMA issue slots on B200).
+// Factor layout in HBM: fac[step][c][FS], FS = even(4N + NRHS) + 2, entry FS - 2 = 1 / pivot; entries left of the
+// diagonal are unspecified.
+// -------------------------------------------------------------------------------------------------
+template <int N, int NRHS>
+struct BvpCfg2 {
+    static constexpr int NC = 2 * N;
+    static constexpr int ROWS = 3 * N;
+    static constexpr int GL = ROWS <= 4 ? 4 : (ROWS <= 8 ? 8 : (ROWS <= 16 ? 16 : 32));
+    static constexpr int ROWLEN = 4 * N + NRHS;
+    static constexpr int RL2 = (ROWLEN + 1) & ~1;
+    static constexpr int FS = RL2 + 2;                    // row stride: padded row | 1/pivot | pad
+    static constexpr int GROUPS_PER_WARP = 32 / GL;
+    static constexpr int WARPS_PER_BLOCK = 4;
+    static constexpr int GROUPS_PER_BLOCK = GROUPS_PER_WARP * WARPS_PER_BLOCK;
+    static constexpr int SMEM_DOUBLES_PER_GROUP = NC * FS + NC;   // factor block | x of the block below (NRHS = 1)
+    static_assert(ROWS <= GL, "one panel row per lane");
+};
+
+template <int N, class Prob>
+__device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs, double* fac, int lane, unsigned gbase,
+                                                   unsigned gmask, bool valid, unsigned int* status) {
+    constexpr int NRHS = Prob::NRHS;
+    using C = BvpCfg2<N, NRHS>;
+    constexpr int NC = C::NC, GL = C::GL, ROWLEN = C::ROWLEN, RL2 = C::RL2, FS = C::FS;
+    double* facs = gs;            // [NC][FS]
+    double* xs = gs + NC * FS;    // [NC]
+    const unsigned lane_bit = 1u << (gbase + lane);
+    const unsigned lt_mask = (lane_bit - 1u) & gmask;
+
+    double a[ROWLEN];
+#pragma unroll
+    for (int c = 0; c < ROWLEN; ++c) a[c] = 0.0;
+    bool act = false, singular = false;
+    const int nsteps = prob.nsteps();
+
+    for (int step = 0; step < nsteps; ++step) {
+        {   // new rows of this step go to the lowest free lanes
+            const unsigned freeb = __ballot_sync(gmask, !act) & gmask;
+            const int rank = __popc(freeb & lt_mask);
+            if (!act && rank < prob.nnew(step)) {
+                act = true;
+                prob.load(step, rank, a);
+            }
+        }
+        const int nleft = prob.nleft(step);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (c < nleft) {
+                const unsigned key = act ? (unsigned)__double2hiint(fabs(a[c])) : 0u;
+                const unsigned mx = __reduce_max_sync(gmask, key);
+                const unsigned cand = __ballot_sync(gmask, act && key == mx);
+                if (mx == 0u) singular = true;
+                double* bc = facs + c * FS;
+                if (act && (cand & lt_mask) == 0u && (cand & lane_bit)) {  // lowest candidate lane = pivot row
+                    act = false;
+                    const int c0 = c & ~1;
+#pragma unroll
+                    for (int cc = c0; cc < RL2; cc += 2) {
+                        const double v0 = (cc < ROWLEN) ? a[cc < ROWLEN ? cc : 0] : 0.0;
+                        const double v1 = (cc + 1 < ROWLEN) ? a[cc + 1 < ROWLEN ? cc + 1 : 0] : 0.0;
+                        *reinterpret_cast<double2*>(bc + cc) = make_double2(v0, v1);
+                    }
+                    bc[RL2] = 1.0 / a[c];
+                }
+                __syncwarp(gmask);
+                if (act) {
+                    const double f = a[c] * bc[RL2];
+#pragma unroll
+                    for (int cc = c + 1; cc < ROWLEN; ++cc) a[cc] = fma(-f, bc[cc], a[cc]);
+                    a[c] = 0.0;
+                }
+            }
+        }
+        __syncwarp(gmask);
+        if (valid) {
+            double* dst = fac + (size_t)step * NC * FS;
+            for (int e = lane; e < nleft * FS; e += GL) dst[e] = facs[e];
+        }
+        __syncwarp(gmask);
+        if (step < nsteps - 1) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                a[j] = a[NC + j];
+                a[NC + j] = 0.0;
+            }
+        }
+    }
+    if (singular && valid) atomicOr(status, 4u);
+
+    if (NRHS == 1) {
+        // ---- lane c owns pivot row c of the block; x of the block below sits in xs
+        for (int step = nsteps - 1; step >= 0; --step) {
+            const int nleft = prob.nleft(step);
+            const int nright = prob.nright(step);
+            if (step < nsteps - 1) {
+                const double* src = fac + (size_t)step * NC * FS;
+                for (int e = lane; e < nleft * FS; e += GL) facs[e] = src[e];
+                __syncwarp(gmask);
+            }
+            const int row = lane < nleft ? lane : 0;
+            const double* my = facs + row * FS;
+            double acc = my[4 * N];
+            for (int jx = 0; jx < nright; ++jx) acc = fma(-my[NC + jx], xs[jx], acc);
+            const double pinv = my[RL2];
+            double myx = 0.0;
+#pragma unroll
+            for (int cc = NC - 1; cc >= 0; --cc) {
+                if (cc < nleft) {
+                    double xv = acc * pinv;
+                    xv = __shfl_sync(gmask, xv, (int)gbase + cc);
+                    if (lane < cc) acc = fma(-my[cc], xv, acc);
+                    if (lane == cc) myx = xv;
+                }
+            }
+            __syncwarp(gmask);
+            if (lane < nleft) {
+                xs[lane] = myx;
+                if (valid) prob.store(step, lane, 0, myx);
+            }
+            __syncwarp(gmask);
+        }
+    } else {
+        // ---- lane r owns right-hand side r: the whole block solve from uniform shared-memory loads
+        const int r = lane < NRHS ? lane : 0;
+        double xn[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) xn[c] = 0.0;
+        for (int step = nsteps - 1; step >= 0; --step) {
+            const int nleft = prob.nleft(step);
+            const int nright = prob.nright(step);
+            if (step < nsteps - 1) {
+                const double* src = fac + (size_t)step * NC * FS;
+                for (int e = lane; e < nleft * FS; e += GL) facs[e] = src[e];
+                __syncwarp(gmask);
+            }
+            double acc[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                acc[c] = 0.0;
+                if (c < nleft) {
+                    const double* u = facs + c * FS;
+                    double s = u[4 * N + r];
+#pragma unroll
+                    for (int jx = 0; jx < NC; ++jx)
+                        if (jx < nright) s = fma(-u[NC + jx], xn[jx], s);
+                    acc[c] = s;
+                }
+            }
+#pragma unroll
+            for (int cc = NC - 1; cc >= 0; --cc) {
+                if (cc < nleft) {
+                    const double xv = acc[cc] * facs[cc * FS + RL2];
+                    acc[cc] = xv;
+#pragma unroll
+                    for (int c = 0; c < cc; ++c) acc[c] = fma(-facs[c * FS + cc], xv, acc[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                xn[c] = acc[c];
+                if (valid && lane < NRHS && c < nleft) prob.store(step, c, r, acc[c]);
+            }
+            __syncwarp(gmask);
+        }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32) k_bvp_v2(ChunkView V) {
+    using C = BvpCfg2<N, 1>;
+    extern __shared__ __align__(16) double smem[];
+    const int lane_w = threadIdx.x & 31;
+    const int gidx_in_block = threadIdx.x / C::GL;
+    const int lane = threadIdx.x % C::GL;
+    const unsigned gbase = (unsigned)((lane_w / C::GL) * C::GL);
+    const unsigned gmask = (C::GL == 32) ? FULL_MASK : (((1u << C::GL) - 1u) << gbase);
+    long long prob = (long long)blockIdx.x * C::GROUPS_PER_BLOCK + gidx_in_block;
+    const long long nprob = (long long)V.nw * V.M;
+    const bool valid = prob < nprob;
+    if (!valid) prob = nprob - 1;
+    const int w = (int)(prob / V.M), ms = (int)(prob % V.M);
+    ForwardRows<N> rows(V, w, ms);
+    double* fac = V.fac + (size_t)prob * V.fac_stride;
+    staircase_solve_v2<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
+                          V.status);
+}
+
+template <int N, int NRHS>
+__global__ void __launch_bounds__(BvpCfg2<N, NRHS>::WARPS_PER_BLOCK * 32) k_bvp_adjoint_v2(ChunkView V, int los0, int nbatch) {
+    using C = BvpCfg2<N, NRHS>;
+    extern __shared__ __align__(16) double smem[];
+    const int lane_w = threadIdx.x & 31;
+    const int gidx_in_block = threadIdx.x / C::GL;
+    const int lane = threadIdx.x % C::GL;
+    const unsigned gbase = (unsigned)((lane_w / C::GL) * C::GL);
+    const unsigned gmask = (C::GL == 32) ? FULL_MASK : (((1u << C::GL) - 1u) << gbase);
+    long long gid = (long long)blockIdx.x * C::GROUPS_PER_BLOCK + gidx_in_block;
+    const long long ngroups = (long long)V.nw * V.M * nbatch;
+    const bool valid = gid < ngroups;
+    if (!valid) gid = ngroups - 1;
+    const int batch = (int)(gid % nbatch);
+    const long long prob = gid / nbatch;
+    const int w = (int)(prob / V.M), ms = (int)(prob % V.M);
+    AdjointRows<N, NRHS> rows(V, w, ms, los0 + batch * NRHS);
+    double* fac = V.fac + (size_t)gid * V.fac_stride;
+    staircase_solve_v2<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
+                          V.status);
+}
+
 template <int N>
 __global__ void __launch_bounds__(BvpCfg<N, 1>::WARPS_PER_BLOCK * 32) k_bvp(ChunkView V) {
     using C = BvpCfg<N, 1>;
@@ -253,28 +474,51 @@ __global__ void __launch_bounds__(BvpCfg<N, NRHS>::WARPS_PER_BLOCK * 32) k_bvp_a
 
 template <int N>
 static void launch_bvp_n(const ChunkView& V, cudaStream_t s) {
-    using C = BvpCfg<N, 1>;
     const long long nprob = (long long)V.nw * V.M;
-    const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_bvp<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+    if constexpr (3 * N <= 32) {
+        using C = BvpCfg2<N, 1>;
+        const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_bvp_v2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        k_bvp_v2<N><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
+    } else {
+        using C = BvpCfg<N, 1>;
+        const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_bvp<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        k_bvp<N><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
     }
-    k_bvp<N><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
 }
 template <int N, int NRHS>
 static void launch_adj_batch(const ChunkView& V, int los0, int nbatch, cudaStream_t s) {
-    using C = BvpCfg<N, NRHS>;
     const long long ngroups = (long long)V.nw * V.M * nbatch;
-    const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_bvp_adjoint<N, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+    if constexpr (3 * N <= 32) {
+        using C = BvpCfg2<N, NRHS>;
+        const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_bvp_adjoint_v2<N, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        k_bvp_adjoint_v2<N, NRHS><<<(unsigned)((ngroups + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK),
+                                    C::WARPS_PER_BLOCK * 32, smem, s>>>(V, los0, nbatch);
+    } else {
+        using C = BvpCfg<N, NRHS>;
+        const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_bvp_adjoint<N, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        k_bvp_adjoint<N, NRHS><<<(unsigned)((ngroups + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK),
+                                 C::WARPS_PER_BLOCK * 32, smem, s>>>(V, los0, nbatch);
     }
-    k_bvp_adjoint<N, NRHS><<<(unsigned)((ngroups + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK),
-                             C::WARPS_PER_BLOCK * 32, smem, s>>>(V, los0, nbatch);
 }
 // Lines of sight are solved in batches of NRHS right-hand sides per factorisation of A^T (a partially filled
 // last batch carries zero columns): 4 when there are at most 4 lines of sight, else 10.

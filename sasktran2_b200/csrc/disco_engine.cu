@@ -130,10 +130,10 @@ size_t DeviceEngine::workspace_bytes_per_wavelength() const {
     if (m_fast) d += 3 * (N * (N + 1) / 2) * M * L + nlos * (L + 1) + nlos * L * 3;  // eigen planes, LOS exponentials
     d += M * L * 2 * N;                                             // x
     if (!m_wf_on) {
-        d += M * (L + 1) * 2 * N * (4 * N + 1);                     // LU pivot rows (forward solve)
+        d += M * bvp_fac_stride((int)N, 1, (int)L);                  // LU pivot rows (forward solve)
     } else {
         const size_t G = m_ngroups, nrhs = adjoint_max_rhs((int)nlos), ngrp = adjoint_groups_per_problem((int)nlos);
-        d += M * ngrp * (L + 1) * 2 * N * (4 * N + nrhs);           // LU pivot rows (forward and adjoint)
+        d += M * ngrp * bvp_fac_stride((int)N, (int)nrhs, (int)L);   // LU pivot rows (forward and adjoint)
         d += M * nlos * 2 * N * L;                                  // adjoint solutions
         d += L * G * nstr;                                          // Legendre derivative directions
         d += M * nlos * L * (G + 4) + M * nlos * L + nlos * 3;      // local lanes, sources, ground terms
@@ -189,13 +189,13 @@ void DeviceEngine::ensure_workspace(int chunk) {
     }
     V.xsol = A("xsol", c * M * L * 2 * N);
     if (!m_wf_on) {
-        V.fac_stride = (L + 1) * 2 * N * (4 * N + 1);
+        V.fac_stride = bvp_fac_stride((int)N, 1, (int)L);
         V.fac = A("fac", c * M * V.fac_stride);
         V.zadj = nullptr;
         V.lay_dbeta = V.wf_loc = V.wf_src = V.wf_gnd = V.wf_native = V.wf_scratch = nullptr;
     } else {
         const size_t G = m_ngroups, nrhs = adjoint_max_rhs((int)nlos), ngrp = adjoint_groups_per_problem((int)nlos);
-        V.fac_stride = (L + 1) * 2 * N * (4 * N + nrhs);
+        V.fac_stride = bvp_fac_stride((int)N, (int)nrhs, (int)L);
         V.fac = A("fac", c * M * ngrp * V.fac_stride);
         V.zadj = A("zadj", c * M * nlos * 2 * N * L);
         V.lay_dbeta = A("lay_dbeta", c * L * G * nstr);

@@ -212,6 +212,13 @@ void launch_wf_surface(const ChunkView& V, const double* d_brdf, double* out, in
 }
 int adjoint_groups_per_problem(int nlos) { const int r = adj_rhs_for(nlos); return (nlos + r - 1) / r; }
 int adjoint_max_rhs(int nlos) { return adj_rhs_for(nlos); }
+// doubles of factor storage per solve group: (L+1) blocks of 2N pivot rows; the one-row-per-lane solver (3N <= 32)
+// pads the rows to an even length and appends 1/pivot (BvpCfg2::FS in disco_bvp.cuh)
+size_t bvp_fac_stride(int N, int nrhs, int L) {
+    const size_t rowlen = 4 * (size_t)N + nrhs;
+    const size_t fs = (3 * N <= 32) ? (((rowlen + 1) & ~(size_t)1) + 2) : rowlen;
+    return (size_t)(L + 1) * 2 * N * fs;
+}
 void launch_radiance(const ChunkView& V, cudaStream_t s) {
     const long long n = (long long)V.nw * V.T.nlos;  // warps
     k_radiance<<<(unsigned)((n + 3) / 4), 128, 0, s>>>(V);

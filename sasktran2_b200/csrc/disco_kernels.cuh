@@ -25,6 +25,7 @@ void launch_wf_map(const ChunkView& V, const MappingView& Mp, int w0, int nw_tot
 void launch_wf_surface(const ChunkView& V, const double* d_brdf, double* out, int w0, cudaStream_t s);
 int adjoint_groups_per_problem(int nlos);
 int adjoint_max_rhs(int nlos);
+size_t bvp_fac_stride(int N, int nrhs, int L);
 void launch_radiance(const ChunkView& V, cudaStream_t s);
 bool nstr_supported(int nstr);
 double measure_fp64_tflops();

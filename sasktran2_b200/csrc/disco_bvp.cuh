@@ -234,9 +234,24 @@ struct BvpCfg2 {
     static constexpr int GROUPS_PER_WARP = 32 / GL;
     static constexpr int WARPS_PER_BLOCK = 4;
     static constexpr int GROUPS_PER_BLOCK = GROUPS_PER_WARP * WARPS_PER_BLOCK;
-    static constexpr int SMEM_DOUBLES_PER_GROUP = NC * FS + NC;   // factor block | x of the block below (NRHS = 1)
+    // factor blocks resident during the back substitution: the one being solved + 2 (1 for the long multi-RHS steps) in flight
+    static constexpr int STAGES = (NRHS == 1) ? 3 : 2;
+    static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS + NC;   // factor block ring | x of the block below (NRHS = 1)
     static_assert(ROWS <= GL, "one panel row per lane");
 };
+
+// 1/x without the library's slow-path call on the critical path of every pivot: MUFU seed, two Newton steps and
+// a residual correction (0 or denormal pivots give inf/garbage; those systems are flagged singular anyway)
+__device__ __forceinline__ double rcp_pivot(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
 
 template <int N, class Prob>
 __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs, double* fac, int lane, unsigned gbase,
@@ -244,8 +259,10 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
     constexpr int NRHS = Prob::NRHS;
     using C = BvpCfg2<N, NRHS>;
     constexpr int NC = C::NC, GL = C::GL, ROWLEN = C::ROWLEN, RL2 = C::RL2, FS = C::FS;
-    double* facs = gs;            // [NC][FS]
-    double* xs = gs + NC * FS;    // [NC]
+    constexpr int CPL = (NC * FS + GL - 1) / GL;  // factor-block elements per lane
+    constexpr int STAGES = C::STAGES;
+    double* ring = gs;                     // [STAGES][NC][FS]; block of step s lives in slot s % STAGES
+    double* xs = gs + STAGES * NC * FS;    // [NC]
     const unsigned lane_bit = 1u << (gbase + lane);
     const unsigned lt_mask = (lane_bit - 1u) & gmask;
 
@@ -264,7 +281,9 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
                 prob.load(step, rank, a);
             }
         }
+        if (step + 1 < nsteps) prob.prefetch(step + 1, lane);  // next step's rows -> L1 while this block is eliminated
         const int nleft = prob.nleft(step);
+        double* facs = ring + (step % STAGES) * NC * FS;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             if (c < nleft) {
@@ -282,7 +301,7 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
                         const double v1 = (cc + 1 < ROWLEN) ? a[cc + 1 < ROWLEN ? cc + 1 : 0] : 0.0;
                         *reinterpret_cast<double2*>(bc + cc) = make_double2(v0, v1);
                     }
-                    bc[RL2] = 1.0 / a[c];
+                    bc[RL2] = rcp_pivot(a[c]);
                 }
                 __syncwarp(gmask);
                 if (act) {
@@ -294,9 +313,16 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
             }
         }
         __syncwarp(gmask);
-        if (valid) {
-            double* dst = fac + (size_t)step * NC * FS;
-            for (int e = lane; e < nleft * FS; e += GL) dst[e] = facs[e];
+        {
+            double tmp[CPL];
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) tmp[i] = facs[(lane + i * GL) < NC * FS ? lane + i * GL : 0];
+            if (valid) {
+                double* dst = fac + (size_t)step * NC * FS;
+#pragma unroll
+                for (int i = 0; i < CPL; ++i)
+                    if (lane + i * GL < nleft * FS) dst[lane + i * GL] = tmp[i];
+            }
         }
         __syncwarp(gmask);
         if (step < nsteps - 1) {
@@ -309,16 +335,35 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
     }
     if (singular && valid) atomicOr(status, 4u);
 
+    // factor blocks come back from HBM through a 3-slot cp.async ring: while block s is solved, blocks s-1 and
+    // s-2 are in flight (16 bytes per lane per copy, no registers)
+    auto fetch_block = [&](int step) {
+        if (step >= 0) {
+            const double* src = fac + (size_t)step * NC * FS;
+            double* dst = ring + (step % STAGES) * NC * FS;
+#pragma unroll
+            for (int i = 0; i < (NC * FS / 2 + GL - 1) / GL; ++i) {
+                const int e = 2 * (lane + i * GL);
+                if (e < NC * FS) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + e) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    __syncwarp(gmask);
+#pragma unroll
+    for (int k = 2; k <= STAGES; ++k) fetch_block(nsteps - k);
+
     if (NRHS == 1) {
         // ---- lane c owns pivot row c of the block; x of the block below sits in xs
         for (int step = nsteps - 1; step >= 0; --step) {
             const int nleft = prob.nleft(step);
             const int nright = prob.nright(step);
-            if (step < nsteps - 1) {
-                const double* src = fac + (size_t)step * NC * FS;
-                for (int e = lane; e < nleft * FS; e += GL) facs[e] = src[e];
-                __syncwarp(gmask);
-            }
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // all but the newest group: block `step` has landed
+            __syncwarp(gmask);
+            const double* facs = ring + (step % STAGES) * NC * FS;
             const int row = lane < nleft ? lane : 0;
             const double* my = facs + row * FS;
             double acc = my[4 * N];
@@ -340,6 +385,7 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
                 if (valid) prob.store(step, lane, 0, myx);
             }
             __syncwarp(gmask);
+            fetch_block(step - STAGES);  // into the slot this step just released
         }
     } else {
         // ---- lane r owns right-hand side r: the whole block solve from uniform shared-memory loads
@@ -350,11 +396,9 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
         for (int step = nsteps - 1; step >= 0; --step) {
             const int nleft = prob.nleft(step);
             const int nright = prob.nright(step);
-            if (step < nsteps - 1) {
-                const double* src = fac + (size_t)step * NC * FS;
-                for (int e = lane; e < nleft * FS; e += GL) facs[e] = src[e];
-                __syncwarp(gmask);
-            }
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp(gmask);
+            const double* facs = ring + (step % STAGES) * NC * FS;
             double acc[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -383,12 +427,13 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
                 if (valid && lane < NRHS && c < nleft) prob.store(step, c, r, acc[c]);
             }
             __syncwarp(gmask);
+            fetch_block(step - STAGES);
         }
     }
 }
 
 template <int N>
-__global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32) k_bvp_v2(ChunkView V) {
+__global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, 4) k_bvp_v2(ChunkView V) {
     using C = BvpCfg2<N, 1>;
     extern __shared__ __align__(16) double smem[];
     const int lane_w = threadIdx.x & 31;
@@ -408,7 +453,7 @@ __global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32) k_bvp_v2(
 }
 
 template <int N, int NRHS>
-__global__ void __launch_bounds__(BvpCfg2<N, NRHS>::WARPS_PER_BLOCK * 32) k_bvp_adjoint_v2(ChunkView V, int los0, int nbatch) {
+__global__ void __launch_bounds__(BvpCfg2<N, NRHS>::WARPS_PER_BLOCK * 32, 4) k_bvp_adjoint_v2(ChunkView V, int los0, int nbatch) {
     using C = BvpCfg2<N, NRHS>;
     extern __shared__ __align__(16) double smem[];
     const int lane_w = threadIdx.x & 31;

@@ -5,6 +5,14 @@
 
 namespace disco {
 
+DISCO_HD void prefetch_line(const void* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // Row loader of the forward system A x = b (sktran_do_rte.cpp:1898-2294, sktran_do_rte.h:116-345)
 template <int N>
 struct ForwardRows {
@@ -91,6 +99,18 @@ struct ForwardRows {
             a[4 * N] = rhs;
         }
     }
+    // lines of layer step+1 (the lower layer of interface step+1), one 128-byte line per lane
+    DISCO_HD void prefetch(int step, int lane) const {
+        const int p = step + 1;
+        if (p >= L) return;
+        constexpr int WL = (N * N * 8 + 127) / 128, KL = (2 * N * 8 + 127) / 128, GLn = (4 * N * 8 + 127) / 128;
+        const char* ptr = nullptr;
+        if (lane < WL) ptr = (const char*)(Wp + (size_t)p * N * N) + 128 * lane;
+        else if (lane < 2 * WL) ptr = (const char*)(Wm + (size_t)p * N * N) + 128 * (lane - WL);
+        else if (lane < 2 * WL + KL) ptr = (const char*)(kth + (size_t)p * 2 * N) + 128 * (lane - 2 * WL);
+        else if (lane < 2 * WL + KL + GLn) ptr = (const char*)(G + (size_t)p * 4 * N) + 128 * (lane - 2 * WL - KL);
+        if (ptr) prefetch_line(ptr);
+    }
     // unknown c of block `step`, right-hand side r
     DISCO_HD void store(int step, int c, int, double v) const {
         V.xsol[(((size_t)w * V.M + ms) * L + step) * 2 * N + c] = v;
@@ -167,6 +187,23 @@ struct AdjointRows {
             const size_t o = (((size_t)w * V.M + ms) * V.T.nlos + los) * L + b;
             a[4 * N + r] = (r < nl) ? V.wvec[o * 2 * N + rank] : 0.0;
         }
+    }
+    // lines of layer `step`: W+-, k|theta and the wvec rows of the batch's lines of sight
+    DISCO_HD void prefetch(int step, int lane) const {
+        const int b = step;
+        if (b >= L) return;
+        constexpr int WL = (N * N * 8 + 127) / 128, KL = (2 * N * 8 + 127) / 128, VL = (2 * N * 8 + 127) / 128;
+        const char* ptr = nullptr;
+        if (lane < WL) ptr = (const char*)(Wp + (size_t)b * N * N) + 128 * lane;
+        else if (lane < 2 * WL) ptr = (const char*)(Wm + (size_t)b * N * N) + 128 * (lane - WL);
+        else if (lane < 2 * WL + KL) ptr = (const char*)(kth + (size_t)b * 2 * N) + 128 * (lane - 2 * WL);
+        else if (lane < 2 * WL + KL + nl * VL) {
+            const int q = lane - 2 * WL - KL;
+            const int los = los0 + q / VL;
+            const size_t o = (((size_t)w * V.M + ms) * V.T.nlos + los) * L + b;
+            ptr = (const char*)(V.wvec + o * 2 * N) + 128 * (q % VL);
+        }
+        if (ptr) prefetch_line(ptr);
     }
     DISCO_HD void store(int step, int c, int r, double v) const {
         if (r >= nl) return;

@@ -227,17 +227,25 @@ template <int N, int NRHS>
 struct BvpCfg2 {
     static constexpr int NC = 2 * N;
     static constexpr int ROWS = 3 * N;
-    static constexpr int GL = ROWS <= 4 ? 4 : (ROWS <= 8 ? 8 : (ROWS <= 16 ? 16 : 32));
+    // panel rows per lane.  R = 2 (two problems per warp for N = 8, every broadcast operand feeding two DFMAs) was
+    // measured SLOWER on B200 (bvp 9.2 -> 15.3 ms per 1000 wavelengths): registers halve the resident warps while the
+    // per-pivot broadcast stays bound by shared-memory instruction throughput (tools/microbench/lu_patterns.cu).
+    static constexpr int R = 1;
+    static constexpr int LANES_ROWS = (ROWS + R - 1) / R > NC ? (ROWS + R - 1) / R : NC;
+    static constexpr int LANES_NEEDED = (NRHS > 1 && NRHS > LANES_ROWS) ? NRHS : LANES_ROWS;  // one RHS per lane in the multi-RHS solve
+    static constexpr int GL = LANES_NEEDED <= 2 ? 2 : (LANES_NEEDED <= 4 ? 4 : (LANES_NEEDED <= 8 ? 8 : (LANES_NEEDED <= 16 ? 16 : 32)));
     static constexpr int ROWLEN = 4 * N + NRHS;
     static constexpr int RL2 = (ROWLEN + 1) & ~1;
     static constexpr int FS = RL2 + 2;                    // row stride: padded row | 1/pivot | pad
     static constexpr int GROUPS_PER_WARP = 32 / GL;
     static constexpr int WARPS_PER_BLOCK = 4;
     static constexpr int GROUPS_PER_BLOCK = GROUPS_PER_WARP * WARPS_PER_BLOCK;
+    static constexpr int MIN_BLOCKS = (R == 1) ? 4 : (NRHS == 1 ? 3 : 2);  // register budget: 128 / 168 / 255 per thread
     // factor blocks resident during the back substitution: the one being solved + 2 (1 for the long multi-RHS steps) in flight
     static constexpr int STAGES = (NRHS == 1) ? 3 : 2;
     static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS + NC;   // factor block ring | x of the block below (NRHS = 1)
-    static_assert(ROWS <= GL, "one panel row per lane");
+    static_assert(ROWS <= GL * R && NC <= GL, "panel rows fit the group; one pivot row per lane in the back substitution");
+    static_assert(NRHS == 1 || NRHS <= GL, "one right-hand side per lane");
 };
 
 // 1/x without the library's slow-path call on the critical path of every pivot: MUFU seed, two Newton steps and
@@ -266,19 +274,42 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
     const unsigned lane_bit = 1u << (gbase + lane);
     const unsigned lt_mask = (lane_bit - 1u) & gmask;
 
-    double a[ROWLEN];
+    constexpr int R = C::R;
+    double a[R][ROWLEN];
+    bool act[R];
 #pragma unroll
-    for (int c = 0; c < ROWLEN; ++c) a[c] = 0.0;
-    bool act = false, singular = false;
+    for (int r = 0; r < R; ++r) {
+        act[r] = false;
+#pragma unroll
+        for (int c = 0; c < ROWLEN; ++c) a[r][c] = 0.0;
+    }
+    bool singular = false;
     const int nsteps = prob.nsteps();
 
     for (int step = 0; step < nsteps; ++step) {
-        {   // new rows of this step go to the lowest free lanes
-            const unsigned freeb = __ballot_sync(gmask, !act) & gmask;
-            const int rank = __popc(freeb & lt_mask);
-            if (!act && rank < prob.nnew(step)) {
-                act = true;
-                prob.load(step, rank, a);
+        {   // new rows of this step go to the lowest free slots (slot id = lane * R + r)
+            unsigned freeb[R];
+            bool wasfree[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                wasfree[r] = !act[r];
+                freeb[r] = __ballot_sync(gmask, wasfree[r]) & gmask;
+            }
+            const int needed = prob.nnew(step);
+            int below = 0;  // free slots in lower lanes
+#pragma unroll
+            for (int r = 0; r < R; ++r) below += __popc(freeb[r] & lt_mask);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (wasfree[r]) {
+                    int rank = below;
+#pragma unroll
+                    for (int r2 = 0; r2 < r; ++r2) rank += wasfree[r2] ? 1 : 0;
+                    if (rank < needed) {
+                        act[r] = true;
+                        prob.load(step, rank, a[r]);
+                    }
+                }
             }
         }
         if (step + 1 < nsteps) prob.prefetch(step + 1, lane);  // next step's rows -> L1 while this block is eliminated
@@ -287,28 +318,61 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             if (c < nleft) {
-                const unsigned key = act ? (unsigned)__double2hiint(fabs(a[c])) : 0u;
+                unsigned key = 0u;
+                int rbest = 0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const unsigned kr = act[r] ? (unsigned)__double2hiint(fabs(a[r][c])) : 0u;
+                    if (act[r] && (kr > key || (r == 0))) {
+                        if (kr > key || key == 0u) {
+                            key = kr;
+                            rbest = r;
+                        }
+                    }
+                }
+                bool any_act = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r) any_act |= act[r];
                 const unsigned mx = __reduce_max_sync(gmask, key);
-                const unsigned cand = __ballot_sync(gmask, act && key == mx);
+                const unsigned cand = __ballot_sync(gmask, any_act && key == mx);
                 if (mx == 0u) singular = true;
                 double* bc = facs + c * FS;
-                if (act && (cand & lt_mask) == 0u && (cand & lane_bit)) {  // lowest candidate lane = pivot row
-                    act = false;
+                if (any_act && key == mx && (cand & lt_mask) == 0u) {  // lowest candidate lane holds the pivot row
                     const int c0 = c & ~1;
 #pragma unroll
-                    for (int cc = c0; cc < RL2; cc += 2) {
-                        const double v0 = (cc < ROWLEN) ? a[cc < ROWLEN ? cc : 0] : 0.0;
-                        const double v1 = (cc + 1 < ROWLEN) ? a[cc + 1 < ROWLEN ? cc + 1 : 0] : 0.0;
-                        *reinterpret_cast<double2*>(bc + cc) = make_double2(v0, v1);
+                    for (int r = 0; r < R; ++r) {
+                        if (r == rbest) {
+                            act[r] = false;
+#pragma unroll
+                            for (int cc = c0; cc < RL2; cc += 2) {
+                                const double v0 = (cc < ROWLEN) ? a[r][cc < ROWLEN ? cc : 0] : 0.0;
+                                const double v1 = (cc + 1 < ROWLEN) ? a[r][cc + 1 < ROWLEN ? cc + 1 : 0] : 0.0;
+                                *reinterpret_cast<double2*>(bc + cc) = make_double2(v0, v1);
+                            }
+                            bc[RL2] = rcp_pivot(a[r][c]);
+                        }
                     }
-                    bc[RL2] = rcp_pivot(a[c]);
                 }
                 __syncwarp(gmask);
-                if (act) {
-                    const double f = a[c] * bc[RL2];
+                {
+                    bool any_left = false;
 #pragma unroll
-                    for (int cc = c + 1; cc < ROWLEN; ++cc) a[cc] = fma(-f, bc[cc], a[cc]);
-                    a[c] = 0.0;
+                    for (int r = 0; r < R; ++r) any_left |= act[r];
+                    if (any_left) {
+                        double f[R];
+                        const double pinv = bc[RL2];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            f[r] = act[r] ? a[r][c] * pinv : 0.0;
+                            a[r][c] = act[r] ? 0.0 : a[r][c];
+                        }
+#pragma unroll
+                        for (int cc = c + 1; cc < ROWLEN; ++cc) {
+                            const double b = bc[cc];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) a[r][cc] = fma(-f[r], b, a[r][cc]);
+                        }
+                    }
                 }
             }
         }
@@ -327,9 +391,12 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
         __syncwarp(gmask);
         if (step < nsteps - 1) {
 #pragma unroll
-            for (int j = 0; j < NC; ++j) {
-                a[j] = a[NC + j];
-                a[NC + j] = 0.0;
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    a[r][j] = a[r][NC + j];
+                    a[r][NC + j] = 0.0;
+                }
             }
         }
     }
@@ -433,7 +500,7 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
 }
 
 template <int N>
-__global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, 4) k_bvp_v2(ChunkView V) {
+__global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, BvpCfg2<N, 1>::MIN_BLOCKS) k_bvp_v2(ChunkView V) {
     using C = BvpCfg2<N, 1>;
     extern __shared__ __align__(16) double smem[];
     const int lane_w = threadIdx.x & 31;
@@ -453,7 +520,7 @@ __global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, 4) k_bvp_
 }
 
 template <int N, int NRHS>
-__global__ void __launch_bounds__(BvpCfg2<N, NRHS>::WARPS_PER_BLOCK * 32, 4) k_bvp_adjoint_v2(ChunkView V, int los0, int nbatch) {
+__global__ void __launch_bounds__(BvpCfg2<N, NRHS>::WARPS_PER_BLOCK * 32, BvpCfg2<N, NRHS>::MIN_BLOCKS) k_bvp_adjoint_v2(ChunkView V, int los0, int nbatch) {
     using C = BvpCfg2<N, NRHS>;
     extern __shared__ __align__(16) double smem[];
     const int lane_w = threadIdx.x & 31;

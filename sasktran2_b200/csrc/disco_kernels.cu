@@ -106,6 +106,95 @@ __global__ void k_wf_chain(ChunkView V, int G) {
     if (idx >= (long long)V.nw * V.T.nlos) return;
     wf_chain_body(V, idx, G);
 }
+// Warp per (wavelength, LOS) version of wf_chain_body (disco_wf_body.h states the arithmetic serially): the lanes
+// own layers, so the azimuth sums stream wf_loc coalesced, the chapman contraction reads rows of the [L][L] matrix
+// coalesced, and the layer -> grid scatter goes through shared-memory atomics (at most two layers per grid point).
+// dynamic shared memory per warp: gT[L+1] | dtau[L+1] | tail[L+1] | native[nloc (2+G) + 1]
+__global__ void __launch_bounds__(128) k_wf_chain_warp(ChunkView V, int G) {
+    extern __shared__ double sm_chain[];
+    const int L = V.T.L, M = V.M, nlos = V.T.nlos, nstr = V.T.nstr, nloc = V.T.nloc;
+    const int NL = G + 4, iTau = G, iOm = G + 1, iT = G + 2, iS = G + 3;
+    const int nnative = nloc * (2 + G) + 1;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* gT = sm_chain + (size_t)wib * (3 * (L + 1) + nnative);
+    double* dtau = gT + (L + 1);
+    double* tail = dtau + (L + 1);
+    double* native = tail + (L + 1);
+    const long long idx = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (idx >= (long long)V.nw * nlos) return;
+    const int w = (int)(idx / nlos), los = (int)(idx % nlos);
+    const double mul = V.T.los_mu[los];
+    const double* od = V.lay_od + (size_t)w * L;
+    const double* sec = V.lay_secant + (size_t)w * L;
+    const double* tr = V.lay_trans + (size_t)w * (L + 1);
+    const double* gnd = V.wf_gnd + (size_t)idx * 3;
+    for (int i = lane; i < nnative; i += 32) native[i] = 0.0;
+    for (int p = lane; p <= L; p += 32) gT[p] = 0.0;
+    __syncwarp();
+    // azimuth sums of the local lanes; omega and scattering lanes go straight to the native derivatives
+    for (int p = lane; p < L; p += 32) {
+        double acc[8];  // NL <= 6
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+        double src = 0.0;
+        for (int ms = 0; ms < M; ++ms) {
+            const double cf = V.T.los_cosmphi[(size_t)los * nstr + V.m_list[ms]];
+            const size_t o = (((size_t)w * M + ms) * nlos + los) * L + p;
+            const double* lc = V.wf_loc + o * NL;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < NL) acc[c] = fma(cf, lc[c], acc[c]);
+            src = fma(cf, V.wf_src[o], src);
+        }
+        const double loc_tau = acc[iTau], loc_om = acc[iOm], g_t = acc[iT], g_s = acc[iS];
+        dtau[p] = loc_tau - g_s * sec[p] / od[p];
+        tail[p] = src;
+        // gT[p] and gT[p+1] receive from layers p-1, p and p, p+1: accumulate with shared-memory atomics
+        atomicAdd(&gT[p], -tr[p] * g_t - g_s / od[p]);
+        atomicAdd(&gT[p + 1], g_s / od[p]);
+        const double totext = V.lay_totext[(size_t)w * L + p], scatext = V.lay_scatext[(size_t)w * L + p];
+        const double ssal = V.lay_ssa[(size_t)w * L + p];
+        for (int c = 0; c < 2; ++c) {
+            const int q = V.interp_idx[p * 2 + c];
+            if (q < 0) continue;
+            const double wq = V.interp_w[p * 2 + c];
+            const double kq = V.ext[(size_t)nloc * w + q], omq = V.ssa[(size_t)nloc * w + q];
+            atomicAdd(&native[nloc + q], wq * loc_om * (kq / totext));
+            atomicAdd(&native[q], wq * loc_om * ((omq - ssal) / totext));
+            for (int g = 0; g < G; ++g) atomicAdd(&native[2 * nloc + g * nloc + q], wq * acc[g] * (omq * kq / scatext));
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        gT[L] += -tr[L] * gnd[1];
+        // LOS attenuation: dI/dtau_q -= (1/mu) (sum_{p>q} src_p + ground)
+        double below = gnd[2];
+        for (int q = L - 1; q >= 0; --q) {
+            dtau[q] -= below / mul;
+            below += tail[q];
+        }
+    }
+    __syncwarp();
+    // slant optical depths: T_{p+1} = sum_{q<=p} chapman[p][q] tau_q  ->  dtau_q += sum_{p>=q} gT[p+1] chapman[p][q]
+    for (int q = lane; q < L; q += 32) {
+        double s = 0.0;
+        for (int pp = q; pp < L; ++pp) s = fma(gT[pp + 1], V.chapman[(size_t)pp * L + q], s);
+        dtau[q] += s;
+    }
+    __syncwarp();
+    for (int p = lane; p < L; p += 32) {
+        const double dh = V.layer_dh[p];
+        for (int c = 0; c < 2; ++c) {
+            const int q = V.interp_idx[p * 2 + c];
+            if (q < 0) continue;
+            atomicAdd(&native[q], V.interp_w[p * 2 + c] * dh * dtau[p]);
+        }
+    }
+    if (lane == 0) native[nloc * (2 + G)] = gnd[0];
+    __syncwarp();
+    double* out = V.wf_native + (size_t)idx * nnative;
+    for (int i = lane; i < nnative; i += 32) out[i] = native[i];
+}
 __global__ void k_wf_map(ChunkView V, MappingView Mp, int w0, int nw_total, int G) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)V.nw * V.T.nlos * Mp.nout) return;
@@ -199,7 +288,17 @@ void launch_bvp_adjoint(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_FN(
 void launch_wf_layer(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_FN(launch_wf_layer_n, V, s) }
 void launch_wf_chain(const ChunkView& V, cudaStream_t s) {
     const long long n = (long long)V.nw * V.T.nlos;
-    k_wf_chain<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(V, V.ngroups);
+    const size_t per_warp = (size_t)(3 * (V.T.L + 1) + V.T.nloc * (2 + V.ngroups) + 1) * sizeof(double);
+    if (V.ngroups + 4 <= 8 && 4 * per_warp <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_wf_chain_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set = true;
+        }
+        k_wf_chain_warp<<<(unsigned)((n + 3) / 4), 128, 4 * per_warp, s>>>(V, V.ngroups);
+    } else {
+        k_wf_chain<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(V, V.ngroups);
+    }
 }
 void launch_wf_map(const ChunkView& V, const MappingView& Mp, int w0, int nw_total, bool log_space, cudaStream_t s) {
     const long long n = (long long)V.nw * V.T.nlos * Mp.nout;

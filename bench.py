@@ -34,16 +34,31 @@ METRIC = "LOS x wavelength radiances/sec (16-stream, 100 layers)"
 UNIT = "radiances/s"
 
 
-def flop_model(nstr, nlayers, nlos, m_list):
-    """Algorithmic flops per wavelength (values only), split by kernel."""
+def flop_model(nstr, nlayers, nlos, m_list, ngroups=1):
+    """Algorithmic flops per wavelength, split by timed kernel group.
+
+    layer, bvp: SURVEY.md section 8d / Appendix B (values only; the BVP figure is LAPACK's banded LU + solve count,
+    the staircase elimination does about a third of it).  Weighting functions (reverse mode):
+      wf_adjoint  one more banded factorisation (of A^T) + one banded solve per line of sight;
+      wf_layer    the layer-local linearisation with NL = ngroups + 4 lanes [eps_g | tau | omega | t | s]: NL times the
+                  values-only particular + LOS work (forward-mode count of the reference's layer duals,
+                  sktran_do_rte.cpp:903-1332, sktran_do_opticallayer.cpp:94-555) + 7 N^3 per eigen-derivative lane
+                  (ngroups + 1 lanes, sktran_do_rte.cpp:198-298) + the adjoint contraction 8 N^2 NL per LOS."""
     N, K, L = nstr // 2, nstr, nlayers
-    layer = bvp = 0.0
+    NL, NH = ngroups + 4, ngroups + 1
+    layer = bvp = wf_adjoint = wf_layer = 0.0
     for m in m_list:
-        layer += L * (6 * N * N * (K - m) + 29 * N**3 + 4 * N * N)          # S+-, eigen-decomposition, W+-
-        layer += L * (12 * N * (K - m) + 10 * N * N + 60 * N)                # Green's function particular solution
-        layer += nlos * L * (6 * N * (K - m) + 8 * N * N + 120 * N)          # LOS source multipliers
-        bvp += 4 * N * L * (3 * N - 1) * (6 * N - 2) + 4 * N * L * (9 * N - 3)  # banded LU + solve (LAPACK count)
-    return {"layer": layer, "bvp": bvp, "total": layer + bvp}
+        homog = L * (6 * N * N * (K - m) + 29 * N**3 + 4 * N * N)            # S+-, eigen-decomposition, W+-
+        part = L * (12 * N * (K - m) + 10 * N * N + 60 * N)                  # Green's function particular solution
+        post = nlos * L * (6 * N * (K - m) + 8 * N * N + 120 * N)            # LOS source multipliers
+        factor = 4 * N * L * (3 * N - 1) * (6 * N - 2)                       # banded LU (LAPACK count)
+        solve = 4 * N * L * (9 * N - 3)                                      # one banded solve
+        layer += homog + part + post
+        bvp += factor + solve
+        wf_adjoint += factor + nlos * solve
+        wf_layer += NL * (part + post) + L * NH * 7 * N**3 + nlos * L * 8 * N * N * NL
+    return {"layer": layer, "bvp": bvp, "wf_adjoint": wf_adjoint, "wf_layer": wf_layer, "total": layer + bvp,
+            "total_wf": layer + bvp + wf_adjoint + wf_layer}
 
 
 def bytes_model(nloc, nleg, nlos, nwf_out=0):
@@ -106,7 +121,7 @@ def oracle_inputs(sc):
                 ext=sc.total_extinction, leg=sc.leg_coeff, albedo=sc.albedo)
 
 
-def time_oracle(sc, sample, threads):
+def time_oracle(sc, sample, threads, with_wf=False):
     """Times the CPU port (oracle) on `sample` wavelengths of the workload with `threads` OpenMP threads."""
     from oracle import oracle
 
@@ -117,8 +132,12 @@ def time_oracle(sc, sample, threads):
     inp["leg"] = np.asfortranarray(sc.leg_coeff[:, :, pick])
     inp["albedo"] = sc.albedo[pick]
     oracle.lib()
+    extra = {}
+    if with_wf and "wf_aerosol_extinction" in sc.mappings:
+        extra = dict(d_leg=np.asfortranarray(sc.mappings["wf_aerosol_extinction"]["d_legendre"][:, :, pick][..., None]),
+                     calc_derivs=True)
     t0 = time.perf_counter()
-    oracle.do_radiance(**inp, nthreads=threads)
+    oracle.do_radiance(**inp, nthreads=threads, **extra)
     dt = time.perf_counter() - t0
     return sample * sc.nlos / dt, dt
 
@@ -146,7 +165,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": float(np.median(dts)) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"pseudo-spherical DO, {args.nstr} streams, {args.layers} layers, {args.nlos} LOS, "
-                               f"values only; CPU port on a {sample}-wavelength sample per step"},
+                               f"CPU port on a {sample}-wavelength sample per step, VALUES ONLY (upper bound for the CPU "
+                               f"path with weighting functions: the port has no reverse-mode linearisation)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} wavelengths x {args.nlos} LOS per step, OpenMP over wavelengths"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -167,7 +187,10 @@ def main():
     ap.add_argument("--nlos", type=int, default=10)
     ap.add_argument("--cpu-sample", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workspace-gb", type=float, default=8.0)
+    ap.add_argument("--workspace-gb", type=float, default=48.0,
+                    help="device workspace per wavelength chunk (B200: 180 GB HBM3e)")
+    ap.add_argument("--cpu-wf-sample", type=int, default=0,
+                    help="also time the CPU port WITH weighting functions (forward-mode duals) on this many wavelengths")
     ap.add_argument("--wf", type=int, default=1, help="1: with weighting functions (O3, NO2, aerosol mappings + albedo), 0: radiances only")
     args = ap.parse_args()
 
@@ -286,7 +309,10 @@ def main():
     check = eng.fetch()["radiance"]
     assert np.all(np.isfinite(check)) and np.all(check > 0), "non-finite radiance in the bench workload"
 
-    # ---- end to end through the reference-facing call with host buffers (e2e)
+    # ---- end to end through the reference-facing call with host buffers (e2e): every step copies the inputs from
+    # (page-locked) host memory, solves, and copies radiances + weighting functions back into page-locked host arrays
+    # that the engine hands out again on the next call (reuse_output_buffers)
+    eng.reuse_output_buffers = True
     for _ in range(min(args.warmup, 2)):
         eng.calculate_radiance(atm, rad_buf)
     barrier()
@@ -296,15 +322,22 @@ def main():
     barrier()
     e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
     e2e_value = units_per_step_all / (e2e_ms * 1e-3)
+    t_last = eng.timings_ms()
+    e2e_breakdown = {"h2d_ms": t_last["h2d"], "kernels_ms": t_last["kernels_total"], "d2h_ms": t_last["d2h"]}
+    e2e_breakdown["host_ms"] = e2e_ms - sum(e2e_breakdown.values())
 
     # ---- roofline of the dominant kernel (FP64 pipe; peak measured live by a DFMA micro-benchmark)
-    fm = flop_model(args.nstr, args.layers, nlos, m_list)
-    dom = max(("layer", "bvp"), key=lambda k: per_kernel.get(k, 0.0))
+    fm = flop_model(args.nstr, args.layers, nlos, m_list, ngroups=1 if with_wf else 0)
+    fast = args.nstr in (4, 8, 16) and os.environ.get("SK_B200_GENERIC", "0") != "1"
+    kernel_names = {
+        "layer": "k_eig_setup + k_eig_jacobi + k_layer_post (+ k_los_atten)" if fast else "k_layer_solve",
+        "bvp": "k_bvp_v2" if args.nstr <= 16 else "k_bvp",
+        "wf_adjoint": "k_bvp_adjoint_v2" if args.nstr <= 16 else "k_bvp_adjoint",
+        "wf_layer": "k_wf_layer_fast" if fast else "k_wf_layer",
+    }
+    launches_per_chunk = {"layer": 4 if fast else 1, "bvp": 1, "wf_adjoint": 1, "wf_layer": 1}
     chunk = info["chunk_wavelengths"]
-    n_launch = args.steps * int(np.ceil(nw / chunk))
-    avg_launch_ms = per_kernel[dom] / max(n_launch, 1)
-    flops_per_launch = fm[dom] * (nw / np.ceil(nw / chunk))
-    achieved_tflops = flops_per_launch / (avg_launch_ms * 1e-3) / 1e12
+    nchunks = int(np.ceil(nw / chunk))
     fp64_peak = None
     try:
         import ctypes as C
@@ -320,13 +353,31 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    step_kernel_ms = max(sum(per_kernel.values()), 1e-12)
+
+    def kernel_roofline(k):
+        ms = per_kernel.get(k, 0.0)
+        if ms <= 0.0:
+            return None
+        n_launch = args.steps * nchunks * launches_per_chunk[k]
+        tf = fm[k] * nw * args.steps / (ms * 1e-3) / 1e12   # algorithmic flops of the group / its device time
+        return {"kernel": kernel_names[k], "achieved": tf, "frac": (tf / fp64_peak) if fp64_peak else None,
+                "share_of_step": ms / step_kernel_ms, "avg_launch_ms": ms / max(n_launch, 1),
+                "flops_per_launch": fm[k] * (nw / nchunks) / launches_per_chunk[k]}
+
+    per_k = {k: kernel_roofline(k) for k in ("layer", "bvp", "wf_adjoint", "wf_layer")}
+    per_k = {k: v for k, v in per_k.items() if v}
+    dom = max(per_k, key=lambda k: per_k[k]["share_of_step"])
+    total_flops = fm["total_wf"] if with_wf else fm["total"]
     roofline = {
-        "bound": "fp64", "kernel": {"layer": "k_layer_solve", "bvp": "k_bvp"}[dom],
-        "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": (achieved_tflops / fp64_peak) if fp64_peak else None, "traffic": None,
+        "bound": "fp64", "kernel": per_k[dom]["kernel"], "achieved": per_k[dom]["achieved"], "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": per_k[dom]["frac"], "traffic": None,
         "peak_source": "DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP64 figure)",
-        "share_of_step": per_kernel[dom] / max(sum(per_kernel.values()), 1e-12),
-        "whole_step": {"flops_per_wavelength": fm["total"], "achieved_tflops": fm["total"] * nw / (ms_per_step * 1e-3) / 1e12 if world == 1 else fm["total"] * nw_total / world / (ms_per_step * 1e-3) / 1e12},
+        "share_of_step": per_k[dom]["share_of_step"], "avg_launch_ms": per_k[dom]["avg_launch_ms"],
+        "flops_per_launch": per_k[dom]["flops_per_launch"],
+        "kernels": per_k,
+        "whole_step": {"flops_per_wavelength": total_flops,
+                       "achieved_tflops": total_flops * (nw_total / world) / (ms_per_step * 1e-3) / 1e12},
         "hbm_view": {"bound": "hbm", "achieved": bytes_model(nloc, nleg, nlos, nwf_out) * (nw_total / world) / (ms_per_step * 1e-3) / 1e9,
                      "peak": hbm_peak, "unit": "GB/s",
                      "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
@@ -346,7 +397,7 @@ def main():
                    "wall_ms_per_step": wall_ms / args.steps},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                "ms_per_step": e2e_ms, "pinned": all(ok for _, ok in pinned)},
+                "ms_per_step": e2e_ms, "pinned": all(ok for _, ok in pinned), "breakdown": e2e_breakdown},
         "gpu_launches": launches_all,
         "kernel_ms_per_step": {k: v / args.steps for k, v in per_kernel.items()},
         "roofline": roofline,
@@ -356,8 +407,13 @@ def main():
         time_oracle(sc, min(args.cpu_sample, cores), cores)
         v, dt = time_oracle(sc, args.cpu_sample, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_sample} wavelengths x {nlos} LOS of the same workload, "
-                                          f"oracle port with OpenMP over wavelengths, {dt:.1f} s"}
+                                "sample": f"{args.cpu_sample} wavelengths x {nlos} LOS of the same atmosphere, oracle port "
+                                          f"with OpenMP over wavelengths, {dt:.1f} s; VALUES ONLY - the port linearises in "
+                                          f"forward mode only, so this is an upper bound for the CPU path with weighting "
+                                          f"functions (the reference's default reverse mode costs ~2.5-3x values only)"}
+        if args.cpu_wf_sample > 0:
+            v2, dt2 = time_oracle(sc, args.cpu_wf_sample, cores, with_wf=True)
+            line["cpu_baseline"]["with_wf_forward_mode"] = {"value": v2, "sample": f"{args.cpu_wf_sample} wavelengths, {dt2:.1f} s"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     for arr, ok in pinned:

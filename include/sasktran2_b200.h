@@ -21,6 +21,7 @@
 #ifndef SASKTRAN2_B200_H
 #define SASKTRAN2_B200_H
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -196,6 +197,9 @@ int sk_b200_engine_info(Engine* engine, int* num_azimuth, int* chunk_wavelengths
 int sk_b200_engine_set_workspace_gb(Engine* engine, double gb);
 /* DFMA micro-benchmark on the current device: the FP64 roofline denominator (TFLOP/s) */
 double sk_b200_measure_fp64_tflops();
+/* page-locked host memory for caller-side buffers (falls back to malloc without a CUDA device) */
+void* sk_b200_host_alloc(size_t nbytes);
+void sk_b200_host_free(void* p);
 /* test/debug: copy a named workspace array of the last solved chunk (names: see disco_engine.cu) */
 long long sk_b200_engine_debug_copy(Engine* engine, const char* name, double* host, long long max_n);
 

@@ -117,6 +117,8 @@ def _declare(lib):
     f("sk_b200_engine_set_workspace_gb", i, vp, d)
     f("sk_b200_measure_fp64_tflops", d)
     f("sk_b200_engine_debug_copy", C.c_longlong, vp, C.c_char_p, c_double_p, C.c_longlong)
+    f("sk_b200_host_alloc", vp, C.c_size_t)
+    f("sk_b200_host_free", None, vp)
 
 
 def lib():
@@ -145,3 +147,30 @@ def check(rc: int, what: str = "") -> None:
 
 def dptr(a):
     return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+class _PinnedBlock:
+    """Owns one sk_b200_host_alloc block; numpy views keep it alive through their .base chain."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = lib().sk_b200_host_alloc(C.c_size_t(max(nbytes, 8)))
+        if not self.ptr:
+            raise MemoryError("sk_b200_host_alloc failed")
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            lib().sk_b200_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape):
+    """float64 C-ordered array in page-locked host memory (plain memory when no CUDA device is present)."""
+    import numpy as np
+
+    n = int(np.prod(shape))
+    blk = _PinnedBlock(8 * n)
+    buf = (C.c_double * max(n, 1)).from_address(blk.ptr)
+    buf._owner = blk  # keeps the block alive as long as any view of `buf` lives
+    return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)

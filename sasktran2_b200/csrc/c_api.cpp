@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <set>
+#include <cstdlib>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -59,9 +62,53 @@ struct ViewingGeometry {
     int num_flux_observers = 0;
 };
 
+// Host memory the library owns and copies to / from the device every call (derivative mappings) is page-locked
+// when a CUDA device is present, so that the H2D copies run at PCIe speed; without a device it is plain malloc.
+static std::mutex g_pin_mu;
+static std::set<void*> g_pinned_ptrs;
+static void* host_alloc(size_t nbytes) {
+    void* p = nullptr;
+    if (nbytes == 0) nbytes = 8;
+    if (cudaMallocHost(&p, nbytes) == cudaSuccess && p) {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        g_pinned_ptrs.insert(p);
+        return p;
+    }
+    (void)cudaGetLastError();
+    p = std::malloc(nbytes);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+static void host_free(void* p) {
+    if (!p) return;
+    bool pinned = false;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        pinned = g_pinned_ptrs.erase(p) > 0;
+    }
+    if (pinned)
+        cudaFreeHost(p);
+    else
+        std::free(p);
+}
+template <class T>
+struct PinnedAlloc {
+    using value_type = T;
+    PinnedAlloc() = default;
+    template <class U>
+    PinnedAlloc(const PinnedAlloc<U>&) {}
+    T* allocate(size_t n) { return static_cast<T*>(host_alloc(n * sizeof(T))); }
+    void deallocate(T* p, size_t) { host_free(p); }
+    template <class U>
+    bool operator==(const PinnedAlloc<U>&) const { return true; }
+    template <class U>
+    bool operator!=(const PinnedAlloc<U>&) const { return false; }
+};
+using PinnedVec = std::vector<double, PinnedAlloc<double>>;
+
 struct MappingImpl {
     int nwavel = 0, nloc = 0, nleg = 0;
-    std::vector<double> d_ssa, d_extinction, scat_factor, d_legendre;
+    PinnedVec d_ssa, d_extinction, scat_factor, d_legendre;
     bool has_d_ssa = false, has_d_extinction = false, has_legendre = false;
     int scat_deriv_index = -1;
     std::string interp_dim = "altitude", assign_name;
@@ -862,6 +909,14 @@ long long sk_b200_engine_debug_copy(Engine* e, const char* name, double* host, l
     return (long long)e->dev->debug_copy(name, host, (size_t)max_n);
 }
 double sk_b200_measure_fp64_tflops() { return disco::measure_fp64_tflops(); }
+void* sk_b200_host_alloc(size_t nbytes) {
+    try {
+        return host_alloc(nbytes);
+    } catch (...) {
+        return nullptr;
+    }
+}
+void sk_b200_host_free(void* p) { host_free(p); }
 int sk_b200_engine_set_workspace_gb(Engine* e, double gb) {
     if (!e || !e->dev) return -1;
     e->dev->set_workspace_gb(gb);

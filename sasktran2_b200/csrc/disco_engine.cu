@@ -235,47 +235,66 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
         CUDA_OK(cudaMemcpyAsync(d_solar, atm.solar + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
         CUDA_OK(cudaMemcpyAsync(d_albedo, atm.albedo + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
     }
-    // weighting-function inputs of the staged range
-    free_wf_inputs();
+    // weighting-function inputs of the staged range.  Device buffers are kept from the previous call when the
+    // request has the same shape (same number of wavelengths, groups, mappings and output sizes).
     m_w0 = w0;
     m_nw_total = atm.nwavel;
-    if (wf && wf->enabled() && nw > 0) {
-        if (wf->d_legendre.size() > 2) throw std::runtime_error("B200 DO path supports at most 2 scattering derivative groups");
-        m_wf_on = true;
-        m_ngroups = (int)wf->d_legendre.size();
-        const size_t nl3 = (size_t)atm.nleg * nloc * nw;
-        if (m_ngroups > 0) {
-            d_dleg = dalloc<double>(nl3 * m_ngroups);
-            for (int g = 0; g < m_ngroups; ++g)
-                CUDA_OK(cudaMemcpyAsync(d_dleg + nl3 * g, wf->d_legendre[g] + (size_t)atm.nleg * nloc * w0,
-                                        sizeof(double) * nl3, cudaMemcpyHostToDevice, m_stream));
+    const bool want_wf = wf && wf->enabled() && nw > 0;
+    bool same_shape = want_wf && m_wf_on && m_wf_nw == nw && m_wf_nleg == atm.nleg &&
+                      m_ngroups == (int)wf->d_legendre.size() && m_maps.size() == wf->mappings.size() &&
+                      m_surfs.size() == wf->surfaces.size();
+    if (same_shape)
+        for (size_t i = 0; i < m_maps.size(); ++i) {
+            const auto& a = m_maps[i].host;
+            const auto& b = wf->mappings[i];
+            if (a.nout != b.nout || (a.scat_factor == nullptr) != (b.scat_factor == nullptr) ||
+                (a.interpolator == nullptr) != (b.interpolator == nullptr))
+                same_shape = false;
         }
+    if (!same_shape) free_wf_inputs();
+    if (want_wf) {
+        if (wf->d_legendre.size() > 2) throw std::runtime_error("B200 DO path supports at most 2 scattering derivative groups");
+        const size_t nl3 = (size_t)atm.nleg * nloc * nw;
         const size_t n2 = nloc * (size_t)nw;
-        for (const auto& mp : wf->mappings) {
-            DevMapping dm;
+        if (!same_shape) {
+            m_wf_on = true;
+            m_wf_nw = nw;
+            m_wf_nleg = atm.nleg;
+            m_ngroups = (int)wf->d_legendre.size();
+            if (m_ngroups > 0) d_dleg = dalloc<double>(nl3 * m_ngroups);
+            for (const auto& mp : wf->mappings) {
+                DevMapping dm;
+                dm.d_ssa = dalloc<double>(n2);
+                dm.d_ext = dalloc<double>(n2);
+                if (mp.scat_factor) dm.scat = dalloc<double>(n2);
+                if (mp.interpolator) dm.interp = dalloc<double>(nloc * (size_t)mp.nout);
+                dm.out = dalloc<double>((size_t)mp.nout * nw * m_plan.nlos);
+                m_maps.push_back(dm);
+            }
+            for (size_t i = 0; i < wf->surfaces.size(); ++i) {
+                DevSurface ds;
+                ds.d_brdf = dalloc<double>(nw);
+                ds.out = dalloc<double>((size_t)nw * m_plan.nlos);
+                m_surfs.push_back(ds);
+            }
+        }
+        for (int g = 0; g < m_ngroups; ++g)
+            CUDA_OK(cudaMemcpyAsync(d_dleg + nl3 * g, wf->d_legendre[g] + (size_t)atm.nleg * nloc * w0,
+                                    sizeof(double) * nl3, cudaMemcpyHostToDevice, m_stream));
+        for (size_t i = 0; i < m_maps.size(); ++i) {
+            DevMapping& dm = m_maps[i];
+            const WfMapping& mp = wf->mappings[i];
             dm.host = mp;
-            dm.d_ssa = dalloc<double>(n2);
-            dm.d_ext = dalloc<double>(n2);
             CUDA_OK(cudaMemcpyAsync(dm.d_ssa, mp.d_ssa + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
             CUDA_OK(cudaMemcpyAsync(dm.d_ext, mp.d_extinction + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
-            if (mp.scat_factor) {
-                dm.scat = dalloc<double>(n2);
+            if (mp.scat_factor)
                 CUDA_OK(cudaMemcpyAsync(dm.scat, mp.scat_factor + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
-            }
-            if (mp.interpolator) {
-                dm.interp = dalloc<double>(nloc * (size_t)mp.nout);
+            if (mp.interpolator)
                 CUDA_OK(cudaMemcpyAsync(dm.interp, mp.interpolator, sizeof(double) * nloc * mp.nout, cudaMemcpyHostToDevice, m_stream));
-            }
-            dm.out = dalloc<double>((size_t)mp.nout * nw * m_plan.nlos);
-            m_maps.push_back(dm);
         }
-        for (const auto& sf : wf->surfaces) {
-            DevSurface ds;
-            ds.host = sf;
-            ds.d_brdf = dalloc<double>(nw);
-            CUDA_OK(cudaMemcpyAsync(ds.d_brdf, sf.d_brdf + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
-            ds.out = dalloc<double>((size_t)nw * m_plan.nlos);
-            m_surfs.push_back(ds);
+        for (size_t i = 0; i < m_surfs.size(); ++i) {
+            m_surfs[i].host = wf->surfaces[i];
+            CUDA_OK(cudaMemcpyAsync(m_surfs[i].d_brdf, wf->surfaces[i].d_brdf + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
         }
     }
     CUDA_OK(cudaEventRecord(m_ev[1], m_stream));

@@ -115,7 +115,7 @@ class DeviceEngine {
     };
     void free_wf_inputs();
     bool m_wf_on = false;
-    int m_ngroups = 0, m_w0 = 0, m_nw_total = 0;
+    int m_ngroups = 0, m_w0 = 0, m_nw_total = 0, m_wf_nw = 0, m_wf_nleg = 0;
     double* d_dleg = nullptr;
     std::vector<DevMapping> m_maps;
     std::vector<DevSurface> m_surfs;

@@ -38,6 +38,11 @@ class Engine:
             raise _lib.SasktranError(f"sk_engine_create failed: {_lib.last_error()}")
         self._keepalive = None
         self._staged_out = None
+        # Output arrays live in page-locked host memory (D2H at PCIe speed).  With reuse_output_buffers = True the
+        # arrays of the previous call with the same shapes are handed out again instead of fresh ones - for
+        # pipelines that consume a result before asking for the next one (bench.py's e2e loop).
+        self.reuse_output_buffers = False
+        self._pool = {}
 
     def __del__(self):
         try:
@@ -48,10 +53,20 @@ class Engine:
             pass
 
     # ---- the reference call -------------------------------------------------------------------------
+    def _buffer(self, key, shape):
+        if self.reuse_output_buffers:
+            buf = self._pool.get(key)
+            if buf is None or buf.shape != tuple(shape):
+                buf = self._pool[key] = _lib.pinned_empty(shape)
+            return buf
+        buf = _lib.pinned_empty(shape)
+        buf[...] = 0.0
+        return buf
+
     def _make_output(self, atmosphere, radiance_buffer=None):
         nw = atmosphere.num_wavel
         nlos = self._viewing_geometry.num_rays
-        rad = radiance_buffer if radiance_buffer is not None else np.zeros((nw, nlos, 1))
+        rad = radiance_buffer if radiance_buffer is not None else self._buffer("radiance", (nw, nlos, 1))
         assert rad.shape == (nw, nlos, 1) and rad.flags["C_CONTIGUOUS"]
         out = _lib.lib().sk_output_create(_lib.dptr(rad), nw * nlos, 1, None, 0)
         res = Result()
@@ -61,14 +76,14 @@ class Engine:
             for name in atmosphere.storage.derivative_mapping_names:
                 m = atmosphere.storage.get_derivative_mapping(name)
                 nout = m.num_output
-                buf = np.zeros((nout, nw, nlos, 1))
+                buf = self._buffer("wf:" + name, (nout, nw, nlos, 1))
                 _lib.check(_lib.lib().sk_output_assign_derivative_memory(out, name.encode(), _lib.dptr(buf),
                                                                          nw * nlos, 1, nout))
                 key = m.assign_name or name
                 res[key] = buf
                 res.dims[key] = (m.interp_dim, "wavelength", "los", "stokes")
             for name in atmosphere.surface._mapping_names:
-                buf = np.zeros((1, nw, nlos, 1))
+                buf = self._buffer("surf:" + name, (1, nw, nlos, 1))
                 _lib.check(_lib.lib().sk_output_assign_surface_derivative_memory(out, name.encode(),
                                                                                  _lib.dptr(buf), nw * nlos, 1))
                 res[name] = buf[0]

@@ -1,6 +1,9 @@
 // Staircase LU (forward and adjoint boundary-value solves) — templates, instantiated per stream count in
 // disco_bvp_inst.cu (one translation unit per N so that the build parallelises).
 #pragma once
+#include <cstdlib>
+#include <type_traits>
+
 #include "disco_bvp_rows.h"
 #include "disco_kernels.cuh"
 
@@ -499,6 +502,328 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Version 3: the panel is distributed in two dimensions over one warp - 8 row lanes x 4 column groups, S = ceil(3N/8)
+// row slots per lane, N panel columns (one window block) per group.  Column block gb of the band lives in group
+// gb mod 4, so the window slides without moving data.  Per pivot the warp exchanges
+//   1 pivot value + S multipliers + N row-segment entries (+ the right-hand-side entries)
+// as 64-bit shuffles - 13 for N = 8 - instead of a 34-double row through shared memory (17 STS.128 from one lane at
+// ~4 MIO cycles each + 17 LDS.128: tools/microbench/lu_patterns.cu, profiles/microbench_lu_r01.txt), all 32 lanes do
+// the rank-1 update (S x N DFMA each), and the registers per thread drop from 128 to ~100.  Pivot rows stay in
+// their registers until the end of the step and are then written to HBM in the layout of version 2
+// (fac[step][c][FS]), so the back substitution is shared with version 2.
+// -------------------------------------------------------------------------------------------------
+template <int I, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < E) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, E>(f);
+    }
+}
+
+template <int N, int NRHS>
+struct BvpCfg3 {
+    static constexpr int NC = 2 * N;
+    static constexpr int S = (3 * N + 7) / 8;          // row slots per lane
+    static constexpr int RQ = (NRHS + 3) / 4;          // right-hand-side columns per group
+    static constexpr int ROWLEN = 4 * N + NRHS;
+    static constexpr int RL2 = (ROWLEN + 1) & ~1;
+    static constexpr int FS = RL2 + 2;
+    static constexpr int GL = 32;
+    static constexpr int WARPS_PER_BLOCK = 4;
+    static constexpr int GROUPS_PER_BLOCK = WARPS_PER_BLOCK;
+    static constexpr int STAGES = 2;   // shared memory, not registers, would otherwise cap the resident warps
+    static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS + NC;
+    static_assert(NC <= 32 && (NRHS == 1 || NRHS <= 32), "back substitution lanes");
+};
+
+// one pivot of the 2D elimination with the pivot row in slot RP (uniform over the warp)
+template <int N, int NRHS, int K, int RP>
+__device__ __forceinline__ void pivot_update_2d(double (&a)[BvpCfg3<N, NRHS>::S][N], double (&rhs)[BvpCfg3<N, NRHS>::S][BvpCfg3<N, NRHS>::RQ],
+                                                bool (&act)[BvpCfg3<N, NRHS>::S], int (&pidx)[BvpCfg3<N, NRHS>::S],
+                                                double (&pinvs)[BvpCfg3<N, NRHS>::S], int c, int ri, int g, int go, int ri_p) {
+    using C = BvpCfg3<N, NRHS>;
+    constexpr int S = C::S, RQ = C::RQ;
+    const bool owner = (g == go);
+    const double pv = __shfl_sync(FULL_MASK, a[RP][K], go * 8 + ri_p);
+    const double pinv = rcp_pivot(pv);
+    if (ri == ri_p) {
+        act[RP] = false;
+        pidx[RP] = c;
+        pinvs[RP] = pinv;
+    }
+    double f[S];
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+        const double fr = (owner && act[r]) ? a[r][K] * pinv : 0.0;
+        f[r] = __shfl_sync(FULL_MASK, fr, go * 8 + ri);
+    }
+    const int src = g * 8 + ri_p;
+#pragma unroll
+    for (int kk = 0; kk < N; ++kk) {
+        // unconditional: left of the pivot column the pivot row is already zero, at the pivot column the result is
+        // overwritten below, inactive rows have f = 0
+        const double sg = __shfl_sync(FULL_MASK, a[RP][kk], src);
+#pragma unroll
+        for (int r = 0; r < S; ++r) a[r][kk] = fma(-f[r], sg, a[r][kk]);
+    }
+    if (owner) {
+#pragma unroll
+        for (int r = 0; r < S; ++r)
+            if (act[r]) a[r][K] = 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+        const double sg = __shfl_sync(FULL_MASK, rhs[RP][q], src);
+#pragma unroll
+        for (int r = 0; r < S; ++r) rhs[r][q] = fma(-f[r], sg, rhs[r][q]);
+    }
+}
+
+template <int N, class Prob>
+__device__ __forceinline__ void staircase_solve_2d(const Prob& prob, double* gs, double* fac, int lane, bool valid,
+                                                   unsigned int* status) {
+    constexpr int NRHS = Prob::NRHS;
+    using C = BvpCfg3<N, NRHS>;
+    constexpr int NC = C::NC, S = C::S, RQ = C::RQ, RL2 = C::RL2, FS = C::FS, STAGES = C::STAGES, GL = 32;
+    const unsigned gmask = FULL_MASK;
+    const unsigned gbase = 0;
+    double* ring = gs;
+    double* xs = gs + STAGES * NC * FS;
+    const int g = lane >> 3, ri = lane & 7;
+
+    double a[S][N], rhs[S][RQ], pinvs[S];
+    bool act[S];
+    int pidx[S];
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+        act[r] = false;
+        pidx[r] = -1;
+        pinvs[r] = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) a[r][k] = 0.0;
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) rhs[r][q] = 0.0;
+    }
+    bool singular = false;
+    const int nsteps = prob.nsteps();
+
+    for (int step = 0; step < nsteps; ++step) {
+        const int par2 = 2 * (step & 1);       // group of window block 0
+        const int wb = (g - par2) & 3;          // window block held by this lane's group
+        {   // new rows -> free (ri, slot) positions, slot-major order; every group keeps identical bookkeeping
+            unsigned freeb[S];
+#pragma unroll
+            for (int r = 0; r < S; ++r) freeb[r] = __ballot_sync(FULL_MASK, !act[r]) & 0xffu;
+            const int needed = prob.nnew(step);
+            int before = 0;
+#pragma unroll
+            for (int r = 0; r < S; ++r) {
+                const int rank = before + __popc(freeb[r] & ((1u << ri) - 1u));
+                if (!act[r] && rank < needed) {
+                    act[r] = true;
+                    prob.load_seg(step, rank, wb, a[r]);
+#pragma unroll
+                    for (int q = 0; q < RQ; ++q) {
+                        const int col = 4 * q + g;  // right-hand-side column held by (group g, local q)
+                        rhs[r][q] = (col < NRHS) ? prob.load_rhs(step, rank, col) : 0.0;
+                    }
+                }
+                before += __popc(freeb[r]);
+            }
+        }
+        if (step + 1 < nsteps) prob.prefetch(step + 1, lane);
+        const int nleft = prob.nleft(step);
+        static_for<0, NC>([&](auto ic) {
+            constexpr int c = decltype(ic)::value;
+            if (c < nleft) {
+                const int go = (par2 + c / N) & 3;
+                const bool owner = (g == go);
+                // candidate key: high word of |a| with the slot number in its two lowest bits (lower slots win
+                // ties), so one REDUX.MAX + one ballot name the pivot row; resolution of the comparison 2^-18
+                unsigned kmax = 0u;
+#pragma unroll
+                for (int r = 0; r < S; ++r) {
+                    const unsigned kr = (owner && act[r]) ? (((unsigned)__double2hiint(fabs(a[r][c % N])) & ~3u) | (unsigned)(3 - r)) : 0u;
+                    kmax = kr > kmax ? kr : kmax;
+                }
+                const unsigned mx = __reduce_max_sync(FULL_MASK, kmax);
+                if ((mx & ~3u) == 0u) singular = true;
+                const unsigned b = __ballot_sync(FULL_MASK, kmax == mx);
+                const int rp = 3 - (int)(mx & 3u);
+                const int ri_p = (__ffs(b) - 1) & 7;
+                // rp is uniform over the warp: one specialised update per slot
+                if (S > 0 && rp == 0) pivot_update_2d<N, NRHS, c % N, 0>(a, rhs, act, pidx, pinvs, c, ri, g, go, ri_p);
+                if (S > 1 && rp == 1) pivot_update_2d<N, NRHS, c % N, (S > 1 ? 1 : 0)>(a, rhs, act, pidx, pinvs, c, ri, g, go, ri_p);
+                if (S > 2 && rp == 2) pivot_update_2d<N, NRHS, c % N, (S > 2 ? 2 : 0)>(a, rhs, act, pidx, pinvs, c, ri, g, go, ri_p);
+            }
+        });
+        // pivot rows of this step -> HBM (version-2 layout), then release the two finished window blocks
+#pragma unroll
+        for (int r = 0; r < S; ++r) {
+            if (pidx[r] >= 0) {
+                if (valid) {
+                    double* dst = fac + ((size_t)step * NC + pidx[r]) * FS;
+                    if (N % 2 == 0) {
+#pragma unroll
+                        for (int k = 0; k < N; k += 2)
+                            *reinterpret_cast<double2*>(dst + wb * N + k) = make_double2(a[r][k], a[r][k + 1 < N ? k + 1 : k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < N; ++k) dst[wb * N + k] = a[r][k];
+                    }
+#pragma unroll
+                    for (int q = 0; q < RQ; ++q)
+                        if (4 * q + g < NRHS) dst[4 * N + 4 * q + g] = rhs[r][q];
+                    if (g == 0) dst[RL2] = pinvs[r];
+                }
+                pidx[r] = -1;
+            }
+        }
+        if (wb < 2) {
+#pragma unroll
+            for (int r = 0; r < S; ++r)
+#pragma unroll
+                for (int k = 0; k < N; ++k) a[r][k] = 0.0;
+        }
+    }
+    if (singular && valid) atomicOr(status, 4u);
+    __threadfence_block();
+    __syncwarp();
+
+    // ---- back substitution (as in version 2; every factor block comes through the cp.async ring)
+    auto fetch_block = [&](int step) {
+        if (step >= 0) {
+            const double* src = fac + (size_t)step * NC * FS;
+            double* dst = ring + (step % STAGES) * NC * FS;
+#pragma unroll
+            for (int i = 0; i < (NC * FS / 2 + GL - 1) / GL; ++i) {
+                const int e = 2 * (lane + i * GL);
+                if (e < NC * FS) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + e) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int k = 1; k <= STAGES; ++k) fetch_block(nsteps - k);
+
+    if (NRHS == 1) {
+        for (int step = nsteps - 1; step >= 0; --step) {
+            const int nleft = prob.nleft(step);
+            const int nright = prob.nright(step);
+            if (STAGES == 3)
+                asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp(gmask);
+            const double* facs = ring + (step % STAGES) * NC * FS;
+            const int row = lane < nleft ? lane : 0;
+            const double* my = facs + row * FS;
+            double acc = my[4 * N];
+            for (int jx = 0; jx < nright; ++jx) acc = fma(-my[NC + jx], xs[jx], acc);
+            const double pinv = my[RL2];
+            double myx = 0.0;
+#pragma unroll
+            for (int cc = NC - 1; cc >= 0; --cc) {
+                if (cc < nleft) {
+                    double xv = acc * pinv;
+                    xv = __shfl_sync(gmask, xv, (int)gbase + cc);
+                    if (lane < cc) acc = fma(-my[cc], xv, acc);
+                    if (lane == cc) myx = xv;
+                }
+            }
+            __syncwarp(gmask);
+            if (lane < nleft) {
+                xs[lane] = myx;
+                if (valid) prob.store(step, lane, 0, myx);
+            }
+            __syncwarp(gmask);
+            fetch_block(step - STAGES);
+        }
+    } else {
+        const int r = lane < NRHS ? lane : 0;
+        double xn[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) xn[c] = 0.0;
+        for (int step = nsteps - 1; step >= 0; --step) {
+            const int nleft = prob.nleft(step);
+            const int nright = prob.nright(step);
+            if (STAGES == 3)
+                asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp(gmask);
+            const double* facs = ring + (step % STAGES) * NC * FS;
+            double acc[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                acc[c] = 0.0;
+                if (c < nleft) {
+                    const double* u = facs + c * FS;
+                    double s = u[4 * N + r];
+#pragma unroll
+                    for (int jx = 0; jx < NC; ++jx)
+                        if (jx < nright) s = fma(-u[NC + jx], xn[jx], s);
+                    acc[c] = s;
+                }
+            }
+#pragma unroll
+            for (int cc = NC - 1; cc >= 0; --cc) {
+                if (cc < nleft) {
+                    const double xv = acc[cc] * facs[cc * FS + RL2];
+                    acc[cc] = xv;
+#pragma unroll
+                    for (int c = 0; c < cc; ++c) acc[c] = fma(-facs[c * FS + cc], xv, acc[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                xn[c] = acc[c];
+                if (valid && lane < NRHS && c < nleft) prob.store(step, c, r, acc[c]);
+            }
+            __syncwarp(gmask);
+            fetch_block(step - STAGES);
+        }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(BvpCfg3<N, 1>::WARPS_PER_BLOCK * 32, 5) k_bvp_v3(ChunkView V) {
+    using C = BvpCfg3<N, 1>;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    long long prob = (long long)blockIdx.x * C::GROUPS_PER_BLOCK + wib;
+    const long long nprob = (long long)V.nw * V.M;
+    const bool valid = prob < nprob;
+    if (!valid) prob = nprob - 1;
+    const int w = (int)(prob / V.M), ms = (int)(prob % V.M);
+    ForwardRows<N> rows(V, w, ms);
+    double* fac = V.fac + (size_t)prob * V.fac_stride;
+    staircase_solve_2d<N>(rows, smem + (size_t)wib * C::SMEM_DOUBLES_PER_GROUP, fac, lane, valid, V.status);
+}
+
+template <int N, int NRHS>
+__global__ void __launch_bounds__(BvpCfg3<N, NRHS>::WARPS_PER_BLOCK * 32, 3) k_bvp_adjoint_v3(ChunkView V, int los0, int nbatch) {
+    using C = BvpCfg3<N, NRHS>;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    long long gid = (long long)blockIdx.x * C::GROUPS_PER_BLOCK + wib;
+    const long long ngroups = (long long)V.nw * V.M * nbatch;
+    const bool valid = gid < ngroups;
+    if (!valid) gid = ngroups - 1;
+    const int batch = (int)(gid % nbatch);
+    const long long prob = gid / nbatch;
+    const int w = (int)(prob / V.M), ms = (int)(prob % V.M);
+    AdjointRows<N, NRHS> rows(V, w, ms, los0 + batch * NRHS);
+    double* fac = V.fac + (size_t)gid * V.fac_stride;
+    staircase_solve_2d<N>(rows, smem + (size_t)wib * C::SMEM_DOUBLES_PER_GROUP, fac, lane, valid, V.status);
+}
+
 template <int N>
 __global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, BvpCfg2<N, 1>::MIN_BLOCKS) k_bvp_v2(ChunkView V) {
     using C = BvpCfg2<N, 1>;
@@ -584,10 +909,30 @@ __global__ void __launch_bounds__(BvpCfg<N, NRHS>::WARPS_PER_BLOCK * 32) k_bvp_a
                        V.status);
 }
 
+// SK_B200_BVP=3 selects the 2D-distributed elimination (version 3) for N = 8.  Measured on B200 it is within 10 % of
+// version 2 (bvp 10.5 vs 9.2, adjoint 16.1 vs 15.2 ms per 1000 wavelengths): version 2 is bound by shared-memory
+// instruction throughput, version 3 by issue/latency of its ~110 instructions per pivot (profiles/README.md).
+static bool bvp_use_2d() {
+    static const bool v = [] {
+        const char* e = std::getenv("SK_B200_BVP");
+        return e && e[0] == '3';
+    }();
+    return v;
+}
+
 template <int N>
 static void launch_bvp_n(const ChunkView& V, cudaStream_t s) {
     const long long nprob = (long long)V.nw * V.M;
-    if constexpr (3 * N <= 32) {
+    if (N == 8 && bvp_use_2d()) {
+        using C = BvpCfg3<N == 8 ? N : 8, 1>;
+        const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_bvp_v3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        k_bvp_v3<8><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
+    } else if constexpr (3 * N <= 32) {
         using C = BvpCfg2<N, 1>;
         const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
         static bool attr_set = false;
@@ -610,7 +955,17 @@ static void launch_bvp_n(const ChunkView& V, cudaStream_t s) {
 template <int N, int NRHS>
 static void launch_adj_batch(const ChunkView& V, int los0, int nbatch, cudaStream_t s) {
     const long long ngroups = (long long)V.nw * V.M * nbatch;
-    if constexpr (3 * N <= 32) {
+    if (N == 8 && bvp_use_2d()) {
+        using C = BvpCfg3<N == 8 ? N : 8, NRHS>;
+        const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_bvp_adjoint_v3<8, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        k_bvp_adjoint_v3<8, NRHS><<<(unsigned)((ngroups + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK),
+                                    C::WARPS_PER_BLOCK * 32, smem, s>>>(V, los0, nbatch);
+    } else if constexpr (3 * N <= 32) {
         using C = BvpCfg2<N, NRHS>;
         const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
         static bool attr_set = false;

@@ -99,6 +99,87 @@ struct ForwardRows {
             a[4 * N] = rhs;
         }
     }
+    // Segment loaders of the 2D-distributed elimination: window block wb (0..3) of new row `rank` of `step`,
+    // i.e. entries a[wb * N .. wb * N + N) of load(), and its right-hand side.
+    DISCO_HD void load_seg(int step, int rank, int wb, double* seg) const {
+        const int p = step;
+#pragma unroll
+        for (int j = 0; j < N; ++j) seg[j] = 0.0;
+        if (step == 0 && rank < N) {  // TOA rows
+            const int i = rank;
+            if (wb == 0) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) seg[j] = Wp[i * N + j];
+            } else if (wb == 1) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) seg[j] = Wm[i * N + j] * kth[N + j];
+            }
+            return;
+        }
+        if (step == 0) rank -= N;
+        const double* Wpu = Wp + (size_t)p * N * N;
+        const double* Wmu = Wm + (size_t)p * N * N;
+        const double* thu = kth + (size_t)p * 2 * N + N;
+        if (p < L - 1) {
+            const bool first = rank < N;
+            const int i = first ? rank : rank - N;
+            if (wb == 0) {
+                const double* A1 = first ? Wmu : Wpu;
+#pragma unroll
+                for (int j = 0; j < N; ++j) seg[j] = A1[i * N + j] * thu[j];
+            } else if (wb == 1) {
+                const double* A2 = first ? Wpu : Wmu;
+#pragma unroll
+                for (int j = 0; j < N; ++j) seg[j] = A2[i * N + j];
+            } else if (wb == 2) {
+                const double* B1 = first ? Wmu + N * N : Wpu + N * N;
+#pragma unroll
+                for (int j = 0; j < N; ++j) seg[j] = -B1[i * N + j];
+            } else {
+                const double* B2 = first ? Wpu + N * N : Wmu + N * N;
+                const double* thl = thu + 2 * N;
+#pragma unroll
+                for (int j = 0; j < N; ++j) seg[j] = -(B2[i * N + j] * thl[j]);
+            }
+        } else if (wb < 2) {  // ground rows
+            const int i = rank;
+            const bool refl = (m == 0);
+            const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
+            const double* surf = V.surf + (size_t)w * (2 * N + 1);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                if (wb == 0) {
+                    double vm = Wmu[i * N + j];
+                    if (refl) vm -= alb2 * surf[j];
+                    seg[j] = vm * thu[j];
+                } else {
+                    double vp = Wpu[i * N + j];
+                    if (refl) vp -= alb2 * surf[N + j];
+                    seg[j] = vp;
+                }
+            }
+        }
+    }
+    DISCO_HD double load_rhs(int step, int rank, int) const {
+        const int p = step;
+        if (step == 0 && rank < N) return -G[rank];
+        if (step == 0) rank -= N;
+        const double* Gu = G + (size_t)p * 4 * N;
+        if (p < L - 1) {
+            const double* Gl = Gu + 4 * N;
+            const bool first = rank < N;
+            const int i = first ? rank : rank - N;
+            return first ? (-Gu[3 * N + i] + Gl[N + i]) : (-Gu[2 * N + i] + Gl[i]);
+        }
+        const int i = rank;
+        double rhs = -Gu[3 * N + i];
+        if (m == 0) {
+            const double* surf = V.surf + (size_t)w * (2 * N + 1);
+            rhs += 2.0 * V.albedo[w] * surf[2 * N];
+            rhs += V.T.csz * V.albedo[w] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
+        }
+        return rhs;
+    }
     // lines of layer step+1 (the lower layer of interface step+1), one 128-byte line per lane
     DISCO_HD void prefetch(int step, int lane) const {
         const int p = step + 1;
@@ -187,6 +268,57 @@ struct AdjointRows {
             const size_t o = (((size_t)w * V.M + ms) * V.T.nlos + los) * L + b;
             a[4 * N + r] = (r < nl) ? V.wvec[o * 2 * N + rank] : 0.0;
         }
+    }
+    // Segment loaders of the 2D-distributed elimination (entries a[wb * N .. wb * N + N) of load())
+    DISCO_HD void load_seg(int step, int rank, int wb, double* seg) const {
+        const int b = step;
+        const bool isL = rank < N;
+        const int j = isL ? rank : rank - N;
+        const double* Wpb = Wp + (size_t)b * N * N;
+        const double* Wmb = Wm + (size_t)b * N * N;
+        const double th = kth[(size_t)b * 2 * N + N + j];
+#pragma unroll
+        for (int i = 0; i < N; ++i) seg[i] = 0.0;
+        if (wb == 0) {
+            if (b == 0) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) seg[i] = isL ? Wpb[i * N + j] : Wmb[i * N + j] * th;
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; ++i) seg[i] = isL ? -Wmb[i * N + j] : -(Wpb[i * N + j] * th);
+            }
+        } else if (wb == 1) {
+            if (b > 0) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) seg[i] = isL ? -Wpb[i * N + j] : -(Wmb[i * N + j] * th);
+            }
+        } else if (b < L - 1) {
+            if (wb == 2) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) seg[i] = isL ? Wmb[i * N + j] * th : Wpb[i * N + j];
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; ++i) seg[i] = isL ? Wpb[i * N + j] * th : Wmb[i * N + j];
+            }
+        } else if (wb == 2) {  // ground block [v- Theta | v+]
+            const bool refl = (m == 0);
+            const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
+            const double* surf = V.surf + (size_t)w * (2 * N + 1);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double vm = Wmb[i * N + j], vp = Wpb[i * N + j];
+                if (refl) {
+                    vm -= alb2 * surf[j];
+                    vp -= alb2 * surf[N + j];
+                }
+                seg[i] = isL ? vm * th : vp;
+            }
+        }
+    }
+    DISCO_HD double load_rhs(int step, int rank, int r) const {
+        if (r >= nl) return 0.0;
+        const size_t o = (((size_t)w * V.M + ms) * V.T.nlos + (los0 + r)) * L + step;
+        return V.wvec[o * 2 * N + rank];
     }
     // lines of layer `step`: W+-, k|theta and the wvec rows of the batch's lines of sight
     DISCO_HD void prefetch(int step, int lane) const {

@@ -61,6 +61,13 @@ def flop_model(nstr, nlayers, nlos, m_list, ngroups=1):
             "total_wf": layer + bvp + wf_adjoint + wf_layer}
 
 
+# DRAM bytes per wavelength (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, divided by
+# the 600 wavelengths of the profiled launch) for the default shape: 16 streams, 100 layers, 10 LOS, weighting
+# functions with one scattering group - profiles/ncu_r01_v5_summary.csv.  Other shapes report traffic = null.
+NCU_DRAM_BYTES_PER_WAVELENGTH = {"layer": (0.811 + 2.022 + 3.610) * 1e9 / 600, "bvp": 9.982e9 / 600,
+                                 "wf_adjoint": 14.144e9 / 600, "wf_layer": 3.496e9 / 600}
+
+
 def bytes_model(nloc, nleg, nlos, nwf_out=0):
     """Algorithmic HBM bytes per wavelength: inputs 8*nloc*(2+nleg) + outputs 8*nlos*(1 + sum nout)."""
     return 8.0 * nloc * (2 + nleg) + 8.0 * nlos * (1 + nwf_out)
@@ -371,7 +378,10 @@ def main():
     total_flops = fm["total_wf"] if with_wf else fm["total"]
     roofline = {
         "bound": "fp64", "kernel": per_k[dom]["kernel"], "achieved": per_k[dom]["achieved"], "peak": fp64_peak,
-        "unit": "TFLOP/s", "frac": per_k[dom]["frac"], "traffic": None,
+        "unit": "TFLOP/s", "frac": per_k[dom]["frac"],
+        "traffic": (NCU_DRAM_BYTES_PER_WAVELENGTH[dom] * (nw / nchunks) / launches_per_chunk[dom]
+                    if (args.nstr, args.layers, nlos, with_wf) == (16, 100, 10, True) else None),
+        "traffic_source": "profiles/ncu_r01_v5_summary.csv (dram bytes per wavelength of the profiled launch x wavelengths per launch)",
         "peak_source": "DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP64 figure)",
         "share_of_step": per_k[dom]["share_of_step"], "avg_launch_ms": per_k[dom]["avg_launch_ms"],
         "flops_per_launch": per_k[dom]["flops_per_launch"],

@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=48.0,
                     help="device workspace per wavelength chunk (B200: 180 GB HBM3e)")
-    ap.add_argument("--cpu-wf-sample", type=int, default=0,
+    ap.add_argument("--cpu-wf-sample", type=int, default=8,
                     help="also time the CPU port WITH weighting functions (forward-mode duals) on this many wavelengths")
     ap.add_argument("--wf", type=int, default=1, help="1: with weighting functions (O3, NO2, aerosol mappings + albedo), 0: radiances only")
     args = ap.parse_args()
@@ -418,9 +418,10 @@ def main():
         v, dt = time_oracle(sc, args.cpu_sample, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_sample} wavelengths x {nlos} LOS of the same atmosphere, oracle port "
-                                          f"with OpenMP over wavelengths, {dt:.1f} s; VALUES ONLY - the port linearises in "
-                                          f"forward mode only, so this is an upper bound for the CPU path with weighting "
-                                          f"functions (the reference's default reverse mode costs ~2.5-3x values only)"}
+                                          f"with OpenMP over wavelengths, {dt:.1f} s; VALUES ONLY, i.e. an upper bound for the "
+                                          f"CPU path with weighting functions: the reference's default (do_backprop = false, "
+                                          f"cpp/lib/config/config.cpp:14) linearises in forward mode like the port "
+                                          f"(with_wf_forward_mode below), its optional reverse mode costs ~2.5-3x values only"}
         if args.cpu_wf_sample > 0:
             v2, dt2 = time_oracle(sc, args.cpu_wf_sample, cores, with_wf=True)
             line["cpu_baseline"]["with_wf_forward_mode"] = {"value": v2, "sample": f"{args.cpu_wf_sample} wavelengths, {dt2:.1f} s"}

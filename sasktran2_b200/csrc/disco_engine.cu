@@ -41,6 +41,13 @@ DeviceEngine::DeviceEngine(const EngineOptions& opt, const HostPlan& plan) : m_o
     if (opt.device >= 0) CUDA_OK(cudaSetDevice(opt.device));
     if (!nstr_supported(plan.nstr))
         throw std::runtime_error("sasktran2_b200: num_streams must be one of 2, 4, 8, 16, 32");
+    if (m_opt.workspace_gb <= 0.0) {
+        // a chunk should hold thousands of wavelengths (tens of thousands of warps per launch) so that the last
+        // wave of every kernel is a small fraction of it; B200 has 180 GB
+        size_t free_b = 0, total_b = 0;
+        CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+        m_opt.workspace_gb = std::min(32.0, 0.25 * (double)free_b / (1024.0 * 1024.0 * 1024.0));
+    }
     CUDA_OK(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking));
     for (auto& ev : m_ev) CUDA_OK(cudaEventCreate(&ev));
     d_mu = upload(plan.mu);

@@ -15,7 +15,7 @@ struct EngineOptions {
     int nstr = 16;
     bool include_ss = true;     // single_scatter_source == discrete_ordinates
     int forced_azimuth = -1;    // num_do_forced_azimuth (<= 0: all nstr orders)
-    double workspace_gb = 8.0;  // per-chunk workspace budget
+    double workspace_gb = -1.0; // per-chunk workspace budget; < 0: min(32 GB, a quarter of the free device memory)
     int device = -1;            // -1: current device
 };
 

@@ -163,9 +163,11 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         }
         for (int los = 0; los < nlos; ++los) {
             const double* __restrict__ tl = tL + los * NSTR + m;
-            double a = 0.0, b = 0.0, da[G > 0 ? G : 1], db[G > 0 ? G : 1];
+            // even and odd (l - m) accumulated separately: two independent DFMA chains per sum, and
+            // lps_minus = even + odd, lps_plus = even - odd without the sign flips
+            double ae = 0.0, ao = 0.0, dae[G > 0 ? G : 1], dao[G > 0 ? G : 1];
 #pragma unroll
-            for (int g = 0; g < G; ++g) da[g] = db[g] = 0.0;
+            for (int g = 0; g < G; ++g) dae[g] = dao[g] = 0.0;
 #pragma unroll
             for (int c = 0; c < NSTR / 4; ++c) {
                 if (4 * c < nl) {
@@ -173,24 +175,25 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
                     for (int r = 0; r < 4; ++r) {
                         const int lo = 4 * c + r;
                         const double x = tl[lo] * tq[lo];
-                        const double sx = (lo & 1) ? -x : x;
-                        a = fma(ob[lo], x, a);
-                        b = fma(ob[lo], sx, b);
+                        if (lo & 1) {
+                            ao = fma(ob[lo], x, ao);
 #pragma unroll
-                        for (int g = 0; g < G; ++g) {
-                            da[g] = fma(obd[g][lo], x, da[g]);
-                            db[g] = fma(obd[g][lo], sx, db[g]);
+                            for (int g = 0; g < G; ++g) dao[g] = fma(obd[g][lo], x, dao[g]);
+                        } else {
+                            ae = fma(ob[lo], x, ae);
+#pragma unroll
+                            for (int g = 0; g < G; ++g) dae[g] = fma(obd[g][lo], x, dae[g]);
                         }
                     }
                 }
             }
             double* o = lpsS + (size_t)los * 2 * NH * N;
-            o[j] = a;          // lps_minus
-            o[N + j] = b;      // lps_plus
+            o[j] = ae + ao;      // lps_minus
+            o[N + j] = ae - ao;  // lps_plus
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                o[(2 + 2 * g) * N + j] = da[g];
-                o[(3 + 2 * g) * N + j] = db[g];
+                o[(2 + 2 * g) * N + j] = dae[g] + dao[g];
+                o[(3 + 2 * g) * N + j] = dae[g] - dao[g];
             }
         }
     }
@@ -317,6 +320,24 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         }
     }
     __syncwarp();  // the exchange area is reused by the LOS reduction below
+    // Stage the adjoint solution slices of every LOS (the 4N entries of z on the layer's two boundaries) into the
+    // head of that LOS's reduction row with cp.async: the HBM latency overlaps pass 3 and the scalar set-up instead of
+    // stalling every LOS iteration (2 warps per scheduler cannot hide it).  Layout per LOS: zt[2N] | zb[2N].
+    {
+        const bool bottom_ = (p == L - 1);
+        for (int los = 0; los < nlos; ++los) {
+            const double* z = V.zadj + (((size_t)w * M + ms) * nlos + los) * ((size_t)2 * N * L);
+            const double* zt = (p == 0) ? z : z + N + (size_t)(p - 1) * 2 * N;
+            const double* zb = z + N + (size_t)p * 2 * N;
+            double* dst = red + (size_t)los * (NL + 1) * N;
+            const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst + j);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0), "l"(zt + j) : "memory");
+            if (p != 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + 8u * N), "l"(zt + N + j) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + 16u * N), "l"(zb + j) : "memory");
+            if (!bottom_) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + 24u * N), "l"(zb + N + j) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 
     // ---- pass 3: Green's coefficients A+-_j with heavy-lane derivatives
     double ap, am, dap[NH], dam[NH];
@@ -445,31 +466,72 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         gsum_v = 2.0 * (surf[2 * N] + s);
     }
 
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // per-LOS scalars are fetched one iteration ahead (software pipelining of the global loads)
+    double n_mu, n_att, n_E, n_inv, n_atop;
+    {
+        const double* ll = V.los_lay + (((size_t)w * nlos + 0) * L + p) * 3;
+        n_mu = V.T.los_mu[0];
+        n_att = ll[0];
+        n_E = ll[1];
+        n_inv = ll[2];
+        n_atop = V.los_att[((size_t)w * nlos + 0) * (L + 1) + p];
+    }
     for (int los = 0; los < nlos; ++los) {
-        const double mu = V.T.los_mu[los];
-        const double* __restrict__ ll = V.los_lay + (((size_t)w * nlos + los) * L + p) * 3;
-        const double att = ll[0], E = ll[1], inv_1mus = ll[2];
-        const double att_top = V.los_att[((size_t)w * nlos + los) * (L + 1) + p];
+        const double mu = n_mu, att = n_att, E = n_E, inv_1mus = n_inv, att_top = n_atop;
+        {
+            const int ln = los + 1 < nlos ? los + 1 : los;
+            const double* ll = V.los_lay + (((size_t)w * nlos + ln) * L + p) * 3;
+            n_mu = V.T.los_mu[ln];
+            n_att = ll[0];
+            n_E = ll[1];
+            n_inv = ll[2];
+            n_atop = V.los_att[((size_t)w * nlos + ln) * (L + 1) + p];
+        }
         // -- source part: Y+-_j and heavy-lane derivatives from the shared phase sums
         const double* __restrict__ ls = lpsS + (size_t)los * 2 * NH * N;
         double Yp = 0.0, Ym = 0.0, dYp[NH], dYm[NH];
+        {
+            // the "b" and "a" halves of every sum are separate DFMA chains (latency, not throughput, limits this
+            // kernel at 8 warps per SM)
+            double Ypa = 0.0, Yma = 0.0, dYpa[NH], dYma[NH], dYpg[G > 0 ? G : 1], dYmg[G > 0 ? G : 1];
 #pragma unroll
-        for (int e = 0; e < NH; ++e) dYp[e] = dYm[e] = 0.0;
+            for (int e = 0; e < NH; ++e) dYp[e] = dYm[e] = dYpa[e] = dYma[e] = 0.0;
 #pragma unroll
-        for (int qq = 0; qq < N; ++qq) {
-            const double a = ls[qq], b = ls[N + qq];  // lps_minus, lps_plus
-            Yp = fma(b, wp[qq], fma(a, wm[qq], Yp));
-            Ym = fma(b, wm[qq], fma(a, wp[qq], Ym));
+            for (int g = 0; g < G; ++g) dYpg[g] = dYmg[g] = 0.0;
+#pragma unroll
+            for (int qq = 0; qq < N; ++qq) {
+                const double a = ls[qq], b = ls[N + qq];  // lps_minus, lps_plus
+                Yp = fma(b, wp[qq], Yp);
+                Ypa = fma(a, wm[qq], Ypa);
+                Ym = fma(b, wm[qq], Ym);
+                Yma = fma(a, wp[qq], Yma);
+#pragma unroll
+                for (int e = 0; e < NH; ++e) {
+                    dYp[e] = fma(b, dwp[e][qq], dYp[e]);
+                    dYpa[e] = fma(a, dwm[e][qq], dYpa[e]);
+                    dYm[e] = fma(b, dwm[e][qq], dYm[e]);
+                    dYma[e] = fma(a, dwp[e][qq], dYma[e]);
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const double da = ls[(2 + 2 * g) * N + qq], db = ls[(3 + 2 * g) * N + qq];
+                    dYpg[g] = fma(db, wp[qq], fma(da, wm[qq], dYpg[g]));
+                    dYmg[g] = fma(db, wm[qq], fma(da, wp[qq], dYmg[g]));
+                }
+            }
+            Yp += Ypa;
+            Ym += Yma;
 #pragma unroll
             for (int e = 0; e < NH; ++e) {
-                dYp[e] = fma(b, dwp[e][qq], fma(a, dwm[e][qq], dYp[e]));
-                dYm[e] = fma(b, dwm[e][qq], fma(a, dwp[e][qq], dYm[e]));
+                dYp[e] += dYpa[e];
+                dYm[e] += dYma[e];
             }
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const double da = ls[(2 + 2 * g) * N + qq], db = ls[(3 + 2 * g) * N + qq];
-                dYp[g] = fma(db, wp[qq], fma(da, wm[qq], dYp[g]));
-                dYm[g] = fma(db, wm[qq], fma(da, wp[qq], dYm[g]));
+                dYp[g] += dYpg[g];
+                dYm[g] += dYmg[g];
             }
         }
         {
@@ -545,9 +607,8 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         for (int c = 0; c < NL; ++c) out[c] *= att_top;
 
         // -- adjoint part: zeta slices of z on the two boundaries of the layer
-        const double* __restrict__ z = V.zadj + (((size_t)w * M + ms) * nlos + los) * nrow;
-        const double* __restrict__ zt = (p == 0) ? z : z + N + (size_t)(p - 1) * 2 * N;
-        const double* __restrict__ zb = z + N + (size_t)p * 2 * N;
+        const double* zt = red + (size_t)los * (NL + 1) * N;  // staged above
+        const double* zb = zt + 2 * N;
         double zg_sum = 0.0;
         if (bottom) {
 #pragma unroll
@@ -555,9 +616,10 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         }
         const double attg = bottom ? V.los_att[((size_t)w * nlos + los) * (L + 1) + L] : 0.0;
         double s21 = 0.0, s34 = 0.0;          // W+.zeta2 + W-.zeta1,  W+.zeta3 + W-.zeta4
-        double dadj[NH];
+        double s21b = 0.0, s34b = 0.0;        // second halves (independent DFMA chains)
+        double dadj[NH], dadjb[NH];
 #pragma unroll
-        for (int e = 0; e < NH; ++e) dadj[e] = 0.0;
+        for (int e = 0; e < NH; ++e) dadj[e] = dadjb[e] = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             double z1, z2, z3, z4;
@@ -575,16 +637,26 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
                 z3 = refl ? 2.0 * wmu[i] * albedo * (zg_sum + attg) : 0.0;
             const double xp = fma(Lj, z1, fma(Aj, z2, fma(Bj, z3, Mj * z4)));
             const double xm = fma(Aj, z1, fma(Lj, z2, fma(Mj, z3, Bj * z4)));
-            s21 = fma(wp[i], z2, fma(wm[i], z1, s21));
-            s34 = fma(wp[i], z3, fma(wm[i], z4, s34));
+            s21 = fma(wp[i], z2, s21);
+            s21b = fma(wm[i], z1, s21b);
+            s34 = fma(wp[i], z3, s34);
+            s34b = fma(wm[i], z4, s34b);
 #pragma unroll
-            for (int e = 0; e < NH; ++e) dadj[e] = fma(dwp[e][i], xp, fma(dwm[e][i], xm, dadj[e]));
+            for (int e = 0; e < NH; ++e) {
+                dadj[e] = fma(dwp[e][i], xp, dadj[e]);
+                dadjb[e] = fma(dwm[e][i], xm, dadjb[e]);
+            }
         }
+        s21 += s21b;
+        s34 += s34b;
+#pragma unroll
+        for (int e = 0; e < NH; ++e) dadj[e] += dadjb[e];
 #pragma unroll
         for (int c = 0; c < NL; ++c) out[c] = fma(dA[c], s21, fma(dB[c], s34, out[c]));
 #pragma unroll
         for (int e = 0; e < NH; ++e) out[e < G ? e : iOm] += dadj[e];
-        // -- partials of this solution -> reduction buffer
+        // -- partials of this solution -> reduction buffer (over the staged z of this LOS: everyone is done reading)
+        __syncwarp();
         double* r = red + (size_t)los * (NL + 1) * N;
 #pragma unroll
         for (int c = 0; c < NL; ++c) r[c * N + j] = out[c];

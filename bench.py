@@ -247,15 +247,9 @@ def main():
 
     start, count = wavelength_block(nw_total, rank, world)
     with_wf = bool(args.wf)
-    sc = scenarios.config2(nwavel=nw_total, nlayers=args.layers, nstr=args.nstr, nlos=args.nlos, with_wf=with_wf) if world == 1 else None
-    if sc is None:
-        # build only this rank's block (same formulae; block boundaries chosen by wavelength_block)
-        full_axis = scenarios.config2  # noqa: F841
-        sc_full = scenarios.config2(nwavel=nw_total, nlayers=args.layers, nstr=args.nstr, nlos=args.nlos, with_wf=with_wf)
-        from sasktran2_b200.parallel import shard_scenario
-
-        sc, start, count = shard_scenario(sc_full, rank, world)
-        del sc_full
+    # every rank builds only its own block of the global spectrum (same formulae as the full scenario)
+    sc = scenarios.config2(nwavel=nw_total, nlayers=args.layers, nstr=args.nstr, nlos=args.nlos, with_wf=with_wf,
+                           block=(start, count))
     sk._lib.check(sk._lib.lib().sk_b200_set_device(local_rank), "set_device")
     _, geo, view, eng, atm = sk.engine_for_scenario(sc)
     if with_wf:

@@ -107,13 +107,18 @@ def config1(nwavel: int = 1000, nlayers: int = 50) -> Scenario:
 
 
 def config2(nwavel: int = 100000, nlayers: int = 100, nstr: int = 16, nlos: int = 10, with_wf: bool = False,
-            seed: int = 0) -> Scenario:
+            seed: int = 0, block: tuple[int, int] | None = None) -> Scenario:
     """C2 (and C5 when with_wf): pseudo-spherical DO, 16 streams, 100 layers, Rayleigh + aerosol (+ O3/NO2
-    absorbers so the atmosphere is not conservative), 10 ground-viewing LOS."""
+    absorbers so the atmosphere is not conservative), 10 ground-viewing LOS.
+
+    `block = (start, count)` builds only wavelengths [start, start + count) of the `nwavel`-point spectrum (what one
+    rank of a wavelength-sharded run owns); the arrays equal the corresponding slices of the full scenario."""
     nleg = nstr
     z = np.linspace(0.0, 100e3, nlayers + 1)
-    lam_frac = np.arange(nwavel) / max(nwavel - 1, 1)
-    s = np.logspace(-1, 1, nwavel)
+    widx = np.arange(nwavel) if block is None else np.arange(block[0], block[0] + block[1])
+    lam_frac = widx / max(nwavel - 1, 1)
+    s = 10.0 ** (-1.0 + 2.0 * lam_frac) if nwavel > 1 else np.array([0.1])
+    nwavel = widx.size
     k_ray = rayleigh_extinction(z)[:, None] * s[None, :]
     k_aer = (1e-5 * np.exp(-z / 3e3))[:, None] * np.ones(nwavel)[None, :]
     n_air = np.exp(-z / 7400.0)

@@ -537,33 +537,58 @@ struct BvpCfg3 {
     static_assert(NC <= 32 && (NRHS == 1 || NRHS <= 32), "back substitution lanes");
 };
 
-// one pivot of the 2D elimination with the pivot row in slot RP (uniform over the warp)
-template <int N, int NRHS, int K, int RP>
+// One pivot of the 2D elimination.  The four lanes that hold the pivot row (row lane ri_p, slot rp - both uniform
+// over the warp) publish their N-column segments and right-hand-side entries in the broadcast buffer `bc`
+// (4 x STS.128 warp-wide instead of 17 from one lane); everyone reads its own group's segment back (uniform per
+// group), the multipliers travel from the owner group by shuffle.
+//   bc layout: [4 groups][N] segments | [4 groups][RQ] right-hand sides
+template <int N, int NRHS, int K>
 __device__ __forceinline__ void pivot_update_2d(double (&a)[BvpCfg3<N, NRHS>::S][N], double (&rhs)[BvpCfg3<N, NRHS>::S][BvpCfg3<N, NRHS>::RQ],
                                                 bool (&act)[BvpCfg3<N, NRHS>::S], int (&pidx)[BvpCfg3<N, NRHS>::S],
-                                                double (&pinvs)[BvpCfg3<N, NRHS>::S], int c, int ri, int g, int go, int ri_p) {
+                                                double (&pinvs)[BvpCfg3<N, NRHS>::S], double* bc, int c, int ri, int g, int go,
+                                                int ri_p, int rp) {
     using C = BvpCfg3<N, NRHS>;
     constexpr int S = C::S, RQ = C::RQ;
     const bool owner = (g == go);
-    const double pv = __shfl_sync(FULL_MASK, a[RP][K], go * 8 + ri_p);
-    const double pinv = rcp_pivot(pv);
-    if (ri == ri_p) {
-        act[RP] = false;
-        pidx[RP] = c;
-        pinvs[RP] = pinv;
+    const bool mine = (ri == ri_p);
+    double* seg_out = bc + g * N;
+    double* rhs_out = bc + 4 * N + g * RQ;
+    // rp is uniform over the warp: real branches (the barrier inside keeps the compiler from predicating the stores
+    // of all S slots - a predicated-off STS.128 still costs its MIO cycles)
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+        if (r == rp) {
+            if (mine) {
+                if (N % 2 == 0) {
+#pragma unroll
+                    for (int kk = 0; kk < N; kk += 2)
+                        *reinterpret_cast<double2*>(seg_out + kk) = make_double2(a[r][kk], a[r][kk + 1 < N ? kk + 1 : kk]);
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < N; ++kk) seg_out[kk] = a[r][kk];
+                }
+#pragma unroll
+                for (int q = 0; q < RQ; ++q) rhs_out[q] = rhs[r][q];
+                act[r] = false;
+                pidx[r] = c;
+            }
+            __syncwarp();
+        }
     }
+    if (rp < 0 || rp >= S) __syncwarp();
+    const double pinv = rcp_pivot(bc[go * N + K]);
     double f[S];
 #pragma unroll
     for (int r = 0; r < S; ++r) {
+        if (mine && r == rp) pinvs[r] = pinv;
         const double fr = (owner && act[r]) ? a[r][K] * pinv : 0.0;
         f[r] = __shfl_sync(FULL_MASK, fr, go * 8 + ri);
     }
-    const int src = g * 8 + ri_p;
+    // unconditional updates: left of the pivot column the pivot row is already zero, at the pivot column the result
+    // is overwritten below, inactive rows (and the pivot row itself) have f = 0
 #pragma unroll
     for (int kk = 0; kk < N; ++kk) {
-        // unconditional: left of the pivot column the pivot row is already zero, at the pivot column the result is
-        // overwritten below, inactive rows have f = 0
-        const double sg = __shfl_sync(FULL_MASK, a[RP][kk], src);
+        const double sg = seg_out[kk];
 #pragma unroll
         for (int r = 0; r < S; ++r) a[r][kk] = fma(-f[r], sg, a[r][kk]);
     }
@@ -574,7 +599,7 @@ __device__ __forceinline__ void pivot_update_2d(double (&a)[BvpCfg3<N, NRHS>::S]
     }
 #pragma unroll
     for (int q = 0; q < RQ; ++q) {
-        const double sg = __shfl_sync(FULL_MASK, rhs[RP][q], src);
+        const double sg = rhs_out[q];
 #pragma unroll
         for (int r = 0; r < S; ++r) rhs[r][q] = fma(-f[r], sg, rhs[r][q]);
     }
@@ -653,9 +678,9 @@ __device__ __forceinline__ void staircase_solve_2d(const Prob& prob, double* gs,
                 const int rp = 3 - (int)(mx & 3u);
                 const int ri_p = (__ffs(b) - 1) & 7;
                 // rp is uniform over the warp: one specialised update per slot
-                if (S > 0 && rp == 0) pivot_update_2d<N, NRHS, c % N, 0>(a, rhs, act, pidx, pinvs, c, ri, g, go, ri_p);
-                if (S > 1 && rp == 1) pivot_update_2d<N, NRHS, c % N, (S > 1 ? 1 : 0)>(a, rhs, act, pidx, pinvs, c, ri, g, go, ri_p);
-                if (S > 2 && rp == 2) pivot_update_2d<N, NRHS, c % N, (S > 2 ? 2 : 0)>(a, rhs, act, pidx, pinvs, c, ri, g, go, ri_p);
+                // two alternating broadcast buffers: one __syncwarp per pivot is enough
+                pivot_update_2d<N, NRHS, c % N>(a, rhs, act, pidx, pinvs, ring + (c & 1) * (4 * N + 4 * RQ), c, ri, g, go,
+                                                ri_p, rp);
             }
         });
         // pivot rows of this step -> HBM (version-2 layout), then release the two finished window blocks
@@ -791,7 +816,7 @@ __device__ __forceinline__ void staircase_solve_2d(const Prob& prob, double* gs,
 }
 
 template <int N>
-__global__ void __launch_bounds__(BvpCfg3<N, 1>::WARPS_PER_BLOCK * 32, 5) k_bvp_v3(ChunkView V) {
+__global__ void __launch_bounds__(BvpCfg3<N, 1>::WARPS_PER_BLOCK * 32, 4) k_bvp_v3(ChunkView V) {
     using C = BvpCfg3<N, 1>;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;

@@ -121,8 +121,21 @@ struct ForwardRows {
         const double* Wmu = Wm + (size_t)p * N * N;
         const double* thu = kth + (size_t)p * 2 * N + N;
         if (p < L - 1) {
+            // interior interface rows, branch-free: the matrix is W+ when (wb odd) == (first half), the layer is
+            // p + (wb >> 1), blocks 0 and 3 carry the layer's theta, blocks 2 and 3 a minus sign
             const bool first = rank < N;
             const int i = first ? rank : rank - N;
+            {
+                const int lay = p + (wb >> 1);
+                const bool plus = ((wb & 1) != 0) == first;
+                const double* Mx = (plus ? Wp : Wm) + (size_t)lay * N * N + i * N;
+                const double* th = kth + (size_t)lay * 2 * N + N;
+                const bool scaled = (wb == 0) || (wb == 3);
+                const double sgn = (wb >= 2) ? -1.0 : 1.0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) seg[j] = sgn * Mx[j] * (scaled ? th[j] : 1.0);
+                return;
+            }
             if (wb == 0) {
                 const double* A1 = first ? Wmu : Wpu;
 #pragma unroll
@@ -279,6 +292,16 @@ struct AdjointRows {
         const double th = kth[(size_t)b * 2 * N + N + j];
 #pragma unroll
         for (int i = 0; i < N; ++i) seg[i] = 0.0;
+        if (b > 0 && b < L - 1) {
+            // interior layers, branch-free: W+ when (wb odd) == isL, theta_j when (wb >= 2) == isL, minus for wb < 2
+            const bool plus = ((wb & 1) != 0) == isL;
+            const double* Mx = (plus ? Wpb : Wmb) + j;
+            const double sc = (((wb >> 1) != 0) == isL) ? th : 1.0;
+            const double f = (wb < 2) ? -sc : sc;
+#pragma unroll
+            for (int i = 0; i < N; ++i) seg[i] = f * Mx[i * N];
+            return;
+        }
         if (wb == 0) {
             if (b == 0) {
 #pragma unroll

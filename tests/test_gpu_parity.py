@@ -339,3 +339,38 @@ def test_cuda_kernel_variants_agree(tmp_path):
             err = np.abs(other[k] - base[k]) / scale
             tol = 1e-4 if "aerosol" in k else 1e-8
             assert err.max() <= tol, (tag, k, float(err.max()))
+
+
+def test_cuda_large_spectrum_properties():
+    """Size-independent properties at a production-size spectrum (3000 wavelengths x 16 orders x 100 layers x 10
+    LOS with weighting functions, ~0.3 s per solve): chunked == unchunked bit for bit, a wavelength block solved
+    alone == the same wavelengths inside the full solve, outputs finite, radiances positive, and the albedo
+    weighting function positive (more reflection, more light)."""
+    import sasktran2_b200 as sk
+    from sasktran2_b200 import scenarios
+
+    nw = 3000
+    sc = scenarios.config2(nwavel=nw, with_wf=True)
+    _, _, _, eng, atm = sk.engine_for_scenario(sc)
+    atm.surface.enable_albedo_derivative("wf_albedo")
+    # one chunk: the per-wavelength figure reported before staging does not include the weighting-function arrays
+    eng.set_workspace_gb(eng.info()["workspace_mb_per_wavelength"] * 2.0 * nw / 1024.0)  # ~80 GB of the 180
+    full = eng.calculate_radiance(atm)
+    for k, v in full.items():
+        if not k.startswith("_"):
+            assert np.all(np.isfinite(v)), k
+    assert np.all(full["radiance"] > 0) and np.all(full["wf_albedo"] > 0)
+    assert eng.info()["chunk_wavelengths"] == nw
+    eng.set_workspace_gb(eng.info()["workspace_mb_per_wavelength"] * 700 / 1024.0)
+    assert eng.info()["chunk_wavelengths"] == 700
+    chunked = eng.calculate_radiance(atm)
+    for k in full:
+        if not k.startswith("_"):
+            np.testing.assert_array_equal(chunked[k], full[k])
+    blk = scenarios.config2(nwavel=nw, with_wf=True, block=(1500, 700))
+    _, _, _, eng2, atm2 = sk.engine_for_scenario(blk)
+    atm2.surface.enable_albedo_derivative("wf_albedo")
+    part = eng2.calculate_radiance(atm2)
+    np.testing.assert_array_equal(part["radiance"], full["radiance"][1500:2200])
+    np.testing.assert_array_equal(part["wf_o3_vmr"], full["wf_o3_vmr"][:, 1500:2200])
+    np.testing.assert_array_equal(part["wf_aerosol_extinction"], full["wf_aerosol_extinction"][:, 1500:2200])

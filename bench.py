@@ -192,7 +192,8 @@ def main():
     ap.add_argument("--nstr", type=int, default=16)
     ap.add_argument("--layers", type=int, default=100)
     ap.add_argument("--nlos", type=int, default=10)
-    ap.add_argument("--cpu-sample", type=int, default=48)
+    ap.add_argument("--cpu-sample", type=int, default=4000,
+                    help="wavelengths of the CPU-port sample (values only; ~10 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=48.0,
                     help="device workspace per wavelength chunk (B200: 180 GB HBM3e)")

@@ -240,6 +240,7 @@ struct BvpCfg2 {
     static constexpr int ROWLEN = 4 * N + NRHS;
     static constexpr int RL2 = (ROWLEN + 1) & ~1;
     static constexpr int FS = RL2 + 2;                    // row stride: padded row | 1/pivot | pad
+    static constexpr int LS = (ROWS + 2) & ~1;            // multiplier row stride: one per panel lane | (pivot lane, row) | pad
     static constexpr int GROUPS_PER_WARP = 32 / GL;
     static constexpr int WARPS_PER_BLOCK = 4;
     static constexpr int GROUPS_PER_BLOCK = GROUPS_PER_WARP * WARPS_PER_BLOCK;
@@ -249,6 +250,7 @@ struct BvpCfg2 {
     static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS + NC;   // factor block ring | x of the block below (NRHS = 1)
     static_assert(ROWS <= GL * R && NC <= GL, "panel rows fit the group; one pivot row per lane in the back substitution");
     static_assert(NRHS == 1 || NRHS <= GL, "one right-hand side per lane");
+    static_assert(NRHS > 1 || (R == 1 && ROWS < GL), "a spare lane records the pivot's (lane, row) next to the multipliers");
 };
 
 // 1/x without the library's slow-path call on the critical path of every pivot: MUFU seed, two Newton steps and
@@ -266,7 +268,7 @@ __device__ __forceinline__ double rcp_pivot(double x) {
 
 template <int N, class Prob>
 __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs, double* fac, int lane, unsigned gbase,
-                                                   unsigned gmask, bool valid, unsigned int* status) {
+                                                   unsigned gmask, bool valid, unsigned int* status, double* lf = nullptr) {
     constexpr int NRHS = Prob::NRHS;
     using C = BvpCfg2<N, NRHS>;
     constexpr int NC = C::NC, GL = C::GL, ROWLEN = C::ROWLEN, RL2 = C::RL2, FS = C::FS;
@@ -280,6 +282,7 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
     constexpr int R = C::R;
     double a[R][ROWLEN];
     bool act[R];
+    int myrow = 0;  // row of A held by this lane (kept for the multiplier record, R = 1)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         act[r] = false;
@@ -288,6 +291,7 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
     }
     bool singular = false;
     const int nsteps = prob.nsteps();
+    constexpr int LS = C::LS;
 
     for (int step = 0; step < nsteps; ++step) {
         {   // new rows of this step go to the lowest free slots (slot id = lane * R + r)
@@ -311,6 +315,7 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
                     if (rank < needed) {
                         act[r] = true;
                         prob.load(step, rank, a[r]);
+                        if (Prob::KEEPS_L) myrow = prob.row_of(step, rank);
                     }
                 }
             }
@@ -357,6 +362,15 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
                     }
                 }
                 __syncwarp(gmask);
+                if (Prob::KEEPS_L && lf != nullptr) {
+                    // record of this pivot for transposed solves with the same factors (k_bvp_tsolve): lane i < 3N
+                    // writes its multiplier (0 when it holds no candidate row), the spare lane 3N the pivot's lane and row
+                    const int plane = __ffs(cand) - 1;
+                    const int prow = __shfl_sync(gmask, myrow, plane);
+                    const double fi = act[0] ? a[0][c] * bc[RL2] : 0.0;
+                    const double rec = (lane < C::ROWS) ? fi : __hiloint2double(prow, plane - (int)gbase);
+                    if (valid && lane <= C::ROWS) lf[((size_t)step * NC + c) * LS + lane] = rec;
+                }
                 {
                     bool any_left = false;
 #pragma unroll
@@ -866,7 +880,172 @@ __global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, BvpCfg2<N
     ForwardRows<N> rows(V, w, ms);
     double* fac = V.fac + (size_t)prob * V.fac_stride;
     staircase_solve_v2<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
-                          V.status);
+                          V.status, V.lfac ? V.lfac + (size_t)prob * V.lfac_stride : nullptr);
+}
+
+// -------------------------------------------------------------------------------------------------
+// K3^T by factor reuse: A^T z = wvec(los) from the factors of the FORWARD elimination - what the reference does with
+// dgbtrs('T') after dgbsv (sktran_do_rte.cpp:1793-1836) - instead of a second factorisation of A^T.
+// The forward kernel (k_bvp_v2 with V.lfac set) leaves, per pivot t = (step, c):
+//   fac [t][FS]: row t of U right of the diagonal (window columns c+1 .. 4N-1 of the step) and 1 / pivot;
+//   lfac[t][LS]: the multiplier f_t[i] of every panel lane i (0 where the lane held no candidate row) and the
+//                pivot's (lane, row of A).
+// With E_t = I - f_t e_{p_t}^T the elimination reads E_n .. E_1 A = P^T U, so
+//   phase 1 (t ascending):  U^T y = wvec        - y_t = w_t / u_tt, then w_cc -= u_{t,cc} y_t over the window;
+//   phase 2 (t descending): z = E_1^T .. E_n^T P^T y - z[row_t] = y_t - sum_i f_t[i] v[i], v[lane_t] = z[row_t],
+// where v[i] is the value of the row currently (in elimination order) held by panel lane i.
+// Mapping: one lane per line of sight, `glt` lanes per (wavelength, order) and floor(32 / glt) problems per warp;
+// every factor operand is a shared-memory load that is uniform over the problem's lanes (no shuffles), the blocks
+// arrive through a two-slot cp.async ring.  4N + 2N + 3N doubles of state per lane.
+// -------------------------------------------------------------------------------------------------
+template <int N>
+struct TsolveCfg {
+    using F = BvpCfg2<N, 1>;
+    static constexpr int NC = F::NC, FS = F::FS, LS = F::LS, ROWS = F::ROWS, RL2 = F::RL2;
+    static constexpr int STAGES = 2;
+    static constexpr int WARPS_PER_BLOCK = 2;
+    static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS;
+    static_assert(LS <= FS, "multiplier blocks share the ring slots of the factor blocks");
+};
+
+template <int N>
+__global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsolve(ChunkView V, int glt, int gpw, int nbatch) {
+    using C = TsolveCfg<N>;
+    constexpr int NC = C::NC, FS = C::FS, LS = C::LS, ROWS = C::ROWS, RL2 = C::RL2, STAGES = C::STAGES;
+    extern __shared__ __align__(16) double smem[];
+    const int L = V.T.L, nlos = V.T.nlos;
+    const int warp = threadIdx.x >> 5, lane_w = threadIdx.x & 31;
+    const int gw_raw = lane_w / glt;
+    const bool in_group = gw_raw < gpw;          // lanes past the last whole group idle along (no copies, no stores)
+    const int gw = in_group ? gw_raw : gpw - 1;
+    const int r = in_group ? lane_w - gw * glt : 0;
+    const int gslot = warp * gpw + gw;
+    long long gid = (long long)blockIdx.x * (C::WARPS_PER_BLOCK * gpw) + gslot;
+    const long long ngroups = (long long)V.nw * V.M * nbatch;
+    const bool valid_group = gid < ngroups;
+    if (!valid_group) gid = ngroups - 1;
+    const int batch = (int)(gid % nbatch);
+    const long long prob = gid / nbatch;
+    int los = batch * glt + r;
+    const bool store_ok = valid_group && in_group && los < nlos;
+    if (los >= nlos) los = nlos - 1;
+    double* ring = smem + (size_t)gslot * C::SMEM_DOUBLES_PER_GROUP;
+    const double* fac = V.fac + (size_t)prob * V.fac_stride;
+    const double* lfac = V.lfac + (size_t)prob * V.lfac_stride;
+    const size_t vo = ((size_t)prob * nlos + los) * ((size_t)2 * N * L);
+    const double* wv = V.wvec + vo;   // [L][2N]
+    double* yb = V.yadj + vo;         // [2N L]
+    double* zb = V.zadj + vo;         // [2N L]
+
+    auto fetch = [&](const double* src, int ndoubles, int slot) {
+        if (src != nullptr && in_group) {
+            double* dst = ring + slot * NC * FS;
+            for (int e = 2 * r; e < ndoubles; e += 2 * glt) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + e) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // ---- phase 1: U^T y = w, window of 4N right-hand-side entries per lane
+    double win[4 * N];
+    {
+        const double2* w2 = reinterpret_cast<const double2*>(wv);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const double2 t = w2[j];
+            win[2 * j] = t.x;
+            win[2 * j + 1] = t.y;
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double2 t = make_double2(0.0, 0.0);
+            if (L > 1) t = w2[N + j];
+            win[NC + 2 * j] = t.x;
+            win[NC + 2 * j + 1] = t.y;
+        }
+    }
+    fetch(fac, NC * FS, 0);
+    for (int step = 0; step < L; ++step) {
+        fetch(step + 1 < L ? fac + (size_t)(step + 1) * NC * FS : nullptr, NC * FS, (step + 1) % STAGES);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const double* ub = ring + (step % STAGES) * NC * FS;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const double* u = ub + c * FS;
+            const double y = win[c] * u[RL2];
+            win[c] = y;
+#pragma unroll
+            for (int cc = c + 1; cc < 4 * N; ++cc) win[cc] = fma(-u[cc], y, win[cc]);
+        }
+        if (store_ok) {
+            double2* y2 = reinterpret_cast<double2*>(yb + (size_t)step * NC);
+#pragma unroll
+            for (int j = 0; j < N; ++j) y2[j] = make_double2(win[2 * j], win[2 * j + 1]);
+        }
+        {
+            const bool more = step + 2 < L;
+            const double2* w2 = reinterpret_cast<const double2*>(wv + (size_t)(more ? step + 2 : 0) * NC);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                double2 t = make_double2(0.0, 0.0);
+                if (more) t = w2[j];
+                win[2 * j] = win[NC + 2 * j];
+                win[2 * j + 1] = win[NC + 2 * j + 1];
+                win[NC + 2 * j] = t.x;
+                win[NC + 2 * j + 1] = t.y;
+            }
+        }
+        __syncwarp();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+
+    // ---- phase 2: z = E_1^T .. E_n^T P^T y
+    double v[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) v[i] = 0.0;
+    fetch(lfac + (size_t)(L - 1) * NC * LS, NC * LS, (L - 1) % STAGES);
+    for (int step = L - 1; step >= 0; --step) {
+        fetch(step > 0 ? lfac + (size_t)(step - 1) * NC * LS : nullptr, NC * LS, (step + STAGES - 1) % STAGES);
+        double y[NC];
+        {
+            // this lane's own phase-1 stores (same thread, same addresses); lanes without a line of sight read zeros
+            const double2* y2 = reinterpret_cast<const double2*>(yb + (size_t)step * NC);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                double2 t = make_double2(0.0, 0.0);
+                if (store_ok) t = y2[j];
+                y[2 * j] = t.x;
+                y[2 * j + 1] = t.y;
+            }
+        }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const double* lb = ring + (step % STAGES) * NC * FS;
+#pragma unroll
+        for (int c = NC - 1; c >= 0; --c) {
+            const double* f = lb + c * LS;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i) {
+                const double t = f[i];
+                if ((i & 3) == 0) s0 = fma(t, v[i], s0);
+                else if ((i & 3) == 1) s1 = fma(t, v[i], s1);
+                else if ((i & 3) == 2) s2 = fma(t, v[i], s2);
+                else s3 = fma(t, v[i], s3);
+            }
+            const double z = y[c] - ((s0 + s1) + (s2 + s3));
+            const double rec = f[ROWS];
+            const int plane = __double2loint(rec), prow = __double2hiint(rec);
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i) v[i] = (i == plane) ? z : v[i];
+            if (store_ok) zb[prow] = z;
+        }
+        __syncwarp();
+    }
 }
 
 template <int N, int NRHS>
@@ -1018,6 +1197,24 @@ static int adj_rhs_for(int nlos) { return nlos <= 4 ? 4 : 10; }
 template <int N>
 static void launch_bvp_adjoint_n(const ChunkView& V, cudaStream_t s) {
     const int nlos = V.T.nlos;
+    if constexpr (3 * N <= 32) {
+        if (V.lfac != nullptr) {  // the forward solve kept its multipliers: transposed solve, no second factorisation
+            using C = TsolveCfg<N>;
+            const int glt = tsolve_lanes(nlos);
+            const int gpw = tsolve_groups_per_warp(N, glt);
+            const int nbatch = (nlos + glt - 1) / glt;
+            const long long ngroups = (long long)V.nw * V.M * nbatch;
+            const int gpb = C::WARPS_PER_BLOCK * gpw;
+            const size_t smem = (size_t)gpb * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(k_bvp_tsolve<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                attr_set = true;
+            }
+            k_bvp_tsolve<N><<<(unsigned)((ngroups + gpb - 1) / gpb), C::WARPS_PER_BLOCK * 32, smem, s>>>(V, glt, gpw, nbatch);
+            return;
+        }
+    }
     const int nrhs = adj_rhs_for(nlos);
     const int nbatch = (nlos + nrhs - 1) / nrhs;
     if (nrhs == 4)

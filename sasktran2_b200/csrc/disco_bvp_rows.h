@@ -17,9 +17,12 @@ DISCO_HD void prefetch_line(const void* p) {
 template <int N>
 struct ForwardRows {
     static constexpr int NRHS = 1;
+    static constexpr bool KEEPS_L = true;  // the forward elimination can record its multipliers (transposed solves)
     const ChunkView& V;
     int w, ms, m, L;
     const double *Wp, *Wm, *kth, *G;
+    // index of new row `rank` of `step` in the row order of A (N TOA rows, 2N per interface, N ground rows)
+    DISCO_HD int row_of(int step, int rank) const { return (step == 0 ? 0 : N + 2 * N * step) + rank; }
     DISCO_HD ForwardRows(const ChunkView& V_, int w_, int ms_) : V(V_), w(w_), ms(ms_) {
         L = V.T.L;
         m = V.m_list[ms];
@@ -216,6 +219,8 @@ struct ForwardRows {
 template <int N, int NRHS_>
 struct AdjointRows {
     static constexpr int NRHS = NRHS_;
+    static constexpr bool KEEPS_L = false;
+    DISCO_HD int row_of(int, int) const { return 0; }
     const ChunkView& V;
     int w, ms, m, L, los0, nl;
     const double *Wp, *Wm, *kth;

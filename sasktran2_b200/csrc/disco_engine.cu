@@ -140,7 +140,10 @@ size_t DeviceEngine::workspace_bytes_per_wavelength() const {
         d += M * bvp_fac_stride((int)N, 1, (int)L);                  // LU pivot rows (forward solve)
     } else {
         const size_t G = m_ngroups, nrhs = adjoint_max_rhs((int)nlos), ngrp = adjoint_groups_per_problem((int)nlos);
-        d += M * ngrp * bvp_fac_stride((int)N, (int)nrhs, (int)L);   // LU pivot rows (forward and adjoint)
+        if (adjoint_reuses_factors((int)N, (int)nlos))               // forward pivot rows + multipliers + U^T y
+            d += M * (bvp_fac_stride((int)N, 1, (int)L) + bvp_lfac_stride((int)N, (int)L)) + M * nlos * 2 * N * L;
+        else
+            d += M * ngrp * bvp_fac_stride((int)N, (int)nrhs, (int)L);   // LU pivot rows (forward and adjoint)
         d += M * nlos * 2 * N * L;                                  // adjoint solutions
         d += L * G * nstr;                                          // Legendre derivative directions
         d += M * nlos * L * (G + 4) + M * nlos * L + nlos * 3;      // local lanes, sources, ground terms
@@ -198,12 +201,23 @@ void DeviceEngine::ensure_workspace(int chunk) {
     if (!m_wf_on) {
         V.fac_stride = bvp_fac_stride((int)N, 1, (int)L);
         V.fac = A("fac", c * M * V.fac_stride);
-        V.zadj = nullptr;
+        V.zadj = V.lfac = V.yadj = nullptr;
+        V.lfac_stride = 0;
         V.lay_dbeta = V.wf_loc = V.wf_src = V.wf_gnd = V.wf_native = V.wf_scratch = nullptr;
     } else {
         const size_t G = m_ngroups, nrhs = adjoint_max_rhs((int)nlos), ngrp = adjoint_groups_per_problem((int)nlos);
-        V.fac_stride = bvp_fac_stride((int)N, (int)nrhs, (int)L);
-        V.fac = A("fac", c * M * ngrp * V.fac_stride);
+        if (adjoint_reuses_factors((int)N, (int)nlos)) {
+            V.fac_stride = bvp_fac_stride((int)N, 1, (int)L);
+            V.fac = A("fac", c * M * V.fac_stride);
+            V.lfac_stride = bvp_lfac_stride((int)N, (int)L);
+            V.lfac = A("lfac", c * M * V.lfac_stride);
+            V.yadj = A("yadj", c * M * nlos * 2 * N * L);
+        } else {
+            V.fac_stride = bvp_fac_stride((int)N, (int)nrhs, (int)L);
+            V.fac = A("fac", c * M * ngrp * V.fac_stride);
+            V.lfac = V.yadj = nullptr;
+            V.lfac_stride = 0;
+        }
         V.zadj = A("zadj", c * M * nlos * 2 * N * L);
         V.lay_dbeta = A("lay_dbeta", c * L * G * nstr);
         V.wf_loc = A("wf_loc", c * M * nlos * L * (G + 4));

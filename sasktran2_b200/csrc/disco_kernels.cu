@@ -11,6 +11,8 @@
 //                       cpp/lib/sktran_disco/sktran_do_rte.cpp:1621-1723, 1898-2294)
 //  K4  k_radiance       thread per (wavelength, LOS): azimuth sum of w.x + v
 //                       (source_term/do_source_planeparallel.cpp:69-158)
+#include <cstdlib>
+
 #include "disco_kernels.cuh"
 #include "disco_wf_body.h"
 
@@ -309,6 +311,24 @@ void launch_wf_surface(const ChunkView& V, const double* d_brdf, double* out, in
     const long long n = (long long)V.nw * V.T.nlos;
     k_wf_surface<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V, d_brdf, out, w0, V.ngroups);
 }
+// The adjoint solve reuses the forward factors when the one-row-per-lane solver applies (3N <= 32) and at least a
+// quarter of the lanes of a warp carry a line of sight; SK_B200_ADJOINT=refactor forces the second factorisation of
+// A^T (k_bvp_adjoint_v2), SK_B200_ADJOINT=reuse the transposed solve whenever it applies.
+bool adjoint_reuses_factors(int N, int nlos) {
+    if (3 * N > 32 || nlos < 1) return false;
+    static const int mode = [] {
+        const char* e = std::getenv("SK_B200_ADJOINT");
+        if (e && e[0] == 'r' && e[1] == 'e' && e[2] == 'f') return 1;
+        if (e && e[0] == 'r' && e[1] == 'e' && e[2] == 'u') return 2;
+        return 0;
+    }();
+    const char* v3 = std::getenv("SK_B200_BVP");
+    if (mode == 1 || (v3 && v3[0] == '3')) return false;  // the 2D elimination keeps no multiplier record
+    if (mode == 2) return true;
+    const int glt = tsolve_lanes(nlos);
+    return tsolve_groups_per_warp(N, glt) * glt >= 8;
+}
+size_t bvp_lfac_stride(int N, int L) { return (size_t)L * 2 * N * ((3 * N + 2) & ~1); }
 int adjoint_groups_per_problem(int nlos) { const int r = adj_rhs_for(nlos); return (nlos + r - 1) / r; }
 int adjoint_max_rhs(int nlos) { return adj_rhs_for(nlos); }
 // doubles of factor storage per solve group: (L+1) blocks of 2N pivot rows; the one-row-per-lane solver (3N <= 32)

@@ -26,6 +26,18 @@ void launch_wf_surface(const ChunkView& V, const double* d_brdf, double* out, in
 int adjoint_groups_per_problem(int nlos);
 int adjoint_max_rhs(int nlos);
 size_t bvp_fac_stride(int N, int nrhs, int L);
+// Transposed solves from the forward factors (k_bvp_tsolve, disco_bvp.cuh): lanes per problem, problems per warp
+// that fit the shared-memory budget, whether the engine uses it for (N, nlos), doubles of multiplier storage per problem
+inline int tsolve_lanes(int nlos) { return nlos < 32 ? nlos : 32; }
+inline int tsolve_groups_per_warp(int N, int glt) {
+    const int fs = ((4 * N + 1 + 1) & ~1) + 2;
+    const int per_group = 2 * (2 * N) * fs * (int)sizeof(double);  // two ring slots of one factor block
+    const int fit = (56 * 1024) / (2 * per_group);                 // two warps per block, four blocks per SM
+    const int g = 32 / glt;
+    return g < fit ? g : (fit < 1 ? 1 : fit);
+}
+bool adjoint_reuses_factors(int N, int nlos);
+size_t bvp_lfac_stride(int N, int L);
 void launch_radiance(const ChunkView& V, cudaStream_t s);
 bool nstr_supported(int nstr);
 double measure_fp64_tflops();

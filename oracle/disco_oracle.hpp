@@ -472,6 +472,7 @@ struct WavelInputs {
     const double* leg;   // [nleg][nloc] (leg fastest: leg[l + nleg*q])
     int nleg;
     const double* f;     // [nloc] delta-M fraction or nullptr
+    const double* d_f = nullptr;  // [nloc * g + q] derivative of f per scattering group, nullptr: no scaling applied
     double solar;        // solar irradiance
     double albedo;       // Lambertian albedo
     // scattering derivative groups: d_leg[l + nleg*(q + nloc*g)] or nullptr
@@ -585,7 +586,10 @@ struct Solver {
                     for (int l = 0; l < nstr; ++l) {
                         double ph = (l < in.nleg) ? in.leg[l + size_t(in.nleg) * last_q] : 0.0;
                         double dl = (l < in.nleg) ? in.d_leg[l + size_t(in.nleg) * (last_q + size_t(nloc) * g)] : 0.0;
-                        seed_dir(Ly.beta[p][l], lanes.scat(p, g), dl + (ph - (2 * l + 1) * f / (1 - f) - leg[l]));
+                        double dir = dl + (ph - (2 * l + 1) * f / (1 - f) - leg[l]);
+                        // applied_f_order > 0 (sktran_do_layerarray.cpp:792-800)
+                        if (in.d_f) dir += -(2 * l + 1) / (1 - f) / (1 - f) * in.d_f[last_q + size_t(nloc) * g];
+                        seed_dir(Ly.beta[p][l], lanes.scat(p, g), dir);
                     }
             }
         }

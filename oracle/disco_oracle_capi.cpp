@@ -16,6 +16,14 @@ const char* oracle_last_error() { return g_last_err.c_str(); }
 // 0: the reference's multiplier formulas (default); 1: removable singularities evaluated with phi/psi
 void oracle_set_stable_multipliers(int on) { oracle::stable_multipliers_ref() = on; }
 
+// delta-M state of the next oracle_do_radiance call: f [nloc, nwavel], d_f [nloc, nwavel, ngroups] (null: unscaled)
+static const double* g_f = nullptr;
+static const double* g_df = nullptr;
+void oracle_set_delta_m(const double* f, const double* d_f) {
+    g_f = f;
+    g_df = d_f;
+}
+
 int oracle_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -55,7 +63,14 @@ int oracle_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nlos, const
                 in.ssa = ssa + size_t(nloc) * w;
                 in.leg = leg + size_t(nleg) * nloc * w;
                 in.nleg = nleg;
-                in.f = nullptr;
+                in.f = g_f ? g_f + size_t(nloc) * w : nullptr;
+                std::vector<double> dfw;
+                if (g_f && g_df && calc_derivs && d_leg && ngroups > 0) {
+                    dfw.resize(size_t(nloc) * ngroups);
+                    for (int g = 0; g < ngroups; ++g)
+                        std::memcpy(&dfw[size_t(nloc) * g], g_df + size_t(nloc) * (w + size_t(nwavel) * g), sizeof(double) * nloc);
+                    in.d_f = dfw.data();
+                }
                 in.solar = solar[w];
                 in.albedo = albedo[w];
                 in.ngroups = G;

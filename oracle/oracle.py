@@ -63,12 +63,14 @@ def _p(a):
 
 def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az,
                 ssa, ext, leg, solar=None, albedo, d_leg=None, include_ss=True, num_azimuth=0,
-                calc_derivs=False, nthreads=0, return_lanes=False, stable=False):
+                calc_derivs=False, nthreads=0, return_lanes=False, stable=False, f=None, d_f=None):
     """Run the oracle.
 
     ssa, ext: [nloc, nwavel] (Fortran order is used internally, as the reference does);
     leg: [nleg, nloc, nwavel]; d_leg: [nleg, nloc, nwavel, ngroups] or None; albedo: [nwavel].
     Returns dict(radiance [nwavel, nlos], native [nwavel, nlos, nloc*(2+G)+1] if calc_derivs).
+    f [nloc, nwavel], d_f [nloc, nwavel, ngroups]: delta-M truncation fraction and its derivatives as left by
+    apply_delta_m_scaling (below); the arrays passed in are then the SCALED ones.
     stable=True switches the particular-solution multipliers from the reference's formulas to the
     singularity-free phi/psi forms (see disco_oracle.hpp, "stable multipliers"); default is the reference's.
     """
@@ -99,12 +101,20 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
         if return_lanes:
             lanes = np.zeros((nwavel, nlos, nl * (G + 2) + 1))
     L.oracle_set_stable_multipliers(ctypes.c_int(int(stable)))
+    if f is not None:
+        f = np.asfortranarray(f, dtype=np.float64)
+        assert f.shape == (nloc, nwavel)
+        if d_f is not None:
+            d_f = np.asfortranarray(d_f, dtype=np.float64)
+            assert d_f.shape == (nloc, nwavel, G)
+    L.oracle_set_delta_m(_p(f), _p(d_f) if f is not None else None)
     rc = L.oracle_do_radiance(
         ctypes.c_int(nstr), ctypes.c_int(nloc), ctypes.c_int(nwavel), ctypes.c_int(nleg), ctypes.c_int(nlos),
         _p(alt), ctypes.c_int(interp), ctypes.c_int(geotype), ctypes.c_double(cos_sza), ctypes.c_double(earth_radius),
         _p(cz), _p(az), _p(ssa), _p(ext), _p(leg), _p(solar), _p(albedo), _p(d_leg), ctypes.c_int(G),
         ctypes.c_int(int(include_ss)), ctypes.c_int(num_azimuth), ctypes.c_int(int(calc_derivs)),
         ctypes.c_int(nthreads), _DGEEV, _p(rad), _p(native), _p(lanes))
+    L.oracle_set_delta_m(None, None)
     if rc != 0:
         raise RuntimeError(f"oracle failed ({rc}): {L.oracle_last_error().decode()}")
     out = {"radiance": rad}
@@ -163,3 +173,40 @@ def apply_mappings(native, mappings, nloc, ngroups):
             s = s @ mp["interpolator"]
         out[name] = np.ascontiguousarray(np.moveaxis(s, 2, 0))
     return out
+
+
+def apply_delta_m_scaling(order, ssa, ext, leg, d_leg=None, mappings=None):
+    """numpy restatement of Atmosphere::apply_delta_m_scaling (cpp/lib/atmosphere/atmosphere.cpp:69-203).
+
+    ssa, ext: [nloc, nwavel]; leg: [nleg, nloc, nwavel]; d_leg: [nleg, nloc, nwavel, G] or None; mappings: dict
+    name -> dict(d_ssa, d_extinction, scat_factor or None, scat_index).  Returns scaled COPIES:
+    dict(ssa, ext, leg, d_leg, f, d_f, mappings); the inputs are left untouched.  order >= nleg: unscaled (f None)."""
+    ssa0 = np.array(ssa, dtype=np.float64)
+    ext0 = np.array(ext, dtype=np.float64)
+    leg = np.array(leg, dtype=np.float64)
+    d_leg = None if d_leg is None else np.array(d_leg, dtype=np.float64)
+    maps = {k: {kk: (np.array(vv, dtype=np.float64) if isinstance(vv, np.ndarray) else vv) for kk, vv in v.items()}
+            for k, v in (mappings or {}).items()}
+    if order >= leg.shape[0]:
+        return dict(ssa=ssa0, ext=ext0, leg=leg, d_leg=d_leg, f=None, d_f=None, mappings=maps)
+    f = leg[order] / (2 * order + 1)                                  # :96-103
+    ext1 = ext0 * (1 - ssa0 * f)                                      # :106-109
+    ssa1 = (1 - f) / (1 - ssa0 * f) * ssa0                            # :112-116
+    d_f = None
+    if d_leg is not None:
+        d_f = d_leg[order] / (2 * order + 1)                          # :119-128  [nloc, nwavel, G]
+    leg = leg / (1 - f)[None]                                         # :140
+    if d_leg is not None:
+        d_leg = (d_leg + leg[..., None] * d_f[None]) / (1 - f)[None, :, :, None]   # :147-151
+    for m in maps.values():                                           # :158-201
+        if m.get("d_extinction") is None:
+            continue
+        dk = m["d_extinction"] * (1 - ssa0 * f)
+        dk = dk - ext0 * f * m["d_ssa"]
+        dw = m["d_ssa"] * (1 - f * (1 - ssa1)) / (1 - ssa0 * f)
+        if m.get("scat_factor") is not None and m.get("scat_index", -1) >= 0:
+            df = d_f[:, :, m["scat_index"]] * m["scat_factor"]
+            dk = dk - ssa0 * ext0 * df
+            dw = dw + df * ssa0 / (1 - ssa0 * f) * (ssa1 - 1)
+        m["d_extinction"], m["d_ssa"] = dk, dw
+    return dict(ssa=ssa1, ext=ext1, leg=leg, d_leg=d_leg, f=f, d_f=d_f, mappings=maps)

@@ -192,6 +192,8 @@ class Atmosphere:
         self.storage = AtmosphereStorage(nloc, numwavel, nleg)
         self.surface = Surface(numwavel)
         self.calculate_derivatives = bool(calculate_derivatives)
+        self._config = config
+        self._applied_delta_m_order = None
         self._h = None
 
     @property
@@ -205,6 +207,12 @@ class Atmosphere:
             if not self._h:
                 raise _lib.SasktranError(_lib.last_error())
         self.storage.finalize_scattering_derivatives()
+        # delta-M scaling is applied by the atmosphere, once, with order = num_streams
+        # (src/sasktran2/atmosphere.py:846-856): in place on the storage arrays and the derivative mappings
+        if self._config is not None and self._config.delta_m_scaling and self._applied_delta_m_order is None:
+            if self._config.num_streams != self.storage._nleg:
+                _lib.check(_lib.lib().sk_atmosphere_apply_delta_m_scaling(self._h, int(self._config.num_streams)))
+                self._applied_delta_m_order = int(self._config.num_streams)
         return self._h
 
     def __del__(self):

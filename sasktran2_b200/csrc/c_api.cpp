@@ -7,6 +7,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <set>
 #include <cstdlib>
 #include <memory>
@@ -137,6 +138,10 @@ struct AtmosphereStorage {
     double *ssa = nullptr, *ext = nullptr, *emission = nullptr, *leg = nullptr, *solar = nullptr;
     std::map<std::string, MappingImpl> mappings;  // name order == the reference's std::map order
     int num_scat_groups = 0;
+    // delta-M scaling state (AtmosphereGridStorageFull::f, d_f, applied_f_order, grid_storage.h:40-60)
+    int applied_f_order = 0;
+    PinnedVec f;                  // [nloc, nwavel] truncation fraction, empty until the scaling is applied
+    std::vector<PinnedVec> d_f;   // per scattering group: [nloc, nwavel]
 };
 
 struct BRDF {
@@ -195,6 +200,7 @@ disco::AtmosphereArrays arrays_of(const Atmosphere* atm) {
     a.ext = s->ext;
     a.leg = s->leg;
     a.solar = s->solar;
+    a.f = s->applied_f_order > 0 ? s->f.data() : nullptr;
     const Surface* sf = atm->surface;
     a.albedo = sf->brdf_args ? sf->brdf_args : sf->default_albedo.data();
     return a;
@@ -232,6 +238,10 @@ int build_wf_request(Engine* e, Atmosphere* atm, OutputC* out, disco::WfRequest&
     req.d_legendre.assign(s->num_scat_groups, nullptr);
     for (auto& kv : s->mappings)
         if (kv.second.is_scattering()) req.d_legendre[kv.second.scat_deriv_index] = kv.second.d_legendre.data();
+    if (s->applied_f_order > 0) {
+        req.d_f.assign(s->num_scat_groups, nullptr);
+        for (int g = 0; g < s->num_scat_groups && g < (int)s->d_f.size(); ++g) req.d_f[g] = s->d_f[g].data();
+    }
     for (auto& kv : out->derivs) {
         auto it = s->mappings.find(kv.first);
         if (it == s->mappings.end()) return fail(-2, "derivative memory assigned for unknown mapping '" + kv.first + "'");
@@ -611,9 +621,83 @@ Atmosphere* sk_atmosphere_create(AtmosphereStorage* storage, Surface* surface, i
     return a;
 }
 void sk_atmosphere_destroy(Atmosphere* a) { delete a; }
-int sk_atmosphere_apply_delta_m_scaling(Atmosphere* a, int) {
-    if (!a) return -1;
-    return fail(-3, "delta-M scaling (cpp/lib/atmosphere/atmosphere.cpp:69-203) is a host pre-pass outside the B200 DO path");
+// Atmosphere::apply_delta_m_scaling (cpp/lib/atmosphere/atmosphere.cpp:69-203): in-place delta-M scaling of the
+// caller's storage arrays and of the derivative mappings, order = number of streams.  It is a host pre-pass over
+// caller-owned host memory upstream and stays one here (threaded over wavelengths); the solve reads the truncation
+// fraction f and its derivatives d_f (layer optics and Legendre derivative directions,
+// sktran_do_layerarray.cpp:396-410, 773-800).
+int sk_atmosphere_apply_delta_m_scaling(Atmosphere* a, int order) {
+    if (!a || !a->storage) return -1;
+    AtmosphereStorage* s = a->storage;
+    if (s->nstokes != 1) return fail(-2, "B200 DO path supports num_stokes = 1 only");
+    if (order < 0) return fail(-2, "delta-M order must be non-negative");
+    if (order >= s->nleg) return 0;  // upstream warns and leaves the atmosphere unscaled
+    if (s->applied_f_order > 0) return fail(-2, "delta-M scaling has already been applied to this storage");
+    if (!s->ssa || !s->ext || !s->leg) return fail(-1, "atmosphere storage arrays are null");
+    sk_atmosphere_storage_finalize_scattering_derivatives(s);
+    const size_t nloc = s->nloc, nw = s->nwavel, nleg = s->nleg;
+    const int G = s->num_scat_groups;
+    s->f.assign(nloc * nw, 0.0);
+    s->d_f.assign(G, PinnedVec());
+    for (auto& v : s->d_f) v.assign(nloc * nw, 0.0);
+    std::vector<MappingImpl*> maps, scat_of_group(G, nullptr);
+    for (auto& kv : s->mappings) {
+        maps.push_back(&kv.second);
+        if (kv.second.is_scattering() && kv.second.scat_deriv_index >= 0) scat_of_group[kv.second.scat_deriv_index] = &kv.second;
+    }
+    const double inv = 1.0 / (2.0 * order + 1.0);
+    auto pass = [&](size_t w0, size_t w1) {
+        for (size_t w = w0; w < w1; ++w) {
+            for (size_t i = 0; i < nloc; ++i) {
+                const size_t iw = i + nloc * w;
+                double* leg = s->leg + nleg * iw;
+                const double f = leg[order] * inv;
+                const double ssa0 = s->ssa[iw], ext0 = s->ext[iw];
+                s->f[iw] = f;
+                const double one_m_wf = 1.0 - ssa0 * f;
+                s->ext[iw] = ext0 * one_m_wf;                  // k* = (1 - w f) k
+                const double ssa1 = (1.0 - f) / one_m_wf * ssa0;   // w* = (1 - f) / (1 - w f) w
+                s->ssa[iw] = ssa1;
+                for (int g = 0; g < G; ++g)
+                    s->d_f[g][iw] = scat_of_group[g] ? scat_of_group[g]->d_legendre[order + nleg * iw] * inv : 0.0;
+                for (size_t j = 0; j < nleg; ++j) {
+                    leg[j] /= (1.0 - f);                       // b* = b / (1 - f)
+                    for (int g = 0; g < G; ++g) {
+                        if (!scat_of_group[g]) continue;
+                        double& db = scat_of_group[g]->d_legendre[j + nleg * iw];
+                        db += leg[j] * s->d_f[g][iw];          // db* = (db + b* df) / (1 - f)
+                        db /= (1.0 - f);
+                    }
+                }
+                for (MappingImpl* m : maps) {
+                    if (!m->has_d_extinction) continue;
+                    if (!m->has_d_ssa) continue;  // allocated below before the pass
+                    double& dk = m->d_extinction[iw];
+                    double& dw = m->d_ssa[iw];
+                    dk *= one_m_wf;
+                    dk -= ext0 * f * dw;
+                    dw *= (1.0 - f * (1.0 - ssa1)) / one_m_wf;
+                    if (m->is_scattering() && m->scat_deriv_index >= 0) {
+                        const double df = s->d_f[m->scat_deriv_index][iw] * m->scat_factor[iw];
+                        dk -= ssa0 * ext0 * df;
+                        dw += df * ssa0 / one_m_wf * (ssa1 - 1.0);
+                    }
+                }
+            }
+        }
+    };
+    for (MappingImpl* m : maps)
+        if (m->has_d_extinction && !m->has_d_ssa) {
+            m->d_ssa.assign(nloc * nw, 0.0);
+            m->has_d_ssa = true;
+        }
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = std::max(1u, std::min<unsigned>(nt, (unsigned)std::max<size_t>(1, nw / 64)));
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; ++t) pool.emplace_back(pass, nw * t / nt, nw * (t + 1) / nt);
+    for (auto& th : pool) th.join();
+    s->applied_f_order = order;
+    return 0;
 }
 
 Surface* sk_surface_create(int nwavel, int nstokes, double* emission) {
@@ -748,8 +832,17 @@ Engine* sk_engine_create(Config* config, Geometry1D* geometry, ViewingGeometry* 
         fail(-2, "B200 DO path: num_stokes must be 1");
         return nullptr;
     }
-    if (config->multiple_scatter_source != 0) {
-        fail(-2, "B200 DO path: multiple_scatter_source must be DiscreteOrdinates (0)");
+    // TwoStream (2): the reference's dedicated two-stream source (cpp_twostream_source.cpp) is, for ground-viewing
+    // rays in plane-parallel / pseudo-spherical geometry, the multiple-scatter-only 2-stream discrete-ordinates
+    // source - upstream asserts their equality to 2e-8 on radiances and weighting functions
+    // (tests/engine/test_twostream.py:104-160).  Here it runs through the DO kernels with N = 1.
+    if (config->multiple_scatter_source == 2) {
+        if (config->num_streams != 2 || config->single_scatter_source != 3) {
+            fail(-2, "B200 DO path: multiple_scatter_source TwoStream needs num_streams = 2 and single_scatter_source None (3)");
+            return nullptr;
+        }
+    } else if (config->multiple_scatter_source != 0) {
+        fail(-2, "B200 DO path: multiple_scatter_source must be DiscreteOrdinates (0) or TwoStream (2)");
         return nullptr;
     }
     if (config->single_scatter_source != 2 && config->single_scatter_source != 3) {
@@ -764,10 +857,8 @@ Engine* sk_engine_create(Config* config, Geometry1D* geometry, ViewingGeometry* 
         fail(-2, "B200 DO path: solar refraction is not supported");
         return nullptr;
     }
-    if (config->apply_delta_scaling) {
-        fail(-2, "B200 DO path: delta scaling is not supported");
-        return nullptr;
-    }
+    // apply_delta_scaling is acted on by the caller (src/sasktran2/atmosphere.py:846-856 calls
+    // sk_atmosphere_apply_delta_m_scaling with order = num_streams); the engine reads the storage's f / d_f.
     for (size_t i = 0; i < viewing->rays.size(); ++i) {
         if (std::abs(viewing->ray_cos_sza[i] - geometry->spec.cos_sza) > 1e-12) {
             fail(-2, "B200 DO path: every ground-viewing ray must use the geometry's cos_sza");

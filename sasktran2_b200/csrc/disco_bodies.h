@@ -56,6 +56,8 @@ struct ChunkView {
     int ngroups;              // scattering derivative groups G
     const double* dleg;       // [G][nleg, nloc, nw_staged]: d_leg_coeff of group g (chunk-offset applied)
     size_t dleg_gstride;      // doubles between groups
+    const double* fdm;        // [1 + G][nloc, nw_staged]: delta-M fraction f | d_f of group g; null: no scaling applied
+    size_t fdm_gstride;       // doubles between the planes of fdm
     double* lay_dbeta;        // [nw][L][G][nstr] layer-level Legendre derivative direction per group
     double* wf_loc;           // [nw][M][nlos][L][G+4]
     double* wf_src;           // [nw][M][nlos][L]
@@ -100,7 +102,15 @@ DISCO_HD void optics_body(const ChunkView& V, long long idx) {
         od += kext * wgt;
         sc += kscat * wgt;
         const int nl = nstr < V.nleg ? nstr : V.nleg;
-        for (int l = 0; l < nl; ++l) beta[l] += wgt * kscat * leg[l + (size_t)V.nleg * q];
+        if (V.fdm) {
+            // delta-M: the truncated forward peak leaves every moment (sktran_do_layerarray.cpp:396-404)
+            const double f = V.fdm[(size_t)nloc * w + q];
+            const double ff = f / (1.0 - f);
+            for (int l = 0; l < nstr; ++l)
+                beta[l] += wgt * kscat * ((l < nl ? leg[l + (size_t)V.nleg * q] : 0.0) - (2 * l + 1) * ff);
+        } else {
+            for (int l = 0; l < nl; ++l) beta[l] += wgt * kscat * leg[l + (size_t)V.nleg * q];
+        }
     }
     if (sc > 0.0) {
         for (int l = 0; l < nstr; ++l) beta[l] /= sc;
@@ -110,15 +120,20 @@ DISCO_HD void optics_body(const ChunkView& V, long long idx) {
     if (V.ngroups > 0) {
         // Layer-level derivative direction of the Legendre moments for each scattering group.  The reference
         // overwrites it for every contributing grid point, so the last (highest) one wins
-        // (sktran_do_layerarray.cpp:761-800); delta-M f = 0 on this path.
+        // (sktran_do_layerarray.cpp:761-800).  With delta-M scaling applied the direction also carries the
+        // truncated peak and d_f (:773, :792-800).
         int ql = V.interp_idx[p * 2 + 1] >= 0 ? V.interp_idx[p * 2 + 1] : V.interp_idx[p * 2];
+        const double f = (V.fdm && ql >= 0) ? V.fdm[(size_t)nloc * w + ql] : 0.0;
         for (int g = 0; g < V.ngroups; ++g) {
             const double* dl = V.dleg + g * V.dleg_gstride + (size_t)V.nleg * nloc * w;
             double* db = V.lay_dbeta + ((size_t)idx * V.ngroups + g) * nstr;
+            const double df = (V.fdm && ql >= 0) ? V.fdm[(1 + g) * V.fdm_gstride + (size_t)nloc * w + ql] : 0.0;
             for (int l = 0; l < nstr; ++l) {
                 const double ph = (l < V.nleg && ql >= 0) ? leg[l + (size_t)V.nleg * ql] : 0.0;
                 const double dv = (l < V.nleg && ql >= 0) ? dl[l + (size_t)V.nleg * ql] : 0.0;
-                db[l] = dv + (ph - beta[l]);
+                double d = dv + (ph - (2 * l + 1) * f / (1.0 - f) - beta[l]);
+                if (V.fdm) d += -(2 * l + 1) / (1.0 - f) / (1.0 - f) * df;
+                db[l] = d;
             }
         }
     }

@@ -517,6 +517,220 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
 }
 
 // -------------------------------------------------------------------------------------------------
+// Version 4 of the forward staircase solve (one right-hand side, one panel row per lane): the elimination of
+// version 2 in blocks of B = 4 pivot columns, so that the shared-memory broadcast - the bound of version 2, 14
+// STS.128 from ONE lane per pivot at ~4 MIO cycles each (profiles/README.md) - is paid once per block by the
+// block's B pivot lanes together:
+//   panel phase   per pivot: REDUX pivot search as in version 2; the pivot lane's B panel entries and 1/pivot travel
+//                 by shuffle (<= B 64-bit shuffles), every candidate row forms its multiplier f_k and updates its
+//                 own panel entries - pivots and multipliers are exactly those of the column-by-column elimination;
+//   block phase   the B pivot lanes publish their RAW trailing entries together (one STS.128 stream for the block),
+//                 every lane applies the rank-B update a -= sum_j M_j raw_j with the composite multipliers
+//                 M = f L11^-1 (L11 = the block's unit lower triangle, exchanged by 6 shuffles): mathematically the
+//                 B rank-1 updates, ~B^2 extra DFMA per lane;
+//   factor rows   the update also runs on the pivot lanes, whose rows thereby become the U rows; they overwrite
+//                 their raw rows in the factor block, which is flushed as in version 2 - layout, back substitution
+//                 and the transposed solves (k_bvp_tsolve) are unchanged.
+// -------------------------------------------------------------------------------------------------
+template <int N, class Prob>
+__device__ __forceinline__ void staircase_solve_v4(const Prob& prob, double* gs, double* fac, int lane, unsigned gbase,
+                                                   unsigned gmask, bool valid, unsigned int* status, double* lf) {
+    static_assert(Prob::NRHS == 1, "forward solve");
+    using C = BvpCfg2<N, 1>;
+    constexpr int NC = C::NC, GL = C::GL, ROWLEN = C::ROWLEN, RL2 = C::RL2, FS = C::FS, LS = C::LS;
+    constexpr int B = NC >= 4 ? 4 : 2;
+    constexpr int CPL = (NC * FS + GL - 1) / GL;
+    constexpr int STAGES = C::STAGES;
+    double* ring = gs;
+    double* xs = gs + STAGES * NC * FS;
+    const unsigned lane_bit = 1u << (gbase + lane);
+    const unsigned lt_mask = (lane_bit - 1u) & gmask;
+
+    double a[ROWLEN];
+    bool act = false;
+    int myrow = 0;
+#pragma unroll
+    for (int c = 0; c < ROWLEN; ++c) a[c] = 0.0;
+    bool singular = false;
+    const int nsteps = prob.nsteps();
+
+    for (int step = 0; step < nsteps; ++step) {
+        {   // new rows of this step go to the lowest free lanes
+            const unsigned freeb = __ballot_sync(gmask, !act) & gmask;
+            const int rank = __popc(freeb & lt_mask);
+            if (!act && rank < prob.nnew(step)) {
+                act = true;
+                prob.load(step, rank, a);
+                myrow = prob.row_of(step, rank);
+            }
+        }
+        if (step + 1 < nsteps) prob.prefetch(step + 1, lane);
+        double* facs = ring + (step % STAGES) * NC * FS;
+#pragma unroll
+        for (int cb = 0; cb < NC / B; ++cb) {
+            const int c0 = cb * B;
+            double fk[B];
+            int mypiv = -1;
+            double mypinv = 0.0;
+            int planes[B];
+            // ---- panel phase
+#pragma unroll
+            for (int k = 0; k < B; ++k) {
+                const int c = c0 + k;
+                const unsigned key = act ? (unsigned)__double2hiint(fabs(a[c])) : 0u;
+                const unsigned mx = __reduce_max_sync(gmask, key);
+                const unsigned cand = __ballot_sync(gmask, act && key == mx);
+                if (mx == 0u) singular = true;
+                const int plane = (cand != 0u) ? __ffs(cand) - 1 : (int)gbase;  // warp lane of the pivot row
+                planes[k] = plane;
+                const bool ispiv = act && key == mx && (cand & lt_mask) == 0u;
+                double pinv = 0.0;
+                if (ispiv) {
+                    act = false;
+                    mypiv = k;
+                    pinv = rcp_pivot(a[c]);
+                    mypinv = pinv;
+                }
+                pinv = __shfl_sync(gmask, pinv, plane);
+                const double f = act ? a[c] * pinv : 0.0;
+                if (lf != nullptr) {
+                    const int prow = __shfl_sync(gmask, myrow, plane);
+                    const double rec = (lane < C::ROWS) ? f : __hiloint2double(prow, plane - (int)gbase);
+                    if (valid && lane <= C::ROWS) lf[((size_t)step * NC + c) * LS + lane] = rec;
+                }
+                if (act) a[c] = 0.0;
+                fk[k] = f;
+#pragma unroll
+                for (int t = k + 1; t < B; ++t) {
+                    const double u = __shfl_sync(gmask, a[c0 + t], plane);
+                    a[c0 + t] = fma(-f, u, a[c0 + t]);
+                }
+            }
+            // ---- composite multipliers M = f T, T = L11^-1 (L11[k][j] = multiplier of pivot lane k against pivot j)
+            double Tm[B][B], Mj[B];
+#pragma unroll
+            for (int k = 1; k < B; ++k)
+#pragma unroll
+                for (int j = 0; j < k; ++j) Tm[k][j] = __shfl_sync(gmask, fk[j], planes[k]);  // L11[k][j] for now
+#pragma unroll
+            for (int j = 0; j < B; ++j) {  // column j of T by forward substitution (in place, rows ascending)
+                double col[B];
+#pragma unroll
+                for (int i = j + 1; i < B; ++i) {
+                    double t = -Tm[i][j];
+#pragma unroll
+                    for (int k = j + 1; k < i; ++k) t = fma(-Tm[i][k], col[k], t);
+                    col[i] = t;
+                }
+                double m = fk[j];
+#pragma unroll
+                for (int k = j + 1; k < B; ++k) m = fma(fk[k], col[k], m);
+                Mj[j] = m;
+            }
+            // ---- the block's pivot lanes publish their raw trailing entries
+            double* myrowp = facs + (c0 + (mypiv >= 0 ? mypiv : 0)) * FS;
+            if (mypiv >= 0) {
+#pragma unroll
+                for (int cc = c0 + B; cc < RL2; cc += 2) {
+                    const double v0 = (cc < ROWLEN) ? a[cc < ROWLEN ? cc : 0] : 0.0;
+                    const double v1 = (cc + 1 < ROWLEN) ? a[cc + 1 < ROWLEN ? cc + 1 : 0] : 0.0;
+                    *reinterpret_cast<double2*>(myrowp + cc) = make_double2(v0, v1);
+                }
+            }
+            __syncwarp(gmask);
+            // ---- rank-B update of the trailing columns (pivot lanes included: their rows become rows of U)
+#pragma unroll
+            for (int cc = c0 + B; cc < ROWLEN; ++cc) {
+                double sacc = a[cc];
+#pragma unroll
+                for (int j = 0; j < B; ++j) sacc = fma(-Mj[j], facs[(c0 + j) * FS + cc], sacc);
+                a[cc] = sacc;
+            }
+            __syncwarp(gmask);
+            if (mypiv >= 0) {  // factor row: panel entries | U trailing entries | 1 / pivot
+#pragma unroll
+                for (int cc = c0; cc < RL2; cc += 2) {
+                    const double v0 = (cc < ROWLEN) ? a[cc < ROWLEN ? cc : 0] : 0.0;
+                    const double v1 = (cc + 1 < ROWLEN) ? a[cc + 1 < ROWLEN ? cc + 1 : 0] : 0.0;
+                    *reinterpret_cast<double2*>(myrowp + cc) = make_double2(v0, v1);
+                }
+                myrowp[RL2] = mypinv;
+            }
+        }
+        __syncwarp(gmask);
+        {
+            double tmp[CPL];
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) tmp[i] = facs[(lane + i * GL) < NC * FS ? lane + i * GL : 0];
+            if (valid) {
+                double* dst = fac + (size_t)step * NC * FS;
+#pragma unroll
+                for (int i = 0; i < CPL; ++i)
+                    if (lane + i * GL < NC * FS) dst[lane + i * GL] = tmp[i];
+            }
+        }
+        __syncwarp(gmask);
+        if (step < nsteps - 1) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                a[j] = a[NC + j];
+                a[NC + j] = 0.0;
+            }
+        }
+    }
+    if (singular && valid) atomicOr(status, 4u);
+
+    // ---- back substitution: identical to version 2 (lane c owns pivot row c of the block; x by shuffle)
+    auto fetch_block = [&](int step) {
+        if (step >= 0) {
+            const double* src = fac + (size_t)step * NC * FS;
+            double* dst = ring + (step % STAGES) * NC * FS;
+#pragma unroll
+            for (int i = 0; i < (NC * FS / 2 + GL - 1) / GL; ++i) {
+                const int e = 2 * (lane + i * GL);
+                if (e < NC * FS) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + e) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    __syncwarp(gmask);
+#pragma unroll
+    for (int k = 2; k <= STAGES; ++k) fetch_block(nsteps - k);
+    for (int step = nsteps - 1; step >= 0; --step) {
+        const int nleft = prob.nleft(step);
+        const int nright = prob.nright(step);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp(gmask);
+        const double* fb = ring + (step % STAGES) * NC * FS;
+        const int row = lane < nleft ? lane : 0;
+        const double* my = fb + row * FS;
+        double acc = my[4 * N];
+        for (int jx = 0; jx < nright; ++jx) acc = fma(-my[NC + jx], xs[jx], acc);
+        const double pinv = my[RL2];
+        double myx = 0.0;
+#pragma unroll
+        for (int cc = NC - 1; cc >= 0; --cc) {
+            if (cc < nleft) {
+                double xv = acc * pinv;
+                xv = __shfl_sync(gmask, xv, (int)gbase + cc);
+                if (lane < cc) acc = fma(-my[cc], xv, acc);
+                if (lane == cc) myx = xv;
+            }
+        }
+        __syncwarp(gmask);
+        if (lane < nleft) {
+            xs[lane] = myx;
+            if (valid) prob.store(step, lane, 0, myx);
+        }
+        __syncwarp(gmask);
+        fetch_block(step - STAGES);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Version 3: the panel is distributed in two dimensions over one warp - 8 row lanes x 4 column groups, S = ceil(3N/8)
 // row slots per lane, N panel columns (one window block) per group.  Column block gb of the band lives in group
 // gb mod 4, so the window slides without moving data.  Per pivot the warp exchanges
@@ -863,7 +1077,7 @@ __global__ void __launch_bounds__(BvpCfg3<N, NRHS>::WARPS_PER_BLOCK * 32, 3) k_b
     staircase_solve_2d<N>(rows, smem + (size_t)wib * C::SMEM_DOUBLES_PER_GROUP, fac, lane, valid, V.status);
 }
 
-template <int N>
+template <int N, bool BLOCKED = false>
 __global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, BvpCfg2<N, 1>::MIN_BLOCKS) k_bvp_v2(ChunkView V) {
     using C = BvpCfg2<N, 1>;
     extern __shared__ __align__(16) double smem[];
@@ -879,8 +1093,13 @@ __global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, BvpCfg2<N
     const int w = (int)(prob / V.M), ms = (int)(prob % V.M);
     ForwardRows<N> rows(V, w, ms);
     double* fac = V.fac + (size_t)prob * V.fac_stride;
-    staircase_solve_v2<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
-                          V.status, V.lfac ? V.lfac + (size_t)prob * V.lfac_stride : nullptr);
+    double* lf = V.lfac ? V.lfac + (size_t)prob * V.lfac_stride : nullptr;
+    if constexpr (BLOCKED)
+        staircase_solve_v4<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
+                              V.status, lf);
+    else
+        staircase_solve_v2<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
+                              V.status, lf);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -904,7 +1123,9 @@ struct TsolveCfg {
     static constexpr int NC = F::NC, FS = F::FS, LS = F::LS, ROWS = F::ROWS, RL2 = F::RL2;
     static constexpr int STAGES = 2;
     static constexpr int WARPS_PER_BLOCK = 2;
-    static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS;
+    // + 4 doubles: the problems of a warp read their rings at the same offset in the same instruction, a 32-byte
+    // skew per problem keeps those 16-byte broadcasts on different banks
+    static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS + 4;
     static_assert(LS <= FS, "multiplier blocks share the ring slots of the factor blocks");
 };
 
@@ -969,6 +1190,17 @@ __global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsol
     fetch(fac, NC * FS, 0);
     for (int step = 0; step < L; ++step) {
         fetch(step + 1 < L ? fac + (size_t)(step + 1) * NC * FS : nullptr, NC * FS, (step + 1) % STAGES);
+        // right-hand-side entries that enter the window after this step: requested now, consumed at the end
+        double2 nxt[N];
+        {
+            const bool more = step + 2 < L;
+            const double2* w2 = reinterpret_cast<const double2*>(wv + (size_t)(more ? step + 2 : 0) * NC);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                nxt[j] = make_double2(0.0, 0.0);
+                if (more) nxt[j] = w2[j];
+            }
+        }
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         const double* ub = ring + (step % STAGES) * NC * FS;
@@ -985,18 +1217,12 @@ __global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsol
 #pragma unroll
             for (int j = 0; j < N; ++j) y2[j] = make_double2(win[2 * j], win[2 * j + 1]);
         }
-        {
-            const bool more = step + 2 < L;
-            const double2* w2 = reinterpret_cast<const double2*>(wv + (size_t)(more ? step + 2 : 0) * NC);
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                double2 t = make_double2(0.0, 0.0);
-                if (more) t = w2[j];
-                win[2 * j] = win[NC + 2 * j];
-                win[2 * j + 1] = win[NC + 2 * j + 1];
-                win[NC + 2 * j] = t.x;
-                win[NC + 2 * j + 1] = t.y;
-            }
+        for (int j = 0; j < N; ++j) {
+            win[2 * j] = win[NC + 2 * j];
+            win[2 * j + 1] = win[NC + 2 * j + 1];
+            win[NC + 2 * j] = nxt[j].x;
+            win[NC + 2 * j + 1] = nxt[j].y;
         }
         __syncwarp();
     }
@@ -1008,20 +1234,22 @@ __global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsol
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) v[i] = 0.0;
     fetch(lfac + (size_t)(L - 1) * NC * LS, NC * LS, (L - 1) % STAGES);
+    // y of a step: this lane's own phase-1 stores (same thread, same addresses), requested one step ahead; lanes
+    // without a line of sight carry zeros
+    auto load_y = [&](int step, double2* dst) {
+        const double2* y2 = reinterpret_cast<const double2*>(yb + (size_t)(step >= 0 ? step : 0) * NC);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            dst[j] = make_double2(0.0, 0.0);
+            if (store_ok && step >= 0) dst[j] = y2[j];
+        }
+    };
+    double2 ycur[N];
+    load_y(L - 1, ycur);
     for (int step = L - 1; step >= 0; --step) {
         fetch(step > 0 ? lfac + (size_t)(step - 1) * NC * LS : nullptr, NC * LS, (step + STAGES - 1) % STAGES);
-        double y[NC];
-        {
-            // this lane's own phase-1 stores (same thread, same addresses); lanes without a line of sight read zeros
-            const double2* y2 = reinterpret_cast<const double2*>(yb + (size_t)step * NC);
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                double2 t = make_double2(0.0, 0.0);
-                if (store_ok) t = y2[j];
-                y[2 * j] = t.x;
-                y[2 * j + 1] = t.y;
-            }
-        }
+        double2 ynext[N];
+        load_y(step - 1, ynext);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         const double* lb = ring + (step % STAGES) * NC * FS;
@@ -1037,13 +1265,16 @@ __global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsol
                 else if ((i & 3) == 2) s2 = fma(t, v[i], s2);
                 else s3 = fma(t, v[i], s3);
             }
-            const double z = y[c] - ((s0 + s1) + (s2 + s3));
+            const double yc = (c & 1) ? ycur[c >> 1].y : ycur[c >> 1].x;
+            const double z = yc - ((s0 + s1) + (s2 + s3));
             const double rec = f[ROWS];
             const int plane = __double2loint(rec), prow = __double2hiint(rec);
 #pragma unroll
             for (int i = 0; i < ROWS; ++i) v[i] = (i == plane) ? z : v[i];
             if (store_ok) zb[prow] = z;
         }
+#pragma unroll
+        for (int j = 0; j < N; ++j) ycur[j] = ynext[j];
         __syncwarp();
     }
 }
@@ -1124,6 +1355,15 @@ static bool bvp_use_2d() {
     return v;
 }
 
+// SK_B200_BVP=2 selects the column-by-column elimination (version 2) instead of the blocked one (version 4)
+static bool bvp_blocked() {
+    static const bool v = [] {
+        const char* e = std::getenv("SK_B200_BVP");
+        return !(e && e[0] == '2');
+    }();
+    return v;
+}
+
 template <int N>
 static void launch_bvp_n(const ChunkView& V, cudaStream_t s) {
     const long long nprob = (long long)V.nw * V.M;
@@ -1144,7 +1384,16 @@ static void launch_bvp_n(const ChunkView& V, cudaStream_t s) {
             cudaFuncSetAttribute(k_bvp_v2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_set = true;
         }
-        k_bvp_v2<N><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
+        if (bvp_blocked()) {
+            static bool attr4_set = false;
+            if (!attr4_set) {
+                cudaFuncSetAttribute(k_bvp_v2<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr4_set = true;
+            }
+            k_bvp_v2<N, true><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
+        } else {
+            k_bvp_v2<N><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
+        }
     } else {
         using C = BvpCfg<N, 1>;
         const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);

@@ -118,6 +118,9 @@ void DeviceEngine::free_inputs() {
         if (p) cudaFree(p);
     d_ext = d_ssa = d_leg = d_solar = d_albedo = d_radiance = nullptr;
     m_cap_nw = m_cap_nleg = 0;
+    if (d_fdm) cudaFree(d_fdm);
+    d_fdm = nullptr;
+    m_cap_fdm = 0;
 }
 
 void DeviceEngine::free_workspace() {
@@ -256,6 +259,24 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
         CUDA_OK(cudaMemcpyAsync(d_solar, atm.solar + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
         CUDA_OK(cudaMemcpyAsync(d_albedo, atm.albedo + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
     }
+    // delta-M truncation fraction and its derivatives (set by sk_atmosphere_apply_delta_m_scaling)
+    m_has_f = atm.f != nullptr && nw > 0;
+    if (m_has_f) {
+        const size_t G = (wf && wf->enabled()) ? wf->d_f.size() : 0;
+        const size_t n2 = nloc * (size_t)nw, need = (1 + G) * n2;
+        if (need > m_cap_fdm) {
+            if (d_fdm) cudaFree(d_fdm);
+            d_fdm = dalloc<double>(need);
+            m_cap_fdm = need;
+        }
+        CUDA_OK(cudaMemcpyAsync(d_fdm, atm.f + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
+        for (size_t g = 0; g < G; ++g) {
+            if (wf->d_f[g])
+                CUDA_OK(cudaMemcpyAsync(d_fdm + (1 + g) * n2, wf->d_f[g] + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
+            else
+                CUDA_OK(cudaMemsetAsync(d_fdm + (1 + g) * n2, 0, sizeof(double) * n2, m_stream));
+        }
+    }
     // weighting-function inputs of the staged range.  Device buffers are kept from the previous call when the
     // request has the same shape (same number of wavelengths, groups, mappings and output sizes).
     m_w0 = w0;
@@ -380,6 +401,8 @@ void DeviceEngine::solve_staged() {
         V.radiance = d_radiance + (size_t)w0 * m_plan.nlos;
         V.dleg = d_dleg ? d_dleg + (size_t)m_nleg * nloc * w0 : nullptr;
         V.dleg_gstride = (size_t)m_nleg * nloc * m_nw;
+        V.fdm = m_has_f ? d_fdm + nloc * w0 : nullptr;
+        V.fdm_gstride = nloc * (size_t)m_nw;
         launch_layer_optics(V, m_stream);
         launch_beam(V, m_stream);
         mark(); slots.push_back(T_OPTICS);

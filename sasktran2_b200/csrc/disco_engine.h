@@ -27,6 +27,7 @@ struct AtmosphereArrays {
     const double* leg = nullptr;    // [nleg, nloc, nwavel]
     const double* solar = nullptr;  // [nwavel]
     const double* albedo = nullptr; // [nwavel]
+    const double* f = nullptr;      // [nloc, nwavel] delta-M truncation fraction, null when no scaling was applied
 };
 
 // Weighting-function request: which derivative mappings to evaluate and where the results go
@@ -47,6 +48,7 @@ struct WfSurface {
 };
 struct WfRequest {
     std::vector<const double*> d_legendre;  // per scattering group: [nleg, nloc, nwavel]
+    std::vector<const double*> d_f;         // per scattering group: [nloc, nwavel] d(delta-M fraction), empty: unscaled
     std::vector<WfMapping> mappings;
     std::vector<WfSurface> surfaces;
     bool enabled() const { return !mappings.empty() || !surfaces.empty(); }
@@ -117,6 +119,9 @@ class DeviceEngine {
     bool m_wf_on = false;
     int m_ngroups = 0, m_w0 = 0, m_nw_total = 0, m_wf_nw = 0, m_wf_nleg = 0;
     double* d_dleg = nullptr;
+    double* d_fdm = nullptr;     // delta-M inputs of the staged range: f | d_f per group, [1 + G][nloc, nw]
+    size_t m_cap_fdm = 0;
+    bool m_has_f = false;
     std::vector<DevMapping> m_maps;
     std::vector<DevSurface> m_surfs;
     bool m_ws_wf = false;

@@ -31,7 +31,7 @@ size_t bvp_fac_stride(int N, int nrhs, int L);
 inline int tsolve_lanes(int nlos) { return nlos < 32 ? nlos : 32; }
 inline int tsolve_groups_per_warp(int N, int glt) {
     const int fs = ((4 * N + 1 + 1) & ~1) + 2;
-    const int per_group = 2 * (2 * N) * fs * (int)sizeof(double);  // two ring slots of one factor block
+    const int per_group = (2 * (2 * N) * fs + 4) * (int)sizeof(double);  // two ring slots of one factor block + skew
     const int fit = (56 * 1024) / (2 * per_group);                 // two warps per block, four blocks per SM
     const int g = 32 / glt;
     return g < fit ? g : (fit < 1 ? 1 : fit);

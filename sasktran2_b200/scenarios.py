@@ -107,13 +107,14 @@ def config1(nwavel: int = 1000, nlayers: int = 50) -> Scenario:
 
 
 def config2(nwavel: int = 100000, nlayers: int = 100, nstr: int = 16, nlos: int = 10, with_wf: bool = False,
-            seed: int = 0, block: tuple[int, int] | None = None) -> Scenario:
+            seed: int = 0, block: tuple[int, int] | None = None, nleg: int | None = None) -> Scenario:
     """C2 (and C5 when with_wf): pseudo-spherical DO, 16 streams, 100 layers, Rayleigh + aerosol (+ O3/NO2
     absorbers so the atmosphere is not conservative), 10 ground-viewing LOS.
 
     `block = (start, count)` builds only wavelengths [start, start + count) of the `nwavel`-point spectrum (what one
-    rank of a wavelength-sharded run owns); the arrays equal the corresponding slices of the full scenario."""
-    nleg = nstr
+    rank of a wavelength-sharded run owns); the arrays equal the corresponding slices of the full scenario.
+    `nleg` > nstr stores more phase moments than streams (what delta-M scaling needs)."""
+    nleg = nstr if nleg is None else nleg
     z = np.linspace(0.0, 100e3, nlayers + 1)
     widx = np.arange(nwavel) if block is None else np.arange(block[0], block[0] + block[1])
     lam_frac = widx / max(nwavel - 1, 1)
@@ -158,10 +159,10 @@ def config2(nwavel: int = 100000, nlayers: int = 100, nstr: int = 16, nlos: int 
 
 
 def small_wf_case(nstr: int = 8, nlayers: int = 12, nwavel: int = 3, nlos: int = 3, interp: int = 1, geotype: int = 1,
-                  seed: int = 1) -> Scenario:
+                  seed: int = 1, nleg: int | None = None) -> Scenario:
     """Small pseudo-spherical Rayleigh + aerosol + absorber case with all three mapping kinds; used by the
     weighting-function tests (finite differences in the spirit of src/sasktran2/test_util/wf.py:9-80)."""
-    sc = config2(nwavel=nwavel, nlayers=nlayers, nstr=nstr, nlos=nlos, with_wf=True, seed=seed)
+    sc = config2(nwavel=nwavel, nlayers=nlayers, nstr=nstr, nlos=nlos, with_wf=True, seed=seed, nleg=nleg)
     sc.name = "small_wf"
     sc.interp = interp
     sc.geotype = geotype

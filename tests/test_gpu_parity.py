@@ -177,7 +177,8 @@ def _oracle_wf(oracle_mod, sc, perturb=0.0, stable=False):
     ora = oracle_mod.do_radiance(nstr=sc.nstr, alt=sc.altitudes, interp=sc.interp, geotype=sc.geotype, cos_sza=sc.cos_sza,
                                  earth_radius=sc.earth_radius, los_cos_vza=sc.los_cos_vza, los_rel_az=sc.los_rel_az,
                                  ssa=sc.ssa, ext=sc.total_extinction * (1.0 + perturb), leg=sc.leg_coeff,
-                                 albedo=sc.albedo, d_leg=d_leg, calc_derivs=True, stable=stable)
+                                 albedo=sc.albedo, d_leg=d_leg, calc_derivs=True, stable=stable,
+                                 **getattr(sc, "delta_m", {}))
     maps = {}
     for n, mp in sc.mappings.items():
         maps[n] = dict(d_ssa=mp["d_ssa"], d_extinction=mp["d_extinction"], scat_factor=mp.get("scat_factor"),
@@ -324,13 +325,14 @@ def _run_variant(env_overrides, tmp_path, tag):
 def test_cuda_kernel_variants_agree(tmp_path):
     """Differential test of the alternative code paths on 40 wavelengths x 16 orders x 31 layers x 10 LOS:
     default (register-resident layer kernels + row-per-lane staircase LU), SK_B200_GENERIC=1 (thread-per-problem
-    layer and weighting-function kernels), SK_B200_BVP=3 (2D-distributed staircase LU) and SK_B200_ADJOINT=refactor
+    layer and weighting-function kernels), SK_B200_BVP=3 (2D-distributed staircase LU), SK_B200_BVP=2 (column-by-column
+    instead of blocked elimination) and SK_B200_ADJOINT=refactor
     (adjoint by a second factorisation of A^T instead of transposed solves with the forward factors).  Different summation
     orders and pivot tie-breaks, same mathematics: 1e-10 on radiances, 1e-8 of the column maximum on weighting
     functions (the amplified scatterer mapping: 1e-4, its noise floor, see _assert_wf)."""
     base = _run_variant({}, tmp_path, "default")
     for tag, env in (("generic", {"SK_B200_GENERIC": "1"}), ("bvp2d", {"SK_B200_BVP": "3"}),
-                     ("adjoint_refactor", {"SK_B200_ADJOINT": "refactor"})):
+                     ("bvp_columnwise", {"SK_B200_BVP": "2"}), ("adjoint_refactor", {"SK_B200_ADJOINT": "refactor"})):
         other = _run_variant(env, tmp_path, tag)
         assert set(other) == set(base)
         np.testing.assert_allclose(other["radiance"], base["radiance"], rtol=1e-10)

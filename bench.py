@@ -34,12 +34,14 @@ METRIC = "LOS x wavelength radiances/sec (16-stream, 100 layers)"
 UNIT = "radiances/s"
 
 
-def flop_model(nstr, nlayers, nlos, m_list, ngroups=1):
+def flop_model(nstr, nlayers, nlos, m_list, ngroups=1, adjoint_refactor=False):
     """Algorithmic flops per wavelength, split by timed kernel group.
 
     layer, bvp: SURVEY.md section 8d / Appendix B (values only; the BVP figure is LAPACK's banded LU + solve count,
     the staircase elimination does about a third of it).  Weighting functions (reverse mode):
-      wf_adjoint  one more banded factorisation (of A^T) + one banded solve per line of sight;
+      wf_adjoint  one banded solve (LAPACK dgbtrs count) per line of sight with the forward factors, as the
+                  reference's backprop does; `adjoint_refactor` adds the second factorisation (of A^T) that the
+                  SK_B200_ADJOINT=refactor path and few-LOS shapes perform;
       wf_layer    the layer-local linearisation with NL = ngroups + 4 lanes [eps_g | tau | omega | t | s]: NL times the
                   values-only particular + LOS work (forward-mode count of the reference's layer duals,
                   sktran_do_rte.cpp:903-1332, sktran_do_opticallayer.cpp:94-555) + 7 N^3 per eigen-derivative lane
@@ -55,7 +57,7 @@ def flop_model(nstr, nlayers, nlos, m_list, ngroups=1):
         solve = 4 * N * L * (9 * N - 3)                                      # one banded solve
         layer += homog + part + post
         bvp += factor + solve
-        wf_adjoint += factor + nlos * solve
+        wf_adjoint += (factor if adjoint_refactor else 0) + nlos * solve
         wf_layer += NL * (part + post) + L * NH * 7 * N**3 + nlos * L * 8 * N * N * NL
     return {"layer": layer, "bvp": bvp, "wf_adjoint": wf_adjoint, "wf_layer": wf_layer, "total": layer + bvp,
             "total_wf": layer + bvp + wf_adjoint + wf_layer}
@@ -63,9 +65,20 @@ def flop_model(nstr, nlayers, nlos, m_list, ngroups=1):
 
 # DRAM bytes per wavelength (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, divided by
 # the 600 wavelengths of the profiled launch) for the default shape: 16 streams, 100 layers, 10 LOS, weighting
-# functions with one scattering group - profiles/ncu_r01_v5_summary.csv.  Other shapes report traffic = null.
-NCU_DRAM_BYTES_PER_WAVELENGTH = {"layer": (0.811 + 2.022 + 3.610) * 1e9 / 600, "bvp": 9.982e9 / 600,
-                                 "wf_adjoint": 14.144e9 / 600, "wf_layer": 3.496e9 / 600}
+# functions with one scattering group - profiles/ncu_r01_v8_summary.csv.  Other shapes report traffic = null.
+NCU_DRAM_BYTES_PER_WAVELENGTH = {"layer": (0.811 + 2.022 + 3.610) * 1e9 / 600, "bvp": (6.079 + 7.717) * 1e9 / 600,
+                                 "wf_adjoint": (10.072 + 2.468) * 1e9 / 600, "wf_layer": 3.496e9 / 600}
+
+
+def tsolve_bytes_model(nstr, nlayers, nlos, n_orders):
+    """Algorithmic HBM bytes per wavelength of the transposed solves (k_bvp_tsolve): per
+    (order, pivot) one factor row (FS doubles) and one multiplier row (LS doubles) read once, per (order, LOS) the
+    right-hand side read, y written and read back, z written (2 N L doubles each)."""
+    N = nstr // 2
+    fs = ((4 * N + 2) & ~1) + 2
+    ls = (3 * N + 2) & ~1
+    n = 2 * N * nlayers
+    return 8.0 * n_orders * (n * (fs + ls) + nlos * 4 * n)
 
 
 def bytes_model(nloc, nleg, nlos, nwf_out=0):
@@ -329,12 +342,13 @@ def main():
     e2e_breakdown["host_ms"] = e2e_ms - sum(e2e_breakdown.values())
 
     # ---- roofline of the dominant kernel (FP64 pipe; peak measured live by a DFMA micro-benchmark)
-    fm = flop_model(args.nstr, args.layers, nlos, m_list, ngroups=1 if with_wf else 0)
+    reuse = bool(sk._lib.lib().sk_b200_adjoint_reuses_factors(args.nstr // 2, nlos))
+    fm = flop_model(args.nstr, args.layers, nlos, m_list, ngroups=1 if with_wf else 0, adjoint_refactor=not reuse)
     fast = args.nstr in (4, 8, 16) and os.environ.get("SK_B200_GENERIC", "0") != "1"
     kernel_names = {
         "layer": "k_eig_setup + k_eig_jacobi + k_layer_post (+ k_los_atten)" if fast else "k_layer_solve",
-        "bvp": "k_bvp_v2" if args.nstr <= 16 else "k_bvp",
-        "wf_adjoint": "k_bvp_adjoint_v2" if args.nstr <= 16 else "k_bvp_adjoint",
+        "bvp": "k_bvp_v2 (blocked elimination)" if args.nstr <= 16 else "k_bvp",
+        "wf_adjoint": ("k_bvp_tsolve" if reuse else "k_bvp_adjoint_v2") if args.nstr <= 16 else "k_bvp_adjoint",
         "wf_layer": "k_wf_layer_fast" if fast else "k_wf_layer",
     }
     launches_per_chunk = {"layer": 4 if fast else 1, "bvp": 1, "wf_adjoint": 1, "wf_layer": 1}
@@ -369,6 +383,12 @@ def main():
 
     per_k = {k: kernel_roofline(k) for k in ("layer", "bvp", "wf_adjoint", "wf_layer")}
     per_k = {k: v for k, v in per_k.items() if v}
+    if reuse and "wf_adjoint" in per_k:
+        # the transposed solves stream the factors once: bounded by HBM, not by the FP64 pipe
+        by = tsolve_bytes_model(args.nstr, args.layers, nlos, len(m_list))
+        gbs = by * nw * args.steps / (per_kernel["wf_adjoint"] * 1e-3) / 1e9
+        per_k["wf_adjoint"]["hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": gbs / hbm_peak, "bytes_per_wavelength": by}
     dom = max(per_k, key=lambda k: per_k[k]["share_of_step"])
     total_flops = fm["total_wf"] if with_wf else fm["total"]
     roofline = {
@@ -376,7 +396,7 @@ def main():
         "unit": "TFLOP/s", "frac": per_k[dom]["frac"],
         "traffic": (NCU_DRAM_BYTES_PER_WAVELENGTH[dom] * (nw / nchunks) / launches_per_chunk[dom]
                     if (args.nstr, args.layers, nlos, with_wf) == (16, 100, 10, True) else None),
-        "traffic_source": "profiles/ncu_r01_v5_summary.csv (dram bytes per wavelength of the profiled launch x wavelengths per launch)",
+        "traffic_source": "profiles/ncu_r01_v8_summary.csv (dram bytes per wavelength of the profiled launch x wavelengths per launch)",
         "peak_source": "DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP64 figure)",
         "share_of_step": per_k[dom]["share_of_step"], "avg_launch_ms": per_k[dom]["avg_launch_ms"],
         "flops_per_launch": per_k[dom]["flops_per_launch"],

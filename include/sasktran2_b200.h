@@ -197,6 +197,9 @@ int sk_b200_engine_info(Engine* engine, int* num_azimuth, int* chunk_wavelengths
 int sk_b200_engine_set_workspace_gb(Engine* engine, double gb);
 /* DFMA micro-benchmark on the current device: the FP64 roofline denominator (TFLOP/s) */
 double sk_b200_measure_fp64_tflops();
+/* 1 when the adjoint boundary-value solve of an (N = num_streams / 2, nlos) problem reuses the forward LU factors
+ * (transposed solves, the reference's dgbtrs('T')), 0 when it factorises A^T a second time. */
+int sk_b200_adjoint_reuses_factors(int n_half_streams, int nlos);
 /* page-locked host memory for caller-side buffers (falls back to malloc without a CUDA device) */
 void* sk_b200_host_alloc(size_t nbytes);
 void sk_b200_host_free(void* p);

@@ -116,6 +116,7 @@ def _declare(lib):
     f("sk_b200_engine_info", i, vp, c_int_p, c_int_p, c_double_p)
     f("sk_b200_engine_set_workspace_gb", i, vp, d)
     f("sk_b200_measure_fp64_tflops", d)
+    f("sk_b200_adjoint_reuses_factors", i, i, i)
     f("sk_b200_engine_debug_copy", C.c_longlong, vp, C.c_char_p, c_double_p, C.c_longlong)
     f("sk_b200_host_alloc", vp, C.c_size_t)
     f("sk_b200_host_free", None, vp)

@@ -999,6 +999,7 @@ long long sk_b200_engine_debug_copy(Engine* e, const char* name, double* host, l
     if (!e || !e->dev || !name || !host) return -1;
     return (long long)e->dev->debug_copy(name, host, (size_t)max_n);
 }
+int sk_b200_adjoint_reuses_factors(int n_half_streams, int nlos) { return disco::adjoint_reuses_factors(n_half_streams, nlos) ? 1 : 0; }
 double sk_b200_measure_fp64_tflops() { return disco::measure_fp64_tflops(); }
 void* sk_b200_host_alloc(size_t nbytes) {
     try {

@@ -1077,8 +1077,11 @@ __global__ void __launch_bounds__(BvpCfg3<N, NRHS>::WARPS_PER_BLOCK * 32, 3) k_b
     staircase_solve_2d<N>(rows, smem + (size_t)wib * C::SMEM_DOUBLES_PER_GROUP, fac, lane, valid, V.status);
 }
 
+#ifndef DISCO_BVP4_MIN_BLOCKS
+#define DISCO_BVP4_MIN_BLOCKS 4
+#endif
 template <int N, bool BLOCKED = false>
-__global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, BvpCfg2<N, 1>::MIN_BLOCKS) k_bvp_v2(ChunkView V) {
+__global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, BLOCKED ? DISCO_BVP4_MIN_BLOCKS : BvpCfg2<N, 1>::MIN_BLOCKS) k_bvp_v2(ChunkView V) {
     using C = BvpCfg2<N, 1>;
     extern __shared__ __align__(16) double smem[];
     const int lane_w = threadIdx.x & 31;

@@ -90,8 +90,10 @@ struct WfCfg {
     static constexpr int EXCH = NSTR * N + 2 * N * N + 2 * N;  // projs | Xs | Xms | lam, pad
     __host__ __device__ static constexpr int lps_doubles(int nlos) { return nlos * 2 * NH * N; }
     __host__ __device__ static constexpr int red_doubles(int nlos) { return nlos * (NL + 1) * N; }
+    // + 2 doubles: the problems of a warp read their private areas at the same offset in the same instruction; a
+    // 16-byte skew per problem puts those broadcasts on different banks (without it every LDS is a 32/N-way conflict)
     __host__ __device__ static constexpr int per_problem(int nlos) {
-        return lps_doubles(nlos) + (red_doubles(nlos) > EXCH ? red_doubles(nlos) : EXCH);
+        return lps_doubles(nlos) + (red_doubles(nlos) > EXCH ? red_doubles(nlos) : EXCH) + 2;
     }
     // block tables: tW[NSTR][N] | tM[NSTR][N] | tL[nlos][NSTR] | lpc[NSTR] | wmu[N]
     __host__ __device__ static constexpr int table_doubles(int nlos) { return 2 * NSTR * N + nlos * NSTR + NSTR + N; }

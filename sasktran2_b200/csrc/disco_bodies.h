@@ -47,10 +47,10 @@ struct ChunkView {
     double* xsol;             // [nw][M][L][2N]        BVP solution L | M
     double* fac;              // [group][fac_stride]   pivot rows of the staircase LU (forward and adjoint)
     size_t fac_stride;        // doubles per solve group: (L+1) * 2N * (4N + max nrhs)
-    double* zadj;             // [nw][M][nlos][2N*L]   adjoint BVP solutions A^T z = wvec (weighting functions)
+    double* zadj;             // [nw][M][2N*L][nlos]   adjoint BVP solutions A^T z = wvec (weighting functions), LOS fastest
     double* lfac;             // [nw*M][lfac_stride]   elimination multipliers of the forward LU, [pivot][LS] (null: not kept)
     size_t lfac_stride;       // doubles per problem: L * 2N * LS
-    double* yadj;             // [nw][M][nlos][2N*L]   U^T y = wvec intermediate of the transposed solve
+    double* yadj;             // [nw][M][2N*L][nlos]   U^T y = wvec intermediate of the transposed solve, LOS fastest
     double* radiance;         // [nw][nlos]
     // ---- weighting functions (null / 0 when not requested)
     int ngroups;              // scattering derivative groups G

@@ -1126,12 +1126,16 @@ struct TsolveCfg {
     static constexpr int NC = F::NC, FS = F::FS, LS = F::LS, ROWS = F::ROWS, RL2 = F::RL2;
     static constexpr int STAGES = 2;
     static constexpr int WARPS_PER_BLOCK = 2;
-    // + 4 doubles: the problems of a warp read their rings at the same offset in the same instruction, a 32-byte
-    // skew per problem keeps those 16-byte broadcasts on different banks
-    static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS + 4;
+    // ring of two factor blocks + 4 doubles: the problems of a warp read their rings at the same offset in the same
+    // instruction, a 32-byte skew per problem keeps those 16-byte broadcasts on different banks
+    __host__ __device__ static constexpr int smem_doubles_per_group(int) { return STAGES * NC * FS + 4; }
     static_assert(LS <= FS, "multiplier blocks share the ring slots of the factor blocks");
 };
 
+// y and z are LOS-fastest in global memory ([t][nlos]) so that the lanes of a problem (one per LOS) touch one or two
+// 128-byte lines per access instead of one line each; the wvec rows ([nlos][L][2N], LOS slowest - the layout K2c
+// writes and K4 streams) are read per lane one step ahead.  (Staging them cooperatively through shared memory was
+// measured slower: the extra 2.9 KB per problem costs a third of the resident problems.)
 template <int N>
 __global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsolve(ChunkView V, int glt, int gpw, int nbatch) {
     using C = TsolveCfg<N>;
@@ -1150,16 +1154,17 @@ __global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsol
     if (!valid_group) gid = ngroups - 1;
     const int batch = (int)(gid % nbatch);
     const long long prob = gid / nbatch;
-    int los = batch * glt + r;
+    const int los0 = batch * glt;
+    int los = los0 + r;
     const bool store_ok = valid_group && in_group && los < nlos;
     if (los >= nlos) los = nlos - 1;
-    double* ring = smem + (size_t)gslot * C::SMEM_DOUBLES_PER_GROUP;
+    double* ring = smem + (size_t)gslot * C::smem_doubles_per_group(glt);
     const double* fac = V.fac + (size_t)prob * V.fac_stride;
     const double* lfac = V.lfac + (size_t)prob * V.lfac_stride;
-    const size_t vo = ((size_t)prob * nlos + los) * ((size_t)2 * N * L);
-    const double* wv = V.wvec + vo;   // [L][2N]
-    double* yb = V.yadj + vo;         // [2N L]
-    double* zb = V.zadj + vo;         // [2N L]
+    const size_t nrow = (size_t)2 * N * L;
+    const double* wv = V.wvec + ((size_t)prob * nlos + los) * nrow;          // this lane's [L][2N]
+    double* yb = V.yadj + (size_t)prob * nrow * nlos + los;                  // y[t * nlos]
+    double* zb = V.zadj + (size_t)prob * nrow * nlos + los;                  // z[row * nlos]
 
     auto fetch = [&](const double* src, int ndoubles, int slot) {
         if (src != nullptr && in_group) {
@@ -1169,8 +1174,8 @@ __global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsol
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + e) : "memory");
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    auto commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
 
     // ---- phase 1: U^T y = w, window of 4N right-hand-side entries per lane
     double win[4 * N];
@@ -1191,8 +1196,10 @@ __global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsol
         }
     }
     fetch(fac, NC * FS, 0);
+    commit();
     for (int step = 0; step < L; ++step) {
         fetch(step + 1 < L ? fac + (size_t)(step + 1) * NC * FS : nullptr, NC * FS, (step + 1) % STAGES);
+        commit();
         // right-hand-side entries that enter the window after this step: requested now, consumed at the end
         double2 nxt[N];
         {
@@ -1216,9 +1223,9 @@ __global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsol
             for (int cc = c + 1; cc < 4 * N; ++cc) win[cc] = fma(-u[cc], y, win[cc]);
         }
         if (store_ok) {
-            double2* y2 = reinterpret_cast<double2*>(yb + (size_t)step * NC);
+            double* yo = yb + (size_t)step * NC * nlos;
 #pragma unroll
-            for (int j = 0; j < N; ++j) y2[j] = make_double2(win[2 * j], win[2 * j + 1]);
+            for (int c = 0; c < NC; ++c) yo[(size_t)c * nlos] = win[c];
         }
 #pragma unroll
         for (int j = 0; j < N; ++j) {
@@ -1237,21 +1244,23 @@ __global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsol
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) v[i] = 0.0;
     fetch(lfac + (size_t)(L - 1) * NC * LS, NC * LS, (L - 1) % STAGES);
+    commit();
     // y of a step: this lane's own phase-1 stores (same thread, same addresses), requested one step ahead; lanes
     // without a line of sight carry zeros
-    auto load_y = [&](int step, double2* dst) {
-        const double2* y2 = reinterpret_cast<const double2*>(yb + (size_t)(step >= 0 ? step : 0) * NC);
+    auto load_y = [&](int step, double* dst) {
+        const double* yi = yb + (size_t)(step >= 0 ? step : 0) * NC * nlos;
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-            dst[j] = make_double2(0.0, 0.0);
-            if (store_ok && step >= 0) dst[j] = y2[j];
+        for (int c = 0; c < NC; ++c) {
+            dst[c] = 0.0;
+            if (store_ok && step >= 0) dst[c] = yi[(size_t)c * nlos];
         }
     };
-    double2 ycur[N];
+    double ycur[NC];
     load_y(L - 1, ycur);
     for (int step = L - 1; step >= 0; --step) {
         fetch(step > 0 ? lfac + (size_t)(step - 1) * NC * LS : nullptr, NC * LS, (step + STAGES - 1) % STAGES);
-        double2 ynext[N];
+        commit();
+        double ynext[NC];
         load_y(step - 1, ynext);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
@@ -1268,16 +1277,15 @@ __global__ void __launch_bounds__(TsolveCfg<N>::WARPS_PER_BLOCK * 32) k_bvp_tsol
                 else if ((i & 3) == 2) s2 = fma(t, v[i], s2);
                 else s3 = fma(t, v[i], s3);
             }
-            const double yc = (c & 1) ? ycur[c >> 1].y : ycur[c >> 1].x;
-            const double z = yc - ((s0 + s1) + (s2 + s3));
+            const double z = ycur[c] - ((s0 + s1) + (s2 + s3));
             const double rec = f[ROWS];
             const int plane = __double2loint(rec), prow = __double2hiint(rec);
 #pragma unroll
             for (int i = 0; i < ROWS; ++i) v[i] = (i == plane) ? z : v[i];
-            if (store_ok) zb[prow] = z;
+            if (store_ok) zb[(size_t)prow * nlos] = z;
         }
 #pragma unroll
-        for (int j = 0; j < N; ++j) ycur[j] = ynext[j];
+        for (int c = 0; c < NC; ++c) ycur[c] = ynext[c];
         __syncwarp();
     }
 }
@@ -1457,7 +1465,7 @@ static void launch_bvp_adjoint_n(const ChunkView& V, cudaStream_t s) {
             const int nbatch = (nlos + glt - 1) / glt;
             const long long ngroups = (long long)V.nw * V.M * nbatch;
             const int gpb = C::WARPS_PER_BLOCK * gpw;
-            const size_t smem = (size_t)gpb * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
+            const size_t smem = (size_t)gpb * C::smem_doubles_per_group(glt) * sizeof(double);
             static bool attr_set = false;
             if (!attr_set) {
                 cudaFuncSetAttribute(k_bvp_tsolve<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);

@@ -368,7 +368,7 @@ struct AdjointRows {
     DISCO_HD void store(int step, int c, int r, double v) const {
         if (r >= nl) return;
         const int row = (step == 0) ? c : N + (step - 1) * 2 * N + c;
-        V.zadj[(((size_t)w * V.M + ms) * V.T.nlos + (los0 + r)) * ((size_t)2 * N * L) + row] = v;
+        V.zadj[(((size_t)w * V.M + ms) * ((size_t)2 * N * L) + row) * V.T.nlos + (los0 + r)] = v;
     }
 };
 

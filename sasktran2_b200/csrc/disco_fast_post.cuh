@@ -247,8 +247,27 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
     const double c_ss1 = (2 * j + 1 < nl) ? -ssa * beta[m + 2 * j + 1] * lpc[m + 2 * j + 1] : 0.0;
     const double albedo = V.albedo[w];
     const double trans_floor = V.lay_trans[(size_t)w * (L + 1) + L];
+    // per-LOS scalars are fetched one iteration ahead (the loop is short on independent work to hide an L2 round trip)
+    double n_mu, n_att, n_E, n_inv, n_atop;
+    {
+        const double* ll0 = V.los_lay + (((size_t)w * nlos + 0) * L + p) * 3;
+        n_mu = V.T.los_mu[0];
+        n_att = ll0[0];
+        n_E = ll0[1];
+        n_inv = ll0[2];
+        n_atop = V.los_att[((size_t)w * nlos + 0) * (L + 1) + p];
+    }
     for (int los = 0; los < nlos; ++los) {
-        const double mu = V.T.los_mu[los];
+        const double mu = n_mu, att = n_att, E = n_E, inv_1mus = n_inv, att_top = n_atop;
+        {
+            const int ln = los + 1 < nlos ? los + 1 : los;
+            const double* lln = V.los_lay + (((size_t)w * nlos + ln) * L + p) * 3;
+            n_mu = V.T.los_mu[ln];
+            n_att = lln[0];
+            n_E = lln[1];
+            n_inv = lln[2];
+            n_atop = V.los_att[((size_t)w * nlos + ln) * (L + 1) + p];
+        }
         const double* __restrict__ tl = tL + los * NSTR + m;
         double Yp = 0.0, Ym = 0.0;
 #pragma unroll
@@ -262,9 +281,6 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
                 }
             }
         }
-        const double* __restrict__ ll = V.los_lay + (((size_t)w * nlos + los) * L + p) * 3;
-        const double att = ll[0], E = ll[1], inv_1mus = ll[2];
-        const double att_top = V.los_att[((size_t)w * nlos + los) * (L + 1) + p];
         const double hp = div_fast(1.0 - thj * att, 1.0 + mu * kj);
         double hm;
         {

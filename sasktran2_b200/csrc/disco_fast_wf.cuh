@@ -326,17 +326,27 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
     // head of that LOS's reduction row with cp.async: the HBM latency overlaps pass 3 and the scalar set-up instead of
     // stalling every LOS iteration (2 warps per scheduler cannot hide it).  Layout per LOS: zt[2N] | zb[2N].
     {
+        // zadj is [row][los] (LOS fastest): the rows of this layer's two boundaries x all LOS are one contiguous run,
+        // copied element by element (lane-contiguous 8-byte chunks) into the per-LOS rows of the reduction area
         const bool bottom_ = (p == L - 1);
-        for (int los = 0; los < nlos; ++los) {
-            const double* z = V.zadj + (((size_t)w * M + ms) * nlos + los) * ((size_t)2 * N * L);
-            const double* zt = (p == 0) ? z : z + N + (size_t)(p - 1) * 2 * N;
-            const double* zb = z + N + (size_t)p * 2 * N;
-            double* dst = red + (size_t)los * (NL + 1) * N;
-            const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst + j);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0), "l"(zt + j) : "memory");
-            if (p != 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + 8u * N), "l"(zt + N + j) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + 16u * N), "l"(zb + j) : "memory");
-            if (!bottom_) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + 24u * N), "l"(zb + N + j) : "memory");
+        const int row0 = (p == 0) ? 0 : N + (p - 1) * 2 * N;
+        const int nrows = ((p == 0) ? N : 2 * N) + (bottom_ ? N : 2 * N);
+        const double* zsrc = V.zadj + (((size_t)w * M + ms) * ((size_t)2 * N * L) + row0) * nlos;
+        const int total = nrows * nlos;
+        int zi = 0, zl = j;  // element e = zi * nlos + zl
+        while (zl >= nlos) {
+            zl -= nlos;
+            ++zi;
+        }
+        for (int e = j; e < total; e += N) {
+            const int off = (p == 0 && zi >= N) ? zi + N : zi;  // the TOA boundary has N rows: zb starts at 2N
+            const unsigned d0 = (unsigned)__cvta_generic_to_shared(red + (size_t)zl * (NL + 1) * N + off);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0), "l"(zsrc + e) : "memory");
+            zl += N;
+            while (zl >= nlos) {
+                zl -= nlos;
+                ++zi;
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }

@@ -415,23 +415,25 @@ DISCO_HD void wf_layer_body(const ChunkView& V, long long idx) {
     const double t_floor = V.lay_trans[(size_t)w * (L + 1) + L];
     const size_t nrow = (size_t)2 * N * L;
     for (int los = 0; los < nlos; ++los) {
-        const double* z = V.zadj + (((size_t)w * M + ms) * nlos + los) * nrow;
+        // zadj is [row][los] (LOS fastest): element `row` of this LOS sits at z[row * nlos]
+        const double* z = V.zadj + ((size_t)w * M + ms) * nrow * nlos + los;
+        const size_t zs = (size_t)nlos;
         D adj(0.0);
         if (p == 0) {
-            for (int i = 0; i < N; ++i) adj = adj - (Gpt[i] + r1[i]) * z[i];
+            for (int i = 0; i < N; ++i) adj = adj - (Gpt[i] + r1[i]) * z[i * zs];
         } else {
-            const double* zt = z + N + (size_t)(p - 1) * 2 * N;
-            for (int i = 0; i < N; ++i) adj = adj + (Gmt[i] + r2[i]) * zt[i] + (Gpt[i] + r1[i]) * zt[N + i];
+            const double* zt = z + (N + (size_t)(p - 1) * 2 * N) * zs;
+            for (int i = 0; i < N; ++i) adj = adj + (Gmt[i] + r2[i]) * zt[i * zs] + (Gpt[i] + r1[i]) * zt[(N + i) * zs];
         }
         double zg_sum = 0.0;
         if (!bottom) {
-            const double* zb = z + N + (size_t)p * 2 * N;
-            for (int i = 0; i < N; ++i) adj = adj - (Gmb[i] + r4[i]) * zb[i] - (Gpb[i] + r3[i]) * zb[N + i];
+            const double* zb = z + (N + (size_t)p * 2 * N) * zs;
+            for (int i = 0; i < N; ++i) adj = adj - (Gmb[i] + r4[i]) * zb[i * zs] - (Gpb[i] + r3[i]) * zb[(N + i) * zs];
         } else {
-            const double* zg = z + N + (size_t)(L - 1) * 2 * N;
+            const double* zg = z + (N + (size_t)(L - 1) * 2 * N) * zs;
             for (int i = 0; i < N; ++i) {
-                adj = adj - (Gmb[i] + r4[i]) * zg[i];
-                zg_sum += zg[i];
+                adj = adj - (Gmb[i] + r4[i]) * zg[i * zs];
+                zg_sum += zg[i * zs];
             }
             if (refl) adj = adj + gsum * (albedo * zg_sum);
         }

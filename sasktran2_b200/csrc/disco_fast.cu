@@ -1,4 +1,6 @@
 // Register-resident fast path of the layer solve (N = 2, 4, 8 streams per hemisphere): instantiations + launchers.
+#include <cstdlib>
+
 #include "disco_fast_eig.cuh"
 #include "disco_fast_post.cuh"
 #include "disco_fast_wf.cuh"
@@ -6,6 +8,21 @@
 namespace disco {
 
 bool fast_path_supported(int N) { return N == 2 || N == 4 || N == 8; }
+
+// blocks per azimuth order of a persistent layer kernel: 8 blocks per SM over all orders (a few waves - short
+// tails, long enough to amortise the table set-up); SK_B200_WF_BLOCKS overrides
+static int wf_fast_blocks_per_order(int M) {
+    static const int total = [] {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const char* e = std::getenv("SK_B200_WF_BLOCKS");
+        const int per_sm = e ? std::atoi(e) : 8;
+        return sms * (per_sm > 0 ? per_sm : 8);
+    }();
+    const int b = (total + M - 1) / M;
+    return b > 0 ? b : 1;
+}
 
 template <int N>
 static void launch_fast_n(const ChunkView& V, cudaStream_t s) {
@@ -23,7 +40,9 @@ static void launch_fast_n(const ChunkView& V, cudaStream_t s) {
         cudaFuncSetAttribute(k_layer_post<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    const dim3 grid_p((unsigned)((nq + PostCfg<N>::PPB - 1) / PostCfg<N>::PPB), (unsigned)V.M);
+    const long long nblk_p = (nq + PostCfg<N>::PPB - 1) / PostCfg<N>::PPB;
+    const long long cap_p = 2LL * wf_fast_blocks_per_order((int)V.M);  // persistent blocks, three resident per SM
+    const dim3 grid_p((unsigned)(nblk_p < cap_p ? nblk_p : cap_p), (unsigned)V.M);
     k_layer_post<N><<<grid_p, 128, smem, s>>>(V);
 }
 

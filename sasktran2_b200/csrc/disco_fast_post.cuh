@@ -118,8 +118,10 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
     const int pib = threadIdx.x / N;                // problem in block
     const unsigned lane = threadIdx.x & 31;
     const unsigned gmask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (lane / N * N));
-    long long q = (long long)blockIdx.x * Cf::PPB + pib;  // w * L + p
+    // persistent blocks: the order's tables are set up once, the block strides over its (wavelength, layer) problems
     const long long nq = (long long)V.nw * L;
+    for (long long qblk = blockIdx.x; qblk * Cf::PPB < nq; qblk += gridDim.x) {
+    long long q = qblk * Cf::PPB + pib;  // w * L + p
     const bool valid = q < nq;
     if (!valid) q = nq - 1;
     const int w = (int)(q / L), p = (int)(q % L);
@@ -310,6 +312,8 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
             V.wvec[o * 2 * N + N + j] = cneg;
             V.vsrc[o * N + j] = v;
         }
+    }
+    __syncwarp();  // the exchange slots are rewritten by the next problem
     }
 }
 

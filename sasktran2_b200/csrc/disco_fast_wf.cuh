@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
     double* Xms = Xs + N * N;                     // [a][i]
     double* lam = Xms + N * N;                    // [i]
 
+    // one pass per block: a persistent variant (block strides over its problems, tables set up once) was measured
+    // 20 % slower - the loop-carried state costs registers this kernel does not have
     long long q = (long long)blockIdx.x * Cf::PPB + pib;  // w * L + p
     const long long nq = (long long)V.nw * L;
     const bool valid = q < nq;

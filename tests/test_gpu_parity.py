@@ -246,7 +246,10 @@ def _assert_wf(oracle_mod, sc, res, perturbations=(1e-12, -1e-12, 3e-12, -3e-12,
 @pytest.mark.parametrize("nstr,interp,geotype,nlos,nlayers", [(4, 2, 0, 2, 9), (8, 1, 1, 3, 12), (16, 1, 1, 6, 25),
                                                              (2, 1, 1, 2, 9), (32, 1, 1, 2, 6),
                                                              # more lines of sight than panel lanes (adjoint RHS batches)
-                                                             (2, 1, 1, 7, 8), (4, 1, 1, 11, 8), (8, 1, 0, 12, 8)])
+                                                             (2, 1, 1, 7, 8), (4, 1, 1, 11, 8), (8, 1, 0, 12, 8),
+                                                             # transposed solves: more LOS than lanes of a warp (two
+                                                             # batches, the last one partly filled), a single layer
+                                                             (4, 1, 1, 37, 5), (8, 1, 1, 5, 1), (2, 1, 0, 33, 1)])
 def test_cuda_weighting_functions_vs_oracle(oracle_mod, nstr, interp, geotype, nlos, nlayers):
     import sasktran2_b200 as sk
     from sasktran2_b200 import scenarios

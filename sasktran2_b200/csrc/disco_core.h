@@ -62,6 +62,9 @@ struct Tables {
     const double* lp_los;  // [los][m][l]
     const double* los_mu;  // [nlos]
     const double* los_cosmphi;  // [nlos][m]  cos(m * azimuth)
+    // per azimuth order, the shared-memory tables of k_wf_layer_fast in its own layout (null: other paths):
+    // [m][ tW[nstr][N] | tM[nstr][N] | tL[nlos][nstr] | lpc[nstr] | wmu[N] ]
+    const double* wf_tab;
 };
 
 // Output of the per-layer solve, thread-local

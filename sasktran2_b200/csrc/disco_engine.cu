@@ -56,6 +56,31 @@ DeviceEngine::DeviceEngine(const EngineOptions& opt, const HostPlan& plan) : m_o
     d_lp_csz = upload(plan.lp_csz);
     d_lp_los = upload(plan.lp_los);
     d_los_mu = upload(plan.los_mu);
+    if (fast_path_supported(plan.N)) {
+        // Tables::wf_tab: what every block of k_wf_layer_fast used to rebuild from lp_mu / lp_los / lp_csz (one FP64
+        // division per entry of tM, 12 % of that kernel's stall samples) - the same products, formed once
+        const int nstr = plan.nstr, N = plan.N, nlos = plan.nlos;
+        const size_t td = 2 * (size_t)nstr * N + (size_t)nlos * nstr + nstr + N;
+        std::vector<double> tab(td * nstr, 0.0);
+        for (int m = 0; m < nstr; ++m) {
+            double* tW = tab.data() + td * m;
+            double* tM = tW + (size_t)nstr * N;
+            double* tL = tM + (size_t)nstr * N;
+            double* lpc = tL + (size_t)nlos * nstr;
+            double* wmu = lpc + nstr;
+            for (int l = 0; l < nstr; ++l)
+                for (int q = 0; q < N; ++q) {
+                    const double lp = plan.lp_mu[((size_t)m * N + q) * nstr + l];
+                    tW[l * N + q] = plan.wt[q] * lp;
+                    tM[l * N + q] = lp / plan.mu[q];
+                }
+            for (int los = 0; los < nlos; ++los)
+                for (int l = 0; l < nstr; ++l) tL[los * nstr + l] = plan.lp_los[((size_t)los * nstr + m) * nstr + l];
+            for (int l = 0; l < nstr; ++l) lpc[l] = plan.lp_csz[(size_t)m * nstr + l];
+            for (int i = 0; i < N; ++i) wmu[i] = plan.wt[i] * plan.mu[i];
+        }
+        d_wf_tab = upload(tab);
+    }
     d_los_cosmphi = upload(plan.los_cosmphi);
     d_layer_dh = upload(plan.layer_dh);
     d_interp_w = upload(plan.interp_w);
@@ -104,7 +129,7 @@ DeviceEngine::~DeviceEngine() {
     free_wf_inputs();
     free_inputs();
     free_workspace();
-    for (void* p : {(void*)d_mu, (void*)d_wt, (void*)d_lp_mu, (void*)d_lp_csz, (void*)d_lp_los, (void*)d_los_mu,
+    for (void* p : {(void*)d_mu, (void*)d_wt, (void*)d_lp_mu, (void*)d_lp_csz, (void*)d_lp_los, (void*)d_los_mu, (void*)d_wf_tab,
                     (void*)d_los_cosmphi, (void*)d_layer_dh, (void*)d_interp_w, (void*)d_interp_idx,
                     (void*)d_chapman, (void*)d_mlist, (void*)d_status})
         if (p) cudaFree(p);
@@ -367,6 +392,7 @@ void DeviceEngine::solve_staged() {
     V.T.lp_csz = d_lp_csz;
     V.T.lp_los = d_lp_los;
     V.T.los_mu = d_los_mu;
+    V.T.wf_tab = d_wf_tab;
     V.T.los_cosmphi = d_los_cosmphi;
     V.layer_dh = d_layer_dh;
     V.interp_idx = d_interp_idx;

@@ -98,6 +98,7 @@ class DeviceEngine {
     cudaEvent_t m_ev[8] = {};
     // geometry tables on device
     double *d_mu = nullptr, *d_wt = nullptr, *d_lp_mu = nullptr, *d_lp_csz = nullptr, *d_lp_los = nullptr;
+    double* d_wf_tab = nullptr;  // per-order tables of the fast weighting-function kernel (Tables::wf_tab)
     double *d_los_mu = nullptr, *d_los_cosmphi = nullptr, *d_layer_dh = nullptr, *d_interp_w = nullptr, *d_chapman = nullptr;
     int *d_interp_idx = nullptr, *d_mlist = nullptr;
     std::vector<int> m_mlist;

@@ -114,16 +114,12 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
     double* wmu = lpc + NSTR;            // [i] w_i mu_i
     const int ms = blockIdx.y;
     const int m = V.m_list[ms];
-    for (int e = threadIdx.x; e < NSTR * N; e += blockDim.x) {
-        const int l = e / N, q = e % N;
-        const double lp = V.T.lp_mu[((size_t)m * N + q) * NSTR + l];
-        tW[e] = V.T.wt[q] * lp;
-        tM[e] = lp / V.T.mu[q];
+    {
+        // the order's tables, precomputed in this layout at engine creation (Tables::wf_tab): one coalesced copy
+        const int td = Cf::table_doubles(nlos);
+        const double* __restrict__ src = V.T.wf_tab + (size_t)m * td;
+        for (int e = threadIdx.x; e < td; e += blockDim.x) smem[e] = src[e];
     }
-    for (int e = threadIdx.x; e < nlos * NSTR; e += blockDim.x)
-        tL[e] = V.T.lp_los[((size_t)(e / NSTR) * NSTR + m) * NSTR + (e % NSTR)];
-    if (threadIdx.x < NSTR) lpc[threadIdx.x] = V.T.lp_csz[(size_t)m * NSTR + threadIdx.x];
-    if (threadIdx.x < N) wmu[threadIdx.x] = V.T.wt[threadIdx.x] * V.T.mu[threadIdx.x];
     __syncthreads();
 
     const int j = threadIdx.x % N;
@@ -335,17 +331,17 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         const int nrows = ((p == 0) ? N : 2 * N) + (bottom_ ? N : 2 * N);
         const double* zsrc = V.zadj + (((size_t)w * M + ms) * ((size_t)2 * N * L) + row0) * nlos;
         const int total = nrows * nlos;
-        int zi = 0, zl = j;  // element e = zi * nlos + zl
-        while (zl >= nlos) {
-            zl -= nlos;
-            ++zi;
-        }
+        const int dq = N / nlos, dr = N - dq * nlos;  // e += N  <=>  (zi, zl) += (dq, dr) with one carry
+        int zi = j / nlos, zl = j - zi * nlos;        // element e = zi * nlos + zl
+        const unsigned red0 = (unsigned)__cvta_generic_to_shared(red);
+        const int toa_shift = (p == 0) ? N : 0;       // the TOA boundary has N rows: zb starts at 2N
         for (int e = j; e < total; e += N) {
-            const int off = (p == 0 && zi >= N) ? zi + N : zi;  // the TOA boundary has N rows: zb starts at 2N
-            const unsigned d0 = (unsigned)__cvta_generic_to_shared(red + (size_t)zl * (NL + 1) * N + off);
+            const int off = (zi >= N) ? zi + toa_shift : zi;
+            const unsigned d0 = red0 + 8u * (unsigned)(zl * (NL + 1) * N + off);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0), "l"(zsrc + e) : "memory");
-            zl += N;
-            while (zl >= nlos) {
+            zi += dq;
+            zl += dr;
+            if (zl >= nlos) {
                 zl -= nlos;
                 ++zi;
             }

@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
             n_inv = lln[2];
             n_atop = V.los_att[((size_t)w * nlos + ln) * (L + 1) + p];
         }
+        const double imu = div_fast(1.0, mu);
         const double* __restrict__ tl = tL + los * NSTR + m;
         double Yp = 0.0, Ym = 0.0;
 #pragma unroll
@@ -288,9 +289,9 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
         {
             const double den = 1.0 - mu * kj;
             if (fabs(den) > 0.0001)
-                hm = od / mu * psi_fast(od, kj, 1.0 / mu, thj, att);
+                hm = od * imu * psi_fast(od, kj, imu, thj, att);
             else
-                hm = thj * od / mu * (1.0 - od * (kj - 1.0 / mu));
+                hm = thj * od * imu * (1.0 - od * (kj - imu));
         }
         const double Dp = (E - trans_top * exp_sec * hm) * inv_spk;
         const double Dm = trans_top * (mu * hp - od * att * psi_ks) * inv_1mus;

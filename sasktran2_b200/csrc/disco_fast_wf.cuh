@@ -215,13 +215,13 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
     double norm = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) norm = fma(wmu[i], fma(wp[i], wp[i], -wm[i] * wm[i]), norm);
-    const double inv_norm = 1.0 / norm;
+    const double inv_norm = div_fast(1.0, norm);
 
     // ---- pass 1: projections of X = W+ + W- (even l - m) and Xm = k (W+ - W-) (odd) -> exchange
     double pr[NSTR];
     {
         const double sc_even = kj * inv_norm;  // lambda_j / n_j,  n_j = k_j norm_j
-        const double sc_odd = inv_norm / kj;   // 1 / n_j
+        const double sc_odd = div_fast(inv_norm, kj);   // 1 / n_j
 #pragma unroll
         for (int lo = 0; lo < NSTR; ++lo) {
             pr[lo] = 0.0;
@@ -286,14 +286,16 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const bool self = (i == j);
-            const double rden = self ? 0.0 : 1.0 / (lamj - lam[i]);
+            const double rden = self ? 0.0 : div_fast(1.0, lamj - lam[i]);
 #pragma unroll
             for (int e = 0; e < NH; ++e) {
-                if (self) dk[e] = P[e][i] / (2.0 * kj);
+                if (self) dk[e] = P[e][i];   // P_jj, scaled below (no division per i)
                 Q[e][i] = P[e][i] * rden;
             }
         }
-        const double ikj = 1.0 / kj;
+        const double ikj = div_fast(1.0, kj);
+#pragma unroll
+        for (int e = 0; e < NH; ++e) dk[e] *= 0.5 * ikj;
 #pragma unroll
         for (int a = 0; a < N; ++a) {
             double dx[NH];
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         Cp.s = -0.5 * trans_top * od * od * thj;
     }
     {
-        const double est = exp_sec * thj, ispk = 1.0 / (secant + kj);
+        const double est = exp_sec * thj, ispk = div_fast(1.0, secant + kj);
         Cm.v = trans_top * (1.0 - est) * ispk;
         Cm.k = (trans_top * od * est - Cm.v) * ispk;
         Cm.a = trans_top * est;
@@ -442,14 +444,15 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
     dB[iTau] = fma(Lj, -kj * thj, ap * Cp.a);
     dA[iS] = am * Cm.s;
     dB[iS] = ap * Cp.s;
-    dA[iT] = amc / trans_top;
-    dB[iT] = apc / trans_top;
+    const double inv_tt = 1.0 / trans_top;  // once per problem (beam transmittances span the double range)
+    dA[iT] = amc * inv_tt;
+    dB[iT] = apc * inv_tt;
 
     const bool bottom = (p == L - 1);
     const bool refl = bottom && (m == 0);
     const double albedo = V.albedo[w];
     const double t_floor = V.lay_trans[(size_t)w * (L + 1) + L];
-    const double inv_spk = 1.0 / (secant + kj);
+    const double inv_spk = div_fast(1.0, secant + kj);
     // this lane's share of the single-scatter phase sum Q (l' = 2j, 2j+1) and its heavy-lane derivatives
     double cq0[NH + 1], cq1[NH + 1];  // [value, d eps_g.., d omega]
     {
@@ -478,6 +481,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
+    const double inv_ssa = div_fast(1.0, ssa);
     // per-LOS scalars are fetched one iteration ahead (software pipelining of the global loads)
     double n_mu, n_att, n_E, n_inv, n_atop;
     {
@@ -490,6 +494,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
     }
     for (int los = 0; los < nlos; ++los) {
         const double mu = n_mu, att = n_att, E = n_E, inv_1mus = n_inv, att_top = n_atop;
+        const double imu = div_fast(1.0, mu);
         {
             const int ln = los + 1 < nlos ? los + 1 : los;
             const double* ll = V.los_lay + (((size_t)w * nlos + ln) * L + p) * 3;
@@ -545,7 +550,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
             }
         }
         {
-            const double iw = 1.0 / ssa;
+            const double iw = inv_ssa;
             dYp[G] = fma(Yp, iw, dYp[G]);
             dYm[G] = fma(Ym, iw, dYm[G]);
         }
@@ -556,11 +561,10 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
             const double iden = div_fast(1.0, 1.0 + mu * kj);
             hp.v = (1.0 - tha) * iden;
             hp.k = (od * tha - hp.v * mu) * iden;
-            hp.a = (kj + 1.0 / mu) * tha * iden;
+            hp.a = (kj + imu) * tha * iden;
         }
         {
             const double den = 1.0 - mu * kj;
-            const double imu = 1.0 / mu;
             if (fabs(den) > 0.0001) {
                 const R3 ps = psi_dual(od, kj, imu, thj, att);
                 hm.v = od * imu * ps.v;
@@ -574,7 +578,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
             }
         }
         const double esa = exp_sec * att;
-        const double E_a = trans_top * inv_1mus * (secant + 1.0 / mu) * esa;
+        const double E_a = trans_top * inv_1mus * (secant + imu) * esa;
         const double E_s = fma(-mu * inv_1mus, E, trans_top * inv_1mus * od * esa);
         {
             const double tes = trans_top * exp_sec;
@@ -589,7 +593,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         {
             const double H_v = od * att * psk.v;
             const double H_k = od * att * psk.k;
-            const double H_a = att * (psk.v - od / mu * psk.v + od * psk.a);
+            const double H_a = att * (psk.v - od * imu * psk.v + od * psk.a);
             const double H_s = od * att * psk.s;
             const double ti = trans_top * inv_1mus;
             Dm.v = ti * (mu * hp.v - H_v);
@@ -606,7 +610,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         double out[NL];
         out[iTau] = fma(Yp, fma(Lj, hp.a, ap * Dm.a), fma(Ym, fma(Mj, hm.a, am * Dp.a), Qj * E_a));
         out[iS] = fma(Yp * ap, Dm.s, fma(Ym * am, Dp.s, Qj * E_s));
-        out[iT] = fma(Yp * ap, Dm.v, fma(Ym * am, Dp.v, Qj * E)) / trans_top;
+        out[iT] = fma(Yp * ap, Dm.v, fma(Ym * am, Dp.v, Qj * E)) * inv_tt;
 #pragma unroll
         for (int e = 0; e < NH; ++e) {
             const int ln = e < G ? e : iOm;

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
     }
     const double f0 = (m == 0 ? 1.0 : 2.0) * (1.0 / (4.0 * kPi));
     {
-        const double rn = f0 / norm;
+        const double rn = div_fast(f0, norm);
         ap *= rn;
         am *= rn;
     }
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
     else
         Cp = trans_top * thj * od * (1.0 - od / 2.0 * (secant - kj));
     if (fabs(secant + kj) > kGreensEps)
-        Cm = trans_top * (1.0 - exp_sec * thj) / (secant + kj);
+        Cm = trans_top * div_fast(1.0 - exp_sec * thj, secant + kj);
     else
         Cm = trans_top * od * (1.0 - od / 2.0 * (secant + kj));
     const double amc = am * Cm, apc = ap * Cp;
@@ -272,18 +272,22 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
         }
         const double imu = div_fast(1.0, mu);
         const double* __restrict__ tl = tL + los * NSTR + m;
-        double Yp = 0.0, Ym = 0.0;
+        double Yp = 0.0, Ym = 0.0, Yp1 = 0.0, Ym1 = 0.0;  // two DFMA chains per sum (latency, not throughput, binds)
 #pragma unroll
         for (int c = 0; c < NSTR / 4; ++c) {
             if (4 * c < nl) {  // uniform; Z is zero-padded up to the next multiple of 4 (tl may run past nl: the
                                // table row is followed by valid shared memory and multiplied by zero)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < 4; r += 2) {
                     Yp = fma(tl[4 * c + r], Zp[4 * c + r], Yp);
                     Ym = fma(tl[4 * c + r], Zm[4 * c + r], Ym);
+                    Yp1 = fma(tl[4 * c + r + 1], Zp[4 * c + r + 1], Yp1);
+                    Ym1 = fma(tl[4 * c + r + 1], Zm[4 * c + r + 1], Ym1);
                 }
             }
         }
+        Yp += Yp1;
+        Ym += Ym1;
         const double hp = div_fast(1.0 - thj * att, 1.0 + mu * kj);
         double hm;
         {

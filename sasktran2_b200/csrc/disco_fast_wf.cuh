@@ -511,10 +511,11 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
             // the "b" and "a" halves of every sum are separate DFMA chains (latency, not throughput, limits this
             // kernel at 8 warps per SM)
             double Ypa = 0.0, Yma = 0.0, dYpa[NH], dYma[NH], dYpg[G > 0 ? G : 1], dYmg[G > 0 ? G : 1];
+            double dYpga[G > 0 ? G : 1], dYmga[G > 0 ? G : 1];
 #pragma unroll
             for (int e = 0; e < NH; ++e) dYp[e] = dYm[e] = dYpa[e] = dYma[e] = 0.0;
 #pragma unroll
-            for (int g = 0; g < G; ++g) dYpg[g] = dYmg[g] = 0.0;
+            for (int g = 0; g < G; ++g) dYpg[g] = dYmg[g] = dYpga[g] = dYmga[g] = 0.0;
 #pragma unroll
             for (int qq = 0; qq < N; ++qq) {
                 const double a = ls[qq], b = ls[N + qq];  // lps_minus, lps_plus
@@ -532,8 +533,10 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const double da = ls[(2 + 2 * g) * N + qq], db = ls[(3 + 2 * g) * N + qq];
-                    dYpg[g] = fma(db, wp[qq], fma(da, wm[qq], dYpg[g]));
-                    dYmg[g] = fma(db, wm[qq], fma(da, wp[qq], dYmg[g]));
+                    dYpg[g] = fma(db, wp[qq], dYpg[g]);
+                    dYpga[g] = fma(da, wm[qq], dYpga[g]);
+                    dYmg[g] = fma(db, wm[qq], dYmg[g]);
+                    dYmga[g] = fma(da, wp[qq], dYmga[g]);
                 }
             }
             Yp += Ypa;
@@ -545,8 +548,8 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
             }
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                dYp[g] += dYpg[g];
-                dYm[g] += dYmg[g];
+                dYp[g] += dYpg[g] + dYpga[g];
+                dYm[g] += dYmg[g] + dYmga[g];
             }
         }
         {

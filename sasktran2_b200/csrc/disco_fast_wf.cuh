@@ -692,9 +692,21 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         const int nrows = nlos * (NL + 1);
         for (int row = j; row < nrows; row += N) {
             const double* r = red + (size_t)row * N;
-            double s = 0.0;
+            double s;
+            if (N >= 4) {  // pairwise tree: log2(N) dependent additions instead of N
+                double t[N];
 #pragma unroll
-            for (int i = 0; i < N; ++i) s += r[i];
+                for (int i = 0; i < N; ++i) t[i] = r[i];
+#pragma unroll
+                for (int w2 = N / 2; w2 >= 1; w2 /= 2)
+#pragma unroll
+                    for (int i = 0; i < w2; ++i) t[i] += t[i + w2];
+                s = t[0];
+            } else {
+                s = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) s += r[i];
+            }
             const int los = row / (NL + 1), c = row % (NL + 1);
             const size_t o = (((size_t)w * M + ms) * nlos + los) * L + p;
             if (c < NL)

@@ -301,7 +301,7 @@ def test_cuda_weighting_functions_config5_shape(oracle_mod):
     _assert_wf(oracle_mod, full, res, perturbations=(1e-12, -1e-12, 1e-11))
 
 
-def _run_variant(env_overrides, tmp_path, tag):
+def _run_variant(env_overrides, tmp_path, tag, nlos=10):
     """Solves one fixed weighting-function scenario in a fresh process (the kernel-selection switches are read once
     per process) and returns its outputs."""
     import os
@@ -312,7 +312,7 @@ def _run_variant(env_overrides, tmp_path, tag):
     code = (
         "import numpy as np, sasktran2_b200 as sk\n"
         "from sasktran2_b200 import scenarios\n"
-        "sc = scenarios.small_wf_case(nstr=16, nlayers=31, nwavel=40, nlos=10)\n"
+        f"sc = scenarios.small_wf_case(nstr=16, nlayers=31, nwavel=40, nlos={nlos})\n"
         "_, _, _, eng, atm = sk.engine_for_scenario(sc)\n"
         "atm.surface.enable_albedo_derivative('wf_albedo')\n"
         "res = eng.calculate_radiance(atm)\n"
@@ -346,6 +346,22 @@ def test_cuda_kernel_variants_agree(tmp_path):
             err = np.abs(other[k] - base[k]) / scale
             tol = 1e-4 if "aerosol" in k else 1e-8
             assert err.max() <= tol, (tag, k, float(err.max()))
+
+
+@pytest.mark.parametrize("nlos", [1, 2])
+def test_cuda_adjoint_paths_agree_for_few_lines_of_sight(tmp_path, nlos):
+    """With one or two lines of sight and 16 streams the engine picks the second factorisation of A^T (too few busy
+    lanes for the transposed solves); forcing the transposed solves (three one-lane problems per warp) must give the
+    same weighting functions."""
+    base = _run_variant({}, tmp_path, f"few_default_{nlos}", nlos=nlos)
+    other = _run_variant({"SK_B200_ADJOINT": "reuse"}, tmp_path, f"few_reuse_{nlos}", nlos=nlos)
+    np.testing.assert_allclose(other["radiance"], base["radiance"], rtol=1e-12)
+    for k in base:
+        if k == "radiance":
+            continue
+        scale = np.abs(base[k]).max(axis=0, keepdims=True) if base[k].ndim == 4 else np.abs(base[k]).max()
+        err = np.abs(other[k] - base[k]) / scale
+        assert err.max() <= (1e-4 if "aerosol" in k else 1e-8), (k, float(err.max()))
 
 
 def test_cuda_large_spectrum_properties():

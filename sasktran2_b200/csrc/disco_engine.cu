@@ -49,6 +49,9 @@ DeviceEngine::DeviceEngine(const EngineOptions& opt, const HostPlan& plan) : m_o
         m_opt.workspace_gb = std::min(32.0, 0.25 * (double)free_b / (1024.0 * 1024.0 * 1024.0));
     }
     CUDA_OK(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&m_copy, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&m_ev_h2d_tail, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&m_ev_out_ready, cudaEventDisableTiming));
     for (auto& ev : m_ev) CUDA_OK(cudaEventCreate(&ev));
     d_mu = upload(plan.mu);
     d_wt = upload(plan.wt);
@@ -135,6 +138,9 @@ DeviceEngine::~DeviceEngine() {
         if (p) cudaFree(p);
     for (auto& ev : m_ev)
         if (ev) cudaEventDestroy(ev);
+    if (m_ev_h2d_tail) cudaEventDestroy(m_ev_h2d_tail);
+    if (m_ev_out_ready) cudaEventDestroy(m_ev_out_ready);
+    if (m_copy) cudaStreamDestroy(m_copy);
     if (m_stream) cudaStreamDestroy(m_stream);
 }
 
@@ -155,7 +161,16 @@ void DeviceEngine::free_workspace() {
     m_ws_chunk = 0;
 }
 
-size_t DeviceEngine::workspace_bytes_per_wavelength() const {
+size_t DeviceEngine::workspace_bytes_per_wavelength() const { return ws_bytes(m_wf_on, m_ngroups); }
+
+int DeviceEngine::planned_chunk(int nw, bool wf_on, int ngroups) const {
+    const double budget = m_opt.workspace_gb * 1024.0 * 1024.0 * 1024.0;
+    long long c = (long long)(budget / (double)ws_bytes(wf_on, ngroups));
+    c = std::max<long long>(c, 1);
+    return (int)std::min<long long>(c, std::max(nw, 1));
+}
+
+size_t DeviceEngine::ws_bytes(bool wf_on, int ngroups) const {
     const size_t N = m_plan.N, L = m_plan.L, nstr = m_plan.nstr, nlos = m_plan.nlos, M = m_mlist.size();
     size_t d = L * (6 + nstr) + 2 * (L + 1);                       // layer optics
     d += 2 * M * L * N * N + M * L * 2 * N + M * L * 4 * N;         // W+, W-, k|theta, G
@@ -164,10 +179,10 @@ size_t DeviceEngine::workspace_bytes_per_wavelength() const {
     d += M * nlos * L * 2 * N + M * nlos * L * vw;                  // wvec, vsrc
     if (m_fast) d += 3 * (N * (N + 1) / 2) * M * L + nlos * (L + 1) + nlos * L * 3;  // eigen planes, LOS exponentials
     d += M * L * 2 * N;                                             // x
-    if (!m_wf_on) {
+    if (!wf_on) {
         d += M * bvp_fac_stride((int)N, 1, (int)L);                  // LU pivot rows (forward solve)
     } else {
-        const size_t G = m_ngroups, nrhs = adjoint_max_rhs((int)nlos), ngrp = adjoint_groups_per_problem((int)nlos);
+        const size_t G = ngroups, nrhs = adjoint_max_rhs((int)nlos), ngrp = adjoint_groups_per_problem((int)nlos);
         if (adjoint_reuses_factors((int)N, (int)nlos))               // forward pivot rows + multipliers + U^T y
             d += M * (bvp_fac_stride((int)N, 1, (int)L) + bvp_lfac_stride((int)N, (int)L)) + M * nlos * 2 * N * L;
         else
@@ -275,14 +290,30 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
     }
     m_nw = nw;
     m_nleg = atm.nleg;
+    // Inside calculate() (m_overlap) only the wavelengths of the first chunk travel on the compute stream; the rest
+    // goes to the copy stream and is awaited by the first chunk that needs it (solve_staged).  Every staged array
+    // is wavelength-slowest, so head and tail are contiguous ranges of each.
+    {
+        const bool wf0 = wf && wf->enabled() && nw > 0;
+        m_h2d_head = (m_overlap && nw > 0) ? planned_chunk(nw, wf0, wf0 ? (int)wf->d_legendre.size() : 0) : nw;
+    }
+    const size_t head = (size_t)m_h2d_head, tail = (size_t)nw - head;
+    // the copy engine serves same-direction copies in submission order, whatever their stream: all heads are
+    // submitted first, the tails are queued here and submitted at the end of stage()
+    struct TailCopy { double* dst; const double* src; size_t bytes; };
+    std::vector<TailCopy> tails;
+    auto h2d = [&](double* dst, const double* src, size_t per_w) {  // src, dst: first staged wavelength
+        if (head > 0)
+            CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(double) * per_w * head, cudaMemcpyHostToDevice, m_stream));
+        if (tail > 0) tails.push_back({dst + per_w * head, src + per_w * head, sizeof(double) * per_w * tail});
+    };
     CUDA_OK(cudaEventRecord(m_ev[0], m_stream));
     if (nw > 0) {
-        CUDA_OK(cudaMemcpyAsync(d_ext, atm.ext + nloc * w0, sizeof(double) * nloc * nw, cudaMemcpyHostToDevice, m_stream));
-        CUDA_OK(cudaMemcpyAsync(d_ssa, atm.ssa + nloc * w0, sizeof(double) * nloc * nw, cudaMemcpyHostToDevice, m_stream));
-        CUDA_OK(cudaMemcpyAsync(d_leg, atm.leg + (size_t)atm.nleg * nloc * w0, sizeof(double) * atm.nleg * nloc * nw,
-                                cudaMemcpyHostToDevice, m_stream));
-        CUDA_OK(cudaMemcpyAsync(d_solar, atm.solar + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
-        CUDA_OK(cudaMemcpyAsync(d_albedo, atm.albedo + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
+        h2d(d_ext, atm.ext + nloc * w0, nloc);
+        h2d(d_ssa, atm.ssa + nloc * w0, nloc);
+        h2d(d_leg, atm.leg + (size_t)atm.nleg * nloc * w0, (size_t)atm.nleg * nloc);
+        h2d(d_solar, atm.solar + w0, 1);
+        h2d(d_albedo, atm.albedo + w0, 1);
     }
     // delta-M truncation fraction and its derivatives (set by sk_atmosphere_apply_delta_m_scaling)
     m_has_f = atm.f != nullptr && nw > 0;
@@ -294,10 +325,10 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
             d_fdm = dalloc<double>(need);
             m_cap_fdm = need;
         }
-        CUDA_OK(cudaMemcpyAsync(d_fdm, atm.f + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
+        h2d(d_fdm, atm.f + nloc * w0, nloc);
         for (size_t g = 0; g < G; ++g) {
             if (wf->d_f[g])
-                CUDA_OK(cudaMemcpyAsync(d_fdm + (1 + g) * n2, wf->d_f[g] + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
+                h2d(d_fdm + (1 + g) * n2, wf->d_f[g] + nloc * w0, nloc);
             else
                 CUDA_OK(cudaMemsetAsync(d_fdm + (1 + g) * n2, 0, sizeof(double) * n2, m_stream));
         }
@@ -346,25 +377,27 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
             }
         }
         for (int g = 0; g < m_ngroups; ++g)
-            CUDA_OK(cudaMemcpyAsync(d_dleg + nl3 * g, wf->d_legendre[g] + (size_t)atm.nleg * nloc * w0,
-                                    sizeof(double) * nl3, cudaMemcpyHostToDevice, m_stream));
+            h2d(d_dleg + nl3 * g, wf->d_legendre[g] + (size_t)atm.nleg * nloc * w0, (size_t)atm.nleg * nloc);
         for (size_t i = 0; i < m_maps.size(); ++i) {
             DevMapping& dm = m_maps[i];
             const WfMapping& mp = wf->mappings[i];
             dm.host = mp;
-            CUDA_OK(cudaMemcpyAsync(dm.d_ssa, mp.d_ssa + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
-            CUDA_OK(cudaMemcpyAsync(dm.d_ext, mp.d_extinction + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
-            if (mp.scat_factor)
-                CUDA_OK(cudaMemcpyAsync(dm.scat, mp.scat_factor + nloc * w0, sizeof(double) * n2, cudaMemcpyHostToDevice, m_stream));
+            h2d(dm.d_ssa, mp.d_ssa + nloc * w0, nloc);
+            h2d(dm.d_ext, mp.d_extinction + nloc * w0, nloc);
+            if (mp.scat_factor) h2d(dm.scat, mp.scat_factor + nloc * w0, nloc);
             if (mp.interpolator)
                 CUDA_OK(cudaMemcpyAsync(dm.interp, mp.interpolator, sizeof(double) * nloc * mp.nout, cudaMemcpyHostToDevice, m_stream));
         }
         for (size_t i = 0; i < m_surfs.size(); ++i) {
             m_surfs[i].host = wf->surfaces[i];
-            CUDA_OK(cudaMemcpyAsync(m_surfs[i].d_brdf, wf->surfaces[i].d_brdf + w0, sizeof(double) * nw, cudaMemcpyHostToDevice, m_stream));
+            h2d(m_surfs[i].d_brdf, wf->surfaces[i].d_brdf + w0, 1);
         }
     }
     CUDA_OK(cudaEventRecord(m_ev[1], m_stream));
+    for (const auto& t : tails) CUDA_OK(cudaMemcpyAsync(t.dst, t.src, t.bytes, cudaMemcpyHostToDevice, m_copy));
+    m_tail_pending = !tails.empty();
+    if (m_tail_pending) CUDA_OK(cudaEventRecord(m_ev_h2d_tail, m_copy));
+    if (m_overlap) return;  // calculate(): the kernels queue right behind the head copies; fetch() reads the timing
     CUDA_OK(cudaStreamSynchronize(m_stream));
     float ms = 0;
     CUDA_OK(cudaEventElapsedTime(&ms, m_ev[0], m_ev[1]));
@@ -419,6 +452,17 @@ void DeviceEngine::solve_staged() {
     mark();
     for (int w0 = 0; w0 < m_nw; w0 += chunk) {
         V.nw = std::min(chunk, m_nw - w0);
+        if (m_tail_pending && w0 + V.nw > m_h2d_head) {  // first chunk that reads inputs copied on m_copy
+            CUDA_OK(cudaStreamWaitEvent(m_stream, m_ev_h2d_tail, 0));
+            m_tail_pending = false;
+        }
+        if (m_overlap && w0 > 0 && w0 + V.nw >= m_nw) {
+            // last chunk: everything before it is final - its way to the host overlaps this chunk's kernels
+            CUDA_OK(cudaEventRecord(m_ev_out_ready, m_stream));
+            CUDA_OK(cudaStreamWaitEvent(m_copy, m_ev_out_ready, 0));
+            copy_outputs(0, w0, m_early_radiance, m_copy);
+            m_early_done = w0;
+        }
         V.ext = d_ext + nloc * w0;
         V.ssa = d_ssa + nloc * w0;
         V.leg = d_leg + (size_t)m_nleg * nloc * w0;
@@ -495,31 +539,62 @@ void DeviceEngine::solve_staged() {
     if (st & 4u) throw std::runtime_error("BVP could not be solved since the coefficient matrix was singular.");
 }
 
+// device -> host copies of the results of staged wavelengths [w_begin, w_end) (radiance [nw][nlos]; weighting
+// functions [nout][nw_total][nlos], one strided copy per mapping)
+void DeviceEngine::copy_outputs(int w_begin, int w_end, double* radiance_host, cudaStream_t s) {
+    if (w_end <= w_begin || m_plan.nlos <= 0) return;
+    const size_t nlos = m_plan.nlos, n = (size_t)(w_end - w_begin), off = (size_t)w_begin * nlos;
+    CUDA_OK(cudaMemcpyAsync(radiance_host + off, d_radiance + off, sizeof(double) * n * nlos, cudaMemcpyDeviceToHost, s));
+    if (m_wf_on) {
+        const size_t width = sizeof(double) * n * nlos;
+        for (auto& dm : m_maps)
+            CUDA_OK(cudaMemcpy2DAsync(dm.host.out + (size_t)m_w0 * nlos + off, sizeof(double) * (size_t)m_nw_total * nlos,
+                                      dm.out + off, sizeof(double) * (size_t)m_nw * nlos, width, dm.host.nout,
+                                      cudaMemcpyDeviceToHost, s));
+        for (auto& ds : m_surfs)
+            CUDA_OK(cudaMemcpyAsync(ds.host.out + (size_t)m_w0 * nlos + off, ds.out + off, width, cudaMemcpyDeviceToHost, s));
+    }
+}
+
 void DeviceEngine::fetch(double* radiance_host) {
     CUDA_OK(cudaEventRecord(m_ev[2], m_stream));
-    if (m_nw > 0 && m_plan.nlos > 0)
-        CUDA_OK(cudaMemcpyAsync(radiance_host, d_radiance, sizeof(double) * (size_t)m_nw * m_plan.nlos,
-                                cudaMemcpyDeviceToHost, m_stream));
-    if (m_wf_on && m_nw > 0) {
-        const size_t nlos = m_plan.nlos;
-        const size_t width = sizeof(double) * (size_t)m_nw * nlos;
-        for (auto& dm : m_maps)
-            CUDA_OK(cudaMemcpy2DAsync(dm.host.out + (size_t)m_w0 * nlos, sizeof(double) * (size_t)m_nw_total * nlos, dm.out,
-                                      width, width, dm.host.nout, cudaMemcpyDeviceToHost, m_stream));
-        for (auto& ds : m_surfs)
-            CUDA_OK(cudaMemcpyAsync(ds.host.out + (size_t)m_w0 * nlos, ds.out, width, cudaMemcpyDeviceToHost, m_stream));
-    }
+    copy_outputs(m_early_done, m_nw, radiance_host, m_stream);   // everything, unless calculate() sent a part ahead
     CUDA_OK(cudaEventRecord(m_ev[3], m_stream));
     CUDA_OK(cudaStreamSynchronize(m_stream));
+    CUDA_OK(cudaStreamSynchronize(m_copy));
+    m_early_done = 0;
     float ms = 0;
     CUDA_OK(cudaEventElapsedTime(&ms, m_ev[2], m_ev[3]));
     m_ms[T_D2H] = ms;
+    if (m_overlap) {  // stage() did not wait: the exposed part of the host -> device copies is read here
+        CUDA_OK(cudaEventElapsedTime(&ms, m_ev[0], m_ev[1]));
+        m_ms[T_H2D] = ms;
+    }
 }
 
+// One call = copy in, solve, copy out, with the copies of all but one chunk hidden behind the kernels
+// (SK_B200_OVERLAP=0 serialises them).
 void DeviceEngine::calculate(const AtmosphereArrays& atm, int w0, int nw, double* radiance_host, const WfRequest* wf) {
-    stage(atm, w0, nw, wf);
-    solve_staged();
-    fetch(radiance_host);
+    static const bool overlap = [] {
+        const char* e = std::getenv("SK_B200_OVERLAP");
+        return !(e && e[0] == '0');
+    }();
+    m_overlap = overlap;
+    m_early_radiance = radiance_host;
+    m_early_done = 0;
+    try {
+        stage(atm, w0, nw, wf);
+        solve_staged();
+        fetch(radiance_host);
+    } catch (...) {
+        m_overlap = false;
+        m_tail_pending = false;
+        m_early_done = 0;
+        cudaStreamSynchronize(m_copy);
+        cudaStreamSynchronize(m_stream);
+        throw;
+    }
+    m_overlap = false;
 }
 
 }  // namespace disco

@@ -95,6 +95,17 @@ class DeviceEngine {
     EngineOptions m_opt;
     HostPlan m_plan;
     cudaStream_t m_stream = nullptr;
+    // copy/compute overlap inside calculate(): inputs beyond the first chunk arrive on m_copy while the first chunk is
+    // solved, outputs of all chunks but the last leave on m_copy while the last chunk is solved
+    cudaStream_t m_copy = nullptr;
+    cudaEvent_t m_ev_h2d_tail = nullptr, m_ev_out_ready = nullptr;
+    bool m_overlap = false, m_tail_pending = false;
+    int m_h2d_head = 0;             // staged wavelengths that the compute stream may touch without waiting for m_copy
+    int m_early_done = 0;           // wavelengths whose outputs are already on their way to the host
+    double* m_early_radiance = nullptr;
+    int planned_chunk(int nw, bool wf_on, int ngroups) const;
+    size_t ws_bytes(bool wf_on, int ngroups) const;
+    void copy_outputs(int w_begin, int w_end, double* radiance_host, cudaStream_t s);
     cudaEvent_t m_ev[8] = {};
     // geometry tables on device
     double *d_mu = nullptr, *d_wt = nullptr, *d_lp_mu = nullptr, *d_lp_csz = nullptr, *d_lp_los = nullptr;

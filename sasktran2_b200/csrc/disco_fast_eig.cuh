@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(128) k_eig_jacobi(ChunkView V) {
             if (!__any_sync(0xffffffffu, any)) break;
         }
     }
-    double k[N];
+    double k[N], kinv_all[N];
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
@@ -254,7 +254,13 @@ __global__ void __launch_bounds__(128) k_eig_jacobi(ChunkView V) {
             bad = true;
             ksq = fabs(ksq) + 1e-300;
         }
-        k[j] = sqrt(ksq);
+        // sqrt and its reciprocal from one Newton-refined rsqrt (the IEEE sqrt / division slow paths cost ~60
+        // instructions per eigenvalue); k is corrected once more so that k * k == ksq to rounding
+        const double ry = rsqrt_nr(ksq);
+        double kk = ksq * ry;
+        kk = fma(0.5 * ry, fma(-kk, kk, ksq), kk);
+        k[j] = kk;
+        kinv_all[j] = ry;
     }
     if (bad && valid) atomicOr(V.status, 2u);
     // X~ = H Z in place (H lower triangular: row i only needs rows <= i, so go bottom-up)
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(128) k_eig_jacobi(ChunkView V) {
     for (int e = 0; e < TS; ++e) Sp[e] = V.eigS[(size_t)e * P + pi];
     double dinv[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) dinv[i] = 0.5 / sqrt(V.T.wt[i] * V.T.mu[i]);
+    for (int i = 0; i < N; ++i) dinv[i] = 0.5 * rsqrt_nr(V.T.wt[i] * V.T.mu[i]);
     double* __restrict__ Wp = V.Wp + idx * N * N;
     double* __restrict__ Wm = V.Wm + idx * N * N;
     constexpr int JB = (N >= 2) ? 2 : 1;  // columns per pass (16-byte stores along j)
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(128) k_eig_jacobi(ChunkView V) {
     for (int j0 = 0; j0 < N; j0 += JB) {
         double kinv[JB];
 #pragma unroll
-        for (int jj = 0; jj < JB; ++jj) kinv[jj] = 1.0 / k[j0 + jj];
+        for (int jj = 0; jj < JB; ++jj) kinv[jj] = kinv_all[j0 + jj];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             double wp[JB], wm[JB];

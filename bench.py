@@ -65,7 +65,7 @@ def flop_model(nstr, nlayers, nlos, m_list, ngroups=1, adjoint_refactor=False):
 
 # DRAM bytes per wavelength (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, divided by
 # the 600 wavelengths of the profiled launch) for the default shape: 16 streams, 100 layers, 10 LOS, weighting
-# functions with one scattering group - profiles/ncu_r01_v11_summary.csv.  Other shapes report traffic = null.
+# functions with one scattering group - profiles/ncu_r01_v12_summary.csv.  Other shapes report traffic = null.
 NCU_DRAM_BYTES_PER_WAVELENGTH = {"layer": (0.813 + 2.020 + 3.324) * 1e9 / 600, "bvp": (6.151 + 7.813) * 1e9 / 600,
                                  "wf_adjoint": (10.033 + 2.442) * 1e9 / 600, "wf_layer": (3.041 + 0.453) * 1e9 / 600}
 
@@ -396,7 +396,7 @@ def main():
         "unit": "TFLOP/s", "frac": per_k[dom]["frac"],
         "traffic": (NCU_DRAM_BYTES_PER_WAVELENGTH[dom] * (nw / nchunks) / launches_per_chunk[dom]
                     if (args.nstr, args.layers, nlos, with_wf) == (16, 100, 10, True) else None),
-        "traffic_source": "profiles/ncu_r01_v11_summary.csv (dram bytes per wavelength of the profiled launch x wavelengths per launch)",
+        "traffic_source": "profiles/ncu_r01_v12_summary.csv (dram bytes per wavelength of the profiled launch x wavelengths per launch)",
         "peak_source": "DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP64 figure)",
         "share_of_step": per_k[dom]["share_of_step"], "avg_launch_ms": per_k[dom]["avg_launch_ms"],
         "flops_per_launch": per_k[dom]["flops_per_launch"],

@@ -37,6 +37,10 @@ typedef struct Surface Surface;
 typedef struct BRDF BRDF;
 typedef struct OutputC OutputC;
 typedef struct Engine Engine;
+typedef struct Geometry2D Geometry2D;
+typedef struct Geodetic Geodetic;
+typedef struct OutputJVP OutputJVP;
+typedef struct OutputVJP OutputVJP;
 
 /* ---- Config: cpp/include/c_api/config.h:1-138 (enum values cpp/include/sasktran2/config.h:41-71,
  *      defaults cpp/lib/config/config.cpp:5-33) ---- */
@@ -80,6 +84,43 @@ int sk_config_get_input_validation_mode(Config* config, int* mode);
 int sk_config_set_input_validation_mode(Config* config, int mode);
 int sk_config_get_log_level(Config* config, int* log_level);
 int sk_config_set_log_level(Config* config, int log_level);
+/* stored and returned; options of sources outside the CUDA path (HR, successive orders, refraction, flux) */
+int sk_config_get_singlescatter_phasemode(Config* config, int* phasemode);
+int sk_config_set_singlescatter_phasemode(Config* config, int phasemode);
+int sk_config_get_num_do_spherical_iterations(Config* config, int* num_iterations);
+int sk_config_set_num_do_spherical_iterations(Config* config, int num_iterations);
+int sk_config_get_num_hr_spherical_iterations(Config* config, int* num_iterations);
+int sk_config_set_num_hr_spherical_iterations(Config* config, int num_iterations);
+int sk_config_get_num_hr_incoming(Config* config, int* num_incoming);
+int sk_config_set_num_hr_incoming(Config* config, int num_incoming);
+int sk_config_get_num_hr_outgoing(Config* config, int* num_outgoing);
+int sk_config_set_num_hr_outgoing(Config* config, int num_outgoing);
+int sk_config_get_num_hr_full_incoming_points(Config* config, int* num_points);
+int sk_config_set_num_hr_full_incoming_points(Config* config, int num_points);
+int sk_config_get_initialize_hr_with_do(Config* config, int* initialize);
+int sk_config_set_initialize_hr_with_do(Config* config, int initialize);
+int sk_config_get_successive_orders_relative_tolerance(Config* config, double* tolerance);
+int sk_config_set_successive_orders_relative_tolerance(Config* config, double tolerance);
+int sk_config_get_successive_orders_absolute_tolerance(Config* config, double* tolerance);
+int sk_config_set_successive_orders_absolute_tolerance(Config* config, double tolerance);
+int sk_config_get_successive_orders_anderson_depth(Config* config, int* depth);
+int sk_config_set_successive_orders_anderson_depth(Config* config, int depth);
+int sk_config_get_successive_orders_damping(Config* config, double* damping);
+int sk_config_set_successive_orders_damping(Config* config, double damping);
+int sk_config_get_num_successive_orders_altitudes(Config* config, int* num_altitudes);
+int sk_config_get_successive_orders_altitude_grid_m(Config* config, double* altitude_grid_m);
+int sk_config_set_successive_orders_altitude_grid_m(Config* config, const double* altitude_grid_m, int num_altitudes);
+int sk_config_get_los_refraction(Config* config, int* refraction);
+int sk_config_set_los_refraction(Config* config, int refraction);
+int sk_config_get_multiple_scatter_refraction(Config* config, int* refraction);
+int sk_config_set_multiple_scatter_refraction(Config* config, int refraction);
+int sk_config_get_stokes_basis(Config* config, int* basis);
+int sk_config_set_stokes_basis(Config* config, int basis);
+int sk_config_get_output_los_optical_depth(Config* config, int* output);
+int sk_config_set_output_los_optical_depth(Config* config, int output);
+int sk_config_get_num_flux_types(Config* config, int* num_flux_types);
+int sk_config_get_flux_types(Config* config, int* flux_types);
+int sk_config_set_flux_types(Config* config, const int* flux_types, int num_flux_types);
 
 /* ---- Geometry1D: cpp/include/c_api/geometry.h:10-21 ---- */
 Geometry1D* sk_geometry1d_create(double cos_sza, double saa, double earth_radius, double* grid_values,
@@ -87,6 +128,19 @@ Geometry1D* sk_geometry1d_create(double cos_sza, double saa, double earth_radius
 void sk_geometry1d_destroy(Geometry1D* geometry);
 int sk_geometry1d_get_num_altitudes(const Geometry1D* geometry);
 int sk_geometry1d_get_altitudes(const Geometry1D* geometry, double* altitudes);
+int sk_geometry1d_get_refractive_index_ptr(const Geometry1D* geometry, double** refractive_index);
+/* Geometry2D (cpp/include/c_api/geometry.h:24-61): not on the path; create returns NULL, accessors -3 */
+Geometry2D* sk_geometry2d_create(double cos_sza, double saa, double earth_radius, const double* altitude_grid_values,
+                                 int num_altitudes, const double* horizontal_angle_grid_values,
+                                 int num_horizontal_locations, int altitude_interp_method);
+void sk_geometry2d_destroy(Geometry2D* geometry);
+int sk_geometry2d_get_location_shape(const Geometry2D* geometry, int* num_horizontal_locations, int* num_altitudes);
+int sk_geometry2d_get_altitudes(const Geometry2D* geometry, double* altitudes);
+int sk_geometry2d_get_horizontal_angles(const Geometry2D* geometry, double* horizontal_angles);
+int sk_geometry2d_get_refractive_index_ptr(const Geometry2D* geometry, const double** refractive_index);
+int sk_geometry2d_get_refractive_index_mut_ptr(Geometry2D* geometry, double** refractive_index);
+int sk_geometry2d_get_location_index(const Geometry2D* geometry, int altitude_index, int horizontal_index,
+                                     int* location_index);
 
 /* ---- ViewingGeometry: cpp/include/c_api/viewing_geometry.h:9-39 ---- */
 ViewingGeometry* sk_viewing_geometry_create();
@@ -94,6 +148,16 @@ void sk_viewing_geometry_destroy(ViewingGeometry* geometry);
 void sk_viewing_geometry_add_ground_viewing_solar(ViewingGeometry* geometry, double cos_sza,
                                                   double relative_azimuth_angle, double observeraltitude,
                                                   double cos_viewing_zenith);
+int sk_viewing_geometry_add_tangent_altitude_solar(ViewingGeometry* geometry, double tangent_altitude_m,
+                                                   double relative_azimuth_angle, double observeraltitude,
+                                                   double cos_sza);
+int sk_viewing_geometry_add_tangent_altitude(ViewingGeometry* geometry, double tangent_altitude_m,
+                                             double observer_altitude_m, double horizontal_angle_radians,
+                                             double viewing_azimuth_radians);
+int sk_viewing_geometry_add_solar_angles_observer_location(ViewingGeometry* geometry, double cos_sza,
+                                                           double relative_azimuth_angle, double cos_viewing_zenith,
+                                                           double observeraltitude);
+int sk_viewing_geometry_add_flux_observer_solar(ViewingGeometry* geometry, double cos_sza, double observeraltitude);
 int sk_viewing_geometry_num_rays(ViewingGeometry* geometry, int* num_rays);
 int sk_viewing_geometry_num_flux_observers(ViewingGeometry* geometry, int* num_observers);
 
@@ -114,6 +178,8 @@ Atmosphere* sk_atmosphere_create(AtmosphereStorage* storage, Surface* surface, i
                                  int calculate_emission_derivatives);
 void sk_atmosphere_destroy(Atmosphere* atmosphere);
 int sk_atmosphere_apply_delta_m_scaling(Atmosphere* atmosphere, int order);
+int sk_atmosphere_mark_changed(Atmosphere* atmosphere);
+int sk_atmosphere_get_revision(Atmosphere* atmosphere, unsigned long long* revision);
 Surface* sk_surface_create(int nwavel, int nstokes, double* emission);
 void sk_surface_destroy(Surface* surface);
 int sk_surface_set_brdf(Surface* surface, BRDF* brdf, double* brdf_args);
@@ -124,6 +190,8 @@ int sk_surface_set_zero(Surface* storage);
 
 /* ---- BRDF: cpp/include/c_api/brdf.h:9-16 (Lambertian only on the CUDA path) ---- */
 BRDF* sk_brdf_create_lambertian(int nstokes);
+BRDF* sk_brdf_create_kokhanovsky(int nstokes);
+BRDF* sk_brdf_create_modis(int nstokes);
 int sk_brdf_get_num_deriv(BRDF* config, int* num_deriv);
 int sk_brdf_get_num_args(BRDF* config, int* num_args);
 void sk_brdf_destroy(BRDF* config);
@@ -135,6 +203,7 @@ int sk_deriv_mapping_get_d_ssa(DerivativeMapping* mapping, double** ssa);
 int sk_deriv_mapping_get_d_extinction(DerivativeMapping* mapping, double** extinction);
 int sk_deriv_mapping_get_scat_factor(DerivativeMapping* mapping, double** scat_factor);
 int sk_deriv_mapping_get_d_legendre(DerivativeMapping* mapping, double** d_legendre);
+int sk_deriv_mapping_get_d_emission(DerivativeMapping* mapping, double** d_emission);
 int sk_deriv_mapping_get_scat_deriv_index(DerivativeMapping* mapping, int* scat_deriv_index);
 int sk_deriv_mapping_set_scat_deriv_index(DerivativeMapping* mapping, int scat_deriv_index);
 int sk_deriv_mapping_get_num_location(DerivativeMapping* mapping, int* num_location);
@@ -154,6 +223,13 @@ int sk_deriv_mapping_get_interpolator(DerivativeMapping* mapping, double** inter
 int sk_surface_deriv_mapping_get_num_wavel(SurfaceDerivativeMapping* mapping, int* num_wavel);
 int sk_surface_deriv_mapping_get_num_brdf_args(SurfaceDerivativeMapping* mapping, int* num_brdf_args);
 int sk_surface_deriv_mapping_get_d_brdf(SurfaceDerivativeMapping* mapping, double** brdf);
+int sk_surface_deriv_mapping_get_d_emission(SurfaceDerivativeMapping* mapping, double** emission);
+int sk_surface_deriv_mapping_get_interpolator(SurfaceDerivativeMapping* mapping, double** interpolator, int* dim1,
+                                              int* dim2);
+int sk_surface_deriv_mapping_set_interpolator(SurfaceDerivativeMapping* mapping, double* interpolator, int dim1,
+                                              int dim2);
+int sk_surface_deriv_mapping_get_interp_dim(SurfaceDerivativeMapping* mapping, const char** name);
+int sk_surface_deriv_mapping_set_interp_dim(SurfaceDerivativeMapping* mapping, const char* name);
 int sk_surface_deriv_mapping_set_zero(SurfaceDerivativeMapping* mapping);
 int sk_surface_deriv_mapping_destroy(SurfaceDerivativeMapping* mapping);
 
@@ -165,6 +241,22 @@ int sk_output_assign_derivative_memory(OutputC* output, const char* name, double
 int sk_output_assign_surface_derivative_memory(OutputC* output, const char* name, double* derivative_mapping,
                                                int nrad, int nstokes);
 
+/* flux outputs, LOS optical depth, JVP / VJP containers (cpp/include/c_api/output.h:22-53): outside the path, -3 / NULL */
+int sk_output_assign_flux_derivative_memory(OutputC* output, const char* name, double* derivative_mapping, int nrad,
+                                            int nderiv);
+int sk_output_assign_surface_flux_derivative_memory(OutputC* output, const char* name, double* derivative_mapping,
+                                                    int nrad);
+int sk_output_get_los_optical_depth(OutputC* output, double** od);
+OutputJVP* sk_output_jvp_create(double* radiance, double* jvp, int nrad, int nstokes);
+void sk_output_jvp_destroy(OutputJVP* output);
+int sk_output_jvp_assign_derivative_tangent(OutputJVP* output, const char* name, const double* tangent, int nparam);
+int sk_output_jvp_assign_surface_tangent(OutputJVP* output, const char* name, const double* tangent, int nparam);
+OutputVJP* sk_output_vjp_create(double* radiance, const double* cotangent, int nrad, int nstokes);
+void sk_output_vjp_destroy(OutputVJP* output);
+int sk_output_vjp_assign_derivative_gradient(OutputVJP* output, const char* name, double* gradient, int nparam);
+int sk_output_vjp_assign_surface_gradient(OutputVJP* output, const char* name, double* gradient, int nparam);
+int sk_output_vjp_finalize(OutputVJP* output);
+
 /* ---- Engine: cpp/include/c_api/engine.h:17-50 ---- */
 Engine* sk_engine_create(Config* engine, Geometry1D* geometry, ViewingGeometry* viewing_geometry);
 int sk_engine_calculate_radiance(Engine* engine, Atmosphere* atmosphere, OutputC* output, int only_initialize);
@@ -175,6 +267,44 @@ int sk_engine_calculate_radiance_block_thread(Engine* engine, OutputC* output, i
                                               int wavelength_count, int thread_idx);
 void sk_engine_destroy(Engine* engine);
 int sk_openmp_support_enabled();
+/* 2-D engine and the JVP / VJP drivers (engine.h:19-41): sk_engine_linearization_backend reports Jacobian-only, so the
+ * Rust layer forms the products from the streamed weighting functions and never calls these; they return -3 / NULL */
+Engine* sk_engine_create_2d(Config* engine, Geometry2D* geometry, ViewingGeometry* viewing_geometry);
+int sk_engine_calculate_jvp(Engine* engine, Atmosphere* atmosphere, OutputJVP* output);
+int sk_engine_initialize_jvp(Engine* engine, Atmosphere* atmosphere, OutputJVP* output);
+int sk_engine_calculate_jvp_wavelength_thread(Engine* engine, OutputJVP* output, int wavelength, int thread_idx);
+int sk_engine_calculate_vjp(Engine* engine, Atmosphere* atmosphere, OutputVJP* output);
+int sk_engine_initialize_vjp(Engine* engine, Atmosphere* atmosphere, OutputVJP* output);
+int sk_engine_calculate_vjp_block_thread(Engine* engine, OutputVJP* output, int wavelength_start, int wavelength_count,
+                                         int thread_idx);
+
+/* ---- Geodetic: cpp/include/c_api/geodetic.h:9-59 (coordinate helper of the Python layer; not on the path: NULL / -3) ---- */
+Geodetic* sk_geodetic_create(double equatorial_radius, double flattening_factor);
+void sk_geodetic_destroy(Geodetic* geodetic);
+int sk_geodetic_get_altitude(const Geodetic* geodetic, double* altitude);
+int sk_geodetic_get_latitude(const Geodetic* geodetic, double* latitude);
+int sk_geodetic_get_longitude(const Geodetic* geodetic, double* longitude);
+int sk_geodetic_get_location(const Geodetic* geodetic, double* x, double* y, double* z);
+int sk_geodetic_get_local_south(const Geodetic* geodetic, double* x, double* y, double* z);
+int sk_geodetic_get_local_up(const Geodetic* geodetic, double* x, double* y, double* z);
+int sk_geodetic_get_local_west(const Geodetic* geodetic, double* x, double* y, double* z);
+int sk_geodetic_get_altitude_intercepts(const Geodetic* geodetic, double altitude, double observer_x, double observer_y,
+                                        double observer_z, double look_vector_x, double look_vector_y,
+                                        double look_vector_z, double* x1, double* y1, double* z1, double* x2,
+                                        double* y2, double* z2);
+int sk_geodetic_from_lat_lon_altitude(const Geodetic* geodetic, double latitude, double longitude, double altitude);
+int sk_geodetic_from_tangent_altitude(const Geodetic* geodetic, double altitude, double observer_x, double observer_y,
+                                      double observer_z, double boresight_x, double boresight_y, double boresight_z,
+                                      double* look_vector_x, double* look_vector_y, double* look_vector_z);
+int sk_geodetic_from_tangent_point(const Geodetic* geodetic, double observer_x, double observer_y, double observer_z,
+                                   double look_vector_x, double look_vector_y, double look_vector_z);
+int sk_geodetic_from_xyz(const Geodetic* geodetic, double x, double y, double z);
+int sk_geodetic_is_valid(const Geodetic* geodetic, int* is_valid);
+int sk_geodetic_get_osculating_spheroid(const Geodetic* geodetic, double* radius, double* offset_x, double* offset_y,
+                                        double* offset_z);
+
+/* ---- cpp/include/c_api/sk_lapack.h: LAPACK dgesv semantics (the Rust Mie / optical code solves small systems with it) ---- */
+long long sk_lapack_dgesv(long long n, long long nrhs, double* a, long long lda, long long* ipiv, double* b, long long ldb);
 
 /* ---- extensions ---- */
 const char* sk_b200_last_error();

@@ -144,6 +144,14 @@ class AtmosphereStorage:
     def finalize_scattering_derivatives(self):
         _lib.check(_lib.lib().sk_atmosphere_storage_finalize_scattering_derivatives(self._h))
 
+    def set_zero(self):
+        """Zero the optical arrays, the derivative mappings and the delta-M state (sk_atmosphere_storage_set_zero)."""
+        _lib.check(_lib.lib().sk_atmosphere_storage_set_zero(self._h))
+
+    def _fingerprint(self):
+        # strided sample of the arrays the delta-M pass rewrites in place (cheap even for GB-size spectra)
+        return tuple(float(a.ravel(order="K")[::4099].sum()) for a in (self.ssa, self.total_extinction, self.leg_coeff))
+
 
 class Surface:
     """Lambertian surface (sk_surface_create + sk_brdf_create_lambertian + sk_surface_set_brdf)."""
@@ -194,6 +202,7 @@ class Atmosphere:
         self.calculate_derivatives = bool(calculate_derivatives)
         self._config = config
         self._applied_delta_m_order = None
+        self._scaled_fingerprint = None
         self._h = None
 
     @property
@@ -209,11 +218,27 @@ class Atmosphere:
         self.storage.finalize_scattering_derivatives()
         # delta-M scaling is applied by the atmosphere, once, with order = num_streams
         # (src/sasktran2/atmosphere.py:846-856): in place on the storage arrays and the derivative mappings
-        if self._config is not None and self._config.delta_m_scaling and self._applied_delta_m_order is None:
-            if self._config.num_streams != self.storage._nleg:
-                _lib.check(_lib.lib().sk_atmosphere_apply_delta_m_scaling(self._h, int(self._config.num_streams)))
-                self._applied_delta_m_order = int(self._config.num_streams)
+        if self._config is not None and self._config.delta_m_scaling:
+            if self._applied_delta_m_order is None:
+                if self._config.num_streams != self.storage._nleg:
+                    _lib.check(_lib.lib().sk_atmosphere_apply_delta_m_scaling(self._h, int(self._config.num_streams)))
+                    self._applied_delta_m_order = int(self._config.num_streams)
+                    self._scaled_fingerprint = self.storage._fingerprint()
+            elif self._scaled_fingerprint != self.storage._fingerprint():
+                # upstream rebuilds the storage from its constituents and rescales on every internal_object()
+                # (src/sasktran2/atmosphere.py:655-662, 846-856); here the caller owns the arrays, so refilling them
+                # without zero_storage() would pair unscaled optics with the stale truncation fractions
+                raise _lib.SasktranError("storage arrays were modified after delta-M scaling was applied to them: call "
+                                         "atmosphere.zero_storage() before refilling ssa / total_extinction / leg_coeff")
         return self._h
+
+    def zero_storage(self) -> None:
+        """Reset storage, mappings and surface to zero for the next fill (sasktran2.Atmosphere._zero_storage,
+        src/sasktran2/atmosphere.py:655-662); delta-M scaling is applied again by the next internal_object()."""
+        self.storage.set_zero()
+        self.surface.albedo[:] = 0.0
+        self._applied_delta_m_order = None
+        self._scaled_fingerprint = None
 
     def __del__(self):
         try:

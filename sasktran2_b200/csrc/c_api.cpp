@@ -15,59 +15,22 @@
 #include <string>
 #include <vector>
 
-#include "disco_engine.h"
+#include "c_api_types.h"
 
 namespace {
 thread_local std::string g_last_error;
 int g_log_level = 3;  // spdlog::level::warn (cpp/lib/config/config.cpp:21)
+std::mutex g_pin_mu;
+std::set<void*> g_pinned_ptrs;
+}  // namespace
 
+namespace skapi {
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
     if (g_log_level <= 4) std::fprintf(stderr, "[sasktran2_b200] %s\n", msg.c_str());
     return code;
 }
-}  // namespace
-
-// ---------------------------------------------------------------------------------------------------
-// handle types
-// ---------------------------------------------------------------------------------------------------
-struct Config {
-    int num_stokes = 1;
-    int multiple_scatter_source = 3;  // none
-    int single_scatter_source = 0;    // exact
-    int num_streams = 16;
-    int num_threads = 1;
-    int threading_model = 0;
-    int wavelength_batch_size = 1;
-    int num_singlescatter_moments = 16;
-    int apply_delta_scaling = 0;
-    int num_do_sza = 1;
-    int num_do_forced_azimuth = -1;
-    int do_backprop = 0;
-    int emission_source = 1;     // none
-    int occultation_source = 1;  // none
-    int solar_refraction = 0;
-    int wf_enabled = 1;
-    int wf_precision = 0;
-    int input_validation_mode = 0;
-    int log_level = 3;
-};
-
-struct Geometry1D {
-    disco::GeometrySpec spec;
-};
-
-struct ViewingGeometry {
-    std::vector<disco::LineOfSight> rays;
-    std::vector<double> ray_cos_sza;
-    int num_flux_observers = 0;
-};
-
-// Host memory the library owns and copies to / from the device every call (derivative mappings) is page-locked
-// when a CUDA device is present, so that the H2D copies run at PCIe speed; without a device it is plain malloc.
-static std::mutex g_pin_mu;
-static std::set<void*> g_pinned_ptrs;
-static void* host_alloc(size_t nbytes) {
+void* host_alloc(size_t nbytes) {
     void* p = nullptr;
     if (nbytes == 0) nbytes = 8;
     if (cudaMallocHost(&p, nbytes) == cudaSuccess && p) {
@@ -80,7 +43,7 @@ static void* host_alloc(size_t nbytes) {
     if (!p) throw std::bad_alloc();
     return p;
 }
-static void host_free(void* p) {
+void host_free(void* p) {
     if (!p) return;
     bool pinned = false;
     {
@@ -92,101 +55,11 @@ static void host_free(void* p) {
     else
         std::free(p);
 }
-template <class T>
-struct PinnedAlloc {
-    using value_type = T;
-    PinnedAlloc() = default;
-    template <class U>
-    PinnedAlloc(const PinnedAlloc<U>&) {}
-    T* allocate(size_t n) { return static_cast<T*>(host_alloc(n * sizeof(T))); }
-    void deallocate(T* p, size_t) { host_free(p); }
-    template <class U>
-    bool operator==(const PinnedAlloc<U>&) const { return true; }
-    template <class U>
-    bool operator!=(const PinnedAlloc<U>&) const { return false; }
-};
-using PinnedVec = std::vector<double, PinnedAlloc<double>>;
+}  // namespace skapi
+using skapi::fail;
+using skapi::host_alloc;
+using skapi::host_free;
 
-struct MappingImpl {
-    int nwavel = 0, nloc = 0, nleg = 0;
-    PinnedVec d_ssa, d_extinction, scat_factor, d_legendre;
-    bool has_d_ssa = false, has_d_extinction = false, has_legendre = false;
-    int scat_deriv_index = -1;
-    std::string interp_dim = "altitude", assign_name;
-    bool log_radiance_space = false;
-    std::vector<double> interpolator;  // column-major [dim1 = nloc, dim2 = nout]
-    int interp_d1 = 0, interp_d2 = 0;
-    bool is_scattering() const { return has_legendre; }
-    int num_output() const { return interp_d2 > 0 ? interp_d2 : nloc; }
-};
-struct DerivativeMapping {
-    MappingImpl* impl;
-};
-
-struct SurfaceMappingImpl {
-    int nwavel = 0, nargs = 1;
-    std::vector<double> d_brdf;  // [nwavel, nargs] column-major
-    bool has_d_brdf = false;
-    std::string interp_dim = "dummy";
-};
-struct SurfaceDerivativeMapping {
-    SurfaceMappingImpl* impl;
-};
-
-struct AtmosphereStorage {
-    int nloc = 0, nwavel = 0, nleg = 0, nstokes = 1;
-    double *ssa = nullptr, *ext = nullptr, *emission = nullptr, *leg = nullptr, *solar = nullptr;
-    std::map<std::string, MappingImpl> mappings;  // name order == the reference's std::map order
-    int num_scat_groups = 0;
-    // delta-M scaling state (AtmosphereGridStorageFull::f, d_f, applied_f_order, grid_storage.h:40-60)
-    int applied_f_order = 0;
-    PinnedVec f;                  // [nloc, nwavel] truncation fraction, empty until the scaling is applied
-    std::vector<PinnedVec> d_f;   // per scattering group: [nloc, nwavel]
-};
-
-struct BRDF {
-    int kind = 0;  // 0 lambertian
-    int nstokes = 1;
-};
-
-struct Surface {
-    int nwavel = 0, nstokes = 1;
-    double* emission = nullptr;
-    BRDF* brdf = nullptr;
-    double* brdf_args = nullptr;  // [nargs, nwavel]; Lambertian: albedo[nwavel]
-    std::vector<double> default_albedo;
-    std::map<std::string, SurfaceMappingImpl> mappings;
-};
-
-struct Atmosphere {
-    AtmosphereStorage* storage = nullptr;
-    Surface* surface = nullptr;
-    bool calc_derivs = false;
-    bool calc_emission_derivs = false;
-};
-
-struct DerivMem {
-    double* ptr;
-    int nrad, nstokes, nderiv;
-};
-struct OutputC {
-    double* radiance = nullptr;
-    int nrad = 0, nstokes = 1;
-    double* flux = nullptr;
-    int nflux = 0;
-    std::map<std::string, DerivMem> derivs;
-    std::map<std::string, DerivMem> surface_derivs;
-};
-
-struct Engine {
-    Config cfg;
-    Geometry1D* geometry = nullptr;
-    ViewingGeometry* viewing = nullptr;
-    std::unique_ptr<disco::DeviceEngine> dev;
-    Atmosphere* atmosphere = nullptr;  // set by calculate_radiance(only_initialize) for block calls
-    int staged_start = 0, staged_count = 0;
-    std::mutex mtx;
-};
 
 namespace {
 
@@ -235,6 +108,8 @@ int build_wf_request(Engine* e, Atmosphere* atm, OutputC* out, disco::WfRequest&
     const int nlos = (int)e->viewing->rays.size();
     const long long nrad = (long long)s->nwavel * nlos;
     sk_atmosphere_storage_finalize_scattering_derivatives(s);
+    if (s->num_scat_groups > 2)  // the weighting-function kernels are instantiated for 0, 1 and 2 groups
+        return fail(-2, "B200 DO path: at most 2 scattering derivative groups per call (got " + std::to_string(s->num_scat_groups) + ")");
     req.d_legendre.assign(s->num_scat_groups, nullptr);
     for (auto& kv : s->mappings)
         if (kv.second.is_scattering()) req.d_legendre[kv.second.scat_deriv_index] = kv.second.d_legendre.data();
@@ -380,7 +255,7 @@ void sk_viewing_geometry_add_ground_viewing_solar(ViewingGeometry* v, double cos
 }
 int sk_viewing_geometry_num_rays(ViewingGeometry* v, int* num_rays) {
     if (!v || !num_rays) return -1;
-    *num_rays = (int)v->rays.size();
+    *num_rays = (int)(v->rays.size() + v->other_rays.size());
     return 0;
 }
 int sk_viewing_geometry_num_flux_observers(ViewingGeometry* v, int* n) {
@@ -465,6 +340,10 @@ int sk_atmosphere_storage_set_zero(AtmosphereStorage* s) {
     if (s->ext) std::fill(s->ext, s->ext + n, 0.0);
     if (s->emission) std::fill(s->emission, s->emission + n, 0.0);
     if (s->leg) std::fill(s->leg, s->leg + n * s->nleg * (s->nstokes == 3 ? 4 : 1), 0.0);
+    // AtmosphereGridStorageFull::set_zero zeroes f (grid_storage.h:319-329): the storage is unscaled again
+    s->applied_f_order = 0;
+    s->f.clear();
+    s->d_f.clear();
     for (auto& kv : s->mappings) {
         DerivativeMapping tmp{&kv.second};
         sk_deriv_mapping_set_zero(&tmp);
@@ -632,7 +511,8 @@ int sk_atmosphere_apply_delta_m_scaling(Atmosphere* a, int order) {
     if (s->nstokes != 1) return fail(-2, "B200 DO path supports num_stokes = 1 only");
     if (order < 0) return fail(-2, "delta-M order must be non-negative");
     if (order >= s->nleg) return 0;  // upstream warns and leaves the atmosphere unscaled
-    if (s->applied_f_order > 0) return fail(-2, "delta-M scaling has already been applied to this storage");
+    // like upstream, every call rescales whatever the storage holds now: the caller refills the arrays
+    // (sk_atmosphere_storage_set_zero + fill) before each application (src/sasktran2/atmosphere.py:655-662, 846-856)
     if (!s->ssa || !s->ext || !s->leg) return fail(-1, "atmosphere storage arrays are null");
     sk_atmosphere_storage_finalize_scattering_derivatives(s);
     const size_t nloc = s->nloc, nw = s->nwavel, nleg = s->nleg;
@@ -855,6 +735,19 @@ Engine* sk_engine_create(Config* config, Geometry1D* geometry, ViewingGeometry* 
     }
     if (config->solar_refraction) {
         fail(-2, "B200 DO path: solar refraction is not supported");
+        return nullptr;
+    }
+    if (!viewing->other_rays.empty()) {
+        fail(-2, "B200 DO path: only GroundViewingSolar rays are supported (tangent-altitude / observer-location rays need "
+                 "the spherical source-table path)");
+        return nullptr;
+    }
+    if (viewing->num_flux_observers > 0) {
+        fail(-2, "B200 DO path: flux observers are not supported");
+        return nullptr;
+    }
+    if (config->los_refraction || config->multiple_scatter_refraction) {
+        fail(-2, "B200 DO path: refraction is not supported");
         return nullptr;
     }
     // apply_delta_scaling is acted on by the caller (src/sasktran2/atmosphere.py:846-856 calls

@@ -1381,25 +1381,22 @@ static void launch_bvp_n(const ChunkView& V, cudaStream_t s) {
     if (N == 8 && bvp_use_2d()) {
         using C = BvpCfg3<N == 8 ? N : 8, 1>;
         const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;
+        if (attr_set.first()) {
             cudaFuncSetAttribute(k_bvp_v3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
         }
         k_bvp_v3<8><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
     } else if constexpr (3 * N <= 32) {
         using C = BvpCfg2<N, 1>;
         const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;
+        if (attr_set.first()) {
             cudaFuncSetAttribute(k_bvp_v2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
         }
         if (bvp_blocked()) {
-            static bool attr4_set = false;
-            if (!attr4_set) {
+            static DeviceOnce attr4_set;
+            if (attr4_set.first()) {
                 cudaFuncSetAttribute(k_bvp_v2<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr4_set = true;
             }
             k_bvp_v2<N, true><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
         } else {
@@ -1408,10 +1405,9 @@ static void launch_bvp_n(const ChunkView& V, cudaStream_t s) {
     } else {
         using C = BvpCfg<N, 1>;
         const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;
+        if (attr_set.first()) {
             cudaFuncSetAttribute(k_bvp<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
         }
         k_bvp<N><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
     }
@@ -1422,30 +1418,27 @@ static void launch_adj_batch(const ChunkView& V, int los0, int nbatch, cudaStrea
     if (N == 8 && bvp_use_2d()) {
         using C = BvpCfg3<N == 8 ? N : 8, NRHS>;
         const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;
+        if (attr_set.first()) {
             cudaFuncSetAttribute(k_bvp_adjoint_v3<8, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
         }
         k_bvp_adjoint_v3<8, NRHS><<<(unsigned)((ngroups + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK),
                                     C::WARPS_PER_BLOCK * 32, smem, s>>>(V, los0, nbatch);
     } else if constexpr (3 * N <= 32) {
         using C = BvpCfg2<N, NRHS>;
         const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;
+        if (attr_set.first()) {
             cudaFuncSetAttribute(k_bvp_adjoint_v2<N, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
         }
         k_bvp_adjoint_v2<N, NRHS><<<(unsigned)((ngroups + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK),
                                     C::WARPS_PER_BLOCK * 32, smem, s>>>(V, los0, nbatch);
     } else {
         using C = BvpCfg<N, NRHS>;
         const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;
+        if (attr_set.first()) {
             cudaFuncSetAttribute(k_bvp_adjoint<N, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
         }
         k_bvp_adjoint<N, NRHS><<<(unsigned)((ngroups + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK),
                                  C::WARPS_PER_BLOCK * 32, smem, s>>>(V, los0, nbatch);
@@ -1466,10 +1459,9 @@ static void launch_bvp_adjoint_n(const ChunkView& V, cudaStream_t s) {
             const long long ngroups = (long long)V.nw * V.M * nbatch;
             const int gpb = C::WARPS_PER_BLOCK * gpw;
             const size_t smem = (size_t)gpb * C::smem_doubles_per_group(glt) * sizeof(double);
-            static bool attr_set = false;
-            if (!attr_set) {
+            static DeviceOnce attr_set;
+            if (attr_set.first()) {
                 cudaFuncSetAttribute(k_bvp_tsolve<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-                attr_set = true;
             }
             k_bvp_tsolve<N><<<(unsigned)((ngroups + gpb - 1) / gpb), C::WARPS_PER_BLOCK * 32, smem, s>>>(V, glt, gpw, nbatch);
             return;

@@ -39,6 +39,7 @@ DeviceEngine::DeviceEngine(const EngineOptions& opt, const HostPlan& plan) : m_o
     if (e != cudaSuccess || ndev == 0)
         throw std::runtime_error("sasktran2_b200: no CUDA device available (there is no CPU fallback)");
     if (opt.device >= 0) CUDA_OK(cudaSetDevice(opt.device));
+    CUDA_OK(cudaGetDevice(&m_device));
     if (!nstr_supported(plan.nstr))
         throw std::runtime_error("sasktran2_b200: num_streams must be one of 2, 4, 8, 16, 32");
     if (m_opt.workspace_gb <= 0.0) {
@@ -129,6 +130,8 @@ void DeviceEngine::free_wf_inputs() {
 }
 
 DeviceEngine::~DeviceEngine() {
+    cudaSetDevice(m_device);
+    for (auto ev : m_marks) cudaEventDestroy(ev);
     free_wf_inputs();
     free_inputs();
     free_workspace();
@@ -203,7 +206,9 @@ int DeviceEngine::chunk_wavelengths() const {
 }
 
 void DeviceEngine::ensure_workspace(int chunk) {
-    if (chunk <= m_ws_chunk && m_ws_wf == m_wf_on) return;
+    // the derivative arrays are sized by the number of scattering groups: an atmosphere with more groups than the
+    // workspace was built for needs a new one even when the chunk fits
+    if (chunk <= m_ws_chunk && m_ws_wf == m_wf_on && (!m_wf_on || m_ws_ngroups == m_ngroups)) return;
     free_workspace();
     const size_t N = m_plan.N, L = m_plan.L, nstr = m_plan.nstr, nlos = m_plan.nlos, M = m_mlist.size();
     const size_t c = chunk;
@@ -270,10 +275,12 @@ void DeviceEngine::ensure_workspace(int chunk) {
         V.wf_scratch = A("wf_scratch", c * nlos * 3 * (L + 1));
     }
     m_ws_wf = m_wf_on;
+    m_ws_ngroups = m_wf_on ? m_ngroups : 0;
     m_ws_chunk = chunk;
 }
 
 void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRequest* wf) {
+    CUDA_OK(cudaSetDevice(m_device));
     if (atm.nloc != m_plan.nloc) throw std::runtime_error("atmosphere and geometry grids differ in size");
     if (w0 < 0 || nw < 0 || w0 + nw > atm.nwavel) throw std::runtime_error("wavelength range out of bounds");
     const size_t nloc = atm.nloc;
@@ -408,6 +415,7 @@ void DeviceEngine::solve_staged() {
     for (int i = T_OPTICS; i < T_NSLOTS; ++i)
         if (i != T_D2H) m_ms[i] = 0.0;
     m_launches = 0;
+    CUDA_OK(cudaSetDevice(m_device));
     if (m_nw == 0 || m_plan.nlos == 0) return;
     const int chunk = chunk_wavelengths();
     ensure_workspace(chunk);
@@ -441,11 +449,16 @@ void DeviceEngine::solve_staged() {
     const size_t nloc = m_plan.nloc;
     struct Span { cudaEvent_t a, b; int slot; };
     // per-kernel timing: events are recorded around every launch; elapsed times are read after the final sync
+    // (the events live in m_marks and are reused by every solve: nothing to leak when a launch throws)
     std::vector<cudaEvent_t> evs;
     std::vector<int> slots;
     auto mark = [&]() {
-        cudaEvent_t ev;
-        CUDA_OK(cudaEventCreate(&ev));
+        if (evs.size() == m_marks.size()) {
+            cudaEvent_t ev;
+            CUDA_OK(cudaEventCreate(&ev));
+            m_marks.push_back(ev);
+        }
+        cudaEvent_t ev = m_marks[evs.size()];
         CUDA_OK(cudaEventRecord(ev, m_stream));
         evs.push_back(ev);
     };
@@ -529,7 +542,6 @@ void DeviceEngine::solve_staged() {
     float tot = 0;
     CUDA_OK(cudaEventElapsedTime(&tot, evs.front(), evs.back()));
     m_ms[T_TOTAL_KERNELS] = tot;
-    for (auto ev : evs) cudaEventDestroy(ev);
     unsigned int st = 0;
     CUDA_OK(cudaMemcpy(&st, d_status, sizeof(st), cudaMemcpyDeviceToHost));
     if (st & 1u) throw std::runtime_error("DO homogeneous solution: S- is not positive definite (invalid phase moments?)");
@@ -557,6 +569,7 @@ void DeviceEngine::copy_outputs(int w_begin, int w_end, double* radiance_host, c
 }
 
 void DeviceEngine::fetch(double* radiance_host) {
+    CUDA_OK(cudaSetDevice(m_device));
     CUDA_OK(cudaEventRecord(m_ev[2], m_stream));
     copy_outputs(m_early_done, m_nw, radiance_host, m_stream);   // everything, unless calculate() sent a part ahead
     CUDA_OK(cudaEventRecord(m_ev[3], m_stream));

@@ -107,6 +107,8 @@ class DeviceEngine {
     size_t ws_bytes(bool wf_on, int ngroups) const;
     void copy_outputs(int w_begin, int w_end, double* radiance_host, cudaStream_t s);
     cudaEvent_t m_ev[8] = {};
+    std::vector<cudaEvent_t> m_marks;   // per-kernel timing events, created once and reused by every solve
+    int m_device = 0;                   // every public method selects it first (engines on several GPUs per process)
     // geometry tables on device
     double *d_mu = nullptr, *d_wt = nullptr, *d_lp_mu = nullptr, *d_lp_csz = nullptr, *d_lp_los = nullptr;
     double* d_wf_tab = nullptr;  // per-order tables of the fast weighting-function kernel (Tables::wf_tab)
@@ -137,6 +139,7 @@ class DeviceEngine {
     std::vector<DevMapping> m_maps;
     std::vector<DevSurface> m_surfs;
     bool m_ws_wf = false;
+    int m_ws_ngroups = 0;     // scattering groups the workspace was sized for (lay_dbeta, wf_loc, wf_native)
     bool m_fast = false;      // register-resident layer solve (disco_fast*.cuh)
     // chunk workspace
     int m_ws_chunk = 0;

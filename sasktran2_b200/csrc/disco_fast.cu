@@ -35,10 +35,9 @@ static void launch_fast_n(const ChunkView& V, cudaStream_t s) {
     k_eig_setup<N><<<grid_t, 128, 0, s>>>(V);
     k_eig_jacobi<N><<<grid_t, 128, 0, s>>>(V);
     const size_t smem = (size_t)post_smem_doubles<N>(V.T.nlos) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         cudaFuncSetAttribute(k_layer_post<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
     }
     const long long nblk_p = (nq + PostCfg<N>::PPB - 1) / PostCfg<N>::PPB;
     const long long cap_p = 2LL * wf_fast_blocks_per_order((int)V.M);  // persistent blocks, three resident per SM
@@ -61,10 +60,9 @@ static void launch_wf_fast_ng(const ChunkView& V, cudaStream_t s) {
     using Cf = WfCfg<N, G>;
     const long long nq = (long long)V.nw * V.T.L;
     const size_t smem = (size_t)Cf::smem_doubles(V.T.nlos) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         cudaFuncSetAttribute(k_wf_layer_fast<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_set = true;
     }
     const dim3 grid((unsigned)((nq + Cf::PPB - 1) / Cf::PPB), (unsigned)V.M);
     k_wf_layer_fast<N, G><<<grid, 128, smem, s>>>(V);

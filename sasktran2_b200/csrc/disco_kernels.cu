@@ -292,10 +292,9 @@ void launch_wf_chain(const ChunkView& V, cudaStream_t s) {
     const long long n = (long long)V.nw * V.T.nlos;
     const size_t per_warp = (size_t)(3 * (V.T.L + 1) + V.T.nloc * (2 + V.ngroups) + 1) * sizeof(double);
     if (V.ngroups + 4 <= 8 && 4 * per_warp <= 200 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;
+        if (attr_set.first()) {
             cudaFuncSetAttribute(k_wf_chain_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
         }
         k_wf_chain_warp<<<(unsigned)((n + 3) / 4), 128, 4 * per_warp, s>>>(V, V.ngroups);
     } else {

@@ -8,6 +8,19 @@
 
 namespace disco {
 
+// cudaFuncSetAttribute is per device: one flag per (call site, device) instead of a process-wide bool
+struct DeviceOnce {
+    unsigned long long seen = 0;
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long bit = 1ull << (d & 63);
+        if (seen & bit) return false;
+        seen |= bit;
+        return true;
+    }
+};
+
 void launch_layer_optics(const ChunkView& V, cudaStream_t s);
 void launch_beam(const ChunkView& V, cudaStream_t s);
 void launch_layer_solve(const ChunkView& V, cudaStream_t s);

@@ -19,6 +19,96 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_library_exports_every_symbol_of_the_reference_c_api():
+    """Link-completeness: every `sk_*` function of the reference's cpp/include/c_api/*.h (list extracted by
+    tests/golden/make_c_api_symbols.py) resolves in libsasktran2_b200.so, so the Rust layer's bindgen prototypes
+    (rust/sasktran2-rs/src/bindings/*.rs) link against it in place of libcsasktran2."""
+    names = (ROOT / "tests" / "golden" / "c_api_symbols.txt").read_text().split()
+    assert len(names) >= 205
+    lib = ctypes.CDLL(str(ROOT / "sasktran2_b200" / "libsasktran2_b200.so"))
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_off_path_entry_points_fail_with_the_reference_codes():
+    lib = ctypes.CDLL(str(ROOT / "sasktran2_b200" / "libsasktran2_b200.so"))
+    lib.sk_b200_last_error.restype = ctypes.c_char_p
+    lib.sk_geodetic_create.restype = ctypes.c_void_p
+    lib.sk_geodetic_create.argtypes = [ctypes.c_double, ctypes.c_double]
+    assert lib.sk_geodetic_create(6378137.0, 1 / 298.257) is None
+    assert b"Geodetic" in lib.sk_b200_last_error()
+    assert lib.sk_engine_calculate_vjp(None, None, None) == -3
+    # stored config options round-trip
+    lib.sk_config_create.restype = ctypes.c_void_p
+    cfg = ctypes.c_void_p(lib.sk_config_create())
+    v = ctypes.c_int(-7)
+    assert lib.sk_config_get_num_hr_incoming(cfg, ctypes.byref(v)) == 0 and v.value == 110
+    assert lib.sk_config_set_stokes_basis(cfg, 2) == 0
+    assert lib.sk_config_get_stokes_basis(cfg, ctypes.byref(v)) == 0 and v.value == 2
+    n = ctypes.c_int(0)
+    assert lib.sk_config_get_num_flux_types(cfg, ctypes.byref(n)) == 0 and n.value == 2
+    d = ctypes.c_double(0)
+    lib.sk_config_set_successive_orders_damping.argtypes = [ctypes.c_void_p, ctypes.c_double]
+    assert lib.sk_config_set_successive_orders_damping(cfg, 0.5) == 0
+    assert lib.sk_config_get_successive_orders_damping(cfg, ctypes.byref(d)) == 0 and d.value == 0.5
+    lib.sk_config_destroy(cfg)
+
+
+def test_sk_lapack_dgesv_matches_numpy():
+    lib = ctypes.CDLL(str(ROOT / "sasktran2_b200" / "libsasktran2_b200.so"))
+    rng = np.random.default_rng(3)
+    n, nrhs = 7, 3
+    a = np.asfortranarray(rng.standard_normal((n, n)))
+    b = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    x_ref = np.linalg.solve(a, b)
+    ipiv = np.zeros(n, dtype=np.int64)
+    ll = ctypes.c_longlong
+    lib.sk_lapack_dgesv.restype = ll
+    lib.sk_lapack_dgesv.argtypes = [ll, ll, ctypes.c_void_p, ll, ctypes.c_void_p, ctypes.c_void_p, ll]
+    assert lib.sk_lapack_dgesv(n, nrhs, a.ctypes.data, n, ipiv.ctypes.data, b.ctypes.data, n) == 0
+    np.testing.assert_allclose(b, x_ref, rtol=1e-10, atol=1e-12)
+    sing = np.zeros((3, 3), order="F")
+    assert lib.sk_lapack_dgesv(3, 1, sing.ctypes.data, 3, ipiv.ctypes.data, b.ctypes.data, n) == 1
+
+
+def test_atmosphere_revision_and_delta_m_reapply():
+    """sk_atmosphere_mark_changed / get_revision (cpp/c_api/atmosphere.cpp:473-507); delta-M scaling can be applied
+    again after sk_atmosphere_storage_set_zero + refill, as upstream does on every internal_object()."""
+    import sasktran2_b200 as sk
+    from sasktran2_b200 import _lib
+
+    cfg = sk.Config()
+    cfg.num_streams = 4
+    cfg.delta_m_scaling = True
+    geo = sk.Geometry1D(0.6, 0.0, 6372000.0, np.linspace(0, 5e4, 6), sk.InterpolationMethod.LinearInterpolation,
+                        sk.GeometryType.PlaneParallel)
+    atm = sk.Atmosphere(geo, cfg, numwavel=2, num_legendre=8, calculate_derivatives=False)
+
+    def fill():
+        atm.storage.ssa[:] = 0.8
+        atm.storage.total_extinction[:] = 1e-5
+        atm.storage.leg_coeff[:] = (0.7 ** np.arange(8) * (2 * np.arange(8) + 1))[:, None, None]
+
+    fill()
+    h = atm.internal_object()
+    scaled = atm.storage.total_extinction.copy()
+    assert np.all(scaled < 1e-5)
+    rev = ctypes.c_ulonglong(99)
+    assert _lib.lib().sk_atmosphere_get_revision(h, ctypes.byref(rev)) == 0 and rev.value == 0
+    assert _lib.lib().sk_atmosphere_mark_changed(h) == 0
+    assert _lib.lib().sk_atmosphere_get_revision(h, ctypes.byref(rev)) == 0 and rev.value == 1
+    atm.internal_object()  # untouched: no second scaling
+    np.testing.assert_array_equal(atm.storage.total_extinction, scaled)
+    fill()                 # refilled without zero_storage(): refused instead of silently mixing scaled / unscaled
+    with pytest.raises(sk.SasktranError):
+        atm.internal_object()
+    atm.zero_storage()
+    assert np.all(atm.storage.ssa == 0)
+    fill()
+    atm.internal_object()
+    np.testing.assert_array_equal(atm.storage.total_extinction, scaled)
+
+
 def test_config_defaults_and_roundtrip():
     import sasktran2_b200 as sk
 

@@ -97,6 +97,67 @@ inline Dual sqrt(const Dual& a) {
 }
 inline double val(double x) { return x; }
 inline double val(const Dual& x) { return x.v; }
+
+// Fixed-size dual number: the K "layer-local" derivative lanes of the reverse-mode linearisation (ReverseSolver
+// below).  Same member names as Dual so that the layer routines are shared.
+template <int K>
+struct FDual {
+    double v;
+    double d[K];
+    FDual() : v(0.0) {
+        for (int i = 0; i < K; ++i) d[i] = 0.0;
+    }
+    FDual(double x) : v(x) {  // NOLINT implicit on purpose
+        for (int i = 0; i < K; ++i) d[i] = 0.0;
+    }
+    FDual& operator+=(const FDual& o) {
+        v += o.v;
+        for (int i = 0; i < K; ++i) d[i] += o.d[i];
+        return *this;
+    }
+    FDual& operator-=(const FDual& o) {
+        v -= o.v;
+        for (int i = 0; i < K; ++i) d[i] -= o.d[i];
+        return *this;
+    }
+    FDual& operator*=(const FDual& o) {
+        for (int i = 0; i < K; ++i) d[i] = d[i] * o.v + v * o.d[i];
+        v *= o.v;
+        return *this;
+    }
+    FDual& operator/=(const FDual& o) {
+        const double q = v / o.v;
+        for (int i = 0; i < K; ++i) d[i] = (d[i] - q * o.d[i]) / o.v;
+        v = q;
+        return *this;
+    }
+};
+template <int K> inline FDual<K> operator+(FDual<K> a, const FDual<K>& b) { return a += b; }
+template <int K> inline FDual<K> operator-(FDual<K> a, const FDual<K>& b) { return a -= b; }
+template <int K> inline FDual<K> operator*(FDual<K> a, const FDual<K>& b) { return a *= b; }
+template <int K> inline FDual<K> operator/(FDual<K> a, const FDual<K>& b) { return a /= b; }
+template <int K> inline FDual<K> operator-(FDual<K> a) {
+    a.v = -a.v;
+    for (int i = 0; i < K; ++i) a.d[i] = -a.d[i];
+    return a;
+}
+template <int K> inline FDual<K> exp(const FDual<K>& a) {
+    FDual<K> r;
+    r.v = std::exp(a.v);
+    for (int i = 0; i < K; ++i) r.d[i] = r.v * a.d[i];
+    return r;
+}
+template <int K> inline FDual<K> sqrt(const FDual<K>& a) {
+    FDual<K> r;
+    r.v = std::sqrt(a.v);
+    for (int i = 0; i < K; ++i) r.d[i] = 0.5 * a.d[i] / r.v;
+    return r;
+}
+template <int K> inline double val(const FDual<K>& x) { return x.v; }
+// number of derivative lanes carried by a value
+inline int ndual(const double&) { return 0; }
+inline int ndual(const Dual& x) { return (int)x.d.size(); }
+template <int K> inline int ndual(const FDual<K>&) { return K; }
 inline double exp(double x) { return std::exp(x); }
 inline double sqrt(double x) { return std::sqrt(x); }
 
@@ -132,6 +193,13 @@ inline Dual phi(const Dual& x) {
     r.v = phi_value(x.v);
     const double dp = phi_deriv(x.v);
     for (size_t i = 0; i < x.d.size(); ++i) r.d[i] = dp * x.d[i];
+    return r;
+}
+template <int K> inline FDual<K> phi(const FDual<K>& x) {
+    FDual<K> r;
+    r.v = phi_value(x.v);
+    const double dp = phi_deriv(x.v);
+    for (int i = 0; i < K; ++i) r.d[i] = dp * x.d[i];
     return r;
 }
 // psi(a; k1, k2) with e1 = exp(-a k1), e2 = exp(-a k2) supplied by the caller
@@ -279,9 +347,64 @@ inline void interp_weights(const std::vector<double>& g, int interp, double x, i
     }
 }
 
+// ---- chapman factors by ray tracing: GeometryLayerArray::calculate_chapman_factors_raytracer
+//      (sktran_do_geometrylayerarray.cpp:122-186) over SphericalShellRayTracer::trace_ray for an observer inside the
+//      atmosphere looking up (cpp/lib/raytracing/spherical_shell.cpp:6-76, 424-455: complete shells from the top of
+//      the atmosphere down to the first grid altitude above the observer, then one partial shell) with straight-line
+//      layer distances (:193-215) and the pseudo-spherical coordinates of cpp/lib/geometry/geometry.cpp:8-35, 155-160
+//      (observer on the z axis at the layer floor, look vector = sun unit vector).  A row of -1 flags "the sun ray
+//      hits the ground" (cos_sza <= 0 is not traced here: the reference's looking-down branches are not restated).
+struct Vec3 {
+    double x, y, z;
+    Vec3 operator+(const Vec3& o) const { return {x + o.x, y + o.y, z + o.z}; }
+    Vec3 operator*(double f) const { return {x * f, y * f, z * f}; }
+    double dot(const Vec3& o) const { return x * o.x + y * o.y + z * o.z; }
+    double norm() const { return std::sqrt(x * x + y * y + z * z); }
+};
+inline void chapman_raytraced(const std::vector<double>& alt, const std::vector<double>& floor_h,
+                              const std::vector<double>& ceil_h, double cos_sza, double earth_radius,
+                              std::vector<double>& chapman) {
+    const int L = (int)floor_h.size(), ng = (int)alt.size();
+    chapman.assign(size_t(L) * L, 0.0);
+    if (!(cos_sza > 0)) throw std::runtime_error("chapman_raytraced: cos_sza must be positive");
+    const Vec3 sun{std::sqrt(1 - cos_sza * cos_sza), 0.0, cos_sza};  // geometry.cpp:19-22 with saa = 0
+    struct Shell { double r_entrance, r_exit; };
+    for (int p = 0; p < L; ++p) {
+        const Vec3 obs{0.0, 0.0, floor_h[p] + earth_radius};              // solar_coordinate_vector, geometry.cpp:157-160
+        const double robs = obs.norm();
+        const double cosv = (obs * (1.0 / robs)).dot(sun);               // ViewingRay::cos_viewing
+        const double rt = robs * std::sqrt(std::max(0.0, 1 - cosv * cosv));  // spherical_shell.cpp:17-19
+        // trace_ray_observer_inside_looking_up (:424-455)
+        const int start_index = int(std::upper_bound(alt.begin(), alt.end(), robs - earth_radius) - alt.begin());
+        std::vector<Shell> layers;
+        for (int i = ng - 1; i != start_index; --i)                       // complete_layer(exit i, ViewingDirection::up = -1), :254-276
+            layers.push_back({alt[i - 1] + earth_radius, alt[i] + earth_radius});
+        layers.push_back({robs, alt[start_index] + earth_radius});       // partial_layer (:278-298)
+        // finalize_ray_geometry (:85-215): from the observer outwards, straight ray
+        Vec3 entrance = obs;
+        for (int i = 0; i < (int)layers.size(); ++i) {
+            const Shell& ly = layers[layers.size() - i - 1];
+            const double dist = std::abs(std::sqrt(std::fmax(ly.r_entrance * ly.r_entrance - rt * rt, 0.0)) -
+                                         std::sqrt(std::fmax(ly.r_exit * ly.r_exit - rt * rt, 0.0)));
+            const Vec3 exitp = entrance + sun * dist;
+            const double average_altitude = (entrance.norm() + exitp.norm()) / 2.0 - earth_radius;
+            int q = 0;
+            for (; q < L; ++q)
+                if (average_altitude >= floor_h[q] && average_altitude <= ceil_h[q]) break;
+            if (q == L) q = L - 1;
+            chapman[size_t(p) * L + q] += dist * 1.0 / (ceil_h[q] - floor_h[q]);
+            entrance = exitp;
+        }
+    }
+}
+
 // geotype: 0 plane-parallel, 1 pseudo-spherical.  sktran_do_geometrylayerarray.cpp:8-119.
-// Pseudo-spherical chapman factors use the straight-line formula (:100-118), which equals the traced
-// result (:122-186) for an unrefracted sun above the horizon.
+// Pseudo-spherical chapman factors: ray traced like the reference (chapman_raytraced above) unless
+// chapman_straight_line_ref() is set, which selects the closed formula of calculate_chapman_factors (:69-119).
+inline int& chapman_straight_line_ref() {
+    static int flag = 0;
+    return flag;
+}
 inline Plan make_plan(int nstr, const std::vector<double>& alt, int interp, int geotype, double cos_sza,
                       double earth_radius, const std::vector<double>& los_cos_vza,
                       const std::vector<double>& los_rel_az) {
@@ -325,6 +448,8 @@ inline Plan make_plan(int nstr, const std::vector<double>& alt, int interp, int 
     if (geotype == 0) {  // :57-61
         for (int p = 0; p < P.L; ++p)
             for (int q = 0; q <= p; ++q) P.chapman[size_t(p) * P.L + q] = 1 / cos_sza;
+    } else if (!chapman_straight_line_ref()) {
+        chapman_raytraced(alt, P.floor_h, P.ceil_h, cos_sza, earth_radius, P.chapman);
     } else {  // :69-119
         double sinthetasq = 1 - cos_sza * cos_sza;
         for (int p = 0; p < P.L; ++p) {
@@ -504,18 +629,21 @@ struct Layers {
 // (sktran_do_types.h:233-251): per layer [scat g=0..G-1][od][ssa]; last layer + [albedo].
 struct Lanes {
     int L = 0, G = 0;
+    bool local = false;  // layer-local lanes of ReverseSolver: the same G + 2 lane numbers for every layer
     int per_layer() const { return G + 2; }
     int total() const { return L * (G + 2) + 1; }
-    int scat(int p, int g) const { return p * (G + 2) + g; }
-    int od(int p) const { return p * (G + 2) + G; }
-    int ssa(int p) const { return p * (G + 2) + G + 1; }
+    int scat(int p, int g) const { return local ? g : p * (G + 2) + g; }
+    int od(int p) const { return local ? G : p * (G + 2) + G; }
+    int ssa(int p) const { return local ? G + 1 : p * (G + 2) + G + 1; }
     int albedo() const { return L * (G + 2); }
 };
 
 inline void seed(double&, int) {}
 inline void seed(Dual& x, int lane) { x.d[lane] = 1.0; }
+template <int K> inline void seed(FDual<K>& x, int lane) { x.d[lane] = 1.0; }
 inline void seed_dir(double&, int, double) {}
 inline void seed_dir(Dual& x, int lane, double v) { x.d[lane] = v; }
+template <int K> inline void seed_dir(FDual<K>& x, int lane, double v) { x.d[lane] = v; }
 
 template <class T>
 struct Solver {
@@ -668,8 +796,9 @@ struct Solver {
             }
     }
     void eig_derivatives(const std::vector<double>&, std::vector<double>&, std::vector<double>&) const {}
-    void eig_derivatives(const std::vector<Dual>& E, std::vector<Dual>& X, std::vector<Dual>& k) const {
-        const int N = P.N, nd = nd_ref();
+    template <class D>
+    void eig_derivatives(const std::vector<D>& E, std::vector<D>& X, std::vector<D>& k) const {
+        const int N = P.N, nd = ndual(E[0]);
         if (nd == 0) return;
         std::vector<double> lhs((N + 1) * (N + 1)), rhs(N + 1);
         DenseLU lu;
@@ -765,10 +894,11 @@ struct Solver {
         }
     }
     static bool is_zero(double x) { return x == 0.0; }
-    static bool is_zero(const Dual& x) {
+    template <class D>
+    static bool is_zero(const D& x) {
         if (x.v != 0.0) return false;
-        for (double t : x.d)
-            if (t != 0.0) return false;
+        for (int i = 0; i < ndual(x); ++i)
+            if (x.d[i] != 0.0) return false;
         return true;
     }
 
@@ -858,7 +988,8 @@ struct Solver {
         }
     }
     static double S_abs(double x) { return std::abs(x); }
-    static Dual S_abs(const Dual& x) { return x.v >= 0 ? x : -x; }
+    template <class D>
+    static D S_abs(const D& x) { return x.v >= 0 ? x : -x; }
     template <class E>
     void bvp_derivs(const std::vector<E>&, const std::vector<double>&, const BandLU&, const std::vector<double>&,
                     std::vector<double>&) const {}
@@ -890,105 +1021,125 @@ struct Solver {
     // ---- post-processing for one (m, LOS): computeReflectedIntensities (sktran_do_layerarray.cpp:5-288),
     //      integrate_source / h_plus / h_minus / E (sktran_do_opticallayer.cpp:94-555, 785-938), upward
     //      recursion (do_source_planeparallel.cpp:69-146).  Observer above the top of the atmosphere.
+    // Ground-leaving radiance of order m toward any line of sight (Lambertian: m = 0 only).  gL / gM (optional):
+    // its partial derivatives w.r.t. the bottom layer's L_q, M_q at fixed layer quantities.
+    T ground_term(int m, const T& trans_bottom, const T& od_last, const T& albedo, const LayerSolution<T>& B,
+                  bool include_ss, double* gL = nullptr, double* gM = nullptr) const {
+        const int N = P.N;
+        if (gL)
+            for (int q = 0; q < N; ++q) gL[q] = gM[q] = 0.0;
+        if (m != 0) return T(0.0);  // Lambertian: max_azimuthal_order == 1
+        T diffuse(0.0);
+        for (int i = 0; i < N; ++i) {
+            T sc = B.Gpb[i];
+            double factor = 2.0 * P.mu[i] * P.wt[i];
+            for (int q = 0; q < N; ++q) {
+                T th = exp(-S_abs(B.k[q]) * od_last);
+                sc += B.Lc[q] * B.Wp[i + q * N] * th;
+                sc += B.Mc[q] * B.Wm[i + q * N];
+                if (gL) {
+                    gL[q] += factor * val(albedo) * val(B.Wp[i + q * N]) * val(th);
+                    gM[q] += factor * val(albedo) * val(B.Wm[i + q * N]);
+                }
+            }
+            diffuse += T(factor) * sc * albedo;
+        }
+        if (include_ss) {
+            T direct = T(P.csz / PI) * trans_bottom * albedo;
+            return direct + diffuse;
+        }
+        return diffuse;
+    }
+    // Source of layer p toward line of sight j for order m, J + V + Q E (full layer, x = 0).  wL / wM (optional): its
+    // partial derivatives w.r.t. L_i, M_i at fixed layer quantities (Y+ h+ and Y- h-).
+    T layer_source(int m, int j, int p, const Layers<T>& Ly, const LayerSolution<T>& S, bool include_ss,
+                   double* wL = nullptr, double* wM = nullptr) const {
+        const int N = P.N, nstr = P.nstr;
+        const double mu = P.los_mu[j];
+        const T& od = Ly.od[p];
+        const T& s = Ly.secant[p];
+        const T& t = Ly.trans[p];
+        // scat_phase_f (sktran_do_lpproduct.h:265-337); note the swapped plus/minus arguments at
+        // sktran_do_opticallayer.cpp:128-130: "plus" carries the (-1)^(l-m) factor.
+        std::vector<T> lps_plus(N), lps_minus(N);
+        for (int q = 0; q < N; ++q) {
+            T a(0.0), bneg(0.0);
+            for (int l = m; l < nstr; ++l) {
+                double pp = P.LPlos(j, m, l) * P.LPmu(m, q, l);
+                a += Ly.beta[p][l] * T(pp);
+                bneg += Ly.beta[p][l] * T(((l - m) % 2 != 0) ? -pp : pp);
+            }
+            lps_minus[q] = a * T(0.5 * P.wt[q]) * Ly.ssa[p];
+            lps_plus[q] = bneg * T(0.5 * P.wt[q]) * Ly.ssa[p];
+        }
+        T Q(0.0);
+        if (include_ss) {
+            T acc(0.0);
+            for (int l = m; l < nstr; ++l) {
+                double pp = P.LPlos(j, m, l) * P.LPcsz(m, l);
+                acc += Ly.beta[p][l] * T(((l - m) % 2 != 0) ? -pp : pp);
+            }
+            double factor = (2.0 - (m == 0 ? 1.0 : 0.0)) * (1.0 / (4.0 * PI));
+            Q = acc * T(factor) * Ly.ssa[p];
+        }
+        // E (x = 0)
+        T e2s = exp(-od * s) * exp(-od / T(mu));
+        T E = t / (T(1.0) + T(mu) * s) * (T(1.0) - e2s);
+        T expfactor = exp(-od * s);
+        T J(0.0), V(0.0);
+        for (int i = 0; i < N; ++i) {
+            T Yp(0.0), Ym(0.0);
+            for (int q = 0; q < N; ++q) {
+                Yp += lps_plus[q] * S.Wp[q + i * N] + lps_minus[q] * S.Wm[q + i * N];
+                Ym += lps_plus[q] * S.Wm[q + i * N] + lps_minus[q] * S.Wp[q + i * N];
+            }
+            const T& k = S.k[i];
+            T hp, hm;
+            {
+                T den = T(1.0) + T(mu) * k;
+                if (std::abs(val(den)) > 0.0001) {
+                    T e2 = exp(-od * k) * exp(-od / T(mu));
+                    hp = (T(1.0) - e2) / den;
+                } else {
+                    hp = od / T(mu) * (T(1.0) - od * (k + T(1.0 / mu)));
+                }
+            }
+            {
+                T den = T(1.0) - T(mu) * k;
+                if (std::abs(val(den)) > 0.0001 && stable_multipliers_ref()) {
+                    hm = od / T(mu) * psi(od, k, T(1.0 / mu), exp(-k * od), exp(-od / T(mu)));
+                } else if (std::abs(val(den)) > 0.0001) {
+                    T e1 = exp(-k * od);
+                    T e2 = exp(-od / T(mu));
+                    hm = (e1 - e2) / den;
+                } else {
+                    T e1 = exp(-k * od);
+                    hm = e1 * od / T(mu) * (T(1.0) - od * (k - T(1.0 / mu)));
+                }
+            }
+            J += Yp * hp * S.Lc[i];
+            J += Ym * hm * S.Mc[i];
+            if (wL) {
+                wL[i] = val(Yp) * val(hp);
+                wM[i] = val(Ym) * val(hm);
+            }
+            T Dp = (-t * expfactor * hm + E) / (s + k);
+            T Dm = stable_multipliers_ref()
+                       ? t * (T(mu) * hp - od * exp(-od / T(mu)) * psi(od, k, s, exp(-k * od), expfactor)) /
+                             (T(1.0) + T(mu) * s)
+                       : (t * hp - E) / (s - k);
+            V += S.Ap[i] * Yp * Dm + S.Am[i] * Ym * Dp;
+        }
+        return J + V + Q * E;
+    }
     T los_component(int m, int j, const Layers<T>& Ly, const T& albedo, const std::vector<LayerSolution<T>>& sol,
                     bool include_ss) const {
-        const int N = P.N, L = P.L, nstr = P.nstr;
+        const int L = P.L;
         const double mu = P.los_mu[j];
-        T I(0.0);
-        if (m == 0) {  // Lambertian: max_azimuthal_order == 1
-            const auto& B = sol[L - 1];
-            T diffuse(0.0);
-            for (int i = 0; i < N; ++i) {
-                T sc = B.Gpb[i];
-                for (int q = 0; q < N; ++q) {
-                    T th = exp(-S_abs(B.k[q]) * Ly.od[L - 1]);
-                    sc += B.Lc[q] * B.Wp[i + q * N] * th;
-                    sc += B.Mc[q] * B.Wm[i + q * N];
-                }
-                double factor = 2.0 * P.mu[i] * P.wt[i];
-                diffuse += T(factor) * sc * albedo;
-            }
-            if (include_ss) {
-                T direct = T(P.csz / PI) * Ly.trans[L] * albedo;
-                I = direct + diffuse;
-            } else {
-                I = diffuse;
-            }
-        }
+        T I = ground_term(m, Ly.trans[L], Ly.od[L - 1], albedo, sol[L - 1], include_ss);
         for (int p = L - 1; p >= 0; --p) {
-            const auto& S = sol[p];
-            const T& od = Ly.od[p];
-            const T& s = Ly.secant[p];
-            const T& t = Ly.trans[p];
-            I = I * exp(-od / T(mu));
-            // scat_phase_f (sktran_do_lpproduct.h:265-337); note the swapped plus/minus arguments at
-            // sktran_do_opticallayer.cpp:128-130: "plus" carries the (-1)^(l-m) factor.
-            std::vector<T> lps_plus(N), lps_minus(N);
-            for (int q = 0; q < N; ++q) {
-                T a(0.0), bneg(0.0);
-                for (int l = m; l < nstr; ++l) {
-                    double pp = P.LPlos(j, m, l) * P.LPmu(m, q, l);
-                    a += Ly.beta[p][l] * T(pp);
-                    bneg += Ly.beta[p][l] * T(((l - m) % 2 != 0) ? -pp : pp);
-                }
-                lps_minus[q] = a * T(0.5 * P.wt[q]) * Ly.ssa[p];
-                lps_plus[q] = bneg * T(0.5 * P.wt[q]) * Ly.ssa[p];
-            }
-            T Q(0.0);
-            if (include_ss) {
-                T acc(0.0);
-                for (int l = m; l < nstr; ++l) {
-                    double pp = P.LPlos(j, m, l) * P.LPcsz(m, l);
-                    acc += Ly.beta[p][l] * T(((l - m) % 2 != 0) ? -pp : pp);
-                }
-                double factor = (2.0 - (m == 0 ? 1.0 : 0.0)) * (1.0 / (4.0 * PI));
-                Q = acc * T(factor) * Ly.ssa[p];
-            }
-            // E (x = 0)
-            T e2s = exp(-od * s) * exp(-od / T(mu));
-            T E = t / (T(1.0) + T(mu) * s) * (T(1.0) - e2s);
-            T expfactor = exp(-od * s);
-            T J(0.0), V(0.0);
-            for (int i = 0; i < N; ++i) {
-                T Yp(0.0), Ym(0.0);
-                for (int q = 0; q < N; ++q) {
-                    Yp += lps_plus[q] * S.Wp[q + i * N] + lps_minus[q] * S.Wm[q + i * N];
-                    Ym += lps_plus[q] * S.Wm[q + i * N] + lps_minus[q] * S.Wp[q + i * N];
-                }
-                const T& k = S.k[i];
-                T hp, hm;
-                {
-                    T den = T(1.0) + T(mu) * k;
-                    if (std::abs(val(den)) > 0.0001) {
-                        T e2 = exp(-od * k) * exp(-od / T(mu));
-                        hp = (T(1.0) - e2) / den;
-                    } else {
-                        hp = od / T(mu) * (T(1.0) - od * (k + T(1.0 / mu)));
-                    }
-                }
-                {
-                    T den = T(1.0) - T(mu) * k;
-                    if (std::abs(val(den)) > 0.0001 && stable_multipliers_ref()) {
-                        hm = od / T(mu) * psi(od, k, T(1.0 / mu), exp(-k * od), exp(-od / T(mu)));
-                    } else if (std::abs(val(den)) > 0.0001) {
-                        T e1 = exp(-k * od);
-                        T e2 = exp(-od / T(mu));
-                        hm = (e1 - e2) / den;
-                    } else {
-                        T e1 = exp(-k * od);
-                        hm = e1 * od / T(mu) * (T(1.0) - od * (k - T(1.0 / mu)));
-                    }
-                }
-                J += Yp * hp * S.Lc[i];
-                J += Ym * hm * S.Mc[i];
-                T Dp = (-t * expfactor * hm + E) / (s + k);
-                T Dm = stable_multipliers_ref()
-                           ? t * (T(mu) * hp - od * exp(-od / T(mu)) * psi(od, k, s, exp(-k * od), expfactor)) /
-                                 (T(1.0) + T(mu) * s)
-                           : (t * hp - E) / (s - k);
-                V += S.Ap[i] * Yp * Dm + S.Am[i] * Ym * Dp;
-            }
-            I += J + V + Q * E;
+            I = I * exp(-Ly.od[p] / T(mu));
+            I += layer_source(m, j, p, Ly, sol[p], include_ss);
         }
         return I;
     }
@@ -1025,6 +1176,219 @@ struct Solver {
     static void store_derivs(const Dual& x, double* out) {
         if (out)
             for (size_t i = 0; i < x.d.size(); ++i) out[i] = x.d[i];
+    }
+};
+
+
+// ---------------------------------------------------------------------------------------------------
+//  Reverse-mode linearisation (config.do_backprop = true): RTESolver::backprop, sktran_do_rte.cpp:1793-1895,
+//  with the reference's layer-sparse duals (LayerDual: a layer quantity carries derivatives w.r.t. that layer's own
+//  parameters only, sktran_do_types.h:233-330) instead of the dense forward-mode lanes of Solver<Dual>.
+//
+//  Per layer the K = G + 5 local lanes are [eps_g (scattering-group directions) | tau | omega | t (beam transmittance
+//  at the layer top) | s (average secant) | albedo (bottom layer only)].  Per (order, line of sight):
+//      I = sum_p A_p S_p(x; layer p) + A_L ground(x; layer L-1),      A_p = prod_{q<p} exp(-tau_q / mu)
+//      dI = (dI at fixed BVP coefficients x) + z^T (db - dA x),       A^T z = dI/dx        (dgbtrs 'T', :1812-1836)
+//  and the dependence of t_p, s_p on the optical depths of the other layers (m_trans_to_C+-, m_secant_to_C+-,
+//  :1844-1893) is the chain  t_p = F0 exp(-sum_q chapman[p-1][q] tau_q),  s_p = (slant_{p+1} - slant_p) / tau_p.
+//  Results are the same layer lanes as Solver<Dual> (checked against it by tests/test_oracle_wf.py).
+// ---------------------------------------------------------------------------------------------------
+template <int G>
+struct ReverseSolver {
+    static constexpr int K = G + 5;
+    static constexpr int iTau = G, iOm = G + 1, iT = G + 2, iS = G + 3, iAlb = G + 4;
+    using T = FDual<K>;
+    const Plan& P;
+    Solver<T> S;
+    ReverseSolver(const Plan& p, dgeev_fn f) : P(p), S(p, f) {}
+
+    struct Entry { int r, c, layer; T a; };
+    struct Rhs { int r, layer; T b; };
+
+    // radiance[nlos], dlane[nlos][L*(G+2)+1] in the lane order of `Lanes` (non-local)
+    void solve_wavelength(const WavelInputs& in, double* radiance, double* dlane, Layers<T>* layers_out = nullptr) {
+        const int L = P.L, N = P.N, nlos = P.nlos, n = 2 * N * L, kl = 3 * N - 1;
+        if ((in.d_leg ? in.ngroups : 0) != G) throw std::runtime_error("ReverseSolver: group count mismatch");
+        // layer optics with local lanes: scat(p, g) -> g, od -> iTau, ssa -> iOm
+        S.lanes.L = L;
+        S.lanes.G = G;
+        S.lanes.local = true;
+        Layers<T> Ly;
+        S.layer_optics(in, Ly);
+        // beam quantities become independent local variables (their cross-layer dependence is the chain at the end)
+        std::vector<double> tval(L + 1), sval(L);
+        for (int p = 0; p <= L; ++p) tval[p] = Ly.trans[p].v;
+        for (int p = 0; p < L; ++p) {
+            sval[p] = Ly.secant[p].v;
+            Ly.secant[p] = T(sval[p]);
+            Ly.secant[p].d[iS] = 1.0;
+            Ly.trans[p] = T(tval[p]);
+            Ly.trans[p].d[iT] = 1.0;
+        }
+        // bottom boundary in the bottom layer's lanes: t_L = t_{L-1} exp(-s_{L-1} tau_{L-1})
+        Ly.trans[L] = Ly.trans[L - 1] * exp(-Ly.secant[L - 1] * Ly.od[L - 1]);
+        T albedo(in.albedo);
+        albedo.d[iAlb] = 1.0;
+
+        const Lanes out_lanes{L, G, false};
+        const int nd = out_lanes.total();
+        std::vector<double> rad(nlos, 0.0);
+        std::vector<double> dloc(size_t(nlos) * L * K, 0.0);  // [los][layer][lane], summed over orders
+        std::vector<LayerSolution<T>> sol(L);
+        std::vector<Entry> ent;
+        std::vector<Rhs> rhs;
+        std::vector<double> bval(n), x(n), wvec(n), srcv(L), wL(N), wM(N), gL(N), gM(N), Acum(L + 1);
+        std::vector<T> src(L);
+        BandLU lu;
+        for (int m = 0; m < in.num_azimuth; ++m) {
+            for (int p = 0; p < L; ++p) {
+                S.homogeneous(m, Ly.ssa[p], Ly.beta[p], sol[p]);
+                S.particular(m, Ly.ssa[p], Ly.beta[p], Ly.od[p], Ly.secant[p], Ly.trans[p], sol[p]);
+            }
+            assemble(m, Ly, albedo, sol, ent, rhs);
+            lu.init(n, kl, kl);
+            for (const auto& e : ent) lu.at(e.r, e.c) = e.a.v;
+            if (lu.factor() != 0) throw std::runtime_error("BVP matrix singular");
+            std::fill(bval.begin(), bval.end(), 0.0);
+            for (const auto& r : rhs) bval[r.r] += r.b.v;
+            x = bval;
+            lu.solve(x.data());
+            for (int p = 0; p < L; ++p) {
+                sol[p].Lc.assign(N, T(0.0));
+                sol[p].Mc.assign(N, T(0.0));
+                for (int j = 0; j < N; ++j) {
+                    sol[p].Lc[j] = T(x[p * 2 * N + j]);       // constants: derivatives w.r.t. x go through z
+                    sol[p].Mc[j] = T(x[p * 2 * N + N + j]);
+                }
+            }
+            for (int j = 0; j < nlos; ++j) {
+                const double mu = P.los_mu[j], cosm = std::cos(m * P.los_az[j]);
+                double* dl = &dloc[size_t(j) * L * K];
+                Acum[0] = 1.0;
+                for (int p = 0; p < L; ++p) Acum[p + 1] = Acum[p] * std::exp(-Ly.od[p].v / mu);
+                double I = 0.0;
+                for (int p = 0; p < L; ++p) {
+                    src[p] = S.layer_source(m, j, p, Ly, sol[p], in.include_ss, wL.data(), wM.data());
+                    for (int i = 0; i < N; ++i) {
+                        wvec[p * 2 * N + i] = Acum[p] * wL[i];
+                        wvec[p * 2 * N + N + i] = Acum[p] * wM[i];
+                    }
+                    I += Acum[p] * src[p].v;
+                }
+                T gnd = S.ground_term(m, Ly.trans[L], Ly.od[L - 1], albedo, sol[L - 1], in.include_ss, gL.data(), gM.data());
+                for (int i = 0; i < N; ++i) {
+                    wvec[(L - 1) * 2 * N + i] += Acum[L] * gL[i];
+                    wvec[(L - 1) * 2 * N + N + i] += Acum[L] * gM[i];
+                }
+                I += Acum[L] * gnd.v;
+                rad[j] += I * cosm;
+                // derivatives at fixed x: sources, ground, line-of-sight attenuation
+                double below = I;
+                for (int p = 0; p < L; ++p) {
+                    for (int k = 0; k < K; ++k) dl[p * K + k] += cosm * Acum[p] * src[p].d[k];
+                    below -= Acum[p] * src[p].v;           // everything emitted below layer p carries exp(-tau_p / mu)
+                    dl[p * K + iTau] += cosm * (-1.0 / mu) * below;
+                }
+                for (int k = 0; k < K; ++k) dl[(L - 1) * K + k] += cosm * Acum[L] * gnd.d[k];
+                // adjoint of the boundary-value problem: A^T z = dI/dx, dI += z^T (db - dA x)
+                lu.solve_transposed(wvec.data());
+                for (const auto& e : ent) {
+                    const double f = cosm * wvec[e.r] * x[e.c];
+                    if (f != 0.0)
+                        for (int k = 0; k < K; ++k) dl[e.layer * K + k] -= f * e.a.d[k];
+                }
+                for (const auto& r : rhs) {
+                    const double f = cosm * wvec[r.r];
+                    if (f != 0.0)
+                        for (int k = 0; k < K; ++k) dl[r.layer * K + k] += f * r.b.d[k];
+                }
+            }
+        }
+        // local lanes -> layer lanes [scat g | od | ssa] + albedo, with the cross-layer chain of t_p and s_p
+        for (int j = 0; j < nlos; ++j) {
+            radiance[j] = rad[j];
+            if (!dlane) continue;
+            const double* dl = &dloc[size_t(j) * L * K];
+            double* out = dlane + size_t(j) * nd;
+            std::fill(out, out + nd, 0.0);
+            for (int p = 0; p < L; ++p) {
+                for (int g = 0; g < G; ++g) out[out_lanes.scat(p, g)] = dl[p * K + g];
+                out[out_lanes.ssa(p)] = dl[p * K + iOm];
+                out[out_lanes.od(p)] += dl[p * K + iTau] - dl[p * K + iS] * sval[p] / Ly.od[p].v;
+                const double dIdt = dl[p * K + iT], dIds = dl[p * K + iS] / Ly.od[p].v;
+                for (int q = 0; q < L; ++q) {
+                    const double c1 = P.chapman[size_t(p) * L + q];
+                    const double c0 = p > 0 ? P.chapman[size_t(p - 1) * L + q] : 0.0;
+                    if (c1 == 0.0 && c0 == 0.0) continue;
+                    out[out_lanes.od(q)] += dIds * (c1 - c0) - dIdt * tval[p] * c0;
+                }
+            }
+            out[out_lanes.albedo()] = dl[(L - 1) * K + iAlb];
+        }
+        if (layers_out) *layers_out = Ly;
+    }
+
+    // bvp*Condition (sktran_do_rte.cpp:1898-2294) with every entry tagged by the one layer whose quantities it holds
+    void assemble(int m, const Layers<T>& Ly, const T& albedo, const std::vector<LayerSolution<T>>& sol,
+                  std::vector<Entry>& ent, std::vector<Rhs>& rhs) const {
+        const int N = P.N, L = P.L, n = 2 * N * L;
+        ent.clear();
+        rhs.clear();
+        std::vector<std::vector<T>> theta(L, std::vector<T>(N));
+        for (int p = 0; p < L; ++p)
+            for (int j = 0; j < N; ++j) theta[p][j] = exp(-Solver<T>::S_abs(sol[p].k[j]) * Ly.od[p]);
+        for (int i = 0; i < N; ++i) {
+            for (int j = 0; j < N; ++j) {
+                ent.push_back({i, j, 0, sol[0].Wp[i + j * N]});
+                ent.push_back({i, j + N, 0, sol[0].Wm[i + j * N] * theta[0][j]});
+            }
+            rhs.push_back({i, 0, -sol[0].Gpt[i]});
+        }
+        for (int bd = 1; bd < L; ++bd) {
+            const int r0 = N + (bd - 1) * 2 * N, c0 = (bd - 1) * 2 * N, u = bd - 1, l = bd;
+            const auto& U = sol[u];
+            const auto& Lo = sol[l];
+            for (int i = 0; i < N; ++i) {
+                for (int j = 0; j < N; ++j) {
+                    ent.push_back({r0 + i + N, c0 + j, u, U.Wp[i + j * N] * theta[u][j]});
+                    ent.push_back({r0 + i + N, c0 + 2 * N + j, l, -Lo.Wp[i + j * N]});
+                    ent.push_back({r0 + i, c0 + j, u, U.Wm[i + j * N] * theta[u][j]});
+                    ent.push_back({r0 + i, c0 + 2 * N + j, l, -Lo.Wm[i + j * N]});
+                    ent.push_back({r0 + i + N, c0 + N + j, u, U.Wm[i + j * N]});
+                    ent.push_back({r0 + i + N, c0 + 3 * N + j, l, -(Lo.Wm[i + j * N] * theta[l][j])});
+                    ent.push_back({r0 + i, c0 + N + j, u, U.Wp[i + j * N]});
+                    ent.push_back({r0 + i, c0 + 3 * N + j, l, -(Lo.Wp[i + j * N] * theta[l][j])});
+                }
+                rhs.push_back({r0 + i, u, -U.Gmb[i]});
+                rhs.push_back({r0 + i, l, Lo.Gmt[i]});
+                rhs.push_back({r0 + i + N, u, -U.Gpb[i]});
+                rhs.push_back({r0 + i + N, l, Lo.Gpt[i]});
+            }
+        }
+        {
+            const int r0 = N + (L - 1) * 2 * N, c0 = n - 2 * N, b = L - 1;
+            const auto& B = sol[b];
+            const bool refl = (m == 0);
+            const double kd = (m == 0) ? 2.0 : 1.0;
+            for (int i = 0; i < N; ++i) {
+                for (int j = 0; j < N; ++j) {
+                    T vm = B.Wm[i + j * N], vp = B.Wp[i + j * N];
+                    if (refl)
+                        for (int q = 0; q < N; ++q) {
+                            vm -= T(kd) * albedo * T(P.wt[q] * P.mu[q]) * B.Wp[q + j * N];
+                            vp -= T(kd) * albedo * T(P.wt[q] * P.mu[q]) * B.Wm[q + j * N];
+                        }
+                    ent.push_back({r0 + i, c0 + j, b, vm * theta[b][j]});
+                    ent.push_back({r0 + i, c0 + N + j, b, vp});
+                }
+                T gds(0.0);
+                if (refl) gds = T(P.csz) * albedo / T(PI) * Ly.trans[L];
+                T um = B.Gmb[i];
+                if (refl)
+                    for (int q = 0; q < N; ++q) um -= T(kd) * albedo * T(P.wt[q] * P.mu[q]) * B.Gpb[q];
+                rhs.push_back({r0 + i, b, gds - um});
+            }
+        }
     }
 };
 

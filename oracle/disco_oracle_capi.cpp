@@ -9,6 +9,22 @@
 static thread_local std::string g_err;
 static std::string g_last_err;
 
+template <int G>
+static void reverse_wavelength(const oracle::Plan& P, oracle::dgeev_fn dgeev, const oracle::WavelInputs& in, int nlos, int nd,
+                               int nnative, double* radiance, double* native, double* lanes_out) {
+    using namespace oracle;
+    ReverseSolver<G> R(P, dgeev);
+    std::vector<double> dlane(size_t(nlos) * nd);
+    Layers<typename ReverseSolver<G>::T> Ly;
+    R.solve_wavelength(in, radiance, dlane.data(), &Ly);
+    Lanes lanes{P.L, G, false};
+    for (int j = 0; j < nlos; ++j) {
+        if (native) map_to_native(P, lanes, in, Ly.tot_ext, Ly.scat_ext, Ly.ssa_value, &dlane[size_t(j) * nd], native + size_t(j) * nnative);
+        if (lanes_out) std::memcpy(lanes_out + size_t(j) * nd, &dlane[size_t(j) * nd], sizeof(double) * nd);
+    }
+}
+
+
 extern "C" {
 
 const char* oracle_last_error() { return g_last_err.c_str(); }
@@ -23,6 +39,14 @@ void oracle_set_delta_m(const double* f, const double* d_f) {
     g_f = f;
     g_df = d_f;
 }
+
+// 0: forward-mode dense duals (the reference's default, do_backprop = false); 1: reverse mode (do_backprop = true,
+// RTESolver::backprop): layer-local duals + transposed band solves per line of sight
+static int g_reverse = 0;
+void oracle_set_reverse_mode(int on) { g_reverse = on; }
+
+// 1: pseudo-spherical chapman factors from the closed straight-line formula instead of the reference's ray tracer
+void oracle_set_chapman_straight_line(int on) { oracle::chapman_straight_line_ref() = on; }
 
 int oracle_num_threads() {
 #ifdef _OPENMP
@@ -93,6 +117,20 @@ int oracle_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nlos, const
                         in.d_leg = dl.data();
                     } else {
                         in.d_leg = nullptr;
+                    }
+                    if (g_reverse) {
+                        double* nat = native ? native + size_t(w) * nlos * nnative : nullptr;
+                        double* lo = lanes_out ? lanes_out + size_t(w) * nlos * nd : nullptr;
+                        double* rw = radiance + size_t(w) * nlos;
+                        switch (G) {
+                            case 0: reverse_wavelength<0>(P, dgeev, in, nlos, nd, nnative, rw, nat, lo); break;
+                            case 1: reverse_wavelength<1>(P, dgeev, in, nlos, nd, nnative, rw, nat, lo); break;
+                            case 2: reverse_wavelength<2>(P, dgeev, in, nlos, nd, nnative, rw, nat, lo); break;
+                            case 3: reverse_wavelength<3>(P, dgeev, in, nlos, nd, nnative, rw, nat, lo); break;
+                            default: throw std::runtime_error("reverse-mode oracle: at most 3 scattering groups");
+                        }
+                        nd_ref() = 0;
+                        continue;
                     }
                     Solver<Dual> S(P, dgeev);
                     S.lanes.L = L;

@@ -63,7 +63,7 @@ def _p(a):
 
 def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az,
                 ssa, ext, leg, solar=None, albedo, d_leg=None, include_ss=True, num_azimuth=0,
-                calc_derivs=False, nthreads=0, return_lanes=False, stable=False, f=None, d_f=None):
+                calc_derivs=False, nthreads=0, return_lanes=False, stable=False, f=None, d_f=None, reverse=False):
     """Run the oracle.
 
     ssa, ext: [nloc, nwavel] (Fortran order is used internally, as the reference does);
@@ -71,6 +71,8 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
     Returns dict(radiance [nwavel, nlos], native [nwavel, nlos, nloc*(2+G)+1] if calc_derivs).
     f [nloc, nwavel], d_f [nloc, nwavel, ngroups]: delta-M truncation fraction and its derivatives as left by
     apply_delta_m_scaling (below); the arrays passed in are then the SCALED ones.
+    reverse=True computes the derivatives in reverse mode (config.do_backprop = true: layer-local duals, one transposed
+    band solve per line of sight, RTESolver::backprop) instead of dense forward-mode duals; same results.
     stable=True switches the particular-solution multipliers from the reference's formulas to the
     singularity-free phi/psi forms (see disco_oracle.hpp, "stable multipliers"); default is the reference's.
     """
@@ -101,6 +103,7 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
         if return_lanes:
             lanes = np.zeros((nwavel, nlos, nl * (G + 2) + 1))
     L.oracle_set_stable_multipliers(ctypes.c_int(int(stable)))
+    L.oracle_set_reverse_mode(ctypes.c_int(int(reverse)))
     if f is not None:
         f = np.asfortranarray(f, dtype=np.float64)
         assert f.shape == (nloc, nwavel)
@@ -125,8 +128,12 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
     return out
 
 
-def plan(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az):
+def plan(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az,
+         chapman_straight_line=False):
+    """Geometry plan of the oracle.  Pseudo-spherical chapman factors are ray traced like the reference
+    (calculate_chapman_factors_raytracer); chapman_straight_line=True selects the closed formula instead."""
     L = lib()
+    L.oracle_set_chapman_straight_line(ctypes.c_int(int(chapman_straight_line)))
     alt = np.ascontiguousarray(alt, dtype=np.float64)
     nloc = alt.size
     cz = np.ascontiguousarray(los_cos_vza, dtype=np.float64)
@@ -140,6 +147,7 @@ def plan(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos
                        ctypes.c_int(geotype), ctypes.c_double(cos_sza), ctypes.c_double(earth_radius), _p(cz), _p(az),
                        _p(out["mu"]), _p(out["wt"]), _p(out["lp_mu"]), _p(out["lp_csz"]), _p(out["lp_los"]),
                        _p(out["W"]), _p(out["chapman"]))
+    L.oracle_set_chapman_straight_line(ctypes.c_int(0))
     if rc != 0:
         raise RuntimeError(f"oracle_plan failed: {L.oracle_last_error().decode()}")
     return out

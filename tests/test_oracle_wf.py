@@ -100,3 +100,26 @@ def test_oracle_stable_multipliers_agree_with_reference_formulas(oracle_mod):
     noise_stb = max(rel(run(True, e)["native"], stb["native"]) for e in (1e-12, -1e-12, 1e-11))
     assert rel(stb["native"], ref["native"]) <= 10.0 * max(noise_ref, noise_stb)
     assert noise_stb < 1e-9
+
+
+@pytest.mark.parametrize("nstr,nlayers,nlos,interp,geotype", [(2, 9, 2, 1, 1), (4, 9, 2, 2, 0), (8, 12, 3, 1, 1), (16, 25, 4, 1, 1),
+                                                              (8, 1, 2, 1, 1)])
+def test_oracle_reverse_mode_matches_forward_mode(oracle_mod, nstr, nlayers, nlos, interp, geotype):
+    """The reverse-mode linearisation (RTESolver::backprop, sktran_do_rte.cpp:1793-1895: layer-local duals, one
+    transposed band solve per line of sight, cross-layer chain of beam transmittance and secant) gives the layer lanes
+    and native derivatives of the dense forward-mode duals, with one and two scattering groups and the albedo lane.
+    Singularity-free multipliers: the two differentiation orders of the reference's direct C+ / D- formulas differ by
+    their own rounding noise (1e-6 of the column maximum at 16 streams, DESIGN.md "Conditioning")."""
+    sc = scn.small_wf_case(nstr=nstr, nlayers=nlayers, nwavel=3, nlos=nlos, interp=interp, geotype=geotype)
+    aer = sc.mappings["wf_aerosol_extinction"]["d_legendre"]
+    for d_leg in (None, aer[..., None], np.stack([aer, 0.5 * aer + 0.1], axis=-1)):
+        kw = dict(nstr=sc.nstr, alt=sc.altitudes, interp=sc.interp, geotype=sc.geotype, cos_sza=sc.cos_sza,
+                  earth_radius=sc.earth_radius, los_cos_vza=sc.los_cos_vza, los_rel_az=sc.los_rel_az, ssa=sc.ssa,
+                  ext=sc.total_extinction, leg=sc.leg_coeff, albedo=sc.albedo, d_leg=d_leg, calc_derivs=True,
+                  return_lanes=True, stable=True)
+        fwd = oracle_mod.do_radiance(**kw)
+        rev = oracle_mod.do_radiance(**kw, reverse=True)
+        np.testing.assert_allclose(rev["radiance"], fwd["radiance"], rtol=1e-12)
+        for key in ("lanes", "native"):
+            scale = np.abs(fwd[key]).max(axis=2, keepdims=True)
+            assert np.max(np.abs(rev[key] - fwd[key]) / scale) < 1e-9, key

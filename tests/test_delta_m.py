@@ -102,8 +102,10 @@ def test_c_abi_delta_m_host_pass_matches_restatement(oracle_mod):
         np.testing.assert_allclose(m.d_ssa, want["mappings"][n]["d_ssa"], rtol=1e-12, atol=1e-300)
         if n in names:
             np.testing.assert_allclose(m.d_leg_coeff, want["d_leg"][..., names.index(n)], rtol=1e-12, atol=1e-14)
-    # a second explicit application is refused (the arrays are already scaled)
-    assert _lib.lib().sk_atmosphere_apply_delta_m_scaling(atm._h, nstr) != 0
+    # like upstream, the C entry point rescales whatever the storage holds (the caller refills between applications;
+    # tests/test_host_logic.py covers zero_storage + refill): after set_zero the storage is unscaled again
+    assert _lib.lib().sk_atmosphere_storage_set_zero(atm.storage._h) == 0
+    assert np.all(atm.storage.leg_coeff == 0)
 
 
 @pytest.mark.gpu

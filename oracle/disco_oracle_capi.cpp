@@ -162,6 +162,52 @@ int oracle_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nlos, const
     }
 }
 
+// Distance of every (wavelength, order, layer) cell to the removable singularities of the reference's multiplier
+// formulas: d_sec = min_j |secant_p - k_j| (C+, D-: sktran_do_rte.cpp:1203-1226, sktran_do_opticallayer.cpp:897-938) and
+// d_los = min_{j, los} |1 - mu_los k_j| (h-: sktran_do_opticallayer.cpp:339-344).  out: [nwavel][nstr][L][2].
+int oracle_degeneracy(int nstr, int nloc, int nwavel, int nleg, int nlos, const double* alt, int interp, int geotype,
+                      double cos_sza, double earth_radius, const double* los_cos_vza, const double* los_rel_az,
+                      const double* ssa, const double* ext, const double* leg, void* dgeev_ptr, double* out) {
+    using namespace oracle;
+    try {
+        std::vector<double> a(alt, alt + nloc), cz(los_cos_vza, los_cos_vza + nlos), az(los_rel_az, los_rel_az + nlos);
+        Plan P = make_plan(nstr, a, interp, geotype, cos_sza, earth_radius, cz, az);
+        const int L = nloc - 1, N = nstr / 2;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int w = 0; w < nwavel; ++w) {
+            WavelInputs in{};
+            in.ext = ext + size_t(nloc) * w;
+            in.ssa = ssa + size_t(nloc) * w;
+            in.leg = leg + size_t(nleg) * nloc * w;
+            in.nleg = nleg;
+            in.f = g_f ? g_f + size_t(nloc) * w : nullptr;
+            in.solar = 1.0;
+            in.d_leg = nullptr;
+            in.ngroups = 0;
+            Solver<double> S(P, (dgeev_fn)dgeev_ptr);
+            Layers<double> Ly;
+            S.layer_optics(in, Ly);
+            LayerSolution<double> sol;
+            for (int m = 0; m < nstr; ++m)
+                for (int p = 0; p < L; ++p) {
+                    S.homogeneous(m, Ly.ssa[p], Ly.beta[p], sol);
+                    double d1 = 1e300, d2 = 1e300;
+                    for (int j = 0; j < N; ++j) {
+                        d1 = std::min(d1, std::abs(Ly.secant[p] - sol.k[j]));
+                        for (int l = 0; l < nlos; ++l) d2 = std::min(d2, std::abs(1.0 - cz[l] * sol.k[j]));
+                    }
+                    double* o = out + ((size_t(w) * nstr + m) * L + p) * 2;
+                    o[0] = d1;
+                    o[1] = d2;
+                }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_err = e.what();
+        return -3;
+    }
+}
+
 // Geometry plan export, for checking the product's host-side tables against the oracle's.
 int oracle_plan(int nstr, int nloc, int nlos, const double* alt, int interp, int geotype, double cos_sza,
                 double earth_radius, const double* los_cos_vza, const double* los_rel_az, double* mu, double* wt,

@@ -128,6 +128,32 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
     return out
 
 
+def degeneracy(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az, ssa, ext, leg,
+               f=None, **_ignored):
+    """Distances [nwavel, nstr (order), L (layer), 2] of every cell to the removable singularities of the reference's
+    multiplier formulas: [..., 0] = min_j |secant - k_j|, [..., 1] = min_{j, los} |1 - mu_los k_j|."""
+    L = lib()
+    alt = np.ascontiguousarray(alt, dtype=np.float64)
+    ssa = np.asfortranarray(ssa, dtype=np.float64)
+    ext = np.asfortranarray(ext, dtype=np.float64)
+    leg = np.asfortranarray(leg, dtype=np.float64)
+    cz = np.ascontiguousarray(los_cos_vza, dtype=np.float64)
+    az = np.ascontiguousarray(los_rel_az, dtype=np.float64)
+    nloc, nwavel = ssa.shape
+    out = np.zeros((nwavel, nstr, nloc - 1, 2))
+    if f is not None:
+        f = np.asfortranarray(f, dtype=np.float64)
+    L.oracle_set_delta_m(_p(f), None)
+    rc = L.oracle_degeneracy(ctypes.c_int(nstr), ctypes.c_int(nloc), ctypes.c_int(nwavel), ctypes.c_int(leg.shape[0]),
+                             ctypes.c_int(cz.size), _p(alt), ctypes.c_int(interp), ctypes.c_int(geotype),
+                             ctypes.c_double(cos_sza), ctypes.c_double(earth_radius), _p(cz), _p(az), _p(ssa), _p(ext),
+                             _p(leg), _DGEEV, _p(out))
+    L.oracle_set_delta_m(None, None)
+    if rc != 0:
+        raise RuntimeError(f"oracle_degeneracy failed: {L.oracle_last_error().decode()}")
+    return out
+
+
 def plan(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az,
          chapman_straight_line=False):
     """Geometry plan of the oracle.  Pseudo-spherical chapman factors are ray traced like the reference

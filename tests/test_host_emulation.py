@@ -111,3 +111,25 @@ def test_kernel_bodies_weighting_functions_match_oracle(emul, oracle_mod, nstr, 
         a, b = native[..., lo:hi], ora["native"][..., lo:hi]
         scale = np.abs(b).max(axis=-1, keepdims=True)
         assert np.max(np.abs(a - b) / scale) < 1e-7, (lo, np.max(np.abs(a - b) / scale))
+
+
+@pytest.mark.parametrize("nstr,nlayers,nlos", [(8, 20, 3), (16, 40, 4)])
+def test_kernel_bodies_pass_the_weighting_function_parity_rules(emul, oracle_mod, nstr, nlayers, nlos):
+    """The parity rules the GPU tests apply to the CUDA results (tests/wf_checks.py: flat 1e-7 against the stable and the
+    reference-formula oracle, explicit list of optically thin grid points for the extinction probe) applied to the
+    product's kernel bodies run on the host, on an atmosphere that reaches 100 km (layer optical depths down to 1e-8)."""
+    from sasktran2_b200 import scenarios
+    from tests import wf_checks
+
+    sc = scenarios.small_wf_case(nstr=nstr, nlayers=nlayers, nwavel=4, nlos=nlos)
+    wf_checks.add_native_probes(sc, scat_probe=True)
+    names = wf_checks.scat_names(sc)
+    d_leg = np.stack([sc.mappings[n]["d_legendre"] for n in names], axis=-1)
+    inp = dict(nstr=sc.nstr, alt=sc.altitudes, interp=sc.interp, geotype=sc.geotype, cos_sza=sc.cos_sza,
+               los_cos_vza=sc.los_cos_vza, los_rel_az=sc.los_rel_az, ssa=sc.ssa, ext=sc.total_extinction,
+               leg=sc.leg_coeff, albedo=sc.albedo)
+    rad, _, native = emul(**inp, d_leg=d_leg, want_native=True)
+    res = wf_checks.candidate_from_native(oracle_mod, sc, rad, native)
+    rep = wf_checks.assert_wf(oracle_mod, sc, res)
+    assert rep["reference"]["wf_o3_vmr"]["rule"] == "flat 1e-7"
+    assert rep["reference"]["wf_probe_k"]["listed_points"]["count"] > 0

@@ -1,19 +1,25 @@
 #!/usr/bin/env python
 """Benchmark of the B200 discrete-ordinates radiance solve (contract: see the task statement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c5|c2|c1|c3]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-A "step" is one pass of the hot path over one batch of synthetic input: the BASELINE.json configs[1]/[4]
-shape (pseudo-spherical DO, 16 streams, 100 layers, Rayleigh + aerosol + absorbers, 10 ground-viewing LOS)
-with `--nwavel` wavelengths PER GPU (weak scaling: every rank solves its own contiguous wavelength block,
-no data-path collective; only the timing reduction uses torch.distributed).
+A "step" is one pass of the hot path over one batch of synthetic input.  Default workload = BASELINE.json configs[4]
+("C5", the configuration the metric is quoted on): full linearisation, pseudo-spherical DO, 16 streams, 100 layers, 10
+ground-viewing LOS, weighting functions w.r.t. O3 VMR, NO2 VMR and aerosol extinction (3 x 101 outputs) + albedo,
+50 000 wavelengths.  With N GPUs the SAME spectrum is sharded into contiguous wavelength blocks, one process per GPU
+(strong scaling); the only exchange is the final gather of radiances and weighting functions onto rank 0.
 
-  value  LOS x wavelength radiances / s, inputs resident in HBM, kernels only (CUDA events inside the library)
-  e2e    the same metric through Engine.calculate_radiance(atmosphere) — the reference-facing call — with
-         pinned HOST buffers: H2D of the inputs and D2H of the results inside the timed region
-  --impl reference   the CPU implementation of the path (oracle port, OpenMP over wavelengths, all host
-         cores) on a bounded sample of the same workload
+  value  LOS x wavelength radiances / s, inputs resident in HBM, kernels only (CUDA events inside the library, max
+         over ranks)
+  e2e    the same metric through the reference-facing call (sk_engine_calculate_radiance / ..._block_thread behind
+         Engine.calculate_radiance) with HOST buffers: H2D of the inputs, the solve, and the results of ALL ranks ending
+         up in rank 0's host arrays, inside the timed region.  N > 1 reports both gather variants: "nccl" (ncclSend /
+         ncclRecv onto GPU 0 inside the library, then one D2H) and "direct" (every rank copies its block straight into
+         the caller's page-locked shared result arrays: N PCIe links instead of one); e2e.value is the faster one.
+  --impl reference   the CPU implementation of the path on the SAME config: the oracle port of the reference's
+         reverse-mode linearisation (RTESolver::backprop), OpenMP over wavelengths on all host cores, on a bounded
+         sample of the workload (the reference itself cannot be built here: Eigen + Rust/cxx generated headers).
 """
 from __future__ import annotations
 
@@ -30,8 +36,24 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "LOS x wavelength radiances/sec (16-stream, 100 layers)"
+METRIC = json.loads((ROOT / "BASELINE.json").read_text())["metric"] if (ROOT / "BASELINE.json").exists() else \
+    "LOS×wavelength radiances/sec (16-stream, 100 layers, with WFs) at 1/2/4/8 B200"
 UNIT = "radiances/s"
+
+# Named workloads (BASELINE.json configs; SURVEY.md section 8d fixes the unspecified details)
+CONFIGS = {
+    "c5": dict(label="configs[4] (C5)", nwavel=50000, nstr=16, layers=100, nlos=10, wf=True,
+               text="full linearisation: pseudo-spherical DO, 16 streams, 100 layers, Rayleigh+aerosol+O3/NO2, 10 ground-viewing "
+                    "LOS, weighting functions w.r.t. O3 VMR, NO2 VMR, aerosol extinction (3 x 101 outputs) and albedo, 50,000 "
+                    "wavelengths"),
+    "c2": dict(label="configs[1] (C2)", nwavel=100000, nstr=16, layers=100, nlos=10, wf=False,
+               text="pseudo-spherical DO, 16 streams, 100 layers, Rayleigh+aerosol, 10 nadir LOS, 100,000 wavelengths, radiances only"),
+    "c1": dict(label="configs[0] (C1)", nwavel=1000, nstr=4, layers=50, nlos=1, wf=False,
+               text="plane-parallel DO, 4 streams, 50 layers, Rayleigh+O3, 1 nadir LOS, 1,000 wavelengths"),
+    "c3": dict(label="configs[2] (C3)", nwavel=1000000, nstr=2, layers=60, nlos=2, wf=False,
+               text="two-stream source (num_streams=2, multiple scatter only), 60 layers, 2 nadir LOS, 1,000,000 line-by-line "
+                    "wavelengths (O2 A-band like)"),
+}
 
 
 def flop_model(nstr, nlayers, nlos, m_list, ngroups=1, adjoint_refactor=False):
@@ -64,10 +86,15 @@ def flop_model(nstr, nlayers, nlos, m_list, ngroups=1, adjoint_refactor=False):
 
 
 # DRAM bytes per wavelength (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, divided by
-# the 600 wavelengths of the profiled launch) for the default shape: 16 streams, 100 layers, 10 LOS, weighting
-# functions with one scattering group - profiles/ncu_r01_v12_summary.csv.  Other shapes report traffic = null.
+# the wavelengths of the profiled launch) for the C5 shape - see NCU_SOURCE.  Other shapes report traffic = null.
+NCU_SOURCE = "profiles/ncu_r01_v12_summary.csv"
 NCU_DRAM_BYTES_PER_WAVELENGTH = {"layer": (0.813 + 2.020 + 3.324) * 1e9 / 600, "bvp": (6.151 + 7.813) * 1e9 / 600,
                                  "wf_adjoint": (10.033 + 2.442) * 1e9 / 600, "wf_layer": (3.041 + 0.453) * 1e9 / 600}
+try:  # a newer capture of this round, written by tools/ncu_summary.py
+    _t = json.loads((ROOT / "profiles" / "ncu_dram_bytes_per_wavelength.json").read_text())
+    NCU_DRAM_BYTES_PER_WAVELENGTH, NCU_SOURCE = _t["bytes_per_wavelength"], _t["source"]
+except Exception:
+    pass
 
 
 def tsolve_bytes_model(nstr, nlayers, nlos, n_orders):
@@ -81,9 +108,9 @@ def tsolve_bytes_model(nstr, nlayers, nlos, n_orders):
     return 8.0 * n_orders * (n * (fs + ls) + nlos * 4 * n)
 
 
-def bytes_model(nloc, nleg, nlos, nwf_out=0):
-    """Algorithmic HBM bytes per wavelength: inputs 8*nloc*(2+nleg) + outputs 8*nlos*(1 + sum nout)."""
-    return 8.0 * nloc * (2 + nleg) + 8.0 * nlos * (1 + nwf_out)
+def bytes_model(nloc, nleg, nlos, nwf_out=0, ngroups=0):
+    """Algorithmic HBM bytes per wavelength: inputs 8 nloc (2 + nleg)(1 + ngroups) + outputs 8 nlos (1 + sum nout)."""
+    return 8.0 * nloc * (2 + nleg) * (1 + ngroups) + 8.0 * nlos * (1 + nwf_out)
 
 
 class ClockSampler:
@@ -135,63 +162,214 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.maxclk, "reasons": sorted(self.reasons)}
 
 
-def oracle_inputs(sc):
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------------
+def build_scenario(cfg_name, nw_total, block, nlos=None, layers=None, nstr=None):
+    from sasktran2_b200 import scenarios
+
+    c = CONFIGS[cfg_name]
+    nlos = c["nlos"] if nlos is None else nlos
+    layers = c["layers"] if layers is None else layers
+    nstr = c["nstr"] if nstr is None else nstr
+    if cfg_name in ("c5", "c2"):
+        return scenarios.config2(nwavel=nw_total, nlayers=layers, nstr=nstr, nlos=nlos, with_wf=c["wf"], block=block)
+    if cfg_name == "c1":
+        sc = scenarios.config1(nwavel=nw_total, nlayers=layers)
+        assert block is None or block == (0, nw_total), "config 1 is a single-GPU case"
+        return sc
+    if cfg_name == "c3":
+        return scenarios.config3(nwavel=nw_total, nlayers=layers, nlos=nlos, block=block)
+    raise ValueError(cfg_name)
+
+
+def make_engine(sc, cfg_name, total_wavelengths=None, start=0):
+    """(config, geometry, viewing geometry, engine, atmosphere) for a scenario block of one named workload."""
+    import sasktran2_b200 as sk
+
+    cfg = sk.Config()
+    cfg.num_streams = sc.nstr
+    cfg.num_stokes = 1
+    if cfg_name == "c3":
+        cfg.multiple_scatter_source = sk.MultipleScatterSource.TwoStream
+        cfg.single_scatter_source = sk.SingleScatterSource.NoSource
+    else:
+        cfg.multiple_scatter_source = sk.MultipleScatterSource.DiscreteOrdinates
+        cfg.single_scatter_source = sk.SingleScatterSource.DiscreteOrdinates
+    cfg.do_backprop = True
+    geo = sk.Geometry1D(sc.cos_sza, 0.0, sc.earth_radius, sc.altitudes, sk.InterpolationMethod(sc.interp),
+                        sk.GeometryType(sc.geotype))
+    view = sk.ViewingGeometry()
+    for cz, az in zip(sc.los_cos_vza, sc.los_rel_az):
+        view.add_ray(sk.GroundViewingSolar(sc.cos_sza, float(az), float(cz), sc.observer_altitude))
+    eng = sk.Engine(cfg, geo, view)
+    atm = sk.Atmosphere.from_scenario(sc, geo, cfg, total_wavelengths=total_wavelengths, wavelength_start=start)
+    if sc.mappings:
+        atm.surface.enable_albedo_derivative("wf_albedo")
+    return cfg, geo, view, eng, atm
+
+
+def oracle_inputs(sc, pick):
     return dict(nstr=sc.nstr, alt=sc.altitudes, interp=sc.interp, geotype=sc.geotype, cos_sza=sc.cos_sza,
-                earth_radius=sc.earth_radius, los_cos_vza=sc.los_cos_vza, los_rel_az=sc.los_rel_az, ssa=sc.ssa,
-                ext=sc.total_extinction, leg=sc.leg_coeff, albedo=sc.albedo)
+                earth_radius=sc.earth_radius, los_cos_vza=sc.los_cos_vza, los_rel_az=sc.los_rel_az,
+                ssa=np.asfortranarray(sc.ssa[:, pick]), ext=np.asfortranarray(sc.total_extinction[:, pick]),
+                leg=np.asfortranarray(sc.leg_coeff[:, :, pick]), albedo=sc.albedo[pick])
 
 
-def time_oracle(sc, sample, threads, with_wf=False):
-    """Times the CPU port (oracle) on `sample` wavelengths of the workload with `threads` OpenMP threads."""
+def run_oracle(sc, pick, threads, cfg_name, stable=False):
+    """The CPU port on wavelengths `pick` of the scenario: same outputs as the GPU arm of that workload (radiances;
+    for C5 also the native derivatives in reverse mode, do_backprop = true).  Returns (result dict, seconds)."""
     from oracle import oracle
 
-    pick = np.linspace(0, sc.nwavel - 1, sample).astype(int)
-    inp = oracle_inputs(sc)
-    inp["ssa"] = np.asfortranarray(sc.ssa[:, pick])
-    inp["ext"] = np.asfortranarray(sc.total_extinction[:, pick])
-    inp["leg"] = np.asfortranarray(sc.leg_coeff[:, :, pick])
-    inp["albedo"] = sc.albedo[pick]
-    oracle.lib()
+    inp = oracle_inputs(sc, pick)
     extra = {}
-    if with_wf and "wf_aerosol_extinction" in sc.mappings:
-        extra = dict(d_leg=np.asfortranarray(sc.mappings["wf_aerosol_extinction"]["d_legendre"][:, :, pick][..., None]),
-                     calc_derivs=True)
+    if cfg_name == "c3":
+        t0 = time.perf_counter()
+        out = oracle.twostream_radiance(**{k: v for k, v in inp.items() if k != "nstr"}, nthreads=threads)
+        return out, time.perf_counter() - t0
+    if CONFIGS[cfg_name]["wf"]:
+        aer = sc.mappings["wf_aerosol_extinction"]["d_legendre"]
+        extra = dict(d_leg=np.asfortranarray(aer[:, :, pick])[..., None], calc_derivs=True, reverse=True, stable=stable)
     t0 = time.perf_counter()
-    oracle.do_radiance(**inp, nthreads=threads, **extra)
-    dt = time.perf_counter() - t0
-    return sample * sc.nlos / dt, dt
+    out = oracle.do_radiance(**inp, nthreads=threads, **extra)
+    return out, time.perf_counter() - t0
+
+
+def oracle_weighting_functions(sc, pick, native):
+    from oracle import oracle
+
+    maps = {}
+    for n, mp in sc.mappings.items():
+        maps[n] = dict(d_ssa=np.asfortranarray(mp["d_ssa"][:, pick]), d_extinction=np.asfortranarray(mp["d_extinction"][:, pick]),
+                       scat_factor=np.asfortranarray(mp["scat_factor"][:, pick]) if "scat_factor" in mp else None,
+                       scat_index=0 if "scat_factor" in mp else -1, interpolator=None)
+    wf = oracle.apply_mappings(native, maps, sc.nloc, 1)
+    wf["wf_albedo"] = native[:, :, -1]
+    return wf
+
+
+def parity_sample(sc, cfg_name, result, nsample, threads):
+    """Compares a strided sample of the TIMED run's outputs (this rank's block) with the oracle: radiance 1e-9; for
+    C5 the O3 / NO2 VMR and albedo weighting functions 1e-7 of the column maximum (singularity-free oracle variant;
+    tests/wf_checks.py holds the full rule set incl. the reference-formula variant)."""
+    pick = np.unique(np.linspace(0, sc.nwavel - 1, nsample).astype(int))
+    ora, _ = run_oracle(sc, pick, threads, cfg_name, stable=True)
+    rad = result["radiance"][pick, :, 0]
+    out = {"wavelengths": int(pick.size), "radiance_max_rel_diff": float(np.max(np.abs(rad / ora["radiance"] - 1.0))),
+           "radiance_tol": 1e-9}
+    ok = out["radiance_max_rel_diff"] < 1e-9
+    if CONFIGS[cfg_name]["wf"]:
+        wf = oracle_weighting_functions(sc, pick, ora["native"])
+        errs = {}
+        for name in ("wf_o3_vmr", "wf_no2_vmr", "wf_aerosol_extinction", "wf_albedo"):
+            got = result[name][:, pick, :, 0] if name != "wf_albedo" else result[name][pick, :, 0]
+            ref = wf[name]
+            errs[name] = float(np.max(np.abs(got - ref) / np.abs(ref).max(axis=0, keepdims=True)))
+        out["wf_max_diff_over_column_max"] = errs
+        out["wf_tol"] = 1e-7
+        out["wf_note"] = "aerosol extinction: 1/k-amplified mapping, reported only (rules: tests/wf_checks.py)"
+        ok = ok and all(errs[n] < 1e-7 for n in ("wf_o3_vmr", "wf_no2_vmr", "wf_albedo"))
+    out["ok"] = bool(ok)
+    return out
+
+
+def cpu_arm(sc, cfg_name, sample, threads):
+    """Times the CPU port on a bounded strided sample of the workload; returns (radiances/s, seconds, description)."""
+    pick = np.unique(np.linspace(0, sc.nwavel - 1, sample).astype(int))
+    _, dt = run_oracle(sc, pick, threads, cfg_name)
+    what = ("oracle port of the reference's reverse-mode linearisation (RTESolver::backprop, do_backprop = true): radiances + "
+            "native derivatives w.r.t. extinction, SSA, one scattering group and albedo at every grid point"
+            if CONFIGS[cfg_name]["wf"] else "oracle port, radiances only")
+    return pick.size * sc.nlos / dt, dt, f"{pick.size} wavelengths x {sc.nlos} LOS strided over the workload's spectrum, {what}, " \
+                                        f"OpenMP over wavelengths on {threads} threads, {dt:.1f} s"
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path.  The reference itself cannot be built here
-    (needs Eigen + Rust/cxx generated headers), so this is the oracle port (kind "port")."""
+    """--impl reference: the CPU implementation of the path on the same config (kind "port": the reference itself needs
+    Eigen + Rust/cxx generated headers and cannot be built in this image)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from sasktran2_b200 import scenarios
-
+    c = CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample
-    sc = scenarios.config2(nwavel=max(sample, 64), nlayers=args.layers, nstr=args.nstr, nlos=args.nlos)
-    time_oracle(sc, min(sample, cores), cores)  # warm-up (thread pool, page-in)
+    sample = args.ref_sample
+    # the sample is drawn from the first `span` wavelengths... no: build a decimated spectrum with the same formulae
+    sc = build_scenario(args.config, c["nwavel"], None) if c["nwavel"] <= 4 * sample else \
+        build_scenario_decimated(args.config, c["nwavel"], sample)
+    cpu_arm(sc, args.config, min(sample, 2 * cores), cores)  # warm-up (thread pool, page-in)
     vals, dts = [], []
     for _ in range(max(args.steps, 1)):
-        v, dt = time_oracle(sc, sample, cores)
+        v, dt, desc = cpu_arm(sc, args.config, sample, cores)
         vals.append(v)
         dts.append(dt)
     v = float(np.median(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": float(np.median(dts)) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": float(np.median(dts)) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"pseudo-spherical DO, {args.nstr} streams, {args.layers} layers, {args.nlos} LOS, "
-                               f"CPU port on a {sample}-wavelength sample per step, VALUES ONLY (upper bound for the CPU "
-                               f"path with weighting functions: the port has no reverse-mode linearisation)"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} wavelengths x {args.nlos} LOS per step, OpenMP over wavelengths"},
+        "config": {"workload": f"{c['label']}: {c['text']}"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def build_scenario_decimated(cfg_name, nw_total, sample):
+    """`sample` wavelengths strided over the nw_total-point spectrum of a workload, built block by block so that the CPU
+    arms never allocate the full spectrum."""
+    import copy
+
+    pick = np.unique(np.linspace(0, nw_total - 1, sample).astype(int))
+    parts = [build_scenario(cfg_name, nw_total, (int(w), 1)) for w in pick]
+    sc = copy.copy(parts[0])
+    sc.ssa = np.asfortranarray(np.concatenate([p.ssa for p in parts], axis=1))
+    sc.total_extinction = np.asfortranarray(np.concatenate([p.total_extinction for p in parts], axis=1))
+    sc.leg_coeff = np.asfortranarray(np.concatenate([p.leg_coeff for p in parts], axis=2))
+    sc.albedo = np.concatenate([p.albedo for p in parts])
+    sc.solar_irradiance = np.concatenate([p.solar_irradiance for p in parts])
+    sc.mappings = {}
+    for n in parts[0].mappings:
+        sc.mappings[n] = {k: np.asfortranarray(np.concatenate([p.mappings[n][k] for p in parts], axis=-1))
+                          for k in parts[0].mappings[n]}
+    return sc
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def quick_config(cfg_name, steps, warmup, local_rank, threads):
+    """Single-GPU line of another named workload (device-resident rate, end-to-end rate, parity sample, roofline view)."""
+    import sasktran2_b200 as sk  # noqa: F401
+
+    c = CONFIGS[cfg_name]
+    t0 = time.perf_counter()
+    sc = build_scenario(cfg_name, c["nwavel"], None)
+    _, _, _, eng, atm = make_engine(sc, cfg_name)
+    eng.set_workspace_gb(48.0)
+    eng.reuse_output_buffers = True
+    eng.stage(atm)
+    for _ in range(warmup):
+        eng.solve_staged()
+    ms = 0.0
+    for _ in range(steps):
+        eng.solve_staged()
+        ms += eng.timings_ms()["kernels_total"]
+    ms /= steps
+    res = eng.fetch()
+    eng.calculate_radiance(atm)
+    t1 = time.perf_counter()
+    for _ in range(steps):
+        res = eng.calculate_radiance(atm)
+    e2e_ms = (time.perf_counter() - t1) * 1e3 / steps
+    units = float(sc.nwavel * sc.nlos)
+    nleg = sc.leg_coeff.shape[0]
+    gbs = bytes_model(sc.nloc, nleg, sc.nlos) * sc.nwavel / (ms * 1e-3) / 1e9
+    out = {"workload": f"{c['label']}: {c['text']}", "value": units / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+           "e2e": {"value": units / (e2e_ms * 1e-3), "ms_per_step": e2e_ms},
+           "hbm_view": {"achieved_gbs": gbs, "bytes_per_wavelength": bytes_model(sc.nloc, nleg, sc.nlos)},
+           "kernel_ms": {k: v for k, v in eng.timings_ms().items() if v > 0 and k not in ("h2d", "d2h")},
+           "parity": parity_sample(sc, cfg_name, res, 16, threads), "setup_s": time.perf_counter() - t0}
+    return out
 
 
 def main():
@@ -200,19 +378,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--nwavel", type=int, default=int(os.environ.get("SK_BENCH_NWAVEL", "20000")),
-                    help="wavelengths per GPU per step")
-    ap.add_argument("--nstr", type=int, default=16)
-    ap.add_argument("--layers", type=int, default=100)
-    ap.add_argument("--nlos", type=int, default=10)
-    ap.add_argument("--cpu-sample", type=int, default=4000,
-                    help="wavelengths of the CPU-port sample (values only; ~10 s on 16 cores)")
+    ap.add_argument("--config", default=os.environ.get("SK_BENCH_CONFIG", "c5"), choices=sorted(CONFIGS))
+    ap.add_argument("--nwavel", type=int, default=int(os.environ.get("SK_BENCH_NWAVEL", "0")),
+                    help="total wavelengths of the spectrum (default: the named configuration's)")
+    ap.add_argument("--cpu-sample", type=int, default=240, help="wavelengths of the cpu_baseline sample (same config)")
+    ap.add_argument("--ref-sample", type=int, default=160, help="wavelengths per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=48.0,
                     help="device workspace per wavelength chunk (B200: 180 GB HBM3e)")
-    ap.add_argument("--cpu-wf-sample", type=int, default=8,
-                    help="also time the CPU port WITH weighting functions (forward-mode duals) on this many wavelengths")
-    ap.add_argument("--wf", type=int, default=1, help="1: with weighting functions (O3, NO2, aerosol mappings + albedo), 0: radiances only")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -223,7 +397,7 @@ def main():
     import torch.distributed as dist
 
     import sasktran2_b200 as sk
-    from sasktran2_b200 import scenarios
+    from sasktran2_b200.parallel import SharedResult, init_nccl_comm, wavelength_block
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -240,59 +414,62 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def reduce_max(x):
+    def reduce(x, op):
         if world == 1:
             return float(x)
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def reduce_sum(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    reduce_max = lambda x: reduce(x, dist.ReduceOp.MAX if world > 1 else None)  # noqa: E731
+    reduce_sum = lambda x: reduce(x, dist.ReduceOp.SUM if world > 1 else None)  # noqa: E731
 
-    # ---- synthetic workload: every rank builds its own contiguous wavelength block of the global spectrum
-    nw_total = args.nwavel * world
-    sc_all_small = None
-    from sasktran2_b200.parallel import wavelength_block
-
-    start, count = wavelength_block(nw_total, rank, world)
-    with_wf = bool(args.wf)
-    # every rank builds only its own block of the global spectrum (same formulae as the full scenario)
-    sc = scenarios.config2(nwavel=nw_total, nlayers=args.layers, nstr=args.nstr, nlos=args.nlos, with_wf=with_wf,
-                           block=(start, count))
+    c = CONFIGS[args.config]
+    nw_total = args.nwavel if args.nwavel > 0 else c["nwavel"]
+    with_wf = c["wf"]
+    starts, counts = zip(*[wavelength_block(nw_total, r, world) for r in range(world)])
+    start, count = starts[rank], counts[rank]
     sk._lib.check(sk._lib.lib().sk_b200_set_device(local_rank), "set_device")
-    _, geo, view, eng, atm = sk.engine_for_scenario(sc)
-    if with_wf:
-        atm.surface.enable_albedo_derivative("wf_albedo")
+    # every rank builds only its own block of the global spectrum (same formulae as the full scenario) and places it at
+    # its offset of full-size caller arrays
+    sc = build_scenario(args.config, nw_total, (start, count))
+    _, geo, view, eng, atm = make_engine(sc, args.config, total_wavelengths=nw_total if world > 1 else None, start=start if world > 1 else 0)
     eng.set_workspace_gb(args.workspace_gb)
     nloc, nleg, nlos, nw = sc.nloc, sc.leg_coeff.shape[0], sc.nlos, sc.nwavel
+    lib = sk._lib.lib()
 
-    # pin the caller-side buffers for the e2e path (the C ABI takes plain host pointers)
-    rad_buf = np.zeros((nw, nlos, 1))
-    pinned = []
-    cudart = torch.cuda.cudart()
-    for arr in (atm.storage.ssa, atm.storage.total_extinction, atm.storage.leg_coeff, atm.storage.solar_irradiance,
-                atm.surface.albedo, rad_buf):
-        rc = cudart.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
-        pinned.append((arr, int(rc) == 0 or "success" in str(rc).lower()))
+    # caller-side result arrays: rank 0 is the caller that ends up holding the whole spectrum
+    shapes = eng.result_shapes(atm)
+    shared = None
+    if world > 1:
+        shared = SharedResult(shapes, rank, f"bench_{os.environ.get('MASTER_PORT', '0')}", barrier)
+        buffers = shared.arrays
+        out_pinned = shared.pinned
+    else:
+        buffers = {k: sk._lib.pinned_empty(s) for k, s in shapes.items()}
+        out_pinned = True
+    # page-lock the caller-side input buffers of this rank's block (the C ABI takes plain host pointers)
+    in_arrays = [atm.storage.ssa, atm.storage.total_extinction, atm.storage.leg_coeff, atm.storage.solar_irradiance,
+                 atm.surface.albedo]
+    registered = []
+    for arr in in_arrays:
+        if lib.sk_b200_host_register(arr.ctypes.data, arr.nbytes) == 0:
+            registered.append(arr)
+    in_pinned = len(registered) == len(in_arrays)
 
-    h2d_bytes = sum(a.nbytes for a in (atm.storage.ssa, atm.storage.total_extinction, atm.storage.leg_coeff,
-                                       atm.storage.solar_irradiance, atm.surface.albedo))
-    d2h_bytes = rad_buf.nbytes
+    per_w_in = 8 * (nloc * (2 + nleg) + 2)
     nwf_out = 0
     if with_wf:
         for mp in sc.mappings.values():
-            h2d_bytes += sum(v.nbytes for v in mp.values() if isinstance(v, np.ndarray))
+            per_w_in += 8 * sum(int(np.prod(v.shape[:-1])) for v in mp.values() if isinstance(v, np.ndarray))
             nwf_out += sc.nloc
         nwf_out += 1
-        d2h_bytes += 8 * nwf_out * nw * nlos
+        per_w_in += 8  # d_brdf
+    per_w_out = 8 * nlos * (1 + nwf_out)
+    h2d_bytes, d2h_bytes = per_w_in * nw_total, per_w_out * nw_total
 
-    # ---- device-resident timing (value)
-    eng.stage(atm, radiance_buffer=rad_buf)
+    # ---- device-resident timing (value): inputs staged once, K solves, CUDA events inside the library
+    eng.stage(atm, start if world > 1 else 0, count, buffers=buffers)
     info = eng.info()
     m_list = list(range(info["num_azimuth"]))
     for _ in range(args.warmup):
@@ -301,66 +478,119 @@ def main():
     barrier()
     sampler.start()
     t0 = time.perf_counter()
-    dev_ms = 0.0
-    per_kernel = {}
-    launches = 0
+    dev_ms, per_kernel, launches = 0.0, {}, 0
     for _ in range(args.steps):
         eng.solve_staged()
         t = eng.timings_ms()
         dev_ms += t["kernels_total"]
-        # weighting functions: adjoint BVP, layer derivatives, cross-layer chain, mapping
         for k in ("optics", "layer", "bvp", "radiance", "wf_adjoint", "wf_layer", "wf_chain", "wf_map"):
             per_kernel[k] = per_kernel.get(k, 0.0) + t.get(k, 0.0)
         launches += eng.kernel_launches()
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
+    wall_ms = reduce_max((time.perf_counter() - t0) * 1e3)
     clocks = sampler.stop()
     dev_ms = reduce_max(dev_ms)
-    wall_ms = reduce_max(wall_ms)
-    units_per_step_all = float(nw_total * nlos)
+    units_per_step = float(nw_total * nlos)
     ms_per_step = dev_ms / args.steps
-    value = units_per_step_all / (ms_per_step * 1e-3)
+    value = units_per_step / (ms_per_step * 1e-3)
     launches_all = int(reduce_sum(launches))
-    check = eng.fetch()["radiance"]
-    assert np.all(np.isfinite(check)) and np.all(check > 0), "non-finite radiance in the bench workload"
 
-    # ---- end to end through the reference-facing call with host buffers (e2e): every step copies the inputs from
-    # (page-locked) host memory, solves, and copies radiances + weighting functions back into page-locked host arrays
-    # that the engine hands out again on the next call (reuse_output_buffers)
-    eng.reuse_output_buffers = True
-    for _ in range(min(args.warmup, 2)):
-        eng.calculate_radiance(atm, rad_buf)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.calculate_radiance(atm, rad_buf)
-    barrier()
-    e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
-    e2e_value = units_per_step_all / (e2e_ms * 1e-3)
-    t_last = eng.timings_ms()
-    e2e_breakdown = {"h2d_ms": t_last["h2d"], "kernels_ms": t_last["kernels_total"], "d2h_ms": t_last["d2h"]}
-    e2e_breakdown["host_ms"] = e2e_ms - sum(e2e_breakdown.values())
+    # ---- end to end (e2e): host buffers in, all results in rank 0's host arrays, inside the timed region
+    gather = None
+    if world == 1:
+        for _ in range(min(args.warmup, 2)):
+            eng.calculate_radiance(atm, buffers=buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            result = eng.calculate_radiance(atm, buffers=buffers)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        t_last = eng.timings_ms()
+        breakdown = {"h2d_ms": t_last["h2d"], "kernels_ms": t_last["kernels_total"], "d2h_ms": t_last["d2h"]}
+        breakdown["host_ms"] = e2e_ms - sum(breakdown.values())
+    else:
+        init_nccl_comm(rank, world)
+        # (a) NCCL gather inside the library: H2D block -> solve -> ncclSend/Recv onto GPU 0 -> one D2H on rank 0
+        def step_nccl():
+            eng.stage(atm, start, count, buffers=buffers)
+            eng.solve_staged()
+            return eng.gather(starts, counts, nw_total, root=0)
+        # (b) direct: every rank's block call writes straight into the caller's shared page-locked arrays
+        def step_direct():
+            return eng.calculate_radiance(atm, buffers=buffers, wavelength_block=(start, count))
+        gather = {}
+        for name, fn in (("nccl", step_nccl), ("direct", step_direct)):
+            for _ in range(min(args.warmup, 2)):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            nccl_ms = d2h_ms = 0.0
+            for _ in range(args.steps):
+                r = fn()
+                if name == "nccl":
+                    nccl_ms += r[1][0]
+                    d2h_ms += r[1][1]
+            barrier()
+            ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
+            gather[name] = {"ms_per_step": ms, "value": units_per_step / (ms * 1e-3)}
+            if name == "nccl":
+                gather[name]["nccl_exchange_ms_max"] = reduce_max(nccl_ms / args.steps)
+                gather[name]["root_d2h_ms"] = reduce_max(d2h_ms / args.steps)
+                gather[name]["bytes_over_nvlink"] = int(per_w_out * (nw_total - counts[0]))
+        best = min(gather, key=lambda k: gather[k]["ms_per_step"])
+        e2e_ms = gather[best]["ms_per_step"]
+        gather["used_for_e2e"] = best
+        gather["limiter"] = ("nccl variant: all results cross GPU 0's single PCIe link after the NVLink exchange; direct variant: "
+                             "every rank's PCIe link carries only its own block")
+        result = {k.replace("wf:", "").replace("surf:", ""): (v if not k.startswith("surf:") else v[0]) for k, v in buffers.items()}
+        breakdown = None
+    e2e_value = units_per_step / (e2e_ms * 1e-3)
+
+    # ---- e2e from pageable caller buffers (what a numpy / ndarray caller hands over without sk_b200_host_alloc)
+    e2e_pageable = None
+    if world == 1:
+        for arr in registered:
+            lib.sk_b200_host_unregister(arr.ctypes.data)
+        registered = []
+        pageable = {k: np.empty(s) for k, s in shapes.items()}
+        eng.calculate_radiance(atm, buffers=pageable)
+        t0 = time.perf_counter()
+        nrep = max(2, min(args.steps, 5))
+        for _ in range(nrep):
+            eng.calculate_radiance(atm, buffers=pageable)
+        ms = (time.perf_counter() - t0) * 1e3 / nrep
+        e2e_pageable = {"value": units_per_step / (ms * 1e-3), "ms_per_step": ms,
+                        "note": "inputs and outputs in pageable host memory (no cudaHostRegister / sk_b200_host_alloc)"}
+        del pageable
+
+    # ---- parity of the timed outputs against the oracle (rank 0's block)
+    threads = os.cpu_count() or 1
+    parity = None
+    if rank == 0:
+        res_local = result
+        if world > 1:   # rank 0's block of the shared full-spectrum arrays
+            res_local = {k: (v[start:start + count] if v.shape[0] == nw_total else v[:, start:start + count]) for k, v in result.items()}
+        parity = parity_sample(sc, args.config, res_local, 12, threads)
+    ok = reduce_max(0.0 if (parity is None or parity["ok"]) else 1.0)
+    if ok != 0.0:
+        raise SystemExit(f"bench.py: timed outputs disagree with the oracle: {parity}")
 
     # ---- roofline of the dominant kernel (FP64 pipe; peak measured live by a DFMA micro-benchmark)
-    reuse = bool(sk._lib.lib().sk_b200_adjoint_reuses_factors(args.nstr // 2, nlos))
-    fm = flop_model(args.nstr, args.layers, nlos, m_list, ngroups=1 if with_wf else 0, adjoint_refactor=not reuse)
-    fast = args.nstr in (4, 8, 16) and os.environ.get("SK_B200_GENERIC", "0") != "1"
+    reuse = bool(lib.sk_b200_adjoint_reuses_factors(sc.nstr // 2, nlos))
+    fm = flop_model(sc.nstr, sc.nloc - 1, nlos, m_list, ngroups=1 if with_wf else 0, adjoint_refactor=not reuse)
+    fast = sc.nstr in (4, 8, 16) and os.environ.get("SK_B200_GENERIC", "0") != "1"
     kernel_names = {
         "layer": "k_eig_setup + k_eig_jacobi + k_layer_post (+ k_los_atten)" if fast else "k_layer_solve",
-        "bvp": "k_bvp_v2 (blocked elimination)" if args.nstr <= 16 else "k_bvp",
-        "wf_adjoint": ("k_bvp_tsolve" if reuse else "k_bvp_adjoint_v2") if args.nstr <= 16 else "k_bvp_adjoint",
+        "bvp": "k_bvp_v2 (blocked elimination)" if sc.nstr <= 16 else "k_bvp",
+        "wf_adjoint": ("k_bvp_tsolve" if reuse else "k_bvp_adjoint_v2") if sc.nstr <= 16 else "k_bvp_adjoint",
         "wf_layer": "k_wf_layer_fast" if fast else "k_wf_layer",
     }
     launches_per_chunk = {"layer": 4 if fast else 1, "bvp": 1, "wf_adjoint": 1, "wf_layer": 1}
     chunk = info["chunk_wavelengths"]
     nchunks = int(np.ceil(nw / chunk))
-    fp64_peak = None
     try:
-        import ctypes as C
-
-        fn = sk._lib.lib().sk_b200_measure_fp64_tflops
-        fn.restype = C.c_double
-        fp64_peak = float(fn())
+        fp64_peak = float(lib.sk_b200_measure_fp64_tflops())
     except Exception:
         fp64_peak = None
     peaks = {}
@@ -384,67 +614,73 @@ def main():
     per_k = {k: kernel_roofline(k) for k in ("layer", "bvp", "wf_adjoint", "wf_layer")}
     per_k = {k: v for k, v in per_k.items() if v}
     if reuse and "wf_adjoint" in per_k:
-        # the transposed solves stream the factors once: bounded by HBM, not by the FP64 pipe
-        by = tsolve_bytes_model(args.nstr, args.layers, nlos, len(m_list))
+        by = tsolve_bytes_model(sc.nstr, sc.nloc - 1, nlos, len(m_list))
         gbs = by * nw * args.steps / (per_kernel["wf_adjoint"] * 1e-3) / 1e9
         per_k["wf_adjoint"]["hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                                       "frac": gbs / hbm_peak, "bytes_per_wavelength": by}
     dom = max(per_k, key=lambda k: per_k[k]["share_of_step"])
     total_flops = fm["total_wf"] if with_wf else fm["total"]
+    alg_bytes = bytes_model(nloc, nleg, nlos, nwf_out, 1 if with_wf else 0)
     roofline = {
         "bound": "fp64", "kernel": per_k[dom]["kernel"], "achieved": per_k[dom]["achieved"], "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": per_k[dom]["frac"],
         "traffic": (NCU_DRAM_BYTES_PER_WAVELENGTH[dom] * (nw / nchunks) / launches_per_chunk[dom]
-                    if (args.nstr, args.layers, nlos, with_wf) == (16, 100, 10, True) else None),
-        "traffic_source": "profiles/ncu_r01_v12_summary.csv (dram bytes per wavelength of the profiled launch x wavelengths per launch)",
+                    if (sc.nstr, sc.nloc - 1, nlos, with_wf) == (16, 100, 10, True) and dom in NCU_DRAM_BYTES_PER_WAVELENGTH else None),
+        "traffic_source": NCU_SOURCE + " (dram bytes per wavelength of the profiled launch x wavelengths per launch)",
         "peak_source": "DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP64 figure)",
         "share_of_step": per_k[dom]["share_of_step"], "avg_launch_ms": per_k[dom]["avg_launch_ms"],
         "flops_per_launch": per_k[dom]["flops_per_launch"],
         "kernels": per_k,
         "whole_step": {"flops_per_wavelength": total_flops,
-                       "achieved_tflops": total_flops * (nw_total / world) / (ms_per_step * 1e-3) / 1e12},
-        "hbm_view": {"bound": "hbm", "achieved": bytes_model(nloc, nleg, nlos, nwf_out) * (nw_total / world) / (ms_per_step * 1e-3) / 1e9,
-                     "peak": hbm_peak, "unit": "GB/s",
+                       "achieved_tflops": total_flops * nw / (ms_per_step * 1e-3) / 1e12,
+                       "frac": (total_flops * nw / (ms_per_step * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None},
+        "hbm_view": {"bound": "hbm", "achieved": alg_bytes * nw / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "algorithmic_bytes_per_wavelength": alg_bytes,
                      "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
     }
     roofline["hbm_view"]["frac"] = roofline["hbm_view"]["achieved"] / hbm_peak
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1] shape: pseudo-spherical DO, {args.nstr} streams, {args.layers} layers, "
-                               f"Rayleigh+aerosol+O3/NO2, {nlos} ground-viewing LOS, {args.nwavel} wavelengths per GPU, "
-                               + ("weighting functions w.r.t. O3 VMR, NO2 VMR, aerosol extinction (3 x 101 outputs) and albedo"
-                                  if with_wf else "radiances only"),
-                   "wavelengths_per_gpu": args.nwavel, "azimuth_orders": len(m_list), "chunk_wavelengths": chunk,
+        "config": {"workload": f"{c['label']}: {c['text']}", "total_wavelengths": nw_total,
+                   "wavelengths_per_gpu": [int(v) for v in counts], "azimuth_orders": len(m_list), "chunk_wavelengths": chunk,
+                   "sharding": "contiguous wavelength blocks, one process per GPU, no exchange inside the solve",
                    "l2": "inputs+workspace per step far exceed the 126 MB L2 (no flush needed)",
                    "wall_ms_per_step": wall_ms / args.steps},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                "ms_per_step": e2e_ms, "pinned": all(ok for _, ok in pinned), "breakdown": e2e_breakdown},
+                "ms_per_step": e2e_ms, "pinned": bool(in_pinned and out_pinned), "breakdown": breakdown, "gather": gather,
+                "pageable": e2e_pageable},
         "gpu_launches": launches_all,
         "kernel_ms_per_step": {k: v / args.steps for k, v in per_kernel.items()},
         "roofline": roofline,
+        "parity_check": parity,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        time_oracle(sc, min(args.cpu_sample, cores), cores)
-        v, dt = time_oracle(sc, args.cpu_sample, cores)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_sample} wavelengths x {nlos} LOS of the same atmosphere, oracle port "
-                                          f"with OpenMP over wavelengths, {dt:.1f} s; VALUES ONLY, i.e. an upper bound for the "
-                                          f"CPU path with weighting functions: the reference's default (do_backprop = false, "
-                                          f"cpp/lib/config/config.cpp:14) linearises in forward mode like the port "
-                                          f"(with_wf_forward_mode below), its optional reverse mode costs ~2.5-3x values only"}
-        if args.cpu_wf_sample > 0:
-            v2, dt2 = time_oracle(sc, args.cpu_wf_sample, cores, with_wf=True)
-            line["cpu_baseline"]["with_wf_forward_mode"] = {"value": v2, "sample": f"{args.cpu_wf_sample} wavelengths, {dt2:.1f} s"}
+        scd = build_scenario_decimated(args.config, nw_total, args.cpu_sample) if nw_total > 4 * args.cpu_sample else sc
+        cpu_arm(scd, args.config, min(args.cpu_sample, 2 * threads), threads)
+        v, dt, desc = cpu_arm(scd, args.config, args.cpu_sample, threads)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        del result, buffers
+        others = {}
+        for name in ("c2", "c1", "c3"):
+            if name == args.config:
+                continue
+            try:
+                others[name] = quick_config(name, 2, 1, local_rank, threads)
+            except Exception as ex:  # a workload whose path is not built yet must not hide the headline
+                others[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        line["other_configs"] = others
     if rank == 0:
         print(json.dumps(line), flush=True)
-    for arr, ok in pinned:
-        if ok:
-            cudart.cudaHostUnregister(arr.ctypes.data)
+    for arr in registered:
+        lib.sk_b200_host_unregister(arr.ctypes.data)
+    if shared is not None:
+        lib.sk_b200_comm_destroy()
+        shared.close(barrier)
     if world > 1:
         dist.destroy_process_group()
 

@@ -325,6 +325,18 @@ long long sk_b200_engine_kernel_launches(Engine* engine);
 /* number of azimuth orders solved and wavelengths per workspace chunk (diagnostics) */
 int sk_b200_engine_info(Engine* engine, int* num_azimuth, int* chunk_wavelengths, double* workspace_mb_per_wavelength);
 int sk_b200_engine_set_workspace_gb(Engine* engine, double gb);
+/* Wavelength-sharded runs (one process per GPU, contiguous wavelength blocks, cpp/lib/engine/engine.cpp:610-622 upstream
+ * shards the same way over host threads): the only exchange is the final gather of radiances and weighting functions
+ * onto one rank over NCCL (NVLink / NVSwitch).  Rank 0 obtains a 128-byte id, the host program hands it to every rank
+ * (any side channel), every rank calls sk_b200_comm_init on its device.  After sk_b200_engine_solve_staged on every
+ * rank, sk_b200_engine_gather_output (collective) leaves the full-spectrum results in `root_output` on rank `root`
+ * (radiance [nw_total * nlos], derivative memory assigned for the same mapping names as the staged outputs);
+ * block_start / block_count [world] give every rank's wavelength block; ms_out[2] = {NCCL exchange, D2H} on this rank. */
+int sk_b200_comm_unique_id(char* id, int nbytes);
+int sk_b200_comm_init(const char* id, int rank, int world);
+int sk_b200_comm_destroy();
+int sk_b200_engine_gather_output(Engine* engine, OutputC* root_output, int root, const int* block_start,
+                                 const int* block_count, int nw_total, double* ms_out);
 /* DFMA micro-benchmark on the current device: the FP64 roofline denominator (TFLOP/s) */
 double sk_b200_measure_fp64_tflops();
 /* 1 when the adjoint boundary-value solve of an (N = num_streams / 2, nlos) problem reuses the forward LU factors
@@ -333,6 +345,9 @@ int sk_b200_adjoint_reuses_factors(int n_half_streams, int nlos);
 /* page-locked host memory for caller-side buffers (falls back to malloc without a CUDA device) */
 void* sk_b200_host_alloc(size_t nbytes);
 void sk_b200_host_free(void* p);
+/* page-lock / release caller-owned host memory in place (cudaHostRegister, portable) */
+int sk_b200_host_register(void* p, size_t nbytes);
+int sk_b200_host_unregister(void* p);
 /* test/debug: copy a named workspace array of the last solved chunk (names: see disco_engine.cu) */
 long long sk_b200_engine_debug_copy(Engine* engine, const char* name, double* host, long long max_n);
 

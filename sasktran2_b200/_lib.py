@@ -118,6 +118,13 @@ def _declare(lib):
     f("sk_b200_measure_fp64_tflops", d)
     f("sk_b200_adjoint_reuses_factors", i, i, i)
     f("sk_b200_engine_debug_copy", C.c_longlong, vp, C.c_char_p, c_double_p, C.c_longlong)
+    f("sk_b200_host_register", i, vp, C.c_size_t)
+    f("sk_b200_host_unregister", i, vp)
+    f("sk_b200_comm_unique_id", i, C.c_char_p, i)
+    f("sk_b200_comm_init", i, C.c_char_p, i, i)
+    f("sk_b200_comm_destroy", i)
+    f("sk_b200_engine_gather_output", i, vp, vp, i, c_int_p, c_int_p, i, c_double_p)
+    f("sk_viewing_geometry_add_tangent_altitude_solar", i, vp, d, d, d, d)
     f("sk_b200_host_alloc", vp, C.c_size_t)
     f("sk_b200_host_free", None, vp)
 

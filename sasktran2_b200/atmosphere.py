@@ -248,24 +248,31 @@ class Atmosphere:
             pass
 
     @classmethod
-    def from_scenario(cls, scenario, model_geometry, config, calculate_derivatives=None):
-        """Fill an atmosphere from a sasktran2_b200.scenarios.Scenario (synthetic inputs)."""
+    def from_scenario(cls, scenario, model_geometry, config, calculate_derivatives=None, total_wavelengths=None,
+                      wavelength_start=0):
+        """Fill an atmosphere from a sasktran2_b200.scenarios.Scenario (synthetic inputs).
+
+        With `total_wavelengths` the storage is sized for a full spectrum of which `scenario` is the block starting at
+        `wavelength_start` (one rank of a wavelength-sharded run holds the caller's array shapes but only fills - and
+        only ever reads - its own block; untouched pages of the zero-initialised arrays cost nothing)."""
         wf = bool(scenario.mappings) if calculate_derivatives is None else calculate_derivatives
-        atm = cls(model_geometry, config, numwavel=scenario.nwavel, calculate_derivatives=wf,
+        nw = scenario.nwavel if total_wavelengths is None else int(total_wavelengths)
+        sl = slice(wavelength_start, wavelength_start + scenario.nwavel)
+        atm = cls(model_geometry, config, numwavel=nw, calculate_derivatives=wf,
                   num_legendre=scenario.leg_coeff.shape[0])
-        atm.storage.ssa[:] = scenario.ssa
-        atm.storage.total_extinction[:] = scenario.total_extinction
-        atm.storage.leg_coeff[:] = scenario.leg_coeff
-        atm.storage.solar_irradiance[:] = scenario.solar_irradiance
-        atm.surface.albedo[:] = scenario.albedo
+        atm.storage.ssa[:, sl] = scenario.ssa
+        atm.storage.total_extinction[:, sl] = scenario.total_extinction
+        atm.storage.leg_coeff[:, :, sl] = scenario.leg_coeff
+        atm.storage.solar_irradiance[sl] = scenario.solar_irradiance
+        atm.surface.albedo[sl] = scenario.albedo
         if wf:
             for name, mp in scenario.mappings.items():
                 m = atm.storage.get_derivative_mapping(name)
-                m.d_extinction[:] = mp["d_extinction"]
-                m.d_ssa[:] = mp["d_ssa"]
+                m.d_extinction[:, sl] = mp["d_extinction"]
+                m.d_ssa[:, sl] = mp["d_ssa"]
                 if "d_legendre" in mp:
-                    m.d_leg_coeff[:] = mp["d_legendre"]
-                    m.scat_factor[:] = mp["scat_factor"]
+                    m.d_leg_coeff[:, :, sl] = mp["d_legendre"]
+                    m.scat_factor[:, sl] = mp["scat_factor"]
                 if mp.get("interpolator") is not None:
                     m.interpolator = mp["interpolator"]
         return atm

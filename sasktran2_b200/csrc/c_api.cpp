@@ -892,6 +892,68 @@ long long sk_b200_engine_debug_copy(Engine* e, const char* name, double* host, l
     if (!e || !e->dev || !name || !host) return -1;
     return (long long)e->dev->debug_copy(name, host, (size_t)max_n);
 }
+// ---- wavelength-sharded runs: one process per GPU, final gather over NCCL (disco_comm.cpp) ----
+static std::unique_ptr<disco::Comm> g_comm;
+int sk_b200_comm_unique_id(char* id, int nbytes) {
+    if (!id || nbytes < (int)sizeof(disco::NcclUniqueId)) return fail(-2, "sk_b200_comm_unique_id: need a 128-byte buffer");
+    try {
+        disco::NcclUniqueId u;
+        disco::comm_unique_id(&u);
+        std::memcpy(id, u.internal, sizeof(u.internal));
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+int sk_b200_comm_init(const char* id, int rank, int world) {
+    if (!id) return fail(-1, "sk_b200_comm_init: null id");
+    try {
+        disco::NcclUniqueId u;
+        std::memcpy(u.internal, id, sizeof(u.internal));
+        g_comm.reset();
+        g_comm = std::make_unique<disco::Comm>(u, rank, world);
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+int sk_b200_comm_destroy() {
+    g_comm.reset();
+    return 0;
+}
+int sk_b200_engine_gather_output(Engine* e, OutputC* root_output, int root, const int* block_start, const int* block_count,
+                                 int nw_total, double* ms_out) {
+    if (!e || !e->dev) return fail(-1, "engine handle is null");
+    if (!g_comm) return fail(-1, "sk_b200_comm_init must be called first");
+    if (!block_start || !block_count) return fail(-1, "sk_b200_engine_gather_output: null block tables");
+    std::lock_guard<std::mutex> lock(e->mtx);
+    try {
+        const int nlos = (int)e->viewing->rays.size();
+        std::vector<double*> maps, surfs;
+        double* rad = nullptr;
+        if (g_comm->rank() == root) {
+            if (!root_output || !root_output->radiance) return fail(-1, "gather root needs an output handle");
+            if ((long long)root_output->nrad != (long long)nw_total * nlos)
+                return fail(-2, "gather root output has the wrong size (expected nw_total * nlos)");
+            rad = root_output->radiance;
+            for (auto& kv : root_output->derivs) {
+                if ((long long)kv.second.nrad != (long long)nw_total * nlos) return fail(-2, "gather root derivative memory has the wrong size");
+                maps.push_back(kv.second.ptr);
+            }
+            for (auto& kv : root_output->surface_derivs) surfs.push_back(kv.second.ptr);
+        }
+        double ms[2] = {0.0, 0.0};
+        e->dev->gather_to_root(*g_comm, root, block_start, block_count, nw_total, rad, maps.data(), surfs.data(), ms);
+        if (ms_out) {
+            ms_out[0] = ms[0];
+            ms_out[1] = ms[1];
+        }
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+
 int sk_b200_adjoint_reuses_factors(int n_half_streams, int nlos) { return disco::adjoint_reuses_factors(n_half_streams, nlos) ? 1 : 0; }
 double sk_b200_measure_fp64_tflops() { return disco::measure_fp64_tflops(); }
 void* sk_b200_host_alloc(size_t nbytes) {
@@ -902,6 +964,27 @@ void* sk_b200_host_alloc(size_t nbytes) {
     }
 }
 void sk_b200_host_free(void* p) { host_free(p); }
+// Page-lock caller-owned host memory in place (numpy / ndarray buffers, shared-memory segments): copies to and from it
+// then run at PCIe speed and overlap with kernels.  Returns 0, or -3 when the range cannot be registered.
+int sk_b200_host_register(void* p, size_t nbytes) {
+    if (!p || nbytes == 0) return -1;
+    cudaError_t err = cudaHostRegister(p, nbytes, cudaHostRegisterPortable);
+    if (err == cudaErrorHostMemoryAlreadyRegistered) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(-3, std::string("cudaHostRegister: ") + cudaGetErrorString(err));
+    }
+    return 0;
+}
+int sk_b200_host_unregister(void* p) {
+    if (!p) return -1;
+    cudaError_t err = cudaHostUnregister(p);
+    (void)cudaGetLastError();
+    return err == cudaSuccess ? 0 : -3;
+}
 int sk_b200_engine_set_workspace_gb(Engine* e, double gb) {
     if (!e || !e->dev) return -1;
     e->dev->set_workspace_gb(gb);

@@ -135,6 +135,7 @@ DeviceEngine::~DeviceEngine() {
     free_wf_inputs();
     free_inputs();
     free_workspace();
+    if (d_gather) cudaFree(d_gather);
     for (void* p : {(void*)d_mu, (void*)d_wt, (void*)d_lp_mu, (void*)d_lp_csz, (void*)d_lp_los, (void*)d_los_mu, (void*)d_wf_tab,
                     (void*)d_los_cosmphi, (void*)d_layer_dh, (void*)d_interp_w, (void*)d_interp_idx,
                     (void*)d_chapman, (void*)d_mlist, (void*)d_status})
@@ -583,6 +584,116 @@ void DeviceEngine::fetch(double* radiance_host) {
         CUDA_OK(cudaEventElapsedTime(&ms, m_ev[0], m_ev[1]));
         m_ms[T_H2D] = ms;
     }
+}
+
+// Final gather of a wavelength-sharded solve: every rank holds its block's results on its device
+// (d_radiance [nw_r][nlos], per mapping [nout][nw_r][nlos], per surface mapping [nw_r][nlos]).  One NCCL group: the
+// other ranks send their arrays to the root over NVLink, the root receives them back to back into one staging buffer
+// and scatters every block into the caller's full-spectrum host arrays (strided rows for the weighting functions).
+void DeviceEngine::gather_to_root(Comm& comm, int root, const int* block_start, const int* block_count, int nw_total,
+                                  double* radiance_host, double* const* mapping_host, double* const* surface_host,
+                                  double ms_out[2]) {
+    CUDA_OK(cudaSetDevice(m_device));
+    const int rank = comm.rank(), world = comm.world();
+    const size_t nlos = (size_t)std::max(m_plan.nlos, 0);
+    if (block_count[rank] != m_nw) throw std::runtime_error("gather_to_root: this rank's block size differs from the staged range");
+    size_t per_w = nlos;  // doubles per wavelength over all outputs
+    if (m_wf_on) {
+        for (auto& dm : m_maps) per_w += (size_t)dm.host.nout * nlos;
+        per_w += m_surfs.size() * nlos;
+    }
+    CUDA_OK(cudaEventRecord(m_ev[4], m_stream));
+    if (rank != root) {
+        comm.group_start();
+        comm.send(d_radiance, (size_t)m_nw * nlos, root, m_stream);
+        if (m_wf_on) {
+            for (auto& dm : m_maps) comm.send(dm.out, (size_t)dm.host.nout * m_nw * nlos, root, m_stream);
+            for (auto& ds : m_surfs) comm.send(ds.out, (size_t)m_nw * nlos, root, m_stream);
+        }
+        comm.group_end();
+        CUDA_OK(cudaEventRecord(m_ev[5], m_stream));
+        CUDA_OK(cudaStreamSynchronize(m_stream));
+        float ms = 0;
+        CUDA_OK(cudaEventElapsedTime(&ms, m_ev[4], m_ev[5]));
+        ms_out[0] = ms;
+        ms_out[1] = 0.0;
+        return;
+    }
+    size_t others = 0;
+    for (int r = 0; r < world; ++r)
+        if (r != root) others += (size_t)block_count[r];
+    if (others * per_w > m_cap_gather) {
+        if (d_gather) cudaFree(d_gather);
+        d_gather = dalloc<double>(others * per_w);
+        m_cap_gather = others * per_w;
+    }
+    // staging layout per source rank: radiance | mapping 0 | mapping 1 | ... | surface 0 | ...
+    comm.group_start();
+    {
+        double* p = d_gather;
+        for (int r = 0; r < world; ++r) {
+            if (r == root) continue;
+            const size_t n = (size_t)block_count[r];
+            comm.recv(p, n * nlos, r, m_stream);
+            p += n * nlos;
+            if (m_wf_on) {
+                for (auto& dm : m_maps) {
+                    comm.recv(p, (size_t)dm.host.nout * n * nlos, r, m_stream);
+                    p += (size_t)dm.host.nout * n * nlos;
+                }
+                for (size_t i = 0; i < m_surfs.size(); ++i) {
+                    comm.recv(p, n * nlos, r, m_stream);
+                    p += n * nlos;
+                }
+            }
+        }
+    }
+    comm.group_end();
+    CUDA_OK(cudaEventRecord(m_ev[5], m_stream));
+    // device -> host: every block into its rows of the full-spectrum arrays
+    const size_t pitch = sizeof(double) * (size_t)nw_total * nlos;
+    auto put = [&](int r, const double* rad, const double* const* maps, const double* const* surfs) {
+        const size_t n = (size_t)block_count[r], off = (size_t)block_start[r] * nlos, width = sizeof(double) * n * nlos;
+        if (n == 0) return;
+        CUDA_OK(cudaMemcpyAsync(radiance_host + off, rad, width, cudaMemcpyDeviceToHost, m_stream));
+        if (!m_wf_on) return;
+        for (size_t i = 0; i < m_maps.size(); ++i)
+            CUDA_OK(cudaMemcpy2DAsync(mapping_host[i] + off, pitch, maps[i], width, width, m_maps[i].host.nout,
+                                      cudaMemcpyDeviceToHost, m_stream));
+        for (size_t i = 0; i < m_surfs.size(); ++i)
+            CUDA_OK(cudaMemcpyAsync(surface_host[i] + off, surfs[i], width, cudaMemcpyDeviceToHost, m_stream));
+    };
+    std::vector<const double*> mp(m_maps.size()), sp(m_surfs.size());
+    for (size_t i = 0; i < m_maps.size(); ++i) mp[i] = m_maps[i].out;
+    for (size_t i = 0; i < m_surfs.size(); ++i) sp[i] = m_surfs[i].out;
+    put(root, d_radiance, mp.data(), sp.data());
+    {
+        const double* p = d_gather;
+        for (int r = 0; r < world; ++r) {
+            if (r == root) continue;
+            const size_t n = (size_t)block_count[r];
+            const double* rad = p;
+            p += n * nlos;
+            if (m_wf_on) {
+                for (size_t i = 0; i < m_maps.size(); ++i) {
+                    mp[i] = p;
+                    p += (size_t)m_maps[i].host.nout * n * nlos;
+                }
+                for (size_t i = 0; i < m_surfs.size(); ++i) {
+                    sp[i] = p;
+                    p += n * nlos;
+                }
+            }
+            put(r, rad, mp.data(), sp.data());
+        }
+    }
+    CUDA_OK(cudaEventRecord(m_ev[6], m_stream));
+    CUDA_OK(cudaStreamSynchronize(m_stream));
+    float a = 0, b = 0;
+    CUDA_OK(cudaEventElapsedTime(&a, m_ev[4], m_ev[5]));
+    CUDA_OK(cudaEventElapsedTime(&b, m_ev[5], m_ev[6]));
+    ms_out[0] = a;
+    ms_out[1] = b;
 }
 
 // One call = copy in, solve, copy out, with the copies of all but one chunk hidden behind the kernels

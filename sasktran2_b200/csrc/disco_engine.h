@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 
+#include "disco_comm.h"
 #include "disco_kernels.cuh"
 #include "disco_plan.h"
 
@@ -71,6 +72,13 @@ class DeviceEngine {
     void fetch(double* radiance_host);
     // stage + solve + fetch
     void calculate(const AtmosphereArrays& atm, int w0, int nw, double* radiance_host, const WfRequest* wf = nullptr);
+    // Wavelength-sharded solve: after solve_staged() on every rank, collect the results of all ranks on `root` over
+    // NCCL and write them into the root's full-spectrum host arrays (radiance [nw_total][nlos]; one
+    // [nout][nw_total][nlos] array per mapping in the order of the staged request; one [nw_total][nlos] per surface
+    // mapping).  block_start / block_count: the wavelength block of every rank.  Host pointers are read on `root` only.
+    // Returns the milliseconds spent in (NCCL exchange, device -> host copies) on this rank.
+    void gather_to_root(Comm& comm, int root, const int* block_start, const int* block_count, int nw_total,
+                        double* radiance_host, double* const* mapping_host, double* const* surface_host, double ms_out[2]);
     bool wf_active() const { return m_wf_on; }
     bool fast_path() const { return m_fast; }
     // test/debug: copy a workspace array of the LAST chunk to the host; returns the number of doubles copied
@@ -141,6 +149,9 @@ class DeviceEngine {
     bool m_ws_wf = false;
     int m_ws_ngroups = 0;     // scattering groups the workspace was sized for (lay_dbeta, wf_loc, wf_native)
     bool m_fast = false;      // register-resident layer solve (disco_fast*.cuh)
+    // staging of the other ranks' results on the gather root
+    double* d_gather = nullptr;
+    size_t m_cap_gather = 0;
     // chunk workspace
     int m_ws_chunk = 0;
     std::vector<void*> m_ws_ptrs;

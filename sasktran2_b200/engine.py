@@ -43,6 +43,7 @@ class Engine:
         # pipelines that consume a result before asking for the next one (bench.py's e2e loop).
         self.reuse_output_buffers = False
         self._pool = {}
+        self._given = None
 
     def __del__(self):
         try:
@@ -54,6 +55,10 @@ class Engine:
 
     # ---- the reference call -------------------------------------------------------------------------
     def _buffer(self, key, shape):
+        if self._given is not None and key in self._given:   # caller-owned result arrays (e.g. shared memory)
+            buf = self._given[key]
+            assert buf.shape == tuple(shape) and buf.flags["C_CONTIGUOUS"] and buf.dtype == np.float64, (key, buf.shape, shape)
+            return buf
         if self.reuse_output_buffers:
             buf = self._pool.get(key)
             if buf is None or buf.shape != tuple(shape):
@@ -63,7 +68,21 @@ class Engine:
         buf[...] = 0.0
         return buf
 
-    def _make_output(self, atmosphere, radiance_buffer=None):
+    def result_shapes(self, atmosphere) -> dict:
+        """Shapes of the arrays a call fills, keyed like the `buffers` argument of calculate_radiance / stage."""
+        nw, nlos = atmosphere.num_wavel, self._viewing_geometry.num_rays
+        shapes = {"radiance": (nw, nlos, 1)}
+        if atmosphere.calculate_derivatives and self._config.wf_enabled:
+            for name in atmosphere.storage.derivative_mapping_names:
+                shapes["wf:" + name] = (atmosphere.storage.get_derivative_mapping(name).num_output, nw, nlos, 1)
+            for name in atmosphere.surface._mapping_names:
+                shapes["surf:" + name] = (1, nw, nlos, 1)
+        return shapes
+
+    def _make_output(self, atmosphere, radiance_buffer=None, buffers=None):
+        self._given = buffers
+        if buffers is not None and radiance_buffer is None:
+            radiance_buffer = buffers.get("radiance")
         nw = atmosphere.num_wavel
         nlos = self._viewing_geometry.num_rays
         rad = radiance_buffer if radiance_buffer is not None else self._buffer("radiance", (nw, nlos, 1))
@@ -91,11 +110,24 @@ class Engine:
                 res["_" + name + "_buf"] = buf
         return out, res
 
-    def calculate_radiance(self, atmosphere, radiance_buffer=None) -> Result:
-        out, res = self._make_output(atmosphere, radiance_buffer)
+    def calculate_radiance(self, atmosphere, radiance_buffer=None, buffers=None, wavelength_block=None) -> Result:
+        """sasktran2.Engine.calculate_radiance.  `buffers` (optional): caller-owned result arrays keyed as in
+        result_shapes().  `wavelength_block = (start, count)` solves only that block of the spectrum and writes it at
+        its place in the full-size result arrays: the reference's Rayon entry points
+        (sk_engine_calculate_radiance(only_initialize = 1) + sk_engine_calculate_radiance_block_thread,
+        rust/sasktran2-rs/src/bindings/engine.rs:314-395), which is also how the ranks of a wavelength-sharded run
+        fill one shared result."""
+        out, res = self._make_output(atmosphere, radiance_buffer, buffers)
         try:
-            rc = _lib.lib().sk_engine_calculate_radiance(self._engine, atmosphere.internal_object(), out, 0)
-            _lib.check(rc, "sk_engine_calculate_radiance")
+            if wavelength_block is None:
+                rc = _lib.lib().sk_engine_calculate_radiance(self._engine, atmosphere.internal_object(), out, 0)
+                _lib.check(rc, "sk_engine_calculate_radiance")
+            else:
+                rc = _lib.lib().sk_engine_calculate_radiance(self._engine, atmosphere.internal_object(), out, 1)
+                _lib.check(rc, "sk_engine_calculate_radiance(only_initialize)")
+                rc = _lib.lib().sk_engine_calculate_radiance_block_thread(self._engine, out, int(wavelength_block[0]),
+                                                                          int(wavelength_block[1]), 0)
+                _lib.check(rc, "sk_engine_calculate_radiance_block_thread")
         finally:
             _lib.lib().sk_output_destroy(out)
         if atmosphere.wavelengths_nm is not None:
@@ -103,12 +135,13 @@ class Engine:
         return res
 
     # ---- device-resident extension (bench / pipelines that keep the atmosphere on the GPU) -----------
-    def stage(self, atmosphere, wavelength_start: int = 0, wavelength_count: int = -1, radiance_buffer=None) -> None:
+    def stage(self, atmosphere, wavelength_start: int = 0, wavelength_count: int = -1, radiance_buffer=None,
+              buffers=None) -> None:
         """Copy the atmosphere (and its derivative mappings when weighting functions are on) to the device."""
         self._keepalive = atmosphere
         if self._staged_out is not None:
             _lib.lib().sk_output_destroy(self._staged_out[0])
-        self._staged_out = self._make_output(atmosphere, radiance_buffer)
+        self._staged_out = self._make_output(atmosphere, radiance_buffer, buffers)
         _lib.check(_lib.lib().sk_b200_engine_stage_atmosphere(self._engine, atmosphere.internal_object(),
                                                               self._staged_out[0], wavelength_start, wavelength_count),
                    "stage")
@@ -121,6 +154,18 @@ class Engine:
         out, res = self._staged_out
         _lib.check(_lib.lib().sk_b200_engine_fetch_output(self._engine, out), "fetch")
         return res
+
+    def gather(self, block_starts, block_counts, nw_total: int, root: int = 0):
+        """Collective of a wavelength-sharded run (sk_b200_comm_init on every rank first): after solve_staged() on every
+        rank, collect all blocks on `root` over NCCL into the result arrays given to stage().  Returns
+        (result on root / None elsewhere, (nccl_ms, d2h_ms) of this rank)."""
+        out, res = self._staged_out
+        starts = (C.c_int * len(block_starts))(*[int(v) for v in block_starts])
+        counts = (C.c_int * len(block_counts))(*[int(v) for v in block_counts])
+        ms = np.zeros(2)
+        _lib.check(_lib.lib().sk_b200_engine_gather_output(self._engine, out, int(root), starts, counts, int(nw_total),
+                                                           _lib.dptr(ms)), "gather")
+        return res, (float(ms[0]), float(ms[1]))
 
     def timings_ms(self) -> dict:
         buf = np.zeros(len(TIMING_NAMES))

@@ -61,3 +61,83 @@ def gather_wavelength_blocks(local: np.ndarray, nwavel: int, wavelength_axis: in
         return np.moveaxis(full, 0, wavelength_axis)
     dist.gather(buf, None, dst=dst)
     return None
+
+
+def init_nccl_comm(rank: int, world: int) -> None:
+    """Create the library's NCCL communicator on every rank of an initialised torch.distributed job: rank 0 draws the
+    128-byte NCCL id (sk_b200_comm_unique_id), torch.distributed only carries it to the other ranks."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(_lib.lib().sk_b200_comm_unique_id(buf, 128), "comm_unique_id")
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().tolist())
+    _lib.check(_lib.lib().sk_b200_comm_init(raw, int(rank), int(world)), "comm_init")
+
+
+class SharedResult:
+    """Result arrays of one spectrum in POSIX shared memory, visible to every rank of a one-box job: rank 0 is "the
+    caller" that ends up holding radiances and weighting functions; every rank writes its wavelength block straight
+    into them (N concurrent device -> host copies into disjoint slices of one buffer).  The
+    segment is page-locked in every process (sk_b200_host_register) so that the copies run at PCIe speed."""
+
+    def __init__(self, shapes: dict, rank: int, tag: str, barrier, pin: bool = True):
+        from multiprocessing import shared_memory
+
+        from . import _lib
+
+        self.rank = rank
+        self._pinned = False
+        sizes = {k: int(np.prod(s)) * 8 for k, s in shapes.items()}
+        total = sum(sizes.values())
+        name = f"sk_b200_{tag}"
+        if rank == 0:
+            try:
+                old = shared_memory.SharedMemory(name=name)
+                old.close()
+                old.unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=max(total, 8))
+        barrier()
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name)
+        self.arrays, off = {}, 0
+        for k, s in shapes.items():
+            self.arrays[k] = np.ndarray(s, dtype=np.float64, buffer=self.shm.buf, offset=off)
+            off += sizes[k]
+        self._base = np.ndarray((max(total, 8),), dtype=np.uint8, buffer=self.shm.buf)
+        if pin:
+            rc = _lib.lib().sk_b200_host_register(self._base.ctypes.data, self._base.nbytes)
+            self._pinned = rc == 0
+        barrier()
+
+    @property
+    def pinned(self) -> bool:
+        return self._pinned
+
+    def close(self, barrier) -> None:
+        from . import _lib
+
+        if self._pinned:
+            _lib.lib().sk_b200_host_unregister(self._base.ctypes.data)
+        self.arrays = {}
+        self._base = None
+        barrier()
+        try:
+            self.shm.close()
+        except BufferError:
+            pass
+        if self.rank == 0:
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass

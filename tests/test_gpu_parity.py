@@ -285,9 +285,12 @@ def test_cuda_weighting_functions_match_finite_differences_of_cuda_radiances():
         numeric = np.zeros_like(analytic)
         base = (k_aer0, k_abs0)
         which = 0 if species == "aer" else 1
+        k_total = build(k_aer0, k_abs0)[0]
         for q in range(z.size):
             for w in range(nwavel):
-                h = 1e-4 * base[which][q, w]
+                # step in units of the local TOTAL extinction: the species' own amount is ~1e-13 at 60 km, a step of
+                # 1e-4 of it would be lost in the rounding of the radiances
+                h = 1e-4 * k_total[q, w]
                 up = [b.copy() for b in base]
                 dn = [b.copy() for b in base]
                 up[which][q, w] += h

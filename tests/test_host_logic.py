@@ -232,3 +232,61 @@ def test_two_rank_gloo_sharding_and_gather():
     for p in procs:
         p.join(timeout=60)
     assert ok == (True, True)
+
+
+def _shared_result_worker(rank, world, port, nwavel, q):
+    import os
+
+    import torch.distributed as dist
+
+    import sasktran2_b200 as sk
+    from sasktran2_b200 import scenarios
+    from sasktran2_b200.parallel import SharedResult, wavelength_block
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    start, count = wavelength_block(nwavel, rank, world)
+    # every rank builds its block and places it in full-size caller arrays (what bench.py / a sharded host program does)
+    blk = scenarios.config2(nwavel=nwavel, nlayers=6, nstr=4, nlos=2, with_wf=True, block=(start, count))
+    cfg = sk.Config()
+    cfg.num_streams = 4
+    geo = sk.Geometry1D(blk.cos_sza, 0.0, blk.earth_radius, blk.altitudes, sk.InterpolationMethod(blk.interp),
+                        sk.GeometryType(blk.geotype))
+    atm = sk.Atmosphere.from_scenario(blk, geo, cfg, total_wavelengths=nwavel, wavelength_start=start)
+    full = scenarios.config2(nwavel=nwavel, nlayers=6, nstr=4, nlos=2, with_wf=True)
+    ok_place = (np.array_equal(atm.storage.ssa[:, start:start + count], full.ssa[:, start:start + count]) and
+                np.array_equal(atm.storage.get_derivative_mapping("wf_o3_vmr").d_ssa[:, start:start + count],
+                               full.mappings["wf_o3_vmr"]["d_ssa"][:, start:start + count]) and
+                not atm.storage.ssa[:, :start].any() and not atm.storage.ssa[:, start + count:].any())
+    shapes = {"radiance": (nwavel, 2, 1), "wf:wf_o3_vmr": (7, nwavel, 2, 1)}
+    shared = SharedResult(shapes, rank, f"test_{port}", dist.barrier, pin=False)
+    # stand-in for the per-rank block solve: every rank writes its block of the caller's arrays
+    shared.arrays["radiance"][start:start + count] = full.albedo[start:start + count, None, None] + np.arange(start, start + count)[:, None, None]
+    shared.arrays["wf:wf_o3_vmr"][:, start:start + count] = full.ssa[:, start:start + count, None, None]
+    dist.barrier()
+    if rank == 0:
+        ok_rad = np.array_equal(shared.arrays["radiance"][:, 0, 0], full.albedo + np.arange(nwavel))
+        ok_wf = np.array_equal(shared.arrays["wf:wf_o3_vmr"][:, :, 1, 0], full.ssa)
+        q.put((bool(ok_place), bool(ok_rad), bool(ok_wf)))
+    else:
+        q.put((bool(ok_place),))
+    shared.close(dist.barrier)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shared_result_arrays():
+    """world_size-2 run of the sharded end-to-end path's host side on CPU (gloo): block placement in full-size caller
+    arrays, result arrays in shared memory that rank 0 (the caller) ends up holding completely."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29741
+    procs = [ctx.Process(target=_shared_result_worker, args=(r, 2, port, 13, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(all(g) for g in got), got

@@ -254,7 +254,7 @@ def parity_sample(sc, cfg_name, result, nsample, threads):
     tests/wf_checks.py holds the full rule set incl. the reference-formula variant)."""
     pick = np.unique(np.linspace(0, sc.nwavel - 1, nsample).astype(int))
     ora, _ = run_oracle(sc, pick, threads, cfg_name, stable=True)
-    rad = result["radiance"][pick, :, 0]
+    rad = result["radiance"][..., 0][pick]
     out = {"wavelengths": int(pick.size), "radiance_max_rel_diff": float(np.max(np.abs(rad / ora["radiance"] - 1.0))),
            "radiance_tol": 1e-9}
     ok = out["radiance_max_rel_diff"] < 1e-9
@@ -262,7 +262,7 @@ def parity_sample(sc, cfg_name, result, nsample, threads):
         wf = oracle_weighting_functions(sc, pick, ora["native"])
         errs = {}
         for name in ("wf_o3_vmr", "wf_no2_vmr", "wf_aerosol_extinction", "wf_albedo"):
-            got = result[name][:, pick, :, 0] if name != "wf_albedo" else result[name][pick, :, 0]
+            got = result[name][..., 0][:, pick] if name != "wf_albedo" else result[name][..., 0][pick]
             ref = wf[name]
             errs[name] = float(np.max(np.abs(got - ref) / np.abs(ref).max(axis=0, keepdims=True)))
         out["wf_max_diff_over_column_max"] = errs

@@ -1,5 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see disco_oracle.hpp).  extern "C" surface for ctypes.
 #include "disco_oracle.hpp"
+#include "twostream_oracle.hpp"
 
 #include <string>
 #ifdef _OPENMP
@@ -200,6 +201,37 @@ int oracle_degeneracy(int nstr, int nloc, int nwavel, int nleg, int nlos, const 
                     o[0] = d1;
                     o[1] = d2;
                 }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_err = e.what();
+        return -3;
+    }
+}
+
+// Dedicated two-stream source (twostream_oracle.hpp).  Same array layouts as oracle_do_radiance; leg needs >= 2 moments;
+// the delta-M fraction set by oracle_set_delta_m enters b1 = leg[1] - 3 f / (1 - f) (cpp_twostream_source.cpp:879-897).
+int oracle_twostream_radiance(int nloc, int nwavel, int nleg, int nlos, const double* alt, int interp, int geotype,
+                              double cos_sza, double earth_radius, const double* los_cos_vza, const double* los_rel_az,
+                              const double* ssa, const double* ext, const double* leg, const double* solar,
+                              const double* albedo, int nthreads, double* radiance) {
+    using namespace oracle;
+    try {
+        if (nleg < 2) throw std::runtime_error("two-stream source needs at least two phase moments");
+        std::vector<double> a(alt, alt + nloc), cz(los_cos_vza, los_cos_vza + nlos), az(los_rel_az, los_rel_az + nlos);
+        Plan P = make_plan(2, a, interp, geotype, cos_sza, earth_radius, cz, az);
+#ifdef _OPENMP
+        if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+        for (int w = 0; w < nwavel; ++w) {
+            std::vector<double> b1(nloc);
+            for (int q = 0; q < nloc; ++q) {
+                const double f = g_f ? g_f[q + size_t(nloc) * w] : 0.0;
+                b1[q] = leg[1 + size_t(nleg) * (q + size_t(nloc) * w)] - 3.0 * f / (1.0 - f);
+            }
+            twostream::solve_wavelength(P, ext + size_t(nloc) * w, ssa + size_t(nloc) * w, b1.data(), solar[w], albedo[w],
+                                        radiance + size_t(w) * nlos);
         }
         return 0;
     } catch (const std::exception& e) {

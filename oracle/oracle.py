@@ -25,7 +25,7 @@ _BLAS = None
 
 def build(force: bool = False) -> Path:
     so = _HERE / "liboracle_disco.so"
-    srcs = [_HERE / "disco_oracle_capi.cpp", _HERE / "disco_oracle.hpp"]
+    srcs = [_HERE / "disco_oracle_capi.cpp", _HERE / "disco_oracle.hpp", _HERE / "twostream_oracle.hpp"]
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(_HERE), "-B" if force else "-s"], check=True, capture_output=True)
     return so
@@ -126,6 +126,34 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
     if lanes is not None:
         out["lanes"] = lanes
     return out
+
+
+def twostream_radiance(*, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az, ssa, ext, leg,
+                       solar=None, albedo, f=None, nthreads=0, **_ignored):
+    """The reference's dedicated two-stream source (multiple scatter only; twostream_oracle.hpp).  Returns
+    dict(radiance [nwavel, nlos])."""
+    L = lib()
+    alt = np.ascontiguousarray(alt, dtype=np.float64)
+    ssa = np.asfortranarray(ssa, dtype=np.float64)
+    ext = np.asfortranarray(ext, dtype=np.float64)
+    leg = np.asfortranarray(leg, dtype=np.float64)
+    cz = np.ascontiguousarray(los_cos_vza, dtype=np.float64)
+    az = np.ascontiguousarray(los_rel_az, dtype=np.float64)
+    nloc, nwavel = ssa.shape
+    solar = np.ones(nwavel) if solar is None else np.ascontiguousarray(solar, dtype=np.float64)
+    albedo = np.ascontiguousarray(np.broadcast_to(albedo, (nwavel,)), dtype=np.float64)
+    rad = np.zeros((nwavel, cz.size))
+    if f is not None:
+        f = np.asfortranarray(f, dtype=np.float64)
+    L.oracle_set_delta_m(_p(f), None)
+    rc = L.oracle_twostream_radiance(ctypes.c_int(nloc), ctypes.c_int(nwavel), ctypes.c_int(leg.shape[0]), ctypes.c_int(cz.size),
+                                     _p(alt), ctypes.c_int(interp), ctypes.c_int(geotype), ctypes.c_double(cos_sza),
+                                     ctypes.c_double(earth_radius), _p(cz), _p(az), _p(ssa), _p(ext), _p(leg), _p(solar),
+                                     _p(albedo), ctypes.c_int(nthreads), _p(rad))
+    L.oracle_set_delta_m(None, None)
+    if rc != 0:
+        raise RuntimeError(f"oracle_twostream_radiance failed: {L.oracle_last_error().decode()}")
+    return {"radiance": rad}
 
 
 def degeneracy(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az, ssa, ext, leg,

@@ -768,6 +768,7 @@ Engine* sk_engine_create(Config* config, Geometry1D* geometry, ViewingGeometry* 
         opt.nstr = config->num_streams;
         opt.include_ss = config->single_scatter_source == 2;
         opt.forced_azimuth = config->num_do_forced_azimuth;
+        opt.twostream = config->multiple_scatter_source == 2;
         if (const char* env = std::getenv("SK_B200_WORKSPACE_GB")) opt.workspace_gb = std::atof(env);
         e->dev = std::make_unique<disco::DeviceEngine>(opt, plan);
         return e;

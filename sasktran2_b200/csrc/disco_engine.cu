@@ -175,6 +175,8 @@ int DeviceEngine::planned_chunk(int nw, bool wf_on, int ngroups) const {
 }
 
 size_t DeviceEngine::ws_bytes(bool wf_on, int ngroups) const {
+    // the dedicated two-stream kernel keeps everything in registers: no per-wavelength workspace at all
+    if (m_opt.twostream && !wf_on && twostream_supported(m_plan.L, m_plan.plane_parallel)) return sizeof(double);
     const size_t N = m_plan.N, L = m_plan.L, nstr = m_plan.nstr, nlos = m_plan.nlos, M = m_mlist.size();
     size_t d = L * (6 + nstr) + 2 * (L + 1);                       // layer optics
     d += 2 * M * L * N * N + M * L * 2 * N + M * L * 4 * N;         // W+, W-, k|theta, G
@@ -221,6 +223,13 @@ void DeviceEngine::ensure_workspace(int chunk) {
         return p;
     };
     ChunkView& V = m_view;
+    if (twostream_direct()) {
+        std::memset(&V, 0, sizeof(V));
+        m_ws_wf = m_wf_on;
+        m_ws_ngroups = 0;
+        m_ws_chunk = chunk;
+        return;
+    }
     V.lay_od = A("lay_od", c * L);
     V.lay_ssa = A("lay_ssa", c * L);
     V.lay_beta = A("lay_beta", c * L * nstr);
@@ -487,6 +496,12 @@ void DeviceEngine::solve_staged() {
         V.dleg_gstride = (size_t)m_nleg * nloc * m_nw;
         V.fdm = m_has_f ? d_fdm + nloc * w0 : nullptr;
         V.fdm_gstride = nloc * (size_t)m_nw;
+        if (twostream_direct()) {
+            launch_twostream(V, m_stream);
+            mark(); slots.push_back(T_LAYER);
+            m_launches += 1;
+            continue;
+        }
         launch_layer_optics(V, m_stream);
         launch_beam(V, m_stream);
         mark(); slots.push_back(T_OPTICS);

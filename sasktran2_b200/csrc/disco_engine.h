@@ -16,6 +16,7 @@ struct EngineOptions {
     int nstr = 16;
     bool include_ss = true;     // single_scatter_source == discrete_ordinates
     int forced_azimuth = -1;    // num_do_forced_azimuth (<= 0: all nstr orders)
+    bool twostream = false;     // multiple_scatter_source == TwoStream: dedicated closed-form kernel when no weighting functions are asked
     double workspace_gb = -1.0; // per-chunk workspace budget; < 0: min(32 GB, a quarter of the free device memory)
     int device = -1;            // -1: current device
 };
@@ -81,6 +82,7 @@ class DeviceEngine {
                         double* radiance_host, double* const* mapping_host, double* const* surface_host, double ms_out[2]);
     bool wf_active() const { return m_wf_on; }
     bool fast_path() const { return m_fast; }
+    bool twostream_direct() const { return m_opt.twostream && !m_wf_on && twostream_supported(m_plan.L, m_plan.plane_parallel); }
     // test/debug: copy a workspace array of the LAST chunk to the host; returns the number of doubles copied
     size_t debug_copy(const char* name, double* host, size_t max_n);
     std::vector<std::pair<std::string, std::pair<double*, size_t>>> m_dbg;

@@ -52,6 +52,9 @@ inline int tsolve_groups_per_warp(int N, int glt) {
 bool adjoint_reuses_factors(int N, int nlos);
 size_t bvp_lfac_stride(int N, int L);
 void launch_radiance(const ChunkView& V, cudaStream_t s);
+// dedicated two-stream source (disco_twostream.cu): radiances of a chunk straight from the staged inputs
+bool twostream_supported(int L, bool plane_parallel);
+void launch_twostream(const ChunkView& V, cudaStream_t s);
 bool nstr_supported(int nstr);
 double measure_fp64_tflops();
 

@@ -158,6 +158,33 @@ def config2(nwavel: int = 100000, nlayers: int = 100, nstr: int = 16, nlos: int 
     return sc
 
 
+def config3(nwavel: int = 1000000, nlayers: int = 60, nlos: int = 2, block: tuple[int, int] | None = None,
+            seed: int = 0) -> Scenario:
+    """C3: two-stream source, 60 layers, line-by-line O2-A-band-like spectrum: k = k_ray + k_line with
+    k_line = 10^U(-9, -3) exp(-z / 8 km) per wavelength (a counter-based hash of the wavelength index, so that a
+    block of the spectrum equals the slice of the full one), beta = [1, 0.1, 0.5], plane parallel, ground-viewing LOS
+    (SURVEY.md section 8d).  `block = (start, count)` builds only that part of the spectrum."""
+    nleg = 3
+    z = np.linspace(0.0, 60e3, nlayers + 1)
+    widx = np.arange(nwavel, dtype=np.uint64) if block is None else np.arange(block[0], block[0] + block[1], dtype=np.uint64)
+    # splitmix64 of (index, seed) -> uniform [0, 1)
+    x = widx + np.uint64(0x9E3779B97F4A7C15) * np.uint64(seed + 1)
+    with np.errstate(over="ignore"):
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    u = (x >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+    k_line = (10.0 ** (-9.0 + 6.0 * u))[None, :] * np.exp(-z / 8e3)[:, None]
+    k_ray = (0.02 * rayleigh_extinction(z))[:, None] * np.ones(widx.size)[None, :]
+    k = k_ray + k_line
+    ssa = k_ray / k
+    leg = np.zeros((nleg, z.size, widx.size))
+    leg[0], leg[1], leg[2] = 1.0, 0.1, 0.5
+    return Scenario("C3", 2, z, 1, 0, 0.6, np.linspace(1.0, 0.8, nlos), np.linspace(0.0, 1.0, nlos), 200e3,
+                    np.asfortranarray(ssa), np.asfortranarray(k), np.asfortranarray(leg), np.full(widx.size, 0.3),
+                    np.ones(widx.size))
+
+
 def small_wf_case(nstr: int = 8, nlayers: int = 12, nwavel: int = 3, nlos: int = 3, interp: int = 1, geotype: int = 1,
                   seed: int = 1, nleg: int | None = None) -> Scenario:
     """Small pseudo-spherical Rayleigh + aerosol + absorber case with all three mapping kinds; used by the

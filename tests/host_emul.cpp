@@ -248,3 +248,37 @@ extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nl
         return -3;
     }
 }
+
+// Dedicated two-stream kernel body (sasktran2_b200/csrc/disco_twostream_body.h) run on the host, one wavelength after the
+// other, two lines of sight per pass like k_twostream<2>.  fdm: delta-M fraction [nloc, nwavel] or null.
+#include "../sasktran2_b200/csrc/disco_twostream_body.h"
+extern "C" int emul_twostream(int nloc, int nwavel, int nleg, int nlos, const double* alt, int interp, int geotype,
+                              double cos_sza, double earth_radius, const double* los_cos_vza, const double* los_rel_az,
+                              const double* ssa, const double* ext, const double* leg, const double* solar,
+                              const double* albedo, const double* fdm, double* radiance) {
+    try {
+        GeometrySpec geo;
+        geo.altitudes.assign(alt, alt + nloc);
+        geo.interp = interp;
+        geo.geotype = geotype;
+        geo.cos_sza = cos_sza;
+        geo.earth_radius = earth_radius;
+        std::vector<LineOfSight> los(nlos);
+        for (int j = 0; j < nlos; ++j) los[j] = {los_cos_vza[j], los_rel_az[j], alt[nloc - 1] + 1.0};
+        HostPlan P = build_plan(2, geo, los);
+        ChunkView V{};
+        V.T.nstr = 2; V.T.N = 1; V.T.L = P.L; V.T.nloc = nloc; V.T.nlos = nlos; V.T.csz = P.csz;
+        V.T.los_mu = P.los_mu.data(); V.T.los_cosmphi = P.los_cosmphi.data();
+        V.layer_dh = P.layer_dh.data(); V.chapman = P.chapman.data(); V.plane_parallel = P.plane_parallel;
+        V.nw = nwavel; V.nleg = nleg; V.ext = ext; V.ssa = ssa; V.leg = leg; V.albedo = albedo; V.solar = solar;
+        V.fdm = fdm;
+        V.radiance = radiance;
+        std::vector<double> od(P.L);
+        for (int w = 0; w < nwavel; ++w)
+            for (int l0 = 0; l0 < nlos; l0 += 2) disco::ts::twostream_body<2>(V, w, l0, P.chapman.data(), od.data(), 1);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -3;
+    }
+}

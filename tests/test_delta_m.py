@@ -203,3 +203,49 @@ def test_cuda_twostream_source_reference_case(oracle_mod):
     for n in a:
         if not n.startswith("_"):
             np.testing.assert_array_equal(a[n], b[n])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geotype,nlos", [(0, 2), (1, 2), (1, 5), (0, 1)])
+def test_cuda_dedicated_twostream_kernel_vs_oracle(oracle_mod, geotype, nlos):
+    """multiple_scatter_source = TwoStream without weighting functions runs the dedicated single-sweep kernel
+    (k_twostream, one launch per chunk): radiances against the restatement of the reference's two-stream source
+    (oracle/twostream_oracle.hpp, 1e-9) on a line-by-line spectrum of the configs[2] shape (60 layers, optical depths
+    over nine decades) and on the reference test's delta-M case."""
+    import sasktran2_b200 as sk
+    from tests.test_oracle_twostream import reference_case
+
+    def run(alt, interp, geotype, cos_sza, los_cos_vza, los_rel_az, ssa, ext, leg, albedo, solar=None, earth_radius=6372000.0,
+            delta_m=False):
+        cfg = sk.Config()
+        cfg.num_streams = 2
+        cfg.delta_m_scaling = delta_m
+        cfg.single_scatter_source = sk.SingleScatterSource.NoSource
+        cfg.multiple_scatter_source = sk.MultipleScatterSource.TwoStream
+        geo = sk.Geometry1D(cos_sza, 0.0, earth_radius, alt, sk.InterpolationMethod(interp), sk.GeometryType(geotype))
+        view = sk.ViewingGeometry()
+        for c, a in zip(los_cos_vza, los_rel_az):
+            view.add_ray(sk.GroundViewingSolar(cos_sza, float(a), float(c), 200_000.0))
+        nw = ssa.shape[1]
+        atm = sk.Atmosphere(geo, cfg, numwavel=nw, calculate_derivatives=False, num_legendre=leg.shape[0])
+        atm.storage.total_extinction[:] = ext
+        atm.storage.ssa[:] = ssa
+        atm.storage.leg_coeff[:] = leg
+        atm.surface.albedo[:] = albedo
+        if solar is not None:
+            atm.storage.solar_irradiance[:] = solar
+        eng = sk.Engine(cfg, geo, view)
+        rad = eng.calculate_radiance(atm)["radiance"][:, :, 0].copy()
+        assert eng.kernel_launches() == 1          # the dedicated kernel, not the discrete-ordinates pipeline
+        return rad
+
+    c3 = scn.config3(nwavel=20000, nlayers=60, nlos=nlos)
+    c3.geotype = geotype
+    inp = dict(alt=c3.altitudes, interp=c3.interp, geotype=c3.geotype, cos_sza=c3.cos_sza, los_cos_vza=c3.los_cos_vza,
+               los_rel_az=c3.los_rel_az, ssa=c3.ssa, ext=c3.total_extinction, leg=c3.leg_coeff, albedo=c3.albedo)
+    np.testing.assert_allclose(run(**inp), oracle_mod.twostream_radiance(**inp)["radiance"], rtol=1e-9)
+    geo, ssa, k, leg = reference_case()
+    geo["geotype"] = geotype
+    sc = oracle_mod.apply_delta_m_scaling(2, ssa, k, leg)
+    want = oracle_mod.twostream_radiance(**geo, ssa=sc["ssa"], ext=sc["ext"], leg=sc["leg"], f=sc["f"])["radiance"]
+    np.testing.assert_allclose(run(**geo, ssa=ssa, ext=k, leg=leg, delta_m=True), want, rtol=1e-9)

@@ -18,7 +18,8 @@ def emul():
     so = ROOT / "tests" / "libhost_emul.so"
     srcs = [ROOT / "tests" / "host_emul.cpp", ROOT / "sasktran2_b200" / "csrc" / "disco_plan.cpp",
             ROOT / "sasktran2_b200" / "csrc" / "disco_core.h", ROOT / "sasktran2_b200" / "csrc" / "disco_bodies.h",
-            ROOT / "sasktran2_b200" / "csrc" / "disco_bvp_rows.h", ROOT / "sasktran2_b200" / "csrc" / "disco_wf_body.h"]
+            ROOT / "sasktran2_b200" / "csrc" / "disco_bvp_rows.h", ROOT / "sasktran2_b200" / "csrc" / "disco_wf_body.h",
+            ROOT / "sasktran2_b200" / "csrc" / "disco_twostream_body.h"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(srcs[0]), str(srcs[1])],
                        check=True)
@@ -57,6 +58,27 @@ def emul():
             return rad, naz.value, native
         return rad, naz.value
 
+    def run_twostream(alt, interp, geotype, cos_sza, los_cos_vza, los_rel_az, ssa, ext, leg, albedo,
+                      earth_radius=6372000.0, solar=None, f=None, **_):
+        alt = np.ascontiguousarray(alt, float)
+        ssa = np.asfortranarray(ssa, float)
+        ext = np.asfortranarray(ext, float)
+        leg = np.asfortranarray(leg, float)
+        nloc, nw, nleg = alt.size, ssa.shape[1], leg.shape[0]
+        cz = np.ascontiguousarray(los_cos_vza, float)
+        az = np.ascontiguousarray(los_rel_az, float)
+        solar = np.ones(nw) if solar is None else np.ascontiguousarray(solar, float)
+        alb = np.ascontiguousarray(np.broadcast_to(albedo, (nw,)), float)
+        fd = None if f is None else np.asfortranarray(f, float)
+        rad = np.zeros((nw, cz.size))
+        rc = lib.emul_twostream(nloc, nw, nleg, cz.size, P(alt), interp, geotype, ctypes.c_double(cos_sza),
+                                ctypes.c_double(earth_radius), P(cz), P(az), P(ssa), P(ext), P(leg), P(solar), P(alb),
+                                P(fd) if fd is not None else None, P(rad))
+        if rc:
+            raise RuntimeError(lib.emul_last_error().decode())
+        return rad
+
+    run.twostream = run_twostream
     return run
 
 
@@ -133,3 +155,34 @@ def test_kernel_bodies_pass_the_weighting_function_parity_rules(emul, oracle_mod
     rep = wf_checks.assert_wf(oracle_mod, sc, res)
     assert rep["reference"]["wf_o3_vmr"]["rule"] == "flat 1e-7"
     assert rep["reference"]["wf_probe_k"]["listed_points"]["count"] > 0
+
+
+@pytest.mark.parametrize("geotype,nlos", [(0, 2), (1, 2), (1, 3), (1, 1)])
+def test_twostream_kernel_body_matches_the_two_stream_oracle(emul, oracle_mod, geotype, nlos):
+    """The single-sweep two-stream kernel body ((U^-T w).z instead of a back substitution, disco_twostream_body.h) against
+    the restatement of the reference's two-stream source (oracle/twostream_oracle.hpp): the reference test's inputs
+    (delta-M scaled), an O2-A-band-like line-by-line case with optical depths over nine decades, thin resonant layers."""
+    from sasktran2_b200 import scenarios
+    from tests.test_oracle_twostream import reference_case
+
+    geo, ssa, k, leg = reference_case()
+    geo["geotype"] = geotype
+    geo["los_cos_vza"] = np.array([0.7, 0.35, 1.0])[:nlos]
+    geo["los_rel_az"] = np.array([0.3, -0.4, 0.0])[:nlos]
+    sc = oracle_mod.apply_delta_m_scaling(2, ssa, k, leg)
+    got = emul.twostream(**geo, ssa=sc["ssa"], ext=sc["ext"], leg=sc["leg"], f=sc["f"])
+    want = oracle_mod.twostream_radiance(**geo, ssa=sc["ssa"], ext=sc["ext"], leg=sc["leg"], f=sc["f"])["radiance"]
+    np.testing.assert_allclose(got, want, rtol=1e-11)
+    thin = k.copy()
+    thin[-3:] *= 1e-9
+    got = emul.twostream(**geo, ssa=ssa, ext=thin, leg=leg)
+    want = oracle_mod.twostream_radiance(**geo, ssa=ssa, ext=thin, leg=leg)["radiance"]
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+    c3 = scenarios.config3(nwavel=200, nlayers=60, nlos=nlos)
+    c3.geotype = geotype
+    inp = dict(alt=c3.altitudes, interp=c3.interp, geotype=c3.geotype, cos_sza=c3.cos_sza, los_cos_vza=c3.los_cos_vza,
+               los_rel_az=c3.los_rel_az, ssa=c3.ssa, ext=c3.total_extinction, leg=c3.leg_coeff, albedo=c3.albedo)
+    got = emul.twostream(**inp)
+    want = oracle_mod.twostream_radiance(**inp)["radiance"]
+    assert np.all(want > 0)
+    np.testing.assert_allclose(got, want, rtol=1e-9)

@@ -38,7 +38,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
 // NLOS lines of sight per thread (grid.y walks batches of NLOS).  Dynamic shared memory: chapman [L][L] | od [L][blockDim]
 // (pseudo-spherical only) after one 16-byte mbarrier slot.
 template <int NLOS>
-__global__ void __launch_bounds__(128) k_twostream(ChunkView V) {
+__global__ void __launch_bounds__(128, 3) k_twostream(ChunkView V) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw);
     double* sh_chap = reinterpret_cast<double*>(smem_raw + 16);

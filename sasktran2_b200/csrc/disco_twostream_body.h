@@ -27,45 +27,63 @@ namespace ts {
 constexpr double kFourPi = 4.0 * kPi;
 
 // ---- removable singularities, cpp_twostream_source.cpp:33-131 ------------------------------------------------------
+// The reference evaluates these with library exp / pow and a convergence-tested series; the same functions are evaluated
+// here from the layer's five exponentials (e^{-k od} per order, e^{-s od}, e^{-od / mu} per line of sight) that the sweep
+// has anyway: every product e^{-(a + b) t} is a multiplication, e^{-x t / 2} a square root, the moment series a fixed
+// Horner polynomial - optically thin layers (the top half of a line-by-line atmosphere) take these branches all the time.
 // g(x) = (1 - e^{-x t}) / x = exp_difference(0, x, t); ex = e^{-x t} supplied by the caller
 DISCO_HD double g_fun(double x, double t, double ex) {
     if (fabs(x * t) > 1.0e-5) return (1.0 - ex) / x;
     const double u = 0.5 * x * t, u2 = u * u;
-    return t * exp(-0.5 * x * t) * (1.0 + u2 * (1.0 / 6.0 + u2 * (1.0 / 120.0 + u2 / 5040.0)));
+    return t * sqrt(ex) * (1.0 + u2 * (1.0 / 6.0 + u2 * (1.0 / 120.0 + u2 / 5040.0)));
 }
 // (e^{-a t} - e^{-b t}) / (b - a) with ea, eb supplied
 DISCO_HD double exp_difference(double a, double b, double t, double ea, double eb) {
     const double delta = b - a;
     if (fabs(delta * t) > 1.0e-5) return (ea - eb) / delta;
     const double u = 0.5 * delta * t, u2 = u * u;
-    return t * exp(-0.5 * (a + b) * t) * (1.0 + u2 * (1.0 / 6.0 + u2 * (1.0 / 120.0 + u2 / 5040.0)));
+    return t * sqrt(ea * eb) * (1.0 + u2 * (1.0 / 6.0 + u2 * (1.0 / 120.0 + u2 / 5040.0)));
 }
-DISCO_HD double exp_moment(int order, double rate, double t) {
-    if (t == 0.0) return 0.0;
-    const double sr = rate * t;
-    double unit;
-    if (fabs(sr) < 0.5) {
-        double ft = 1.0;
-        unit = 0.0;
-        for (int term = 0; term < 40; ++term) {
-            const double c = ft / (double)(order + term + 1);
-            unit += c;
-            if (fabs(c) <= 2.220446049250313e-16 * fmax(fabs(unit), 1.0)) break;
-            ft *= -sr / (double)(term + 1);
+// exp_moment(1, r, t) and exp_moment(3, r, t) (:33-63): M_n = int_0^t s^n e^{-r s} ds = t^{n+1} u_n(r t),
+// u_n(x) = sum_j (-x)^j / (j! (n + j + 1)) for |x| < 0.5, else the upward recurrence u_n = (n u_{n-1} - e^{-x}) / x
+// from u_0 = (1 - e^{-x}) / x.  er = e^{-r t}.
+DISCO_HD void exp_moments_1_3(double r, double t, double er, double& m1, double& m3) {
+    const double x = r * t, t2 = t * t;
+    double u1, u3;
+    if (fabs(x) < 0.5) {
+        // coefficients 1 / (j! (j + 2)) and 1 / (j! (j + 4)), j = 0 .. 15 (0.5^16 / 16! < 1e-18)
+        constexpr double c1[16] = {1.0 / 2, 1.0 / 3, 1.0 / 8, 1.0 / 30, 1.0 / 144, 1.0 / 840, 1.0 / 5760, 1.0 / 45360,
+                                   1.0 / 403200, 1.0 / 3991680, 1.0 / 43545600, 1.0 / 518918400, 1.0 / 6706022400.0,
+                                   1.0 / 93405312000.0, 1.0 / 1394852659200.0, 1.0 / 22230464256000.0};
+        constexpr double c3[16] = {1.0 / 4, 1.0 / 5, 1.0 / 12, 1.0 / 42, 1.0 / 192, 1.0 / 1080, 1.0 / 7200, 1.0 / 55440,
+                                   1.0 / 483840, 1.0 / 4717440, 1.0 / 50803200, 1.0 / 598752000, 1.0 / 7664025600.0,
+                                   1.0 / 105859353600.0, 1.0 / 1569209241600.0, 1.0 / 24845812992000.0};
+        const double y = -x;
+        u1 = c1[15];
+        u3 = c3[15];
+#pragma unroll
+        for (int j = 14; j >= 0; --j) {
+            u1 = u1 * y + c1[j];
+            u3 = u3 * y + c3[j];
         }
     } else {
-        const double e = exp(-sr);
-        unit = -expm1(-sr) / sr;
-        for (int cur = 1; cur <= order; ++cur) unit = ((double)cur * unit - e) / sr;
+        const double rx = 1.0 / x;
+        const double u0 = (1.0 - er) * rx;
+        u1 = (u0 - er) * rx;
+        const double u2 = (2.0 * u1 - er) * rx;
+        u3 = (3.0 * u2 - er) * rx;
     }
-    return pow(t, (double)(order + 1)) * unit;
+    m1 = t2 * u1;
+    m3 = t2 * t2 * u3;
 }
-// [g(a) - g(b)] / (b - a), integrated_exp_difference :100-131
-DISCO_HD double integrated_exp_difference(double a, double b, double t, double ea, double eb) {
+// [g(a) - g(b)] / (b - a), integrated_exp_difference :100-131; ga = g(a), gb = g(b) are values the sweep has already
+DISCO_HD double integrated_exp_difference(double a, double b, double t, double ea, double eb, double ga, double gb) {
     const double delta = b - a;
-    if (fabs(delta * t) > 1.0e-4) return (g_fun(a, t, ea) - g_fun(b, t, eb)) / delta;
-    const double mid = 0.5 * (a + b), hd = 0.5 * delta;
-    return exp_moment(1, mid, t) + hd * hd * exp_moment(3, mid, t) / 6.0;
+    if (fabs(delta * t) > 1.0e-4) return (ga - gb) / delta;
+    const double hd = 0.5 * delta;
+    double m1, m3;
+    exp_moments_1_3(0.5 * (a + b), t, sqrt(ea * eb), m1, m3);
+    return m1 + hd * hd * m3 / 6.0;
 }
 
 DISCO_HD double positive_ratio(double num, double den) { return den > 0.0 ? num / den : 0.0; }
@@ -164,11 +182,11 @@ DISCO_HD void twostream_body(const ChunkView& V, int w, int los0, const double* 
         const double trans = exp(-slant_top) * irradiance;                   // beam at the layer top
         const double expo = exp(-rate * od);
         // ---- line-of-sight exponentials of this layer
-        double beam[NLOS], src_int[NLOS];
+        double beam[NLOS], g_si[NLOS];
 #pragma unroll
         for (int j = 0; j < NLOS; ++j) {
             beam[j] = exp(-od * inv_view[j]);
-            src_int[j] = inv_view[j] * g_fun(rate + inv_view[j], od, expo * beam[j]);   // (1 - e^{-(s + 1/mu) od}) / (1 + s mu)
+            g_si[j] = g_fun(rate + inv_view[j], od, expo * beam[j]);   // source_integral = g / mu = (1 - e^{-(s + 1/mu) od}) / (1 + s mu)
         }
         const bool last_layer = l == n - 1;
 #pragma unroll
@@ -196,7 +214,8 @@ DISCO_HD void twostream_body(const ChunkView& V, int w, int los0, const double* 
             }
             const double ap = (qp * xp + qm * xm) * inv_norm, am = (qm * xp + qp * xm) * inv_norm;
             const double cp = trans * exp_difference(k, rate, od, omega, expo);
-            const double cm = trans * g_fun(rate + k, od, omega * expo);
+            const double g_sk = g_fun(rate + k, od, omega * expo);
+            const double cm = trans * g_sk;
             const double gpt = am * cm * xm, gpb = ap * cp * xp, gmt = am * cm * xp, gmb = ap * cp * xm;
             // ---- build_and_solve_explicit_bvp: the rows that become complete with this layer
             AzState& A = S[az];
@@ -224,9 +243,12 @@ DISCO_HD void twostream_body(const ChunkView& V, int w, int los0, const double* 
                 }
                 const double yp = lp * xp + lm * xm, ym = lp * xm + lm * xp;
                 const double hm = inv_view[j] * exp_difference(k, inv_view[j], od, omega, beam[j]);
-                const double hp = inv_view[j] * g_fun(k + inv_view[j], od, omega * beam[j]);
-                const double dp_ratio = inv_view[j] * integrated_exp_difference(rate + k, rate + inv_view[j], od, expo * omega, expo * beam[j]);
-                const double dm_ratio = inv_view[j] * integrated_exp_difference(k + inv_view[j], rate + inv_view[j], od, omega * beam[j], expo * beam[j]);
+                const double g_ki = g_fun(k + inv_view[j], od, omega * beam[j]);
+                const double hp = inv_view[j] * g_ki;
+                const double dp_ratio = inv_view[j] * integrated_exp_difference(rate + k, rate + inv_view[j], od, expo * omega,
+                                                                                expo * beam[j], g_sk, g_si[j]);
+                const double dm_ratio = inv_view[j] * integrated_exp_difference(k + inv_view[j], rate + inv_view[j], od, omega * beam[j],
+                                                                                expo * beam[j], g_ki, g_si[j]);
                 const double azw = az == 0 ? 1.0 : azw1[j];
                 const double particular = ap * yp * (trans * dm_ratio) + am * ym * (trans * dp_ratio);
                 integrated[j] += azw * particular * att[j];

@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see disco_oracle.hpp).  extern "C" surface for ctypes.
 #include "disco_oracle.hpp"
 #include "twostream_oracle.hpp"
+#include "limb_oracle.hpp"
 
 #include <string>
 #ifdef _OPENMP
@@ -232,6 +233,97 @@ int oracle_twostream_radiance(int nloc, int nwavel, int nleg, int nlos, const do
             }
             twostream::solve_wavelength(P, ext + size_t(nloc) * w, ssa + size_t(nloc) * w, b1.data(), solar[w], albedo[w],
                                         radiance + size_t(w) * nlos);
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_err = e.what();
+        return -3;
+    }
+}
+
+// Spherical line-of-sight path (limb_oracle.hpp).  rays: [nrays][5] = kind (0 GroundViewingSolar(cos_sza, rel_az, cos_vza,
+// observer_altitude), 1 TangentAltitudeSolar(tangent_altitude, rel_az, observer_altitude, cos_sza)) followed by the four
+// constructor arguments.  ms_do: multiple_scatter_source = DiscreteOrdinates (interpolated DO source table);
+// ss_exact: single_scatter_source = Exact.  radiance, los_od: [nwavel, nrays] C-order.
+int oracle_limb_radiance(int nstr, int nloc, int nwavel, int nleg, int nrays, const double* alt, int interp, double cos_sza,
+                         double saa, double earth_radius, const double* rays, int num_sza, int ms_do, int ss_exact,
+                         int num_ss_moments, const double* ssa, const double* ext, const double* leg, const double* solar,
+                         const double* albedo, oracle::dgeev_fn dgeev, int nthreads, double* radiance, double* los_od) {
+    using namespace oracle;
+    try {
+        std::vector<double> a(alt, alt + nloc);
+        std::vector<limb::RaySpec> specs(nrays);
+        for (int i = 0; i < nrays; ++i) {
+            specs[i].kind = (int)rays[i * 5];
+            for (int k = 0; k < 4; ++k) specs[i].p[k] = rays[i * 5 + 1 + k];
+        }
+        limb::LimbGeometry G(nstr, a, interp, cos_sza, saa, earth_radius, specs, num_sza);
+        limb::LimbConfig cfg;
+        cfg.ms_do = ms_do != 0;
+        cfg.ss_exact = ss_exact != 0;
+        cfg.num_ss_moments = num_ss_moments;
+        limb::LimbSolver S(G, cfg, dgeev);
+        std::string err;
+#ifdef _OPENMP
+        if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic)
+        for (int w = 0; w < nwavel; ++w) {
+            try {
+                WavelInputs in{};
+                in.ext = ext + size_t(nloc) * w;
+                in.ssa = ssa + size_t(nloc) * w;
+                in.leg = leg + size_t(nleg) * nloc * w;
+                in.nleg = nleg;
+                in.f = nullptr;
+                in.solar = solar[w];
+                in.albedo = albedo[w];
+                in.d_leg = nullptr;
+                in.ngroups = 0;
+                in.include_ss = false;
+                in.num_azimuth = nstr;
+                S.solve_wavelength(in, radiance + size_t(w) * nrays, los_od ? los_od + size_t(w) * nrays : nullptr);
+            } catch (const std::exception& e) {
+#pragma omp critical
+                err = e.what();
+            }
+        }
+        if (!err.empty()) throw std::runtime_error(err);
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_err = e.what();
+        return -3;
+    }
+}
+
+// Geometry export of the spherical path for checking the product's host-side ray tracer: per ray the number of layers,
+// ground flag, and per layer [layer_distance, od_quad_start, od_quad_end, cos_sza_entrance, cos_sza_exit, saz_entrance,
+// saz_exit, r_entrance, r_exit] (9 doubles, at most max_layers per ray); cos_scatter [nrays]: cosine of the
+// single-scattering angle of each (straight) ray.
+int oracle_limb_geometry(int nloc, int nrays, const double* alt, int interp, double cos_sza, double saa, double earth_radius,
+                         const double* rays, int max_layers, int* nlayers, int* ground_hit, double* layer_data,
+                         double* cos_scatter) {
+    using namespace oracle;
+    try {
+        std::vector<double> a(alt, alt + nloc);
+        std::vector<limb::RaySpec> specs(nrays);
+        for (int i = 0; i < nrays; ++i) {
+            specs[i].kind = (int)rays[i * 5];
+            for (int k = 0; k < 4; ++k) specs[i].p[k] = rays[i * 5 + 1 + k];
+        }
+        limb::LimbGeometry G(2, a, interp, cos_sza, saa, earth_radius, specs, 1);
+        for (int i = 0; i < nrays; ++i) {
+            const auto& r = G.rays[i];
+            nlayers[i] = (int)r.layers.size();
+            ground_hit[i] = r.ground_is_hit ? 1 : 0;
+            cos_scatter[i] = G.cos_scatter[i];
+            for (int j = 0; j < (int)r.layers.size() && j < max_layers; ++j) {
+                const auto& l = r.layers[j];
+                double* o = layer_data + (size_t(i) * max_layers + j) * 9;
+                o[0] = l.layer_distance; o[1] = l.od_quad_start; o[2] = l.od_quad_end;
+                o[3] = l.cos_sza_entrance; o[4] = l.cos_sza_exit; o[5] = l.saz_entrance; o[6] = l.saz_exit;
+                o[7] = l.r_entrance; o[8] = l.r_exit;
+            }
         }
         return 0;
     } catch (const std::exception& e) {

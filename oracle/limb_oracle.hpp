@@ -1,0 +1,913 @@
+// =====================================================================================================
+//  ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product.
+//
+//  CPU restatement (plain C++17, no Eigen) of SASKTRAN2's SPHERICAL line-of-sight path for NSTOKES = 1
+//  (BASELINE config 4): straight-ray spherical-shell ray tracing, the
+//  line-of-sight source integrator, the discrete-ordinates multiple-scatter source table with its
+//  (cos zenith x altitude x SZA x azimuth order) interpolation, and the exact single-scatter source.
+//  Values only (no weighting functions), observer outside the atmosphere, Lambertian surface, no refraction.
+//
+//  Every function cites the reference file:line (relative to /root/reference/cpp) whose arithmetic it restates.
+//  Parity pin: tests/test_oracle_limb.py checks this code against the reference's own golden radiances and
+//  line-of-sight optical depths of tests/engine/test_1d_solver_regression.py:112-239 (spherical geometry,
+//  8 streams, 2 ground-viewing + 2 limb rays, 3 wavelengths, rtol 5e-7).
+//
+//  The per-SZA discrete-ordinates solve itself is oracle::Solver<double> of disco_oracle.hpp.
+// =====================================================================================================
+#pragma once
+#include <array>
+#include <utility>
+
+#include "disco_oracle.hpp"
+
+namespace oracle {
+namespace limb {
+
+// ---------------------------------------------------------------------------------------------------
+//  small vector algebra (what the reference does with Eigen::Vector3d / Eigen::AngleAxis)
+// ---------------------------------------------------------------------------------------------------
+struct V3 {
+    double x = 0, y = 0, z = 0;
+    V3 operator+(const V3& o) const { return {x + o.x, y + o.y, z + o.z}; }
+    V3 operator-(const V3& o) const { return {x - o.x, y - o.y, z - o.z}; }
+    V3 operator*(double f) const { return {x * f, y * f, z * f}; }
+    double dot(const V3& o) const { return x * o.x + y * o.y + z * o.z; }
+    V3 cross(const V3& o) const { return {y * o.z - z * o.y, z * o.x - x * o.z, x * o.y - y * o.x}; }
+    double norm() const { return std::sqrt(x * x + y * y + z * z); }
+    V3 normalized() const {
+        double n = norm();
+        return {x / n, y / n, z / n};
+    }
+};
+// Eigen::AngleAxis<double>(angle, axis).matrix() * v for a unit axis (Rodrigues)
+inline V3 rotate(const V3& v, const V3& axis, double angle) {
+    const double c = std::cos(angle), s = std::sin(angle);
+    return v * c + axis.cross(v) * s + axis * (axis.dot(v) * (1 - c));
+}
+
+// Coordinates(cos_sza, saa, earth_radius, geotype, force_sun_z = false), lib/geometry/geometry.cpp:8-23
+struct Coordinates {
+    V3 x_unit{1, 0, 0}, y_unit{0, 1, 0}, z_unit{0, 0, 1}, sun_unit;
+    double earth_radius = 0;
+    Coordinates(double cos_sza, double saa, double re) : earth_radius(re) {
+        V3 sun_horiz = x_unit * std::cos(saa) + y_unit * std::sin(saa);
+        sun_unit = z_unit * cos_sza + sun_horiz * std::sqrt(1 - cos_sza * cos_sza);
+    }
+    // geometry.cpp:155-182 (spherical branch)
+    V3 solar_coordinate_vector(double cos_sza, double saa, double altitude) const {
+        V3 normal = sun_unit.cross(z_unit);
+        if (normal.norm() == 0)
+            normal = y_unit;
+        else
+            normal = normal.normalized();
+        V3 v = rotate(sun_unit, normal, std::acos(cos_sza));
+        v = rotate(v, sun_unit, saa);
+        return v * (altitude + earth_radius);
+    }
+    // geometry.cpp:199-232 (spherical: local up = location direction)
+    V3 look_vector_from_azimuth(const V3& location, double saa, double cos_viewing) const {
+        V3 local_up = location.normalized();
+        V3 sun_horiz = sun_unit - local_up * local_up.dot(sun_unit);
+        if (sun_horiz.norm() == 0) sun_horiz = y_unit;
+        sun_horiz = sun_horiz.normalized();
+        V3 horiz_look = rotate(sun_horiz, local_up, -saa);
+        double viewing_angle = PI / 2 - std::acos(-cos_viewing);
+        return rotate(horiz_look, local_up.cross(horiz_look), viewing_angle);
+    }
+    double cos_sza_at_reference() const { return z_unit.dot(sun_unit); }  // include/sasktran2/geometry.h:217-219
+};
+
+struct Location {  // include/sasktran2/geometry.h:23-49
+    V3 position;
+    bool on_exact_altitude = false;
+    int lower_alt_index = -1;
+    double radius() const { return position.norm(); }
+    double cos_zenith_angle(const V3& other) const { return position.dot(other) / (position.norm() * other.norm()); }
+};
+struct ViewingRay {  // include/sasktran2/viewinggeometry.h:14-28
+    Location observer;
+    V3 look_away;
+    double cos_viewing() const { return observer.cos_zenith_angle(look_away); }
+};
+
+// lib/viewinggeometry/tangentaltitudesolar.cpp:33-62
+inline ViewingRay tangent_altitude_solar(const Coordinates& g, double tangent_altitude, double rel_az, double observer_altitude,
+                                         double cos_sza) {
+    ViewingRay ray;
+    V3 tangent_point = g.solar_coordinate_vector(cos_sza, 0.0, tangent_altitude);
+    ray.look_away = g.look_vector_from_azimuth(tangent_point, rel_az, 0);
+    double a = g.earth_radius + observer_altitude, b = g.earth_radius + tangent_altitude;
+    double s = std::sqrt(a * a - b * b);
+    ray.observer.position = tangent_point - ray.look_away * s;
+    return ray;
+}
+// lib/viewinggeometry/groundviewing.cpp:16-60 (spherical branch)
+inline ViewingRay ground_viewing_solar(const Coordinates& g, double cos_sza, double rel_az, double cos_vza, double observer_altitude) {
+    ViewingRay r;
+    V3 ground = g.solar_coordinate_vector(cos_sza, 0.0, 0.0);
+    r.look_away = g.look_vector_from_azimuth(ground, -(PI - rel_az), cos_vza) * -1.0;
+    double b = 2.0 * g.earth_radius * cos_vza;
+    double c = -(2.0 * g.earth_radius * observer_altitude + observer_altitude * observer_altitude);
+    double dist = (-b + std::sqrt(b * b - 4 * c)) / 2;
+    r.observer.position = ground - r.look_away * dist;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+//  Grid::calculate_interpolation_weights, lib/grids/grid.cpp:43-300, out-of-bounds mode "extend"
+//  (interp 0 shell, 1 linear, 2 lower; constant_spacing as resolved by the Grid constructor :9-27)
+// ---------------------------------------------------------------------------------------------------
+struct Grid {
+    std::vector<double> g;
+    int interp = 1;
+    bool constant = false;
+    double x0 = 0, dx = 0;
+    Grid() {}
+    // spacing: 0 constant, 1 variable, 2 automatic
+    Grid(std::vector<double> values, int spacing, int interp_) : g(std::move(values)), interp(interp_) {
+        if (spacing == 2) {
+            constant = true;
+            if (g.size() > 1) {
+                double d0 = g[1] - g[0];
+                for (size_t i = 1; i < g.size(); ++i) {
+                    double di = g[i] - g[i - 1];
+                    if (std::abs(di - d0) > 1e-12 * std::min(std::abs(di), std::abs(d0))) constant = false;
+                }
+            }
+        } else {
+            constant = spacing == 0;
+        }
+        if (constant && g.size() > 1) {
+            x0 = g[0];
+            dx = g[1] - g[0];
+        }
+    }
+    void weights(double x, int idx[2], double w[2], int& n) const {
+        const int ng = (int)g.size();
+        if (ng == 1) {
+            idx[0] = idx[1] = 0; w[0] = 1; w[1] = 0; n = 1;
+            return;
+        }
+        if (interp == 2) {  // :222-289
+            for (int i = 0; i < ng - 1; ++i)
+                if (x + 0.1 >= g[i] && x < g[i + 1]) {
+                    idx[0] = i; idx[1] = 0; w[0] = 1; w[1] = 0; n = 1;
+                    return;
+                }
+            idx[0] = (x < g[0]) ? 0 : ng - 2; idx[1] = 0; w[0] = 1; w[1] = 0; n = 1;
+            return;
+        }
+        if (constant) {  // :45-127
+            if (x < x0) {
+                idx[0] = idx[1] = 0; w[0] = 1; w[1] = 0; n = 1;
+                return;
+            }
+            int i = int(std::floor((x - x0) / dx));
+            if (i >= ng - 1) {
+                idx[0] = ng - 1; idx[1] = 0; w[0] = 1; w[1] = 0; n = 1;
+                return;
+            }
+            idx[0] = i; idx[1] = i + 1; n = 2;
+            if (interp == 1) {
+                w[1] = (x - g[i]) / dx;
+                w[0] = 1 - w[1];
+            } else {
+                w[0] = w[1] = 0.5;
+            }
+            return;
+        }
+        // :130-212
+        if (x < g[0]) {
+            idx[0] = idx[1] = 0; w[0] = 1; w[1] = 0; n = 1;
+            return;
+        }
+        if (x > g[ng - 1]) {
+            idx[0] = ng - 1; idx[1] = 0; w[0] = 1; w[1] = 0; n = 1;
+            return;
+        }
+        int i = int(std::lower_bound(g.begin(), g.end(), x) - g.begin());
+        if (i == 0) i += 1;
+        idx[0] = i - 1; idx[1] = i; n = 2;
+        if (interp == 0) {
+            w[0] = w[1] = 0.5;
+        } else {
+            w[1] = (x - g[i - 1]) / (g[i] - g[i - 1]);
+            w[0] = 1 - w[1];
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+//  Traced rays: include/sasktran2/raytracing.h:40-120 (LayerGeometry), lib/raytracing/spherical_shell.cpp
+// ---------------------------------------------------------------------------------------------------
+struct Layer {
+    Location entrance, exit;   // entrance: the boundary closer to the observer
+    double r_entrance = 0, r_exit = 0;
+    V3 average_look_away;
+    double layer_distance = 0;
+    double od_quad_start = 0, od_quad_end = 0, od_quad_start_fraction = 0, od_quad_end_fraction = 0;
+    double saz_entrance = 0, saz_exit = 0, cos_sza_entrance = 0, cos_sza_exit = 0;
+    // shared stencil of the layer (add_interpolation_weights, raytracing.h:390-470)
+    int nidx = 0;
+    int idx[4] = {0, 0, 0, 0};
+    double w_entrance[4] = {0, 0, 0, 0}, w_exit[4] = {0, 0, 0, 0}, w_od[4] = {0, 0, 0, 0};
+};
+struct TracedRay {
+    ViewingRay observer_and_look;
+    bool ground_is_hit = false;
+    double tangent_radius = 0;
+    std::vector<Layer> layers;   // layers[0] is the one farthest from the observer
+};
+
+struct Geometry1D {
+    Coordinates coords;
+    Grid alt;   // altitude grid, automatic spacing, geometry interpolation method
+    Geometry1D(double cos_sza, double saa, double re, const std::vector<double>& altitudes, int interp)
+        : coords(cos_sza, saa, re), alt(altitudes, 2, interp) {}
+    // Geometry1D::assign_interpolation_weights, lib/geometry/geometry1d.cpp:20-84 (spherical)
+    void assign_interpolation_weights(const Location& loc, int idx[2], double w[2], int& n) const {
+        double a = loc.radius() - coords.earth_radius;
+        const bool valid = loc.lower_alt_index >= 0 && loc.lower_alt_index < (int)alt.g.size();
+        if (loc.on_exact_altitude && valid && std::abs(a - alt.g[loc.lower_alt_index]) <= 1.0) {
+            idx[0] = loc.lower_alt_index; idx[1] = 0; w[0] = 1; w[1] = 0; n = 1;
+            return;
+        }
+        alt.weights(a, idx, w, n);
+    }
+};
+
+// calculate_csz_saz, raytracing.h:319-349 (spherical)
+inline void calculate_csz_saz(const V3& sun_unit, const Location& loc, const V3& look_away, double& csz, double& saa) {
+    V3 up = loc.position.normalized();
+    csz = up.dot(sun_unit);
+    V3 los_projected = (look_away - up * look_away.dot(up)).normalized();
+    V3 sun_projected = (sun_unit - up * sun_unit.dot(up)).normalized();
+    V3 y_axis = up.cross(sun_projected);
+    saa = std::atan2(y_axis.dot(los_projected), sun_projected.dot(los_projected));
+}
+
+// add_od_quadrature, raytracing.h:478-560 (spherical geometry, straight rays: curvature_factor = 1)
+inline void add_od_quadrature(Layer& layer, int interp) {
+    double r0 = layer.entrance.radius(), r1 = layer.exit.radius(), dr = r1 - r0;
+    layer.average_look_away = (layer.exit.position - layer.entrance.position).normalized();
+    if (interp == 2) {
+        if (r0 < r1) {
+            layer.od_quad_start = layer.layer_distance;
+            layer.od_quad_end = 0.0;
+        } else {
+            layer.od_quad_start = 0.0;
+            layer.od_quad_end = layer.layer_distance;
+        }
+        layer.od_quad_start_fraction = layer.od_quad_end_fraction = 0.5;
+        return;
+    }
+    if (std::abs(dr) < 0.001 || interp == 0) {
+        layer.od_quad_start = layer.od_quad_end = layer.layer_distance / 2;
+        layer.od_quad_start_fraction = layer.od_quad_end_fraction = 0.5;
+        return;
+    }
+    double costheta0 = layer.entrance.cos_zenith_angle(layer.average_look_away);
+    double costheta1 = layer.exit.cos_zenith_angle(layer.average_look_away);
+    double t0 = r0 * costheta0, t1 = r1 * costheta1;
+    double rt = r0 * std::sqrt(1.0 - costheta0 * costheta0);
+    double dt1, dt2;
+    if (t1 >= t0) {
+        dt1 = t1 - t0;
+        if (std::abs(rt) < 10)
+            dt2 = 0.5 * (r1 * t1 - r0 * t0);
+        else
+            dt2 = 0.5 * ((r1 * t1 - r0 * t0) + rt * rt * std::log((r1 + t1) / (r0 + t0)));
+    } else {
+        dt1 = t0 - t1;
+        if (std::abs(rt) < 10)
+            dt2 = 0.5 * (r0 + t0 - r1 * t1);   // sic (raytracing.h:544)
+        else
+            dt2 = 0.5 * ((r0 * t0 - r1 * t1) + rt * rt * std::log((r0 + t0) / (r1 + t1)));
+    }
+    layer.od_quad_start = (r1 * dt1 - dt2) / dr;
+    layer.od_quad_end = -1 * (r0 * dt1 - dt2) / dr;
+    layer.od_quad_start_fraction = layer.od_quad_start / (layer.od_quad_start + layer.od_quad_end);
+    layer.od_quad_end_fraction = layer.od_quad_end / (layer.od_quad_start + layer.od_quad_end);
+}
+
+// add_interpolation_weights, raytracing.h:390-470
+inline void add_interpolation_weights(Layer& layer, const Geometry1D& geo) {
+    int ei[2], xi[2], en, xn;
+    double ew[2], xw[2];
+    geo.assign_interpolation_weights(layer.entrance, ei, ew, en);
+    geo.assign_interpolation_weights(layer.exit, xi, xw, xn);
+    int count = 0;
+    auto add = [&](const int* ii, const double* ww, int n) {
+        for (int k = 0; k < n; ++k) {
+            if (ww[k] == 0.0) continue;
+            if (std::find(layer.idx, layer.idx + count, ii[k]) == layer.idx + count) layer.idx[count++] = ii[k];
+        }
+    };
+    add(ei, ew, en);
+    add(xi, xw, xn);
+    std::sort(layer.idx, layer.idx + count);
+    layer.nidx = count;
+    auto acc = [&](const int* ii, const double* ww, int n, double* out) {
+        for (int k = 0; k < n; ++k) {
+            if (ww[k] == 0.0) continue;
+            out[std::find(layer.idx, layer.idx + count, ii[k]) - layer.idx] += ww[k];
+        }
+    };
+    acc(ei, ew, en, layer.w_entrance);
+    acc(xi, xw, xn, layer.w_exit);
+    for (int k = 0; k < count; ++k)
+        layer.w_od[k] = layer.w_entrance[k] * layer.od_quad_start + layer.w_exit[k] * layer.od_quad_end;
+}
+
+struct RayTracer {  // SphericalShellRayTracer, straight rays
+    const Geometry1D& geo;
+    const std::vector<double>& alt;
+    double re;
+    explicit RayTracer(const Geometry1D& g) : geo(g), alt(g.alt.g), re(g.coords.earth_radius) {}
+
+    // spherical_shell.cpp:254-276
+    void complete_layer(Layer& layer, int exit_index, int direction) const {
+        layer.r_entrance = alt[exit_index + direction] + re;
+        layer.r_exit = alt[exit_index] + re;
+        layer.entrance.on_exact_altitude = true;
+        layer.entrance.lower_alt_index = exit_index + direction;
+        layer.exit.on_exact_altitude = true;
+        layer.exit.lower_alt_index = exit_index;
+    }
+    // :278-298
+    void partial_layer(Layer& layer, const ViewingRay& ray, int start_index, int direction) const {
+        layer.r_entrance = (ray.observer.radius() - re) + re;
+        layer.r_exit = alt[start_index] + re;
+        layer.exit.on_exact_altitude = true;
+        layer.exit.lower_alt_index = start_index;
+        layer.entrance.on_exact_altitude = false;
+        layer.entrance.lower_alt_index = direction < 0 ? start_index + direction : start_index;
+    }
+    // :300-346
+    void tangent_layer(Layer& layer, int upper_index, double tangent_altitude, int direction) const {
+        int ti = upper_index - 1;
+        bool exact = std::abs(tangent_altitude - alt[ti]) <= 1e-4;
+        if (!exact && std::abs(tangent_altitude - alt[upper_index]) <= 1e-4) {
+            ti = upper_index;
+            exact = true;
+        }
+        double entrance_altitude, exit_altitude;
+        if (direction == -1) {  // ViewingDirection::up
+            entrance_altitude = tangent_altitude;
+            exit_altitude = alt[upper_index];
+            layer.exit.on_exact_altitude = true;
+            layer.exit.lower_alt_index = upper_index;
+            layer.entrance.on_exact_altitude = exact;
+            layer.entrance.lower_alt_index = ti;
+        } else {
+            exit_altitude = tangent_altitude;
+            entrance_altitude = alt[upper_index];
+            layer.entrance.on_exact_altitude = true;
+            layer.entrance.lower_alt_index = upper_index;
+            layer.exit.on_exact_altitude = exact;
+            layer.exit.lower_alt_index = ti;
+        }
+        layer.r_entrance = entrance_altitude + re;
+        layer.r_exit = exit_altitude + re;
+    }
+    // distance_to_altitude, raytracing.h:826-866 (direction down = 1, side nearside = 1)
+    double distance_to_altitude_down_nearside(const ViewingRay& ray, double altitude) const {
+        double cz = std::abs(ray.observer.cos_zenith_angle(ray.look_away));
+        double ro = ray.observer.radius(), rr = re + altitude;
+        double rtsq = ro * ro * (1 - cz * cz);
+        double tangent_distance = ro * cz;
+        double from_tangent;
+        if (rtsq > rr * rr) {
+            if (std::abs(rtsq - rr * rr) < 100)
+                from_tangent = 0.0;
+            else
+                throw std::runtime_error("limb oracle: distance to a shell that does not exist");
+        } else {
+            from_tangent = std::sqrt(std::abs(rr * rr - rtsq));
+        }
+        return tangent_distance - from_tangent;
+    }
+
+    // trace_ray, spherical_shell.cpp:6-76 (no refraction)
+    void trace(const ViewingRay& ray, TracedRay& out) const {
+        out = TracedRay();
+        const int ng = (int)alt.size();
+        const double cv = ray.cos_viewing();
+        const double rt = ray.observer.radius() * std::sqrt(std::max(0.0, 1 - cv * cv));
+        out.tangent_radius = rt;
+        out.observer_and_look = ray;
+        const double tangent_altitude = rt - re;
+        const double obs_alt = ray.observer.radius() - re;
+        if (obs_alt >= alt[ng - 1]) {
+            if (cv > 0) return;  // looking up from outside: empty ray
+            if (tangent_altitude > alt[0]) {
+                // trace_ray_observer_outside_limb_viewing, :222-262
+                int above = int(std::upper_bound(alt.begin(), alt.end(), tangent_altitude) - alt.begin());
+                int numlayer = 2 * (ng - above);
+                out.layers.resize(numlayer);
+                if (numlayer == 0) return;
+                int c = 0;
+                for (int i = ng - 1; i != above; --i) complete_layer(out.layers[c++], i, -1);
+                tangent_layer(out.layers[c++], above, tangent_altitude, -1);
+                tangent_layer(out.layers[c++], above, tangent_altitude, 1);
+                for (int i = above; i < ng - 1; ++i) complete_layer(out.layers[c++], i, 1);
+            } else {
+                // trace_ray_observer_outside_ground_viewing, :207-220
+                out.ground_is_hit = true;
+                out.layers.resize(ng - 1);
+                for (int i = 0; i < ng - 1; ++i) complete_layer(out.layers[i], i, 1);
+            }
+        } else {
+            if (cv > 0) {
+                // trace_ray_observer_inside_looking_up, :424-455
+                int start = int(std::upper_bound(alt.begin(), alt.end(), obs_alt) - alt.begin());
+                out.layers.resize(ng - start);
+                int c = 0;
+                for (int i = ng - 1; i != start; --i) complete_layer(out.layers[c++], i, -1);
+                partial_layer(out.layers[c], ray, start, -1);
+            } else {
+                // the sun below the local horizon of a line-of-sight point: the reference's looking-down branches
+                // (:457-551) are not restated; flag the ray as blocked only when it really reaches the ground
+                if (tangent_altitude <= alt[0]) {
+                    out.ground_is_hit = true;
+                    return;
+                }
+                throw std::runtime_error("limb oracle: observer inside the atmosphere looking down is not restated");
+            }
+        }
+        finalize(out);
+    }
+
+    // finalize_ray_geometry, spherical_shell.cpp:85-205 (straight ray)
+    void finalize(TracedRay& r) const {
+        const int nl = (int)r.layers.size();
+        const int ng = (int)alt.size();
+        const double rt = r.tangent_radius;
+        for (int i = 0; i < nl; ++i) {
+            Layer& layer = r.layers[nl - i - 1];
+            if (i == 0) {
+                if (r.observer_and_look.observer.radius() - re < alt[ng - 1]) {
+                    layer.entrance.position = r.observer_and_look.observer.position;
+                } else {
+                    layer.entrance.position = r.observer_and_look.observer.position +
+                                              r.observer_and_look.look_away *
+                                                  distance_to_altitude_down_nearside(r.observer_and_look, alt[ng - 1]);
+                }
+            } else {
+                const Layer& prev = r.layers[nl - i];
+                layer.entrance.position = prev.exit.position;  // flags of the entrance keep this layer's own values
+            }
+            layer.layer_distance = std::abs(std::sqrt(std::fmax(layer.r_entrance * layer.r_entrance - rt * rt, 0)) -
+                                            std::sqrt(std::fmax(layer.r_exit * layer.r_exit - rt * rt, 0.0)));
+            layer.average_look_away = r.observer_and_look.look_away;
+            layer.exit.position = layer.entrance.position + layer.average_look_away * layer.layer_distance;
+            add_od_quadrature(layer, geo.alt.interp);
+            add_interpolation_weights(layer, geo);
+            calculate_csz_saz(geo.coords.sun_unit, layer.entrance, layer.average_look_away, layer.cos_sza_entrance, layer.saz_entrance);
+            calculate_csz_saz(geo.coords.sun_unit, layer.exit, layer.average_look_away, layer.cos_sza_exit, layer.saz_exit);
+        }
+    }
+};
+// NOTE on `layer.entrance = previous.exit` (spherical_shell.cpp:138-141): the reference copies the whole Location
+// (position AND on_exact_altitude / lower_alt_index).  The exit of the previous (nearer) layer and the entrance of this
+// one are the same boundary with the same flags by construction (complete / tangent / partial layers above), so
+// copying only the position is equivalent.
+
+struct RaySpec {
+    int kind;        // 0 GroundViewingSolar(cos_sza, rel_az, cos_vza, observer_altitude), 1 TangentAltitudeSolar(tangent_altitude, rel_az, observer_altitude, cos_sza)
+    double p[4];     // in the constructor's argument order
+};
+
+// ---------------------------------------------------------------------------------------------------
+//  Geometry-only part of the spherical engine: traced rays, optical-depth stencils, the DO source
+//  interpolators and the solar geometry of the exact single-scatter source
+// ---------------------------------------------------------------------------------------------------
+struct SourcePoint { int index; double weight; };   // entry of one sparse interpolation vector
+
+struct LimbGeometry {
+    Geometry1D geo;
+    int nstr = 0, nsza = 0, nalt = 0, nang = 100;
+    std::vector<TracedRay> rays;
+    Grid sza_grid, altitude_grid, cos_angle_grid;
+    int ground_start = 0, npoints = 0;
+    std::vector<char> need;                                       // m_need_to_calculate_map
+    std::vector<std::vector<std::vector<SourcePoint>>> los_interp;    // [ray][layer] -> sparse vector over the source table
+    std::vector<std::vector<SourcePoint>> ground_interp;              // [ray] (empty unless the ground is hit)
+    std::vector<std::vector<std::array<int, 2>>> mid_idx;             // [ray][layer] SSA interpolation at the layer mid-point
+    std::vector<std::vector<std::array<double, 2>>> mid_w;
+    std::vector<std::vector<int>> mid_n;
+    // exact single scatter: one solar ray per layer boundary of every line of sight (solartransmissionexact.cpp:36-96)
+    std::vector<std::vector<std::vector<std::pair<int, double>>>> solar_rows;   // [ray][boundary] -> sparse row of the OD matrix
+    std::vector<std::vector<char>> solar_ground_hit;
+    std::vector<double> cos_scatter;   // [ray]
+
+    LimbGeometry(int nstr_, const std::vector<double>& alt, int interp, double cos_sza, double saa, double re,
+                 const std::vector<RaySpec>& specs, int num_sza)
+        : geo(cos_sza, saa, re, alt, interp), nstr(nstr_) {
+        RayTracer tracer(geo);
+        rays.resize(specs.size());
+        for (size_t i = 0; i < specs.size(); ++i) {
+            const RaySpec& s = specs[i];
+            ViewingRay vr = s.kind == 0 ? ground_viewing_solar(geo.coords, s.p[0], s.p[1], s.p[2], s.p[3])
+                                        : tangent_altitude_solar(geo.coords, s.p[0], s.p[1], s.p[2], s.p[3]);
+            tracer.trace(vr, rays[i]);
+        }
+        // DOSource::generate_sza_grid, source_term/do_source.cpp:61-92
+        double mn = 1, mx = -1;
+        for (const auto& r : rays)
+            for (const auto& l : r.layers) {
+                mn = std::min({mn, l.cos_sza_entrance, l.cos_sza_exit});
+                mx = std::max({mx, l.cos_sza_entrance, l.cos_sza_exit});
+            }
+        std::vector<double> sg;
+        if (num_sza == 1) {
+            sg = {geo.coords.cos_sza_at_reference()};
+        } else {
+            for (int i = 0; i < num_sza; ++i) sg.push_back(mn + (mx - mn) * i / (num_sza - 1));  // Eigen LinSpaced
+            sg.back() = mx;
+        }
+        nsza = (int)sg.size();
+        sza_grid = Grid(sg, 0, 1);
+        // DOSourceDiffuseStorage ctor, do_source_diffuse_storage.cpp:8-64
+        const int L = (int)alt.size() - 1;
+        std::vector<double> mid(L);
+        for (int q = 0; q < L; ++q) mid[q] = (alt[q] + alt[q + 1]) / 2.0;   // (ceiling + floor) / 2, reversed to ascending
+        altitude_grid = Grid(mid, 1, 1);
+        nalt = L;
+        std::vector<double> ca(nang);
+        for (int i = 0; i < nang; ++i) ca[i] = -1.0 + 2.0 * i / (nang - 1);
+        ca.back() = 1.0;
+        cos_angle_grid = Grid(ca, 1, 1);
+        ground_start = nalt * nang * nstr * nsza;
+        npoints = ground_start + nang * nstr * nsza;
+        need.assign(npoints, 0);
+        build_interpolators();
+        build_solar_geometry(tracer);
+    }
+    int linear_storage_index(int a, int lidx, int s, int m) const {   // :415-424
+        return a + nang * lidx + nang * nalt * s + nang * nalt * nsza * m;
+    }
+    int ground_storage_index(int a, int s, int m) const { return a + nang * s + nang * nsza * m + ground_start; }   // :426-433
+
+    void build_interpolators() {
+        const double re = geo.coords.earth_radius;
+        los_interp.resize(rays.size());
+        ground_interp.resize(rays.size());
+        mid_idx.resize(rays.size());
+        mid_w.resize(rays.size());
+        mid_n.resize(rays.size());
+        for (size_t i = 0; i < rays.size(); ++i) {
+            const TracedRay& ray = rays[i];
+            los_interp[i].resize(ray.layers.size());
+            mid_idx[i].resize(ray.layers.size());
+            mid_w[i].resize(ray.layers.size());
+            mid_n[i].resize(ray.layers.size());
+            for (size_t j = 0; j < ray.layers.size(); ++j) {
+                const Layer& layer = ray.layers[j];
+                // geometry_interpolator, do_source_diffuse_storage.cpp:84-209 (spherical, azimuth weights included)
+                double altitude = (layer.entrance.radius() + layer.exit.radius()) / 2.0 - re;
+                double cos_angle = -(layer.entrance.cos_zenith_angle(layer.average_look_away) +
+                                     layer.exit.cos_zenith_angle(layer.average_look_away)) / 2.0;
+                double azi = (layer.saz_entrance + layer.saz_exit) / 2.0;
+                double cos_sza = (layer.cos_sza_entrance + layer.cos_sza_exit) / 2.0;
+                int ai[2], gi[2], si[2], an, gn, sn;
+                double aw[2], gw[2], sw[2];
+                altitude_grid.weights(altitude, ai, aw, an);
+                cos_angle_grid.weights(cos_angle, gi, gw, gn);
+                sza_grid.weights(cos_sza, si, sw, sn);
+                auto& vec = los_interp[i][j];
+                for (int s = 0; s < sn; ++s)
+                    for (int a = 0; a < an; ++a)
+                        for (int g = 0; g < gn; ++g) {
+                            double weight = aw[a] * gw[g] * sw[s];
+                            for (int k = 0; k < nstr; ++k) {
+                                int index = linear_storage_index(gi[g], ai[a], si[s], k);
+                                need[index] = 1;
+                                set_coeff(vec, index, std::cos(k * azi) * weight);
+                            }
+                        }
+                // DOSource::construct_los_location_interpolator, do_source.cpp:94-124: SSA at the mid-point
+                Location mid;
+                mid.position = (layer.entrance.position + layer.exit.position) * 0.5;
+                int mi[2], mn;
+                double mw[2];
+                geo.assign_interpolation_weights(mid, mi, mw, mn);
+                mid_idx[i][j] = {mi[0], mi[1]};
+                mid_w[i][j] = {mw[0], mw[1]};
+                mid_n[i][j] = mn;
+            }
+            if (ray.ground_is_hit && !ray.layers.empty()) {
+                // create_ground_source_interpolator, :211-267
+                const V3& location = ray.layers[0].entrance.position;   // sic: entrance of layers[0] (do_source_interpolated_pp.cpp:65-72)
+                const V3& direction = ray.layers[0].average_look_away;
+                Location tmp;
+                tmp.position = location;
+                double csz, saa;
+                calculate_csz_saz(geo.coords.sun_unit, tmp, direction, csz, saa);
+                int si[2], gi[2], sn, gn;
+                double sw[2], gw[2];
+                sza_grid.weights(csz, si, sw, sn);
+                double mu = location.normalized().dot(direction * -1.0);
+                cos_angle_grid.weights(mu, gi, gw, gn);
+                if (cos_angle_grid.g[gi[0]] < 0) gi[0] = gi[1];
+                auto& vec = ground_interp[i];
+                for (int s = 0; s < sn; ++s)
+                    for (int g = 0; g < gn; ++g) {
+                        double weight = sw[s] * gw[g];
+                        for (int m = 0; m < nstr; ++m) {
+                            int index = ground_storage_index(gi[g], si[s], m);
+                            need[index] = 1;
+                            set_coeff(vec, index, weight * std::cos(m * (PI - saa)));
+                        }
+                    }
+            }
+        }
+    }
+    // Eigen::SparseVector::coeffRef(index) = value: assignment, not accumulation
+    static void set_coeff(std::vector<SourcePoint>& v, int index, double value) {
+        for (auto& e : v)
+            if (e.index == index) {
+                e.weight = value;
+                return;
+            }
+        v.push_back({index, value});
+    }
+
+    void build_solar_geometry(const RayTracer& tracer) {
+        solar_rows.resize(rays.size());
+        solar_ground_hit.resize(rays.size());
+        cos_scatter.assign(rays.size(), 0.0);
+        ViewingRay to_sun;
+        to_sun.look_away = geo.coords.sun_unit;
+        TracedRay traced;
+        for (size_t i = 0; i < rays.size(); ++i) {
+            const TracedRay& ray = rays[i];
+            const int nl = (int)ray.layers.size();
+            solar_rows[i].assign(nl + 1, {});
+            solar_ground_hit[i].assign(nl + 1, 0);
+            auto fill = [&](int row, const Location& from) {
+                to_sun.observer = from;
+                tracer.trace(to_sun, traced);
+                if (traced.ground_is_hit) {
+                    solar_ground_hit[i][row] = 1;
+                    return;
+                }
+                // assign_dense_matrix_column: accumulate the optical-depth stencil of every layer of the solar ray
+                for (const auto& l : traced.layers)
+                    for (int k = 0; k < l.nidx; ++k) {
+                        bool found = false;
+                        for (auto& e : solar_rows[i][row])
+                            if (e.first == l.idx[k]) {
+                                e.second += l.w_od[k];
+                                found = true;
+                            }
+                        if (!found) solar_rows[i][row].push_back({l.idx[k], l.w_od[k]});
+                    }
+            };
+            for (int j = 0; j < nl; ++j) {
+                if (j == 0) fill(0, ray.layers[0].exit);
+                fill(j + 1, ray.layers[j].entrance);
+            }
+            if (nl > 0) {
+                // PhaseHandler::initialize_geometry, lib/phasefunction/phasehandler.cpp:241-262 (straight rays: one
+                // scattering angle per ray from layers[0]); stokes_scattering_factors, math/scattering.h:77-96
+                V3 incoming = geo.coords.sun_unit * -1.0, outgoing = ray.layers[0].average_look_away * -1.0;
+                double c = incoming.dot(outgoing);
+                cos_scatter[i] = std::max(-1.0, std::min(1.0, c));
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+//  Per-wavelength part
+// ---------------------------------------------------------------------------------------------------
+struct LimbConfig {
+    bool ms_do = true;       // multiple_scatter_source = discrete_ordinates (DOSourceInterpolatedPostProcessing)
+    bool ss_exact = false;   // single_scatter_source = exact (SingleScatterSource<SolarTransmissionExact>)
+    int num_ss_moments = 16; // config.num_singlescatter_moments
+};
+
+struct LimbSolver {
+    const LimbGeometry& G;
+    LimbConfig cfg;
+    dgeev_fn dgeev;
+    std::vector<Plan> plans;   // one per SZA
+    std::vector<double> lp_ang;  // [a][m][l] d^l_{m0}(acos cos_angle[a]) (LegendrePhaseStorage::fill)
+    std::vector<double> wig_ss;  // [ray][l] d^l_{00}(scattering angle)
+
+    LimbSolver(const LimbGeometry& g, const LimbConfig& c, dgeev_fn f) : G(g), cfg(c), dgeev(f) {
+        std::vector<double> no_los;
+        for (int s = 0; s < G.nsza; ++s)
+            // DOSource::initialize_geometry, do_source.cpp:137-150: a PersistentConfiguration + GeometryLayerArray per SZA;
+            // chapman factors by ray tracing (spherical == the pseudo-spherical construction up to a rotation)
+            plans.push_back(make_plan(G.nstr, G.geo.alt.g, G.geo.alt.interp, 1, G.sza_grid.g[s], G.geo.coords.earth_radius, no_los, no_los));
+        const int nstr = G.nstr;
+        lp_ang.assign(size_t(G.nang) * nstr * nstr, 0.0);
+        for (int a = 0; a < G.nang; ++a)
+            for (int m = 0; m < nstr; ++m)
+                for (int l = 0; l < nstr; ++l)
+                    lp_ang[(size_t(a) * nstr + m) * nstr + l] = wigner_d_m0(m, l, std::acos(G.cos_angle_grid.g[a]));
+        wig_ss.assign(G.rays.size() * size_t(cfg.num_ss_moments), 0.0);
+        for (size_t i = 0; i < G.rays.size(); ++i)
+            for (int l = 0; l < cfg.num_ss_moments; ++l)
+                wig_ss[i * cfg.num_ss_moments + l] = wigner_d_m0(0, l, std::acos(G.cos_scatter[i]));
+    }
+
+    // DOSource::calculate (do_source.cpp:17-59) + DOSourceDiffuseStorage::accumulate_sources / accumulate_ground_sources
+    // (do_source_diffuse_storage.cpp:436-1098): fills the linear source table of one wavelength
+    void source_table(const WavelInputs& in, std::vector<double>& table) const {
+        const int nstr = G.nstr, N = nstr / 2, L = G.nalt;
+        table.assign(G.npoints, 0.0);
+        std::vector<char> converged(G.npoints, 0);
+        for (int s = 0; s < G.nsza; ++s) {
+            const Plan& P = plans[s];
+            Solver<double> S(P, dgeev);
+            S.lanes.L = L;
+            S.lanes.G = 0;
+            Layers<double> Ly;
+            S.layer_optics(in, Ly);
+            std::vector<LayerSolution<double>> sol(L);
+            bool all_converged = false;
+            for (int m = 0; m < nstr; ++m) {
+                for (int p = 0; p < L; ++p) {
+                    S.homogeneous(m, Ly.ssa[p], Ly.beta[p], sol[p]);
+                    S.particular(m, Ly.ssa[p], Ly.beta[p], Ly.od[p], Ly.secant[p], Ly.trans[p], sol[p]);
+                }
+                S.bvp(m, Ly, in.albedo, sol);
+                if (m >= 2) all_converged = true;
+                // ---- accumulate_ground_sources (:436-695): Lambertian, max_azimuthal_order = 1
+                if (m < 1) {
+                    const LayerSolution<double>& B = sol[L - 1];
+                    for (int a = 0; a < G.nang; ++a) {
+                        int index = G.ground_storage_index(a, s, m);
+                        if (!G.need[index] || converged[index]) continue;
+                        double diffuse = 0.0;
+                        for (int i = 0; i < N; ++i) {
+                            double sc = B.Gpb[i];
+                            for (int j = 0; j < N; ++j) {
+                                sc += B.Lc[j] * B.Wp[i + j * N] * std::exp(-B.k[j] * Ly.od[L - 1]);
+                                sc += B.Mc[j] * B.Wm[i + j * N];
+                            }
+                            double factor = 2.0 * P.mu[i] * P.wt[i];   // (1 + delta_m0) mu w
+                            diffuse += factor * sc * in.albedo;       // compute_expansion: brdf * pi = albedo
+                        }
+                        table[index] = diffuse;
+                    }
+                }
+                // ---- accumulate_sources (:697-1098)
+                for (int lidx = 0; lidx < L; ++lidx) {
+                    const int p = L - lidx - 1;
+                    const LayerSolution<double>& Sol = sol[p];
+                    const double altitude = G.altitude_grid.g[lidx];
+                    const double layer_fraction = (P.ceil_h[p] - altitude) / (P.ceil_h[p] - P.floor_h[p]);
+                    const double tau = Ly.od[p], sec = Ly.secant[p], trans = Ly.trans[p], ssa = Ly.ssa[p];
+                    const double x = layer_fraction * tau;
+                    std::vector<double> hp(N), hm(N), Dm(N), Dp(N);
+                    for (int i = 0; i < N; ++i) {   // sktran_do_postprocessing.h:20-193 (values)
+                        const double k = Sol.k[i];
+                        hp[i] = std::exp(-1.0 * k * tau * layer_fraction);
+                        hm[i] = std::exp(-k * tau * (1 - layer_fraction));
+                        Dm[i] = (std::exp(-x * k) - std::exp(-x * sec)) * (trans / (sec - k));
+                        double ef2 = std::exp(-tau * sec) * std::exp(-(tau - x) * k);
+                        Dp[i] = (std::exp(-x * sec) - ef2) * (trans / (k + sec));
+                    }
+                    for (int a = 0; a < G.nang; ++a) {
+                        const int index = G.linear_storage_index(a, lidx, s, m);
+                        if (!G.need[index] || converged[index]) continue;
+                        // scat_phase_f (sktran_do_lpproduct.h:265-337) with the swapped plus/minus arguments of :864-872
+                        std::vector<double> lps_plus(N), lps_minus(N);
+                        for (int q = 0; q < N; ++q) {
+                            double av = 0.0, bneg = 0.0;
+                            for (int l = m; l < nstr; ++l) {
+                                double pp = lp_ang[(size_t(a) * nstr + m) * nstr + l] * P.LPmu(m, q, l);
+                                av += Ly.beta[p][l] * pp;
+                                bneg += Ly.beta[p][l] * (((l - m) % 2 != 0) ? -pp : pp);
+                            }
+                            lps_minus[q] = av * (0.5 * P.wt[q]) * ssa;
+                            lps_plus[q] = bneg * (0.5 * P.wt[q]) * ssa;
+                        }
+                        double value = 0.0;
+                        for (int i = 0; i < N; ++i) {
+                            double Yp = 0.0, Ym = 0.0;
+                            for (int q = 0; q < N; ++q) {
+                                Yp += lps_plus[q] * Sol.Wp[q + i * N] + lps_minus[q] * Sol.Wm[q + i * N];
+                                Ym += lps_plus[q] * Sol.Wm[q + i * N] + lps_minus[q] * Sol.Wp[q + i * N];
+                            }
+                            value += Yp * hp[i] * Sol.Lc[i];
+                            value += Ym * hm[i] * Sol.Mc[i];
+                            value += (Sol.Ap[i] * Yp * Dm[i] + Sol.Am[i] * Ym * Dp[i]);
+                        }
+                        value /= ssa;
+                        table[index] = value;
+                        if (m >= 2) {   // convergence in azimuth order, :1032-1060
+                            double prev = table[G.linear_storage_index(a, lidx, s, m - 1)];
+                            double prev_prev = table[G.linear_storage_index(a, lidx, s, m - 2)];
+                            if ((std::abs(value / prev) < 1e-4 || prev < 1e-10) && (std::abs(value / prev_prev) < 1e-4 || prev_prev < 1e-10)) {
+                                for (int azi = m + 1; azi < nstr; ++azi) converged[G.linear_storage_index(a, lidx, s, azi)] = 1;
+                            } else {
+                                all_converged = false;
+                            }
+                        }
+                    }
+                }
+                if (all_converged) break;
+            }
+        }
+    }
+
+    // SourceIntegrator::integrate_ray (lib/sourceintegrator/sourceintegrator.cpp:519-575) over
+    // DOSourceInterpolatedPostProcessing::{end_of_ray_source, integrated_source} (do_source_interpolated_pp.cpp:95-210)
+    // and SingleScatterSource::{end_of_ray_source_single, integrated_source_constant} (lib/solar/singlescattersource.cpp:573-700, 949-1167)
+    void solve_wavelength(const WavelInputs& in, double* radiance, double* los_od) const {
+        std::vector<double> table;
+        if (cfg.ms_do) source_table(in, table);
+        const int nleg = in.nleg;
+        for (size_t i = 0; i < G.rays.size(); ++i) {
+            const TracedRay& ray = G.rays[i];
+            const int nl = (int)ray.layers.size();
+            // solar transmission at the layer boundaries (singlescattersource.cpp:102-160)
+            std::vector<double> solar_trans;
+            if (cfg.ss_exact) {
+                solar_trans.assign(nl + 1, 0.0);
+                for (int b = 0; b <= nl; ++b) {
+                    if (nl == 0 || G.solar_ground_hit[i][b]) continue;
+                    double od = 0.0;
+                    for (const auto& e : G.solar_rows[i][b]) od += e.second * in.ext[e.first];
+                    solar_trans[b] = std::exp(-od) * in.solar;
+                }
+            }
+            double I = 0.0, total_od = 0.0;
+            // end-of-ray sources
+            if (cfg.ms_do && ray.ground_is_hit) {
+                double gs = 0.0;
+                for (const auto& e : G.ground_interp[i]) gs += e.weight * table[e.index];
+                I += gs;
+            }
+            if (cfg.ss_exact && ray.ground_is_hit && nl > 0) {
+                const Layer& first = ray.layers[0];
+                double mu_in, phi;
+                calculate_csz_saz(G.geo.coords.sun_unit, first.exit, first.average_look_away, mu_in, phi);
+                if (mu_in > 0.0) I += solar_trans[0] * (in.albedo / PI) * mu_in;   // Lambertian brdf = albedo / pi
+            }
+            for (int j = 0; j < nl; ++j) {
+                const Layer& layer = ray.layers[j];
+                double od = 0.0;
+                for (int k = 0; k < layer.nidx; ++k)
+                    if (layer.w_od[k] != 0.0) od += layer.w_od[k] * in.ext[layer.idx[k]];
+                total_od += od;
+                const double attenuation = std::exp(-od);
+                I *= attenuation;
+                if (cfg.ms_do && !(layer.layer_distance < 1e-4)) {   // MINIMUM_SHELL_SIZE_M, internal_common.h:23
+                    double omega = 0.0;
+                    for (int k = 0; k < G.mid_n[i][j]; ++k) omega += in.ssa[G.mid_idx[i][j][k]] * G.mid_w[i][j][k];
+                    double source_factor = 1 - attenuation;
+                    double sv = 0.0;
+                    for (const auto& e : G.los_interp[i][j]) sv += e.weight * table[e.index];
+                    I += omega * source_factor * sv;
+                }
+                if (cfg.ss_exact) {
+                    auto endpoint = [&](const double* w, double strans) {
+                        // scattering_source (include/sasktran2/solartransmission.h:733-800) + PhaseHandler::calculate / scatter
+                        // (phasehandler.cpp:380-412, 677-700): phase of every contributing grid point at the ray's scattering angle
+                        double ssa = 0, k = 0, phase = 0;
+                        int nz = 0;
+                        for (int c = 0; c < layer.nidx; ++c) nz += w[c] != 0.0;
+                        for (int c = 0; c < layer.nidx; ++c) {
+                            if (w[c] == 0.0) continue;
+                            const int q = layer.idx[c];
+                            ssa += in.ssa[q] * w[c];
+                            k += in.ext[q] * w[c];
+                            int max_order = 1;   // determine_maximum_order, atmosphere/grid_storage.h:233-246
+                            for (int l = 0; l < nleg; ++l)
+                                if (in.leg[l + size_t(nleg) * q] != 0) max_order = l + 1;
+                            max_order = std::min(max_order, cfg.num_ss_moments);
+                            double ph = 0;
+                            for (int l = 0; l < max_order; ++l) ph += in.leg[l + size_t(nleg) * q] * wig_ss[i * cfg.num_ss_moments + l];
+                            phase += (nz == 1) ? ph : ph * w[c];   // single-node stencil: the weight is not applied (:683-685)
+                        }
+                        return k * ssa * strans / (PI * 4) * phase;
+                    };
+                    const bool lower = G.geo.alt.interp == 2;
+                    const double* ws = layer.w_entrance;
+                    const double* we = layer.w_exit;
+                    if (lower) {   // singlescattersource.cpp:1049-1078
+                        if (layer.r_exit > layer.r_entrance)
+                            we = layer.w_entrance;
+                        else
+                            ws = layer.w_exit;
+                    }
+                    double start = endpoint(ws, solar_trans[j + 1]);
+                    double end = endpoint(we, solar_trans[j]);
+                    double sf = std::abs(od) < 1e-12 ? 1.0 : -std::expm1(-od) / od;
+                    I += sf * (start * layer.od_quad_start_fraction + end * layer.od_quad_end_fraction) * layer.layer_distance;
+                }
+            }
+            radiance[i] = I;
+            if (los_od) los_od[i] = total_od;
+        }
+    }
+};
+
+}  // namespace limb
+}  // namespace oracle

@@ -25,7 +25,7 @@ _BLAS = None
 
 def build(force: bool = False) -> Path:
     so = _HERE / "liboracle_disco.so"
-    srcs = [_HERE / "disco_oracle_capi.cpp", _HERE / "disco_oracle.hpp", _HERE / "twostream_oracle.hpp"]
+    srcs = [_HERE / "disco_oracle_capi.cpp", _HERE / "disco_oracle.hpp", _HERE / "twostream_oracle.hpp", _HERE / "limb_oracle.hpp"]
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(_HERE), "-B" if force else "-s"], check=True, capture_output=True)
     return so
@@ -272,3 +272,59 @@ def apply_delta_m_scaling(order, ssa, ext, leg, d_leg=None, mappings=None):
             dw = dw + df * ssa0 / (1 - ssa0 * f) * (ssa1 - 1)
         m["d_extinction"], m["d_ssa"] = dk, dw
     return dict(ssa=ssa1, ext=ext1, leg=leg, d_leg=d_leg, f=f, d_f=d_f, mappings=maps)
+
+
+def _ray_table(rays):
+    """rays: list of ("ground", cos_sza, rel_az, cos_vza, observer_altitude) / ("tangent", tangent_altitude, rel_az,
+    observer_altitude, cos_sza) in the argument order of the reference's GroundViewingSolar / TangentAltitudeSolar."""
+    tab = np.zeros((len(rays), 5))
+    for i, r in enumerate(rays):
+        tab[i, 0] = {"ground": 0.0, "tangent": 1.0}[r[0]]
+        tab[i, 1:] = r[1:5]
+    return tab
+
+
+def limb_radiance(*, nstr, alt, interp, cos_sza, saa=0.0, earth_radius=6372000.0, rays, num_sza=2, ms_do=True,
+                  ss_exact=False, num_ss_moments=16, ssa, ext, leg, solar=None, albedo, nthreads=0):
+    """Spherical line-of-sight path (oracle/limb_oracle.hpp): DO multiple-scatter source table interpolated onto the
+    traced rays (+ exact single scatter when ss_exact).  Returns dict(radiance [nwavel, nrays], los_optical_depth)."""
+    L = lib()
+    alt = np.ascontiguousarray(alt, dtype=np.float64)
+    ssa = np.asfortranarray(ssa, dtype=np.float64)
+    ext = np.asfortranarray(ext, dtype=np.float64)
+    leg = np.asfortranarray(leg, dtype=np.float64)
+    nloc, nwavel = ssa.shape
+    nleg = leg.shape[0]
+    albedo = np.ascontiguousarray(albedo, dtype=np.float64)
+    solar = np.ones(nwavel) if solar is None else np.ascontiguousarray(solar, dtype=np.float64)
+    tab = _ray_table(rays)
+    rad = np.zeros((nwavel, len(rays)))
+    od = np.zeros((nwavel, len(rays)))
+    rc = L.oracle_limb_radiance(nstr, nloc, nwavel, nleg, len(rays), _p(alt), int(interp), ctypes.c_double(cos_sza),
+                                ctypes.c_double(saa), ctypes.c_double(earth_radius), _p(tab), int(num_sza), int(ms_do),
+                                int(ss_exact), int(num_ss_moments), _p(ssa), _p(ext), _p(leg), _p(solar), _p(albedo), _DGEEV,
+                                int(nthreads), _p(rad), _p(od))
+    if rc != 0:
+        raise RuntimeError(f"oracle_limb_radiance failed: {L.oracle_last_error().decode()}")
+    return dict(radiance=rad, los_optical_depth=od)
+
+
+def limb_geometry(*, alt, interp, cos_sza, saa=0.0, earth_radius=6372000.0, rays, max_layers=512):
+    """Traced-ray geometry of the limb oracle: dict(nlayers [nrays], ground_hit [nrays], layers [nrays, max_layers, 9])
+    with per layer (layer_distance, od_quad_start, od_quad_end, cos_sza_entrance, cos_sza_exit, saz_entrance, saz_exit,
+    r_entrance, r_exit); layers[0] is the one farthest from the observer."""
+    L = lib()
+    alt = np.ascontiguousarray(alt, dtype=np.float64)
+    tab = _ray_table(rays)
+    n = len(rays)
+    nl = np.zeros(n, dtype=np.int32)
+    gh = np.zeros(n, dtype=np.int32)
+    data = np.zeros((n, max_layers, 9))
+    csc = np.zeros(n)
+    ip = ctypes.POINTER(ctypes.c_int)
+    rc = L.oracle_limb_geometry(alt.size, n, _p(alt), int(interp), ctypes.c_double(cos_sza), ctypes.c_double(saa),
+                                ctypes.c_double(earth_radius), _p(tab), int(max_layers), nl.ctypes.data_as(ip),
+                                gh.ctypes.data_as(ip), _p(data), _p(csc))
+    if rc != 0:
+        raise RuntimeError(f"oracle_limb_geometry failed: {L.oracle_last_error().decode()}")
+    return dict(nlayers=nl, ground_hit=gh, layers=data, cos_scatter=csc)

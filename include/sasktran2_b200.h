@@ -337,6 +337,13 @@ int sk_b200_comm_init(const char* id, int rank, int world);
 int sk_b200_comm_destroy();
 int sk_b200_engine_gather_output(Engine* engine, OutputC* root_output, int root, const int* block_start,
                                  const int* block_count, int nw_total, double* ms_out);
+/* Host-only check of the spherical ("limb") geometry plan that sk_engine_create builds for geometrytype::spherical
+ * (replaces cpp/lib/raytracing/spherical_shell.cpp + the geometry_interpolator of
+ * cpp/lib/sktran_disco/source_term/do_source_diffuse_storage.cpp:84-209 + cpp/lib/solar/solartransmissionexact.cpp:36-96):
+ * per ray 6 doubles [line-of-sight optical depth for `ext` [nloc], segments, sum of DO interpolation weights,
+ * cos(single-scattering angle), solar optical depth at the far end, at the near end (-1: blocked by the ground)]. */
+int sk_b200_limb_plan_check(Geometry1D* geometry, ViewingGeometry* viewing, int nstr, int num_sza, const double* ext,
+                            double* per_ray, int* num_points, double* sza_grid);
 /* DFMA micro-benchmark on the current device: the FP64 roofline denominator (TFLOP/s) */
 double sk_b200_measure_fp64_tflops();
 /* 1 when the adjoint boundary-value solve of an (N = num_streams / 2, nlos) problem reuses the forward LU factors

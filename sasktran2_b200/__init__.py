@@ -10,7 +10,7 @@ from .enums import (GeometryType, InterpolationMethod, MultipleScatterSource, Si
 from ._lib import SasktranError, LibraryMissing
 from .config import Config
 from .geometry import Geometry1D
-from .viewinggeo import GroundViewingSolar, ViewingGeometry
+from .viewinggeo import GroundViewingSolar, TangentAltitudeSolar, ViewingGeometry
 from .atmosphere import Atmosphere
 from .engine import Engine
 from . import scenarios

@@ -37,7 +37,8 @@ def _declare(lib):
     for n in ("num_stokes", "multiple_scatter_source", "single_scatter_source", "num_streams", "num_threads",
               "threading_model", "wavelength_batch_size", "num_singlescatter_moments", "apply_delta_scaling",
               "num_do_sza", "num_do_forced_azimuth", "do_backprop", "emission_source", "occultation_source",
-              "solar_refraction", "wf_enabled", "wf_precision", "input_validation_mode", "log_level"):
+              "solar_refraction", "wf_enabled", "wf_precision", "input_validation_mode", "log_level",
+              "output_los_optical_depth"):
         f(f"sk_config_get_{n}", i, vp, c_int_p)
         f(f"sk_config_set_{n}", i, vp, i)
     f("sk_geometry1d_create", vp, d, d, d, c_double_p, i, i, i)
@@ -125,6 +126,8 @@ def _declare(lib):
     f("sk_b200_comm_destroy", i)
     f("sk_b200_engine_gather_output", i, vp, vp, i, c_int_p, c_int_p, i, c_double_p)
     f("sk_viewing_geometry_add_tangent_altitude_solar", i, vp, d, d, d, d)
+    f("sk_output_get_los_optical_depth", i, vp, C.POINTER(C.POINTER(C.c_double)))
+    f("sk_b200_limb_plan_check", i, vp, vp, i, i, c_double_p, c_double_p, c_int_p, c_double_p)
     f("sk_b200_host_alloc", vp, C.c_size_t)
     f("sk_b200_host_free", None, vp)
 

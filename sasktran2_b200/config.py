@@ -49,3 +49,4 @@ class Config:
     wf_enabled = _int_prop("wf_enabled", bool)
     wf_precision = _int_prop("wf_precision", WeightingFunctionPrecision)
     log_level = _int_prop("log_level")
+    output_los_optical_depth = _int_prop("output_los_optical_depth", bool)

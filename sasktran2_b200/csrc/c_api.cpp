@@ -94,7 +94,7 @@ int validate(const Engine* e, const Atmosphere* atm, const OutputC* out, bool ch
     if (check_output) {
         if (!out || !out->radiance) return fail(-1, "output handle is null");
         if (out->nstokes != 1) return fail(-2, "output num_stokes must be 1");
-        const long long need = (long long)s->nwavel * (long long)e->viewing->rays.size();
+        const long long need = (long long)s->nwavel * (long long)e->ncols();
         if (out->nrad != need) return fail(-2, "output radiance has the wrong size (expected nwavel * nlos)");
     }
     return 0;
@@ -105,7 +105,7 @@ int build_wf_request(Engine* e, Atmosphere* atm, OutputC* out, disco::WfRequest&
     if (!out || !(atm->calc_derivs && e->cfg.wf_enabled && e->cfg.wf_precision == 0)) return 0;
     if (out->derivs.empty() && out->surface_derivs.empty()) return 0;
     AtmosphereStorage* s = atm->storage;
-    const int nlos = (int)e->viewing->rays.size();
+    const int nlos = e->ncols();
     const long long nrad = (long long)s->nwavel * nlos;
     sk_atmosphere_storage_finalize_scattering_derivatives(s);
     if (s->num_scat_groups > 2)  // the weighting-function kernels are instantiated for 0, 1 and 2 groups
@@ -158,10 +158,19 @@ int run_range(Engine* e, Atmosphere* atm, OutputC* out, int start, int count) {
         disco::WfRequest req;
         int rc = build_wf_request(e, atm, out, req);
         if (rc != 0) return rc;
-        const int nlos = (int)e->viewing->rays.size();
+        const int nlos = e->ncols();
         e->dev->calculate(arrays_of(atm), start, count, out->radiance + (size_t)start * nlos, req.enabled() ? &req : nullptr);
         e->staged_start = start;
         e->staged_count = count;
+        if (e->dev->limb() && e->cfg.output_los_optical_depth) {
+            // Output::m_los_optical_depth is (nwavel, nlos) column-major upstream (cpp/lib/output/output.cpp:57-60)
+            const size_t nw_total = (size_t)atm->storage->nwavel;
+            out->los_optical_depth.resize(nw_total * nlos, 0.0);
+            std::vector<double> tmp((size_t)count * nlos);
+            e->dev->fetch_los_optical_depth(tmp.data());
+            for (int w = 0; w < count; ++w)
+                for (int r = 0; r < nlos; ++r) out->los_optical_depth[(size_t)(start + w) + nw_total * r] = tmp[(size_t)w * nlos + r];
+        }
         return 0;
     } catch (const std::exception& ex) {
         return fail(-3, ex.what());
@@ -252,10 +261,11 @@ void sk_viewing_geometry_add_ground_viewing_solar(ViewingGeometry* v, double cos
     if (!v) return;
     v->rays.push_back({cos_viewing_zenith, relative_azimuth_angle, observeraltitude});
     v->ray_cos_sza.push_back(cos_sza);
+    v->ordered.push_back({0, {cos_sza, relative_azimuth_angle, cos_viewing_zenith, observeraltitude}});
 }
 int sk_viewing_geometry_num_rays(ViewingGeometry* v, int* num_rays) {
     if (!v || !num_rays) return -1;
-    *num_rays = (int)(v->rays.size() + v->other_rays.size());
+    *num_rays = (int)(v->rays.size() + v->num_tangent_rays + v->other_rays.size());
     return 0;
 }
 int sk_viewing_geometry_num_flux_observers(ViewingGeometry* v, int* n) {
@@ -702,6 +712,70 @@ int sk_output_assign_surface_derivative_memory(OutputC* o, const char* name, dou
 // ---------------------------------------------------------------------------------------------------
 // Engine
 // ---------------------------------------------------------------------------------------------------
+// Spherical geometry (geometrytype::spherical): traced lines of sight, DOSourceInterpolatedPostProcessing for the
+// multiple-scatter source and SingleScatterSource<SolarTransmissionExact> for the single scatter
+// (cpp/lib/engine/engine.cpp:78-112, 210-220, 285-365).  SingleScatterSource::DiscreteOrdinates adds no
+// line-of-sight term in this geometry, exactly as upstream.
+static Engine* create_limb_engine(Config* config, Geometry1D* geometry, ViewingGeometry* viewing) {
+    const int ms = config->multiple_scatter_source, ss = config->single_scatter_source;
+    if (ms != 0 && ms != 3) {
+        fail(-2, "B200 limb path: multiple_scatter_source must be DiscreteOrdinates (0) or NoSource (3)");
+        return nullptr;
+    }
+    if (ss != 0 && ss != 2 && ss != 3) {
+        fail(-2, "B200 limb path: single_scatter_source must be Exact (0), DiscreteOrdinates (2) or NoSource (3)");
+        return nullptr;
+    }
+    if (config->emission_source != 1 || config->occultation_source != 1) {
+        fail(-2, "B200 limb path: emission and occultation sources are not supported");
+        return nullptr;
+    }
+    if (config->solar_refraction || config->los_refraction || config->multiple_scatter_refraction) {
+        fail(-2, "B200 limb path: refraction is not supported");
+        return nullptr;
+    }
+    if (!viewing->other_rays.empty() || viewing->num_flux_observers > 0) {
+        fail(-2, "B200 limb path: only GroundViewingSolar and TangentAltitudeSolar rays are supported");
+        return nullptr;
+    }
+    if (config->singlescatter_phasemode != 0) {
+        fail(-2, "B200 limb path: the single-scatter phase function is evaluated from the Legendre moments only");
+        return nullptr;
+    }
+    if (ss == 0 && ms == 0 && config->num_singlescatter_moments < config->num_streams) {   // cpp/lib/config/config.cpp:98-107
+        fail(-2, "Invalid number of single scatter moments, must be at least the number of streams");
+        return nullptr;
+    }
+    try {
+        auto* e = new Engine();
+        e->cfg = *config;
+        e->geometry = geometry;
+        e->viewing = viewing;
+        disco::LimbOptions lo;
+        lo.num_sza = config->num_do_sza;
+        lo.ms_do = ms == 0;
+        lo.ss_exact = ss == 0;
+        lo.num_ss_moments = config->num_singlescatter_moments;
+        disco::LimbPlan limb = disco::build_limb_plan(config->num_streams, geometry->spec, viewing->ordered, lo);
+        // stream tables of the DO solves: the pseudo-spherical construction without lines of sight
+        disco::GeometrySpec gs = geometry->spec;
+        gs.geotype = 1;
+        gs.cos_sza = limb.sza_grid.empty() ? gs.cos_sza : limb.sza_grid[0];
+        if (!(gs.cos_sza > 0.0)) gs.cos_sza = 1.0;   // single scatter only: the DO tables are never used
+        disco::HostPlan plan = disco::build_plan(config->num_streams, gs, {});
+        disco::EngineOptions opt;
+        opt.nstr = config->num_streams;
+        opt.include_ss = false;
+        opt.forced_azimuth = -1;   // DOSource::calculate loops over all num_do_streams orders (do_source.cpp:47-57)
+        if (const char* env = std::getenv("SK_B200_WORKSPACE_GB")) opt.workspace_gb = std::atof(env);
+        e->dev = std::make_unique<disco::DeviceEngine>(opt, plan, limb);
+        return e;
+    } catch (const std::exception& ex) {
+        fail(-3, ex.what());
+        return nullptr;
+    }
+}
+
 Engine* sk_engine_create(Config* config, Geometry1D* geometry, ViewingGeometry* viewing) {
     if (!config || !geometry || !viewing) {
         fail(-1, "sk_engine_create: null handle");
@@ -710,6 +784,11 @@ Engine* sk_engine_create(Config* config, Geometry1D* geometry, ViewingGeometry* 
     // Refuse everything outside the CUDA path loudly (there is no CPU fallback)
     if (config->num_stokes != 1) {
         fail(-2, "B200 DO path: num_stokes must be 1");
+        return nullptr;
+    }
+    if (geometry->spec.geotype == 2) return create_limb_engine(config, geometry, viewing);
+    if (viewing->num_tangent_rays > 0) {
+        fail(-2, "TangentAltitude ray construction can only be used in spherical geometry mode.");
         return nullptr;
     }
     // TwoStream (2): the reference's dedicated two-stream source (cpp_twostream_source.cpp) is, for ground-viewing
@@ -866,7 +945,7 @@ int sk_b200_engine_fetch_output(Engine* e, OutputC* out) {
     if (!out || !out->radiance) return fail(-1, "output handle is null");
     std::lock_guard<std::mutex> lock(e->mtx);
     try {
-        const int nlos = (int)e->viewing->rays.size();
+        const int nlos = e->ncols();
         if ((long long)out->nrad < (long long)(e->staged_start + e->staged_count) * nlos)
             return fail(-2, "output radiance too small for the staged wavelength range");
         e->dev->fetch(out->radiance + (size_t)e->staged_start * nlos);
@@ -929,7 +1008,7 @@ int sk_b200_engine_gather_output(Engine* e, OutputC* root_output, int root, cons
     if (!block_start || !block_count) return fail(-1, "sk_b200_engine_gather_output: null block tables");
     std::lock_guard<std::mutex> lock(e->mtx);
     try {
-        const int nlos = (int)e->viewing->rays.size();
+        const int nlos = e->ncols();
         std::vector<double*> maps, surfs;
         double* rad = nullptr;
         if (g_comm->rank() == root) {
@@ -949,6 +1028,48 @@ int sk_b200_engine_gather_output(Engine* e, OutputC* root_output, int root, cons
             ms_out[0] = ms[0];
             ms_out[1] = ms[1];
         }
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+
+// Host-only check of the spherical geometry plan (no device needed): traces the viewing rays and returns, per ray,
+// [line-of-sight optical depth for the extinction profile `ext` [nloc], number of segments, sum of the DO source
+// interpolation weights, cosine of the single-scattering angle, solar optical depth at the far end of the ray, solar
+// optical depth at the near end] (6 doubles per ray); *num_points = needed source-table points, sza_grid [num_sza].
+int sk_b200_limb_plan_check(Geometry1D* geometry, ViewingGeometry* viewing, int nstr, int num_sza, const double* ext,
+                            double* per_ray, int* num_points, double* sza_grid) {
+    if (!geometry || !viewing || !ext || !per_ray) return fail(-1, "sk_b200_limb_plan_check: null argument");
+    try {
+        disco::LimbOptions lo;
+        lo.num_sza = num_sza;
+        lo.ms_do = true;
+        lo.ss_exact = true;
+        disco::LimbPlan P = disco::build_limb_plan(nstr, geometry->spec, viewing->ordered, lo);
+        for (int r = 0; r < P.nrays; ++r) {
+            double od = 0.0, wsum = 0.0;
+            for (int sg = P.seg_start[r]; sg < P.seg_start[r + 1]; ++sg) {
+                for (int k = 0; k < disco::kLimbStencil; ++k) od += P.od_w[(size_t)sg * disco::kLimbStencil + k] * ext[P.od_idx[(size_t)sg * disco::kLimbStencil + k]];
+                for (int e = 0; e < disco::kLimbSrcEntries; ++e) wsum += P.src_w[(size_t)sg * disco::kLimbSrcEntries + e];
+            }
+            auto solar_od = [&](int b) {
+                double v = 0.0;
+                for (int e = P.sol_start[b]; e < P.sol_start[b + 1]; ++e) v += P.sol_w[e] * ext[P.sol_idx[e]];
+                return P.sol_blocked[b] ? -1.0 : v;
+            };
+            const int b0 = P.seg_start[r] + r, nb = P.seg_start[r + 1] - P.seg_start[r];
+            double* o = per_ray + (size_t)r * 6;
+            o[0] = od;
+            o[1] = nb;
+            o[2] = wsum;
+            o[3] = P.ray_cos_scatter[r];
+            o[4] = solar_od(b0);
+            o[5] = solar_od(b0 + nb);
+        }
+        if (num_points) *num_points = P.npts;
+        if (sza_grid)
+            for (int i = 0; i < P.nsza; ++i) sza_grid[i] = P.sza_grid[i];
         return 0;
     } catch (const std::exception& ex) {
         return fail(-3, ex.what());

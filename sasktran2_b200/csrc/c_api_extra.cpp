@@ -134,7 +134,9 @@ int sk_geometry2d_get_location_index(const Geometry2D*, int, int, int*) { return
 int sk_viewing_geometry_add_tangent_altitude_solar(ViewingGeometry* v, double tangent_altitude_m, double relative_azimuth_angle,
                                                    double observeraltitude, double cos_sza) {
     if (!v) return -1;
-    v->other_rays.push_back({1, tangent_altitude_m, relative_azimuth_angle, observeraltitude, cos_sza});
+    // spherical path (row a14): TangentAltitudeSolar(tangent_altitude, rel_az, observer_altitude, cos_sza)
+    v->ordered.push_back({1, {tangent_altitude_m, relative_azimuth_angle, observeraltitude, cos_sza}});
+    v->num_tangent_rays += 1;
     return 0;
 }
 int sk_viewing_geometry_add_tangent_altitude(ViewingGeometry* v, double tangent_altitude_m, double observer_altitude_m,
@@ -221,8 +223,13 @@ int sk_output_assign_surface_flux_derivative_memory(OutputC* o, const char*, dou
 }
 int sk_output_get_los_optical_depth(OutputC* o, double** od) {
     if (!o || !od) return -1;
-    *od = nullptr;
-    return unsupported("line-of-sight optical depth output");
+    // cpp/c_api/output.cpp:311-326: pointer to the [nwavel, nlos] matrix the engine filled (config.output_los_optical_depth)
+    if (o->los_optical_depth.empty()) {
+        *od = nullptr;
+        return skapi::fail(-2, "line-of-sight optical depths were not computed (spherical path with config.output_los_optical_depth only)");
+    }
+    *od = o->los_optical_depth.data();
+    return 0;
 }
 OutputJVP* sk_output_jvp_create(double*, double*, int, int) {
     unsupported("the JVP driver (sk_engine_linearization_backend reports Jacobian-only)");

@@ -71,9 +71,11 @@ struct OtherRay {
     double a, b, c, d;
 };
 struct ViewingGeometry {
+    std::vector<disco::LimbRay> ordered;   // every solar-angle ray in the order it was added (spherical path)
     std::vector<disco::LineOfSight> rays;
     std::vector<double> ray_cos_sza;
     std::vector<OtherRay> other_rays;
+    int num_tangent_rays = 0;
     int num_flux_observers = 0;
 };
 
@@ -162,6 +164,7 @@ struct DerivMem {
     int nrad, nstokes, nderiv;
 };
 struct OutputC {
+    std::vector<double> los_optical_depth;  // [nwavel, nlos] column-major as upstream (Output::m_los_optical_depth), filled when the config asks
     double* radiance = nullptr;
     int nrad = 0, nstokes = 1;
     double* flux = nullptr;
@@ -175,6 +178,7 @@ struct Engine {
     Geometry1D* geometry = nullptr;
     ViewingGeometry* viewing = nullptr;
     std::unique_ptr<disco::DeviceEngine> dev;
+    int ncols() const { return dev ? dev->radiance_columns() : 0; }  // radiance columns: lines of sight
     Atmosphere* atmosphere = nullptr;  // set by calculate_radiance(only_initialize) for block calls
     int staged_start = 0, staged_count = 0;
     std::mutex mtx;

@@ -34,6 +34,73 @@ static T* upload(const std::vector<T>& v) {
 }
 
 DeviceEngine::DeviceEngine(const EngineOptions& opt, const HostPlan& plan) : m_opt(opt), m_plan(plan) {
+    m_nrad = plan.nlos;
+    init(opt);
+}
+
+DeviceEngine::DeviceEngine(const EngineOptions& opt, const HostPlan& plan, const LimbPlan& limb)
+    : m_opt(opt), m_plan(plan), m_is_limb(true), m_limb(limb) {
+    if (plan.nlos != 0) throw std::runtime_error("limb engine: the DO plan must not carry lines of sight");
+    m_nrad = limb.nrays;
+    init(opt);
+    init_limb();
+}
+
+template <class T>
+static T* upload_tracked(const std::vector<T>& v, std::vector<void*>& owner) {
+    T* p = upload(v);
+    owner.push_back((void*)p);
+    return p;
+}
+
+// device copies of the limb geometry tables and of the per-SZA solar tables
+void DeviceEngine::init_limb() {
+    const LimbPlan& P = m_limb;
+    LimbView& Lv = m_lview;
+    std::memset(&Lv, 0, sizeof(Lv));
+    Lv.nrays = P.nrays;
+    Lv.nsza = P.nsza;
+    Lv.npts = P.npts;
+    Lv.nseg = P.nseg;
+    Lv.nss = P.nss;
+    Lv.ms_do = P.ms_do ? 1 : 0;
+    Lv.ss_exact = P.ss_exact ? 1 : 0;
+    auto& own = m_limb_ptrs;
+    Lv.layer_fraction = upload_tracked(P.layer_fraction, own);
+    Lv.lp_ang = upload_tracked(P.lp_ang, own);
+    Lv.pt_angle = upload_tracked(P.pt_angle, own);
+    Lv.pt_alt = upload_tracked(P.pt_alt, own);
+    Lv.pt_sza = upload_tracked(P.pt_sza, own);
+    Lv.seg_start = upload_tracked(P.seg_start, own);
+    Lv.od_idx = upload_tracked(P.od_idx, own);
+    Lv.od_w = upload_tracked(P.od_w, own);
+    Lv.ent_w = upload_tracked(P.ent_w, own);
+    Lv.exit_w = upload_tracked(P.exit_w, own);
+    Lv.mid_idx = upload_tracked(P.mid_idx, own);
+    Lv.mid_w = upload_tracked(P.mid_w, own);
+    Lv.seg_len = upload_tracked(P.seg_len, own);
+    Lv.seg_qfrac = upload_tracked(P.seg_qfrac, own);
+    Lv.seg_lower = upload_tracked(P.seg_lower, own);
+    Lv.src_pt = upload_tracked(P.src_pt, own);
+    Lv.src_w = upload_tracked(P.src_w, own);
+    Lv.src_cos = upload_tracked(P.src_cos, own);
+    Lv.gnd_hit = upload_tracked(P.gnd_hit, own);
+    Lv.gnd_sza_idx = upload_tracked(P.gnd_sza_idx, own);
+    Lv.gnd_sza_w = upload_tracked(P.gnd_sza_w, own);
+    Lv.gnd_mu_in = upload_tracked(P.gnd_mu_in, own);
+    Lv.wig_ss = upload_tracked(P.wig_ss, own);
+    Lv.sol_start = upload_tracked(P.sol_start, own);
+    Lv.sol_idx = upload_tracked(P.sol_idx, own);
+    Lv.sol_w = upload_tracked(P.sol_w, own);
+    Lv.sol_blocked = upload_tracked(P.sol_blocked, own);
+    for (const HostPlan& sp : P.sza_plans) {
+        d_sza_lp_csz.push_back(upload_tracked(sp.lp_csz, own));
+        d_sza_chapman.push_back(upload_tracked(sp.chapman, own));
+    }
+}
+
+void DeviceEngine::init(const EngineOptions& opt) {
+    const HostPlan& plan = m_plan;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -136,6 +203,9 @@ DeviceEngine::~DeviceEngine() {
     free_inputs();
     free_workspace();
     if (d_gather) cudaFree(d_gather);
+    for (void* p : m_limb_ptrs)
+        if (p) cudaFree(p);
+    if (d_los_od) cudaFree(d_los_od);
     for (void* p : {(void*)d_mu, (void*)d_wt, (void*)d_lp_mu, (void*)d_lp_csz, (void*)d_lp_los, (void*)d_los_mu, (void*)d_wf_tab,
                     (void*)d_los_cosmphi, (void*)d_layer_dh, (void*)d_interp_w, (void*)d_interp_idx,
                     (void*)d_chapman, (void*)d_mlist, (void*)d_status})
@@ -185,6 +255,11 @@ size_t DeviceEngine::ws_bytes(bool wf_on, int ngroups) const {
     d += M * nlos * L * 2 * N + M * nlos * L * vw;                  // wvec, vsrc
     if (m_fast) d += 3 * (N * (N + 1) / 2) * M * L + nlos * (L + 1) + nlos * L * 3;  // eigen planes, LOS exponentials
     d += M * L * 2 * N;                                             // x
+    if (m_is_limb) {
+        const size_t nsza = m_limb.nsza, npts = m_limb.npts, nrays = m_limb.nrays;
+        if (m_limb.ms_do) d += nsza * L * M * nstr + nsza + npts * M;    // Legendre projections, ground source, source table
+        if (m_limb.ss_exact) d += nrays * m_plan.nloc;                     // single-scatter phase function
+    }
     if (!wf_on) {
         d += M * bvp_fac_stride((int)N, 1, (int)L);                  // LU pivot rows (forward solve)
     } else {
@@ -256,6 +331,16 @@ void DeviceEngine::ensure_workspace(int chunk) {
         V.los_lay = A("los_lay", c * nlos * L * 3);
     }
     V.xsol = A("xsol", c * M * L * 2 * N);
+    if (m_is_limb) {
+        const size_t nsza = m_limb.nsza, npts = m_limb.npts, nrays = m_limb.nrays;
+        m_lview.coef = m_lview.ground = m_lview.table = m_lview.phase = nullptr;
+        if (m_limb.ms_do) {
+            m_lview.coef = A("limb_coef", c * nsza * L * M * nstr);
+            m_lview.ground = A("limb_ground", c * nsza);
+            m_lview.table = A("limb_table", c * npts * M);
+        }
+        if (m_limb.ss_exact) m_lview.phase = A("limb_phase", c * nrays * m_plan.nloc);
+    }
     if (!m_wf_on) {
         V.fac_stride = bvp_fac_stride((int)N, 1, (int)L);
         V.fac = A("fac", c * M * V.fac_stride);
@@ -301,7 +386,11 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
         d_leg = dalloc<double>((size_t)atm.nleg * nloc * nw);
         d_solar = dalloc<double>(nw);
         d_albedo = dalloc<double>(nw);
-        d_radiance = dalloc<double>((size_t)nw * std::max(m_plan.nlos, 1));
+        d_radiance = dalloc<double>((size_t)nw * std::max(m_nrad, 1));
+        if (m_is_limb) {
+            if (d_los_od) cudaFree(d_los_od);
+            d_los_od = dalloc<double>((size_t)nw * std::max(m_nrad, 1));
+        }
         m_cap_nw = nw;
         m_cap_nleg = atm.nleg;
     }
@@ -355,6 +444,7 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
     m_w0 = w0;
     m_nw_total = atm.nwavel;
     const bool want_wf = wf && wf->enabled() && nw > 0;
+    if (want_wf && m_is_limb) throw std::runtime_error("B200 limb path: weighting functions are not supported in spherical geometry");
     bool same_shape = want_wf && m_wf_on && m_wf_nw == nw && m_wf_nleg == atm.nleg &&
                       m_ngroups == (int)wf->d_legendre.size() && m_maps.size() == wf->mappings.size() &&
                       m_surfs.size() == wf->surfaces.size();
@@ -426,7 +516,7 @@ void DeviceEngine::solve_staged() {
         if (i != T_D2H) m_ms[i] = 0.0;
     m_launches = 0;
     CUDA_OK(cudaSetDevice(m_device));
-    if (m_nw == 0 || m_plan.nlos == 0) return;
+    if (m_nw == 0 || m_nrad == 0) return;
     const int chunk = chunk_wavelengths();
     ensure_workspace(chunk);
     CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(unsigned int), m_stream));
@@ -491,7 +581,7 @@ void DeviceEngine::solve_staged() {
         V.leg = d_leg + (size_t)m_nleg * nloc * w0;
         V.albedo = d_albedo + w0;
         V.solar = d_solar + w0;
-        V.radiance = d_radiance + (size_t)w0 * m_plan.nlos;
+        V.radiance = d_radiance + (size_t)w0 * m_nrad;
         V.dleg = d_dleg ? d_dleg + (size_t)m_nleg * nloc * w0 : nullptr;
         V.dleg_gstride = (size_t)m_nleg * nloc * m_nw;
         V.fdm = m_has_f ? d_fdm + nloc * w0 : nullptr;
@@ -499,6 +589,49 @@ void DeviceEngine::solve_staged() {
         if (twostream_direct()) {
             launch_twostream(V, m_stream);
             mark(); slots.push_back(T_LAYER);
+            m_launches += 1;
+            continue;
+        }
+        if (m_is_limb) {
+            // Spherical line-of-sight path: the layer optics once, then per SZA of the DO grid the beam, the layer
+            // solutions and the BVP with that SZA's chapman factors and solar Legendre table, each followed by the
+            // projection of the diffuse field; finally the source table and the line-of-sight integration.
+            LimbView Lv = m_lview;
+            Lv.radiance = V.radiance;
+            Lv.los_od = d_los_od ? d_los_od + (size_t)w0 * m_nrad : nullptr;
+            if (m_limb.ms_do) {
+                launch_layer_optics(V, m_stream);
+                mark(); slots.push_back(T_OPTICS);
+                m_launches += 1;
+                for (int sz = 0; sz < m_limb.nsza; ++sz) {
+                    V.T.csz = m_limb.sza_grid[sz];
+                    V.T.lp_csz = d_sza_lp_csz[sz];
+                    V.chapman = d_sza_chapman[sz];
+                    launch_beam(V, m_stream);
+                    mark(); slots.push_back(T_OPTICS);
+                    if (m_fast) {
+                        launch_layer_solve_fast(V, m_stream);
+                        m_launches += 2;
+                    } else {
+                        launch_layer_solve(V, m_stream);
+                    }
+                    mark(); slots.push_back(T_LAYER);
+                    launch_bvp(V, m_stream);
+                    mark(); slots.push_back(T_BVP);
+                    launch_limb_coef(V, Lv, sz, m_stream);
+                    mark(); slots.push_back(T_LIMB_SOURCE);
+                    m_launches += 4;
+                }
+                launch_limb_table(V, Lv, m_stream);
+                mark(); slots.push_back(T_LIMB_SOURCE);
+                m_launches += 1;
+            }
+            if (m_limb.ss_exact) {
+                launch_limb_phase(V, Lv, m_stream);
+                m_launches += 1;
+            }
+            launch_limb_integrate(V, Lv, m_stream);
+            mark(); slots.push_back(T_LIMB_INTEGRATE);
             m_launches += 1;
             continue;
         }
@@ -570,8 +703,8 @@ void DeviceEngine::solve_staged() {
 // device -> host copies of the results of staged wavelengths [w_begin, w_end) (radiance [nw][nlos]; weighting
 // functions [nout][nw_total][nlos], one strided copy per mapping)
 void DeviceEngine::copy_outputs(int w_begin, int w_end, double* radiance_host, cudaStream_t s) {
-    if (w_end <= w_begin || m_plan.nlos <= 0) return;
-    const size_t nlos = m_plan.nlos, n = (size_t)(w_end - w_begin), off = (size_t)w_begin * nlos;
+    if (w_end <= w_begin || m_nrad <= 0) return;
+    const size_t nlos = m_nrad, n = (size_t)(w_end - w_begin), off = (size_t)w_begin * nlos;
     CUDA_OK(cudaMemcpyAsync(radiance_host + off, d_radiance + off, sizeof(double) * n * nlos, cudaMemcpyDeviceToHost, s));
     if (m_wf_on) {
         const size_t width = sizeof(double) * n * nlos;
@@ -601,6 +734,13 @@ void DeviceEngine::fetch(double* radiance_host) {
     }
 }
 
+void DeviceEngine::fetch_los_optical_depth(double* host) {
+    CUDA_OK(cudaSetDevice(m_device));
+    if (!m_is_limb || !d_los_od) throw std::runtime_error("line-of-sight optical depths are produced by the spherical path only");
+    CUDA_OK(cudaMemcpyAsync(host, d_los_od, sizeof(double) * (size_t)m_nw * m_nrad, cudaMemcpyDeviceToHost, m_stream));
+    CUDA_OK(cudaStreamSynchronize(m_stream));
+}
+
 // Final gather of a wavelength-sharded solve: every rank holds its block's results on its device
 // (d_radiance [nw_r][nlos], per mapping [nout][nw_r][nlos], per surface mapping [nw_r][nlos]).  One NCCL group: the
 // other ranks send their arrays to the root over NVLink, the root receives them back to back into one staging buffer
@@ -610,7 +750,7 @@ void DeviceEngine::gather_to_root(Comm& comm, int root, const int* block_start, 
                                   double ms_out[2]) {
     CUDA_OK(cudaSetDevice(m_device));
     const int rank = comm.rank(), world = comm.world();
-    const size_t nlos = (size_t)std::max(m_plan.nlos, 0);
+    const size_t nlos = (size_t)std::max(m_nrad, 0);
     if (block_count[rank] != m_nw) throw std::runtime_error("gather_to_root: this rank's block size differs from the staged range");
     size_t per_w = nlos;  // doubles per wavelength over all outputs
     if (m_wf_on) {

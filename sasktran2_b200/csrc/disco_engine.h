@@ -8,6 +8,7 @@
 
 #include "disco_comm.h"
 #include "disco_kernels.cuh"
+#include "disco_limb.cuh"
 #include "disco_plan.h"
 
 namespace disco {
@@ -56,11 +57,14 @@ struct WfRequest {
     bool enabled() const { return !mappings.empty() || !surfaces.empty(); }
 };
 
-enum TimingSlot { T_H2D = 0, T_OPTICS, T_LAYER, T_BVP, T_RADIANCE, T_D2H, T_TOTAL_KERNELS, T_WF, T_WF_ADJOINT, T_WF_LAYER, T_WF_CHAIN, T_WF_MAP, T_NSLOTS };
+enum TimingSlot { T_H2D = 0, T_OPTICS, T_LAYER, T_BVP, T_RADIANCE, T_D2H, T_TOTAL_KERNELS, T_WF, T_WF_ADJOINT, T_WF_LAYER, T_WF_CHAIN, T_WF_MAP, T_LIMB_SOURCE, T_LIMB_INTEGRATE, T_NSLOTS };
 
 class DeviceEngine {
   public:
     DeviceEngine(const EngineOptions& opt, const HostPlan& plan);
+    // Spherical line-of-sight path: `plan` carries the stream tables and no lines of sight, `limb` the traced rays, the
+    // DO source-table layout and one (cos SZA, chapman) set per SZA of the DO grid.  Radiance columns = limb.nrays.
+    DeviceEngine(const EngineOptions& opt, const HostPlan& plan, const LimbPlan& limb);
     ~DeviceEngine();
     DeviceEngine(const DeviceEngine&) = delete;
     DeviceEngine& operator=(const DeviceEngine&) = delete;
@@ -71,6 +75,10 @@ class DeviceEngine {
     void solve_staged();
     // Copy radiance [nw, nlos] of the staged range back to the host.
     void fetch(double* radiance_host);
+    // limb path: line-of-sight optical depths [nw, nrays] of the staged range (after solve_staged)
+    void fetch_los_optical_depth(double* host);
+    bool limb() const { return m_is_limb; }
+    int radiance_columns() const { return m_nrad; }
     // stage + solve + fetch
     void calculate(const AtmosphereArrays& atm, int w0, int nw, double* radiance_host, const WfRequest* wf = nullptr);
     // Wavelength-sharded solve: after solve_staged() on every rank, collect the results of all ranks on `root` over
@@ -97,6 +105,8 @@ class DeviceEngine {
     void set_workspace_gb(double gb) { m_opt.workspace_gb = gb; }
 
   private:
+    void init(const EngineOptions& opt);
+    void init_limb();
     void free_inputs();
     void free_workspace();
     void ensure_workspace(int chunk);
@@ -160,6 +170,14 @@ class DeviceEngine {
     ChunkView m_view{};
     double m_ms[T_NSLOTS] = {};
     long long m_launches = 0;
+    // ---- spherical line-of-sight path
+    bool m_is_limb = false;
+    int m_nrad = 0;                 // radiance columns: DO lines of sight, or traced rays of the limb path
+    LimbPlan m_limb;
+    LimbView m_lview{};
+    std::vector<void*> m_limb_ptrs; // geometry tables on the device
+    std::vector<double*> d_sza_lp_csz, d_sza_chapman;   // per SZA of the DO grid
+    double* d_los_od = nullptr;     // [nw][nrays] of the staged range
 };
 
 }  // namespace disco

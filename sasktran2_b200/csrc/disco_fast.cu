@@ -27,7 +27,7 @@ static int wf_fast_blocks_per_order(int M) {
 template <int N>
 static void launch_fast_n(const ChunkView& V, cudaStream_t s) {
     const long long nq = (long long)V.nw * V.T.L;
-    {
+    if (V.T.nlos > 0) {   // the spherical path solves the layers without plane-parallel lines of sight
         const long long n = (long long)V.nw * V.T.nlos * (V.T.L + 1);
         k_los_atten<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V);
     }

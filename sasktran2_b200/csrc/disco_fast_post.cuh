@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
     const double albedo = V.albedo[w];
     const double trans_floor = V.lay_trans[(size_t)w * (L + 1) + L];
     // per-LOS scalars are fetched one iteration ahead (the loop is short on independent work to hide an L2 round trip)
-    double n_mu, n_att, n_E, n_inv, n_atop;
-    {
+    double n_mu = 1.0, n_att = 0.0, n_E = 0.0, n_inv = 0.0, n_atop = 0.0;
+    if (nlos > 0) {
         const double* ll0 = V.los_lay + (((size_t)w * nlos + 0) * L + p) * 3;
         n_mu = V.T.los_mu[0];
         n_att = ll0[0];

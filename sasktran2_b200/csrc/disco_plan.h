@@ -41,6 +41,9 @@ struct HostPlan {
     bool plane_parallel = true;
 };
 
+// Wigner function d^l_{m0}(acos coszen) (cpp/include/sasktran2/math/wigner.h:56-149)
+double wigner_dm0(int m, int l, double coszen);
+
 // Throws std::runtime_error with a reference-style message on unsupported / invalid input.
 HostPlan build_plan(int nstr, const GeometrySpec& geo, const std::vector<LineOfSight>& los);
 

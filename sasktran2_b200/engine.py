@@ -10,7 +10,7 @@ import numpy as np
 from . import _lib
 
 TIMING_NAMES = ("h2d", "optics", "layer", "bvp", "radiance", "d2h", "kernels_total", "wf", "wf_adjoint", "wf_layer",
-                "wf_chain", "wf_map")
+                "wf_chain", "wf_map", "limb_source", "limb_integrate")
 
 
 class Result(dict):
@@ -128,6 +128,13 @@ class Engine:
                 rc = _lib.lib().sk_engine_calculate_radiance_block_thread(self._engine, out, int(wavelength_block[0]),
                                                                           int(wavelength_block[1]), 0)
                 _lib.check(rc, "sk_engine_calculate_radiance_block_thread")
+            if self._config.output_los_optical_depth and self._geometry.geometry_type == 2:
+                # Output::los_optical_depth (src/sasktran2/engine.py: "los_optical_depth" [wavelength, los])
+                od = C.POINTER(C.c_double)()
+                _lib.check(_lib.lib().sk_output_get_los_optical_depth(out, C.byref(od)), "sk_output_get_los_optical_depth")
+                nw, nlos = res["radiance"].shape[:2]
+                res["los_optical_depth"] = np.ctypeslib.as_array(od, shape=(nlos, nw)).T.copy()
+                res.dims["los_optical_depth"] = ("wavelength", "los")
         finally:
             _lib.lib().sk_output_destroy(out)
         if atmosphere.wavelengths_nm is not None:

@@ -17,6 +17,16 @@ class GroundViewingSolar:
     observer_altitude_m: float
 
 
+@dataclass
+class TangentAltitudeSolar:
+    """A limb line of sight through a tangent point given by its altitude and solar angles (spherical geometry only,
+    cpp/lib/viewinggeometry/tangentaltitudesolar.cpp:5-62)."""
+    tangent_altitude_m: float
+    relative_azimuth: float
+    observer_altitude_m: float
+    cos_sza: float
+
+
 class ViewingGeometry:
     def __init__(self):
         self._viewing_geometry = _lib.lib().sk_viewing_geometry_create()
@@ -30,11 +40,16 @@ class ViewingGeometry:
             pass
 
     def add_ray(self, ray) -> None:
-        if not isinstance(ray, GroundViewingSolar):
-            raise NotImplementedError("the B200 DO path supports GroundViewingSolar rays only")
-        _lib.lib().sk_viewing_geometry_add_ground_viewing_solar(
-            self._viewing_geometry, float(ray.cos_sza), float(ray.relative_azimuth), float(ray.observer_altitude_m),
-            float(ray.cos_viewing_zenith))
+        if isinstance(ray, TangentAltitudeSolar):
+            _lib.check(_lib.lib().sk_viewing_geometry_add_tangent_altitude_solar(
+                self._viewing_geometry, float(ray.tangent_altitude_m), float(ray.relative_azimuth),
+                float(ray.observer_altitude_m), float(ray.cos_sza)), "add_tangent_altitude_solar")
+        elif isinstance(ray, GroundViewingSolar):
+            _lib.lib().sk_viewing_geometry_add_ground_viewing_solar(
+                self._viewing_geometry, float(ray.cos_sza), float(ray.relative_azimuth), float(ray.observer_altitude_m),
+                float(ray.cos_viewing_zenith))
+        else:
+            raise NotImplementedError("the B200 path supports GroundViewingSolar and TangentAltitudeSolar rays")
         self.observer_rays.append(ray)
 
     @property

@@ -50,6 +50,9 @@ CONFIGS = {
                text="pseudo-spherical DO, 16 streams, 100 layers, Rayleigh+aerosol, 10 nadir LOS, 100,000 wavelengths, radiances only"),
     "c1": dict(label="configs[0] (C1)", nwavel=1000, nstr=4, layers=50, nlos=1, wf=False,
                text="plane-parallel DO, 4 streams, 50 layers, Rayleigh+O3, 1 nadir LOS, 1,000 wavelengths"),
+    "c4": dict(label="configs[3] (C4)", nwavel=10000, nstr=16, layers=100, nlos=100, wf=False,
+               text="OSIRIS-style limb: spherical geometry, exact single scatter + 16-stream DO multiple-scatter source table "
+                    "(2 SZAs), 100 tangent-altitude LOS (10-60 km), 100 layers, 10,000 wavelengths"),
     "c3": dict(label="configs[2] (C3)", nwavel=1000000, nstr=2, layers=60, nlos=2, wf=False,
                text="two-stream source (num_streams=2, multiple scatter only), 60 layers, 2 nadir LOS, 1,000,000 line-by-line "
                     "wavelengths (O2 A-band like)"),
@@ -180,6 +183,8 @@ def build_scenario(cfg_name, nw_total, block, nlos=None, layers=None, nstr=None)
         return sc
     if cfg_name == "c3":
         return scenarios.config3(nwavel=nw_total, nlayers=layers, nlos=nlos, block=block)
+    if cfg_name == "c4":
+        return scenarios.config4(nwavel=nw_total, nlayers=layers, nstr=nstr, nrays=nlos, block=block)
     raise ValueError(cfg_name)
 
 
@@ -193,15 +198,22 @@ def make_engine(sc, cfg_name, total_wavelengths=None, start=0):
     if cfg_name == "c3":
         cfg.multiple_scatter_source = sk.MultipleScatterSource.TwoStream
         cfg.single_scatter_source = sk.SingleScatterSource.NoSource
+    elif cfg_name == "c4":
+        cfg.multiple_scatter_source = sk.MultipleScatterSource.DiscreteOrdinates
+        cfg.single_scatter_source = sk.SingleScatterSource.Exact
+        cfg.num_sza = sc.num_sza
+        cfg.num_singlescatter_moments = sc.leg_coeff.shape[0]
     else:
         cfg.multiple_scatter_source = sk.MultipleScatterSource.DiscreteOrdinates
         cfg.single_scatter_source = sk.SingleScatterSource.DiscreteOrdinates
     cfg.do_backprop = True
-    geo = sk.Geometry1D(sc.cos_sza, 0.0, sc.earth_radius, sc.altitudes, sk.InterpolationMethod(sc.interp),
+    geo = sk.Geometry1D(sc.cos_sza, sc.saa, sc.earth_radius, sc.altitudes, sk.InterpolationMethod(sc.interp),
                         sk.GeometryType(sc.geotype))
     view = sk.ViewingGeometry()
     for cz, az in zip(sc.los_cos_vza, sc.los_rel_az):
         view.add_ray(sk.GroundViewingSolar(sc.cos_sza, float(az), float(cz), sc.observer_altitude))
+    for r in sc.rays:
+        view.add_ray(sk.TangentAltitudeSolar(*r[1:5]) if r[0] == "tangent" else sk.GroundViewingSolar(*r[1:5]))
     eng = sk.Engine(cfg, geo, view)
     atm = sk.Atmosphere.from_scenario(sc, geo, cfg, total_wavelengths=total_wavelengths, wavelength_start=start)
     if sc.mappings:
@@ -226,6 +238,13 @@ def run_oracle(sc, pick, threads, cfg_name, stable=False):
     if cfg_name == "c3":
         t0 = time.perf_counter()
         out = oracle.twostream_radiance(**{k: v for k, v in inp.items() if k != "nstr"}, nthreads=threads)
+        return out, time.perf_counter() - t0
+    if cfg_name == "c4":
+        t0 = time.perf_counter()
+        out = oracle.limb_radiance(nstr=sc.nstr, alt=sc.altitudes, interp=sc.interp, cos_sza=sc.cos_sza, saa=sc.saa,
+                                   earth_radius=sc.earth_radius, rays=sc.rays, num_sza=sc.num_sza, ms_do=True, ss_exact=True,
+                                   num_ss_moments=sc.leg_coeff.shape[0], ssa=inp["ssa"], ext=inp["ext"], leg=inp["leg"],
+                                   albedo=inp["albedo"], nthreads=threads, exact_tangent=stable)
         return out, time.perf_counter() - t0
     if CONFIGS[cfg_name]["wf"]:
         aer = sc.mappings["wf_aerosol_extinction"]["d_legendre"]
@@ -368,7 +387,7 @@ def quick_config(cfg_name, steps, warmup, local_rank, threads):
            "e2e": {"value": units / (e2e_ms * 1e-3), "ms_per_step": e2e_ms},
            "hbm_view": {"achieved_gbs": gbs, "bytes_per_wavelength": bytes_model(sc.nloc, nleg, sc.nlos)},
            "kernel_ms": {k: v for k, v in eng.timings_ms().items() if v > 0 and k not in ("h2d", "d2h")},
-           "parity": parity_sample(sc, cfg_name, res, 16, threads), "setup_s": time.perf_counter() - t0}
+           "parity": parity_sample(sc, cfg_name, res, 8 if cfg_name == "c4" else 16, threads), "setup_s": time.perf_counter() - t0}
     return out
 
 
@@ -666,7 +685,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_other_configs:
         del result, buffers
         others = {}
-        for name in ("c2", "c1", "c3"):
+        for name in ("c2", "c1", "c3", "c4"):
             if name == args.config:
                 continue
             try:

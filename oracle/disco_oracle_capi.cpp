@@ -241,6 +241,9 @@ int oracle_twostream_radiance(int nloc, int nwavel, int nleg, int nlos, const do
     }
 }
 
+// 1: tangent-layer lengths without the reference's rounding-dependent 0.1 m error (limb_oracle.hpp, exact_tangent_ref)
+void oracle_set_exact_tangent(int on) { oracle::limb::exact_tangent_ref() = on; }
+
 // Spherical line-of-sight path (limb_oracle.hpp).  rays: [nrays][5] = kind (0 GroundViewingSolar(cos_sza, rel_az, cos_vza,
 // observer_altitude), 1 TangentAltitudeSolar(tangent_altitude, rel_az, observer_altitude, cos_sza)) followed by the four
 // constructor arguments.  ms_do: multiple_scatter_source = DiscreteOrdinates (interpolated DO source table);

@@ -200,7 +200,20 @@ struct Grid {
 // ---------------------------------------------------------------------------------------------------
 //  Traced rays: include/sasktran2/raytracing.h:40-120 (LayerGeometry), lib/raytracing/spherical_shell.cpp
 // ---------------------------------------------------------------------------------------------------
+// The reference computes a tangent layer's length as | sqrt(r_far^2 - rt^2) - sqrt(max(r_tan^2 - rt^2, 0)) | with
+// r_tan = (rt - R) + R (spherical_shell.cpp:176-184, 300-346).  r_tan differs from rt by one rounding (~1e-9 m), so
+// r_tan^2 - rt^2 is either <= 0 (clamped: exact) or ~ +1e-2 m^2, whose square root shortens BOTH tangent layers by
+// ~0.1 m - a rounding-direction dependent error of up to ~3e-7 of a limb optical depth (the reference's golden limb
+// optical depths carry it: 2.1e-7 off the exact integral, inside its 5e-7 cross-platform tolerance).  With this flag set
+// the tangent end contributes exactly 0 (NOT the reference's arithmetic; used by the tests to separate that noise from
+// real differences).  Default off.
+inline int& exact_tangent_ref() {
+    static int flag = 0;
+    return flag;
+}
+
 struct Layer {
+    int tangent_end = 0;       // 0: none, 1: the entrance is the tangent point, 2: the exit is
     Location entrance, exit;   // entrance: the boundary closer to the observer
     double r_entrance = 0, r_exit = 0;
     V3 average_look_away;
@@ -352,6 +365,7 @@ struct RayTracer {  // SphericalShellRayTracer, straight rays
             exact = true;
         }
         double entrance_altitude, exit_altitude;
+        layer.tangent_end = direction == -1 ? 1 : 2;
         if (direction == -1) {  // ViewingDirection::up
             entrance_altitude = tangent_altitude;
             exit_altitude = alt[upper_index];
@@ -457,8 +471,11 @@ struct RayTracer {  // SphericalShellRayTracer, straight rays
                 const Layer& prev = r.layers[nl - i];
                 layer.entrance.position = prev.exit.position;  // flags of the entrance keep this layer's own values
             }
-            layer.layer_distance = std::abs(std::sqrt(std::fmax(layer.r_entrance * layer.r_entrance - rt * rt, 0)) -
-                                            std::sqrt(std::fmax(layer.r_exit * layer.r_exit - rt * rt, 0.0)));
+            double se = std::sqrt(std::fmax(layer.r_entrance * layer.r_entrance - rt * rt, 0));
+            double sx = std::sqrt(std::fmax(layer.r_exit * layer.r_exit - rt * rt, 0.0));
+            if (exact_tangent_ref() && layer.tangent_end == 1) se = 0.0;
+            if (exact_tangent_ref() && layer.tangent_end == 2) sx = 0.0;
+            layer.layer_distance = std::abs(se - sx);
             layer.average_look_away = r.observer_and_look.look_away;
             layer.exit.position = layer.entrance.position + layer.average_look_away * layer.layer_distance;
             add_od_quadrature(layer, geo.alt.interp);

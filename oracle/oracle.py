@@ -285,10 +285,13 @@ def _ray_table(rays):
 
 
 def limb_radiance(*, nstr, alt, interp, cos_sza, saa=0.0, earth_radius=6372000.0, rays, num_sza=2, ms_do=True,
-                  ss_exact=False, num_ss_moments=16, ssa, ext, leg, solar=None, albedo, nthreads=0):
+                  ss_exact=False, num_ss_moments=16, ssa, ext, leg, solar=None, albedo, nthreads=0, exact_tangent=False):
     """Spherical line-of-sight path (oracle/limb_oracle.hpp): DO multiple-scatter source table interpolated onto the
-    traced rays (+ exact single scatter when ss_exact).  Returns dict(radiance [nwavel, nrays], los_optical_depth)."""
+    traced rays (+ exact single scatter when ss_exact).  Returns dict(radiance [nwavel, nrays], los_optical_depth).
+    exact_tangent=True removes the reference's rounding-dependent ~0.1 m error of the tangent-layer lengths (see
+    limb_oracle.hpp, exact_tangent_ref); default is the reference's arithmetic."""
     L = lib()
+    L.oracle_set_exact_tangent(int(exact_tangent))
     alt = np.ascontiguousarray(alt, dtype=np.float64)
     ssa = np.asfortranarray(ssa, dtype=np.float64)
     ext = np.asfortranarray(ext, dtype=np.float64)
@@ -309,11 +312,12 @@ def limb_radiance(*, nstr, alt, interp, cos_sza, saa=0.0, earth_radius=6372000.0
     return dict(radiance=rad, los_optical_depth=od)
 
 
-def limb_geometry(*, alt, interp, cos_sza, saa=0.0, earth_radius=6372000.0, rays, max_layers=512):
+def limb_geometry(*, alt, interp, cos_sza, saa=0.0, earth_radius=6372000.0, rays, max_layers=512, exact_tangent=False):
     """Traced-ray geometry of the limb oracle: dict(nlayers [nrays], ground_hit [nrays], layers [nrays, max_layers, 9])
     with per layer (layer_distance, od_quad_start, od_quad_end, cos_sza_entrance, cos_sza_exit, saz_entrance, saz_exit,
     r_entrance, r_exit); layers[0] is the one farthest from the observer."""
     L = lib()
+    L.oracle_set_exact_tangent(int(exact_tangent))
     alt = np.ascontiguousarray(alt, dtype=np.float64)
     tab = _ray_table(rays)
     n = len(rays)

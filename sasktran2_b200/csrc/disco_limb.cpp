@@ -127,6 +127,7 @@ struct EndPoint {
 struct Seg {
     EndPoint near_pt, far_pt;        // near: the end closer to the observer ("entrance" upstream)
     double r_near = 0, r_far = 0;
+    int tangent_end = 0;             // 1: the near end is the tangent point, 2: the far end is
     Vec look{0, 0, 0};
     double length = 0;
     double q_near = 0, q_far = 0, qf_near = 0.5, qf_far = 0.5;   // optical-depth quadrature coefficients and their fractions
@@ -189,6 +190,7 @@ struct Tracer {
             ti = upper;
             exact = true;
         }
+        s.tangent_end = far_side ? 1 : 2;
         if (far_side) {  // near end = tangent point, far end = the grid altitude above it
             s.r_near = tangent_alt + re();
             s.r_far = alt[upper] + re();
@@ -286,8 +288,13 @@ struct Tracer {
             } else {
                 s.near_pt.pos = p.segs[n - i].far_pt.pos;
             }
-            s.length = std::abs(std::sqrt(std::fmax(s.r_near * s.r_near - rt * rt, 0.0)) -
-                                std::sqrt(std::fmax(s.r_far * s.r_far - rt * rt, 0.0)));
+            // Along-ray coordinate of both ends measured from the tangent point.  The reference evaluates
+            // sqrt(max(r^2 - rt^2, 0)) for the tangent end too, with r = (rt - R) + R one rounding away from rt: depending
+            // on the rounding direction both tangent segments come out ~0.1 m short (up to 3e-7 of a limb optical depth;
+            // its own golden limb optical depths are 2.1e-7 off the exact integral).  Here the tangent end is exactly 0.
+            const double t_near = s.tangent_end == 1 ? 0.0 : std::sqrt(std::fmax(s.r_near * s.r_near - rt * rt, 0.0));
+            const double t_far = s.tangent_end == 2 ? 0.0 : std::sqrt(std::fmax(s.r_far * s.r_far - rt * rt, 0.0));
+            s.length = std::abs(t_near - t_far);
             s.far_pt.pos = s.near_pt.pos + p.look * s.length;
             quadrature(s);
             stencils(s);

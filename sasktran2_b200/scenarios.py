@@ -34,6 +34,11 @@ class Scenario:
     # weighting-function mappings: name -> dict(d_extinction, d_ssa [nloc,nw] F, optional d_legendre
     # [nleg,nloc,nw] F + scat_factor [nloc,nw] F)
     mappings: dict = field(default_factory=dict)
+    # spherical (limb) scenarios: rays in the oracle's notation, ("tangent", tangent_altitude, rel_az, observer_altitude,
+    # cos_sza) / ("ground", cos_sza, rel_az, cos_vza, observer_altitude); SZAs of the DO source table; solar azimuth
+    rays: list = field(default_factory=list)
+    num_sza: int = 1
+    saa: float = 0.0
 
     @property
     def nwavel(self) -> int:
@@ -45,7 +50,7 @@ class Scenario:
 
     @property
     def nlos(self) -> int:
-        return self.los_cos_vza.size
+        return len(self.rays) if self.rays else self.los_cos_vza.size
 
 
 # Grey continuum absorption as a fraction of the Rayleigh extinction.  It keeps every layer's single-scatter
@@ -155,6 +160,21 @@ def config2(nwavel: int = 100000, nlayers: int = 100, nstr: int = 16, nlos: int 
         sc.mappings["wf_aerosol_extinction"] = dict(d_extinction=np.asfortranarray(d_ext), d_ssa=np.asfortranarray(d_ssa),
                                                     d_legendre=np.asfortranarray(d_leg),
                                                     scat_factor=np.asfortranarray(scat_factor))
+    return sc
+
+
+def config4(nwavel: int = 10000, nlayers: int = 100, nstr: int = 16, nrays: int = 100, num_sza: int = 2,
+            block: tuple[int, int] | None = None) -> Scenario:
+    """C4: OSIRIS-style limb scan in spherical geometry: exact single scatter + discrete-ordinates multiple-scatter
+    source, `nrays` TangentAltitudeSolar lines of sight (tangent altitudes linspace(10, 60 km), relative azimuth 0.3,
+    observer at 200 km, cos_sza 0.6), `num_sza` SZAs for the DO source table, the C2 atmosphere."""
+    sc = config2(nwavel=nwavel, nlayers=nlayers, nstr=nstr, nlos=1, with_wf=False, block=block)
+    sc.name = "C4"
+    sc.geotype = 2
+    sc.los_cos_vza = np.zeros(0)
+    sc.los_rel_az = np.zeros(0)
+    sc.rays = [("tangent", float(h), 0.3, 200e3, sc.cos_sza) for h in np.linspace(10e3, 60e3, nrays)]
+    sc.num_sza = num_sza
     return sc
 
 

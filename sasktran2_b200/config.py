@@ -50,3 +50,4 @@ class Config:
     wf_precision = _int_prop("wf_precision", WeightingFunctionPrecision)
     log_level = _int_prop("log_level")
     output_los_optical_depth = _int_prop("output_los_optical_depth", bool)
+    input_validation_mode = _int_prop("input_validation_mode")

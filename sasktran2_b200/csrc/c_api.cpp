@@ -766,6 +766,7 @@ static Engine* create_limb_engine(Config* config, Geometry1D* geometry, ViewingG
         disco::EngineOptions opt;
         opt.nstr = config->num_streams;
         opt.include_ss = false;
+        opt.validate_inputs = config->input_validation_mode != 2;
         opt.forced_azimuth = -1;   // DOSource::calculate loops over all num_do_streams orders (do_source.cpp:47-57)
         if (const char* env = std::getenv("SK_B200_WORKSPACE_GB")) opt.workspace_gb = std::atof(env);
         e->dev = std::make_unique<disco::DeviceEngine>(opt, plan, limb);
@@ -848,6 +849,7 @@ Engine* sk_engine_create(Config* config, Geometry1D* geometry, ViewingGeometry* 
         opt.include_ss = config->single_scatter_source == 2;
         opt.forced_azimuth = config->num_do_forced_azimuth;
         opt.twostream = config->multiple_scatter_source == 2;
+        opt.validate_inputs = config->input_validation_mode != 2;   // InputValidationMode::disabled
         if (const char* env = std::getenv("SK_B200_WORKSPACE_GB")) opt.workspace_gb = std::atof(env);
         e->dev = std::make_unique<disco::DeviceEngine>(opt, plan);
         return e;

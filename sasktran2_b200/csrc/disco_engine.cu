@@ -586,6 +586,10 @@ void DeviceEngine::solve_staged() {
         V.dleg_gstride = (size_t)m_nleg * nloc * m_nw;
         V.fdm = m_has_f ? d_fdm + nloc * w0 : nullptr;
         V.fdm_gstride = nloc * (size_t)m_nw;
+        if (m_opt.validate_inputs) {
+            launch_validate_inputs(V, m_stream);
+            m_launches += 1;
+        }
         if (twostream_direct()) {
             launch_twostream(V, m_stream);
             mark(); slots.push_back(T_LAYER);
@@ -693,6 +697,12 @@ void DeviceEngine::solve_staged() {
     m_ms[T_TOTAL_KERNELS] = tot;
     unsigned int st = 0;
     CUDA_OK(cudaMemcpy(&st, d_status, sizeof(st), cudaMemcpyDeviceToHost));
+    // input validation (cpp/include/sasktran2/validation/validation.h:12-64) comes first: bad inputs also trip the solver bits
+    if (st & 8u) throw std::runtime_error("Invalid input: Atmosphere total extinction contains non-finite values");
+    if (st & 16u) throw std::runtime_error("Invalid input: Atmosphere total extinction contains values less than 0");
+    if (st & 32u) throw std::runtime_error("Invalid input: Atmosphere single scatter albedo contains non-finite values");
+    if (st & 64u) throw std::runtime_error("Invalid input: Atmosphere single scatter albedo contains values less than 0");
+    if (st & 128u) throw std::runtime_error("Invalid input: Atmosphere single scatter albedo contains values greater than 1");
     if (st & 1u) throw std::runtime_error("DO homogeneous solution: S- is not positive definite (invalid phase moments?)");
     if (st & 2u)
         throw std::runtime_error(

@@ -20,6 +20,7 @@ struct EngineOptions {
     bool twostream = false;     // multiple_scatter_source == TwoStream: dedicated closed-form kernel when no weighting functions are asked
     double workspace_gb = -1.0; // per-chunk workspace budget; < 0: min(32 GB, a quarter of the free device memory)
     int device = -1;            // -1: current device
+    bool validate_inputs = true; // config.input_validation_mode != disabled: device pre-pass over extinction / SSA
 };
 
 // Caller-owned host arrays in the reference's C-ABI layouts (cpp/include/c_api/atmosphere.h:86-91)

@@ -32,10 +32,61 @@ __global__ void k_layer_optics(ChunkView V) {
 // -------------------------------------------------------------------------------------------------
 // K1b: thickness scan + solar beam
 // -------------------------------------------------------------------------------------------------
-__global__ void k_beam(ChunkView V) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per wavelength (beam_body in disco_bodies.h is the serial statement used by the host emulation): lane 0
+// runs the thickness scan in the reference's summation order, then the lanes share the O(L^2) chapman products - the
+// one-thread-per-wavelength version kept 3 % of the warps of 10 blocks busy for 2 % of a step.
+__global__ void __launch_bounds__(128) k_beam(ChunkView V) {
+    const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
     if (w >= V.nw) return;
-    beam_body(V, w);
+    const int L = V.T.L;
+    double* od = V.lay_od + (size_t)w * L;
+    double* cum = V.lay_cumod + (size_t)w * (L + 1);
+    double* sec = V.lay_secant + (size_t)w * L;
+    double* tr = V.lay_trans + (size_t)w * (L + 1);
+    if (lane == 0) {
+        double ceiling = 0.0, floor_d = 0.0;
+        cum[0] = 0.0;
+        for (int p = 0; p < L; ++p) {
+            floor_d += od[p];
+            od[p] = floor_d - ceiling;  // M_OPTICAL_THICKNESS (sktran_do_opticallayer.cpp:21)
+            ceiling = floor_d;
+            cum[p + 1] = floor_d;
+        }
+    }
+    __syncwarp();
+    const double f0 = V.solar[w];
+    if (lane == 0) tr[0] = f0;
+    // slant optical depth to the floor of layer p; the one to its ceiling (p - 1) is recomputed by the same lane so
+    // that no cross-lane exchange is needed
+    for (int p = lane; p < L; p += 32) {
+        const double* ch = V.chapman + (size_t)p * L;
+        double slant = 0.0;
+        for (int q = 0; q <= p; ++q) slant += ch[q] * od[q];
+        double prev = 0.0;
+        if (p > 0) {
+            const double* chp = V.chapman + (size_t)(p - 1) * L;
+            for (int q = 0; q < p; ++q) prev += chp[q] * od[q];
+        }
+        sec[p] = (slant - prev) / od[p];
+        tr[p + 1] = exp(-slant) * f0;
+    }
+}
+
+// Input validation pre-pass (Sasktran2::validate_input_atmosphere, cpp/lib/engine/engine.cpp:481-540;
+// cpp/include/sasktran2/validation/validation.h:12-64): extinction finite and >= 0, single-scatter albedo finite and
+// in [0, 1].  One thread per (grid point, wavelength) of the chunk; offenders raise status bits 8 .. 128.
+__global__ void k_validate_inputs(ChunkView V) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)V.nw * V.T.nloc) return;
+    const double k = V.ext[idx], a = V.ssa[idx];
+    unsigned bits = 0u;
+    if (!isfinite(k)) bits |= 8u;
+    else if (k < 0.0) bits |= 16u;
+    if (!isfinite(a)) bits |= 32u;
+    else if (a < 0.0) bits |= 64u;
+    else if (a > 1.0) bits |= 128u;
+    if (bits) atomicOr(V.status, bits);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -89,7 +140,11 @@ void launch_layer_optics(const ChunkView& V, cudaStream_t s) {
     const long long n = (long long)V.nw * V.T.L;
     k_layer_optics<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V);
 }
-void launch_beam(const ChunkView& V, cudaStream_t s) { k_beam<<<(V.nw + 63) / 64, 64, 0, s>>>(V); }
+void launch_beam(const ChunkView& V, cudaStream_t s) { k_beam<<<(unsigned)(((long long)V.nw * 32 + 127) / 128), 128, 0, s>>>(V); }
+void launch_validate_inputs(const ChunkView& V, cudaStream_t s) {
+    const long long n = (long long)V.nw * V.T.nloc;
+    if (n > 0) k_validate_inputs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(V);
+}
 
 template <int N>
 static void launch_layer_solve_n(const ChunkView& V, cudaStream_t s) {

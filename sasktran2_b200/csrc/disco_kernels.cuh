@@ -23,6 +23,7 @@ struct DeviceOnce {
 
 void launch_layer_optics(const ChunkView& V, cudaStream_t s);
 void launch_beam(const ChunkView& V, cudaStream_t s);
+void launch_validate_inputs(const ChunkView& V, cudaStream_t s);
 void launch_layer_solve(const ChunkView& V, cudaStream_t s);
 // register-resident path for N = 2, 4, 8 (disco_fast*.cuh); needs the eig*/los_* planes and vsrc_w = N
 bool fast_path_supported(int N);

@@ -80,7 +80,8 @@ static void launch_wf_fast_n(const ChunkView& V, cudaStream_t s) {
 size_t wf_layer_fast_smem_bytes(int N, int G, int nlos) {
     const int nstr = 2 * N, NL = G + 4, NH = G + 1, ppb = (32 / N) * 4;
     const int exch = nstr * N + 2 * N * N + 2 * N, red = nlos * (NL + 1) * N;
-    const int per_problem = nlos * 2 * NH * N + (red > exch ? red : exch) + 2;  // WfCfg::per_problem
+    const int raw = nlos * 2 * NH * N + (red > exch ? red : exch);
+    const int per_problem = raw + ((4 - raw % 16) + 16) % 16;  // WfCfg::per_problem
     return sizeof(double) * (size_t)(2 * nstr * N + nlos * nstr + nstr + N + ppb * per_problem);
 }
 void launch_wf_layer_fast(const ChunkView& V, cudaStream_t s) {

@@ -90,10 +90,16 @@ struct WfCfg {
     static constexpr int EXCH = NSTR * N + 2 * N * N + 2 * N;  // projs | Xs | Xms | lam, pad
     __host__ __device__ static constexpr int lps_doubles(int nlos) { return nlos * 2 * NH * N; }
     __host__ __device__ static constexpr int red_doubles(int nlos) { return nlos * (NL + 1) * N; }
-    // + 2 doubles: the problems of a warp read their private areas at the same offset in the same instruction; a
-    // 16-byte skew per problem puts those broadcasts on different banks (without it every LDS is a 32/N-way conflict)
+    // Skew between the private areas of a warp's 32/N problems: the stride is padded to 4 (mod 16) doubles = 8 banks.
+    // Broadcast reads (every problem its own address, LDS.64 / LDS.128) then land on disjoint banks, and the "lane j
+    // writes element j" stores of the 32/N problems (N consecutive doubles each) overlap at most two deep, the minimum
+    // for 256 bytes.  (The former 2-double skew left the stores four deep: 38 % of this kernel's shared wavefronts
+    // were bank conflicts in profiles/ncu_r02_v1_summary.csv.)
+    __host__ __device__ static constexpr int per_problem_raw(int nlos) {
+        return lps_doubles(nlos) + (red_doubles(nlos) > EXCH ? red_doubles(nlos) : EXCH);
+    }
     __host__ __device__ static constexpr int per_problem(int nlos) {
-        return lps_doubles(nlos) + (red_doubles(nlos) > EXCH ? red_doubles(nlos) : EXCH) + 2;
+        return per_problem_raw(nlos) + ((4 - per_problem_raw(nlos) % 16) + 16) % 16;
     }
     // block tables: tW[NSTR][N] | tM[NSTR][N] | tL[nlos][NSTR] | lpc[NSTR] | wmu[N]
     __host__ __device__ static constexpr int table_doubles(int nlos) { return 2 * NSTR * N + nlos * NSTR + NSTR + N; }

@@ -236,7 +236,7 @@ def test_cuda_dedicated_twostream_kernel_vs_oracle(oracle_mod, geotype, nlos):
             atm.storage.solar_irradiance[:] = solar
         eng = sk.Engine(cfg, geo, view)
         rad = eng.calculate_radiance(atm)["radiance"][:, :, 0].copy()
-        assert eng.kernel_launches() == 1          # the dedicated kernel, not the discrete-ordinates pipeline
+        assert eng.kernel_launches() == 2          # input validation + the dedicated kernel, not the discrete-ordinates pipeline
         return rad
 
     c3 = scn.config3(nwavel=20000, nlayers=60, nlos=nlos)

@@ -16,7 +16,7 @@ from .engine import Engine
 from . import scenarios
 
 
-def engine_for_scenario(sc, num_threads: int = 1, do_backprop: bool = True):
+def engine_for_scenario(sc, num_threads: int = 1, do_backprop: bool = True, input_validation: bool = True):
     """Build (config, geometry, viewing geometry, engine, atmosphere) for a synthetic Scenario."""
     cfg = Config()
     cfg.num_streams = sc.nstr
@@ -24,6 +24,8 @@ def engine_for_scenario(sc, num_threads: int = 1, do_backprop: bool = True):
     cfg.multiple_scatter_source = MultipleScatterSource.DiscreteOrdinates
     cfg.single_scatter_source = SingleScatterSource.DiscreteOrdinates
     cfg.do_backprop = do_backprop
+    if not input_validation:
+        cfg.input_validation_mode = 2   # InputValidationMode::disabled
     geo = Geometry1D(sc.cos_sza, 0.0, sc.earth_radius, sc.altitudes, InterpolationMethod(sc.interp),
                      GeometryType(sc.geotype))
     view = ViewingGeometry()

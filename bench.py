@@ -375,16 +375,24 @@ def quick_config(cfg_name, steps, warmup, local_rank, threads):
         ms += eng.timings_ms()["kernels_total"]
     ms /= steps
     res = eng.fetch()
+    # end to end: page-locked caller buffers (sk_b200_host_register on the input arrays, result arrays from sk_b200_host_alloc)
+    lib = sk._lib.lib()
+    ins = [atm.storage.ssa, atm.storage.total_extinction, atm.storage.leg_coeff, atm.storage.solar_irradiance, atm.surface.albedo]
+    registered = [a for a in ins if lib.sk_b200_host_register(a.ctypes.data, a.nbytes) == 0]
     eng.calculate_radiance(atm)
     t1 = time.perf_counter()
     for _ in range(steps):
         res = eng.calculate_radiance(atm)
     e2e_ms = (time.perf_counter() - t1) * 1e3 / steps
+    for a in registered:
+        lib.sk_b200_host_unregister(a.ctypes.data)
     units = float(sc.nwavel * sc.nlos)
     nleg = sc.leg_coeff.shape[0]
     gbs = bytes_model(sc.nloc, nleg, sc.nlos) * sc.nwavel / (ms * 1e-3) / 1e9
     out = {"workload": f"{c['label']}: {c['text']}", "value": units / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-           "e2e": {"value": units / (e2e_ms * 1e-3), "ms_per_step": e2e_ms},
+           "e2e": {"value": units / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "pinned": len(registered) == len(ins),
+                   "h2d_bytes_per_step": int(sum(a.nbytes for a in ins)), "d2h_bytes_per_step": int(8 * units)},
+           "gpu_launches": int(eng.kernel_launches()),
            "hbm_view": {"achieved_gbs": gbs, "bytes_per_wavelength": bytes_model(sc.nloc, nleg, sc.nlos)},
            "kernel_ms": {k: v for k, v in eng.timings_ms().items() if v > 0 and k not in ("h2d", "d2h")},
            "parity": parity_sample(sc, cfg_name, res, 8 if cfg_name == "c4" else 16, threads), "setup_s": time.perf_counter() - t0}
@@ -444,6 +452,31 @@ def main():
     reduce_sum = lambda x: reduce(x, dist.ReduceOp.SUM if world > 1 else None)  # noqa: E731
 
     c = CONFIGS[args.config]
+    if args.config in ("c1", "c3", "c4"):
+        # named workloads other than the headline: one single-GPU line in the contract's format
+        if world > 1:
+            raise SystemExit("bench.py: --config c1 / c3 / c4 are single-GPU lines (the scaling run is the default config)")
+        sk._lib.check(sk._lib.lib().sk_b200_set_device(local_rank), "set_device")
+        if args.nwavel > 0:
+            CONFIGS[args.config] = dict(c, nwavel=args.nwavel)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        q = quick_config(args.config, args.steps, args.warmup, local_rank, os.cpu_count() or 1)
+        clocks = sampler.stop()
+        if not q["parity"]["ok"]:
+            raise SystemExit(f"bench.py: timed outputs disagree with the oracle: {q['parity']}")
+        line = {"metric": METRIC, "value": q["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": q["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": {"workload": q["workload"]}, "clocks": clocks,
+                "e2e": dict(q["e2e"], unit=UNIT), "gpu_launches": q["gpu_launches"], "kernel_ms_per_step": q["kernel_ms"],
+                "roofline": {"bound": "hbm", "achieved": q["hbm_view"]["achieved_gbs"], "unit": "GB/s",
+                             "peak": json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs", 6650.0)
+                             if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0,
+                             "traffic": None, "note": "algorithmic input + output bytes over the device-resident step time"},
+                "parity_check": q["parity"]}
+        line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
+        print(json.dumps(line), flush=True)
+        return
     nw_total = args.nwavel if args.nwavel > 0 else c["nwavel"]
     with_wf = c["wf"]
     starts, counts = zip(*[wavelength_block(nw_total, r, world) for r in range(world)])

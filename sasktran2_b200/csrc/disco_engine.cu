@@ -93,6 +93,7 @@ void DeviceEngine::init_limb() {
     Lv.sol_idx = upload_tracked(P.sol_idx, own);
     Lv.sol_w = upload_tracked(P.sol_w, own);
     Lv.sol_blocked = upload_tracked(P.sol_blocked, own);
+    Lv.ray_order = upload_tracked(P.ray_order, own);
     for (const HostPlan& sp : P.sza_plans) {
         d_sza_lp_csz.push_back(upload_tracked(sp.lp_csz, own));
         d_sza_chapman.push_back(upload_tracked(sp.chapman, own));

@@ -595,6 +595,11 @@ LimbPlan build_limb_plan(int nstr, const GeometrySpec& geo, const std::vector<Li
             }
     }
     P.nbnd = (int)P.sol_blocked.size();
+    P.ray_order.resize(P.nrays);
+    for (int r = 0; r < P.nrays; ++r) P.ray_order[r] = r;
+    std::stable_sort(P.ray_order.begin(), P.ray_order.end(), [&](int a, int b) {
+        return P.seg_start[a + 1] - P.seg_start[a] > P.seg_start[b + 1] - P.seg_start[b];
+    });
     return P;
 }
 

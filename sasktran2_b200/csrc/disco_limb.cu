@@ -14,10 +14,13 @@
 //   k_limb_integrate thread per (ray, wavelength): SourceIntegrator::integrate_ray (lib/sourceintegrator/sourceintegrator.cpp:519-575)
 //                    over the interpolated DO source (do_source_interpolated_pp.cpp:95-210) and the exact single-scatter
 //                    source (lib/solar/singlescattersource.cpp:573-640, 949-1167)
-// Layouts: every per-chunk array of this path is wavelength-FASTEST ([...][nw]) so that the 32 lanes of a warp (32
-// consecutive wavelengths of one ray / point / layer) read and write consecutive addresses; the geometry tables are
-// uniform across a warp (broadcast loads).
+// Layouts: the source table and the ground source are wavelength-FASTEST ([...][nw]) so that the 32 lanes of a warp (32
+// consecutive wavelengths of one ray / table point) read and write consecutive addresses; the Legendre projections
+// are [..][w][l] (one 128-byte run per problem), the phase function [ray][w][grid point] like the atmosphere inputs;
+// the geometry tables are uniform across a warp (broadcast loads).
 #include "disco_limb.cuh"
+
+#include <cstdlib>
 
 namespace disco {
 
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(128) k_limb_coef(ChunkView V, LimbView Lv, int
     }
     // c_l = beta_l / 2 sum_q w_q P_l^m(mu_q) ((-1)^(l-m) E_q + F_q): the single-scatter albedo of scat_phase_f cancels
     // against the division by it at do_source_diffuse_storage.cpp:1030
-    double* __restrict__ out = Lv.coef + ((((size_t)s * L + p) * M + ms) * NSTR) * nw + w;
+    double* __restrict__ out = Lv.coef + ((((size_t)s * L + p) * M + ms) * nw + w) * NSTR;
     for (int l = 0; l < NSTR; ++l) {
         double c = 0.0;
         if (l >= m) {
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(128) k_limb_coef(ChunkView V, LimbView Lv, int
             for (int i = 0; i < N; ++i) c += V.T.wt[i] * lp[i * NSTR + l] * (sgn * E[i] + F[i]);
             c *= 0.5 * beta[l];
         }
-        out[(size_t)l * nw] = c;
+        out[l] = c;
     }
     // upwelling Lambertian ground source, order 0 (accumulate_ground_sources, :436-695)
     if (p == L - 1 && m == 0) {
@@ -126,6 +129,145 @@ __global__ void __launch_bounds__(128) k_limb_coef(ChunkView V, LimbView Lv, int
     }
 }
 
+
+// S1 for N = 2, 4, 8: N lanes per (wavelength, layer) problem, lane j = solution j in the column phase (column j of W+-
+// in registers, loaded like k_layer_post: the lanes of a problem read consecutive doubles) and stream j in the row
+// phase.  Persistent blocks per azimuth order; exchanges through per-problem shared memory:
+//   Q+-_i (lane i)                      -> all lanes        A+-_j = (Q+ . W+_j + Q- . W-_j) / norm_j
+//   a_j W+_qj + b_j W-_qj (lane j)      -> lane q sums      E_q, F_q: the diffuse field at stream q
+//   E_q, F_q (lane q)                   -> all lanes        c_l for the lane's two Legendre orders
+template <int N>
+struct LimbCoefCfg {
+    static constexpr int NSTR = 2 * N, PPW = 32 / N, PPB = PPW * 4;
+    static constexpr int PER_PROBLEM = 2 * N + 2 * N * N + 2 * N + 4;   // xq | tr[2][N][N] | ef | skew (8 banks)
+    static constexpr int TABLE = NSTR * N + NSTR + N;                    // tW[l][q] | lpc[l] | wmu[q]
+    static constexpr int SMEM = TABLE + PPB * PER_PROBLEM;
+};
+
+template <int N>
+__global__ void __launch_bounds__(128) k_limb_coef_lanes(ChunkView V, LimbView Lv, int s) {
+    using Cf = LimbCoefCfg<N>;
+    constexpr int NSTR = Cf::NSTR;
+    __shared__ __align__(16) double smem[Cf::SMEM];
+    const int L = V.T.L, M = V.M, nw = V.nw;
+    double* tW = smem;               // [l][q] w_q P_l^m(mu_q)
+    double* lpc = tW + NSTR * N;     // [l]
+    double* wmu = lpc + NSTR;        // [q]
+    const int ms = blockIdx.y;
+    const int m = V.m_list[ms];
+    for (int e = threadIdx.x; e < NSTR * N; e += blockDim.x) {
+        const int l = e / N, q = e % N;
+        tW[e] = V.T.wt[q] * V.T.lp_mu[((size_t)m * N + q) * NSTR + l];
+    }
+    if (threadIdx.x < NSTR) lpc[threadIdx.x] = V.T.lp_csz[(size_t)m * NSTR + threadIdx.x];
+    if (threadIdx.x < N) wmu[threadIdx.x] = V.T.wt[threadIdx.x] * V.T.mu[threadIdx.x];
+    __syncthreads();
+    const int j = threadIdx.x % N;
+    const int pib = threadIdx.x / N;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned gmask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (lane / N * N));
+    double* xq = smem + Cf::TABLE + (size_t)pib * Cf::PER_PROBLEM;   // [2N]  Q+ | Q-
+    double* tr = xq + 2 * N;                                         // [2][N][N]
+    double* ef = tr + 2 * N * N;                                     // [2N]  E | F
+    const double f0 = (m == 0 ? 1.0 : 2.0) * (1.0 / (4.0 * kPi));
+    const long long nq = (long long)nw * L;
+    for (long long qblk = blockIdx.x; qblk * Cf::PPB < nq; qblk += gridDim.x) {
+        long long q = qblk * Cf::PPB + pib;   // w * L + p
+        const bool valid = q < nq;
+        if (!valid) q = nq - 1;
+        const int w = (int)(q / L), p = (int)(q % L);
+        const size_t idx = ((size_t)w * M + ms) * L + p;
+        const double od = V.lay_od[q], ssa = V.lay_ssa[q], sec = V.lay_secant[q];
+        const double trans = V.lay_trans[(size_t)w * (L + 1) + p];
+        const double* __restrict__ beta = V.lay_beta + (size_t)q * NSTR;
+        // column j of W+-
+        double wp[N], wm[N];
+        {
+            const double* __restrict__ Wp = V.Wp + idx * N * N + j;
+            const double* __restrict__ Wm = V.Wm + idx * N * N + j;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                wp[i] = Wp[i * N];
+                wm[i] = Wm[i * N];
+            }
+        }
+        const double kj = V.kth[idx * 2 * N + j];
+        const double Lj = V.xsol[idx * 2 * N + j], Mj = V.xsol[idx * 2 * N + N + j];
+        // row phase: Q+-_i for stream i = j (sktran_do_rte.cpp:556-580)
+        {
+            double sp = 0.0, sm = 0.0;
+            for (int l = m; l < NSTR; ++l) {
+                const double pp = beta[l] * tW[l * N + j] * lpc[l];   // w_i folded into tW
+                sp += pp;
+                sm += ((l - m) & 1) ? -pp : pp;
+            }
+            xq[j] = sp * f0 * ssa;
+            xq[N + j] = sm * f0 * ssa;
+        }
+        __syncwarp();
+        double norm = 0.0, ap = 0.0, am = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double qp = xq[i], qm = xq[N + i];
+            norm = fma(wmu[i], fma(wp[i], wp[i], -wm[i] * wm[i]), norm);
+            ap = fma(qp, wp[i], fma(qm, wm[i], ap));
+            am = fma(qm, wp[i], fma(qp, wm[i], am));
+        }
+        ap /= norm;
+        am /= norm;
+        const double frac = Lv.layer_fraction[p];
+        const double x = frac * od;
+        const double exs = exp(-x * sec), ets = exp(-od * sec), exk = exp(-x * kj);
+        const double hp = exp(-1.0 * kj * od * frac), hm = exp(-kj * od * (1.0 - frac));
+        const double Dm = trans * x * psi_value(x, kj, sec, exk, exs);
+        const double Dp = trans * (exs - ets * exp(-(od - x) * kj)) / (kj + sec);
+        const double a = hp * Lj + ap * Dm, b = hm * Mj + am * Dp;
+        // this solution's share of the diffuse field at every stream -> transpose through shared memory
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            tr[i * N + j] = fma(wp[i], a, wm[i] * b);
+            tr[N * N + i * N + j] = fma(wm[i], a, wp[i] * b);
+        }
+        __syncwarp();
+        {
+            double e = 0.0, f = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                e += tr[j * N + c];
+                f += tr[N * N + j * N + c];
+            }
+            ef[j] = e;
+            ef[N + j] = f;
+        }
+        __syncwarp();
+        // c_l for l = 2j, 2j + 1
+        if (valid) {
+            double* __restrict__ out = Lv.coef + ((((size_t)s * L + p) * M + ms) * nw + w) * NSTR;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int l = 2 * j + r;
+                double c = 0.0;
+                if (l >= m) {
+                    const double sgn = ((l - m) & 1) ? -1.0 : 1.0;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) c = fma(tW[l * N + i], fma(sgn, ef[i], ef[N + i]), c);
+                    c *= 0.5 * beta[l];
+                }
+                out[l] = c;
+            }
+        }
+        // order-0 Lambertian ground source from the surface sums of the bottom layer (written by the layer kernel)
+        if (p == L - 1 && m == 0) {
+            const double* surf = V.surf + (size_t)w * (2 * N + 1);
+            double t = fma(Lj * V.kth[idx * 2 * N + N + j], surf[j], Mj * surf[N + j]);
+#pragma unroll
+            for (int off = N / 2; off > 0; off >>= 1) t += __shfl_xor_sync(gmask, t, off);
+            if (valid && j == 0) Lv.ground[(size_t)s * nw + w] = 2.0 * V.albedo[w] * (surf[2 * N] + t);
+        }
+        __syncwarp();   // the exchange areas are rewritten by the next problem
+    }
+}
+
 __global__ void __launch_bounds__(128) k_limb_table(ChunkView V, LimbView Lv) {
     const int L = V.T.L, M = V.M, nw = V.nw, nstr = V.T.nstr;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,7 +275,7 @@ __global__ void __launch_bounds__(128) k_limb_table(ChunkView V, LimbView Lv) {
     const int w = (int)(tid % nw);
     const int pt = (int)(tid / nw);
     const int a = Lv.pt_angle[pt], p = L - 1 - Lv.pt_alt[pt], s = Lv.pt_sza[pt];
-    const double* __restrict__ coef = Lv.coef + (((size_t)s * L + p) * M) * nstr * nw + w;
+    const double* __restrict__ coef = Lv.coef + ((size_t)s * L + p) * M * nw * nstr;   // [ms][w][l]
     double* __restrict__ tab = Lv.table + (size_t)pt * M * nw + w;
     double prev = 0.0, prev_prev = 0.0;
     bool stopped = false;
@@ -142,7 +284,8 @@ __global__ void __launch_bounds__(128) k_limb_table(ChunkView V, LimbView Lv) {
         double v = 0.0;
         if (!stopped) {
             const double* __restrict__ la = Lv.lp_ang + ((size_t)a * nstr + m) * nstr;
-            for (int l = m; l < nstr; ++l) v += la[l] * coef[((size_t)ms * nstr + l) * nw];
+            const double* __restrict__ cf = coef + ((size_t)ms * nw + w) * nstr;
+            for (int l = m; l < nstr; ++l) v += la[l] * cf[l];
             // convergence in azimuth order (:1032-1060): later orders of this point stay zero
             if (m >= 2 && (fabs(v / prev) < 1e-4 || prev < 1e-10) && (fabs(v / prev_prev) < 1e-4 || prev_prev < 1e-10)) stopped = true;
         }
@@ -153,29 +296,37 @@ __global__ void __launch_bounds__(128) k_limb_table(ChunkView V, LimbView Lv) {
 }
 
 __global__ void __launch_bounds__(128) k_limb_phase(ChunkView V, LimbView Lv) {
+    // thread per (wavelength, grid point), grid point fastest: the Legendre moments are read once (consecutive threads
+    // read consecutive 8 nleg-byte runs) and every ray's phase value is written coalesced into phase[ray][w][q]
     const int nw = V.nw, nloc = V.T.nloc, nleg = V.nleg;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= (long long)nw * nloc * Lv.nrays) return;
-    const int w = (int)(tid % nw);
-    const int q = (int)((tid / nw) % nloc);
-    const int r = (int)(tid / ((long long)nw * nloc));
-    const double* __restrict__ leg = V.leg + (size_t)nleg * ((size_t)q + (size_t)nloc * w);
-    const double* __restrict__ wig = Lv.wig_ss + (size_t)r * Lv.nss;
+    if (tid >= (long long)nw * nloc) return;
+    const double* __restrict__ leg = V.leg + (size_t)nleg * tid;
     // the reference sums up to the last non-zero stored moment, at most num_singlescatter_moments
     const int nl = nleg < Lv.nss ? nleg : Lv.nss;
     int max_order = 1;
     for (int l = 0; l < nleg; ++l)
         if (leg[l] != 0.0) max_order = l + 1;
     if (max_order > nl) max_order = nl;
-    double ph = 0.0;
-    for (int l = 0; l < max_order; ++l) ph += leg[l] * wig[l];
-    Lv.phase[((size_t)r * nloc + q) * nw + w] = ph;
+    constexpr int KR = 16;   // moments kept in registers
+    double lg[KR];
+#pragma unroll
+    for (int l = 0; l < KR; ++l) lg[l] = (l < max_order) ? leg[l] : 0.0;
+    for (int r = 0; r < Lv.nrays; ++r) {
+        const double* __restrict__ wig = Lv.wig_ss + (size_t)r * Lv.nss;
+        double ph = 0.0;
+#pragma unroll
+        for (int l = 0; l < KR; ++l)
+            if (l < Lv.nss) ph = fma(lg[l], wig[l], ph);
+        for (int l = KR; l < max_order; ++l) ph = fma(leg[l], wig[l], ph);
+        Lv.phase[(size_t)r * nw * nloc + tid] = ph;
+    }
 }
 
-__global__ void __launch_bounds__(128) k_limb_integrate(ChunkView V, LimbView Lv) {
+__global__ void __launch_bounds__(64) k_limb_integrate(ChunkView V, LimbView Lv) {
     const int nw = V.nw, nloc = V.T.nloc, M = V.M;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
+    const int r = Lv.ray_order[blockIdx.y];   // longest rays first: the last wave of blocks is made of short ones
     if (w >= nw) return;
     const double* __restrict__ ext = V.ext + (size_t)nloc * w;
     const double* __restrict__ ssa = V.ssa + (size_t)nloc * w;
@@ -200,7 +351,7 @@ __global__ void __launch_bounds__(128) k_limb_integrate(ChunkView V, LimbView Lv
         const double mu_in = Lv.gnd_mu_in[r];
         if (Lv.ss_exact && mu_in > 0.0) I += t_far * (V.albedo[w] / kPi) * mu_in;
     }
-    const double* __restrict__ phase = Lv.phase + (size_t)r * nloc * nw + w;
+    const double* __restrict__ phase = Lv.phase + ((size_t)r * nw + w) * nloc;
     for (int sg = s0; sg < s1; ++sg) {
         const int* __restrict__ idx = Lv.od_idx + (size_t)sg * kLimbStencil;
         const double* __restrict__ ow = Lv.od_w + (size_t)sg * kLimbStencil;
@@ -240,7 +391,7 @@ __global__ void __launch_bounds__(128) k_limb_integrate(ChunkView V, LimbView Lv
                 for (int c = 0; c < kLimbStencil; ++c) {
                     if (wt[c] == 0.0) continue;
                     const int q = idx[c];
-                    const double pq = phase[(size_t)q * nw];
+                    const double pq = phase[q];
                     a += ssa[q] * wt[c];
                     k += ext[q] * wt[c];
                     ph += pq * wt[c];
@@ -262,9 +413,38 @@ __global__ void __launch_bounds__(128) k_limb_integrate(ChunkView V, LimbView Lv
     if (Lv.los_od) Lv.los_od[(size_t)w * Lv.nrays + r] = total_od;
 }
 
+template <int N>
+static void launch_limb_coef_lanes(const ChunkView& V, const LimbView& Lv, int s, cudaStream_t st) {
+    using Cf = LimbCoefCfg<N>;
+    const long long nq = (long long)V.nw * V.T.L;
+    const long long nblk = (nq + Cf::PPB - 1) / Cf::PPB;
+    static const int cap = [] {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return sms * 16;   // persistent blocks over all orders: a few waves
+    }();
+    long long per_order = (cap + V.M - 1) / V.M;
+    if (per_order < 1) per_order = 1;
+    const dim3 grid((unsigned)(nblk < per_order ? nblk : per_order), (unsigned)V.M);
+    k_limb_coef_lanes<N><<<grid, 128, 0, st>>>(V, Lv, s);
+}
+
 void launch_limb_coef(const ChunkView& V, const LimbView& Lv, int s, cudaStream_t st) {
     const long long n = (long long)V.nw * V.T.L * V.M;
     const unsigned grid = (unsigned)((n + 127) / 128);
+    static const bool generic = [] {
+        const char* g = std::getenv("SK_B200_GENERIC");
+        return g && g[0] == '1';
+    }();
+    if (!generic) {
+        switch (V.T.N) {
+            case 2: launch_limb_coef_lanes<2>(V, Lv, s, st); return;
+            case 4: launch_limb_coef_lanes<4>(V, Lv, s, st); return;
+            case 8: launch_limb_coef_lanes<8>(V, Lv, s, st); return;
+            default: break;
+        }
+    }
     switch (V.T.N) {
         case 1: k_limb_coef<1><<<grid, 128, 0, st>>>(V, Lv, s); break;
         case 2: k_limb_coef<2><<<grid, 128, 0, st>>>(V, Lv, s); break;
@@ -279,13 +459,13 @@ void launch_limb_table(const ChunkView& V, const LimbView& Lv, cudaStream_t st) 
     if (n > 0) k_limb_table<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(V, Lv);
 }
 void launch_limb_phase(const ChunkView& V, const LimbView& Lv, cudaStream_t st) {
-    const long long n = (long long)V.nw * V.T.nloc * Lv.nrays;
-    if (n > 0) k_limb_phase<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(V, Lv);
+    const long long n = (long long)V.nw * V.T.nloc;
+    if (n > 0 && Lv.nrays > 0) k_limb_phase<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(V, Lv);
 }
 void launch_limb_integrate(const ChunkView& V, const LimbView& Lv, cudaStream_t st) {
     if (V.nw <= 0 || Lv.nrays <= 0) return;
-    const dim3 grid((unsigned)((V.nw + 127) / 128), (unsigned)Lv.nrays);
-    k_limb_integrate<<<grid, 128, 0, st>>>(V, Lv);
+    const dim3 grid((unsigned)((V.nw + 63) / 64), (unsigned)Lv.nrays);
+    k_limb_integrate<<<grid, 64, 0, st>>>(V, Lv);
 }
 
 }  // namespace disco

@@ -29,11 +29,12 @@ struct LimbView {
     const int *sol_start, *sol_idx;
     const double* sol_w;
     const int* sol_blocked;
+    const int* ray_order;   // rays sorted by decreasing number of segments (block scheduling order of the integrator)
     // per-chunk arrays, wavelength fastest
-    double* coef;      // [nsza][L][M][nstr][nw]  Legendre projection of the diffuse field at the sampled altitude
+    double* coef;      // [nsza][L][M][nw][nstr]  Legendre projection of the diffuse field at the sampled altitude
     double* ground;    // [nsza][nw]              order-0 Lambertian ground source
     double* table;     // [npts][M][nw]           source table at the needed (cos zenith, altitude, SZA) points
-    double* phase;     // [nrays][nloc][nw]       single-scatter phase function of every grid point at the ray's angle
+    double* phase;     // [nrays][nw][nloc]       single-scatter phase function of every grid point at the ray's angle
     double* radiance;  // [nw][nrays]
     double* los_od;    // [nw][nrays] or null
 };

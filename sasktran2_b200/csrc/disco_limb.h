@@ -63,6 +63,7 @@ struct LimbPlan {
     std::vector<int> sol_idx;
     std::vector<double> sol_w;
     std::vector<int> sol_blocked;         // [nbnd] the solar ray hits the ground
+    std::vector<int> ray_order;           // [nrays] rays by decreasing number of segments
     // diagnostics (tests): per-ray geometric summaries
     std::vector<double> ray_cos_scatter;  // [nrays]
 };

@@ -605,6 +605,70 @@ struct WavelInputs {
     int ngroups;
     bool include_ss;     // single_scatter_source == discrete_ordinates
     int num_azimuth;     // nstr or num_do_forced_azimuth
+    // surface BRDF: 0 Lambertian (albedo above), 1 snow (Kokhanovsky), 2 MODIS kernels; args [nargs] of this wavelength
+    int brdf_kind = 0;
+    const double* brdf_args = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------
+//  Surface BRDF models (cpp/include/sasktran2/atmosphere/surface.h:112-362) and their azimuthal Fourier
+//  expansion (SurfaceStorage::compute_expansion, cpp/include/sktran_disco/sktran_do_surface.h:49-91)
+// ---------------------------------------------------------------------------------------------------
+inline double brdf_value(int kind, const double* args, double mu_in, double mu_out, double phi_diff) {
+    if (kind == 1) {  // SnowKokhanovsky, surface.h:151-199
+        auto K0 = [](double mu) { return (3.0 / 7.0) * (1.0 + 2.0 * mu); };
+        double mus = mu_in, muv = mu_out;
+        double ss = std::sqrt(1 - mus * mus), sv = std::sqrt(1 - muv * muv);
+        double cost = std::max(-1.0, std::min(1.0, -mus * muv + ss * sv * std::cos(phi_diff)));
+        double theta = std::acos(cost) * 180.0 / PI;
+        double alpha = std::sqrt(4 * PI * args[0]);
+        double pth = 11.1 * std::exp(-0.087 * theta) + 1.1 * std::exp(-0.014 * theta);
+        double r0 = (1.247 + 1.186 * (mus + muv) + 5.157 * mus * muv + pth) / (4.0 * (mus + muv));
+        return r0 * std::exp(-alpha * K0(mus) * K0(muv) / r0) / PI;
+    }
+    if (kind == 2) {  // MODIS (Ross-thick / Li-sparse-R), surface.h:246-294
+        double csza = mu_in, cvza = mu_out;
+        double ssza = std::sqrt(1 - csza * csza), svza = std::sqrt(1 - cvza * cvza);
+        double tsza = ssza / csza, tvza = svza / cvza;
+        double craa = -std::cos(phi_diff), sraa = std::sin(phi_diff);
+        double csa = std::max(-1.0, std::min(1.0, csza * cvza + ssza * svza * craa));
+        double sa = std::acos(csa), ssa = std::sin(sa);
+        double k_vol = ((0.5 * PI - sa) * csa + ssa) / (csza + cvza) - 0.25 * PI;
+        double d2 = tsza * tsza + tvza * tvza - 2 * tsza * tvza * craa;
+        double ct = std::max(-1.0, std::min(1.0, 2 * std::sqrt(d2 + tsza * tsza * tvza * tvza * sraa * sraa) * csza * cvza / (csza + cvza)));
+        double t = std::acos(ct), st = std::sin(t);
+        double o = (t - st * ct) * (csza + cvza) / (PI * csza * cvza);
+        double k_geo = o - (csza + cvza - 0.5 * (1 + csa)) / (csza * cvza);
+        return (args[0] + args[1] * k_vol + args[2] * k_geo) / PI;
+    }
+    return args[0] / PI;  // Lambertian, surface.h:112-122
+}
+inline void gauss_legendre(int n, std::vector<double>& x, std::vector<double>& w);
+inline double compute_expansion(int m, int kind, const double* args, double mu_out, double mu_in) {
+    if (kind == 0) return m == 0 ? args[0] : 0.0;  // max_azimuthal_order() == 1: brdf * pi for m = 0, nothing above
+    static std::vector<double> qx, qw;  // 512-point Gauss-Legendre rule (getQuadratureAbscissae / Weights (512))
+    if (qx.empty()) {
+        std::vector<double> x, w;
+        gauss_legendre(512, x, w);
+#pragma omp critical(oracle_brdf_quadrature)
+        if (qx.empty()) {
+            qw = w;
+            qx = x;
+        }
+    }
+    double result = 0;
+    for (size_t i = 0; i < qx.size() / 2; ++i) {
+        const double a[4] = {0.5 * qx[i] + 0.5, -0.5 * qx[i] + 0.5, 0.5 * qx[i] - 0.5, -0.5 * qx[i] - 0.5};
+        const double w = 0.5 * qw[i];
+        for (int k = 0; k < 4; ++k) result += w * brdf_value(kind, args, mu_in, mu_out, PI * a[k]) * std::cos(m * PI * a[k]);
+    }
+    return result * 0.5 * PI * (2.0 - (m == 0 ? 1.0 : 0.0));
+}
+// Expansion coefficients of one azimuth order for the stream / solar / line-of-sight pairs the solver needs
+// (Surface::calculate, sktran_do_surface.h:153-217)
+struct SurfaceExpansion {
+    bool general = false;
+    std::vector<double> ss, sun, los, lsun;  // [N*N] (out i, in q), [N], [nlos*N], [nlos]
 };
 
 template <class T>
@@ -650,6 +714,7 @@ struct Solver {
     const Plan& P;
     dgeev_fn dgeev;
     Lanes lanes;
+    const SurfaceExpansion* surf = nullptr;  // non-Lambertian surface of the order being solved (values only)
     Solver(const Plan& p, dgeev_fn f) : P(p), dgeev(f) {}
 
     // ---- layer optics: OpticalLayerArray ctor, sktran_do_layerarray.cpp:332-477 + OpticalLayer ctor
@@ -942,28 +1007,31 @@ struct Solver {
                 b[r0 + i + N] = -U.Gpb[i] + Lo.Gpt[i];
             }
         }
-        // ground (:2075-2128, :2270-2294).  Lambertian: rho = albedo for every pair, only m = 0.
+        // ground (:2075-2128, :2270-2294).  Lambertian: rho = albedo for every pair, only m = 0; a general BRDF
+        // reflects every order with rho_m(mu_i, mu_q) (sktran_do_rte.h:116-345)
         {
             int r0 = N + (L - 1) * 2 * N, c0 = n - 2 * N;
             const auto& B = sol[L - 1];
-            bool refl = (m == 0);
+            const bool gen = surf && surf->general;
+            bool refl = gen || (m == 0);
             double kd = (m == 0) ? 2.0 : 1.0;
+            auto rho = [&](int i, int q) { return gen ? T(surf->ss[i * N + q]) : albedo; };
             for (int i = 0; i < N; ++i) {
                 for (int j = 0; j < N; ++j) {
                     T vm = B.Wm[i + j * N], vp = B.Wp[i + j * N];
                     if (refl)
                         for (int q = 0; q < N; ++q) {
-                            vm -= T(kd) * albedo * T(P.wt[q] * P.mu[q]) * B.Wp[q + j * N];
-                            vp -= T(kd) * albedo * T(P.wt[q] * P.mu[q]) * B.Wm[q + j * N];
+                            vm -= T(kd) * rho(i, q) * T(P.wt[q] * P.mu[q]) * B.Wp[q + j * N];
+                            vp -= T(kd) * rho(i, q) * T(P.wt[q] * P.mu[q]) * B.Wm[q + j * N];
                         }
                     ent.push_back({r0 + i, c0 + j, vm * theta[L - 1][j]});
                     ent.push_back({r0 + i, c0 + N + j, vp});
                 }
                 T gds(0.0);
-                if (refl) gds = T(P.csz) * albedo / T(PI) * Ly.trans[L];
+                if (refl) gds = T(P.csz) * (gen ? T(surf->sun[i]) : albedo) / T(PI) * Ly.trans[L];
                 T um = B.Gmb[i];
                 if (refl)
-                    for (int q = 0; q < N; ++q) um -= T(kd) * albedo * T(P.wt[q] * P.mu[q]) * B.Gpb[q];
+                    for (int q = 0; q < N; ++q) um -= T(kd) * rho(i, q) * T(P.wt[q] * P.mu[q]) * B.Gpb[q];
                 b[r0 + i] = gds - um;
             }
         }
@@ -1023,16 +1091,18 @@ struct Solver {
     //      recursion (do_source_planeparallel.cpp:69-146).  Observer above the top of the atmosphere.
     // Ground-leaving radiance of order m toward any line of sight (Lambertian: m = 0 only).  gL / gM (optional):
     // its partial derivatives w.r.t. the bottom layer's L_q, M_q at fixed layer quantities.
-    T ground_term(int m, const T& trans_bottom, const T& od_last, const T& albedo, const LayerSolution<T>& B,
-                  bool include_ss, double* gL = nullptr, double* gM = nullptr) const {
+    T ground_term(int m, const T& trans_bottom, const T& od_last, const T& albedo_in, const LayerSolution<T>& B,
+                  bool include_ss, double* gL = nullptr, double* gM = nullptr, int los = -1) const {
         const int N = P.N;
         if (gL)
             for (int q = 0; q < N; ++q) gL[q] = gM[q] = 0.0;
-        if (m != 0) return T(0.0);  // Lambertian: max_azimuthal_order == 1
+        const bool gen = surf && surf->general && los >= 0;
+        if (m != 0 && !gen) return T(0.0);  // Lambertian: max_azimuthal_order == 1
         T diffuse(0.0);
         for (int i = 0; i < N; ++i) {
+            const T albedo = gen ? T(surf->los[los * N + i]) : albedo_in;   // rho_m(mu_los, mu_i)
             T sc = B.Gpb[i];
-            double factor = 2.0 * P.mu[i] * P.wt[i];
+            double factor = (m == 0 ? 2.0 : 1.0) * P.mu[i] * P.wt[i];
             for (int q = 0; q < N; ++q) {
                 T th = exp(-S_abs(B.k[q]) * od_last);
                 sc += B.Lc[q] * B.Wp[i + q * N] * th;
@@ -1045,7 +1115,7 @@ struct Solver {
             diffuse += T(factor) * sc * albedo;
         }
         if (include_ss) {
-            T direct = T(P.csz / PI) * trans_bottom * albedo;
+            T direct = T(P.csz / PI) * trans_bottom * (gen ? T(surf->lsun[los]) : albedo_in);
             return direct + diffuse;
         }
         return diffuse;
@@ -1136,7 +1206,7 @@ struct Solver {
                     bool include_ss) const {
         const int L = P.L;
         const double mu = P.los_mu[j];
-        T I = ground_term(m, Ly.trans[L], Ly.od[L - 1], albedo, sol[L - 1], include_ss);
+        T I = ground_term(m, Ly.trans[L], Ly.od[L - 1], albedo, sol[L - 1], include_ss, nullptr, nullptr, j);
         for (int p = L - 1; p >= 0; --p) {
             I = I * exp(-Ly.od[p] / T(mu));
             I += layer_source(m, j, p, Ly, sol[p], include_ss);
@@ -1155,10 +1225,27 @@ struct Solver {
         seed(albedo, lanes.albedo());
         std::vector<T> rad(nlos, T(0.0));
         std::vector<LayerSolution<T>> sol(L);
+        SurfaceExpansion sx;
         for (int m = 0; m < in.num_azimuth; ++m) {
             for (int p = 0; p < L; ++p) {
                 homogeneous(m, Ly.ssa[p], Ly.beta[p], sol[p]);
                 particular(m, Ly.ssa[p], Ly.beta[p], Ly.od[p], Ly.secant[p], Ly.trans[p], sol[p]);
+            }
+            if (in.brdf_kind != 0) {   // Surface::calculate(m), sktran_do_surface.h:153-217
+                if (ndual(albedo) != 0) throw std::runtime_error("oracle: weighting functions with a non-Lambertian BRDF are not restated");
+                const int N = P.N;
+                sx.general = true;
+                sx.ss.assign(size_t(N) * N, 0.0);
+                sx.sun.assign(N, 0.0);
+                sx.los.assign(size_t(nlos) * N, 0.0);
+                sx.lsun.assign(nlos, 0.0);
+                for (int i = 0; i < N; ++i) {
+                    for (int q = 0; q < N; ++q) sx.ss[i * N + q] = compute_expansion(m, in.brdf_kind, in.brdf_args, P.mu[i], P.mu[q]);
+                    sx.sun[i] = compute_expansion(m, in.brdf_kind, in.brdf_args, P.mu[i], P.csz);
+                    for (int j = 0; j < nlos; ++j) sx.los[j * N + i] = compute_expansion(m, in.brdf_kind, in.brdf_args, P.los_mu[j], P.mu[i]);
+                }
+                for (int j = 0; j < nlos; ++j) sx.lsun[j] = compute_expansion(m, in.brdf_kind, in.brdf_args, P.los_mu[j], P.csz);
+                surf = &sx;
             }
             bvp(m, Ly, albedo, sol);
             for (int j = 0; j < nlos; ++j) {
@@ -1170,6 +1257,7 @@ struct Solver {
             radiance[j] = val(rad[j]);
             store_derivs(rad[j], dlane ? dlane + size_t(j) * nd_ref() : nullptr);
         }
+        surf = nullptr;
         if (layers_out) *layers_out = Ly;
     }
     static void store_derivs(const double&, double*) {}

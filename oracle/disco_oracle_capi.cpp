@@ -42,6 +42,23 @@ void oracle_set_delta_m(const double* f, const double* d_f) {
     g_df = d_f;
 }
 
+// surface BRDF of the next oracle_do_radiance call: kind 0 Lambertian (the albedo argument), 1 snow (Kokhanovsky),
+// 2 MODIS; args [nargs, nwavel] column-major (Surface::brdf_args)
+static int g_brdf_kind = 0, g_brdf_nargs = 1;
+static const double* g_brdf_args = nullptr;
+void oracle_set_brdf(int kind, int nargs, const double* args) {
+    g_brdf_kind = kind;
+    g_brdf_nargs = nargs;
+    g_brdf_args = args;
+}
+// Fourier coefficient of a BRDF model (SurfaceStorage::compute_expansion) and the model itself, for the tests
+double oracle_brdf_expansion(int m, int kind, const double* args, double mu_out, double mu_in) {
+    return oracle::compute_expansion(m, kind, args, mu_out, mu_in);
+}
+double oracle_brdf_value(int kind, const double* args, double mu_in, double mu_out, double phi_diff) {
+    return oracle::brdf_value(kind, args, mu_in, mu_out, phi_diff);
+}
+
 // 0: forward-mode dense duals (the reference's default, do_backprop = false); 1: reverse mode (do_backprop = true,
 // RTESolver::backprop): layer-local duals + transposed band solves per line of sight
 static int g_reverse = 0;
@@ -99,6 +116,10 @@ int oracle_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nlos, const
                 }
                 in.solar = solar[w];
                 in.albedo = albedo[w];
+                if (g_brdf_kind != 0 && g_brdf_args) {
+                    in.brdf_kind = g_brdf_kind;
+                    in.brdf_args = g_brdf_args + size_t(g_brdf_nargs) * w;
+                }
                 in.ngroups = G;
                 in.include_ss = include_ss != 0;
                 in.num_azimuth = num_azimuth > 0 ? num_azimuth : nstr;

@@ -63,7 +63,8 @@ def _p(a):
 
 def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az,
                 ssa, ext, leg, solar=None, albedo, d_leg=None, include_ss=True, num_azimuth=0,
-                calc_derivs=False, nthreads=0, return_lanes=False, stable=False, f=None, d_f=None, reverse=False):
+                calc_derivs=False, nthreads=0, return_lanes=False, stable=False, f=None, d_f=None, reverse=False,
+                brdf_kind=0, brdf_args=None):
     """Run the oracle.
 
     ssa, ext: [nloc, nwavel] (Fortran order is used internally, as the reference does);
@@ -111,6 +112,10 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
             d_f = np.asfortranarray(d_f, dtype=np.float64)
             assert d_f.shape == (nloc, nwavel, G)
     L.oracle_set_delta_m(_p(f), _p(d_f) if f is not None else None)
+    if brdf_kind:
+        brdf_args = np.asfortranarray(brdf_args, dtype=np.float64)   # [nargs, nwavel]
+        assert brdf_args.ndim == 2 and brdf_args.shape[1] == nwavel
+        L.oracle_set_brdf(ctypes.c_int(int(brdf_kind)), ctypes.c_int(brdf_args.shape[0]), _p(brdf_args))
     rc = L.oracle_do_radiance(
         ctypes.c_int(nstr), ctypes.c_int(nloc), ctypes.c_int(nwavel), ctypes.c_int(nleg), ctypes.c_int(nlos),
         _p(alt), ctypes.c_int(interp), ctypes.c_int(geotype), ctypes.c_double(cos_sza), ctypes.c_double(earth_radius),
@@ -118,6 +123,7 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
         ctypes.c_int(int(include_ss)), ctypes.c_int(num_azimuth), ctypes.c_int(int(calc_derivs)),
         ctypes.c_int(nthreads), _DGEEV, _p(rad), _p(native), _p(lanes))
     L.oracle_set_delta_m(None, None)
+    L.oracle_set_brdf(ctypes.c_int(0), ctypes.c_int(1), None)
     if rc != 0:
         raise RuntimeError(f"oracle failed ({rc}): {L.oracle_last_error().decode()}")
     out = {"radiance": rad}
@@ -332,3 +338,19 @@ def limb_geometry(*, alt, interp, cos_sza, saa=0.0, earth_radius=6372000.0, rays
     if rc != 0:
         raise RuntimeError(f"oracle_limb_geometry failed: {L.oracle_last_error().decode()}")
     return dict(nlayers=nl, ground_hit=gh, layers=data, cos_scatter=csc)
+
+
+def brdf_value(kind, args, mu_in, mu_out, phi_diff):
+    """BRDF model of the reference (cpp/include/sasktran2/atmosphere/surface.h): kind 0 Lambertian, 1 snow, 2 MODIS."""
+    L = lib()
+    L.oracle_brdf_value.restype = ctypes.c_double
+    a = np.ascontiguousarray(args, dtype=np.float64)
+    return L.oracle_brdf_value(int(kind), _p(a), ctypes.c_double(mu_in), ctypes.c_double(mu_out), ctypes.c_double(phi_diff))
+
+
+def brdf_expansion(m, kind, args, mu_out, mu_in):
+    """Azimuthal Fourier coefficient rho_m(mu_out, mu_in) (SurfaceStorage::compute_expansion, 512-point quadrature)."""
+    L = lib()
+    L.oracle_brdf_expansion.restype = ctypes.c_double
+    a = np.ascontiguousarray(args, dtype=np.float64)
+    return L.oracle_brdf_expansion(int(m), int(kind), _p(a), ctypes.c_double(mu_out), ctypes.c_double(mu_in))

@@ -69,6 +69,8 @@ def _declare(lib):
     f("sk_surface_get_derivative_mapping_name", i, vp, i, C.POINTER(C.c_char_p))
     f("sk_surface_set_zero", i, vp)
     f("sk_brdf_create_lambertian", vp, i)
+    f("sk_brdf_create_modis", vp, i)
+    f("sk_brdf_create_kokhanovsky", vp, i)
     f("sk_brdf_get_num_deriv", i, vp, c_int_p)
     f("sk_brdf_get_num_args", i, vp, c_int_p)
     f("sk_brdf_destroy", None, vp)

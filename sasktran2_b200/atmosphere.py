@@ -172,6 +172,16 @@ class Surface:
         except Exception:
             pass
 
+    def use_modis(self, isotropic, volumetric, geometric):
+        """Kernel-based MODIS BRDF (sk_brdf_create_modis; reference: sasktran2.constituent.MODIS): isotropic +
+        Ross-thick volumetric + Li-sparse-R geometric kernel weights, scalars or [nwavel] arrays.  Radiances only."""
+        self.brdf_args = np.zeros((3, self._nwavel), order="F")
+        self.brdf_args[0], self.brdf_args[1], self.brdf_args[2] = isotropic, volumetric, geometric
+        old = self._brdf
+        self._brdf = _lib.lib().sk_brdf_create_modis(1)
+        _lib.check(_lib.lib().sk_surface_set_brdf(self._h, self._brdf, _lib.dptr(self.brdf_args)))
+        _lib.lib().sk_brdf_destroy(old)
+
     def enable_albedo_derivative(self, name: str = "wf_albedo"):
         """Registers a surface mapping with d_brdf = 1 (d radiance / d albedo)."""
         h = C.c_void_p()

@@ -76,6 +76,12 @@ disco::AtmosphereArrays arrays_of(const Atmosphere* atm) {
     a.f = s->applied_f_order > 0 ? s->f.data() : nullptr;
     const Surface* sf = atm->surface;
     a.albedo = sf->brdf_args ? sf->brdf_args : sf->default_albedo.data();
+    if (sf->brdf && sf->brdf->kind != 0) {   // kernel-based model: brdf_args is [nargs, nwavel] (Surface::brdf_args upstream)
+        a.brdf_kind = sf->brdf->kind;
+        a.brdf_nargs = disco::brdf_num_args(sf->brdf->kind);
+        a.brdf_args = sf->brdf_args;
+        a.albedo = nullptr;
+    }
     return a;
 }
 
@@ -90,7 +96,13 @@ int validate(const Engine* e, const Atmosphere* atm, const OutputC* out, bool ch
     if (!s->ssa || !s->ext || !s->leg || !s->solar) return fail(-1, "atmosphere storage arrays are null");
     if (s->nleg < 1) return fail(-2, "atmosphere storage needs at least one phase moment");
     if (atm->surface->nwavel != s->nwavel) return fail(-2, "surface and storage have a different number of wavelengths");
-    if (atm->surface->brdf && atm->surface->brdf->kind != 0) return fail(-2, "B200 DO path supports the Lambertian BRDF only");
+    if (atm->surface->brdf && atm->surface->brdf->kind == 1)
+        return fail(-2, "B200 DO path: the snow BRDF (Kokhanovsky) is not supported (Lambertian and MODIS are)");
+    if (atm->surface->brdf && atm->surface->brdf->kind != 0 && !atm->surface->brdf_args)
+        return fail(-1, "surface BRDF arguments are null");
+    if (atm->surface->brdf && atm->surface->brdf->kind != 0 && atm->calc_derivs && e->cfg.wf_enabled && check_output && out &&
+        !(out->derivs.empty() && out->surface_derivs.empty()))
+        return fail(-2, "B200 DO path: weighting functions with a non-Lambertian BRDF are not supported");
     if (check_output) {
         if (!out || !out->radiance) return fail(-1, "output handle is null");
         if (out->nstokes != 1) return fail(-2, "output num_stokes must be 1");
@@ -673,14 +685,15 @@ BRDF* sk_brdf_create_lambertian(int nstokes) {
     b->nstokes = nstokes;
     return b;
 }
+// cpp/include/sasktran2/atmosphere/surface.h: Lambertian 1 / 1, SnowKokhanovsky 1 / 1, MODIS 3 / 3
 int sk_brdf_get_num_deriv(BRDF* b, int* n) {
     if (!b || !n) return -1;
-    *n = 1;
+    *n = disco::brdf_num_args(b->kind);
     return 0;
 }
 int sk_brdf_get_num_args(BRDF* b, int* n) {
     if (!b || !n) return -1;
-    *n = 1;
+    *n = disco::brdf_num_args(b->kind);
     return 0;
 }
 void sk_brdf_destroy(BRDF* b) { delete b; }

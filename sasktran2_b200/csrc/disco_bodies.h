@@ -72,6 +72,11 @@ struct ChunkView {
     double* los_lay;          // [nw][nlos][L][3] exp(-od / mu_los) | E | 1 / (1 + mu secant)
     int vsrc_w;               // entries of vsrc per (w, m, los, layer): 1 (generic path) or N (per-solution partials)
     unsigned int* status;     // error bits
+    // ---- kernel-based (non-Lambertian) surface: null for the Lambertian closed form.  With gsurf set, `albedo` points
+    //      at zeros, so every Lambertian term of the layer kernels and row loaders vanishes (disco_brdf.h).
+    const double* gsurf;      // [nw][M][2N^2 + 2N]: SP[i][j] | SM[i][j] | SG[i] | rho_m(mu_i, mu_0)
+    double* gsurf_out;        // the same array, writable (k_surface_general)
+    int gsurf_stride;
 };
 
 

@@ -82,12 +82,18 @@ struct ForwardRows {
             const bool refl = (m == 0);
             const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
             const double* surf = V.surf + (size_t)w * (2 * N + 1);
+            // kernel-based BRDF: every order reflects, with per-stream sums prepared by k_surface_general
+            const double* gs = V.gsurf ? V.gsurf + ((size_t)w * V.M + ms) * V.gsurf_stride : nullptr;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 double vm = Wmu[i * N + j], vp = Wpu[i * N + j];
                 if (refl) {
                     vm -= alb2 * surf[j];      // - (1+d_m0) rho sum_q w mu W+_qj
                     vp -= alb2 * surf[N + j];  // - (1+d_m0) rho sum_q w mu W-_qj
+                }
+                if (gs) {
+                    vm -= gs[i * N + j];
+                    vp -= gs[N * N + i * N + j];
                 }
                 a[j] = vm * thu[j];
                 a[N + j] = vp;
@@ -99,6 +105,7 @@ struct ForwardRows {
                 rhs += alb2 * surf[2 * N];
                 rhs += V.T.csz * V.albedo[w] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
             }
+            if (gs) rhs += gs[2 * N * N + i] + V.T.csz * gs[2 * N * N + N + i] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
             a[4 * N] = rhs;
         }
     }
@@ -162,15 +169,18 @@ struct ForwardRows {
             const bool refl = (m == 0);
             const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
             const double* surf = V.surf + (size_t)w * (2 * N + 1);
+            const double* gs = V.gsurf ? V.gsurf + ((size_t)w * V.M + ms) * V.gsurf_stride : nullptr;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 if (wb == 0) {
                     double vm = Wmu[i * N + j];
                     if (refl) vm -= alb2 * surf[j];
+                    if (gs) vm -= gs[i * N + j];
                     seg[j] = vm * thu[j];
                 } else {
                     double vp = Wpu[i * N + j];
                     if (refl) vp -= alb2 * surf[N + j];
+                    if (gs) vp -= gs[N * N + i * N + j];
                     seg[j] = vp;
                 }
             }
@@ -193,6 +203,10 @@ struct ForwardRows {
             const double* surf = V.surf + (size_t)w * (2 * N + 1);
             rhs += 2.0 * V.albedo[w] * surf[2 * N];
             rhs += V.T.csz * V.albedo[w] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
+        }
+        if (V.gsurf) {
+            const double* gs = V.gsurf + ((size_t)w * V.M + ms) * V.gsurf_stride;
+            rhs += gs[2 * N * N + i] + V.T.csz * gs[2 * N * N + N + i] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
         }
         return rhs;
     }

@@ -207,6 +207,8 @@ DeviceEngine::~DeviceEngine() {
     for (void* p : m_limb_ptrs)
         if (p) cudaFree(p);
     if (d_los_od) cudaFree(d_los_od);
+    for (void* p : {(void*)d_brdf_args, (void*)d_zero_albedo, (void*)d_brdf_Rss, (void*)d_brdf_rsun, (void*)d_brdf_Rls, (void*)d_brdf_rlsun})
+        if (p) cudaFree(p);
     for (void* p : {(void*)d_mu, (void*)d_wt, (void*)d_lp_mu, (void*)d_lp_csz, (void*)d_lp_los, (void*)d_los_mu, (void*)d_wf_tab,
                     (void*)d_los_cosmphi, (void*)d_layer_dh, (void*)d_interp_w, (void*)d_interp_idx,
                     (void*)d_chapman, (void*)d_mlist, (void*)d_status})
@@ -256,6 +258,7 @@ size_t DeviceEngine::ws_bytes(bool wf_on, int ngroups) const {
     d += M * nlos * L * 2 * N + M * nlos * L * vw;                  // wvec, vsrc
     if (m_fast) d += 3 * (N * (N + 1) / 2) * M * L + nlos * (L + 1) + nlos * L * 3;  // eigen planes, LOS exponentials
     d += M * L * 2 * N;                                             // x
+    if (m_brdf_kind != 0) d += M * (2 * N * N + 2 * N);             // kernel-based surface sums
     if (m_is_limb) {
         const size_t nsza = m_limb.nsza, npts = m_limb.npts, nrays = m_limb.nrays;
         if (m_limb.ms_do) d += nsza * L * M * nstr + nsza + npts * M;    // Legendre projections, ground source, source table
@@ -287,7 +290,7 @@ int DeviceEngine::chunk_wavelengths() const {
 void DeviceEngine::ensure_workspace(int chunk) {
     // the derivative arrays are sized by the number of scattering groups: an atmosphere with more groups than the
     // workspace was built for needs a new one even when the chunk fits
-    if (chunk <= m_ws_chunk && m_ws_wf == m_wf_on && (!m_wf_on || m_ws_ngroups == m_ngroups)) return;
+    if (chunk <= m_ws_chunk && m_ws_wf == m_wf_on && (!m_wf_on || m_ws_ngroups == m_ngroups) && m_ws_brdf == (m_brdf_kind != 0)) return;
     free_workspace();
     const size_t N = m_plan.N, L = m_plan.L, nstr = m_plan.nstr, nlos = m_plan.nlos, M = m_mlist.size();
     const size_t c = chunk;
@@ -301,6 +304,7 @@ void DeviceEngine::ensure_workspace(int chunk) {
     ChunkView& V = m_view;
     if (twostream_direct()) {
         std::memset(&V, 0, sizeof(V));
+        m_ws_brdf = m_brdf_kind != 0;
         m_ws_wf = m_wf_on;
         m_ws_ngroups = 0;
         m_ws_chunk = chunk;
@@ -332,6 +336,10 @@ void DeviceEngine::ensure_workspace(int chunk) {
         V.los_lay = A("los_lay", c * nlos * L * 3);
     }
     V.xsol = A("xsol", c * M * L * 2 * N);
+    V.gsurf = V.gsurf_out = nullptr;
+    V.gsurf_stride = (int)(2 * N * N + 2 * N);
+    if (m_brdf_kind != 0) V.gsurf = V.gsurf_out = A("gsurf", c * M * V.gsurf_stride);
+    m_ws_brdf = m_brdf_kind != 0;
     if (m_is_limb) {
         const size_t nsza = m_limb.nsza, npts = m_limb.npts, nrays = m_limb.nrays;
         m_lview.coef = m_lview.ground = m_lview.table = m_lview.phase = nullptr;
@@ -420,7 +428,41 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
         h2d(d_ssa, atm.ssa + nloc * w0, nloc);
         h2d(d_leg, atm.leg + (size_t)atm.nleg * nloc * w0, (size_t)atm.nleg * nloc);
         h2d(d_solar, atm.solar + w0, 1);
-        h2d(d_albedo, atm.albedo + w0, 1);
+        if (atm.albedo && atm.brdf_kind == 0) h2d(d_albedo, atm.albedo + w0, 1);
+    }
+    // kernel-based surface: Fourier coefficients of the kernels (once per engine and model), arguments of the range
+    m_brdf_kind = atm.brdf_kind;
+    if (m_brdf_kind != 0 && nw > 0) {
+        if (m_is_limb) throw std::runtime_error("B200 limb path supports the Lambertian BRDF only");
+        if (wf && wf->enabled()) throw std::runtime_error("B200 DO path: weighting functions with a non-Lambertian BRDF are not supported");
+        if (twostream_direct()) throw std::runtime_error("B200 two-stream kernel supports the Lambertian BRDF only");
+        if (m_plan.N > 16) throw std::runtime_error("B200 DO path: kernel-based BRDFs need num_streams <= 32");
+        if (m_brdf_tab_kind != m_brdf_kind) {
+            const BrdfTables T = build_brdf_tables(m_brdf_kind, m_plan);
+            for (double** p : {&d_brdf_Rss, &d_brdf_rsun, &d_brdf_Rls, &d_brdf_rlsun})
+                if (*p) {
+                    cudaFree(*p);
+                    *p = nullptr;
+                }
+            d_brdf_Rss = upload(T.Rss);
+            d_brdf_rsun = upload(T.rsun);
+            d_brdf_Rls = upload(T.Rls);
+            d_brdf_rlsun = upload(T.rlsun);
+            m_brdf_nk = T.nk;
+            m_brdf_tab_kind = m_brdf_kind;
+        }
+        m_brdf_nargs = atm.brdf_nargs;
+        if (m_brdf_nargs != brdf_num_args(m_brdf_kind) || !atm.brdf_args) throw std::runtime_error("BRDF arguments do not match the BRDF model");
+        const size_t need = (size_t)m_brdf_nargs * nw;
+        if (need > m_cap_brdf) {
+            if (d_brdf_args) cudaFree(d_brdf_args);
+            if (d_zero_albedo) cudaFree(d_zero_albedo);
+            d_brdf_args = dalloc<double>(need);
+            d_zero_albedo = dalloc<double>(need);
+            CUDA_OK(cudaMemset(d_zero_albedo, 0, sizeof(double) * need));
+            m_cap_brdf = need;
+        }
+        h2d(d_brdf_args, atm.brdf_args + (size_t)m_brdf_nargs * w0, (size_t)m_brdf_nargs);
     }
     // delta-M truncation fraction and its derivatives (set by sk_atmosphere_apply_delta_m_scaling)
     m_has_f = atm.f != nullptr && nw > 0;
@@ -580,7 +622,7 @@ void DeviceEngine::solve_staged() {
         V.ext = d_ext + nloc * w0;
         V.ssa = d_ssa + nloc * w0;
         V.leg = d_leg + (size_t)m_nleg * nloc * w0;
-        V.albedo = d_albedo + w0;
+        V.albedo = (m_brdf_kind != 0) ? d_zero_albedo + w0 : d_albedo + w0;
         V.solar = d_solar + w0;
         V.radiance = d_radiance + (size_t)w0 * m_nrad;
         V.dleg = d_dleg ? d_dleg + (size_t)m_nleg * nloc * w0 : nullptr;
@@ -648,6 +690,18 @@ void DeviceEngine::solve_staged() {
             m_launches += 3;
         } else {
             launch_layer_solve(V, m_stream);
+        }
+        if (m_brdf_kind != 0) {
+            BrdfView B;
+            B.nk = m_brdf_nk;
+            B.nargs = m_brdf_nargs;
+            B.Rss = d_brdf_Rss;
+            B.rsun = d_brdf_rsun;
+            B.Rls = d_brdf_Rls;
+            B.rlsun = d_brdf_rlsun;
+            B.args = d_brdf_args + (size_t)m_brdf_nargs * w0;
+            launch_surface_general(V, B, m_stream);
+            m_launches += 1;
         }
         mark(); slots.push_back(T_LAYER);
         launch_bvp(V, m_stream);

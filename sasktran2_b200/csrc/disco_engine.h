@@ -8,6 +8,7 @@
 
 #include "disco_comm.h"
 #include "disco_kernels.cuh"
+#include "disco_brdf.h"
 #include "disco_limb.cuh"
 #include "disco_plan.h"
 
@@ -32,6 +33,9 @@ struct AtmosphereArrays {
     const double* solar = nullptr;  // [nwavel]
     const double* albedo = nullptr; // [nwavel]
     const double* f = nullptr;      // [nloc, nwavel] delta-M truncation fraction, null when no scaling was applied
+    // surface BRDF (cpp/include/c_api/brdf.h): 0 Lambertian (`albedo`), 2 MODIS with brdf_args [3, nwavel] column-major
+    int brdf_kind = 0, brdf_nargs = 1;
+    const double* brdf_args = nullptr;
 };
 
 // Weighting-function request: which derivative mappings to evaluate and where the results go
@@ -179,6 +183,13 @@ class DeviceEngine {
     std::vector<void*> m_limb_ptrs; // geometry tables on the device
     std::vector<double*> d_sza_lp_csz, d_sza_chapman;   // per SZA of the DO grid
     double* d_los_od = nullptr;     // [nw][nrays] of the staged range
+    // ---- kernel-based surface BRDF
+    int m_brdf_kind = 0, m_brdf_tab_kind = 0, m_brdf_nargs = 1;
+    double *d_brdf_args = nullptr, *d_zero_albedo = nullptr;
+    size_t m_cap_brdf = 0;
+    double *d_brdf_Rss = nullptr, *d_brdf_rsun = nullptr, *d_brdf_Rls = nullptr, *d_brdf_rlsun = nullptr;
+    int m_brdf_nk = 0;
+    bool m_ws_brdf = false;
 };
 
 }  // namespace disco

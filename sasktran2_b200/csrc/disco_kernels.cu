@@ -136,6 +136,83 @@ __global__ void __launch_bounds__(128) k_radiance(ChunkView V) {
 // -------------------------------------------------------------------------------------------------
 // launchers
 // -------------------------------------------------------------------------------------------------
+// Kernel-based surface (disco_brdf.h): per (wavelength, azimuth order) the coupling rows
+//   R[i][q] = (1 + delta_m0) rho_m(mu_i, mu_q) w_q mu_q = sum_k args_k(w) Rss[k][m][i][q]   (streams)
+//   Rl[los][q] likewise for the lines of sight
+// applied to the bottom layer's solution: SP = R W+, SM = R W-, SG = R G+bottom for the ground rows of the BVP
+// (sktran_do_rte.h:116-345), and the ground-leaving radiance toward every line of sight added to the bottom layer's
+// wvec / vsrc (OpticalLayerArray::computeReflectedIntensities, sktran_do_layerarray.cpp:5-288).
+// One block per (wavelength, order); thread t < N: stream row t, N <= t < N + nlos: line of sight t - N.
+__global__ void k_surface_general(ChunkView V, BrdfView B) {
+    const int N = V.T.N, M = V.M, L = V.T.L, nlos = V.T.nlos, nstr = V.T.nstr;
+    const int w = blockIdx.x / M, ms = blockIdx.x % M;
+    const int m = V.m_list[ms];
+    const int t = threadIdx.x;
+    if (t >= N + nlos) return;
+    const size_t idxb = ((size_t)w * M + ms) * L + (L - 1);
+    const double* __restrict__ Wp = V.Wp + idxb * N * N;
+    const double* __restrict__ Wm = V.Wm + idxb * N * N;
+    const double* __restrict__ th = V.kth + idxb * 2 * N + N;
+    const double* __restrict__ Gpb = V.G + idxb * 4 * N + 2 * N;
+    const bool stream = t < N;
+    const int los = t - N;
+    double R[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) R[q] = 0.0;
+    double rsun = 0.0;
+    for (int k = 0; k < B.nk; ++k) {
+        const double a = B.args[k + (size_t)B.nargs * w];
+        const double* __restrict__ tab = stream ? B.Rss + (((size_t)k * nstr + m) * N + t) * N
+                                                : B.Rls + (((size_t)k * nstr + m) * nlos + los) * N;
+        rsun += a * (stream ? B.rsun[((size_t)k * nstr + m) * N + t] : B.rlsun[((size_t)k * nstr + m) * nlos + los]);
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if (q < N) R[q] = fma(a, tab[q], R[q]);
+    }
+    double sg = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+        if (q < N) sg = fma(R[q], Gpb[q], sg);
+    const double t_floor = V.lay_trans[(size_t)w * (L + 1) + L];
+    if (stream) {
+        double* __restrict__ gs = V.gsurf_out + ((size_t)w * M + ms) * V.gsurf_stride;
+        for (int j = 0; j < N; ++j) {
+            double sp = 0.0, sm = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (q < N) {
+                    sp = fma(R[q], Wp[q * N + j], sp);
+                    sm = fma(R[q], Wm[q * N + j], sm);
+                }
+            gs[t * N + j] = sp;
+            gs[N * N + t * N + j] = sm;
+        }
+        gs[2 * N * N + t] = sg;
+        gs[2 * N * N + N + t] = rsun;
+    } else {
+        const size_t o = (((size_t)w * M + ms) * nlos + los) * L + (L - 1);
+        const double attg = exp(-V.lay_cumod[(size_t)w * (L + 1) + L] / V.T.los_mu[los]);
+        double* __restrict__ wv = V.wvec + o * 2 * N;
+        for (int j = 0; j < N; ++j) {
+            double lp = 0.0, lm = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (q < N) {
+                    lp = fma(R[q], Wp[q * N + j], lp);
+                    lm = fma(R[q], Wm[q * N + j], lm);
+                }
+            wv[j] += attg * lp * th[j];
+            wv[N + j] += attg * lm;
+        }
+        const double direct = V.include_ss ? V.T.csz / kPi * t_floor * rsun : 0.0;
+        V.vsrc[o * V.vsrc_w] += attg * (sg + direct);
+    }
+}
+void launch_surface_general(const ChunkView& V, const BrdfView& B, cudaStream_t s) {
+    const int threads = ((V.T.N + V.T.nlos + 31) / 32) * 32;
+    k_surface_general<<<(unsigned)((long long)V.nw * V.M), threads, 0, s>>>(V, B);
+}
+
 void launch_layer_optics(const ChunkView& V, cudaStream_t s) {
     const long long n = (long long)V.nw * V.T.L;
     k_layer_optics<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V);

@@ -21,6 +21,13 @@ struct DeviceOnce {
     }
 };
 
+// kernel-based BRDF (disco_brdf.h): device tables of the kernels' Fourier coefficients + this chunk's arguments
+struct BrdfView {
+    int nk, nargs;
+    const double *Rss, *rsun, *Rls, *rlsun;
+    const double* args;   // [nargs][nw] of the chunk (k + nargs * w)
+};
+void launch_surface_general(const ChunkView& V, const BrdfView& B, cudaStream_t s);
 void launch_layer_optics(const ChunkView& V, cudaStream_t s);
 void launch_beam(const ChunkView& V, cudaStream_t s);
 void launch_validate_inputs(const ChunkView& V, cudaStream_t s);

@@ -6,34 +6,6 @@
 
 namespace disco {
 
-// d^l_{m0}(acos x) by the upward recurrence in l (cpp/include/sasktran2/math/wigner.h:56-149, n = 0).
-double wigner_dm0(int m, int l, double coszen) {
-    if (l < m) return 0.0;
-    const double theta = std::acos(coszen);
-    const double x = std::cos(theta);
-    double fact = 1.0;  // (2m)! / (m! m!)
-    for (int i = 2 * m; i > 1; --i) {
-        fact *= double(i);
-        if (i <= m) fact /= double(i);
-        if (i <= m) fact /= double(i);
-    }
-    const int zeta = (m > 0 && (m % 2 != 0)) ? -1 : 1;
-    double cur = zeta * std::pow(2.0, -double(m)) * std::sqrt(fact) * std::pow(1 - x, double(m) / 2.0) *
-                 std::pow(1 + x, double(m) / 2.0);
-    double prev = 0.0;
-    for (int ll = m + 1; ll <= l; ++ll) {
-        double mult = 1.0 / (std::sqrt(double(ll * ll - m * m)) * ll);
-        double a = (2 * ll - 1) * (ll * x);
-        double b = ll * std::sqrt(double((ll - 1) * (ll - 1) - m * m));
-        double next = mult * (a * cur - b * prev);
-        prev = cur;
-        cur = next;
-    }
-    return cur;
-}
-
-namespace {
-
 // Gauss-Legendre rule of order n on (-1, 1), ascending nodes.  The reference reads the same numbers from
 // the gauss-quad crate / 25-digit tables (sktran_do_quadrature.cpp:25-63); Newton's method in extended
 // precision lands on the same doubles.
@@ -71,6 +43,34 @@ void gauss_rule(int n, std::vector<double>& nodes, std::vector<double>& weights)
         weights[k] = weights[n - 1 - k] = (double)w;
     }
 }
+
+// d^l_{m0}(acos x) by the upward recurrence in l (cpp/include/sasktran2/math/wigner.h:56-149, n = 0).
+double wigner_dm0(int m, int l, double coszen) {
+    if (l < m) return 0.0;
+    const double theta = std::acos(coszen);
+    const double x = std::cos(theta);
+    double fact = 1.0;  // (2m)! / (m! m!)
+    for (int i = 2 * m; i > 1; --i) {
+        fact *= double(i);
+        if (i <= m) fact /= double(i);
+        if (i <= m) fact /= double(i);
+    }
+    const int zeta = (m > 0 && (m % 2 != 0)) ? -1 : 1;
+    double cur = zeta * std::pow(2.0, -double(m)) * std::sqrt(fact) * std::pow(1 - x, double(m) / 2.0) *
+                 std::pow(1 + x, double(m) / 2.0);
+    double prev = 0.0;
+    for (int ll = m + 1; ll <= l; ++ll) {
+        double mult = 1.0 / (std::sqrt(double(ll * ll - m * m)) * ll);
+        double a = (2 * ll - 1) * (ll * x);
+        double b = ll * std::sqrt(double((ll - 1) * (ll - 1) - m * m));
+        double next = mult * (a * cur - b * prev);
+        prev = cur;
+        cur = next;
+    }
+    return cur;
+}
+
+namespace {
 
 // Grid::calculate_interpolation_weights (cpp/lib/grids/grid.cpp:43-300), in-bounds cases
 void grid_weights(const std::vector<double>& g, int interp, double x, int idx[2], double w[2]) {

@@ -41,6 +41,8 @@ struct HostPlan {
     bool plane_parallel = true;
 };
 
+// Gauss-Legendre rule of order n on (-1, 1), ascending nodes
+void gauss_rule(int n, std::vector<double>& nodes, std::vector<double>& weights);
 // Wigner function d^l_{m0}(acos coszen) (cpp/include/sasktran2/math/wigner.h:56-149)
 double wigner_dm0(int m, int l, double coszen);
 

@@ -182,6 +182,16 @@ class Surface:
         _lib.check(_lib.lib().sk_surface_set_brdf(self._h, self._brdf, _lib.dptr(self.brdf_args)))
         _lib.lib().sk_brdf_destroy(old)
 
+    def use_snow_kokhanovsky(self, arg):
+        """Snow BRDF of Kokhanovsky (sk_brdf_create_kokhanovsky; reference: sasktran2.constituent.SnowKokhanovsky):
+        arg = (chi + M) / wavelength * L, scalar or [nwavel].  Radiances only."""
+        self.brdf_args = np.zeros((1, self._nwavel), order="F")
+        self.brdf_args[0] = arg
+        old = self._brdf
+        self._brdf = _lib.lib().sk_brdf_create_kokhanovsky(1)
+        _lib.check(_lib.lib().sk_surface_set_brdf(self._h, self._brdf, _lib.dptr(self.brdf_args)))
+        _lib.lib().sk_brdf_destroy(old)
+
     def enable_albedo_derivative(self, name: str = "wf_albedo"):
         """Registers a surface mapping with d_brdf = 1 (d radiance / d albedo)."""
         h = C.c_void_p()

@@ -96,8 +96,6 @@ int validate(const Engine* e, const Atmosphere* atm, const OutputC* out, bool ch
     if (!s->ssa || !s->ext || !s->leg || !s->solar) return fail(-1, "atmosphere storage arrays are null");
     if (s->nleg < 1) return fail(-2, "atmosphere storage needs at least one phase moment");
     if (atm->surface->nwavel != s->nwavel) return fail(-2, "surface and storage have a different number of wavelengths");
-    if (atm->surface->brdf && atm->surface->brdf->kind == 1)
-        return fail(-2, "B200 DO path: the snow BRDF (Kokhanovsky) is not supported (Lambertian and MODIS are)");
     if (atm->surface->brdf && atm->surface->brdf->kind != 0 && !atm->surface->brdf_args)
         return fail(-1, "surface BRDF arguments are null");
     if (atm->surface->brdf && atm->surface->brdf->kind != 0 && atm->calc_derivs && e->cfg.wf_enabled && check_output && out &&

@@ -29,8 +29,52 @@ double brdf_kernel_value(int kind, int k, double mu_in, double mu_out, double ph
     return (o - (cs + cv - 0.5 * (1 + csa)) / (cs * cv)) / kPiB;
 }
 
+SnowTables build_snow_tables(const HostPlan& plan) {
+    SnowTables T;
+    const int N = plan.N, nlos = plan.nlos;
+    T.N = N;
+    T.nlos = nlos;
+    T.npairs = N * N + N + nlos * N + nlos;
+    std::vector<double> qx, qw;
+    gauss_rule(512, qx, qw);
+    // the reference visits phi = pi (+-0.5 x +- 0.5) for the first 256 nodes with weight w / 2 each: two |phi| per node
+    for (int i = 0; i < 256; ++i)
+        for (double a : {0.5 * qx[i] + 0.5, -0.5 * qx[i] + 0.5}) {
+            T.cosphi.push_back(std::cos(kPiB * a));
+            T.weight.push_back(2.0 * 0.5 * qw[i]);
+        }
+    T.nsamples = (int)T.cosphi.size();
+    T.r0.assign((size_t)T.npairs * T.nsamples, 0.0);
+    T.g.assign((size_t)T.npairs * T.nsamples, 0.0);
+    T.scale.assign(T.npairs, 1.0);
+    auto fill = [&](int pair, double mu_out, double mu_in, double scale) {
+        // SnowKokhanovsky::brdf, cpp/include/sasktran2/atmosphere/surface.h:151-199
+        const double mus = mu_in, muv = mu_out;
+        const double ss = std::sqrt(1 - mus * mus), sv = std::sqrt(1 - muv * muv);
+        const double k0k0 = (3.0 / 7.0) * (1.0 + 2.0 * mus) * (3.0 / 7.0) * (1.0 + 2.0 * muv);
+        for (int s = 0; s < T.nsamples; ++s) {
+            const double cost = std::max(-1.0, std::min(1.0, -mus * muv + ss * sv * T.cosphi[s]));
+            const double theta = std::acos(cost) * 180.0 / kPiB;
+            const double p = 11.1 * std::exp(-0.087 * theta) + 1.1 * std::exp(-0.014 * theta);
+            const double r0 = (1.247 + 1.186 * (mus + muv) + 5.157 * mus * muv + p) / (4.0 * (mus + muv));
+            T.r0[(size_t)pair * T.nsamples + s] = r0;
+            T.g[(size_t)pair * T.nsamples + s] = k0k0 / r0;
+        }
+        T.scale[pair] = scale;
+    };
+    for (int i = 0; i < N; ++i) {
+        for (int q = 0; q < N; ++q) fill(i * N + q, plan.mu[i], plan.mu[q], plan.wt[q] * plan.mu[q]);
+        fill(N * N + i, plan.mu[i], plan.csz, 1.0);
+    }
+    for (int j = 0; j < nlos; ++j) {
+        for (int q = 0; q < N; ++q) fill(N * N + N + j * N + q, plan.los_mu[j], plan.mu[q], plan.wt[q] * plan.mu[q]);
+        fill(N * N + N + nlos * N + j, plan.los_mu[j], plan.csz, 1.0);
+    }
+    return T;
+}
+
 BrdfTables build_brdf_tables(int kind, const HostPlan& plan) {
-    if (kind != kBrdfModis) throw std::runtime_error("B200 DO path: only the Lambertian and MODIS BRDFs are supported");
+    if (kind != kBrdfModis) throw std::runtime_error("build_brdf_tables: only the MODIS model is kernel based");
     BrdfTables T;
     T.kind = kind;
     T.nk = 3;

@@ -207,7 +207,8 @@ DeviceEngine::~DeviceEngine() {
     for (void* p : m_limb_ptrs)
         if (p) cudaFree(p);
     if (d_los_od) cudaFree(d_los_od);
-    for (void* p : {(void*)d_brdf_args, (void*)d_zero_albedo, (void*)d_brdf_Rss, (void*)d_brdf_rsun, (void*)d_brdf_Rls, (void*)d_brdf_rlsun})
+    for (void* p : {(void*)d_brdf_args, (void*)d_zero_albedo, (void*)d_brdf_Rss, (void*)d_brdf_rsun, (void*)d_brdf_Rls, (void*)d_brdf_rlsun,
+                    (void*)d_snow_r0, (void*)d_snow_g, (void*)d_snow_cos, (void*)d_snow_w, (void*)d_snow_scale})
         if (p) cudaFree(p);
     for (void* p : {(void*)d_mu, (void*)d_wt, (void*)d_lp_mu, (void*)d_lp_csz, (void*)d_lp_los, (void*)d_los_mu, (void*)d_wf_tab,
                     (void*)d_los_cosmphi, (void*)d_layer_dh, (void*)d_interp_w, (void*)d_interp_idx,
@@ -259,6 +260,7 @@ size_t DeviceEngine::ws_bytes(bool wf_on, int ngroups) const {
     if (m_fast) d += 3 * (N * (N + 1) / 2) * M * L + nlos * (L + 1) + nlos * L * 3;  // eigen planes, LOS exponentials
     d += M * L * 2 * N;                                             // x
     if (m_brdf_kind != 0) d += M * (2 * N * N + 2 * N);             // kernel-based surface sums
+    if (m_brdf_kind == kBrdfKokhanovsky) d += M * (N * N + N + nlos * N + nlos);   // per-wavelength Fourier coefficients
     if (m_is_limb) {
         const size_t nsza = m_limb.nsza, npts = m_limb.npts, nrays = m_limb.nrays;
         if (m_limb.ms_do) d += nsza * L * M * nstr + nsza + npts * M;    // Legendre projections, ground source, source table
@@ -290,7 +292,7 @@ int DeviceEngine::chunk_wavelengths() const {
 void DeviceEngine::ensure_workspace(int chunk) {
     // the derivative arrays are sized by the number of scattering groups: an atmosphere with more groups than the
     // workspace was built for needs a new one even when the chunk fits
-    if (chunk <= m_ws_chunk && m_ws_wf == m_wf_on && (!m_wf_on || m_ws_ngroups == m_ngroups) && m_ws_brdf == (m_brdf_kind != 0)) return;
+    if (chunk <= m_ws_chunk && m_ws_wf == m_wf_on && (!m_wf_on || m_ws_ngroups == m_ngroups) && m_ws_brdf == (m_brdf_kind != 0) && (m_brdf_kind == 0 || m_ws_brdf_kind == m_brdf_kind)) return;
     free_workspace();
     const size_t N = m_plan.N, L = m_plan.L, nstr = m_plan.nstr, nlos = m_plan.nlos, M = m_mlist.size();
     const size_t c = chunk;
@@ -340,6 +342,9 @@ void DeviceEngine::ensure_workspace(int chunk) {
     V.gsurf_stride = (int)(2 * N * N + 2 * N);
     if (m_brdf_kind != 0) V.gsurf = V.gsurf_out = A("gsurf", c * M * V.gsurf_stride);
     m_ws_brdf = m_brdf_kind != 0;
+    m_ws_brdf_kind = m_brdf_kind;
+    d_brdf_pw = nullptr;
+    if (m_brdf_kind == kBrdfKokhanovsky) d_brdf_pw = A("brdf_pw", c * M * (N * N + N + nlos * N + nlos));
     if (m_is_limb) {
         const size_t nsza = m_limb.nsza, npts = m_limb.npts, nrays = m_limb.nrays;
         m_lview.coef = m_lview.ground = m_lview.table = m_lview.phase = nullptr;
@@ -438,17 +443,29 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
         if (twostream_direct()) throw std::runtime_error("B200 two-stream kernel supports the Lambertian BRDF only");
         if (m_plan.N > 16) throw std::runtime_error("B200 DO path: kernel-based BRDFs need num_streams <= 32");
         if (m_brdf_tab_kind != m_brdf_kind) {
-            const BrdfTables T = build_brdf_tables(m_brdf_kind, m_plan);
-            for (double** p : {&d_brdf_Rss, &d_brdf_rsun, &d_brdf_Rls, &d_brdf_rlsun})
+            for (double** p : {&d_brdf_Rss, &d_brdf_rsun, &d_brdf_Rls, &d_brdf_rlsun, &d_snow_r0, &d_snow_g, &d_snow_cos, &d_snow_w, &d_snow_scale})
                 if (*p) {
                     cudaFree(*p);
                     *p = nullptr;
                 }
-            d_brdf_Rss = upload(T.Rss);
-            d_brdf_rsun = upload(T.rsun);
-            d_brdf_Rls = upload(T.Rls);
-            d_brdf_rlsun = upload(T.rlsun);
-            m_brdf_nk = T.nk;
+            if (m_brdf_kind == kBrdfKokhanovsky) {
+                const SnowTables T = build_snow_tables(m_plan);
+                d_snow_r0 = upload(T.r0);
+                d_snow_g = upload(T.g);
+                d_snow_cos = upload(T.cosphi);
+                d_snow_w = upload(T.weight);
+                d_snow_scale = upload(T.scale);
+                m_snow_npairs = T.npairs;
+                m_snow_nsamples = T.nsamples;
+                m_brdf_nk = 0;
+            } else {
+                const BrdfTables T = build_brdf_tables(m_brdf_kind, m_plan);
+                d_brdf_Rss = upload(T.Rss);
+                d_brdf_rsun = upload(T.rsun);
+                d_brdf_Rls = upload(T.Rls);
+                d_brdf_rlsun = upload(T.rlsun);
+                m_brdf_nk = T.nk;
+            }
             m_brdf_tab_kind = m_brdf_kind;
         }
         m_brdf_nargs = atm.brdf_nargs;
@@ -700,6 +717,21 @@ void DeviceEngine::solve_staged() {
             B.Rls = d_brdf_Rls;
             B.rlsun = d_brdf_rlsun;
             B.args = d_brdf_args + (size_t)m_brdf_nargs * w0;
+            B.pw = nullptr;
+            B.pw_out = nullptr;
+            B.npairs = m_snow_npairs;
+            B.nsamples = m_snow_nsamples;
+            B.snow_r0 = d_snow_r0;
+            B.snow_g = d_snow_g;
+            B.snow_cos = d_snow_cos;
+            B.snow_w = d_snow_w;
+            B.snow_scale = d_snow_scale;
+            if (m_brdf_kind == kBrdfKokhanovsky) {
+                B.pw_out = d_brdf_pw;
+                launch_brdf_expand_snow(V, B, m_stream);
+                B.pw = d_brdf_pw;
+                m_launches += 1;
+            }
             launch_surface_general(V, B, m_stream);
             m_launches += 1;
         }

@@ -190,6 +190,11 @@ class DeviceEngine {
     double *d_brdf_Rss = nullptr, *d_brdf_rsun = nullptr, *d_brdf_Rls = nullptr, *d_brdf_rlsun = nullptr;
     int m_brdf_nk = 0;
     bool m_ws_brdf = false;
+    int m_ws_brdf_kind = 0;
+    // snow model: sample tables (device) and the per-chunk coefficient array
+    double *d_snow_r0 = nullptr, *d_snow_g = nullptr, *d_snow_cos = nullptr, *d_snow_w = nullptr, *d_snow_scale = nullptr;
+    int m_snow_npairs = 0, m_snow_nsamples = 0;
+    double* d_brdf_pw = nullptr;   // workspace: [chunk][M][npairs]
 };
 
 }  // namespace disco

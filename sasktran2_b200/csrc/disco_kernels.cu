@@ -143,6 +143,45 @@ __global__ void __launch_bounds__(128) k_radiance(ChunkView V) {
 // (sktran_do_rte.h:116-345), and the ground-leaving radiance toward every line of sight added to the bottom layer's
 // wvec / vsrc (OpticalLayerArray::computeReflectedIntensities, sktran_do_layerarray.cpp:5-288).
 // One block per (wavelength, order); thread t < N: stream row t, N <= t < N + nlos: line of sight t - N.
+// Snow BRDF (Kokhanovsky): Fourier coefficients of r0 exp(-alpha K0 K0 / r0) / pi for every (stream / sun / LOS) pair of
+// one wavelength by the reference's azimuth quadrature (sktran_do_surface.h:49-91) over the host tables of r0 and
+// K0 K0 / r0; cos(m phi) by the Chebyshev recurrence.  Thread per (wavelength, pair); output pw[w][m][pair] in the
+// convention of the kernel tables ((1 + delta_m0) w_q mu_q folded into the stream-incidence pairs).
+__global__ void __launch_bounds__(128) k_brdf_expand_snow(ChunkView V, BrdfView B) {
+    const int npairs = B.npairs, M = V.M;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)V.nw * npairs) return;
+    const int pair = (int)(tid % npairs), w = (int)(tid / npairs);
+    const double alpha = sqrt(4.0 * kPi * B.args[(size_t)B.nargs * w]);
+    const double* __restrict__ r0 = B.snow_r0 + (size_t)pair * B.nsamples;
+    const double* __restrict__ g = B.snow_g + (size_t)pair * B.nsamples;
+    double acc[32];
+#pragma unroll
+    for (int m = 0; m < 32; ++m) acc[m] = 0.0;
+    for (int s = 0; s < B.nsamples; ++s) {
+        const double f = B.snow_w[s] * r0[s] * exp(-alpha * g[s]) * (1.0 / kPi);
+        const double c1 = B.snow_cos[s];
+        double cm1 = 1.0, cm = c1;   // cos(0 phi), cos(1 phi)
+        acc[0] += f;
+#pragma unroll
+        for (int m = 1; m < 32; ++m) {
+            if (m < V.T.nstr) acc[m] = fma(f, cm, acc[m]);
+            const double nx = fma(2.0 * c1, cm, -cm1);
+            cm1 = cm;
+            cm = nx;
+        }
+    }
+    const int NN = V.T.N * V.T.N;
+    const bool incidence = pair < NN || (pair >= NN + V.T.N && pair < npairs - V.T.nlos);   // stream-incidence pairs
+    for (int ms = 0; ms < M; ++ms) {
+        const int m = V.m_list[ms];
+        // compute_expansion: result * 0.5 pi (2 - delta_m0); the weights already carry both mirror images of phi
+        double v = acc[m] * 0.5 * kPi * (m == 0 ? 1.0 : 2.0);
+        if (incidence) v *= (m == 0 ? 2.0 : 1.0) * B.snow_scale[pair];
+        B.pw_out[((size_t)w * M + ms) * npairs + pair] = v;
+    }
+}
+
 __global__ void k_surface_general(ChunkView V, BrdfView B) {
     const int N = V.T.N, M = V.M, L = V.T.L, nlos = V.T.nlos, nstr = V.T.nstr;
     const int w = blockIdx.x / M, ms = blockIdx.x % M;
@@ -160,7 +199,15 @@ __global__ void k_surface_general(ChunkView V, BrdfView B) {
 #pragma unroll
     for (int q = 0; q < 16; ++q) R[q] = 0.0;
     double rsun = 0.0;
-    for (int k = 0; k < B.nk; ++k) {
+    if (B.pw) {   // per-wavelength coefficients (snow model): pw[w][ms][pair]
+        const double* __restrict__ pw = B.pw + ((size_t)w * M + ms) * B.npairs;
+        const double* __restrict__ tab = stream ? pw + t * N : pw + N * N + N + los * N;
+        rsun = stream ? pw[N * N + t] : pw[N * N + N + nlos * N + los];
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if (q < N) R[q] = tab[q];
+    }
+    for (int k = 0; k < (B.pw ? 0 : B.nk); ++k) {
         const double a = B.args[k + (size_t)B.nargs * w];
         const double* __restrict__ tab = stream ? B.Rss + (((size_t)k * nstr + m) * N + t) * N
                                                 : B.Rls + (((size_t)k * nstr + m) * nlos + los) * N;
@@ -207,6 +254,10 @@ __global__ void k_surface_general(ChunkView V, BrdfView B) {
         const double direct = V.include_ss ? V.T.csz / kPi * t_floor * rsun : 0.0;
         V.vsrc[o * V.vsrc_w] += attg * (sg + direct);
     }
+}
+void launch_brdf_expand_snow(const ChunkView& V, const BrdfView& B, cudaStream_t s) {
+    const long long n = (long long)V.nw * B.npairs;
+    if (n > 0) k_brdf_expand_snow<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V, B);
 }
 void launch_surface_general(const ChunkView& V, const BrdfView& B, cudaStream_t s) {
     const int threads = ((V.T.N + V.T.nlos + 31) / 32) * 32;

@@ -1,5 +1,5 @@
-"""Kernel-based surface BRDF: the MODIS model (isotropic + Ross-thick + Li-sparse-R,
-cpp/include/sasktran2/atmosphere/surface.h:246-362) through the discrete-ordinates solve.
+"""Non-Lambertian surface BRDFs: the MODIS model (isotropic + Ross-thick + Li-sparse-R) and the snow
+model of Kokhanovsky (cpp/include/sasktran2/atmosphere/surface.h:140-362) through the discrete-ordinates solve.
 
 The reference holds no numbers for it (tests/constituent/test_modis.py only runs it and checks finite differences), so
 the oracle's restatement of the models and of SurfaceStorage::compute_expansion (sktran_do_surface.h:49-91) is pinned by
@@ -84,6 +84,34 @@ def test_cuda_modis_brdf_vs_oracle(nstr, generic):
     ora = oracle.do_radiance(**_oracle_kw(sc), brdf_kind=2, brdf_args=args)["radiance"]
     err = np.max(np.abs(rad / ora - 1))
     print(f"MODIS nstr={nstr} generic={generic}: max rel diff vs oracle {err:.2e}")
+    assert err < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nstr", [4, 8, 16])
+def test_cuda_snow_brdf_vs_oracle(nstr):
+    """Snow BRDF of Kokhanovsky (not linear in its argument): device quadrature per wavelength against the oracle's."""
+    sc, _ = _case(nstr=nstr)
+    arg = np.linspace(2e-7, 5e-6, sc.nwavel)[None, :]
+
+    def run():
+        cfg = sk.Config()
+        cfg.num_streams = sc.nstr
+        cfg.multiple_scatter_source = sk.MultipleScatterSource.DiscreteOrdinates
+        cfg.single_scatter_source = sk.SingleScatterSource.DiscreteOrdinates
+        geo = sk.Geometry1D(sc.cos_sza, 0.0, sc.earth_radius, sc.altitudes, sk.InterpolationMethod(sc.interp), sk.GeometryType(sc.geotype))
+        view = sk.ViewingGeometry()
+        for cz, az in zip(sc.los_cos_vza, sc.los_rel_az):
+            view.add_ray(sk.GroundViewingSolar(sc.cos_sza, float(az), float(cz), sc.observer_altitude))
+        eng = sk.Engine(cfg, geo, view)
+        atm = sk.Atmosphere.from_scenario(sc, geo, cfg, calculate_derivatives=False)
+        atm.surface.use_snow_kokhanovsky(arg[0])
+        return eng.calculate_radiance(atm)["radiance"][:, :, 0]
+
+    rad = run()
+    ora = oracle.do_radiance(**_oracle_kw(sc), brdf_kind=1, brdf_args=arg)["radiance"]
+    err = np.max(np.abs(rad / ora - 1))
+    print(f"snow nstr={nstr}: max rel diff vs oracle {err:.2e}")
     assert err < 1e-9
 
 

@@ -77,6 +77,11 @@ struct ChunkView {
     const double* gsurf;      // [nw][M][2N^2 + 2N]: SP[i][j] | SM[i][j] | SG[i] | rho_m(mu_i, mu_0)
     double* gsurf_out;        // the same array, writable (k_surface_general)
     int gsurf_stride;
+    // ---- several solar zenith angles sharing one homogeneous solution and one factorisation (spherical path): the
+    //      arrays that depend on the SZA exist nsza times; slice s starts s * stride doubles after the pointers above
+    int nsza;                 // 0 / 1: single SZA
+    size_t sza_G, sza_surf, sza_trans, sza_xsol;   // strides of G, surf, lay_trans, xsol
+    double sza_csz[4];        // cos(SZA) of every slice
 };
 
 

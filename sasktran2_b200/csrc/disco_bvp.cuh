@@ -247,7 +247,7 @@ struct BvpCfg2 {
     static constexpr int MIN_BLOCKS = (R == 1) ? 4 : (NRHS == 1 ? 3 : 2);  // register budget: 128 / 168 / 255 per thread
     // factor blocks resident during the back substitution: the one being solved + 2 (1 for the long multi-RHS steps) in flight
     static constexpr int STAGES = (NRHS == 1) ? 3 : 2;
-    static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS + NC;   // factor block ring | x of the block below (NRHS = 1)
+    static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS + NC * (NRHS <= 4 ? NRHS : 1);   // factor block ring | x of the block below (row-owner substitution)
     static_assert(ROWS <= GL * R && NC <= GL, "panel rows fit the group; one pivot row per lane in the back substitution");
     static_assert(NRHS == 1 || NRHS <= GL, "one right-hand side per lane");
     static_assert(NRHS > 1 || (R == 1 && ROWS < GL), "a spare lane records the pivot's (lane, row) next to the multipliers");
@@ -440,7 +440,53 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
 #pragma unroll
     for (int k = 2; k <= STAGES; ++k) fetch_block(nsteps - k);
 
-    if (NRHS == 1) {
+    if constexpr (NRHS > 1 && Prob::ROW_OWNER_BACKSUB) {
+        // ---- a few right-hand sides (one per solar zenith angle): lane c owns pivot row c for every one of them
+        for (int step = nsteps - 1; step >= 0; --step) {
+            const int nleft = prob.nleft(step);
+            const int nright = prob.nright(step);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp(gmask);
+            const double* facs = ring + (step % STAGES) * NC * FS;
+            const int row = lane < nleft ? lane : 0;
+            const double* my = facs + row * FS;
+            double acc[NRHS], myx[NRHS];
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                acc[r] = my[4 * N + r];
+                myx[r] = 0.0;
+            }
+            for (int jx = 0; jx < nright; ++jx) {
+                const double u = my[NC + jx];
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) acc[r] = fma(-u, xs[r * NC + jx], acc[r]);
+            }
+            const double pinv = my[RL2];
+#pragma unroll
+            for (int cc = NC - 1; cc >= 0; --cc) {
+                if (cc < nleft) {
+                    const double u = my[cc];
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) {
+                        double xv = acc[r] * pinv;
+                        xv = __shfl_sync(gmask, xv, (int)gbase + cc);
+                        if (lane < cc) acc[r] = fma(-u, xv, acc[r]);
+                        if (lane == cc) myx[r] = xv;
+                    }
+                }
+            }
+            __syncwarp(gmask);
+            if (lane < nleft) {
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) {
+                    xs[r * NC + lane] = myx[r];
+                    if (valid) prob.store(step, lane, r, myx[r]);
+                }
+            }
+            __syncwarp(gmask);
+            fetch_block(step - STAGES);
+        }
+    } else if (NRHS == 1) {
         // ---- lane c owns pivot row c of the block; x of the block below sits in xs
         for (int step = nsteps - 1; step >= 0; --step) {
             const int nleft = prob.nleft(step);
@@ -1353,6 +1399,47 @@ __global__ void __launch_bounds__(BvpCfg<N, NRHS>::WARPS_PER_BLOCK * 32) k_bvp_a
     double* fac = V.fac + (size_t)gid * V.fac_stride;
     staircase_solve<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
                        V.status);
+}
+
+// Forward solve of NRHS solar geometries sharing one matrix (ForwardRowsMulti): the column-by-column elimination with
+// NRHS right-hand-side columns, row-owner back substitution per right-hand side.
+template <int N, int NRHS>
+__global__ void __launch_bounds__(BvpCfg2<N, NRHS>::WARPS_PER_BLOCK * 32, BvpCfg2<N, NRHS>::MIN_BLOCKS) k_bvp_multi(ChunkView V) {
+    using C = BvpCfg2<N, NRHS>;
+    extern __shared__ __align__(16) double smem[];
+    const int lane_w = threadIdx.x & 31;
+    const int gidx_in_block = threadIdx.x / C::GL;
+    const int lane = threadIdx.x % C::GL;
+    const unsigned gbase = (unsigned)((lane_w / C::GL) * C::GL);
+    const unsigned gmask = (C::GL == 32) ? FULL_MASK : (((1u << C::GL) - 1u) << gbase);
+    long long prob = (long long)blockIdx.x * C::GROUPS_PER_BLOCK + gidx_in_block;
+    const long long nprob = (long long)V.nw * V.M;
+    const bool valid = prob < nprob;
+    if (!valid) prob = nprob - 1;
+    const int w = (int)(prob / V.M), ms = (int)(prob % V.M);
+    ForwardRowsMulti<N, NRHS> rows(V, w, ms);
+    double* fac = V.fac + (size_t)prob * V.fac_stride;
+    staircase_solve_v2<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid, V.status);
+}
+template <int N, int NRHS>
+static void launch_bvp_multi_nr(const ChunkView& V, cudaStream_t s) {
+    using C = BvpCfg2<N, NRHS>;
+    const long long nprob = (long long)V.nw * V.M;
+    const size_t smem = (size_t)C::GROUPS_PER_BLOCK * C::SMEM_DOUBLES_PER_GROUP * sizeof(double);
+    static DeviceOnce attr_set;
+    if (attr_set.first()) cudaFuncSetAttribute(k_bvp_multi<N, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_bvp_multi<N, NRHS><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
+}
+template <int N>
+static void launch_bvp_multi_n(const ChunkView& V, cudaStream_t s) {
+    if constexpr (3 * N <= 32) {
+        switch (V.nsza) {
+            case 2: launch_bvp_multi_nr<N, 2>(V, s); break;
+            case 3: launch_bvp_multi_nr<N, 3>(V, s); break;
+            case 4: launch_bvp_multi_nr<N, 4>(V, s); break;
+            default: break;
+        }
+    }
 }
 
 // SK_B200_BVP=3 selects the 2D-distributed elimination (version 3) for N = 8.  Measured on B200 it is within 10 % of

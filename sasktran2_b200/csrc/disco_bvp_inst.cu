@@ -7,4 +7,5 @@
 namespace disco {
 void DISCO_CAT(launch_bvp_n, DISCO_N)(const ChunkView& V, cudaStream_t s) { launch_bvp_n<DISCO_N>(V, s); }
 void DISCO_CAT(launch_bvp_adjoint_n, DISCO_N)(const ChunkView& V, cudaStream_t s) { launch_bvp_adjoint_n<DISCO_N>(V, s); }
+void DISCO_CAT(launch_bvp_multi_n, DISCO_N)(const ChunkView& V, cudaStream_t s) { launch_bvp_multi_n<DISCO_N>(V, s); }
 }  // namespace disco

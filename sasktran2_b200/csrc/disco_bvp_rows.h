@@ -18,6 +18,7 @@ template <int N>
 struct ForwardRows {
     static constexpr int NRHS = 1;
     static constexpr bool KEEPS_L = true;  // the forward elimination can record its multipliers (transposed solves)
+    static constexpr bool ROW_OWNER_BACKSUB = false;
     const ChunkView& V;
     int w, ms, m, L;
     const double *Wp, *Wm, *kth, *G;
@@ -228,12 +229,57 @@ struct ForwardRows {
     }
 };
 
+// Forward system of several solar zenith angles at once (spherical path): the matrix - homogeneous solutions, surface
+// coupling - does not depend on the SZA, only the right-hand side does (Green's particular solutions G, direct beam on
+// the ground).  Right-hand side r comes from slice r of the per-SZA arrays (ChunkView::sza_*); one factorisation, NRHS
+// substitutions.  The reference factorises once per SZA (DOSource::calculate, source_term/do_source.cpp:35-58).
+template <int N, int NRHS_>
+struct ForwardRowsMulti : ForwardRows<N> {
+    using Base = ForwardRows<N>;
+    static constexpr int NRHS = NRHS_;
+    static constexpr bool KEEPS_L = false;
+    static constexpr bool ROW_OWNER_BACKSUB = true;   // few right-hand sides: lane c owns pivot row c for each of them
+    DISCO_HD ForwardRowsMulti(const ChunkView& V_, int w_, int ms_) : Base(V_, w_, ms_) {}
+    DISCO_HD double rhs_of(int step, int rank, int r) const {
+        const ChunkView& V = this->V;
+        const int L = this->L, w = this->w;
+        const double* G = this->G + (size_t)r * V.sza_G;
+        const int p = step;
+        if (step == 0 && rank < N) return -G[rank];
+        if (step == 0) rank -= N;
+        const double* Gu = G + (size_t)p * 4 * N;
+        if (p < L - 1) {
+            const double* Gl = Gu + 4 * N;
+            const bool first = rank < N;
+            const int i = first ? rank : rank - N;
+            return first ? (-Gu[3 * N + i] + Gl[N + i]) : (-Gu[2 * N + i] + Gl[i]);
+        }
+        double rhs = -Gu[3 * N + rank];
+        if (this->m == 0) {
+            const double* surf = V.surf + (size_t)r * V.sza_surf + (size_t)w * (2 * N + 1);
+            rhs += 2.0 * V.albedo[w] * surf[2 * N];
+            rhs += V.sza_csz[r] * V.albedo[w] / kPi * V.lay_trans[(size_t)r * V.sza_trans + (size_t)w * (L + 1) + L];
+        }
+        return rhs;
+    }
+    DISCO_HD void load(int step, int rank, double* a) const {
+        Base::load(step, rank, a);   // matrix part and the right-hand side of slice 0
+#pragma unroll
+        for (int r = 1; r < NRHS; ++r) a[4 * N + r] = rhs_of(step, rank, r);
+    }
+    DISCO_HD void store(int step, int c, int r, double v) const {
+        const ChunkView& V = this->V;
+        V.xsol[(size_t)r * V.sza_xsol + (((size_t)this->w * V.M + this->ms) * this->L + step) * 2 * N + c] = v;
+    }
+};
+
 // Row loader of the transposed system A^T z = wvec(los): equation block b = columns of layer b, unknown
 // blocks = rows of A (TOA rows, interface rows, ground rows).
 template <int N, int NRHS_>
 struct AdjointRows {
     static constexpr int NRHS = NRHS_;
     static constexpr bool KEEPS_L = false;
+    static constexpr bool ROW_OWNER_BACKSUB = false;
     DISCO_HD int row_of(int, int) const { return 0; }
     const ChunkView& V;
     int w, ms, m, L, los0, nl;

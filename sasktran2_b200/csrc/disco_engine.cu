@@ -100,6 +100,14 @@ void DeviceEngine::init_limb() {
     }
 }
 
+bool DeviceEngine::limb_shared_factorisation() const {
+    static const bool off = [] {
+        const char* e = std::getenv("SK_B200_LIMB_SHARED");
+        return e && e[0] == '0';
+    }();
+    return m_is_limb && m_fast && !off && bvp_multi_supported(m_plan.N, m_limb.nsza);
+}
+
 void DeviceEngine::init(const EngineOptions& opt) {
     const HostPlan& plan = m_plan;
     int ndev = 0;
@@ -264,6 +272,8 @@ size_t DeviceEngine::ws_bytes(bool wf_on, int ngroups) const {
     if (m_is_limb) {
         const size_t nsza = m_limb.nsza, npts = m_limb.npts, nrays = m_limb.nrays;
         if (m_limb.ms_do) d += nsza * L * M * nstr + nsza + npts * M;    // Legendre projections, ground source, source table
+        if (m_limb.ms_do && limb_shared_factorisation())   // per-SZA copies of secant, beam, G, surface sums, x (+ wider factor rows)
+            d += (nsza - 1) * (L + (L + 1) + M * L * 4 * N + (2 * N + 1) + M * L * 2 * N) + M * (bvp_fac_stride((int)N, (int)nsza, (int)L) - bvp_fac_stride((int)N, 1, (int)L));
         if (m_limb.ss_exact) d += nrays * m_plan.nloc;                     // single-scatter phase function
     }
     if (!wf_on) {
@@ -315,16 +325,17 @@ void DeviceEngine::ensure_workspace(int chunk) {
     V.lay_od = A("lay_od", c * L);
     V.lay_ssa = A("lay_ssa", c * L);
     V.lay_beta = A("lay_beta", c * L * nstr);
-    V.lay_secant = A("lay_secant", c * L);
-    V.lay_trans = A("lay_trans", c * (L + 1));
+    const size_t zs = (m_is_limb && m_limb.ms_do && limb_shared_factorisation()) ? (size_t)m_limb.nsza : 1;   // per-SZA slices
+    V.lay_secant = A("lay_secant", zs * c * L);
+    V.lay_trans = A("lay_trans", zs * c * (L + 1));
     V.lay_cumod = A("lay_cumod", c * (L + 1));
     V.lay_totext = A("lay_totext", c * L);
     V.lay_scatext = A("lay_scatext", c * L);
     V.Wp = A("Wp", c * M * L * N * N);
     V.Wm = A("Wm", c * M * L * N * N);
     V.kth = A("kth", c * M * L * 2 * N);
-    V.G = A("G", c * M * L * 4 * N);
-    V.surf = A("surf", c * (2 * N + 1));
+    V.G = A("G", zs * c * M * L * 4 * N);
+    V.surf = A("surf", zs * c * (2 * N + 1));
     V.wvec = A("wvec", c * M * nlos * L * 2 * N);
     V.vsrc_w = m_fast ? (int)N : 1;
     V.vsrc = A("vsrc", c * M * nlos * L * V.vsrc_w);
@@ -337,7 +348,7 @@ void DeviceEngine::ensure_workspace(int chunk) {
         V.los_att = A("los_att", c * nlos * (L + 1));
         V.los_lay = A("los_lay", c * nlos * L * 3);
     }
-    V.xsol = A("xsol", c * M * L * 2 * N);
+    V.xsol = A("xsol", zs * c * M * L * 2 * N);
     V.gsurf = V.gsurf_out = nullptr;
     V.gsurf_stride = (int)(2 * N * N + 2 * N);
     if (m_brdf_kind != 0) V.gsurf = V.gsurf_out = A("gsurf", c * M * V.gsurf_stride);
@@ -356,7 +367,7 @@ void DeviceEngine::ensure_workspace(int chunk) {
         if (m_limb.ss_exact) m_lview.phase = A("limb_phase", c * nrays * m_plan.nloc);
     }
     if (!m_wf_on) {
-        V.fac_stride = bvp_fac_stride((int)N, 1, (int)L);
+        V.fac_stride = bvp_fac_stride((int)N, (int)zs, (int)L);
         V.fac = A("fac", c * M * V.fac_stride);
         V.zadj = V.lfac = V.yadj = nullptr;
         V.lfac_stride = 0;
@@ -667,11 +678,51 @@ void DeviceEngine::solve_staged() {
                 launch_layer_optics(V, m_stream);
                 mark(); slots.push_back(T_OPTICS);
                 m_launches += 1;
-                for (int sz = 0; sz < m_limb.nsza; ++sz) {
+                if (limb_shared_factorisation()) {
+                    // The homogeneous solutions and the BVP matrix do not depend on the solar zenith angle: one eigen-solve
+                    // and one factorisation serve every SZA of the source table; only the beam, the particular solutions
+                    // and the right-hand sides are per SZA (the reference redoes everything per SZA, do_source.cpp:35-58).
+                    const size_t cw = (size_t)m_ws_chunk;
+                    const size_t sSec = cw * V.T.L, sTr = cw * (V.T.L + 1), sG = cw * V.M * V.T.L * 4 * V.T.N,
+                                 sSurf = cw * (2 * V.T.N + 1), sX = cw * V.M * V.T.L * 2 * V.T.N;
+                    ChunkView B0 = V;   // slice 0 = the base pointers
+                    auto slice = [&](int sz) {
+                        ChunkView S = B0;
+                        S.T.csz = m_limb.sza_grid[sz];
+                        S.T.lp_csz = d_sza_lp_csz[sz];
+                        S.chapman = d_sza_chapman[sz];
+                        S.lay_secant = B0.lay_secant + sz * sSec;
+                        S.lay_trans = B0.lay_trans + sz * sTr;
+                        S.G = B0.G + sz * sG;
+                        S.surf = B0.surf + sz * sSurf;
+                        S.xsol = B0.xsol + sz * sX;
+                        return S;
+                    };
+                    for (int sz = 0; sz < m_limb.nsza; ++sz) launch_beam(slice(sz), m_stream, sz == 0);
+                    mark(); slots.push_back(T_OPTICS);
+                    launch_layer_eig_fast(B0, m_stream);
+                    for (int sz = 0; sz < m_limb.nsza; ++sz) launch_layer_post_fast(slice(sz), m_stream);
+                    mark(); slots.push_back(T_LAYER);
+                    ChunkView Mv = B0;
+                    Mv.nsza = m_limb.nsza;
+                    Mv.T.csz = m_limb.sza_grid[0];
+                    Mv.T.lp_csz = d_sza_lp_csz[0];
+                    Mv.sza_G = sG;
+                    Mv.sza_surf = sSurf;
+                    Mv.sza_trans = sTr;
+                    Mv.sza_xsol = sX;
+                    for (int sz = 0; sz < m_limb.nsza; ++sz) Mv.sza_csz[sz] = m_limb.sza_grid[sz];
+                    launch_bvp_multi(Mv, m_stream);
+                    mark(); slots.push_back(T_BVP);
+                    for (int sz = 0; sz < m_limb.nsza; ++sz) launch_limb_coef(slice(sz), Lv, sz, m_stream);
+                    mark(); slots.push_back(T_LIMB_SOURCE);
+                    m_launches += 2 * m_limb.nsza + 2 + m_limb.nsza + 1;
+                }
+                for (int sz = 0; sz < (limb_shared_factorisation() ? 0 : m_limb.nsza); ++sz) {
                     V.T.csz = m_limb.sza_grid[sz];
                     V.T.lp_csz = d_sza_lp_csz[sz];
                     V.chapman = d_sza_chapman[sz];
-                    launch_beam(V, m_stream);
+                    launch_beam(V, m_stream, sz == 0);
                     mark(); slots.push_back(T_OPTICS);
                     if (m_fast) {
                         launch_layer_solve_fast(V, m_stream);

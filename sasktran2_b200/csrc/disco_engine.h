@@ -112,6 +112,8 @@ class DeviceEngine {
   private:
     void init(const EngineOptions& opt);
     void init_limb();
+    // spherical path: one eigen-solve and one BVP factorisation for all SZAs of the source table (SK_B200_LIMB_SHARED=0: per SZA)
+    bool limb_shared_factorisation() const;
     void free_inputs();
     void free_workspace();
     void ensure_workspace(int chunk);

@@ -25,15 +25,19 @@ static int wf_fast_blocks_per_order(int M) {
 }
 
 template <int N>
-static void launch_fast_n(const ChunkView& V, cudaStream_t s) {
+static void launch_eig_n(const ChunkView& V, cudaStream_t s) {
+    const long long nq = (long long)V.nw * V.T.L;
+    const dim3 grid_t((unsigned)((nq + 127) / 128), (unsigned)V.M);
+    k_eig_setup<N><<<grid_t, 128, 0, s>>>(V);
+    k_eig_jacobi<N><<<grid_t, 128, 0, s>>>(V);
+}
+template <int N>
+static void launch_post_n(const ChunkView& V, cudaStream_t s) {
     const long long nq = (long long)V.nw * V.T.L;
     if (V.T.nlos > 0) {   // the spherical path solves the layers without plane-parallel lines of sight
         const long long n = (long long)V.nw * V.T.nlos * (V.T.L + 1);
         k_los_atten<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V);
     }
-    const dim3 grid_t((unsigned)((nq + 127) / 128), (unsigned)V.M);
-    k_eig_setup<N><<<grid_t, 128, 0, s>>>(V);
-    k_eig_jacobi<N><<<grid_t, 128, 0, s>>>(V);
     const size_t smem = (size_t)post_smem_doubles<N>(V.T.nlos) * sizeof(double);
     static DeviceOnce attr_set;
     if (attr_set.first()) {
@@ -45,14 +49,26 @@ static void launch_fast_n(const ChunkView& V, cudaStream_t s) {
     k_layer_post<N><<<grid_p, 128, smem, s>>>(V);
 }
 
-// launches 4 kernels
-void launch_layer_solve_fast(const ChunkView& V, cudaStream_t s) {
+void launch_layer_eig_fast(const ChunkView& V, cudaStream_t s) {
     switch (V.T.N) {
-        case 2: launch_fast_n<2>(V, s); break;
-        case 4: launch_fast_n<4>(V, s); break;
-        case 8: launch_fast_n<8>(V, s); break;
+        case 2: launch_eig_n<2>(V, s); break;
+        case 4: launch_eig_n<4>(V, s); break;
+        case 8: launch_eig_n<8>(V, s); break;
         default: break;
     }
+}
+void launch_layer_post_fast(const ChunkView& V, cudaStream_t s) {
+    switch (V.T.N) {
+        case 2: launch_post_n<2>(V, s); break;
+        case 4: launch_post_n<4>(V, s); break;
+        case 8: launch_post_n<8>(V, s); break;
+        default: break;
+    }
+}
+// launches 4 kernels
+void launch_layer_solve_fast(const ChunkView& V, cudaStream_t s) {
+    launch_layer_eig_fast(V, s);
+    launch_layer_post_fast(V, s);
 }
 
 template <int N, int G>

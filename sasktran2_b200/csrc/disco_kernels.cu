@@ -35,7 +35,7 @@ __global__ void k_layer_optics(ChunkView V) {
 // One warp per wavelength (beam_body in disco_bodies.h is the serial statement used by the host emulation): lane 0
 // runs the thickness scan in the reference's summation order, then the lanes share the O(L^2) chapman products - the
 // one-thread-per-wavelength version kept 3 % of the warps of 10 blocks busy for 2 % of a step.
-__global__ void __launch_bounds__(128) k_beam(ChunkView V) {
+__global__ void __launch_bounds__(128) k_beam(ChunkView V, int scan_od) {
     const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= V.nw) return;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) k_beam(ChunkView V) {
     double* cum = V.lay_cumod + (size_t)w * (L + 1);
     double* sec = V.lay_secant + (size_t)w * L;
     double* tr = V.lay_trans + (size_t)w * (L + 1);
-    if (lane == 0) {
+    if (lane == 0 && scan_od) {   // once per chunk: a second SZA reuses the thicknesses of the first
         double ceiling = 0.0, floor_d = 0.0;
         cum[0] = 0.0;
         for (int p = 0; p < L; ++p) {
@@ -268,7 +268,9 @@ void launch_layer_optics(const ChunkView& V, cudaStream_t s) {
     const long long n = (long long)V.nw * V.T.L;
     k_layer_optics<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V);
 }
-void launch_beam(const ChunkView& V, cudaStream_t s) { k_beam<<<(unsigned)(((long long)V.nw * 32 + 127) / 128), 128, 0, s>>>(V); }
+void launch_beam(const ChunkView& V, cudaStream_t s, bool scan_od) {
+    k_beam<<<(unsigned)(((long long)V.nw * 32 + 127) / 128), 128, 0, s>>>(V, scan_od ? 1 : 0);
+}
 void launch_validate_inputs(const ChunkView& V, cudaStream_t s) {
     const long long n = (long long)V.nw * V.T.nloc;
     if (n > 0) k_validate_inputs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(V);
@@ -280,7 +282,7 @@ static void launch_layer_solve_n(const ChunkView& V, cudaStream_t s) {
     k_layer_solve<N><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V);
 }
 // per-N entry points live in disco_bvp_inst.cu (compiled once per N)
-#define DISCO_DECL_BVP(N) void launch_bvp_n##N(const ChunkView&, cudaStream_t); void launch_bvp_adjoint_n##N(const ChunkView&, cudaStream_t);
+#define DISCO_DECL_BVP(N) void launch_bvp_n##N(const ChunkView&, cudaStream_t); void launch_bvp_adjoint_n##N(const ChunkView&, cudaStream_t); void launch_bvp_multi_n##N(const ChunkView&, cudaStream_t);
 DISCO_DECL_BVP(1) DISCO_DECL_BVP(2) DISCO_DECL_BVP(4) DISCO_DECL_BVP(8) DISCO_DECL_BVP(16)
 static int adj_rhs_for(int nlos) { return nlos <= 4 ? 4 : 10; }
 #define DISCO_DECL_WF(N) void launch_wf_layer_n##N(const ChunkView&, cudaStream_t);
@@ -470,6 +472,8 @@ void launch_layer_solve(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_N(l
     }
 void launch_bvp(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_FN(launch_bvp_n, V, s) }
 void launch_bvp_adjoint(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_FN(launch_bvp_adjoint_n, V, s) }
+bool bvp_multi_supported(int N, int nsza) { return 3 * N <= 32 && nsza >= 2 && nsza <= 4; }
+void launch_bvp_multi(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_FN(launch_bvp_multi_n, V, s) }
 void launch_wf_layer(const ChunkView& V, cudaStream_t s) { DISCO_DISPATCH_FN(launch_wf_layer_n, V, s) }
 void launch_wf_chain(const ChunkView& V, cudaStream_t s) {
     const long long n = (long long)V.nw * V.T.nlos;

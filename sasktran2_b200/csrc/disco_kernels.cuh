@@ -35,12 +35,18 @@ struct BrdfView {
 void launch_surface_general(const ChunkView& V, const BrdfView& B, cudaStream_t s);
 void launch_brdf_expand_snow(const ChunkView& V, const BrdfView& B, cudaStream_t s);
 void launch_layer_optics(const ChunkView& V, cudaStream_t s);
-void launch_beam(const ChunkView& V, cudaStream_t s);
+void launch_beam(const ChunkView& V, cudaStream_t s, bool scan_od = true);
 void launch_validate_inputs(const ChunkView& V, cudaStream_t s);
 void launch_layer_solve(const ChunkView& V, cudaStream_t s);
 // register-resident path for N = 2, 4, 8 (disco_fast*.cuh); needs the eig*/los_* planes and vsrc_w = N
 bool fast_path_supported(int N);
 void launch_layer_solve_fast(const ChunkView& V, cudaStream_t s);
+// the two halves of the above: homogeneous solutions (independent of the solar geometry), particular solutions + LOS terms
+void launch_layer_eig_fast(const ChunkView& V, cudaStream_t s);
+void launch_layer_post_fast(const ChunkView& V, cudaStream_t s);
+// forward BVP of V.nsza solar geometries with one factorisation (2 <= nsza <= 4, N <= 8)
+bool bvp_multi_supported(int N, int nsza);
+void launch_bvp_multi(const ChunkView& V, cudaStream_t s);
 void launch_wf_layer_fast(const ChunkView& V, cudaStream_t s);
 size_t wf_layer_fast_smem_bytes(int N, int G, int nlos);
 void launch_bvp(const ChunkView& V, cudaStream_t s);

@@ -247,7 +247,7 @@ struct BvpCfg2 {
     static constexpr int MIN_BLOCKS = (R == 1) ? 4 : (NRHS == 1 ? 3 : 2);  // register budget: 128 / 168 / 255 per thread
     // factor blocks resident during the back substitution: the one being solved + 2 (1 for the long multi-RHS steps) in flight
     static constexpr int STAGES = (NRHS == 1) ? 3 : 2;
-    static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS + NC * (NRHS <= 4 ? NRHS : 1);   // factor block ring | x of the block below (row-owner substitution)
+    static constexpr int SMEM_DOUBLES_PER_GROUP = STAGES * NC * FS + NC * (NRHS <= 4 ? NRHS : 1) + 2;   // factor block ring | x of the block below (row-owner substitution) | two mbarriers (TMA row staging)
     static_assert(ROWS <= GL * R && NC <= GL, "panel rows fit the group; one pivot row per lane in the back substitution");
     static_assert(NRHS == 1 || NRHS <= GL, "one right-hand side per lane");
     static_assert(NRHS > 1 || (R == 1 && ROWS < GL), "a spare lane records the pivot's (lane, row) next to the multipliers");
@@ -578,7 +578,33 @@ __device__ __forceinline__ void staircase_solve_v2(const Prob& prob, double* gs,
 //                 their raw rows in the factor block, which is flushed as in version 2 - layout, back substitution
 //                 and the transposed solves (k_bvp_tsolve) are unchanged.
 // -------------------------------------------------------------------------------------------------
-template <int N, class Prob>
+// ---- TMA helpers (1-D bulk copies global -> shared, completion on an mbarrier of the warp's shared-memory area)
+__device__ __forceinline__ void bvp_mbar_init(unsigned long long* bar, unsigned count) {
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bvp_mbar_expect(unsigned long long* bar, unsigned bytes) {
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bvp_tma_load(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(gmem_src), "r"(bytes), "r"(mb)
+                 : "memory");
+}
+__device__ __forceinline__ void bvp_mbar_wait(unsigned long long* bar, unsigned phase) {
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(mb),
+        "r"(phase)
+        : "memory");
+}
+
+template <int N, class Prob, bool TMA = false>
 __device__ __forceinline__ void staircase_solve_v4(const Prob& prob, double* gs, double* fac, int lane, unsigned gbase,
                                                    unsigned gmask, bool valid, unsigned int* status, double* lf) {
     static_assert(Prob::NRHS == 1, "forward solve");
@@ -600,18 +626,62 @@ __device__ __forceinline__ void staircase_solve_v4(const Prob& prob, double* gs,
     bool singular = false;
     const int nsteps = prob.nsteps();
 
+    // TMA variant: the solutions of layer p (W+-, k | theta, G) arrive as one tile per layer in ring slots 1 and 2 (free
+    // during the elimination: the factor block of every step but the last is assembled in slot 0), one step ahead of
+    // their use, by per-row bulk copies issued from the lanes of the warp - off the LSU data pipe that bounds this kernel.
+    constexpr int TRS = Prob::TILE_RS, TD = Prob::TILE_DOUBLES;
+    static_assert(!TMA || TD <= NC * FS, "a layer tile fits a ring slot");
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(xs + NC);   // [2], after x of the block below
+    auto tile_of = [&](int layer) { return ring + (1 + (layer & 1)) * NC * FS; };
+    auto issue_tile = [&](int layer) {
+        if (layer >= nsteps) return;
+        double* t = tile_of(layer);
+        unsigned long long* bar = bars + (layer & 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0) bvp_mbar_expect(bar, (unsigned)((2 * N * N + 6 * N) * sizeof(double)));
+        __syncwarp(gmask);
+        if (lane < N) bvp_tma_load(t + lane * TRS, prob.tile_src_wp(layer) + lane * N, N * sizeof(double), bar);
+        else if (lane < 2 * N) bvp_tma_load(t + N * TRS + (lane - N) * TRS, prob.tile_src_wm(layer) + (lane - N) * N, N * sizeof(double), bar);
+        else if (lane == 2 * N) bvp_tma_load(t + 2 * N * TRS, prob.tile_src_kth(layer), 2 * N * sizeof(double), bar);
+        else if (lane == 2 * N + 1) bvp_tma_load(t + 2 * N * TRS + 2 * N, prob.tile_src_g(layer), 4 * N * sizeof(double), bar);
+    };
+    if (TMA) {
+        if (lane == 0) {
+            bvp_mbar_init(bars, 1);
+            bvp_mbar_init(bars + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp(gmask);
+        issue_tile(0);
+        issue_tile(1);
+    }
+
     for (int step = 0; step < nsteps; ++step) {
+        if (TMA) {
+            if (step == 0) bvp_mbar_wait(bars, 0);
+            if (step + 1 < nsteps) bvp_mbar_wait(bars + ((step + 1) & 1), (unsigned)(((step + 1) >> 1) & 1));
+        }
         {   // new rows of this step go to the lowest free lanes
             const unsigned freeb = __ballot_sync(gmask, !act) & gmask;
             const int rank = __popc(freeb & lt_mask);
             if (!act && rank < prob.nnew(step)) {
                 act = true;
-                prob.load(step, rank, a);
+                if (TMA)
+                    prob.load_tiles(step, rank, a, tile_of(step), tile_of(step + 1));
+                else
+                    prob.load(step, rank, a);
                 myrow = prob.row_of(step, rank);
             }
         }
-        if (step + 1 < nsteps) prob.prefetch(step + 1, lane);
-        double* facs = ring + (step % STAGES) * NC * FS;
+        if (TMA) {
+            __syncwarp(gmask);          // every lane has read the tile of layer `step`: its slot takes layer step + 2
+            issue_tile(step + 2);
+        } else if (step + 1 < nsteps) {
+            prob.prefetch(step + 1, lane);
+        }
+        // TMA: slot 0 until the last step, whose block must sit where the back substitution expects it (its slot is a
+        // tile slot, no longer needed: the last step's rows are loaded)
+        double* facs = ring + ((TMA && step < nsteps - 1) ? 0 : (step % STAGES)) * NC * FS;
 #pragma unroll
         for (int cb = 0; cb < NC / B; ++cb) {
             const int c0 = cb * B;
@@ -1126,7 +1196,7 @@ __global__ void __launch_bounds__(BvpCfg3<N, NRHS>::WARPS_PER_BLOCK * 32, 3) k_b
 #ifndef DISCO_BVP4_MIN_BLOCKS
 #define DISCO_BVP4_MIN_BLOCKS 4
 #endif
-template <int N, bool BLOCKED = false>
+template <int N, bool BLOCKED = false, bool TMA = false>
 __global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, BLOCKED ? DISCO_BVP4_MIN_BLOCKS : BvpCfg2<N, 1>::MIN_BLOCKS) k_bvp_v2(ChunkView V) {
     using C = BvpCfg2<N, 1>;
     extern __shared__ __align__(16) double smem[];
@@ -1144,8 +1214,8 @@ __global__ void __launch_bounds__(BvpCfg2<N, 1>::WARPS_PER_BLOCK * 32, BLOCKED ?
     double* fac = V.fac + (size_t)prob * V.fac_stride;
     double* lf = V.lfac ? V.lfac + (size_t)prob * V.lfac_stride : nullptr;
     if constexpr (BLOCKED)
-        staircase_solve_v4<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
-                              V.status, lf);
+        staircase_solve_v4<N, ForwardRows<N>, TMA>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask,
+                                                   valid, V.status, lf);
     else
         staircase_solve_v2<N>(rows, smem + (size_t)gidx_in_block * C::SMEM_DOUBLES_PER_GROUP, fac, lane, gbase, gmask, valid,
                               V.status, lf);
@@ -1480,7 +1550,21 @@ static void launch_bvp_n(const ChunkView& V, cudaStream_t s) {
         if (attr_set.first()) {
             cudaFuncSetAttribute(k_bvp_v2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-        if (bvp_blocked()) {
+        // SK_B200_BVP_TMA=1: the rows of every step come from layer tiles staged in shared memory by the TMA engine
+        // (per-row cp.async.bulk into padded rows, mbarrier per tile slot) instead of L1-prefetched global loads.
+        // Measured on B200 (C5 shape, 4000 wavelengths): 37.1 ms against 35.4 ms for the global loads - 18 small bulk
+        // copies per layer and warp cost more than the 64-byte-per-lane row loads they replace - so it is opt-in.
+        static const bool use_tma = [] {
+            const char* e = std::getenv("SK_B200_BVP_TMA");
+            return e && e[0] == '1';
+        }();
+        if (bvp_blocked() && use_tma && N >= 2 && C::GL >= 2 * N + 2) {
+            static DeviceOnce attr5_set;
+            if (attr5_set.first()) {
+                cudaFuncSetAttribute(k_bvp_v2<N, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            }
+            k_bvp_v2<N, true, true><<<(unsigned)((nprob + C::GROUPS_PER_BLOCK - 1) / C::GROUPS_PER_BLOCK), C::WARPS_PER_BLOCK * 32, smem, s>>>(V);
+        } else if (bvp_blocked()) {
             static DeviceOnce attr4_set;
             if (attr4_set.first()) {
                 cudaFuncSetAttribute(k_bvp_v2<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -110,6 +110,86 @@ struct ForwardRows {
             a[4 * N] = rhs;
         }
     }
+    // ---- the same rows from shared-memory tiles of the layers' solutions (brought in by the TMA engine, disco_bvp.cuh):
+    //      tile of one layer = W+ rows | W- rows (row stride TILE_RS doubles: conflict-free LDS.128 for 8 lanes) |
+    //      k, theta [2N] | G [4N]
+    static constexpr int TILE_RS = N + 2;
+    static constexpr int TILE_DOUBLES = 2 * N * TILE_RS + 6 * N;
+    DISCO_HD void load_tiles(int step, int rank, double* a, const double* tu, const double* tl) const {
+        const int p = step;
+        const double* Wpu = tu;
+        const double* Wmu = tu + N * TILE_RS;
+        const double* thu = tu + 2 * N * TILE_RS + N;
+        const double* Gu = tu + 2 * N * TILE_RS + 2 * N;
+        if (step == 0 && rank < N) {
+            const int i = rank;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                a[j] = Wpu[i * TILE_RS + j];
+                a[N + j] = Wmu[i * TILE_RS + j] * thu[j];
+                a[2 * N + j] = 0.0;
+                a[3 * N + j] = 0.0;
+            }
+            a[4 * N] = -Gu[i];
+            return;
+        }
+        if (step == 0) rank -= N;
+        if (p < L - 1) {
+            const double* Wpl = tl;
+            const double* Wml = tl + N * TILE_RS;
+            const double* thl = tl + 2 * N * TILE_RS + N;
+            const double* Gl = tl + 2 * N * TILE_RS + 2 * N;
+            const bool first = rank < N;
+            const int i = first ? rank : rank - N;
+            const double* A1 = first ? Wmu : Wpu;
+            const double* A2 = first ? Wpu : Wmu;
+            const double* B1 = first ? Wml : Wpl;
+            const double* B2 = first ? Wpl : Wml;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                a[j] = A1[i * TILE_RS + j] * thu[j];
+                a[N + j] = A2[i * TILE_RS + j];
+                a[2 * N + j] = -B1[i * TILE_RS + j];
+                a[3 * N + j] = -(B2[i * TILE_RS + j] * thl[j]);
+            }
+            a[4 * N] = first ? (-Gu[3 * N + i] + Gl[N + i]) : (-Gu[2 * N + i] + Gl[i]);
+        } else {
+            const int i = rank;
+            const bool refl = (m == 0);
+            const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
+            const double* surf = V.surf + (size_t)w * (2 * N + 1);
+            const double* gs = V.gsurf ? V.gsurf + ((size_t)w * V.M + ms) * V.gsurf_stride : nullptr;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                double vm = Wmu[i * TILE_RS + j], vp = Wpu[i * TILE_RS + j];
+                if (refl) {
+                    vm -= alb2 * surf[j];
+                    vp -= alb2 * surf[N + j];
+                }
+                if (gs) {
+                    vm -= gs[i * N + j];
+                    vp -= gs[N * N + i * N + j];
+                }
+                a[j] = vm * thu[j];
+                a[N + j] = vp;
+                a[2 * N + j] = 0.0;
+                a[3 * N + j] = 0.0;
+            }
+            double rhs = -Gu[3 * N + i];
+            if (refl) {
+                rhs += alb2 * surf[2 * N];
+                rhs += V.T.csz * V.albedo[w] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
+            }
+            if (gs) rhs += gs[2 * N * N + i] + V.T.csz * gs[2 * N * N + N + i] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
+            a[4 * N] = rhs;
+        }
+    }
+    // global sources of a layer's tile (device only)
+    DISCO_HD const double* tile_src_wp(int p) const { return Wp + (size_t)p * N * N; }
+    DISCO_HD const double* tile_src_wm(int p) const { return Wm + (size_t)p * N * N; }
+    DISCO_HD const double* tile_src_kth(int p) const { return kth + (size_t)p * 2 * N; }
+    DISCO_HD const double* tile_src_g(int p) const { return G + (size_t)p * 4 * N; }
+
     // Segment loaders of the 2D-distributed elimination: window block wb (0..3) of new row `rank` of `step`,
     // i.e. entries a[wb * N .. wb * N + N) of load(), and its right-hand side.
     DISCO_HD void load_seg(int step, int rank, int wb, double* seg) const {

@@ -408,8 +408,8 @@ def main():
     ap.add_argument("--config", default=os.environ.get("SK_BENCH_CONFIG", "c5"), choices=sorted(CONFIGS))
     ap.add_argument("--nwavel", type=int, default=int(os.environ.get("SK_BENCH_NWAVEL", "0")),
                     help="total wavelengths of the spectrum (default: the named configuration's)")
-    ap.add_argument("--cpu-sample", type=int, default=240, help="wavelengths of the cpu_baseline sample (same config)")
-    ap.add_argument("--ref-sample", type=int, default=160, help="wavelengths per step of --impl reference")
+    ap.add_argument("--cpu-sample", type=int, default=2000, help="wavelengths of the cpu_baseline sample (same config; about 15 s on 16 cores)")
+    ap.add_argument("--ref-sample", type=int, default=640, help="wavelengths per step of --impl reference (about 5 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=48.0,

@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(128) k_limb_coef(ChunkView V, LimbView Lv, int
 template <int N>
 struct LimbCoefCfg {
     static constexpr int NSTR = 2 * N, PPW = 32 / N, PPB = PPW * 4;
-    static constexpr int PER_PROBLEM = 2 * N + 2 * N * N + 2 * N + 4;   // xq | tr[2][N][N] | ef | skew (8 banks)
+    static constexpr int TRS = N + 1;                                    // padded row of the transpose buffers: lane j reads row j
+    static constexpr int PER_PROBLEM_RAW = 2 * N + 2 * N * TRS + 2 * N;  // xq | tr[2][N][N + 1] | ef
+    static constexpr int PER_PROBLEM = PER_PROBLEM_RAW + ((4 - PER_PROBLEM_RAW % 16) + 16) % 16;   // stride = 4 (mod 16) doubles: 8-bank skew between problems
     static constexpr int TABLE = NSTR * N + NSTR + N;                    // tW[l][q] | lpc[l] | wmu[q]
     static constexpr int SMEM = TABLE + PPB * PER_PROBLEM;
 };
@@ -168,7 +170,8 @@ __global__ void __launch_bounds__(128) k_limb_coef_lanes(ChunkView V, LimbView L
     const unsigned gmask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (lane / N * N));
     double* xq = smem + Cf::TABLE + (size_t)pib * Cf::PER_PROBLEM;   // [2N]  Q+ | Q-
     double* tr = xq + 2 * N;                                         // [2][N][N]
-    double* ef = tr + 2 * N * N;                                     // [2N]  E | F
+    constexpr int TRS = Cf::TRS;
+    double* ef = tr + 2 * N * TRS;                                   // [2N]  E | F
     const double f0 = (m == 0 ? 1.0 : 2.0) * (1.0 / (4.0 * kPi));
     const long long nq = (long long)nw * L;
     for (long long qblk = blockIdx.x; qblk * Cf::PPB < nq; qblk += gridDim.x) {
@@ -225,16 +228,16 @@ __global__ void __launch_bounds__(128) k_limb_coef_lanes(ChunkView V, LimbView L
         // this solution's share of the diffuse field at every stream -> transpose through shared memory
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            tr[i * N + j] = fma(wp[i], a, wm[i] * b);
-            tr[N * N + i * N + j] = fma(wm[i], a, wp[i] * b);
+            tr[i * TRS + j] = fma(wp[i], a, wm[i] * b);
+            tr[N * TRS + i * TRS + j] = fma(wm[i], a, wp[i] * b);
         }
         __syncwarp();
         {
             double e = 0.0, f = 0.0;
 #pragma unroll
             for (int c = 0; c < N; ++c) {
-                e += tr[j * N + c];
-                f += tr[N * N + j * N + c];
+                e += tr[j * TRS + c];
+                f += tr[N * TRS + j * TRS + c];
             }
             ef[j] = e;
             ef[N + j] = f;

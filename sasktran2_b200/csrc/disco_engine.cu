@@ -795,7 +795,7 @@ void DeviceEngine::solve_staged() {
         if (m_wf_on) {
             launch_bvp_adjoint(V, m_stream);
             mark(); slots.push_back(T_WF_ADJOINT);
-            if (m_fast && wf_layer_fast_smem_bytes(m_plan.N, m_ngroups, m_plan.nlos) <= 200 * 1024)
+            if (m_fast && wf_layer_fast_tile(m_plan.N, m_ngroups, m_plan.nlos) > 0)
                 launch_wf_layer_fast(V, m_stream);
             else
                 launch_wf_layer(V, m_stream);

@@ -71,17 +71,46 @@ void launch_layer_solve_fast(const ChunkView& V, cudaStream_t s) {
     launch_layer_post_fast(V, s);
 }
 
+// Shared memory of k_wf_layer_fast<N, G> for nlos lines of sight processed tlos at a time (bytes; WfCfg's own formulas)
+static size_t wf_fast_smem_bytes(int N, int G, int nlos, int tlos) {
+    const int nstr = 2 * N, NL = G + 4, NH = G + 1, ppb = (32 / N) * 4;
+    const int exch = nstr * N + 2 * N * N + 2 * N, red = tlos * (NL + 1) * N;
+    const int raw = tlos * 2 * NH * N + (red > exch ? red : exch);
+    const int per_problem = raw + ((4 - raw % 16) + 16) % 16;  // WfCfg::per_problem
+    return sizeof(double) * (size_t)(2 * nstr * N + nlos * nstr + nstr + N + ppb * per_problem);
+}
+// Lines of sight per tile: the largest tile with which two blocks stay resident per SM (228 KB, 1 KB reserved per
+// block), then balanced over the tiles; 0 = the order tables alone do not fit (thousands of LOS: generic kernel).
+int wf_layer_fast_tile(int N, int G, int nlos) {
+    if (nlos < 1 || (N != 2 && N != 4 && N != 8) || G > 2) return 0;
+    const size_t budget = 113 * 1024;
+    int tmax = 0;
+    for (int t = 1; t <= nlos && wf_fast_smem_bytes(N, G, nlos, t) <= budget; ++t) tmax = t;
+    if (tmax == 0) return 0;
+    // test switch: cap the tile (SK_B200_WF_TILE=3 tiles even ten lines of sight)
+    static const int cap = [] { const char* e = std::getenv("SK_B200_WF_TILE"); return e ? std::atoi(e) : 0; }();
+    if (cap < 0) return 0;   // SK_B200_WF_TILE=-1: the generic thread-per-problem kernel (differential tests, timing)
+    if (cap > 0 && cap < tmax) tmax = cap;
+    const int ntiles = (nlos + tmax - 1) / tmax;
+    return (nlos + ntiles - 1) / ntiles;
+}
+
 template <int N, int G>
 static void launch_wf_fast_ng(const ChunkView& V, cudaStream_t s) {
     using Cf = WfCfg<N, G>;
     const long long nq = (long long)V.nw * V.T.L;
-    const size_t smem = (size_t)Cf::smem_doubles(V.T.nlos) * sizeof(double);
+    const int tlos = wf_layer_fast_tile(N, G, V.T.nlos);
+    const size_t smem = (size_t)(Cf::table_doubles(V.T.nlos) + Cf::PPB * Cf::per_problem(tlos)) * sizeof(double);
     static DeviceOnce attr_set;
     if (attr_set.first()) {
-        cudaFuncSetAttribute(k_wf_layer_fast<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_wf_layer_fast<N, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_wf_layer_fast<N, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     }
     const dim3 grid((unsigned)((nq + Cf::PPB - 1) / Cf::PPB), (unsigned)V.M);
-    k_wf_layer_fast<N, G><<<grid, 128, smem, s>>>(V);
+    if (tlos >= V.T.nlos)
+        k_wf_layer_fast<N, G, false><<<grid, 128, smem, s>>>(V, tlos);
+    else
+        k_wf_layer_fast<N, G, true><<<grid, 128, smem, s>>>(V, tlos);
 }
 template <int N>
 static void launch_wf_fast_n(const ChunkView& V, cudaStream_t s) {
@@ -91,14 +120,6 @@ static void launch_wf_fast_n(const ChunkView& V, cudaStream_t s) {
         case 2: launch_wf_fast_ng<N, 2>(V, s); break;
         default: break;
     }
-}
-// shared memory the fast weighting-function kernel needs for this problem shape (bytes)
-size_t wf_layer_fast_smem_bytes(int N, int G, int nlos) {
-    const int nstr = 2 * N, NL = G + 4, NH = G + 1, ppb = (32 / N) * 4;
-    const int exch = nstr * N + 2 * N * N + 2 * N, red = nlos * (NL + 1) * N;
-    const int raw = nlos * 2 * NH * N + (red > exch ? red : exch);
-    const int per_problem = raw + ((4 - raw % 16) + 16) % 16;  // WfCfg::per_problem
-    return sizeof(double) * (size_t)(2 * nstr * N + nlos * nstr + nstr + N + ppb * per_problem);
 }
 void launch_wf_layer_fast(const ChunkView& V, cudaStream_t s) {
     switch (V.T.N) {

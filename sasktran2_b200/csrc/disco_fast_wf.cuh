@@ -106,13 +106,17 @@ struct WfCfg {
     __host__ __device__ static constexpr int smem_doubles(int nlos) { return table_doubles(nlos) + PPB * per_problem(nlos); }
 };
 
-template <int N, int G>
-__global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
+template <int N, int G, bool TILED>
+__global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg) {
+    // TILED: lines of sight in tiles of tlos.  The per-LOS private areas (phase sums, staged adjoint slices, reduction
+    // rows) are sized for one tile and reused tile after tile, so the shared-memory footprint does not grow with nlos.
+    // The untiled instantiation (all LOS fit, tlos = nlos) has no tile loop: its registers are all spoken for.
     using Cf = WfCfg<N, G>;
     constexpr int NSTR = Cf::NSTR, NL = Cf::NL, NH = Cf::NH;
     constexpr int iTau = G, iOm = G + 1, iT = G + 2, iS = G + 3;
     extern __shared__ __align__(16) double smem[];
     const int L = V.T.L, M = V.M, nlos = V.T.nlos;
+    const int tlos = TILED ? tlos_arg : nlos;
     double* tW = smem;                   // [l][q]  w_q P_l^m(mu_q)
     double* tM = tW + NSTR * N;          // [l][a]  P_l^m(mu_a) / mu_a
     double* tL = tM + NSTR * N;          // [los][l]
@@ -132,9 +136,9 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
     const int pib = threadIdx.x / N;
     const unsigned lane = threadIdx.x & 31;
     const unsigned gmask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (lane / N * N));
-    double* pp = smem + Cf::table_doubles(nlos) + (size_t)pib * Cf::per_problem(nlos);
-    double* lpsS = pp;                            // [los][2 NH][q]: minus, plus, then (d minus, d plus) per group
-    double* red = pp + Cf::lps_doubles(nlos);     // [los][NL + 1][j]   (aliases the eigen exchange area)
+    double* pp = smem + Cf::table_doubles(nlos) + (size_t)pib * Cf::per_problem(tlos);
+    double* lpsS = pp;                            // [los in tile][2 NH][q]: minus, plus, then (d minus, d plus) per group
+    double* red = pp + Cf::lps_doubles(tlos);     // [los in tile][NL + 1][j]   (aliases the eigen exchange area)
     double* projs = red;                          // [lo][i]
     double* Xs = projs + NSTR * N;                // [a][i]
     double* Xms = Xs + N * N;                     // [a][i]
@@ -155,7 +159,8 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
     const int nl = NSTR - m;
     const double f0 = (m == 0 ? 1.0 : 2.0) * (1.0 / (4.0 * kPi));
 
-    // ---- prologue: LOS phase sums lps-+[q] (lane q) and their eps_g derivatives for every LOS -> shared memory
+    // ---- prologue: LOS phase sums lps-+[q] (lane q) and their eps_g derivatives for the first tile -> shared memory
+    const int nt0 = TILED ? (nlos < tlos ? nlos : tlos) : nlos;
     {
         double ob[NSTR], tq[NSTR], obd[G > 0 ? G : 1][NSTR];
 #pragma unroll
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
 #pragma unroll
             for (int g = 0; g < G; ++g) obd[g][lo] = in ? ssa * dbeta[g * NSTR + l] : 0.0;
         }
-        for (int los = 0; los < nlos; ++los) {
+        for (int los = 0; los < nt0; ++los) {
             const double* __restrict__ tl = tL + los * NSTR + m;
             // even and odd (l - m) accumulated separately: two independent DFMA chains per sum, and
             // lps_minus = even + odd, lps_plus = even - odd without the sign flips
@@ -328,34 +333,35 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         }
     }
     __syncwarp();  // the exchange area is reused by the LOS reduction below
-    // Stage the adjoint solution slices of every LOS (the 4N entries of z on the layer's two boundaries) into the
-    // head of that LOS's reduction row with cp.async: the HBM latency overlaps pass 3 and the scalar set-up instead of
+    // Stage the adjoint solution slices of a tile's LOS (the 4N entries of z on the layer's two boundaries) into the
+    // head of each LOS's reduction row with cp.async: the HBM latency overlaps pass 3 and the scalar set-up instead of
     // stalling every LOS iteration (2 warps per scheduler cannot hide it).  Layout per LOS: zt[2N] | zb[2N].
-    {
-        // zadj is [row][los] (LOS fastest): the rows of this layer's two boundaries x all LOS are one contiguous run,
-        // copied element by element (lane-contiguous 8-byte chunks) into the per-LOS rows of the reduction area
+    // zadj is [row][los] (LOS fastest): the rows of this layer's two boundaries x the tile's LOS are runs of nt
+    // contiguous elements (one run when the tile is all LOS), copied element by element (lane-contiguous 8-byte chunks)
+    const unsigned red0 = (unsigned)__cvta_generic_to_shared(red);
+    auto stage_z = [&](int los0, int nt) {
         const bool bottom_ = (p == L - 1);
         const int row0 = (p == 0) ? 0 : N + (p - 1) * 2 * N;
         const int nrows = ((p == 0) ? N : 2 * N) + (bottom_ ? N : 2 * N);
-        const double* zsrc = V.zadj + (((size_t)w * M + ms) * ((size_t)2 * N * L) + row0) * nlos;
-        const int total = nrows * nlos;
-        const int dq = N / nlos, dr = N - dq * nlos;  // e += N  <=>  (zi, zl) += (dq, dr) with one carry
-        int zi = j / nlos, zl = j - zi * nlos;        // element e = zi * nlos + zl
-        const unsigned red0 = (unsigned)__cvta_generic_to_shared(red);
-        const int toa_shift = (p == 0) ? N : 0;       // the TOA boundary has N rows: zb starts at 2N
+        const double* zsrc = V.zadj + (((size_t)w * M + ms) * ((size_t)2 * N * L) + row0) * nlos + los0;
+        const int total = nrows * nt;
+        const int dq = N / nt, dr = N - dq * nt;  // e += N  <=>  (zi, zl) += (dq, dr) with one carry
+        int zi = j / nt, zl = j - zi * nt;        // element e = zi * nt + zl
+        const int toa_shift = (p == 0) ? N : 0;   // the TOA boundary has N rows: zb starts at 2N
         for (int e = j; e < total; e += N) {
             const int off = (zi >= N) ? zi + toa_shift : zi;
             const unsigned d0 = red0 + 8u * (unsigned)(zl * (NL + 1) * N + off);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0), "l"(zsrc + e) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0), "l"(zsrc + (size_t)zi * nlos + zl) : "memory");
             zi += dq;
             zl += dr;
-            if (zl >= nlos) {
-                zl -= nlos;
+            if (zl >= nt) {
+                zl -= nt;
                 ++zi;
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-    }
+    };
+    stage_z(0, nt0);
 
     // ---- pass 3: Green's coefficients A+-_j with heavy-lane derivatives
     double ap, am, dap[NH], dam[NH];
@@ -498,7 +504,48 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         n_inv = ll[2];
         n_atop = V.los_att[((size_t)w * nlos + 0) * (L + 1) + p];
     }
-    for (int los = 0; los < nlos; ++los) {
+    int los0 = 0;
+    do {
+    const int nt = TILED ? (nlos - los0 < tlos ? nlos - los0 : tlos) : nlos;
+    if (TILED && los0 > 0) {
+        // later tiles: the previous tile's rows have been reduced; restage z and recompute the phase sums (the
+        // first tile's register tables are gone: the operands come back from shared memory / L1, same summation order)
+        __syncwarp();
+        stage_z(los0, nt);
+        for (int t = 0; t < nt; ++t) {
+            const double* __restrict__ tl = tL + (los0 + t) * NSTR + m;
+            double ae = 0.0, ao = 0.0, dae[G > 0 ? G : 1], dao[G > 0 ? G : 1];
+#pragma unroll
+            for (int g = 0; g < G; ++g) dae[g] = dao[g] = 0.0;
+#pragma unroll 2
+            for (int lo = 0; lo < nl; ++lo) {
+                const int l = m + lo;
+                const double x = tl[lo] * (0.5 * tW[l * N + j]);
+                const double obv = ssa * beta[l];
+                if (lo & 1) {
+                    ao = fma(obv, x, ao);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) dao[g] = fma(ssa * dbeta[g * NSTR + l], x, dao[g]);
+                } else {
+                    ae = fma(obv, x, ae);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) dae[g] = fma(ssa * dbeta[g * NSTR + l], x, dae[g]);
+                }
+            }
+            double* o = lpsS + (size_t)t * 2 * NH * N;
+            o[j] = ae + ao;
+            o[N + j] = ae - ao;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                o[(2 + 2 * g) * N + j] = dae[g] + dao[g];
+                o[(3 + 2 * g) * N + j] = dae[g] - dao[g];
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+    for (int tt = 0; tt < nt; ++tt) {
+        const int los = los0 + tt;
         const double mu = n_mu, att = n_att, E = n_E, inv_1mus = n_inv, att_top = n_atop;
         const double imu = div_fast(1.0, mu);
         {
@@ -511,7 +558,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
             n_atop = V.los_att[((size_t)w * nlos + ln) * (L + 1) + p];
         }
         // -- source part: Y+-_j and heavy-lane derivatives from the shared phase sums
-        const double* __restrict__ ls = lpsS + (size_t)los * 2 * NH * N;
+        const double* __restrict__ ls = lpsS + (size_t)tt * 2 * NH * N;
         double Yp = 0.0, Ym = 0.0, dYp[NH], dYm[NH];
         {
             // the "b" and "a" halves of every sum are separate DFMA chains (latency, not throughput, limits this
@@ -630,7 +677,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         for (int c = 0; c < NL; ++c) out[c] *= att_top;
 
         // -- adjoint part: zeta slices of z on the two boundaries of the layer
-        const double* zt = red + (size_t)los * (NL + 1) * N;  // staged above
+        const double* zt = red + (size_t)tt * (NL + 1) * N;  // staged above
         const double* zb = zt + 2 * N;
         double zg_sum = 0.0;
         if (bottom) {
@@ -680,7 +727,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
         for (int e = 0; e < NH; ++e) out[e < G ? e : iOm] += dadj[e];
         // -- partials of this solution -> reduction buffer (over the staged z of this LOS: everyone is done reading)
         __syncwarp();
-        double* r = red + (size_t)los * (NL + 1) * N;
+        double* r = red + (size_t)tt * (NL + 1) * N;
 #pragma unroll
         for (int c = 0; c < NL; ++c) r[c * N + j] = out[c];
         r[NL * N + j] = srcj * att_top;
@@ -695,7 +742,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
     __syncwarp();
     // ---- sum over the solutions j and store: rows (los, c) are dealt round-robin to the problem's lanes
     if (valid) {
-        const int nrows = nlos * (NL + 1);
+        const int nrows = nt * (NL + 1);
         for (int row = j; row < nrows; row += N) {
             const double* r = red + (size_t)row * N;
             double s;
@@ -713,7 +760,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) s += r[i];
             }
-            const int los = row / (NL + 1), c = row % (NL + 1);
+            const int los = los0 + row / (NL + 1), c = row % (NL + 1);
             const size_t o = (((size_t)w * M + ms) * nlos + los) * L + p;
             if (c < NL)
                 V.wf_loc[o * NL + c] = s;
@@ -721,6 +768,8 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V) {
                 V.wf_src[o] = s;
         }
     }
+    los0 += tlos;
+    } while (TILED && los0 < nlos);
 }
 
 }  // namespace disco

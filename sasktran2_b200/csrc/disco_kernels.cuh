@@ -48,7 +48,7 @@ void launch_layer_post_fast(const ChunkView& V, cudaStream_t s);
 bool bvp_multi_supported(int N, int nsza);
 void launch_bvp_multi(const ChunkView& V, cudaStream_t s);
 void launch_wf_layer_fast(const ChunkView& V, cudaStream_t s);
-size_t wf_layer_fast_smem_bytes(int N, int G, int nlos);
+int wf_layer_fast_tile(int N, int G, int nlos);   // lines of sight per tile of k_wf_layer_fast, 0: not applicable
 void launch_bvp(const ChunkView& V, cudaStream_t s);
 void launch_bvp_adjoint(const ChunkView& V, cudaStream_t s);
 struct MappingView;

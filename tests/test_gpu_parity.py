@@ -194,7 +194,11 @@ def _subsample(full, pick):
                                                              (2, 1, 1, 7, 8), (4, 1, 1, 11, 8), (8, 1, 0, 12, 8),
                                                              # transposed solves: more LOS than lanes of a warp (two
                                                              # batches, the last one partly filled), a single layer
-                                                             (4, 1, 1, 37, 5), (8, 1, 1, 5, 1), (2, 1, 0, 33, 1)])
+                                                             (4, 1, 1, 37, 5), (8, 1, 1, 5, 1), (2, 1, 0, 33, 1),
+                                                             # more LOS than one shared-memory tile of the layer
+                                                             # weighting-function kernel (tiles of 7: 4 tiles, the
+                                                             # last one short; 100 LOS: C4's count)
+                                                             (16, 1, 1, 24, 6), (8, 1, 0, 60, 5), (16, 1, 1, 100, 3)])
 def test_cuda_weighting_functions_vs_oracle(oracle_mod, nstr, interp, geotype, nlos, nlayers):
     import sasktran2_b200 as sk
     from sasktran2_b200 import scenarios
@@ -377,6 +381,16 @@ def _run_variant(env_overrides, tmp_path, tag, nlos=10):
     env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
     subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=root)
     return dict(np.load(out))
+
+
+def test_cuda_wf_los_tiles_bit_identical(tmp_path):
+    """k_wf_layer_fast in tiles of 3 lines of sight (SK_B200_WF_TILE=3: tiles 3+3+3+1 of the 10) against the untiled
+    instantiation: the tiles recompute the same sums in the same order, so every output is bit-identical."""
+    base = _run_variant({}, tmp_path, "untiled")
+    other = _run_variant({"SK_B200_WF_TILE": "3"}, tmp_path, "tiled3")
+    assert set(other) == set(base)
+    for k in base:
+        assert np.array_equal(other[k], base[k]), (k, float(np.abs(other[k] - base[k]).max()))
 
 
 def test_cuda_kernel_variants_agree(tmp_path):

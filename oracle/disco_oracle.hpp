@@ -608,6 +608,11 @@ struct WavelInputs {
     // surface BRDF: 0 Lambertian (albedo above), 1 snow (Kokhanovsky), 2 MODIS kernels; args [nargs] of this wavelength
     int brdf_kind = 0;
     const double* brdf_args = nullptr;
+    // thermal emission (config.emission_source == discrete_ordinates): emission_source at the grid points [nloc] of
+    // this wavelength (nullptr: no atmospheric emission) and the surface emission (Surface::emission, 0 by default;
+    // the reference adds it whatever the emission source is, sktran_do_rte.h:229-235)
+    const double* emission = nullptr;
+    double surface_emission = 0.0;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -676,6 +681,7 @@ struct LayerSolution {
     std::vector<T> k;              // [N] eigval
     std::vector<T> Wp, Wm;         // [N*N] column-major W(i + N*j): stream i, solution j
     std::vector<T> Ap, Am;         // [N]
+    std::vector<T> Ath;            // [N] thermal Green's coefficient (A+ = A- for the scalar thermal source), empty: none
     std::vector<T> Gpt, Gpb, Gmt, Gmb;  // [N]
     std::vector<T> Lc, Mc;         // [N] BVP coefficients
 };
@@ -687,6 +693,8 @@ struct Layers {
     std::vector<T> secant;            // [L]
     std::vector<T> trans;             // [L+1] beam transmittance at boundaries (incl. F0)
     std::vector<double> tot_ext, scat_ext, ssa_value;  // per-layer scalars used by the WF mapping
+    std::vector<double> b0, b1;       // [L] thermal source b0 exp(-b1 x) of the layer, empty: no thermal emission
+    double surface_emission = 0.0;
 };
 
 // Lane bookkeeping for T = Dual: lane index of (layer p, kind) in the reference's sorted order
@@ -729,6 +737,13 @@ struct Solver {
         Ly.scat_ext.assign(L, 0.0);
         Ly.ssa_value.assign(L, 0.0);
         double ceiling_depth = 0, floor_depth = 0;
+        Ly.b0.clear();
+        Ly.b1.clear();
+        Ly.surface_emission = in.surface_emission;
+        if (in.emission) {
+            Ly.b0.assign(L, 0.0);
+            Ly.b1.assign(L, 0.0);
+        }
         for (int p = 0; p < L; ++p) {
             double dh = P.ceil_h[p] - P.floor_h[p];
             double od = 0, ssa = 0;
@@ -757,6 +772,24 @@ struct Solver {
             ssa /= od;
             od *= dh;
             floor_depth += od;
+            if (in.emission) {
+                // thermal source S(x) = b0 exp(-b1 x): emission at the highest / lowest contributing grid point
+                // (sktran_do_layerarray.cpp:341-370, 459-470)
+                int min_q = -1, max_q = -1;
+                for (int q = 0; q < nloc; ++q)
+                    if (P.W[size_t(p) * nloc + q] > 0) {
+                        if (min_q < 0) min_q = q;
+                        max_q = q;
+                    }
+                double b0_top = max_q >= 0 ? in.emission[max_q] : 0.0;
+                double b0_bot = (min_q >= 0 && min_q != max_q) ? in.emission[min_q] : b0_top;
+                double b1 = 0.0;
+                if (od > 1e-10 && b0_top > 1e-30 && b0_bot > 1e-30 &&
+                    std::abs(b0_top - b0_bot) > 1e-15 * std::max(b0_top, b0_bot))
+                    b1 = std::log(b0_top / b0_bot) / od;
+                Ly.b0[p] = b0_top;
+                Ly.b1[p] = b1;
+            }
             double total_ext = od / dh;
             double scat_ext = total_ext * ssa;
             scat_ext = std::max(scat_ext, total_ext * SSA_DITHER);
@@ -958,6 +991,40 @@ struct Solver {
             }
         }
     }
+    // ---- thermal particular solution, order 0 only: solveParticularGreenThermal (sktran_do_rte.cpp:1335-1617), added on
+    //      top of the solar G+-.  Values only (the reference's derivative lanes of b0 / b1 are not restated).
+    void particular_thermal(const T& ssa, const T& od, double b0, double b1, LayerSolution<T>& S) const {
+        const int N = P.N;
+        S.Ath.assign(N, T(0.0));
+        const double tau = val(od), e_b1 = std::exp(-tau * b1);
+        for (int j = 0; j < N; ++j) {
+            T norm(0.0), a(0.0);
+            for (int i = 0; i < N; ++i) {
+                const T& wp = S.Wp[i + j * N];
+                const T& wm = S.Wm[i + j * N];
+                norm += T(P.wt[i] * P.mu[i]) * (wp * wp - wm * wm);
+                a += T(P.wt[i]) * (T(1.0) - ssa) * (wp + wm);
+            }
+            a = a / norm;
+            S.Ath[j] = a;
+            const double k = val(S.k[j]), e_k = std::exp(-tau * k);
+            double Cp, Cm;
+            if (std::abs(b1 - k) > GREENS_EPS)
+                Cp = b0 * (e_k - e_b1) / (b1 - k);
+            else
+                Cp = b0 * e_k * tau * (1 - tau / 2 * (b1 - k));
+            if (std::abs(b1 + k) > GREENS_EPS)
+                Cm = b0 * (1 - e_b1 * e_k) / (b1 + k);
+            else
+                Cm = b0 * tau * (1 - tau / 2 * (b1 + k));
+            for (int i = 0; i < N; ++i) {
+                S.Gpt[i] += a * T(Cm) * S.Wm[i + j * N];
+                S.Gmt[i] += a * T(Cm) * S.Wp[i + j * N];
+                S.Gpb[i] += a * T(Cp) * S.Wp[i + j * N];
+                S.Gmb[i] += a * T(Cp) * S.Wm[i + j * N];
+            }
+        }
+    }
     static bool is_zero(double x) { return x == 0.0; }
     template <class D>
     static bool is_zero(const D& x) {
@@ -1028,7 +1095,8 @@ struct Solver {
                     ent.push_back({r0 + i, c0 + N + j, vp});
                 }
                 T gds(0.0);
-                if (refl) gds = T(P.csz) * (gen ? T(surf->sun[i]) : albedo) / T(PI) * Ly.trans[L];
+                if (m == 0) gds = T(Ly.surface_emission);   // ground_direct_sun: thermal source, sktran_do_rte.h:229-235
+                if (refl) gds += T(P.csz) * (gen ? T(surf->sun[i]) : albedo) / T(PI) * Ly.trans[L];
                 T um = B.Gmb[i];
                 if (refl)
                     for (int q = 0; q < N; ++q) um -= T(kd) * rho(i, q) * T(P.wt[q] * P.mu[q]) * B.Gpb[q];
@@ -1156,6 +1224,13 @@ struct Solver {
         T e2s = exp(-od * s) * exp(-od / T(mu));
         T E = t / (T(1.0) + T(mu) * s) * (T(1.0) - e2s);
         T expfactor = exp(-od * s);
+        // E_thermal at x = 0 (sktran_do_opticallayer.cpp:941-957)
+        const bool thermal = (m == 0) && !Ly.b0.empty() && !S.Ath.empty();
+        T E_th(0.0);
+        if (thermal) {
+            const double b0 = Ly.b0[p], b1 = Ly.b1[p];
+            E_th = T(b0 / (1.0 + mu * b1)) * (T(1.0) - exp(-od * T(b1)) * exp(-od / T(mu)));
+        }
         T J(0.0), V(0.0);
         for (int i = 0; i < N; ++i) {
             T Yp(0.0), Ym(0.0);
@@ -1199,14 +1274,28 @@ struct Solver {
                              (T(1.0) + T(mu) * s)
                        : (t * hp - E) / (s - k);
             V += S.Ap[i] * Yp * Dm + S.Am[i] * Ym * Dp;
+            if (thermal) {
+                // thermal part of V (sktran_do_opticallayer.cpp:421-478); the reference has no series branch for
+                // b1 -> k_i here
+                const double b0 = Ly.b0[p], b1 = Ly.b1[p];
+                T e_b1 = exp(-od * T(b1));
+                T Dp_th = (-T(b0) * e_b1 * hm + E_th) / (T(b1) + k);
+                T Dm_th = (T(b0) * hp - E_th) / (T(b1) - k);
+                V += S.Ath[i] * Yp * Dm_th + S.Ath[i] * Ym * Dp_th;
+            }
         }
-        return J + V + Q * E;
+        T src = J + V + Q * E;
+        if (thermal) src += E_th * (T(1.0) - Ly.ssa[p]);   // :524-531
+        return src;
     }
     T los_component(int m, int j, const Layers<T>& Ly, const T& albedo, const std::vector<LayerSolution<T>>& sol,
                     bool include_ss) const {
         const int L = P.L;
         const double mu = P.los_mu[j];
         T I = ground_term(m, Ly.trans[L], Ly.od[L - 1], albedo, sol[L - 1], include_ss, nullptr, nullptr, j);
+        // surface emission leaves the ground unreflected; the reference adds it inside its direct-bounce branch
+        // (sktran_do_layerarray.cpp:225-266)
+        if (m == 0 && include_ss) I += T(Ly.surface_emission);
         for (int p = L - 1; p >= 0; --p) {
             I = I * exp(-Ly.od[p] / T(mu));
             I += layer_source(m, j, p, Ly, sol[p], include_ss);
@@ -1230,6 +1319,11 @@ struct Solver {
             for (int p = 0; p < L; ++p) {
                 homogeneous(m, Ly.ssa[p], Ly.beta[p], sol[p]);
                 particular(m, Ly.ssa[p], Ly.beta[p], Ly.od[p], Ly.secant[p], Ly.trans[p], sol[p]);
+                sol[p].Ath.clear();
+                if (in.emission && m == 0) {   // sktran_do_rte.cpp:154-156
+                    if (ndual(albedo) != 0) throw std::runtime_error("oracle: weighting functions with thermal emission are not restated");
+                    particular_thermal(Ly.ssa[p], Ly.od[p], Ly.b0[p], Ly.b1[p], sol[p]);
+                }
             }
             if (in.brdf_kind != 0) {   // Surface::calculate(m), sktran_do_surface.h:153-217
                 if (ndual(albedo) != 0) throw std::runtime_error("oracle: weighting functions with a non-Lambertian BRDF are not restated");

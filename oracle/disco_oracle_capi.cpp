@@ -51,6 +51,14 @@ void oracle_set_brdf(int kind, int nargs, const double* args) {
     g_brdf_nargs = nargs;
     g_brdf_args = args;
 }
+// thermal emission of the next oracle_do_radiance call (config.emission_source = discrete_ordinates): emission_source
+// [nloc, nwavel] column-major (nullptr: none) and the surface emission [nwavel] (nullptr: zero)
+static const double* g_emission = nullptr;
+static const double* g_surface_emission = nullptr;
+void oracle_set_emission(const double* emission, const double* surface_emission) {
+    g_emission = emission;
+    g_surface_emission = surface_emission;
+}
 // Fourier coefficient of a BRDF model (SurfaceStorage::compute_expansion) and the model itself, for the tests
 double oracle_brdf_expansion(int m, int kind, const double* args, double mu_out, double mu_in) {
     return oracle::compute_expansion(m, kind, args, mu_out, mu_in);
@@ -120,6 +128,10 @@ int oracle_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nlos, const
                     in.brdf_kind = g_brdf_kind;
                     in.brdf_args = g_brdf_args + size_t(g_brdf_nargs) * w;
                 }
+                if (g_emission) in.emission = g_emission + size_t(nloc) * w;
+                if (g_surface_emission) in.surface_emission = g_surface_emission[w];
+                if ((g_emission || g_surface_emission) && calc_derivs)
+                    throw std::runtime_error("oracle: weighting functions with thermal emission are not restated");
                 in.ngroups = G;
                 in.include_ss = include_ss != 0;
                 in.num_azimuth = num_azimuth > 0 ? num_azimuth : nstr;

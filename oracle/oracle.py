@@ -64,7 +64,7 @@ def _p(a):
 def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, los_cos_vza, los_rel_az,
                 ssa, ext, leg, solar=None, albedo, d_leg=None, include_ss=True, num_azimuth=0,
                 calc_derivs=False, nthreads=0, return_lanes=False, stable=False, f=None, d_f=None, reverse=False,
-                brdf_kind=0, brdf_args=None):
+                brdf_kind=0, brdf_args=None, emission=None, surface_emission=None):
     """Run the oracle.
 
     ssa, ext: [nloc, nwavel] (Fortran order is used internally, as the reference does);
@@ -74,6 +74,8 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
     apply_delta_m_scaling (below); the arrays passed in are then the SCALED ones.
     reverse=True computes the derivatives in reverse mode (config.do_backprop = true: layer-local duals, one transposed
     band solve per line of sight, RTESolver::backprop) instead of dense forward-mode duals; same results.
+    emission [nloc, nwavel] / surface_emission [nwavel]: thermal sources of config.emission_source = DiscreteOrdinates
+    (radiances only).
     stable=True switches the particular-solution multipliers from the reference's formulas to the
     singularity-free phi/psi forms (see disco_oracle.hpp, "stable multipliers"); default is the reference's.
     """
@@ -116,6 +118,12 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
         brdf_args = np.asfortranarray(brdf_args, dtype=np.float64)   # [nargs, nwavel]
         assert brdf_args.ndim == 2 and brdf_args.shape[1] == nwavel
         L.oracle_set_brdf(ctypes.c_int(int(brdf_kind)), ctypes.c_int(brdf_args.shape[0]), _p(brdf_args))
+    if emission is not None:
+        emission = np.asfortranarray(emission, dtype=np.float64)
+        assert emission.shape == (nloc, nwavel)
+    if surface_emission is not None:
+        surface_emission = np.ascontiguousarray(np.broadcast_to(surface_emission, (nwavel,)), dtype=np.float64)
+    L.oracle_set_emission(_p(emission), _p(surface_emission))
     rc = L.oracle_do_radiance(
         ctypes.c_int(nstr), ctypes.c_int(nloc), ctypes.c_int(nwavel), ctypes.c_int(nleg), ctypes.c_int(nlos),
         _p(alt), ctypes.c_int(interp), ctypes.c_int(geotype), ctypes.c_double(cos_sza), ctypes.c_double(earth_radius),
@@ -124,6 +132,7 @@ def do_radiance(*, nstr, alt, interp, geotype, cos_sza, earth_radius=6372000.0, 
         ctypes.c_int(nthreads), _DGEEV, _p(rad), _p(native), _p(lanes))
     L.oracle_set_delta_m(None, None)
     L.oracle_set_brdf(ctypes.c_int(0), ctypes.c_int(1), None)
+    L.oracle_set_emission(None, None)
     if rc != 0:
         raise RuntimeError(f"oracle failed ({rc}): {L.oracle_last_error().decode()}")
     out = {"radiance": rad}

@@ -5,7 +5,7 @@ Python host layer mirroring the reference's `sasktran2` package for this path:
 Everything numeric happens in libsasktran2_b200.so (hand-written CUDA for sm_100a behind the reference's
 `sk_*` C ABI, include/sasktran2_b200.h).  There is no CPU fallback.
 """
-from .enums import (GeometryType, InterpolationMethod, MultipleScatterSource, SingleScatterSource, ThreadingModel,
+from .enums import (EmissionSource, GeometryType, InterpolationMethod, MultipleScatterSource, SingleScatterSource, ThreadingModel,
                     WeightingFunctionPrecision)
 from ._lib import SasktranError, LibraryMissing
 from .config import Config

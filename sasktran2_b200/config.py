@@ -4,7 +4,7 @@ from __future__ import annotations
 import ctypes as C
 
 from . import _lib
-from .enums import MultipleScatterSource, SingleScatterSource, ThreadingModel, WeightingFunctionPrecision
+from .enums import EmissionSource, MultipleScatterSource, SingleScatterSource, ThreadingModel, WeightingFunctionPrecision
 
 
 def _int_prop(name, wrap=int, doc=None):
@@ -39,6 +39,7 @@ class Config:
     wavelength_batch_size = _int_prop("wavelength_batch_size")
     multiple_scatter_source = _int_prop("multiple_scatter_source", MultipleScatterSource)
     single_scatter_source = _int_prop("single_scatter_source", SingleScatterSource)
+    emission_source = _int_prop("emission_source", EmissionSource)
     threading_model = _int_prop("threading_model", ThreadingModel)
     num_forced_azimuth = _int_prop("num_do_forced_azimuth")
     do_backprop = _int_prop("do_backprop", bool)

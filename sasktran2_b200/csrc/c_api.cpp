@@ -63,7 +63,7 @@ using skapi::host_free;
 
 namespace {
 
-disco::AtmosphereArrays arrays_of(const Atmosphere* atm) {
+disco::AtmosphereArrays arrays_of(const Engine* e, const Atmosphere* atm) {
     disco::AtmosphereArrays a;
     const AtmosphereStorage* s = atm->storage;
     a.nloc = s->nloc;
@@ -82,6 +82,16 @@ disco::AtmosphereArrays arrays_of(const Atmosphere* atm) {
         a.brdf_args = sf->brdf_args;
         a.albedo = nullptr;
     }
+    // thermal sources.  emission_source = discrete_ordinates (2) puts the storage's emission_source array into the DO
+    // solve (sktran_do_layerarray.cpp:309-311); the surface emission enters the ground boundary whatever the emission
+    // source is (sktran_do_rte.h:229-235) - it is passed on only when some wavelength has a non-zero value
+    if (e->cfg.emission_source == 2) a.emission = s->emission;
+    if (sf->emission)
+        for (int w = 0; w < sf->nwavel; ++w)
+            if (sf->emission[w] != 0.0) {
+                a.surface_emission = sf->emission;
+                break;
+            }
     return a;
 }
 
@@ -101,6 +111,11 @@ int validate(const Engine* e, const Atmosphere* atm, const OutputC* out, bool ch
     if (atm->surface->brdf && atm->surface->brdf->kind != 0 && atm->calc_derivs && e->cfg.wf_enabled && check_output && out &&
         !(out->derivs.empty() && out->surface_derivs.empty()))
         return fail(-2, "B200 DO path: weighting functions with a non-Lambertian BRDF are not supported");
+    if (e->cfg.emission_source == 2 && !s->emission)
+        return fail(-1, "emission_source is DiscreteOrdinates but the atmosphere storage has no emission_source array");
+    if (e->cfg.emission_source == 2 && atm->calc_derivs && e->cfg.wf_enabled && check_output && out &&
+        !(out->derivs.empty() && out->surface_derivs.empty()))
+        return fail(-2, "B200 DO path: weighting functions with thermal emission are not supported");
     if (check_output) {
         if (!out || !out->radiance) return fail(-1, "output handle is null");
         if (out->nstokes != 1) return fail(-2, "output num_stokes must be 1");
@@ -169,7 +184,7 @@ int run_range(Engine* e, Atmosphere* atm, OutputC* out, int start, int count) {
         int rc = build_wf_request(e, atm, out, req);
         if (rc != 0) return rc;
         const int nlos = e->ncols();
-        e->dev->calculate(arrays_of(atm), start, count, out->radiance + (size_t)start * nlos, req.enabled() ? &req : nullptr);
+        e->dev->calculate(arrays_of(e, atm), start, count, out->radiance + (size_t)start * nlos, req.enabled() ? &req : nullptr);
         e->staged_start = start;
         e->staged_count = count;
         if (e->dev->limb() && e->cfg.output_los_optical_depth) {
@@ -820,8 +835,12 @@ Engine* sk_engine_create(Config* config, Geometry1D* geometry, ViewingGeometry* 
         fail(-2, "B200 DO path: single_scatter_source must be DiscreteOrdinates (2) or None (3)");
         return nullptr;
     }
-    if (config->emission_source != 1) {
-        fail(-2, "B200 DO path: emission sources are not supported");
+    if (config->emission_source != 1 && config->emission_source != 2) {
+        fail(-2, "B200 DO path: emission_source must be None (1) or DiscreteOrdinates (2)");
+        return nullptr;
+    }
+    if (config->emission_source == 2 && config->multiple_scatter_source == 2) {
+        fail(-2, "B200 two-stream path: emission sources are not supported");
         return nullptr;
     }
     if (config->solar_refraction) {
@@ -934,7 +953,7 @@ int sk_b200_engine_stage_atmosphere(Engine* e, Atmosphere* atm, OutputC* out, in
         disco::WfRequest req;
         rc = build_wf_request(e, atm, out, req);
         if (rc != 0) return rc;
-        e->dev->stage(arrays_of(atm), wavelength_start, wavelength_count, req.enabled() ? &req : nullptr);
+        e->dev->stage(arrays_of(e, atm), wavelength_start, wavelength_count, req.enabled() ? &req : nullptr);
         e->atmosphere = atm;
         e->staged_start = wavelength_start;
         e->staged_count = wavelength_count;

@@ -24,6 +24,8 @@ struct ChunkView {
     const double* leg;        // [nleg, nloc, nw]
     const double* albedo;     // [nw]
     const double* solar;      // [nw]
+    const double* emission;   // [nloc, nw] thermal emission source (emission_source = discrete_ordinates), null: none
+    const double* semis;      // [nw] surface emission, null: none
     int include_ss;
     int M;                    // azimuth orders actually solved
     const int* m_list;        // [M] azimuth order of each solved slot
@@ -36,6 +38,7 @@ struct ChunkView {
     double* lay_cumod;        // [nw][L+1] vertical optical depth above each boundary
     double* lay_totext;       // [nw][L]
     double* lay_scatext;      // [nw][L]
+    double* lay_thermal;      // [nw][L][2] thermal source b0 exp(-b1 x) of the layer: b0 | b1 (written when emission is set)
     // per (w, m, layer) solution
     double* Wp;               // [nw][M][L][N*N] row-major (stream, solution)
     double* Wm;
@@ -150,6 +153,25 @@ DISCO_HD void optics_body(const ChunkView& V, long long idx) {
     double ssa_l = sc / od;
     const double dh = V.layer_dh[p];
     od *= dh;
+    if (V.emission) {
+        // thermal source S(x) = b0 exp(-b1 x), x from the layer top: emission at the highest / lowest grid point that
+        // contributes to the layer (sktran_do_layerarray.cpp:341-370, 459-470)
+        const double* em = V.emission + (size_t)nloc * w;
+        int min_q = -1, max_q = -1;
+        for (int c = 0; c < 2; ++c) {
+            const int q = V.interp_idx[p * 2 + c];
+            if (q < 0 || !(V.interp_w[p * 2 + c] > 0.0)) continue;
+            if (min_q < 0 || q < min_q) min_q = q;
+            if (max_q < 0 || q > max_q) max_q = q;
+        }
+        const double b0_top = max_q >= 0 ? em[max_q] : 0.0;
+        const double b0_bot = (min_q >= 0 && min_q != max_q) ? em[min_q] : b0_top;
+        double b1 = 0.0;
+        if (od > 1e-10 && b0_top > 1e-30 && b0_bot > 1e-30 && fabs(b0_top - b0_bot) > 1e-15 * fmax(b0_top, b0_bot))
+            b1 = log(b0_top / b0_bot) / od;
+        V.lay_thermal[(size_t)idx * 2] = b0_top;
+        V.lay_thermal[(size_t)idx * 2 + 1] = b1;
+    }
     const double total_ext = od / dh;
     double scat_ext = total_ext * ssa_l;
     scat_ext = fmax(scat_ext, total_ext * kSsaDither);
@@ -208,6 +230,9 @@ DISCO_HD void layer_problem_body(const ChunkView& V, long long idx) {
     LayerSol<N> S;
     layer_solve<N>(V.T, m, od, ssa, beta, secant, trans_top, S);
     if (S.status) raise_status(V.status, (unsigned)S.status);
+    const bool thermal = V.emission && m == 0;   // thermal sources only enter order 0 (sktran_do_rte.cpp:1337-1340)
+    const double b0 = thermal ? V.lay_thermal[wl * 2] : 0.0, b1 = thermal ? V.lay_thermal[wl * 2 + 1] : 0.0;
+    if (thermal) thermal_particular<N>(V.T, od, ssa, b0, b1, S);
 
     double* Wp = V.Wp + (size_t)idx * N * N;
     double* Wm = V.Wm + (size_t)idx * N * N;
@@ -252,7 +277,7 @@ DISCO_HD void layer_problem_body(const ChunkView& V, long long idx) {
     const double trans_floor = V.lay_trans[(size_t)w * (L + 1) + L];
     for (int los = 0; los < nlos; ++los) {
         double cpos[N], cneg[N], v;
-        los_layer_terms<N>(V.T, m, los, od, ssa, beta, secant, trans_top, V.include_ss != 0, S, cpos, cneg, v);
+        los_layer_terms<N>(V.T, m, los, od, ssa, beta, secant, trans_top, V.include_ss != 0, S, cpos, cneg, v, thermal, b0, b1);
         const double mu = V.T.los_mu[los];
         const double att = exp(-cum_top / mu);
         const size_t o = (((size_t)w * M + ms) * nlos + los) * L + p;
@@ -268,6 +293,9 @@ DISCO_HD void layer_problem_body(const ChunkView& V, long long idx) {
             }
             double direct = V.include_ss ? V.T.csz / kPi * trans_floor : 0.0;
             vv += attg * (direct + 2.0 * sG);
+            // surface emission leaves the ground unreflected, inside the reference's direct-bounce branch
+            // (sktran_do_layerarray.cpp:225-266)
+            if (V.semis && V.include_ss) vv += exp(-cum_all / mu) * V.semis[w];
         } else {
             for (int j = 0; j < N; ++j) {
                 wv[j] = cpos[j] * att;

@@ -107,6 +107,7 @@ struct ForwardRows {
                 rhs += V.T.csz * V.albedo[w] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
             }
             if (gs) rhs += gs[2 * N * N + i] + V.T.csz * gs[2 * N * N + N + i] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
+            if (refl && V.semis) rhs += V.semis[w];   // surface emission (ground_direct_sun, sktran_do_rte.h:229-235)
             a[4 * N] = rhs;
         }
     }
@@ -181,6 +182,7 @@ struct ForwardRows {
                 rhs += V.T.csz * V.albedo[w] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
             }
             if (gs) rhs += gs[2 * N * N + i] + V.T.csz * gs[2 * N * N + N + i] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
+            if (refl && V.semis) rhs += V.semis[w];   // surface emission (ground_direct_sun, sktran_do_rte.h:229-235)
             a[4 * N] = rhs;
         }
     }
@@ -289,6 +291,7 @@ struct ForwardRows {
             const double* gs = V.gsurf + ((size_t)w * V.M + ms) * V.gsurf_stride;
             rhs += gs[2 * N * N + i] + V.T.csz * gs[2 * N * N + N + i] / kPi * V.lay_trans[(size_t)w * (L + 1) + L];
         }
+        if (m == 0 && V.semis) rhs += V.semis[w];
         return rhs;
     }
     // lines of layer step+1 (the lower layer of interface step+1), one 128-byte line per lane

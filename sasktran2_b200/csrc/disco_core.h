@@ -75,6 +75,7 @@ struct LayerSol {
     double Wp[N * N];     // row-major W+(i,j): stream i, solution j
     double Wm[N * N];
     double Ap[N], Am[N];  // Green's function coefficients
+    double Ath[N];        // thermal Green's coefficient (A+ = A-), only set by thermal_particular
     double Gpt[N], Gmt[N], Gpb[N], Gmb[N];
     int status;           // 0 ok, 1 Cholesky failed, 2 non-positive eigenvalue
 };
@@ -257,13 +258,48 @@ DISCO_HD void layer_solve(const Tables& T, int m, double od, double ssa, const d
     }
 }
 
+// Thermal source S(x) = b0 exp(-b1 x) of a layer (order 0 only): Green's function particular solution added on top of
+// the solar one (RTESolver::solveParticularGreenThermal, sktran_do_rte.cpp:1335-1617).  The source is isotropic, so
+// Q+- = w_i (1 - ssa) and A+ = A-.
+template <int N>
+DISCO_HD void thermal_particular(const Tables& T, double od, double ssa, double b0, double b1, LayerSol<N>& S) {
+    const double e_b1 = exp(-od * b1);
+    for (int j = 0; j < N; ++j) {
+        double norm = 0.0, a = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const double wp = S.Wp[i * N + j], wm = S.Wm[i * N + j];
+            norm += T.wt[i] * T.mu[i] * (wp * wp - wm * wm);
+            a += T.wt[i] * (1.0 - ssa) * (wp + wm);
+        }
+        a /= norm;
+        S.Ath[j] = a;
+        const double kj = S.k[j], e_k = S.theta[j];
+        double Cp, Cm;
+        if (fabs(b1 - kj) > kGreensEps)
+            Cp = b0 * (e_k - e_b1) / (b1 - kj);
+        else
+            Cp = b0 * e_k * od * (1.0 - od / 2.0 * (b1 - kj));
+        if (fabs(b1 + kj) > kGreensEps)
+            Cm = b0 * (1.0 - e_b1 * e_k) / (b1 + kj);
+        else
+            Cm = b0 * od * (1.0 - od / 2.0 * (b1 + kj));
+        const double amc = a * Cm, apc = a * Cp;
+        for (int i = 0; i < N; ++i) {
+            S.Gpt[i] += amc * S.Wm[i * N + j];
+            S.Gmt[i] += amc * S.Wp[i * N + j];
+            S.Gpb[i] += apc * S.Wp[i * N + j];
+            S.Gmb[i] += apc * S.Wm[i * N + j];
+        }
+    }
+}
+
 // Source-function multipliers of one layer toward one line of sight (observer above the atmosphere):
 //   source = sum_j cpos[j] L_j + cneg[j] M_j + v
 // i.e. cpos = Y+ h+, cneg = Y- h-, v = V + Q E  (sktran_do_opticallayer.cpp:284-321, 384-393, 513).
 template <int N>
 DISCO_HD void los_layer_terms(const Tables& T, int m, int los, double od, double ssa, const double* beta,
                               double secant, double trans_top, bool include_ss, const LayerSol<N>& S, double* cpos,
-                              double* cneg, double& v) {
+                              double* cneg, double& v, bool thermal = false, double b0 = 0.0, double b1 = 0.0) {
     constexpr int NSTR = 2 * N;
     const double mu = T.los_mu[los];
     const double* lp = T.lp_mu + (size_t)m * N * NSTR;
@@ -292,6 +328,9 @@ DISCO_HD void los_layer_terms(const Tables& T, int m, int los, double od, double
     double att = exp(-od / mu);
     double expfactor = exp(-od * secant);
     double E = trans_top / (1.0 + mu * secant) * (1.0 - expfactor * att);
+    // thermal source (order 0): E_thermal at x = 0 (sktran_do_opticallayer.cpp:941-957)
+    const double e_b1 = thermal ? exp(-od * b1) : 0.0;
+    const double E_th = thermal ? b0 / (1.0 + mu * b1) * (1.0 - e_b1 * att) : 0.0;
     double V = 0.0;
     for (int j = 0; j < N; ++j) {
         double Yp = 0.0, Ym = 0.0;
@@ -321,8 +360,14 @@ DISCO_HD void los_layer_terms(const Tables& T, int m, int los, double od, double
         double Dp = (-trans_top * expfactor * hm + E) / (secant + k);
         double Dm = trans_top * (mu * hp - od * att * psi_value(od, k, secant, S.theta[j], expfactor)) / (1.0 + mu * secant);
         V += S.Ap[j] * Yp * Dm + S.Am[j] * Ym * Dp;
+        if (thermal) {  // sktran_do_opticallayer.cpp:421-478 (the reference has no series branch for b1 -> k here)
+            const double Dp_th = (-b0 * e_b1 * hm + E_th) / (b1 + k);
+            const double Dm_th = (b0 * hp - E_th) / (b1 - k);
+            V += S.Ath[j] * (Yp * Dm_th + Ym * Dp_th);
+        }
     }
     v = V + Q * E;
+    if (thermal) v += E_th * (1.0 - ssa);  // :524-531
 }
 
 }  // namespace disco

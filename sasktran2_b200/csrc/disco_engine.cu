@@ -235,6 +235,10 @@ void DeviceEngine::free_inputs() {
         if (p) cudaFree(p);
     d_ext = d_ssa = d_leg = d_solar = d_albedo = d_radiance = nullptr;
     m_cap_nw = m_cap_nleg = 0;
+    if (d_emission) cudaFree(d_emission);
+    if (d_semis) cudaFree(d_semis);
+    d_emission = d_semis = nullptr;
+    m_cap_emission = m_cap_semis = 0;
     if (d_fdm) cudaFree(d_fdm);
     d_fdm = nullptr;
     m_cap_fdm = 0;
@@ -331,6 +335,7 @@ void DeviceEngine::ensure_workspace(int chunk) {
     V.lay_cumod = A("lay_cumod", c * (L + 1));
     V.lay_totext = A("lay_totext", c * L);
     V.lay_scatext = A("lay_scatext", c * L);
+    V.lay_thermal = A("lay_thermal", c * L * 2);
     V.Wp = A("Wp", c * M * L * N * N);
     V.Wm = A("Wm", c * M * L * N * N);
     V.kth = A("kth", c * M * L * 2 * N);
@@ -445,6 +450,30 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
         h2d(d_leg, atm.leg + (size_t)atm.nleg * nloc * w0, (size_t)atm.nleg * nloc);
         h2d(d_solar, atm.solar + w0, 1);
         if (atm.albedo && atm.brdf_kind == 0) h2d(d_albedo, atm.albedo + w0, 1);
+    }
+    // thermal sources (radiances only; the reference's emission derivative lanes are not implemented)
+    m_emission_on = atm.emission != nullptr && nw > 0;
+    m_semis_on = atm.surface_emission != nullptr && nw > 0;
+    if (m_emission_on || m_semis_on) {
+        if (m_is_limb) throw std::runtime_error("B200 limb path: emission sources are not supported");
+        if (twostream_direct()) throw std::runtime_error("B200 two-stream kernel: emission sources are not supported");
+        if (wf && wf->enabled()) throw std::runtime_error("B200 DO path: weighting functions with thermal emission are not supported");
+    }
+    if (m_emission_on) {
+        if (nw > m_cap_emission) {
+            if (d_emission) cudaFree(d_emission);
+            d_emission = dalloc<double>(nloc * nw);
+            m_cap_emission = nw;
+        }
+        h2d(d_emission, atm.emission + nloc * w0, nloc);
+    }
+    if (m_semis_on) {
+        if (nw > m_cap_semis) {
+            if (d_semis) cudaFree(d_semis);
+            d_semis = dalloc<double>(nw);
+            m_cap_semis = nw;
+        }
+        h2d(d_semis, atm.surface_emission + w0, 1);
     }
     // kernel-based surface: Fourier coefficients of the kernels (once per engine and model), arguments of the range
     m_brdf_kind = atm.brdf_kind;
@@ -652,6 +681,8 @@ void DeviceEngine::solve_staged() {
         V.leg = d_leg + (size_t)m_nleg * nloc * w0;
         V.albedo = (m_brdf_kind != 0) ? d_zero_albedo + w0 : d_albedo + w0;
         V.solar = d_solar + w0;
+        V.emission = m_emission_on ? d_emission + nloc * w0 : nullptr;
+        V.semis = m_semis_on ? d_semis + w0 : nullptr;
         V.radiance = d_radiance + (size_t)w0 * m_nrad;
         V.dleg = d_dleg ? d_dleg + (size_t)m_nleg * nloc * w0 : nullptr;
         V.dleg_gstride = (size_t)m_nleg * nloc * m_nw;

@@ -36,6 +36,10 @@ struct AtmosphereArrays {
     // surface BRDF (cpp/include/c_api/brdf.h): 0 Lambertian (`albedo`), 2 MODIS with brdf_args [3, nwavel] column-major
     int brdf_kind = 0, brdf_nargs = 1;
     const double* brdf_args = nullptr;
+    // thermal emission solved by the discrete-ordinates path (config.emission_source = discrete_ordinates):
+    // emission_source at the grid points [nloc, nwavel] (null: none) and the surface emission [nwavel] (null: none)
+    const double* emission = nullptr;
+    const double* surface_emission = nullptr;
 };
 
 // Weighting-function request: which derivative mappings to evaluate and where the results go
@@ -145,6 +149,9 @@ class DeviceEngine {
     // staged inputs
     int m_nw = 0, m_nleg = 0, m_cap_nw = 0, m_cap_nleg = 0;
     double *d_ext = nullptr, *d_ssa = nullptr, *d_leg = nullptr, *d_solar = nullptr, *d_albedo = nullptr;
+    double *d_emission = nullptr, *d_semis = nullptr;   // thermal sources of the staged range (allocated on first use)
+    int m_cap_emission = 0, m_cap_semis = 0;
+    bool m_emission_on = false, m_semis_on = false;
     double* d_radiance = nullptr;
     unsigned int* d_status = nullptr;
     // weighting functions

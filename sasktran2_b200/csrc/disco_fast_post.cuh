@@ -192,7 +192,32 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
         Cm = trans_top * div_fast(1.0 - exp_sec * thj, secant + kj);
     else
         Cm = trans_top * od * (1.0 - od / 2.0 * (secant + kj));
-    const double amc = am * Cm, apc = ap * Cp;
+    double amc = am * Cm, apc = ap * Cp;
+    // thermal source S(x) = b0 exp(-b1 x) of the layer, order 0 only (solveParticularGreenThermal,
+    // sktran_do_rte.cpp:1335-1617): isotropic, so A+ = A- = (1 - ssa) sum_i w_i (W+_ij + W-_ij) / norm_j; its
+    // A C products join the solar ones in G+-
+    const bool thermal = (V.emission != nullptr) && (m == 0);   // uniform over the block
+    double ath = 0.0, b0 = 0.0, b1 = 0.0, e_b1 = 0.0;
+    if (thermal) {
+        b0 = V.lay_thermal[(size_t)q * 2];
+        b1 = V.lay_thermal[(size_t)q * 2 + 1];
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) a = fma(V.T.wt[i], wp[i] + wm[i], a);
+        ath = (1.0 - ssa) * a / norm;
+        e_b1 = exp(-od * b1);
+        double Cpt, Cmt;
+        if (fabs(b1 - kj) > kGreensEps)
+            Cpt = b0 * (thj - e_b1) / (b1 - kj);
+        else
+            Cpt = b0 * thj * od * (1.0 - od / 2.0 * (b1 - kj));
+        if (fabs(b1 + kj) > kGreensEps)
+            Cmt = b0 * (1.0 - e_b1 * thj) / (b1 + kj);
+        else
+            Cmt = b0 * od * (1.0 - od / 2.0 * (b1 + kj));
+        amc = fma(ath, Cmt, amc);
+        apc = fma(ath, Cpt, apc);
+    }
     xch[pib * 2 * N + j] = amc;
     xch[pib * 2 * N + N + j] = apc;
     __syncwarp();
@@ -303,6 +328,15 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
         // this lane's share of the particular + single-scatter term (summed over j by k_radiance)
         double v = ap * Yp * Dm + am * Ym * Dp;
         if (V.include_ss) v = fma(f0 * E, fma(c_ss0, tl[2 * j], c_ss1 * tl[2 * j + 1]), v);
+        if (thermal) {
+            // thermal part of V and the unscattered emission E_thermal (1 - ssa) (sktran_do_opticallayer.cpp:421-478,
+            // 524-531, 941-957; x = 0); the latter once per problem
+            const double E_th = b0 / (1.0 + mu * b1) * (1.0 - e_b1 * att);
+            const double Dp_th = (E_th - b0 * e_b1 * hm) / (b1 + kj);
+            const double Dm_th = (b0 * hp - E_th) / (b1 - kj);
+            v = fma(ath, fma(Yp, Dm_th, Ym * Dp_th), v);
+            if (j == 0) v = fma(E_th, 1.0 - ssa, v);
+        }
         v *= att_top;
         if (ground) {
             // ground-leaving radiance toward the LOS (sktran_do_layerarray.cpp:5-288), attenuated by the column
@@ -310,6 +344,8 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
             cpos = fma(attg * 2.0 * spj, thj, cpos);
             cneg = fma(attg * 2.0, smj, cneg);
             if (j == 0) v += attg * ((V.include_ss ? V.T.csz / kPi * trans_floor : 0.0) + 2.0 * sG);
+            // surface emission: unreflected, inside the reference's direct-bounce branch (sktran_do_layerarray.cpp:225-266)
+            if (j == 0 && V.semis && V.include_ss) v += V.los_att[((size_t)w * nlos + los) * (L + 1) + L] * V.semis[w];
         }
         if (valid) {
             const size_t o = (((size_t)w * M + ms) * nlos + los) * L + p;

@@ -18,6 +18,14 @@ class SingleScatterSource(IntEnum):
     NoSource = 3
 
 
+class EmissionSource(IntEnum):
+    Standard = 0
+    NoSource = 1
+    DiscreteOrdinates = 2
+    VolumeEmissionRate = 3
+    TwoStream = 4
+
+
 class InterpolationMethod(IntEnum):
     ShellInterpolation = 0
     LinearInterpolation = 1

@@ -158,6 +158,14 @@ extern "C" long long emul_dump(const char* name, double* out, long long max_n) {
     return 0;
 }
 
+// thermal sources of the next emul_do_radiance call: emission_source [nloc, nwavel] and surface emission [nwavel]
+static const double* g_emission = nullptr;
+static const double* g_semis = nullptr;
+extern "C" void emul_set_emission(const double* emission, const double* surface_emission) {
+    g_emission = emission;
+    g_semis = surface_emission;
+}
+
 extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nlos, const double* alt, int interp,
                                 int geotype, double cos_sza, double earth_radius, const double* los_cos_vza,
                                 const double* los_rel_az, const double* ssa, const double* ext, const double* leg,
@@ -196,6 +204,7 @@ extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nl
         auto A = [&](size_t n) { store.emplace_back(n, 0.0); return store.back().data(); };
         V.lay_od = A(c * L); V.lay_ssa = A(c * L); V.lay_beta = A(c * L * nstr); V.lay_secant = A(c * L);
         V.lay_trans = A(c * (L + 1)); V.lay_cumod = A(c * (L + 1)); V.lay_totext = A(c * L); V.lay_scatext = A(c * L);
+        V.lay_thermal = A(c * L * 2); V.emission = g_emission; V.semis = g_semis;
         V.Wp = A(c * M * L * N * N); V.Wm = A(c * M * L * N * N); V.kth = A(c * M * L * 2 * N);
         V.G = A(c * M * L * 4 * N); V.surf = A(c * (2 * N + 1)); V.wvec = A(c * M * nlos * L * 2 * N);
         V.vsrc_w = 1;

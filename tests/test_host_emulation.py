@@ -30,7 +30,8 @@ def emul():
         return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
     def run(nstr, alt, interp, geotype, cos_sza, los_cos_vza, los_rel_az, ssa, ext, leg, albedo,
-            earth_radius=6372000.0, include_ss=True, solar=None, d_leg=None, want_native=False, **_):
+            earth_radius=6372000.0, include_ss=True, solar=None, d_leg=None, want_native=False, emission=None,
+            surface_emission=None, **_):
         alt = np.ascontiguousarray(alt, float)
         ssa = np.asfortranarray(ssa, float)
         ext = np.asfortranarray(ext, float)
@@ -48,10 +49,14 @@ def emul():
             dl = np.asfortranarray(d_leg, float)  # [nleg, nloc, nw, G]
             G = dl.shape[3]
         native = np.zeros((nw, cz.size, nloc * (2 + G) + 1)) if want_native else None
+        em = None if emission is None else np.asfortranarray(emission, float)
+        se = None if surface_emission is None else np.ascontiguousarray(np.broadcast_to(surface_emission, (nw,)), float)
+        lib.emul_set_emission(P(em) if em is not None else None, P(se) if se is not None else None)
         rc = lib.emul_do_radiance(nstr, nloc, nw, nleg, cz.size, P(alt), interp, geotype, ctypes.c_double(cos_sza),
                                   ctypes.c_double(earth_radius), P(cz), P(az), P(ssa), P(ext), P(leg), P(solar), P(alb),
                                   int(include_ss), P(rad), ctypes.byref(naz), P(dl) if dl is not None else None, G,
                                   P(native) if native is not None else None)
+        lib.emul_set_emission(None, None)
         if rc:
             raise RuntimeError(lib.emul_last_error().decode())
         if want_native:

@@ -41,12 +41,16 @@ static void launch_post_n(const ChunkView& V, cudaStream_t s) {
     const size_t smem = (size_t)post_smem_doubles<N>(V.T.nlos) * sizeof(double);
     static DeviceOnce attr_set;
     if (attr_set.first()) {
-        cudaFuncSetAttribute(k_layer_post<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_layer_post<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_layer_post<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
     const long long nblk_p = (nq + PostCfg<N>::PPB - 1) / PostCfg<N>::PPB;
     const long long cap_p = 2LL * wf_fast_blocks_per_order((int)V.M);  // persistent blocks, three resident per SM
     const dim3 grid_p((unsigned)(nblk_p < cap_p ? nblk_p : cap_p), (unsigned)V.M);
-    k_layer_post<N><<<grid_p, 128, smem, s>>>(V);
+    if (V.emission)
+        k_layer_post<N, true><<<grid_p, 128, smem, s>>>(V);
+    else
+        k_layer_post<N, false><<<grid_p, 128, smem, s>>>(V);
 }
 
 void launch_layer_eig_fast(const ChunkView& V, cudaStream_t s) {

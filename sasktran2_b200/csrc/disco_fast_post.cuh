@@ -89,7 +89,9 @@ __host__ __device__ constexpr int post_smem_doubles(int nlos) {
     return PostCfg<N>::NSTR * N + nlos * PostCfg<N>::NSTR + PostCfg<N>::NSTR + N + PostCfg<N>::PPB * 2 * N;
 }
 
-template <int N>
+// THERMAL: the instantiation with the thermal-emission terms (its extra live values cost the third resident block, so
+// the solar-only instantiation stays as it was)
+template <int N, bool THERMAL>
 __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
     using Cf = PostCfg<N>;
     constexpr int NSTR = Cf::NSTR;
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
     // thermal source S(x) = b0 exp(-b1 x) of the layer, order 0 only (solveParticularGreenThermal,
     // sktran_do_rte.cpp:1335-1617): isotropic, so A+ = A- = (1 - ssa) sum_i w_i (W+_ij + W-_ij) / norm_j; its
     // A C products join the solar ones in G+-
-    const bool thermal = (V.emission != nullptr) && (m == 0);   // uniform over the block
+    const bool thermal = THERMAL && (m == 0);   // uniform over the block
     double ath = 0.0, b0 = 0.0, b1 = 0.0, e_b1 = 0.0;
     if (thermal) {
         b0 = V.lay_thermal[(size_t)q * 2];

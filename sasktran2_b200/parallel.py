@@ -110,6 +110,13 @@ class SharedResult:
         barrier()
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name)
+            # Python < 3.13 registers attached segments with the resource tracker as if this process owned them and
+            # then warns about a "leak" (and tries a second unlink) at exit; rank 0 owns and unlinks the segment
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.arrays, off = {}, 0
         for k, s in shapes.items():
             self.arrays[k] = np.ndarray(s, dtype=np.float64, buffer=self.shm.buf, offset=off)

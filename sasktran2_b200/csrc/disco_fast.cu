@@ -29,7 +29,12 @@ static void launch_eig_n(const ChunkView& V, cudaStream_t s) {
     const long long nq = (long long)V.nw * V.T.L;
     const dim3 grid_t((unsigned)((nq + 127) / 128), (unsigned)V.M);
     k_eig_setup<N><<<grid_t, 128, 0, s>>>(V);
-    k_eig_jacobi<N><<<grid_t, 128, 0, s>>>(V);
+    // SK_B200_JACOBI=unrolled: the sweep as straight-line code (differential testing of the rolled rounds)
+    static const bool unrolled = [] { const char* e = std::getenv("SK_B200_JACOBI"); return e && e[0] == 'u'; }();
+    if (unrolled)
+        k_eig_jacobi<N, false><<<grid_t, 128, 0, s>>>(V);
+    else
+        k_eig_jacobi<N, true><<<grid_t, 128, 0, s>>>(V);
 }
 template <int N>
 static void launch_post_n(const ChunkView& V, cudaStream_t s) {

@@ -224,7 +224,34 @@ struct JacobiRounds<N, N - 1> {
     __device__ __forceinline__ static bool run(double (&)[N * (N + 1) / 2], double (&)[N * N]) { return false; }
 };
 
+// Relabelling between the rounds of a sweep: the circle tournament of round R + 1 is the one of round R with every
+// player but the last moved down by one, so permuting C (rows and columns) and the columns of Z by
+// pi(x) = x - 1 mod (N - 1), pi(N - 1) = N - 1 lets every round run the pairs of round 0.  All of C and Z is rewritten
+// by the round's rotations anyway: the permutation is a renaming of their results (register moves at most), and the loop
+// body is one round (a seventh of the 4 096 straight-line instructions whose instruction-cache misses were 2.2 of this
+// kernel's 5 stall cycles per issue).  After N - 1 rounds (one sweep) the labels are back where they started.
 template <int N>
+__device__ __forceinline__ void jacobi_relabel(double (&C)[N * (N + 1) / 2], double (&Z)[N * N]) {
+    constexpr int TS = N * (N + 1) / 2;
+    double Cn[TS], Zn[N * N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int pi = (i == N - 1) ? N - 1 : (i + N - 2) % (N - 1);
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const int pj = (j == N - 1) ? N - 1 : (j + N - 2) % (N - 1);
+            Cn[tri_idx(pi, pj)] = C[tri_idx(i, j)];
+        }
+#pragma unroll
+        for (int r = 0; r < N; ++r) Zn[r * N + pi] = Z[r * N + i];
+    }
+#pragma unroll
+    for (int e = 0; e < TS; ++e) C[e] = Cn[e];
+#pragma unroll
+    for (int e = 0; e < N * N; ++e) Z[e] = Zn[e];
+}
+
+template <int N, bool ROLLED>
 __global__ void __launch_bounds__(128) k_eig_jacobi(ChunkView V) {
     constexpr int TS = N * (N + 1) / 2;
     const int ms = blockIdx.y;
@@ -241,7 +268,16 @@ __global__ void __launch_bounds__(128) k_eig_jacobi(ChunkView V) {
     for (int e = 0; e < N * N; ++e) Z[e] = (e / N == e % N) ? 1.0 : 0.0;
     if (N > 1) {
         for (int sweep = 0; sweep < 40; ++sweep) {
-            const bool any = JacobiRounds<N, 0>::run(C, Z);
+            bool any = false;
+            if (ROLLED && N > 2) {
+#pragma unroll 1
+                for (int round = 0; round < N - 1; ++round) {
+                    any |= JacobiPairs<N, 0, 0>::run(C, Z);
+                    jacobi_relabel<N>(C, Z);
+                }
+            } else {
+                any = JacobiRounds<N, 0>::run(C, Z);
+            }
             if (!__any_sync(0xffffffffu, any)) break;
         }
     }

@@ -398,14 +398,14 @@ def test_cuda_kernel_variants_agree(tmp_path):
     default (register-resident layer kernels + row-per-lane staircase LU), SK_B200_GENERIC=1 (thread-per-problem
     layer and weighting-function kernels), SK_B200_BVP=3 (2D-distributed staircase LU), SK_B200_BVP=2 (column-by-column
     instead of blocked elimination), SK_B200_BVP_TMA=1 (rows of the blocked elimination from TMA-staged layer tiles) and
-    SK_B200_ADJOINT=refactor
+    SK_B200_ADJOINT=refactor, SK_B200_JACOBI=unrolled (the Jacobi sweep as straight-line code instead of one rolled round)
     (adjoint by a second factorisation of A^T instead of transposed solves with the forward factors).  Different summation
     orders and pivot tie-breaks, same mathematics: 1e-10 on radiances, 1e-8 of the column maximum on weighting
     functions (the amplified scatterer mapping: 1e-4, its noise floor, see _assert_wf)."""
     base = _run_variant({}, tmp_path, "default")
     for tag, env in (("generic", {"SK_B200_GENERIC": "1"}), ("bvp2d", {"SK_B200_BVP": "3"}),
                      ("bvp_columnwise", {"SK_B200_BVP": "2"}), ("adjoint_refactor", {"SK_B200_ADJOINT": "refactor"}),
-                     ("bvp_tma_rows", {"SK_B200_BVP_TMA": "1"})):
+                     ("bvp_tma_rows", {"SK_B200_BVP_TMA": "1"}), ("jacobi_unrolled", {"SK_B200_JACOBI": "unrolled"})):
         other = _run_variant(env, tmp_path, tag)
         assert set(other) == set(base)
         np.testing.assert_allclose(other["radiance"], base["radiance"], rtol=1e-10)

@@ -65,6 +65,9 @@ struct Tables {
     // per azimuth order, the shared-memory tables of k_wf_layer_fast in its own layout (null: other paths):
     // [m][ tW[nstr][N] | tM[nstr][N] | tL[nlos][nstr] | lpc[nstr] | wmu[N] ]
     const double* wf_tab;
+    // [m][nlos] 1: P_l^m(mu_los) = 0 for every l (m > 0 at exactly nadir) - order m gives this line of sight nothing,
+    // the register-resident layer kernels skip its multipliers and partials; null: not tabulated
+    const unsigned char* los_zero;
 };
 
 // Output of the per-layer solve, thread-local

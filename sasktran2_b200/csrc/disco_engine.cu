@@ -160,6 +160,24 @@ void DeviceEngine::init(const EngineOptions& opt) {
             for (int i = 0; i < N; ++i) wmu[i] = plan.wt[i] * plan.mu[i];
         }
         d_wf_tab = upload(tab);
+        // Tables::los_zero: orders that reach a line of sight with an identically zero Legendre table
+        if (nlos > 0) {
+            std::vector<unsigned char> lz((size_t)nstr * nlos, 0);
+            bool any = false;
+            for (int m = 0; m < nstr; ++m)
+                for (int los = 0; los < nlos; ++los) {
+                    bool zero = true;
+                    for (int l = 0; l < nstr && zero; ++l)
+                        if (plan.lp_los[((size_t)los * nstr + m) * nstr + l] != 0.0) zero = false;
+                    lz[(size_t)m * nlos + los] = zero ? 1 : 0;
+                    any = any || zero;
+                }
+            const char* skip = std::getenv("SK_B200_LOS_SKIP");   // =0: solve the zero orders too (timing / tests)
+            if (any && !(skip && skip[0] == '0')) {
+                CUDA_OK(cudaMalloc(&d_los_zero, lz.size()));
+                CUDA_OK(cudaMemcpy(d_los_zero, lz.data(), lz.size(), cudaMemcpyHostToDevice));
+            }
+        }
     }
     d_los_cosmphi = upload(plan.los_cosmphi);
     d_layer_dh = upload(plan.layer_dh);
@@ -218,6 +236,7 @@ DeviceEngine::~DeviceEngine() {
     for (void* p : {(void*)d_brdf_args, (void*)d_zero_albedo, (void*)d_brdf_Rss, (void*)d_brdf_rsun, (void*)d_brdf_Rls, (void*)d_brdf_rlsun,
                     (void*)d_snow_r0, (void*)d_snow_g, (void*)d_snow_cos, (void*)d_snow_w, (void*)d_snow_scale})
         if (p) cudaFree(p);
+    if (d_los_zero) cudaFree(d_los_zero);
     for (void* p : {(void*)d_mu, (void*)d_wt, (void*)d_lp_mu, (void*)d_lp_csz, (void*)d_lp_los, (void*)d_los_mu, (void*)d_wf_tab,
                     (void*)d_los_cosmphi, (void*)d_layer_dh, (void*)d_interp_w, (void*)d_interp_idx,
                     (void*)d_chapman, (void*)d_mlist, (void*)d_status})
@@ -634,6 +653,7 @@ void DeviceEngine::solve_staged() {
     V.T.lp_los = d_lp_los;
     V.T.los_mu = d_los_mu;
     V.T.wf_tab = d_wf_tab;
+    V.T.los_zero = d_los_zero;
     V.T.los_cosmphi = d_los_cosmphi;
     V.layer_dh = d_layer_dh;
     V.interp_idx = d_interp_idx;

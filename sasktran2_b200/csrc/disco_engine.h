@@ -149,6 +149,7 @@ class DeviceEngine {
     // staged inputs
     int m_nw = 0, m_nleg = 0, m_cap_nw = 0, m_cap_nleg = 0;
     double *d_ext = nullptr, *d_ssa = nullptr, *d_leg = nullptr, *d_solar = nullptr, *d_albedo = nullptr;
+    unsigned char* d_los_zero = nullptr;   // Tables::los_zero
     double *d_emission = nullptr, *d_semis = nullptr;   // thermal sources of the staged range (allocated on first use)
     int m_cap_emission = 0, m_cap_semis = 0;
     bool m_emission_on = false, m_semis_on = false;

@@ -297,6 +297,15 @@ __global__ void __launch_bounds__(128) k_layer_post(ChunkView V) {
             n_inv = lln[2];
             n_atop = V.los_att[((size_t)w * nlos + ln) * (L + 1) + p];
         }
+        if (V.T.los_zero && V.T.los_zero[m * nlos + los]) {   // order m gives this LOS nothing (uniform over the block)
+            if (valid) {
+                const size_t o = (((size_t)w * M + ms) * nlos + los) * L + p;
+                V.wvec[o * 2 * N + j] = 0.0;
+                V.wvec[o * 2 * N + N + j] = 0.0;
+                V.vsrc[o * N + j] = 0.0;
+            }
+            continue;
+        }
         const double imu = div_fast(1.0, mu);
         const double* __restrict__ tl = tL + los * NSTR + m;
         double Yp = 0.0, Ym = 0.0, Yp1 = 0.0, Ym1 = 0.0;  // two DFMA chains per sum (latency, not throughput, binds)

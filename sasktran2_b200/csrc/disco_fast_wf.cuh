@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
 
     // ---- pass 2: eigen-derivatives for the heavy lanes e = eps_0..eps_{G-1}, omega
     double dwp[NH][N], dwm[NH][N], dk[NH];
+    const double ikj = div_fast(1.0, kj);
     {
         double P[NH][N], dxm[NH][N];
 #pragma unroll
@@ -304,7 +305,6 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
                 Q[e][i] = P[e][i] * rden;
             }
         }
-        const double ikj = div_fast(1.0, kj);
 #pragma unroll
         for (int e = 0; e < NH; ++e) dk[e] *= 0.5 * ikj;
 #pragma unroll
@@ -342,22 +342,28 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
     auto stage_z = [&](int los0, int nt) {
         const bool bottom_ = (p == L - 1);
         const int row0 = (p == 0) ? 0 : N + (p - 1) * 2 * N;
-        const int nrows = ((p == 0) ? N : 2 * N) + (bottom_ ? N : 2 * N);
+        const int nrows = ((p == 0) ? N : 2 * N) + (bottom_ ? N : 2 * N);   // <= 4 N: at most four rows per lane
+        const int toa_shift = (p == 0) ? N : 0;       // the TOA boundary has N rows: zb starts at 2N
         const double* zsrc = V.zadj + (((size_t)w * M + ms) * ((size_t)2 * N * L) + row0) * nlos + los0;
-        const int total = nrows * nt;
-        const int dq = N / nt, dr = N - dq * nt;  // e += N  <=>  (zi, zl) += (dq, dr) with one carry
-        int zi = j / nt, zl = j - zi * nt;        // element e = zi * nt + zl
-        const int toa_shift = (p == 0) ? N : 0;   // the TOA boundary has N rows: zb starts at 2N
-        for (int e = j; e < total; e += N) {
-            const int off = (zi >= N) ? zi + toa_shift : zi;
-            const unsigned d0 = red0 + 8u * (unsigned)(zl * (NL + 1) * N + off);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0), "l"(zsrc + (size_t)zi * nlos + zl) : "memory");
-            zi += dq;
-            zl += dr;
-            if (zl >= nt) {
-                zl -= nt;
-                ++zi;
-            }
+        // lane j copies rows j, j + N, j + 2N, j + 3N of every LOS of the tile: the row bookkeeping is done once, the
+        // copies of one LOS are four cp.async with fixed offsets (the element-by-element walk over the contiguous
+        // run cost ~25 instructions per 8-byte copy)
+        unsigned doff[4];
+        const double* src[4];
+        bool ok[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int zi = j + r * N;
+            ok[r] = zi < nrows;
+            doff[r] = red0 + 8u * (unsigned)((zi >= N) ? zi + toa_shift : zi);
+            src[r] = zsrc + (size_t)zi * nlos;
+        }
+        for (int t = 0; t < nt; ++t) {
+            const unsigned d0 = 8u * (unsigned)(t * (NL + 1) * N);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (ok[r])
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(doff[r] + d0), "l"(src[r] + t) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -374,14 +380,12 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
             if (lo < nl) {
                 const int l = m + lo;
                 const double* __restrict__ t = tW + l * N;
-                double u = 0.0, v = 0.0, du[NH], dv[NH];
+                double du[NH], dv[NH];
 #pragma unroll
                 for (int e = 0; e < NH; ++e) du[e] = dv[e] = 0.0;
 #pragma unroll
                 for (int qq = 0; qq < N; ++qq) {
                     const double x = t[qq];
-                    u = fma(x, wp[qq], u);
-                    v = fma(x, wm[qq], v);
 #pragma unroll
                     for (int e = 0; e < NH; ++e) {
                         du[e] = fma(x, dwp[e][qq], du[e]);
@@ -390,8 +394,9 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
                 }
                 const double bl = beta[l], lc = lpc[l];
                 const double c = ssa * bl * lc;
-                const double s1 = (lo & 1) ? (u - v) : (u + v);   // u + s v
-                const double s2 = (lo & 1) ? (v - u) : (u + v);   // s u + v
+                // u +- v are pass 1's projections: pr[lo] = u + v (even l - m), k_j (u - v) (odd)
+                const double s1 = (lo & 1) ? pr[lo] * ikj : pr[lo];   // u + s v
+                const double s2 = (lo & 1) ? -s1 : s1;                // s u + v
                 apn = fma(c, s1, apn);
                 amn = fma(c, s2, amn);
 #pragma unroll
@@ -556,6 +561,13 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
             n_E = ll[1];
             n_inv = ll[2];
             n_atop = V.los_att[((size_t)w * nlos + ln) * (L + 1) + p];
+        }
+        if (V.T.los_zero && V.T.los_zero[m * nlos + los]) {
+            // nothing of order m reaches this line of sight (uniform over the block): zero partials, no multipliers
+            double* r = red + (size_t)tt * (NL + 1) * N;
+#pragma unroll
+            for (int c = 0; c <= NL; ++c) r[c * N + j] = 0.0;
+            continue;
         }
         // -- source part: Y+-_j and heavy-lane derivatives from the shared phase sums
         const double* __restrict__ ls = lpsS + (size_t)tt * 2 * NH * N;

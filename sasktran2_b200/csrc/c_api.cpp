@@ -843,6 +843,15 @@ Engine* sk_engine_create(Config* config, Geometry1D* geometry, ViewingGeometry* 
         fail(-2, "B200 two-stream path: emission sources are not supported");
         return nullptr;
     }
+    // Config::validate_config, cpp/lib/config/config.cpp:127-141
+    if (config->emission_source == 2 && config->single_scatter_source != 2) {
+        fail(-2, "emission_source=discrete_ordinates requires single_scatter_source=discrete_ordinates");
+        return nullptr;
+    }
+    if (config->emission_source == 2 && config->multiple_scatter_source != 0) {
+        fail(-2, "emission_source=discrete_ordinates requires multiple_scatter_source=discrete_ordinates");
+        return nullptr;
+    }
     if (config->solar_refraction) {
         fail(-2, "B200 DO path: solar refraction is not supported");
         return nullptr;

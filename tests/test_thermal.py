@@ -212,3 +212,19 @@ def test_cuda_refuses_weighting_functions_with_thermal_emission():
         atm = sk.Atmosphere.from_scenario(sc, geo, cfg, calculate_derivatives=True)
         atm.storage.emission_source[:] = em
         eng.calculate_radiance(atm)
+
+
+@pytest.mark.gpu
+def test_cuda_emission_do_requires_do_scattering_sources():
+    """Config::validate_config (cpp/lib/config/config.cpp:127-141; tests/input_validation/test_emission_validation.py)."""
+    sc = scenarios.small_wf_case(nstr=4, nlayers=5, nwavel=2, nlos=1)
+    geo = sk.Geometry1D(sc.cos_sza, 0.0, sc.earth_radius, sc.altitudes, sk.InterpolationMethod(sc.interp), sk.GeometryType(sc.geotype))
+    view = sk.ViewingGeometry()
+    view.add_ray(sk.GroundViewingSolar(sc.cos_sza, 0.0, 1.0, sc.observer_altitude))
+    cfg = sk.Config()
+    cfg.num_streams = 4
+    cfg.multiple_scatter_source = sk.MultipleScatterSource.DiscreteOrdinates
+    cfg.single_scatter_source = sk.SingleScatterSource.NoSource
+    cfg.emission_source = sk.EmissionSource.DiscreteOrdinates
+    with pytest.raises(sk.SasktranError, match="requires single_scatter_source"):
+        sk.Engine(cfg, geo, view)

@@ -1326,7 +1326,9 @@ struct Solver {
                 }
             }
             if (in.brdf_kind != 0) {   // Surface::calculate(m), sktran_do_surface.h:153-217
-                if (ndual(albedo) != 0) throw std::runtime_error("oracle: weighting functions with a non-Lambertian BRDF are not restated");
+                // The BRDF does not depend on the atmosphere: its Fourier coefficients enter the ground rows and the
+                // ground-leaving term as constants, and the forward-mode lanes of the atmosphere go through unchanged
+                // (the albedo lane is meaningless here - derivatives w.r.t. BRDF arguments are not restated).
                 const int N = P.N;
                 sx.general = true;
                 sx.ss.assign(size_t(N) * N, 0.0);

@@ -153,6 +153,8 @@ int oracle_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nlos, const
                     } else {
                         in.d_leg = nullptr;
                     }
+                    if (g_reverse && in.brdf_kind != 0)
+                        throw std::runtime_error("reverse-mode oracle: Lambertian surfaces only (use the forward-mode lanes)");
                     if (g_reverse) {
                         double* nat = native ? native + size_t(w) * nlos * nnative : nullptr;
                         double* lo = lanes_out ? lanes_out + size_t(w) * nlos * nd : nullptr;

@@ -109,8 +109,8 @@ int validate(const Engine* e, const Atmosphere* atm, const OutputC* out, bool ch
     if (atm->surface->brdf && atm->surface->brdf->kind != 0 && !atm->surface->brdf_args)
         return fail(-1, "surface BRDF arguments are null");
     if (atm->surface->brdf && atm->surface->brdf->kind != 0 && atm->calc_derivs && e->cfg.wf_enabled && check_output && out &&
-        !(out->derivs.empty() && out->surface_derivs.empty()))
-        return fail(-2, "B200 DO path: weighting functions with a non-Lambertian BRDF are not supported");
+        !out->surface_derivs.empty())
+        return fail(-2, "B200 DO path: weighting functions w.r.t. the arguments of a non-Lambertian BRDF are not supported");
     if (e->cfg.emission_source == 2 && !s->emission)
         return fail(-1, "emission_source is DiscreteOrdinates but the atmosphere storage has no emission_source array");
     if (e->cfg.emission_source == 2 && atm->calc_derivs && e->cfg.wf_enabled && check_output && out &&

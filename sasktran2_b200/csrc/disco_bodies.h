@@ -80,6 +80,10 @@ struct ChunkView {
     const double* gsurf;      // [nw][M][2N^2 + 2N]: SP[i][j] | SM[i][j] | SG[i] | rho_m(mu_i, mu_0)
     double* gsurf_out;        // the same array, writable (k_surface_general)
     int gsurf_stride;
+    // weighting functions above such a surface: [nw][M][N + nlos][N + 1] reflection rows of the streams and the LOS:
+    // (1 + delta_m0) w_q mu_q rho_m(row, mu_q) | rho_m(row, mu_0)   (null: radiances only)
+    double* gsurf_rows;
+    int wf_bottom_only;       // 1: k_wf_layer solves only the layer on the ground (k_wf_layer_fast leaves it out)
     // ---- several solar zenith angles sharing one homogeneous solution and one factorisation (spherical path): the
     //      arrays that depend on the SZA exist nsza times; slice s starts s * stride doubles after the pointers above
     int nsza;                 // 0 / 1: single SZA
@@ -303,6 +307,102 @@ DISCO_HD void layer_problem_body(const ChunkView& V, long long idx) {
             }
         }
         V.vsrc[o] = vv;
+    }
+}
+
+// Kernel-based (non-Lambertian) surface, device view of the tables of disco_brdf.h
+struct BrdfView {
+    int nk, nargs;
+    const double *Rss, *rsun, *Rls, *rlsun;
+    const double* args;   // [nargs][nw] of the chunk (k + nargs * w)
+    // snow model: per-wavelength coefficients pw[w][M][npairs] written by k_brdf_expand_snow from the sample tables
+    const double* pw;
+    double* pw_out;
+    int npairs, nsamples;
+    const double *snow_r0, *snow_g, *snow_cos, *snow_w, *snow_scale;
+};
+
+// K2s body: one (wavelength, azimuth slot, row): row t < N is stream t, row N + los a line of sight.  R = sum_k args_k
+// R^k_m(row, .) from the host tables (or the per-wavelength coefficients of the snow model), then the products with the
+// bottom layer's solution that the BVP ground rows need (stream rows) / the ground-leaving radiance toward the LOS
+// (sktran_do_rte.h:116-345, sktran_do_layerarray.cpp:5-288), and the rows themselves for the weighting functions.
+DISCO_HD void surface_general_body(const ChunkView& V, const BrdfView& B, int w, int ms, int t) {
+    const int N = V.T.N, M = V.M, L = V.T.L, nlos = V.T.nlos, nstr = V.T.nstr;
+    const int m = V.m_list[ms];
+    if (t >= N + nlos) return;
+    const size_t idxb = ((size_t)w * M + ms) * L + (L - 1);
+    const double* Wp = V.Wp + idxb * N * N;
+    const double* Wm = V.Wm + idxb * N * N;
+    const double* th = V.kth + idxb * 2 * N + N;
+    const double* Gpb = V.G + idxb * 4 * N + 2 * N;
+    const bool stream = t < N;
+    const int los = t - N;
+    double R[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) R[q] = 0.0;
+    double rsun = 0.0;
+    if (B.pw) {   // per-wavelength coefficients (snow model): pw[w][ms][pair]
+        const double* pw = B.pw + ((size_t)w * M + ms) * B.npairs;
+        const double* tab = stream ? pw + t * N : pw + N * N + N + los * N;
+        rsun = stream ? pw[N * N + t] : pw[N * N + N + nlos * N + los];
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if (q < N) R[q] = tab[q];
+    }
+    for (int k = 0; k < (B.pw ? 0 : B.nk); ++k) {
+        const double a = B.args[k + (size_t)B.nargs * w];
+        const double* tab = stream ? B.Rss + (((size_t)k * nstr + m) * N + t) * N
+                                                : B.Rls + (((size_t)k * nstr + m) * nlos + los) * N;
+        rsun += a * (stream ? B.rsun[((size_t)k * nstr + m) * N + t] : B.rlsun[((size_t)k * nstr + m) * nlos + los]);
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if (q < N) R[q] = fma(a, tab[q], R[q]);
+    }
+    double sg = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+        if (q < N) sg = fma(R[q], Gpb[q], sg);
+    const double t_floor = V.lay_trans[(size_t)w * (L + 1) + L];
+    if (stream) {
+        double* gs = V.gsurf_out + ((size_t)w * M + ms) * V.gsurf_stride;
+        for (int j = 0; j < N; ++j) {
+            double sp = 0.0, sm = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (q < N) {
+                    sp = fma(R[q], Wp[q * N + j], sp);
+                    sm = fma(R[q], Wm[q * N + j], sm);
+                }
+            gs[t * N + j] = sp;
+            gs[N * N + t * N + j] = sm;
+        }
+        gs[2 * N * N + t] = sg;
+        gs[2 * N * N + N + t] = rsun;
+    }
+    if (V.gsurf_rows) {   // reflection rows for the weighting-function kernels
+        double* row = V.gsurf_rows + (((size_t)w * M + ms) * (N + nlos) + t) * (N + 1);
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if (q < N) row[q] = R[q];
+        row[N] = rsun;
+    }
+    if (!stream) {
+        const size_t o = (((size_t)w * M + ms) * nlos + los) * L + (L - 1);
+        const double attg = exp(-V.lay_cumod[(size_t)w * (L + 1) + L] / V.T.los_mu[los]);
+        double* wv = V.wvec + o * 2 * N;
+        for (int j = 0; j < N; ++j) {
+            double lp = 0.0, lm = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (q < N) {
+                    lp = fma(R[q], Wp[q * N + j], lp);
+                    lm = fma(R[q], Wm[q * N + j], lm);
+                }
+            wv[j] += attg * lp * th[j];
+            wv[N + j] += attg * lm;
+        }
+        const double direct = V.include_ss ? V.T.csz / kPi * t_floor * rsun : 0.0;
+        V.vsrc[o * V.vsrc_w] += attg * (sg + direct);
     }
 }
 

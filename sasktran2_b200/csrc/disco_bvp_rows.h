@@ -413,12 +413,17 @@ struct AdjointRows {
             const bool refl = (m == 0);
             const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
             const double* surf = V.surf + (size_t)w * (2 * N + 1);
+            const double* gs = V.gsurf ? V.gsurf + ((size_t)w * V.M + ms) * V.gsurf_stride : nullptr;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 double vm = Wmb[i * N + j], vp = Wpb[i * N + j];
                 if (refl) {
                     vm -= alb2 * surf[j];
                     vp -= alb2 * surf[N + j];
+                }
+                if (gs) {   // kernel-based BRDF: every order reflects (rows of k_surface_general)
+                    vm -= gs[i * N + j];
+                    vp -= gs[N * N + i * N + j];
                 }
                 a[2 * N + i] = isL ? vm * th : vp;
             }
@@ -475,12 +480,17 @@ struct AdjointRows {
             const bool refl = (m == 0);
             const double alb2 = refl ? 2.0 * V.albedo[w] : 0.0;
             const double* surf = V.surf + (size_t)w * (2 * N + 1);
+            const double* gs = V.gsurf ? V.gsurf + ((size_t)w * V.M + ms) * V.gsurf_stride : nullptr;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 double vm = Wmb[i * N + j], vp = Wpb[i * N + j];
                 if (refl) {
                     vm -= alb2 * surf[j];
                     vp -= alb2 * surf[N + j];
+                }
+                if (gs) {
+                    vm -= gs[i * N + j];
+                    vp -= gs[N * N + i * N + j];
                 }
                 seg[i] = isL ? vm * th : vp;
             }

@@ -291,6 +291,7 @@ size_t DeviceEngine::ws_bytes(bool wf_on, int ngroups) const {
     if (m_fast) d += 3 * (N * (N + 1) / 2) * M * L + nlos * (L + 1) + nlos * L * 3;  // eigen planes, LOS exponentials
     d += M * L * 2 * N;                                             // x
     if (m_brdf_kind != 0) d += M * (2 * N * N + 2 * N);             // kernel-based surface sums
+    if (m_brdf_kind != 0 && wf_on) d += M * (N + nlos) * (N + 1);   // reflection rows for the weighting functions
     if (m_brdf_kind == kBrdfKokhanovsky) d += M * (N * N + N + nlos * N + nlos);   // per-wavelength Fourier coefficients
     if (m_is_limb) {
         const size_t nsza = m_limb.nsza, npts = m_limb.npts, nrays = m_limb.nrays;
@@ -376,6 +377,7 @@ void DeviceEngine::ensure_workspace(int chunk) {
     V.gsurf = V.gsurf_out = nullptr;
     V.gsurf_stride = (int)(2 * N * N + 2 * N);
     if (m_brdf_kind != 0) V.gsurf = V.gsurf_out = A("gsurf", c * M * V.gsurf_stride);
+    V.gsurf_rows = (m_brdf_kind != 0 && m_wf_on) ? A("gsurf_rows", c * M * (N + nlos) * (N + 1)) : nullptr;
     m_ws_brdf = m_brdf_kind != 0;
     m_ws_brdf_kind = m_brdf_kind;
     d_brdf_pw = nullptr;
@@ -498,7 +500,11 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
     m_brdf_kind = atm.brdf_kind;
     if (m_brdf_kind != 0 && nw > 0) {
         if (m_is_limb) throw std::runtime_error("B200 limb path supports the Lambertian BRDF only");
-        if (wf && wf->enabled()) throw std::runtime_error("B200 DO path: weighting functions with a non-Lambertian BRDF are not supported");
+        if (wf && wf->enabled()) {
+            // atmospheric weighting functions above a kernel-based BRDF are solved; those w.r.t. its arguments are not
+            if (!wf->surfaces.empty())
+                throw std::runtime_error("B200 DO path: weighting functions w.r.t. the arguments of a non-Lambertian BRDF are not supported");
+        }
         if (twostream_direct()) throw std::runtime_error("B200 two-stream kernel supports the Lambertian BRDF only");
         if (m_plan.N > 16) throw std::runtime_error("B200 DO path: kernel-based BRDFs need num_streams <= 32");
         if (m_brdf_tab_kind != m_brdf_kind) {
@@ -846,10 +852,21 @@ void DeviceEngine::solve_staged() {
         if (m_wf_on) {
             launch_bvp_adjoint(V, m_stream);
             mark(); slots.push_back(T_WF_ADJOINT);
-            if (m_fast && wf_layer_fast_tile(m_plan.N, m_ngroups, m_plan.nlos) > 0)
-                launch_wf_layer_fast(V, m_stream);
-            else
+            const bool general_brdf = m_brdf_kind != 0;
+            if (general_brdf) {   // the ground terms of every order are accumulated (k_wf_layer, kernel-based BRDF)
+                CUDA_OK(cudaMemsetAsync(V.wf_gnd, 0, sizeof(double) * (size_t)V.nw * m_plan.nlos * 3, m_stream));
+            }
+            if (m_fast && wf_layer_fast_tile(m_plan.N, m_ngroups, m_plan.nlos) > 0) {
+                ChunkView Vw = V;
+                Vw.wf_bottom_only = general_brdf ? 1 : 0;
+                launch_wf_layer_fast(Vw, m_stream);
+                if (general_brdf) {   // the layer on the ground: generic kernel with the reflection rows
+                    launch_wf_layer(Vw, m_stream);
+                    m_launches += 1;
+                }
+            } else {
                 launch_wf_layer(V, m_stream);
+            }
             mark(); slots.push_back(T_WF_LAYER);
             launch_wf_chain(V, m_stream);
             mark(); slots.push_back(T_WF_CHAIN);

@@ -148,9 +148,12 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
     // 20 % slower - the loop-carried state costs registers this kernel does not have
     long long q = (long long)blockIdx.x * Cf::PPB + pib;  // w * L + p
     const long long nq = (long long)V.nw * L;
-    const bool valid = q < nq;
+    bool valid = q < nq;
     if (!valid) q = nq - 1;
     const int w = (int)(q / L), p = (int)(q % L);
+    // above a kernel-based BRDF the layer on the ground is left to k_wf_layer (every order reflects there, with the
+    // reflection rows of k_surface_general): its lanes run along and store nothing
+    if (V.wf_bottom_only && p == L - 1) valid = false;
     const size_t idx = ((size_t)w * M + ms) * L + p;
     const double od = V.lay_od[q], ssa = V.lay_ssa[q], secant = V.lay_secant[q];
     const double trans_top = V.lay_trans[(size_t)w * (L + 1) + p];
@@ -167,10 +170,11 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
         for (int lo = 0; lo < NSTR; ++lo) {
             const bool in = lo < nl;
             const int l = in ? m + lo : m;
-            ob[lo] = in ? ssa * beta[l] : 0.0;
+            // the stream factor is folded into the moment factors once (one product less per moment and LOS below)
             tq[lo] = in ? 0.5 * tW[l * N + j] : 0.0;
+            ob[lo] = in ? ssa * beta[l] * tq[lo] : 0.0;
 #pragma unroll
-            for (int g = 0; g < G; ++g) obd[g][lo] = in ? ssa * dbeta[g * NSTR + l] : 0.0;
+            for (int g = 0; g < G; ++g) obd[g][lo] = in ? ssa * dbeta[g * NSTR + l] * tq[lo] : 0.0;
         }
         for (int los = 0; los < nt0; ++los) {
             const double* __restrict__ tl = tL + los * NSTR + m;
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const int lo = 4 * c + r;
-                        const double x = tl[lo] * tq[lo];
+                        const double x = tl[lo];
                         if (lo & 1) {
                             ao = fma(ob[lo], x, ao);
 #pragma unroll
@@ -525,16 +529,16 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
 #pragma unroll 2
             for (int lo = 0; lo < nl; ++lo) {
                 const int l = m + lo;
-                const double x = tl[lo] * (0.5 * tW[l * N + j]);
-                const double obv = ssa * beta[l];
+                const double x = tl[lo], tqv = 0.5 * tW[l * N + j];
+                const double obv = ssa * beta[l] * tqv;
                 if (lo & 1) {
                     ao = fma(obv, x, ao);
 #pragma unroll
-                    for (int g = 0; g < G; ++g) dao[g] = fma(ssa * dbeta[g * NSTR + l], x, dao[g]);
+                    for (int g = 0; g < G; ++g) dao[g] = fma(ssa * dbeta[g * NSTR + l] * tqv, x, dao[g]);
                 } else {
                     ae = fma(obv, x, ae);
 #pragma unroll
-                    for (int g = 0; g < G; ++g) dae[g] = fma(ssa * dbeta[g * NSTR + l], x, dae[g]);
+                    for (int g = 0; g < G; ++g) dae[g] = fma(ssa * dbeta[g * NSTR + l] * tqv, x, dae[g]);
                 }
             }
             double* o = lpsS + (size_t)t * 2 * NH * N;

@@ -183,77 +183,7 @@ __global__ void __launch_bounds__(128) k_brdf_expand_snow(ChunkView V, BrdfView 
 }
 
 __global__ void k_surface_general(ChunkView V, BrdfView B) {
-    const int N = V.T.N, M = V.M, L = V.T.L, nlos = V.T.nlos, nstr = V.T.nstr;
-    const int w = blockIdx.x / M, ms = blockIdx.x % M;
-    const int m = V.m_list[ms];
-    const int t = threadIdx.x;
-    if (t >= N + nlos) return;
-    const size_t idxb = ((size_t)w * M + ms) * L + (L - 1);
-    const double* __restrict__ Wp = V.Wp + idxb * N * N;
-    const double* __restrict__ Wm = V.Wm + idxb * N * N;
-    const double* __restrict__ th = V.kth + idxb * 2 * N + N;
-    const double* __restrict__ Gpb = V.G + idxb * 4 * N + 2 * N;
-    const bool stream = t < N;
-    const int los = t - N;
-    double R[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) R[q] = 0.0;
-    double rsun = 0.0;
-    if (B.pw) {   // per-wavelength coefficients (snow model): pw[w][ms][pair]
-        const double* __restrict__ pw = B.pw + ((size_t)w * M + ms) * B.npairs;
-        const double* __restrict__ tab = stream ? pw + t * N : pw + N * N + N + los * N;
-        rsun = stream ? pw[N * N + t] : pw[N * N + N + nlos * N + los];
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-            if (q < N) R[q] = tab[q];
-    }
-    for (int k = 0; k < (B.pw ? 0 : B.nk); ++k) {
-        const double a = B.args[k + (size_t)B.nargs * w];
-        const double* __restrict__ tab = stream ? B.Rss + (((size_t)k * nstr + m) * N + t) * N
-                                                : B.Rls + (((size_t)k * nstr + m) * nlos + los) * N;
-        rsun += a * (stream ? B.rsun[((size_t)k * nstr + m) * N + t] : B.rlsun[((size_t)k * nstr + m) * nlos + los]);
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-            if (q < N) R[q] = fma(a, tab[q], R[q]);
-    }
-    double sg = 0.0;
-#pragma unroll
-    for (int q = 0; q < 16; ++q)
-        if (q < N) sg = fma(R[q], Gpb[q], sg);
-    const double t_floor = V.lay_trans[(size_t)w * (L + 1) + L];
-    if (stream) {
-        double* __restrict__ gs = V.gsurf_out + ((size_t)w * M + ms) * V.gsurf_stride;
-        for (int j = 0; j < N; ++j) {
-            double sp = 0.0, sm = 0.0;
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-                if (q < N) {
-                    sp = fma(R[q], Wp[q * N + j], sp);
-                    sm = fma(R[q], Wm[q * N + j], sm);
-                }
-            gs[t * N + j] = sp;
-            gs[N * N + t * N + j] = sm;
-        }
-        gs[2 * N * N + t] = sg;
-        gs[2 * N * N + N + t] = rsun;
-    } else {
-        const size_t o = (((size_t)w * M + ms) * nlos + los) * L + (L - 1);
-        const double attg = exp(-V.lay_cumod[(size_t)w * (L + 1) + L] / V.T.los_mu[los]);
-        double* __restrict__ wv = V.wvec + o * 2 * N;
-        for (int j = 0; j < N; ++j) {
-            double lp = 0.0, lm = 0.0;
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-                if (q < N) {
-                    lp = fma(R[q], Wp[q * N + j], lp);
-                    lm = fma(R[q], Wm[q * N + j], lm);
-                }
-            wv[j] += attg * lp * th[j];
-            wv[N + j] += attg * lm;
-        }
-        const double direct = V.include_ss ? V.T.csz / kPi * t_floor * rsun : 0.0;
-        V.vsrc[o * V.vsrc_w] += attg * (sg + direct);
-    }
+    surface_general_body(V, B, blockIdx.x / V.M, blockIdx.x % V.M, threadIdx.x);
 }
 void launch_brdf_expand_snow(const ChunkView& V, const BrdfView& B, cudaStream_t s) {
     const long long n = (long long)V.nw * B.npairs;

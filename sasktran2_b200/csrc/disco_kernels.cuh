@@ -22,16 +22,6 @@ struct DeviceOnce {
 };
 
 // kernel-based BRDF (disco_brdf.h): device tables of the kernels' Fourier coefficients + this chunk's arguments
-struct BrdfView {
-    int nk, nargs;
-    const double *Rss, *rsun, *Rls, *rlsun;
-    const double* args;   // [nargs][nw] of the chunk (k + nargs * w)
-    // snow model: per-wavelength coefficients pw[w][M][npairs] written by k_brdf_expand_snow from the sample tables
-    const double* pw;
-    double* pw_out;
-    int npairs, nsamples;
-    const double *snow_r0, *snow_g, *snow_cos, *snow_w, *snow_scale;
-};
 void launch_surface_general(const ChunkView& V, const BrdfView& B, cudaStream_t s);
 void launch_brdf_expand_snow(const ChunkView& V, const BrdfView& B, cudaStream_t s);
 void launch_layer_optics(const ChunkView& V, cudaStream_t s);

@@ -399,7 +399,19 @@ DISCO_HD void wf_layer_body(const ChunkView& V, long long idx) {
         r4[i] = a4;
     }
     const bool bottom = (p == L - 1);
-    const bool refl = bottom && (m == 0);
+    // kernel-based BRDF (every order reflects): rows[(N + nlos)][N + 1] of this (wavelength, order) hold
+    // (1 + delta_m0) w_q mu_q rho_m(row, mu_q) | rho_m(row, mu_0) for the stream rows and the LOS rows (k_surface_general)
+    const bool general = bottom && V.gsurf_rows != nullptr;
+    const double* grow = general ? V.gsurf_rows + ((size_t)w * M + ms) * (size_t)(N + nlos) * (N + 1) : nullptr;
+    D Xg[N];   // downwelling field at the streams on the ground: G+bottom_q + sum_j (W+_qj Theta_j L_j + W-_qj M_j)
+    if (general) {
+        for (int q = 0; q < N; ++q) {
+            D acc = Gpb[q];
+            for (int j = 0; j < N; ++j) acc = acc + Wp[q * N + j] * theta[j] * Lc[j] + Wm[q * N + j] * Mc[j];
+            Xg[q] = acc;
+        }
+    }
+    const bool refl = bottom && (m == 0) && !general;
     const double albedo = V.albedo[w];
     D gsum(0.0);  // 2 sG + 2 sum_j (s+_j Theta_j L_j + s-_j M_j): the surface-reflected stream integral
     if (refl) {
@@ -436,6 +448,13 @@ DISCO_HD void wf_layer_body(const ChunkView& V, long long idx) {
                 zg_sum += zg[i * zs];
             }
             if (refl) adj = adj + gsum * (albedo * zg_sum);
+            if (general) {   // ground rows: - sum_q R(i, q) X_q on the left, + csz rho(i, sun) t_floor / pi on the right
+                for (int q = 0; q < N; ++q) {
+                    double c = 0.0;
+                    for (int i = 0; i < N; ++i) c += zg[i * zs] * grow[i * (N + 1) + q];
+                    adj = adj + Xg[q] * c;
+                }
+            }
         }
         const double mul = V.T.los_mu[los];
         const double att = exp(-cum_top / mul);
@@ -452,6 +471,30 @@ DISCO_HD void wf_layer_body(const ChunkView& V, long long idx) {
             gnd[0] = attg * (direct + gsum.v) + zg_sum * (V.T.csz * t_floor / kPi + gsum.v);  // d/d albedo
             gnd[1] = (V.include_ss ? attg * albedo * V.T.csz / kPi : 0.0) + zg_sum * V.T.csz * albedo / kPi;  // d/d t_floor
             gnd[2] = attg * albedo * (direct + gsum.v);                                        // ground term value
+        }
+        if (general) {
+            // ground-leaving radiance of this order toward the LOS and the pieces of the cross-layer chain, summed over
+            // the orders with their azimuth factors (wf_gnd is zeroed by the caller; one writer per (w, order, LOS))
+            const double attg = exp(-cum_all / mul);
+            const double* lrow = grow + (size_t)(N + los) * (N + 1);
+            D refl_los(0.0);
+            for (int q = 0; q < N; ++q) refl_los = refl_los + Xg[q] * lrow[q];
+            tot = tot + refl_los * attg;
+            const double cf = V.T.los_cosmphi[(size_t)los * V.T.nstr + m];
+            const double direct = V.include_ss ? V.T.csz / kPi * t_floor * lrow[N] : 0.0;
+            double zsun = 0.0;
+            const double* zg = z + (N + (size_t)(L - 1) * 2 * N) * zs;
+            for (int i = 0; i < N; ++i) zsun += zg[i * zs] * grow[i * (N + 1) + N];
+            double* gnd = V.wf_gnd + ((size_t)w * nlos + los) * 3;
+            const double g1 = cf * ((V.include_ss ? attg * lrow[N] * V.T.csz / kPi : 0.0) + zsun * V.T.csz / kPi);
+            const double g2 = cf * attg * (direct + refl_los.v);
+#if defined(__CUDA_ARCH__)
+            atomicAdd(gnd + 1, g1);
+            atomicAdd(gnd + 2, g2);
+#else
+            gnd[1] += g1;
+            gnd[2] += g2;
+#endif
         }
         double* out = V.wf_loc + o * NL;
         for (int i = 0; i < NL; ++i) out[i] = tot.d[i];

@@ -14,6 +14,7 @@
 #include "../sasktran2_b200/csrc/disco_bvp_rows.h"
 #include "../sasktran2_b200/csrc/disco_wf_body.h"
 #include "../sasktran2_b200/csrc/disco_plan.h"
+#include "../sasktran2_b200/csrc/disco_brdf.h"
 
 using namespace disco;
 
@@ -128,12 +129,18 @@ static void run_wf(ChunkView& V, unsigned* status) {
     for (long long i = 0; i < (long long)V.nw * V.T.nlos; ++i) wf_chain_body(V, i, G);
 }
 
+static const BrdfView* g_brdf_view = nullptr;   // set by emul_do_radiance when a MODIS surface was requested
+
 template <int N>
 static void run_all(ChunkView& V, unsigned* status, bool wf) {
     const int L = V.T.L;
     for (long long i = 0; i < (long long)V.nw * L; ++i) optics_body(V, i);
     for (int w = 0; w < V.nw; ++w) beam_body(V, w);
     for (long long i = 0; i < (long long)V.nw * V.M * L; ++i) layer_problem_body<N>(V, i);
+    if (g_brdf_view)   // kernel-based surface: one "thread" per (wavelength, order, stream / LOS row)
+        for (int w = 0; w < V.nw; ++w)
+            for (int ms = 0; ms < V.M; ++ms)
+                for (int t = 0; t < V.T.N + V.T.nlos; ++t) surface_general_body(V, *g_brdf_view, w, ms, t);
     for (int w = 0; w < V.nw; ++w)
         for (int ms = 0; ms < V.M; ++ms) bvp_emul<N>(V, w, ms, status);
     for (long long i = 0; i < (long long)V.nw * V.T.nlos; ++i) radiance_body(V, i);
@@ -165,6 +172,10 @@ extern "C" void emul_set_emission(const double* emission, const double* surface_
     g_emission = emission;
     g_semis = surface_emission;
 }
+
+// MODIS surface of the next emul_do_radiance call: args [3, nwavel] column-major (null: Lambertian)
+static const double* g_modis_args = nullptr;
+extern "C" void emul_set_modis(const double* args) { g_modis_args = args; }
 
 extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nlos, const double* alt, int interp,
                                 int geotype, double cos_sza, double earth_radius, const double* los_cos_vza,
@@ -223,6 +234,21 @@ extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nl
             V.wf_gnd = A(c * nlos * 3);
             V.wf_scratch = A(c * nlos * 3 * (L + 1));
             V.wf_native = native;
+        }
+        BrdfTables BT;
+        BrdfView BV{};
+        std::vector<double> zero_albedo(nwavel, 0.0);
+        g_brdf_view = nullptr;
+        if (g_modis_args) {
+            BT = build_brdf_tables(kBrdfModis, P);
+            BV.nk = BT.nk; BV.nargs = 3; BV.Rss = BT.Rss.data(); BV.rsun = BT.rsun.data(); BV.Rls = BT.Rls.data();
+            BV.rlsun = BT.rlsun.data(); BV.args = g_modis_args;
+            V.albedo = zero_albedo.data();
+            V.gsurf_stride = (int)(2 * N * N + 2 * N);
+            V.gsurf_out = A(c * M * V.gsurf_stride);
+            V.gsurf = V.gsurf_out;
+            if (wf) V.gsurf_rows = A(c * M * (N + nlos) * (N + 1));
+            g_brdf_view = &BV;
         }
         unsigned status = 0;
         V.status = &status;

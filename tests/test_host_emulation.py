@@ -17,11 +17,12 @@ ROOT = Path(__file__).resolve().parent.parent
 def emul():
     so = ROOT / "tests" / "libhost_emul.so"
     srcs = [ROOT / "tests" / "host_emul.cpp", ROOT / "sasktran2_b200" / "csrc" / "disco_plan.cpp",
+            ROOT / "sasktran2_b200" / "csrc" / "disco_brdf.cpp",
             ROOT / "sasktran2_b200" / "csrc" / "disco_core.h", ROOT / "sasktran2_b200" / "csrc" / "disco_bodies.h",
             ROOT / "sasktran2_b200" / "csrc" / "disco_bvp_rows.h", ROOT / "sasktran2_b200" / "csrc" / "disco_wf_body.h",
             ROOT / "sasktran2_b200" / "csrc" / "disco_twostream_body.h"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
-        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(srcs[0]), str(srcs[1])],
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(srcs[0]), str(srcs[1]), str(srcs[2])],
                        check=True)
     lib = ctypes.CDLL(str(so))
     lib.emul_last_error.restype = ctypes.c_char_p
@@ -31,7 +32,7 @@ def emul():
 
     def run(nstr, alt, interp, geotype, cos_sza, los_cos_vza, los_rel_az, ssa, ext, leg, albedo,
             earth_radius=6372000.0, include_ss=True, solar=None, d_leg=None, want_native=False, emission=None,
-            surface_emission=None, **_):
+            surface_emission=None, modis_args=None, **_):
         alt = np.ascontiguousarray(alt, float)
         ssa = np.asfortranarray(ssa, float)
         ext = np.asfortranarray(ext, float)
@@ -52,11 +53,14 @@ def emul():
         em = None if emission is None else np.asfortranarray(emission, float)
         se = None if surface_emission is None else np.ascontiguousarray(np.broadcast_to(surface_emission, (nw,)), float)
         lib.emul_set_emission(P(em) if em is not None else None, P(se) if se is not None else None)
+        ma = None if modis_args is None else np.asfortranarray(modis_args, float)   # [3, nwavel]
+        lib.emul_set_modis(P(ma) if ma is not None else None)
         rc = lib.emul_do_radiance(nstr, nloc, nw, nleg, cz.size, P(alt), interp, geotype, ctypes.c_double(cos_sza),
                                   ctypes.c_double(earth_radius), P(cz), P(az), P(ssa), P(ext), P(leg), P(solar), P(alb),
                                   int(include_ss), P(rad), ctypes.byref(naz), P(dl) if dl is not None else None, G,
                                   P(native) if native is not None else None)
         lib.emul_set_emission(None, None)
+        lib.emul_set_modis(None)
         if rc:
             raise RuntimeError(lib.emul_last_error().decode())
         if want_native:

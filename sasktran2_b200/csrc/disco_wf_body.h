@@ -246,6 +246,56 @@ DISCO_HD Dk<NL> los_source_dual(const Tables& T, int m, int los, const Dk<NL>& o
     return src + Q * E;
 }
 
+// Kernel-based BRDF, layer on the ground (every order reflects).  Kept out of line on the device: wf_layer_body is at
+// the register allocator's limit (255 registers, 19 KB of stack at N = 8) and inlining these rarely taken paths changed
+// the code generated for every other layer.
+#if defined(__CUDA_ARCH__)
+#define DISCO_NOINLINE __noinline__
+#else
+#define DISCO_NOINLINE
+#endif
+// downwelling field at the streams on the ground: X_q = G+bottom_q + sum_j (W+_qj Theta_j L_j + W-_qj M_j)
+template <int N, int NL>
+DISCO_HD DISCO_NOINLINE void wf_ground_field(const Dk<NL>* Gpb, const Dk<NL>* Wp, const Dk<NL>* Wm, const Dk<NL>* theta,
+                                             const double* Lc, const double* Mc, Dk<NL>* Xg) {
+    for (int q = 0; q < N; ++q) {
+        Dk<NL> acc = Gpb[q];
+        for (int j = 0; j < N; ++j) acc = acc + Wp[q * N + j] * theta[j] * Lc[j] + Wm[q * N + j] * Mc[j];
+        Xg[q] = acc;
+    }
+}
+// One line of sight: the reflection terms of the ground rows (adjoint part) and of the ground-leaving radiance, added
+// to `tot`; the ground pieces of the cross-layer chain accumulated over the orders with their azimuth factor.
+//   grow: [(N + nlos)][N + 1] rows (1 + delta_m0) w_q mu_q rho_m(row, mu_q) | rho_m(row, mu_0) of this (wavelength, order)
+template <int N, int NL>
+DISCO_HD DISCO_NOINLINE void wf_ground_general(const ChunkView& V, int w, int m, int los, const double* grow,
+                                               const Dk<NL>* Xg, const double* zg, size_t zs, double attg, double t_floor,
+                                               Dk<NL>& tot) {
+    for (int q = 0; q < N; ++q) {
+        double c = 0.0;   // ground rows: - sum_q R(i, q) X_q on the left-hand side
+        for (int i = 0; i < N; ++i) c += zg[i * zs] * grow[i * (N + 1) + q];
+        tot = tot + Xg[q] * c;
+    }
+    const double* lrow = grow + (size_t)(N + los) * (N + 1);
+    Dk<NL> refl_los(0.0);
+    for (int q = 0; q < N; ++q) refl_los = refl_los + Xg[q] * lrow[q];
+    tot = tot + refl_los * attg;
+    const double cf = V.T.los_cosmphi[(size_t)los * V.T.nstr + m];
+    const double direct = V.include_ss ? V.T.csz / kPi * t_floor * lrow[N] : 0.0;
+    double zsun = 0.0;   // right-hand side of the ground rows: csz rho(i, sun) t_floor / pi
+    for (int i = 0; i < N; ++i) zsun += zg[i * zs] * grow[i * (N + 1) + N];
+    double* gnd = V.wf_gnd + ((size_t)w * V.T.nlos + los) * 3;
+    const double g1 = cf * ((V.include_ss ? attg * lrow[N] * V.T.csz / kPi : 0.0) + zsun * V.T.csz / kPi);
+    const double g2 = cf * attg * (direct + refl_los.v);
+#if defined(__CUDA_ARCH__)
+    atomicAdd(gnd + 1, g1);   // wf_gnd is zeroed by the caller; one writer per (wavelength, order, LOS)
+    atomicAdd(gnd + 2, g2);
+#else
+    gnd[1] += g1;
+    gnd[2] += g2;
+#endif
+}
+
 // K5 body: one (wavelength, azimuth slot, layer).  G = number of scattering groups, NL = G + 4 local lanes
 // ordered [eps_0..eps_{G-1} | tau | omega | t | s].
 //   wf_loc [nw][M][nlos][L][NL]   d(I_m,los)/d(local lane of layer p) (direct + adjoint parts, LOS-attenuated)
@@ -401,16 +451,10 @@ DISCO_HD void wf_layer_body(const ChunkView& V, long long idx) {
     const bool bottom = (p == L - 1);
     // kernel-based BRDF (every order reflects): rows[(N + nlos)][N + 1] of this (wavelength, order) hold
     // (1 + delta_m0) w_q mu_q rho_m(row, mu_q) | rho_m(row, mu_0) for the stream rows and the LOS rows (k_surface_general)
-    const bool general = bottom && V.gsurf_rows != nullptr;
+    const bool general = bottom && V.gsurf_rows != nullptr && V.gsurf != nullptr;
     const double* grow = general ? V.gsurf_rows + ((size_t)w * M + ms) * (size_t)(N + nlos) * (N + 1) : nullptr;
-    D Xg[N];   // downwelling field at the streams on the ground: G+bottom_q + sum_j (W+_qj Theta_j L_j + W-_qj M_j)
-    if (general) {
-        for (int q = 0; q < N; ++q) {
-            D acc = Gpb[q];
-            for (int j = 0; j < N; ++j) acc = acc + Wp[q * N + j] * theta[j] * Lc[j] + Wm[q * N + j] * Mc[j];
-            Xg[q] = acc;
-        }
-    }
+    D Xg[N];
+    if (general) wf_ground_field<N, NL>(Gpb, Wp, Wm, theta, Lc, Mc, Xg);
     const bool refl = bottom && (m == 0) && !general;
     const double albedo = V.albedo[w];
     D gsum(0.0);  // 2 sG + 2 sum_j (s+_j Theta_j L_j + s-_j M_j): the surface-reflected stream integral
@@ -448,13 +492,6 @@ DISCO_HD void wf_layer_body(const ChunkView& V, long long idx) {
                 zg_sum += zg[i * zs];
             }
             if (refl) adj = adj + gsum * (albedo * zg_sum);
-            if (general) {   // ground rows: - sum_q R(i, q) X_q on the left, + csz rho(i, sun) t_floor / pi on the right
-                for (int q = 0; q < N; ++q) {
-                    double c = 0.0;
-                    for (int i = 0; i < N; ++i) c += zg[i * zs] * grow[i * (N + 1) + q];
-                    adj = adj + Xg[q] * c;
-                }
-            }
         }
         const double mul = V.T.los_mu[los];
         const double att = exp(-cum_top / mul);
@@ -472,30 +509,8 @@ DISCO_HD void wf_layer_body(const ChunkView& V, long long idx) {
             gnd[1] = (V.include_ss ? attg * albedo * V.T.csz / kPi : 0.0) + zg_sum * V.T.csz * albedo / kPi;  // d/d t_floor
             gnd[2] = attg * albedo * (direct + gsum.v);                                        // ground term value
         }
-        if (general) {
-            // ground-leaving radiance of this order toward the LOS and the pieces of the cross-layer chain, summed over
-            // the orders with their azimuth factors (wf_gnd is zeroed by the caller; one writer per (w, order, LOS))
-            const double attg = exp(-cum_all / mul);
-            const double* lrow = grow + (size_t)(N + los) * (N + 1);
-            D refl_los(0.0);
-            for (int q = 0; q < N; ++q) refl_los = refl_los + Xg[q] * lrow[q];
-            tot = tot + refl_los * attg;
-            const double cf = V.T.los_cosmphi[(size_t)los * V.T.nstr + m];
-            const double direct = V.include_ss ? V.T.csz / kPi * t_floor * lrow[N] : 0.0;
-            double zsun = 0.0;
-            const double* zg = z + (N + (size_t)(L - 1) * 2 * N) * zs;
-            for (int i = 0; i < N; ++i) zsun += zg[i * zs] * grow[i * (N + 1) + N];
-            double* gnd = V.wf_gnd + ((size_t)w * nlos + los) * 3;
-            const double g1 = cf * ((V.include_ss ? attg * lrow[N] * V.T.csz / kPi : 0.0) + zsun * V.T.csz / kPi);
-            const double g2 = cf * attg * (direct + refl_los.v);
-#if defined(__CUDA_ARCH__)
-            atomicAdd(gnd + 1, g1);
-            atomicAdd(gnd + 2, g2);
-#else
-            gnd[1] += g1;
-            gnd[2] += g2;
-#endif
-        }
+        if (general)
+            wf_ground_general<N, NL>(V, w, m, los, grow, Xg, z + (N + (size_t)(L - 1) * 2 * N) * zs, zs, exp(-cum_all / mul), t_floor, tot);
         double* out = V.wf_loc + o * NL;
         for (int i = 0; i < NL; ++i) out[i] = tot.d[i];
         V.wf_src[o] = srcval;

@@ -266,11 +266,13 @@ extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nl
             D("lay_od", V.lay_od, c * L); D("lay_secant", V.lay_secant, c * L); D("lay_trans", V.lay_trans, c * (L + 1));
             D("lay_beta", V.lay_beta, c * L * nstr); D("kth", V.kth, c * M * L * 2 * N); D("Wp", V.Wp, c * M * L * N * N);
             D("G", V.G, c * M * L * 4 * N); D("wvec", V.wvec, c * M * nlos * L * 2 * N); D("vsrc", V.vsrc, c * M * nlos * L);
-            D("xsol", V.xsol, c * M * L * 2 * N);
+            D("xsol", V.xsol, c * M * L * 2 * N); D("Wm", V.Wm, c * M * L * N * N); D("lay_ssa", V.lay_ssa, c * L);
+            D("lay_cumod", V.lay_cumod, c * (L + 1));
             if (wf) {
                 D("zadj", V.zadj, c * M * nlos * 2 * N * L); D("lay_dbeta", V.lay_dbeta, c * L * G * nstr);
                 D("wf_loc", V.wf_loc, c * M * nlos * L * (G + 4)); D("wf_src", V.wf_src, c * M * nlos * L);
                 D("wf_gnd", V.wf_gnd, c * nlos * 3);
+                if (V.gsurf_rows) D("gsurf_rows", V.gsurf_rows, c * M * (N + nlos) * (N + 1));
             }
         }
         if (status) {

@@ -244,7 +244,7 @@ def test_cuda_atmospheric_wf_above_a_brdf_surface_vs_oracle(nstr, kind, generic,
 from .test_host_emulation import emul  # noqa: E402,F401  (fixture)
 
 
-@pytest.mark.parametrize("nstr,nlos", [(4, 3), (8, 2), (2, 2)])
+@pytest.mark.parametrize("nstr,nlos", [(4, 3), (8, 2), (2, 2), (16, 5)])
 def test_kernel_bodies_modis_surface_and_wf_above_it_match_the_oracle(emul, nstr, nlos):  # noqa: F811
     from . import wf_checks
 

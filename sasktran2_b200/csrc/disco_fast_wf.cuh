@@ -125,12 +125,29 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
     const int ms = blockIdx.y;
     const int m = V.m_list[ms];
     {
-        // the order's tables, precomputed in this layout at engine creation (Tables::wf_tab): one coalesced copy
-        const int td = Cf::table_doubles(nlos);
-        const double* __restrict__ src = V.T.wf_tab + (size_t)m * td;
-        for (int e = threadIdx.x; e < td; e += blockDim.x) smem[e] = src[e];
+        // The order's Legendre tables, precomputed in this layout at engine creation (Tables::wf_tab), come in as ONE
+        // bulk copy of the TMA engine (cp.async.bulk global -> shared, completion on an mbarrier): no LSU
+        // instructions, and the block's threads set up their problem while it is in flight.  The size is a multiple of
+        // 16 bytes for every instantiated N (N even); source and destination are 16-byte aligned.
+        __shared__ __align__(8) unsigned long long tab_bar;
+        const unsigned td_bytes = (unsigned)(Cf::table_doubles(nlos) * sizeof(double));
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&tab_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(td_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(smem)),
+                         "l"(V.T.wf_tab + (size_t)m * Cf::table_doubles(nlos)), "r"(td_bytes), "r"(bar)
+                         : "memory");
+        }
+        __syncthreads();   // the barrier is initialised before anyone polls it
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+            "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar)
+            : "memory");
     }
-    __syncthreads();
 
     const int j = threadIdx.x % N;
     const int pib = threadIdx.x / N;

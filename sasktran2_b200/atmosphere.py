@@ -204,6 +204,22 @@ class Surface:
             self._mapping_names.append(name)
 
 
+    def enable_brdf_argument_derivative(self, name: str, arg: int, num_args: int = 3):
+        """Registers a surface mapping with d_brdf[:, arg] = 1: d radiance / d (BRDF argument `arg`), e.g. the weight of
+        one MODIS kernel (upstream: surface.derivative_mappings[name].d_brdf is [nwavel, num_args]).  Call after
+        use_modis()."""
+        h = C.c_void_p()
+        _lib.check(_lib.lib().sk_surface_get_derivative_mapping(self._h, name.encode(), C.byref(h)))
+        p = _lib.c_double_p()
+        _lib.check(_lib.lib().sk_surface_deriv_mapping_get_d_brdf(h, C.byref(p)))
+        d = np.ctypeslib.as_array(p, shape=(num_args, self._nwavel))   # column-major [nwavel, num_args]
+        d[:] = 0.0
+        d[arg] = 1.0
+        _lib.lib().sk_surface_deriv_mapping_destroy(h)
+        if name not in self._mapping_names:
+            self._mapping_names.append(name)
+
+
 class Atmosphere:
     def __init__(self, model_geometry, config, wavelengths_nm=None, numwavel=None, calculate_derivatives=True,
                  num_legendre=None):

@@ -108,9 +108,9 @@ int validate(const Engine* e, const Atmosphere* atm, const OutputC* out, bool ch
     if (atm->surface->nwavel != s->nwavel) return fail(-2, "surface and storage have a different number of wavelengths");
     if (atm->surface->brdf && atm->surface->brdf->kind != 0 && !atm->surface->brdf_args)
         return fail(-1, "surface BRDF arguments are null");
-    if (atm->surface->brdf && atm->surface->brdf->kind != 0 && atm->calc_derivs && e->cfg.wf_enabled && check_output && out &&
+    if (atm->surface->brdf && atm->surface->brdf->kind == 1 && atm->calc_derivs && e->cfg.wf_enabled && check_output && out &&
         !out->surface_derivs.empty())
-        return fail(-2, "B200 DO path: weighting functions w.r.t. the arguments of a non-Lambertian BRDF are not supported");
+        return fail(-2, "B200 DO path: weighting functions w.r.t. the argument of the snow BRDF are not supported");
     if (e->cfg.emission_source == 2 && !s->emission)
         return fail(-1, "emission_source is DiscreteOrdinates but the atmosphere storage has no emission_source array");
     if (e->cfg.emission_source == 2 && atm->calc_derivs && e->cfg.wf_enabled && check_output && out &&
@@ -172,6 +172,8 @@ int build_wf_request(Engine* e, Atmosphere* atm, OutputC* out, disco::WfRequest&
         sk_surface_deriv_mapping_get_d_brdf(&tmp, &dummy);
         disco::WfSurface sf;
         sf.d_brdf = it->second.d_brdf.data();
+        sf.nargs = it->second.nargs;
+        sf.nwavel = (size_t)it->second.nwavel;
         sf.out = kv.second.ptr;
         req.surfaces.push_back(sf);
     }
@@ -636,7 +638,7 @@ int sk_surface_get_derivative_mapping(Surface* s, const char* name, SurfaceDeriv
     if (it == s->mappings.end()) {
         SurfaceMappingImpl m;
         m.nwavel = s->nwavel;
-        m.nargs = 1;
+        m.nargs = (s->brdf && s->brdf->kind != 0) ? disco::brdf_num_args(s->brdf->kind) : 1;   // d_brdf is [nwavel, num_args] upstream
         it = s->mappings.emplace(name, std::move(m)).first;
     }
     *mapping = new SurfaceDerivativeMapping{&it->second};

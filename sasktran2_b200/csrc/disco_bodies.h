@@ -84,6 +84,11 @@ struct ChunkView {
     // (1 + delta_m0) w_q mu_q rho_m(row, mu_q) | rho_m(row, mu_0)   (null: radiances only)
     double* gsurf_rows;
     int wf_bottom_only;       // 1: k_wf_layer solves only the layer on the ground (k_wf_layer_fast leaves it out)
+    // weighting functions w.r.t. the weights of a linear kernel model (MODIS): the kernels' own Fourier tables
+    // (disco_brdf.h layouts) and the accumulated derivatives wf_gndk[nw][nlos][brdf_nk]; null: not requested
+    const double *brdf_Rss, *brdf_rsun, *brdf_Rls, *brdf_rlsun;
+    int brdf_nk;
+    double* wf_gndk;
     // ---- several solar zenith angles sharing one homogeneous solution and one factorisation (spherical path): the
     //      arrays that depend on the SZA exist nsza times; slice s starts s * stride doubles after the pointers above
     int nsza;                 // 0 / 1: single SZA

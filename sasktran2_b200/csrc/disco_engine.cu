@@ -378,6 +378,7 @@ void DeviceEngine::ensure_workspace(int chunk) {
     V.gsurf_stride = (int)(2 * N * N + 2 * N);
     if (m_brdf_kind != 0) V.gsurf = V.gsurf_out = A("gsurf", c * M * V.gsurf_stride);
     V.gsurf_rows = (m_brdf_kind != 0 && m_wf_on) ? A("gsurf_rows", c * M * (N + nlos) * (N + 1)) : nullptr;
+    V.wf_gndk = (m_brdf_kind != 0 && m_wf_on) ? A("wf_gndk", c * nlos * 4) : nullptr;   // at most 3 kernel weights
     m_ws_brdf = m_brdf_kind != 0;
     m_ws_brdf_kind = m_brdf_kind;
     d_brdf_pw = nullptr;
@@ -502,8 +503,9 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
         if (m_is_limb) throw std::runtime_error("B200 limb path supports the Lambertian BRDF only");
         if (wf && wf->enabled()) {
             // atmospheric weighting functions above a kernel-based BRDF are solved; those w.r.t. its arguments are not
-            if (!wf->surfaces.empty())
-                throw std::runtime_error("B200 DO path: weighting functions w.r.t. the arguments of a non-Lambertian BRDF are not supported");
+            // ... except for the weights of a linear kernel model (MODIS), whose tables are the derivatives
+            if (!wf->surfaces.empty() && m_brdf_kind != kBrdfModis)
+                throw std::runtime_error("B200 DO path: weighting functions w.r.t. the argument of the snow BRDF are not supported");
         }
         if (twostream_direct()) throw std::runtime_error("B200 two-stream kernel supports the Lambertian BRDF only");
         if (m_plan.N > 16) throw std::runtime_error("B200 DO path: kernel-based BRDFs need num_streams <= 32");
@@ -603,7 +605,7 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
             }
             for (size_t i = 0; i < wf->surfaces.size(); ++i) {
                 DevSurface ds;
-                ds.d_brdf = dalloc<double>(nw);
+                ds.d_brdf = dalloc<double>((size_t)nw * std::max(wf->surfaces[i].nargs, 1));
                 ds.out = dalloc<double>((size_t)nw * m_plan.nlos);
                 m_surfs.push_back(ds);
             }
@@ -622,7 +624,8 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
         }
         for (size_t i = 0; i < m_surfs.size(); ++i) {
             m_surfs[i].host = wf->surfaces[i];
-            h2d(m_surfs[i].d_brdf, wf->surfaces[i].d_brdf + w0, 1);
+            for (int k = 0; k < std::max(wf->surfaces[i].nargs, 1); ++k)   // one column per BRDF argument
+                h2d(m_surfs[i].d_brdf + (size_t)k * nw, wf->surfaces[i].d_brdf + (size_t)k * wf->surfaces[i].nwavel + w0, 1);
         }
     }
     CUDA_OK(cudaEventRecord(m_ev[1], m_stream));
@@ -855,6 +858,16 @@ void DeviceEngine::solve_staged() {
             const bool general_brdf = m_brdf_kind != 0;
             if (general_brdf) {   // the ground terms of every order are accumulated (k_wf_layer, kernel-based BRDF)
                 CUDA_OK(cudaMemsetAsync(V.wf_gnd, 0, sizeof(double) * (size_t)V.nw * m_plan.nlos * 3, m_stream));
+                V.wf_gndk = nullptr;
+                if (!m_surfs.empty()) {   // weights of the MODIS kernels
+                    V.brdf_Rss = d_brdf_Rss;
+                    V.brdf_rsun = d_brdf_rsun;
+                    V.brdf_Rls = d_brdf_Rls;
+                    V.brdf_rlsun = d_brdf_rlsun;
+                    V.brdf_nk = m_brdf_nk;
+                    V.wf_gndk = m_view.wf_gndk;
+                    CUDA_OK(cudaMemsetAsync(V.wf_gndk, 0, sizeof(double) * (size_t)V.nw * m_plan.nlos * m_brdf_nk, m_stream));
+                }
             }
             if (m_fast && wf_layer_fast_tile(m_plan.N, m_ngroups, m_plan.nlos) > 0) {
                 ChunkView Vw = V;
@@ -884,7 +897,10 @@ void DeviceEngine::solve_staged() {
                 m_launches += dm.host.log_radiance_space ? 2 : 1;
             }
             for (auto& ds : m_surfs) {
-                launch_wf_surface(V, ds.d_brdf, ds.out, w0, m_stream);
+                if (general_brdf)
+                    launch_wf_surface_args(V, ds.d_brdf, (size_t)m_nw, ds.out, w0, m_stream);
+                else
+                    launch_wf_surface(V, ds.d_brdf, ds.out, w0, m_stream);
                 m_launches += 1;
             }
             mark(); slots.push_back(T_WF_MAP);

@@ -55,7 +55,9 @@ struct WfMapping {
     double* out = nullptr;                // [nout][nwavel][nlos]
 };
 struct WfSurface {
-    const double* d_brdf = nullptr;       // [nwavel]
+    const double* d_brdf = nullptr;       // [nwavel, nargs] column-major (Lambertian: nargs = 1)
+    int nargs = 1;
+    size_t nwavel = 0;                    // column stride of d_brdf
     double* out = nullptr;                // [nwavel][nlos]
 };
 struct WfRequest {

@@ -325,6 +325,15 @@ __global__ void k_wf_surface(ChunkView V, const double* d_brdf, double* out, int
     const int w = (int)(idx / V.T.nlos);
     out[(size_t)w0 * V.T.nlos + idx] = V.wf_native[(size_t)idx * nnative + nnative - 1] * d_brdf[w0 + w];
 }
+// weighting functions w.r.t. the weights of a linear kernel BRDF: out = sum_k d_brdf[k][w] dI/d(weight k)
+__global__ void k_wf_surface_args(ChunkView V, const double* d_brdf, size_t arg_stride, double* out, int w0) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)V.nw * V.T.nlos) return;
+    const int w = (int)(idx / V.T.nlos);
+    double acc = 0.0;
+    for (int k = 0; k < V.brdf_nk; ++k) acc += V.wf_gndk[(size_t)idx * V.brdf_nk + k] * d_brdf[(size_t)k * arg_stride + w0 + w];
+    out[(size_t)w0 * V.T.nlos + idx] = acc;
+}
 __global__ void k_wf_log_scale(ChunkView V, double* out, int nout, int w0, int nw_total) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)V.nw * V.T.nlos * nout) return;
@@ -422,6 +431,10 @@ void launch_wf_map(const ChunkView& V, const MappingView& Mp, int w0, int nw_tot
     const long long n = (long long)V.nw * V.T.nlos * Mp.nout;
     k_wf_map<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V, Mp, w0, nw_total, V.ngroups);
     if (log_space) k_wf_log_scale<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V, Mp.out, Mp.nout, w0, nw_total);
+}
+void launch_wf_surface_args(const ChunkView& V, const double* d_brdf, size_t arg_stride, double* out, int w0, cudaStream_t s) {
+    const long long n = (long long)V.nw * V.T.nlos;
+    k_wf_surface_args<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V, d_brdf, arg_stride, out, w0);
 }
 void launch_wf_surface(const ChunkView& V, const double* d_brdf, double* out, int w0, cudaStream_t s) {
     const long long n = (long long)V.nw * V.T.nlos;

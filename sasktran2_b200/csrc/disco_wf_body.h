@@ -294,6 +294,32 @@ DISCO_HD DISCO_NOINLINE void wf_ground_general(const ChunkView& V, int w, int m,
     gnd[1] += g1;
     gnd[2] += g2;
 #endif
+    if (V.wf_gndk) {
+        // d/d(weight of kernel k): the BRDF is linear in the weights, so the partial derivative of the ground rows and of
+        // the ground-leaving term at fixed solution is the same expression with kernel k's own Fourier coefficients
+        const int nstr = V.T.nstr, nlos = V.T.nlos;
+        const double sun = V.T.csz / kPi * t_floor;
+        for (int k = 0; k < V.brdf_nk; ++k) {
+            const double* Rs = V.brdf_Rss + (((size_t)k * nstr + m) * N) * N;          // [i][q]
+            const double* rs = V.brdf_rsun + ((size_t)k * nstr + m) * N;               // [i]
+            const double* Rl = V.brdf_Rls + (((size_t)k * nstr + m) * nlos + los) * N; // [q]
+            const double rl = V.brdf_rlsun[((size_t)k * nstr + m) * nlos + los];
+            double acc = V.include_ss ? sun * rl : 0.0;
+            for (int q = 0; q < N; ++q) acc += Rl[q] * Xg[q].v;
+            acc *= attg;
+            for (int i = 0; i < N; ++i) {
+                double row = sun * rs[i];
+                for (int q = 0; q < N; ++q) row += Rs[i * N + q] * Xg[q].v;
+                acc += zg[i * zs] * row;
+            }
+            double* dst = V.wf_gndk + ((size_t)w * nlos + los) * V.brdf_nk + k;
+#if defined(__CUDA_ARCH__)
+            atomicAdd(dst, cf * acc);
+#else
+            *dst += cf * acc;
+#endif
+        }
+    }
 }
 
 // K5 body: one (wavelength, azimuth slot, layer).  G = number of scattering groups, NL = G + 4 local lanes

@@ -247,7 +247,12 @@ extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nl
             V.gsurf_stride = (int)(2 * N * N + 2 * N);
             V.gsurf_out = A(c * M * V.gsurf_stride);
             V.gsurf = V.gsurf_out;
-            if (wf) V.gsurf_rows = A(c * M * (N + nlos) * (N + 1));
+            if (wf) {
+                V.gsurf_rows = A(c * M * (N + nlos) * (N + 1));
+                V.brdf_Rss = BT.Rss.data(); V.brdf_rsun = BT.rsun.data(); V.brdf_Rls = BT.Rls.data(); V.brdf_rlsun = BT.rlsun.data();
+                V.brdf_nk = BT.nk;
+                V.wf_gndk = A(c * nlos * BT.nk);
+            }
             g_brdf_view = &BV;
         }
         unsigned status = 0;
@@ -273,6 +278,7 @@ extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nl
                 D("wf_loc", V.wf_loc, c * M * nlos * L * (G + 4)); D("wf_src", V.wf_src, c * M * nlos * L);
                 D("wf_gnd", V.wf_gnd, c * nlos * 3);
                 if (V.gsurf_rows) D("gsurf_rows", V.gsurf_rows, c * M * (N + nlos) * (N + 1));
+                if (V.wf_gndk) D("wf_gndk", V.wf_gndk, c * nlos * V.brdf_nk);
             }
         }
         if (status) {

@@ -127,10 +127,23 @@ def test_cuda_modis_isotropic_only_equals_lambertian_path():
 
 @pytest.mark.gpu
 def test_cuda_non_lambertian_refusals():
-    sc, args = _case(nstr=4)
+    """The snow model is not linear in its argument: a weighting function w.r.t. it is refused (MODIS weights are solved)."""
+    sc, _ = _case(nstr=4)
     sc.mappings = scenarios.small_wf_case(nstr=4, nlayers=10, nwavel=4, nlos=3).mappings
-    with pytest.raises(_lib.SasktranError):     # weighting functions w.r.t. the arguments of a kernel-based BRDF (wf_albedo)
-        _run(sc, args, calc_derivs=True)
+    cfg = sk.Config()
+    cfg.num_streams = sc.nstr
+    cfg.multiple_scatter_source = sk.MultipleScatterSource.DiscreteOrdinates
+    cfg.single_scatter_source = sk.SingleScatterSource.DiscreteOrdinates
+    geo = sk.Geometry1D(sc.cos_sza, 0.0, sc.earth_radius, sc.altitudes, sk.InterpolationMethod(sc.interp), sk.GeometryType(sc.geotype))
+    view = sk.ViewingGeometry()
+    for cz, az in zip(sc.los_cos_vza, sc.los_rel_az):
+        view.add_ray(sk.GroundViewingSolar(sc.cos_sza, float(az), float(cz), sc.observer_altitude))
+    eng = sk.Engine(cfg, geo, view)
+    atm = sk.Atmosphere.from_scenario(sc, geo, cfg, calculate_derivatives=True)
+    atm.surface.use_snow_kokhanovsky(np.linspace(2e-7, 5e-6, sc.nwavel))
+    atm.surface.enable_brdf_argument_derivative("wf_snow", 0, num_args=1)
+    with pytest.raises(_lib.SasktranError, match="snow BRDF"):
+        eng.calculate_radiance(atm)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -266,3 +279,82 @@ def test_kernel_bodies_modis_surface_and_wf_above_it_match_the_oracle(emul, nstr
         r, g = ref[:, :, block * nloc:(block + 1) * nloc], got[:, :, block * nloc:(block + 1) * nloc]
         scale = np.abs(r).max(axis=2, keepdims=True)
         assert np.max(np.abs(g - r) / scale) < 1e-7, (block, float(np.max(np.abs(g - r) / scale)))
+
+
+def _modis_args(nwavel):
+    args = np.zeros((3, nwavel))
+    args[0] = np.linspace(0.1, 0.4, nwavel)
+    args[1] = np.linspace(0.02, 0.08, nwavel)
+    args[2] = np.linspace(0.05, 0.01, nwavel)
+    return args
+
+
+def _oracle_fd_wrt_kernel_weights(sc, args, h=1e-5):
+    """Central differences of the oracle's radiances w.r.t. the three MODIS kernel weights: [3, nwavel, nlos] (the
+    reference's own criterion for weighting functions, src/sasktran2/test_util/wf.py:9-80)."""
+    out = []
+    for k in range(3):
+        up, dn = args.copy(), args.copy()
+        up[k] += h
+        dn[k] -= h
+        out.append((oracle.do_radiance(**_oracle_kw(sc), brdf_kind=2, brdf_args=up)["radiance"] -
+                    oracle.do_radiance(**_oracle_kw(sc), brdf_kind=2, brdf_args=dn)["radiance"]) / (2 * h))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("nstr,nlos", [(4, 3), (8, 2), (16, 4)])
+def test_kernel_bodies_modis_weight_derivatives_match_finite_differences(emul, nstr, nlos):  # noqa: F811
+    import ctypes
+
+    from . import wf_checks
+    from .test_host_emulation import ROOT
+
+    sc = scenarios.small_wf_case(nstr=nstr, nlayers=7, nwavel=3, nlos=nlos)
+    args = _modis_args(sc.nwavel)
+    names = wf_checks.scat_names(sc)
+    d_leg = np.stack([sc.mappings[n]["d_legendre"] for n in names], axis=-1)
+    emul(**wf_checks.oracle_inputs(sc), d_leg=d_leg, want_native=True, modis_args=args)
+    hl = ctypes.CDLL(str(ROOT / "tests" / "libhost_emul.so"))
+    hl.emul_dump.restype = ctypes.c_longlong
+    buf = np.zeros(sc.nwavel * nlos * 3)
+    n = hl.emul_dump(b"wf_gndk", buf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_longlong(buf.size))
+    assert n == buf.size
+    got = buf.reshape(sc.nwavel, nlos, 3).transpose(2, 0, 1)
+    fd = _oracle_fd_wrt_kernel_weights(sc, args)
+    np.testing.assert_allclose(got, fd, rtol=2e-7, atol=1e-9 * np.abs(fd).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nstr,generic,nlos", [(8, False, 4), (16, False, 5), (16, True, 3), (4, False, 24)])
+def test_cuda_modis_weight_derivatives_vs_finite_differences(nstr, generic, nlos):
+    """d radiance / d (weight of MODIS kernel k) through the surface derivative mappings (d_brdf[:, k] = 1), next to the
+    atmospheric weighting functions of the same call; against central differences of the oracle's radiances."""
+    sc = scenarios.small_wf_case(nstr=nstr, nlayers=9, nwavel=4, nlos=nlos)
+    args = _modis_args(sc.nwavel)
+    cfg = sk.Config()
+    cfg.num_streams = sc.nstr
+    cfg.multiple_scatter_source = sk.MultipleScatterSource.DiscreteOrdinates
+    cfg.single_scatter_source = sk.SingleScatterSource.DiscreteOrdinates
+    geo = sk.Geometry1D(sc.cos_sza, 0.0, sc.earth_radius, sc.altitudes, sk.InterpolationMethod(sc.interp), sk.GeometryType(sc.geotype))
+    view = sk.ViewingGeometry()
+    for cz, az in zip(sc.los_cos_vza, sc.los_rel_az):
+        view.add_ray(sk.GroundViewingSolar(sc.cos_sza, float(az), float(cz), sc.observer_altitude))
+    if generic:
+        os.environ["SK_B200_GENERIC"] = "1"
+    try:
+        eng = sk.Engine(cfg, geo, view)
+        atm = sk.Atmosphere.from_scenario(sc, geo, cfg, calculate_derivatives=True)
+        atm.surface.use_modis(args[0], args[1], args[2])
+        for k, name in enumerate(("wf_brdf_iso", "wf_brdf_vol", "wf_brdf_geo")):
+            atm.surface.enable_brdf_argument_derivative(name, k)
+        res = eng.calculate_radiance(atm)
+    finally:
+        os.environ.pop("SK_B200_GENERIC", None)
+    fd = _oracle_fd_wrt_kernel_weights(sc, args)
+    for k, name in enumerate(("wf_brdf_iso", "wf_brdf_vol", "wf_brdf_geo")):
+        got = np.asarray(res[name]).reshape(sc.nwavel, nlos)
+        np.testing.assert_allclose(got, fd[k], rtol=2e-7, atol=1e-9 * np.abs(fd).max())
+    # the atmospheric weighting functions of the same call are unaffected
+    _, wf = _oracle_wf_brdf(sc, 2, args)
+    err = np.abs(res["wf_o3_vmr"][..., 0] - wf["wf_o3_vmr"]) / np.abs(wf["wf_o3_vmr"]).max(axis=0, keepdims=True)
+    assert err.max() < 1e-7

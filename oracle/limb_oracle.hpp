@@ -158,7 +158,9 @@ struct Grid {
             return;
         }
         if (constant) {  // :45-127
-            if (x < x0) {
+            // a degenerate grid (all points equal: e.g. the SZA grid of an exactly vertical ray, LinSpaced(n, a, a)) makes
+            // the reference divide by a zero spacing; every point sits on the first entry
+            if (!(dx > 0.0) || x < x0) {
                 idx[0] = idx[1] = 0; w[0] = 1; w[1] = 0; n = 1;
                 return;
             }
@@ -435,10 +437,27 @@ struct RayTracer {  // SphericalShellRayTracer, straight rays
             if (cv > 0) {
                 // trace_ray_observer_inside_looking_up, :424-455
                 int start = int(std::upper_bound(alt.begin(), alt.end(), obs_alt) - alt.begin());
+                // Solar rays start on the boundaries of the line-of-sight layers, i.e. ON grid altitudes up to the rounding
+                // of |position| - R.  The reference takes whichever side the rounding falls on: below, a zero-length
+                // partial layer plus the complete shell; at or above, a "partial" layer spanning the whole shell whose
+                // lower end is NOT an exact point - with shell interpolation that end then carries the shell's mean
+                // extinction instead of the grid point's, so the optical depth of that shell differs between the two
+                // outcomes (linear interpolation: identical).  The exact variant (the flag that also removes the
+                // tangent-layer rounding, see exact_tangent_ref) snaps such a start onto its grid altitude, within the
+                // reference's own 1e-4 m exactness tolerance of tangent points (spherical_shell.cpp:300-310).
+                int snap = -1;
+                if (exact_tangent_ref())
+                    for (int i = 0; i < ng; ++i)
+                        if (std::abs(obs_alt - alt[i]) <= 1e-4) snap = i;
+                if (snap >= 0) start = snap + 1;
+                if (start >= ng) return;   // on (or above) the top altitude: nothing to trace
                 out.layers.resize(ng - start);
                 int c = 0;
                 for (int i = ng - 1; i != start; --i) complete_layer(out.layers[c++], i, -1);
-                partial_layer(out.layers[c], ray, start, -1);
+                if (snap >= 0)
+                    complete_layer(out.layers[c], start, -1);
+                else
+                    partial_layer(out.layers[c], ray, start, -1);
             } else {
                 // the sun below the local horizon of a line-of-sight point: the reference's looking-down branches
                 // (:457-551) are not restated; flag the ray as blocked only when it really reaches the ground

@@ -95,7 +95,8 @@ struct Axis {
         double frac;
         if (uniform) {
             const double x0 = g[0], dx = g[1] - g[0];
-            if (x < x0) return single(0);
+            // degenerate grid (the SZA grid of an exactly vertical ray is LinSpaced(n, a, a)): everything on the first entry
+            if (!(dx > 0.0) || x < x0) return single(0);
             lo = (int)std::floor((x - x0) / dx);
             if (lo >= n - 1) return single(n - 1);
             frac = (x - g[lo]) / dx;
@@ -237,17 +238,34 @@ struct Tracer {
                 for (int i = 0; i < ng - 1; ++i) full_shell(out.segs[i], alt, re(), i, +1);
             }
         } else if (cv > 0) {
-            const int start = (int)(std::upper_bound(alt.begin(), alt.end(), obs_alt) - alt.begin());
+            int start = (int)(std::upper_bound(alt.begin(), alt.end(), obs_alt) - alt.begin());
+            // A start ON a grid altitude (solar rays leave from the boundaries of the line-of-sight layers) is an exact
+            // point of the grid: the reference lets the rounding of |position| - R decide between a zero-length partial
+            // shell below and a whole-shell "partial" layer with an inexact lower end, which changes that shell's
+            // optical depth under shell interpolation (limb_oracle.hpp, trace).  Snapped here within the reference's own
+            // 1e-4 m exactness tolerance of tangent points.
+            int snap = -1;
+            for (int i = 0; i < ng; ++i)
+                if (std::abs(obs_alt - alt[i]) <= 1e-4) snap = i;
+            if (snap >= 0) start = snap + 1;
+            if (start >= ng) {
+                out.segs.clear();
+                return;
+            }
             out.segs.resize(ng - start);
             int c = 0;
             for (int i = ng - 1; i != start; --i) full_shell(out.segs[c++], alt, re(), i, -1);
-            Seg& s = out.segs[c];  // partial shell from the observer up to the next grid altitude (:278-298)
-            s.r_near = obs_alt + re();
-            s.r_far = alt[start] + re();
-            s.far_pt.exact = true;
-            s.far_pt.grid = start;
-            s.near_pt.exact = false;
-            s.near_pt.grid = start - 1;
+            if (snap >= 0) {
+                full_shell(out.segs[c], alt, re(), start, -1);
+            } else {
+                Seg& s = out.segs[c];  // partial shell from the observer up to the next grid altitude (:278-298)
+                s.r_near = obs_alt + re();
+                s.r_far = alt[start] + re();
+                s.far_pt.exact = true;
+                s.far_pt.grid = start;
+                s.near_pt.exact = false;
+                s.near_pt.grid = start - 1;
+            }
         } else {
             if (tangent_alt <= alt[0]) {
                 out.ground = true;  // a blocked solar ray only needs its flag

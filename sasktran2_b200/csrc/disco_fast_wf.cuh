@@ -63,7 +63,10 @@ __device__ __forceinline__ R3 psi_dual(double a, double k1, double k2, double e1
     double ph, dph;
     if (k2 >= k1) {
         const double x = a * (k2 - k1);
-        const double ratio = (x > 0.1 && e1 > 0.0) ? div_fast(e2, e1) : 0.0;
+        // e2 / e1 = exp(-x).  div_fast seeds from a single-precision reciprocal: exponentials of optically thick layers
+        // leave the float range long before they underflow in double (exp(-k tau) < 1e-38 at k tau > 87), where the
+        // quotient comes from the exponential itself
+        const double ratio = (x > 0.1 && e1 > 0.0) ? (e1 > 1e-30 ? div_fast(e2, e1) : exp(-x)) : 0.0;
         phi_pair(x, ratio, ph, dph);
         r.v = e1 * ph;
         r.k = -a * e1 * (ph + dph);
@@ -71,7 +74,7 @@ __device__ __forceinline__ R3 psi_dual(double a, double k1, double k2, double e1
         r.s = a * e1 * dph;
     } else {
         const double x = a * (k1 - k2);
-        const double ratio = (x > 0.1 && e2 > 0.0) ? div_fast(e1, e2) : 0.0;
+        const double ratio = (x > 0.1 && e2 > 0.0) ? (e2 > 1e-30 ? div_fast(e1, e2) : exp(-x)) : 0.0;
         phi_pair(x, ratio, ph, dph);
         r.v = e2 * ph;
         r.k = a * e2 * dph;

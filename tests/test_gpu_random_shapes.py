@@ -21,6 +21,9 @@ def _cases(n=72, seed=20261019):
         nstr = int(rng.choice([2, 4, 8, 16, 16, 8]))
         c = dict(nstr=nstr, nlayers=int(rng.integers(1, 61 if i % 3 == 0 else 34)), nlos=int(rng.integers(1, 22 if i % 4 == 0 else 14)),
                  nwavel=int(rng.integers(1, 7)), emission=bool(rng.random() < 0.3),
+                 # solar and viewing geometry, surface brightness, optical thickness away from the scenario's defaults
+                 cos_sza=float(rng.choice([0.6, 0.6, rng.uniform(0.08, 1.0)])), nadir=bool(rng.random() < 0.3),
+                 albedo=float(rng.choice([-1.0, -1.0, 0.0, 0.97, 1.0])), kscale=float(rng.choice([1.0, 1.0, 0.02, 8.0, 100.0, 1e-4])),
                  interp=int(rng.choice([1, 2])), geotype=int(rng.choice([0, 1])), seed=int(rng.integers(1, 1000)),
                  surface=str(rng.choice(["lambertian", "lambertian", "modis", "snow"])), wf=bool(rng.random() < 0.7),
                  # switches that are read per engine (the others are latched once per process)
@@ -37,6 +40,13 @@ CASES = _cases()
 def test_cuda_random_shape_vs_oracle(case):
     sc = scenarios.small_wf_case(nstr=case["nstr"], nlayers=case["nlayers"], nwavel=case["nwavel"], nlos=case["nlos"],
                                  interp=case["interp"], geotype=case["geotype"], seed=case["seed"])
+    sc.cos_sza = case["cos_sza"]
+    if case["nadir"]:
+        sc.los_cos_vza = np.array(sc.los_cos_vza, dtype=float)
+        sc.los_cos_vza[0] = 1.0          # exactly nadir: every order above 0 vanishes for this line of sight
+    if case["albedo"] >= 0.0:
+        sc.albedo = np.full(sc.nwavel, case["albedo"])
+    sc.total_extinction = np.asfortranarray(sc.total_extinction * case["kscale"])   # the mappings stay valid linear maps
     wf = case["wf"]
     if not wf:
         sc.mappings = {}

@@ -188,7 +188,7 @@ def config3(nwavel: int = 1000000, nlayers: int = 60, nlos: int = 2, block: tupl
     z = np.linspace(0.0, 60e3, nlayers + 1)
     widx = np.arange(nwavel, dtype=np.uint64) if block is None else np.arange(block[0], block[0] + block[1], dtype=np.uint64)
     # splitmix64 of (index, seed) -> uniform [0, 1)
-    x = widx + np.uint64(0x9E3779B97F4A7C15) * np.uint64(seed + 1)
+    x = widx + np.uint64((0x9E3779B97F4A7C15 * (seed + 1)) % (1 << 64))   # wraps like the 64-bit multiply
     with np.errstate(over="ignore"):
         x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)

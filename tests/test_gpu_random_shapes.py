@@ -167,3 +167,45 @@ def test_cuda_random_limb_case_vs_oracle(case):
     # reference's own result that the product (always 1/2 : 1/2, the shell's constant extinction) does not follow.
     ref = oracle.limb_radiance(**c, ms_do=case["ms"], ss_exact=(case["ss"] == "exact"))
     np.testing.assert_allclose(res["radiance"][:, :, 0], ref["radiance"], rtol=(2e-2 if case["interp"] == 0 else 5e-7))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# dedicated two-stream source (k_twostream): random layer counts, lines of sight, geometry, albedo and optical thickness
+# ---------------------------------------------------------------------------------------------------------------------
+def _twostream_cases(n=24, seed=777):
+    rng = np.random.default_rng(seed)
+    return [dict(nlayers=int(rng.integers(1, 121)), nlos=int(rng.integers(1, 7)), nwavel=int(rng.integers(1, 400)),
+                 geotype=int(rng.choice([0, 1])), interp=int(rng.choice([1, 2])), cos_sza=float(rng.uniform(0.1, 1.0)),
+                 albedo=float(rng.choice([0.0, 0.3, 1.0])), kscale=float(rng.choice([1.0, 1e-3, 30.0])), nadir=bool(rng.random() < 0.4),
+                 seed=int(rng.integers(0, 1000))) for _ in range(n)]
+
+
+TWOSTREAM_CASES = _twostream_cases()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", TWOSTREAM_CASES, ids=[f"{i}-L{c['nlayers']}-los{c['nlos']}-w{c['nwavel']}" for i, c in enumerate(TWOSTREAM_CASES)])
+def test_cuda_random_twostream_case_vs_oracle(case):
+    c3 = scenarios.config3(nwavel=case["nwavel"], nlayers=case["nlayers"], nlos=case["nlos"], seed=case["seed"])
+    cz = np.array(c3.los_cos_vza, dtype=float)
+    if case["nadir"]:
+        cz[0] = 1.0
+    inp = dict(alt=c3.altitudes, interp=case["interp"], geotype=case["geotype"], cos_sza=case["cos_sza"], los_cos_vza=cz,
+               los_rel_az=c3.los_rel_az, ssa=c3.ssa, ext=np.asfortranarray(c3.total_extinction * case["kscale"]), leg=c3.leg_coeff,
+               albedo=np.full(case["nwavel"], case["albedo"]))
+    cfg = sk.Config()
+    cfg.num_streams = 2
+    cfg.single_scatter_source = sk.SingleScatterSource.NoSource
+    cfg.multiple_scatter_source = sk.MultipleScatterSource.TwoStream
+    geo = sk.Geometry1D(inp["cos_sza"], 0.0, 6372000.0, inp["alt"], sk.InterpolationMethod(inp["interp"]), sk.GeometryType(inp["geotype"]))
+    view = sk.ViewingGeometry()
+    for c, a in zip(inp["los_cos_vza"], inp["los_rel_az"]):
+        view.add_ray(sk.GroundViewingSolar(inp["cos_sza"], float(a), float(c), 200_000.0))
+    atm = sk.Atmosphere(geo, cfg, numwavel=case["nwavel"], calculate_derivatives=False, num_legendre=inp["leg"].shape[0])
+    atm.storage.total_extinction[:] = inp["ext"]
+    atm.storage.ssa[:] = inp["ssa"]
+    atm.storage.leg_coeff[:] = inp["leg"]
+    atm.surface.albedo[:] = inp["albedo"]
+    rad = sk.Engine(cfg, geo, view).calculate_radiance(atm)["radiance"][:, :, 0]
+    want = oracle.twostream_radiance(**inp)["radiance"]
+    np.testing.assert_allclose(rad, want, rtol=1e-9, atol=1e-300)

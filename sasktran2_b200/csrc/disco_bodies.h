@@ -89,6 +89,9 @@ struct ChunkView {
     const double *brdf_Rss, *brdf_rsun, *brdf_Rls, *brdf_rlsun;
     int brdf_nk;
     double* wf_gndk;
+    // per-order ground pieces above a kernel-based BRDF, [nw][M][nlos][2 + brdf_nk]: d/dT_floor | ground term | weights;
+    // summed over the orders in a fixed order by wf_ground_reduce_body (bit-reproducible, no floating-point atomics)
+    double* wf_gnd_part;
     // ---- several solar zenith angles sharing one homogeneous solution and one factorisation (spherical path): the
     //      arrays that depend on the SZA exist nsza times; slice s starts s * stride doubles after the pointers above
     int nsza;                 // 0 / 1: single SZA

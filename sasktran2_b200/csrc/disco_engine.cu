@@ -379,6 +379,7 @@ void DeviceEngine::ensure_workspace(int chunk) {
     if (m_brdf_kind != 0) V.gsurf = V.gsurf_out = A("gsurf", c * M * V.gsurf_stride);
     V.gsurf_rows = (m_brdf_kind != 0 && m_wf_on) ? A("gsurf_rows", c * M * (N + nlos) * (N + 1)) : nullptr;
     V.wf_gndk = (m_brdf_kind != 0 && m_wf_on) ? A("wf_gndk", c * nlos * 4) : nullptr;   // at most 3 kernel weights
+    V.wf_gnd_part = (m_brdf_kind != 0 && m_wf_on) ? A("wf_gnd_part", c * M * nlos * 5) : nullptr;
     m_ws_brdf = m_brdf_kind != 0;
     m_ws_brdf_kind = m_brdf_kind;
     d_brdf_pw = nullptr;
@@ -856,18 +857,14 @@ void DeviceEngine::solve_staged() {
             launch_bvp_adjoint(V, m_stream);
             mark(); slots.push_back(T_WF_ADJOINT);
             const bool general_brdf = m_brdf_kind != 0;
-            if (general_brdf) {   // the ground terms of every order are accumulated (k_wf_layer, kernel-based BRDF)
-                CUDA_OK(cudaMemsetAsync(V.wf_gnd, 0, sizeof(double) * (size_t)V.nw * m_plan.nlos * 3, m_stream));
-                V.wf_gndk = nullptr;
-                if (!m_surfs.empty()) {   // weights of the MODIS kernels
-                    V.brdf_Rss = d_brdf_Rss;
-                    V.brdf_rsun = d_brdf_rsun;
-                    V.brdf_Rls = d_brdf_Rls;
-                    V.brdf_rlsun = d_brdf_rlsun;
-                    V.brdf_nk = m_brdf_nk;
-                    V.wf_gndk = m_view.wf_gndk;
-                    CUDA_OK(cudaMemsetAsync(V.wf_gndk, 0, sizeof(double) * (size_t)V.nw * m_plan.nlos * m_brdf_nk, m_stream));
-                }
+            if (general_brdf) {   // per-order ground pieces (k_wf_layer), summed in slot order afterwards
+                V.brdf_nk = (m_brdf_kind == kBrdfModis) ? m_brdf_nk : 0;
+                V.brdf_Rss = d_brdf_Rss;
+                V.brdf_rsun = d_brdf_rsun;
+                V.brdf_Rls = d_brdf_Rls;
+                V.brdf_rlsun = d_brdf_rlsun;
+                V.wf_gnd_part = m_view.wf_gnd_part;
+                V.wf_gndk = m_surfs.empty() ? nullptr : m_view.wf_gndk;   // weights of the MODIS kernels
             }
             if (m_fast && wf_layer_fast_tile(m_plan.N, m_ngroups, m_plan.nlos) > 0) {
                 ChunkView Vw = V;
@@ -879,6 +876,10 @@ void DeviceEngine::solve_staged() {
                 }
             } else {
                 launch_wf_layer(V, m_stream);
+            }
+            if (general_brdf) {
+                launch_wf_ground_reduce(V, m_stream);
+                m_launches += 1;
             }
             mark(); slots.push_back(T_WF_LAYER);
             launch_wf_chain(V, m_stream);

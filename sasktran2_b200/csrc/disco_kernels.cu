@@ -432,6 +432,15 @@ void launch_wf_map(const ChunkView& V, const MappingView& Mp, int w0, int nw_tot
     k_wf_map<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V, Mp, w0, nw_total, V.ngroups);
     if (log_space) k_wf_log_scale<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V, Mp.out, Mp.nout, w0, nw_total);
 }
+__global__ void k_wf_ground_reduce(ChunkView V) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)V.nw * V.T.nlos) return;
+    wf_ground_reduce_body(V, idx);
+}
+void launch_wf_ground_reduce(const ChunkView& V, cudaStream_t s) {
+    const long long n = (long long)V.nw * V.T.nlos;
+    k_wf_ground_reduce<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V);
+}
 void launch_wf_surface_args(const ChunkView& V, const double* d_brdf, size_t arg_stride, double* out, int w0, cudaStream_t s) {
     const long long n = (long long)V.nw * V.T.nlos;
     k_wf_surface_args<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(V, d_brdf, arg_stride, out, w0);

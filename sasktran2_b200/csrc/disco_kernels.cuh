@@ -45,6 +45,7 @@ struct MappingView;
 void launch_wf_layer(const ChunkView& V, cudaStream_t s);
 void launch_wf_chain(const ChunkView& V, cudaStream_t s);
 void launch_wf_map(const ChunkView& V, const MappingView& Mp, int w0, int nw_total, bool log_space, cudaStream_t s);
+void launch_wf_ground_reduce(const ChunkView& V, cudaStream_t s);   // per-order ground pieces -> wf_gnd / wf_gndk
 void launch_wf_surface_args(const ChunkView& V, const double* d_brdf, size_t arg_stride, double* out, int w0, cudaStream_t s);
 void launch_wf_surface(const ChunkView& V, const double* d_brdf, double* out, int w0, cudaStream_t s);
 int adjoint_groups_per_problem(int nlos);

@@ -268,7 +268,7 @@ DISCO_HD DISCO_NOINLINE void wf_ground_field(const Dk<NL>* Gpb, const Dk<NL>* Wp
 // to `tot`; the ground pieces of the cross-layer chain accumulated over the orders with their azimuth factor.
 //   grow: [(N + nlos)][N + 1] rows (1 + delta_m0) w_q mu_q rho_m(row, mu_q) | rho_m(row, mu_0) of this (wavelength, order)
 template <int N, int NL>
-DISCO_HD DISCO_NOINLINE void wf_ground_general(const ChunkView& V, int w, int m, int los, const double* grow,
+DISCO_HD DISCO_NOINLINE void wf_ground_general(const ChunkView& V, int w, int ms, int m, int los, const double* grow,
                                                const Dk<NL>* Xg, const double* zg, size_t zs, double attg, double t_floor,
                                                Dk<NL>& tot) {
     for (int q = 0; q < N; ++q) {
@@ -284,42 +284,48 @@ DISCO_HD DISCO_NOINLINE void wf_ground_general(const ChunkView& V, int w, int m,
     const double direct = V.include_ss ? V.T.csz / kPi * t_floor * lrow[N] : 0.0;
     double zsun = 0.0;   // right-hand side of the ground rows: csz rho(i, sun) t_floor / pi
     for (int i = 0; i < N; ++i) zsun += zg[i * zs] * grow[i * (N + 1) + N];
-    double* gnd = V.wf_gnd + ((size_t)w * V.T.nlos + los) * 3;
-    const double g1 = cf * ((V.include_ss ? attg * lrow[N] * V.T.csz / kPi : 0.0) + zsun * V.T.csz / kPi);
-    const double g2 = cf * attg * (direct + refl_los.v);
-#if defined(__CUDA_ARCH__)
-    atomicAdd(gnd + 1, g1);   // wf_gnd is zeroed by the caller; one writer per (wavelength, order, LOS)
-    atomicAdd(gnd + 2, g2);
-#else
-    gnd[1] += g1;
-    gnd[2] += g2;
-#endif
-    if (V.wf_gndk) {
-        // d/d(weight of kernel k): the BRDF is linear in the weights, so the partial derivative of the ground rows and of
-        // the ground-leaving term at fixed solution is the same expression with kernel k's own Fourier coefficients
-        const int nstr = V.T.nstr, nlos = V.T.nlos;
-        const double sun = V.T.csz / kPi * t_floor;
-        for (int k = 0; k < V.brdf_nk; ++k) {
-            const double* Rs = V.brdf_Rss + (((size_t)k * nstr + m) * N) * N;          // [i][q]
-            const double* rs = V.brdf_rsun + ((size_t)k * nstr + m) * N;               // [i]
-            const double* Rl = V.brdf_Rls + (((size_t)k * nstr + m) * nlos + los) * N; // [q]
-            const double rl = V.brdf_rlsun[((size_t)k * nstr + m) * nlos + los];
-            double acc = V.include_ss ? sun * rl : 0.0;
-            for (int q = 0; q < N; ++q) acc += Rl[q] * Xg[q].v;
-            acc *= attg;
-            for (int i = 0; i < N; ++i) {
-                double row = sun * rs[i];
-                for (int q = 0; q < N; ++q) row += Rs[i * N + q] * Xg[q].v;
-                acc += zg[i * zs] * row;
-            }
-            double* dst = V.wf_gndk + ((size_t)w * nlos + los) * V.brdf_nk + k;
-#if defined(__CUDA_ARCH__)
-            atomicAdd(dst, cf * acc);
-#else
-            *dst += cf * acc;
-#endif
+    const int nk = V.wf_gndk ? V.brdf_nk : 0;
+    double* part = V.wf_gnd_part + ((((size_t)w * V.M + ms) * V.T.nlos + los) * (size_t)(2 + V.brdf_nk));
+    part[0] = cf * ((V.include_ss ? attg * lrow[N] * V.T.csz / kPi : 0.0) + zsun * V.T.csz / kPi);
+    part[1] = cf * attg * (direct + refl_los.v);
+    // d/d(weight of kernel k): the BRDF is linear in the weights, so the partial derivative of the ground rows and of
+    // the ground-leaving term at fixed solution is the same expression with kernel k's own Fourier coefficients
+    const int nstr = V.T.nstr, nlos = V.T.nlos;
+    const double sun = V.T.csz / kPi * t_floor;
+    for (int k = 0; k < nk; ++k) {
+        const double* Rs = V.brdf_Rss + (((size_t)k * nstr + m) * N) * N;          // [i][q]
+        const double* rs = V.brdf_rsun + ((size_t)k * nstr + m) * N;               // [i]
+        const double* Rl = V.brdf_Rls + (((size_t)k * nstr + m) * nlos + los) * N; // [q]
+        const double rl = V.brdf_rlsun[((size_t)k * nstr + m) * nlos + los];
+        double acc = V.include_ss ? sun * rl : 0.0;
+        for (int q = 0; q < N; ++q) acc += Rl[q] * Xg[q].v;
+        acc *= attg;
+        for (int i = 0; i < N; ++i) {
+            double row = sun * rs[i];
+            for (int q = 0; q < N; ++q) row += Rs[i * N + q] * Xg[q].v;
+            acc += zg[i * zs] * row;
         }
+        part[2 + k] = cf * acc;
     }
+}
+
+// Sum of the per-order ground pieces in slot order: one (wavelength, LOS)
+DISCO_HD void wf_ground_reduce_body(const ChunkView& V, long long idx) {
+    const int nlos = V.T.nlos, M = V.M, stride = 2 + V.brdf_nk;
+    const int w = (int)(idx / nlos), los = (int)(idx % nlos);
+    double g1 = 0.0, g2 = 0.0, gk[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int ms = 0; ms < M; ++ms) {
+        const double* part = V.wf_gnd_part + (((size_t)w * M + ms) * nlos + los) * (size_t)stride;
+        g1 += part[0];
+        g2 += part[1];
+        for (int k = 0; k < V.brdf_nk && k < 4; ++k) gk[k] += part[2 + k];
+    }
+    double* gnd = V.wf_gnd + (size_t)idx * 3;
+    gnd[0] = 0.0;
+    gnd[1] = g1;
+    gnd[2] = g2;
+    if (V.wf_gndk)
+        for (int k = 0; k < V.brdf_nk && k < 4; ++k) V.wf_gndk[(size_t)idx * V.brdf_nk + k] = gk[k];
 }
 
 // K5 body: one (wavelength, azimuth slot, layer).  G = number of scattering groups, NL = G + 4 local lanes
@@ -536,7 +542,7 @@ DISCO_HD void wf_layer_body(const ChunkView& V, long long idx) {
             gnd[2] = attg * albedo * (direct + gsum.v);                                        // ground term value
         }
         if (general)
-            wf_ground_general<N, NL>(V, w, m, los, grow, Xg, z + (N + (size_t)(L - 1) * 2 * N) * zs, zs, exp(-cum_all / mul), t_floor, tot);
+            wf_ground_general<N, NL>(V, w, ms, m, los, grow, Xg, z + (N + (size_t)(L - 1) * 2 * N) * zs, zs, exp(-cum_all / mul), t_floor, tot);
         double* out = V.wf_loc + o * NL;
         for (int i = 0; i < NL; ++i) out[i] = tot.d[i];
         V.wf_src[o] = srcval;

@@ -126,6 +126,8 @@ static void run_wf(ChunkView& V, unsigned* status) {
     for (int w = 0; w < V.nw; ++w)
         for (int ms = 0; ms < V.M; ++ms) bvp_adjoint_emul<N>(V, w, ms, status);
     for (long long i = 0; i < (long long)V.nw * V.M * V.T.L; ++i) wf_layer_body<N, G>(V, i);
+    if (V.gsurf_rows)
+        for (long long i = 0; i < (long long)V.nw * V.T.nlos; ++i) wf_ground_reduce_body(V, i);
     for (long long i = 0; i < (long long)V.nw * V.T.nlos; ++i) wf_chain_body(V, i, G);
 }
 
@@ -252,6 +254,7 @@ extern "C" int emul_do_radiance(int nstr, int nloc, int nwavel, int nleg, int nl
                 V.brdf_Rss = BT.Rss.data(); V.brdf_rsun = BT.rsun.data(); V.brdf_Rls = BT.Rls.data(); V.brdf_rlsun = BT.rlsun.data();
                 V.brdf_nk = BT.nk;
                 V.wf_gndk = A(c * nlos * BT.nk);
+                V.wf_gnd_part = A(c * M * nlos * (2 + BT.nk));
             }
             g_brdf_view = &BV;
         }

@@ -225,3 +225,52 @@ def test_cuda_random_twostream_case_vs_oracle(case):
     rad = sk.Engine(cfg, geo, view).calculate_radiance(atm)["radiance"][:, :, 0]
     want = oracle.twostream_radiance(**inp)["radiance"]
     np.testing.assert_allclose(rad, want, rtol=1e-9, atol=1e-300)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# one engine, many kinds of call: workspace and staging state must not leak from one call into the next
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("nstr", [8, 16])
+def test_cuda_engine_reused_across_call_kinds_equals_fresh_engines(nstr):
+    """Radiance-only, weighting functions, MODIS / snow surfaces with and without weighting functions, thermal emission,
+    different spectrum lengths - in a shuffled order on ONE engine; every result bit-identical to a fresh engine's."""
+    base = scenarios.small_wf_case(nstr=nstr, nlayers=11, nwavel=6, nlos=4)
+    cfg = sk.Config()
+    cfg.num_streams = nstr
+    cfg.multiple_scatter_source = sk.MultipleScatterSource.DiscreteOrdinates
+    cfg.single_scatter_source = sk.SingleScatterSource.DiscreteOrdinates
+    geo = sk.Geometry1D(base.cos_sza, 0.0, base.earth_radius, base.altitudes, sk.InterpolationMethod(base.interp), sk.GeometryType(base.geotype))
+    view = sk.ViewingGeometry()
+    for cz, az in zip(base.los_cos_vza, base.los_rel_az):
+        view.add_ray(sk.GroundViewingSolar(base.cos_sza, float(az), float(cz), base.observer_altitude))
+
+    def atmosphere(kind):
+        nw = {"short": 2}.get(kind, 6)
+        sc = scenarios.small_wf_case(nstr=nstr, nlayers=11, nwavel=nw, nlos=4)
+        wf = kind in ("wf", "modis_wf", "snow_wf", "modis_weights", "short")
+        if not wf:
+            sc.mappings = {}
+        atm = sk.Atmosphere.from_scenario(sc, geo, cfg, calculate_derivatives=wf)
+        if kind.startswith("modis"):
+            atm.surface.use_modis(np.linspace(0.1, 0.3, nw), np.linspace(0.02, 0.05, nw), np.linspace(0.03, 0.01, nw))
+        if kind.startswith("snow"):
+            atm.surface.use_snow_kokhanovsky(np.linspace(3e-7, 3e-6, nw))
+        if kind == "modis_weights":
+            for k, name in enumerate(("wf_iso", "wf_vol", "wf_geo")):
+                atm.surface.enable_brdf_argument_derivative(name, k)
+        if kind in ("wf", "short"):
+            atm.surface.enable_albedo_derivative("wf_albedo")
+        return atm
+
+    kinds = ["rad", "wf", "modis", "modis_wf", "snow", "snow_wf", "modis_weights", "short", "wf", "rad", "modis_wf", "short"]
+    rng = np.random.default_rng(5)
+    rng.shuffle(kinds)
+    shared = sk.Engine(cfg, geo, view)
+    for kind in kinds:
+        got = shared.calculate_radiance(atmosphere(kind))
+        want = sk.Engine(cfg, geo, view).calculate_radiance(atmosphere(kind))
+        assert set(got) == set(want), kind
+        for k in want:
+            if not k.startswith("_"):
+                assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), (kind, k)

@@ -164,3 +164,35 @@ def test_cuda_limb_chunked_equals_unchunked():
     finally:
         del os.environ["SK_B200_WORKSPACE_GB"]
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("observer_altitude", [200_000.0, 700_000.0, 35_786_000.0])
+def test_cuda_limb_vertical_rays_and_distant_observers(observer_altitude):
+    """An exactly vertical ground-viewing ray (every point at one SZA: the SZA grid of the source table degenerates to
+    LinSpaced(n, a, a), on which the reference divides by a zero spacing), a nearly vertical one, backward azimuth, a
+    grazing tangent ray; observers from low orbit to geostationary."""
+    c = limb_case(nstr=8, nlayers=20, nwavel=3, nrays=2, seed=3)
+    o = observer_altitude
+    c["rays"] = [("ground", 0.6, 0.8, 1.0, o), ("ground", 0.6, 0.0, 0.999999, o), ("ground", 0.6, 3.14159, 0.35, o),
+                 ("tangent", 25_000.0, 0.0, o, 0.6), ("tangent", 1_000.0, 3.1, o, 0.6)]
+    res = _run(c, sk.MultipleScatterSource.DiscreteOrdinates, sk.SingleScatterSource.Exact)
+    ora = oracle.limb_radiance(**c, ms_do=True, ss_exact=True, exact_tangent=True)
+    assert np.all(np.isfinite(res["radiance"]))
+    np.testing.assert_allclose(res["radiance"][:, :, 0], ora["radiance"], rtol=1e-9)
+
+
+def test_limb_plan_of_a_vertical_ray_does_not_index_out_of_range():
+    """CPU part of the above: the host plan (and the oracle) for the degenerate SZA grid."""
+    c = limb_case(nstr=4, nlayers=10, nwavel=2, nrays=2, seed=1)
+    c["rays"] = [("ground", 0.6, 0.8, 1.0, 200_000.0)]
+    geo, view = _geometry_and_view(c)
+    ext = np.ascontiguousarray(c["ext"][:, 0])
+    out = np.zeros((1, 6))
+    npts = C.c_int(0)
+    sza = np.zeros(2)
+    _lib.check(_lib.lib().sk_b200_limb_plan_check(geo._geometry, view._viewing_geometry, 4, 2, _lib.dptr(ext), _lib.dptr(out),
+                                                  C.byref(npts), _lib.dptr(sza)), "limb_plan_check")
+    ora = oracle.limb_radiance(**c, ms_do=True, ss_exact=True, exact_tangent=True)
+    np.testing.assert_allclose(out[0, 0], ora["los_optical_depth"][0, 0], rtol=1e-12)
+    assert np.all(np.isfinite(ora["radiance"]))

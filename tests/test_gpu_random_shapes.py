@@ -263,11 +263,24 @@ def test_cuda_engine_reused_across_call_kinds_equals_fresh_engines(nstr):
             atm.surface.enable_albedo_derivative("wf_albedo")
         return atm
 
-    kinds = ["rad", "wf", "modis", "modis_wf", "snow", "snow_wf", "modis_weights", "short", "wf", "rad", "modis_wf", "short"]
+    kinds = ["rad", "wf", "modis", "modis_wf", "snow", "snow_wf", "modis_weights", "short", "wf", "rad", "modis_wf", "short",
+             "refused", "invalid", "rad", "refused", "modis_wf"]
     rng = np.random.default_rng(5)
     rng.shuffle(kinds)
     shared = sk.Engine(cfg, geo, view)
     for kind in kinds:
+        if kind == "refused":     # a refused request (weighting function w.r.t. the snow model's argument) ...
+            atm = atmosphere("snow_wf")
+            atm.surface.enable_brdf_argument_derivative("wf_snow", 0, num_args=1)
+            with pytest.raises(sk.SasktranError):
+                shared.calculate_radiance(atm)
+            continue              # ... and a failed input validation leave the engine usable
+        if kind == "invalid":
+            atm = atmosphere("wf")
+            atm.storage.ssa[2, 1] = 1.5
+            with pytest.raises(sk.SasktranError):
+                shared.calculate_radiance(atm)
+            continue
         got = shared.calculate_radiance(atmosphere(kind))
         want = sk.Engine(cfg, geo, view).calculate_radiance(atmosphere(kind))
         assert set(got) == set(want), kind

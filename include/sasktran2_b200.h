@@ -70,6 +70,9 @@ int sk_config_get_num_do_forced_azimuth(Config* config, int* num_forced_azimuth)
 int sk_config_set_num_do_forced_azimuth(Config* config, int num_forced_azimuth);
 int sk_config_get_do_backprop(Config* config, int* do_backprop);
 int sk_config_set_do_backprop(Config* config, int do_backprop);
+/* emission source (cpp/include/sasktran2/config.h:122-128): 1 none, 2 discrete_ordinates - the storage's emission_source
+   array goes through the DO solve (plane-parallel / pseudo-spherical, radiances only; needs both scattering sources on the
+   DO path as upstream's Config::validate_config); 0 standard, 3 volume_emission_rate, 4 twostream: engine creation fails */
 int sk_config_get_emission_source(Config* config, int* emission_source);
 int sk_config_set_emission_source(Config* config, int emission_source);
 int sk_config_get_occultation_source(Config* config, int* occultation_source);
@@ -222,6 +225,8 @@ int sk_deriv_mapping_clear_interpolator(DerivativeMapping* mapping);
 int sk_deriv_mapping_get_interpolator(DerivativeMapping* mapping, double** interpolator, int* dim1, int* dim2);
 int sk_surface_deriv_mapping_get_num_wavel(SurfaceDerivativeMapping* mapping, int* num_wavel);
 int sk_surface_deriv_mapping_get_num_brdf_args(SurfaceDerivativeMapping* mapping, int* num_brdf_args);
+/* d_brdf is [num_wavel, num_brdf_args] column-major (the surface's BRDF at the time the mapping is first requested):
+   Lambertian 1 column (albedo), MODIS 3 (kernel weights); a mapping on the snow model's argument is refused at solve time */
 int sk_surface_deriv_mapping_get_d_brdf(SurfaceDerivativeMapping* mapping, double** brdf);
 int sk_surface_deriv_mapping_get_d_emission(SurfaceDerivativeMapping* mapping, double** emission);
 int sk_surface_deriv_mapping_get_interpolator(SurfaceDerivativeMapping* mapping, double** interpolator, int* dim1,

@@ -474,6 +474,14 @@ void DeviceEngine::stage(const AtmosphereArrays& atm, int w0, int nw, const WfRe
         h2d(d_solar, atm.solar + w0, 1);
         if (atm.albedo && atm.brdf_kind == 0) h2d(d_albedo, atm.albedo + w0, 1);
     }
+    // multiple_scatter_source = TwoStream outside the dedicated kernel (weighting functions, or a grid too tall for its
+    // shared-memory tables) runs the 2-stream discrete-ordinates kernels.  The two-stream source averages a layer as the
+    // mean of its two grid points whatever the interpolation method (cpp_twostream_source.cpp:1923-2122); the DO layers
+    // follow the geometry's interpolation - the same numbers for linear interpolation only (the identity upstream tests).
+    if (m_opt.twostream && !twostream_direct_for(wf && wf->enabled()) && m_plan.interp != 1 && nw > 0)
+        throw std::runtime_error("B200 two-stream source: weighting functions (and grids above ~150 layers in pseudo-spherical "
+                                 "geometry) are solved by the 2-stream discrete-ordinates kernels, which equal the two-stream "
+                                 "source for linear interpolation only");
     // thermal sources (radiances only; the reference's emission derivative lanes are not implemented)
     m_emission_on = atm.emission != nullptr && nw > 0;
     m_semis_on = atm.surface_emission != nullptr && nw > 0;

@@ -102,6 +102,7 @@ class DeviceEngine {
     bool wf_active() const { return m_wf_on; }
     bool fast_path() const { return m_fast; }
     bool twostream_direct() const { return m_opt.twostream && !m_wf_on && twostream_supported(m_plan.L, m_plan.plane_parallel); }
+    bool twostream_direct_for(bool wf_requested) const { return m_opt.twostream && !wf_requested && twostream_supported(m_plan.L, m_plan.plane_parallel); }
     // test/debug: copy a workspace array of the LAST chunk to the host; returns the number of doubles copied
     size_t debug_copy(const char* name, double* host, size_t max_n);
     std::vector<std::pair<std::string, std::pair<double*, size_t>>> m_dbg;

@@ -485,7 +485,9 @@ __global__ void __launch_bounds__(128) k_wf_layer_fast(ChunkView V, int tlos_arg
     dB[iTau] = fma(Lj, -kj * thj, ap * Cp.a);
     dA[iS] = am * Cm.s;
     dB[iS] = ap * Cp.s;
-    const double inv_tt = 1.0 / trans_top;  // once per problem (beam transmittances span the double range)
+    // once per problem (beam transmittances span the double range; below it - slant optical depths above 745 - every
+    // particular term is exactly zero and so is its derivative chain)
+    const double inv_tt = trans_top > 1e-290 ? 1.0 / trans_top : 0.0;   // (denormal beams would overflow the reciprocal)
     dA[iT] = amc * inv_tt;
     dB[iT] = apc * inv_tt;
 

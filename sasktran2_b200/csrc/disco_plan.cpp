@@ -130,6 +130,7 @@ HostPlan build_plan(int nstr, const GeometrySpec& geo, const std::vector<LineOfS
     P.nlos = (int)los.size();
     P.csz = geo.cos_sza;
     P.plane_parallel = geo.geotype == 0;
+    P.interp = geo.interp;
     const int N = P.N, L = P.L;
 
     P.mu.assign(nstr, 0.0);

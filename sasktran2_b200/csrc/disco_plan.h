@@ -27,6 +27,7 @@ struct GeometrySpec {
 
 struct HostPlan {
     int nstr = 0, N = 0, L = 0, nloc = 0, nlos = 0;
+    int interp = 1;                    // the geometry's interpolation method (GeometrySpec::interp)
     double csz = 0.0;
     std::vector<double> mu, wt;        // [nstr]; first N are mu > 0
     std::vector<double> lp_mu;         // [m][i<N][l]

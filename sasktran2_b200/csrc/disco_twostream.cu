@@ -67,10 +67,17 @@ size_t twostream_smem_bytes(int L, bool plane_parallel, int threads) {
     return 16 + sizeof(double) * ((size_t)L * L + (size_t)L * threads);
 }
 
-bool twostream_supported(int L, bool plane_parallel) { return twostream_smem_bytes(L, plane_parallel, 128) <= 220 * 1024; }
+// Threads per block: the pseudo-spherical kernel keeps the L x L chapman table plus one optical-depth column per thread
+// in shared memory; tall grids run with narrower blocks (128 -> 64 -> 32 threads), 0: does not fit (L > ~150)
+static int twostream_threads(int L, bool plane_parallel) {
+    for (int t : {128, 64, 32})
+        if (twostream_smem_bytes(L, plane_parallel, t) <= 220 * 1024) return t;
+    return 0;
+}
+bool twostream_supported(int L, bool plane_parallel) { return twostream_threads(L, plane_parallel) > 0; }
 
 void launch_twostream(const ChunkView& V, cudaStream_t s) {
-    const int threads = 128;
+    const int threads = twostream_threads(V.T.L, V.plane_parallel != 0);
     const size_t smem = twostream_smem_bytes(V.T.L, V.plane_parallel != 0, threads);
     const int nlos = V.T.nlos;
     const unsigned gx = (unsigned)((V.nw + threads - 1) / threads);
